@@ -1,0 +1,137 @@
+"""The oracle (oracle/css_oracle.py) against golden vectors produced by the reference itself
+(tests/golden/make_golden.py) and against the reference's own known-answer tests.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import css_oracle as O
+from conftest import rel_l2
+
+
+def _cfg(g):
+    return O.OracleCfg(activity_th=float(g["activity_th"]), segment_size_sec=float(g["segment_size_sec"]),
+                       hop_size_sec=float(g["hop_size_sec"]))
+
+
+def _mixture(g):
+    return g["mixture_int16"].astype(np.float32) / np.float32(g["mixture_scale"])
+
+
+def _segments(g):
+    plan = O.plan_segments(len(g["mixture_int16"]), 16000, _cfg(g))
+    X = g["stft"]
+    T = plan.segment_frames
+    segs = np.zeros((plan.num_segments, 257, T, 7), np.complex64)
+    for i in range(plan.num_segments):
+        st = i * plan.hop_frames
+        en = min(st + T, plan.mix_frames)
+        segs[i, :, :en - st] = X[:, st:en]
+    return plan, segs
+
+
+def test_morphology_known_answer(golden):
+    # reference utils/numpy_utils.py:16-22
+    arr = np.array([1, 1, 0, 1, 1, 1, 0, 0, 0, 1, 1, 0, 0], dtype=bool)
+    assert np.array_equal(O.erode(arr, 1), [1, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0])
+    assert np.array_equal(O.dilate(arr, 1), [1, 1, 1, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0])
+    assert np.array_equal(O.erode(golden["morph_in"], 1), golden["morph_erode"])
+    assert np.array_equal(O.dilate(golden["morph_in"], 1), golden["morph_dilate"])
+
+
+def test_pit_known_answer():
+    # reference css/training/losses.py:109-123 (mse, permutation (3,0,2,1), loss exactly 0)
+    rng = np.random.default_rng(43236)
+    p = (3, 0, 2, 1)
+    for _ in range(5):
+        targets = rng.random((100, 257, 4)).astype(np.float32)
+        preds = targets[..., p]
+        c = O.pit_cost_mse(preds, targets)
+        perm = O.assign(c)
+        assert tuple(perm) == p
+        assert c[np.arange(4), perm].mean() == 0.0
+        assert np.array_equal(preds, targets[..., perm])
+        assert tuple(O.assign_bruteforce(c)) == p
+
+
+def test_plan_matches_reference_ints(golden):
+    plan = O.plan_segments(len(golden["mixture_int16"]), 16000, _cfg(golden))
+    assert plan.segment_frames == int(golden["segment_frames"])
+    assert plan.mix_frames == golden["stft"].shape[1]
+    assert plan.num_segments == golden["masks"].shape[0]
+    full = O.plan_segments(28_800_000, 16000, O.OracleCfg())          # 30 min
+    assert (full.segment_frames, full.hop_frames, full.m0_frames, full.m1_frames) == (186, 93, 9, 18)
+    assert (full.dilation_frames, full.erosion_frames) == (24, 12)
+    assert (full.mix_frames, full.num_segments) == (112_499, 1209)
+
+
+def test_stft_vs_reference(golden):
+    X = O.stft(_mixture(golden))
+    assert X.shape == golden["stft"].shape
+    assert rel_l2(X, golden["stft"]) < 2e-6
+    # DC / Nyquist: real up to the sin(pi_f32) residue of th.polar, same sign pattern
+    for k in (0, 256):
+        assert np.array_equal(np.signbit(X[k].imag), np.signbit(golden["stft"][k].imag))
+        assert np.array_equal(X[k].imag != 0, golden["stft"][k].real < 0)
+
+
+def test_segment_weights_vs_reference(golden):
+    w = golden["seg_weights"]
+    assert np.abs(O.calc_segment_weight(186, 9, 18) - w[0]).max() < 1e-7
+    assert np.abs(O.calc_segment_weight(186, 9, 18, is_first=True) - w[1]).max() < 1e-7
+    assert np.abs(O.calc_segment_weight(186, 9, 18, is_last=True) - w[2]).max() < 1e-7
+
+
+def test_features_vs_reference(golden):
+    _, segs = _segments(golden)
+    f = O.css_features(segs[0])
+    assert f.shape == golden["feat0"].shape
+    assert np.abs(f - golden["feat0"]).max() < 5e-5          # no +-pi flips anywhere, incl. bins 0 / 256
+    assert rel_l2(f, golden["feat0"]) < 1e-6
+
+
+def test_masks_vs_reference(golden, small_weights):
+    m = O.conformer_masks(small_weights, golden["feat0"][None])[0]
+    ref = golden["masks"][0]                                 # segment 0 was not shuffled
+    assert np.abs(m - ref).max() < 5e-5
+    assert rel_l2(m, ref) < 1e-5
+
+
+def test_mvdr_vs_reference(golden):
+    _, segs = _segments(golden)
+    for j, i in enumerate((1, 2)):
+        m = golden["masks"][i]
+        mix = segs[i].transpose(2, 0, 1)
+        y32 = O.make_mvdr(m[:3], m[3:], mix, np.float32)
+        y64 = O.make_mvdr(m[:3], m[3:], mix, np.float64)
+        assert rel_l2(y64, golden["mvdr64"][j]) < 1e-6       # fp64-lifted: same answer (stored as c64)
+        # fp32: same algorithm, same LAPACK -- inside the reference's own fp32 noise
+        floor = rel_l2(golden["mvdr"][j], golden["mvdr64"][j])
+        assert rel_l2(y32, golden["mvdr"][j]) < max(10 * floor, 1e-3)
+
+
+def test_istft_vs_reference(golden):
+    y = O.istft(golden["istft_in"])
+    assert y.shape == golden["istft_out"].shape
+    assert rel_l2(y, golden["istft_out"]) < 2e-6
+
+
+def test_stitch_chain_vs_reference(golden, small_weights):
+    """Stages II+III of css.py fed with the reference's per-segment masks: permutations and
+    activity bit-exact, stitched masks / waveforms to float32 round-off."""
+    x = _mixture(golden)[None]
+    wavs, side = O.separate_and_stitch(x, small_weights, 16000, _cfg(golden), masks_override=golden["masks"],
+                                       mvdr_dtype=np.float64, return_stages=True)
+    assert np.array_equal(side["perms"][1:], golden["perms"])
+    assert not np.array_equal(golden["perms"], np.tile(np.arange(3), (3, 1)))   # the chain is exercised
+    assert rel_l2(side["mask_stitched"], golden["mask_stitched"]) < 1e-6
+    assert np.array_equal(side["activity_b"], golden["activity_b"])
+    assert np.array_equal(side["activity_final"], golden["activity_final"])
+    assert 0.2 < golden["activity_b"].mean() < 0.8
+    # waveforms: the reference ran its MVDR in complex64, we compare the fp64-lifted chain and
+    # bound it by the reference's own fp32-vs-fp64 distance
+    floor = max(rel_l2(golden["mvdr"][j], golden["mvdr64"][j]) for j in range(2))
+    for k in range(3):
+        assert wavs[k].shape == golden["wavs"][k].shape
+        assert rel_l2(wavs[k], golden["wavs"][k]) < max(5 * floor, 1e-3)
+    wavs32, _ = O.separate_and_stitch(x, small_weights, 16000, _cfg(golden), masks_override=golden["masks"])
+    for k in range(3):
+        assert rel_l2(wavs32[k], golden["wavs"][k]) < max(5 * floor, 1e-3)
