@@ -1,0 +1,168 @@
+/*
+ * nsf_b200.h -- C ABI of the B200-native NOTSOFAR CSS hot path (libnsf_b200.so).
+ *
+ * The reference (microsoft/NOTSOFAR1-Challenge) is pure Python and has no FFI of its own;
+ * its drop-in boundary is the Python plug-in `css_inference` / `separate_and_stitch`
+ * (css/css.py:51,110).  This header is the thin native layer *below* that boundary: one
+ * entry point per stage of the reference's hot path, each citing the reference code it
+ * replaces.  `notsofar_b200/css.py` mirrors the reference's Python signatures on top of it.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer (HBM) owned by the caller unless marked `host`;
+ *     nothing is allocated or freed inside except by nsf_conformer_create/destroy
+ *     (a small host-side handle; weights stay in the caller's blob);
+ *   - all calls are stream-ordered on `stream` (a cudaStream_t passed as void*), do not
+ *     synchronise, and are re-entrant;
+ *   - return value: 0 = ok, negative = error (NSF_ERR_*); nsf_last_error() gives the text
+ *     (thread-local);
+ *   - complex data is interleaved (re, im) float32 ("c64"), as torch.complex64 / numpy
+ *     complex64 store it;
+ *   - F = 257 bins (frame 512, hop 256), C = 7 microphones, S = 3 speakers, Nn noise masks.
+ *
+ * HBM layouts (row-major, last index fastest)
+ *   audio      x      [N][C]                    f32   (reference speech_mix[0], css.py:110)
+ *   mixture    X      [F][T_long][C]            c64   (reference stft_mix[0], css.py:155)
+ *   features   feat   [n_seg*T][ldf]            f32   (time-major rows; ldf >= 257*C)
+ *   masks      masks  [n_seg][S+Nn][F][T]       f32   (reference: tuple of [1,F,T], conformer.py:308)
+ *   separated  Y      [n_seg][S][F][T]          c64   (reference separated_seg, css.py:227)
+ *   stitched   mask_st[F][T_long][S]            f32   (reference side_info['mask_stitched'][0])
+ *              S_st   [S][T_long][F]            c64   (frame-major, feeds the iSTFT)
+ *   waveforms  wav    [S][N_out]                f32   N_out = (T_long-1)*256 + 512
+ */
+#ifndef NSF_B200_H_
+#define NSF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSF_OK                 0
+#define NSF_ERR_INVALID_ARG   -1
+#define NSF_ERR_CUDA          -2
+#define NSF_ERR_UNSUPPORTED   -3
+
+#define NSF_NUM_BINS   257
+#define NSF_FRAME_LEN  512
+#define NSF_FRAME_HOP  256
+
+/* GEMM engines of the mask network */
+#define NSF_GEMM_SIMT_FP32   0   /* CUDA-core fp32 FMA (bit-faithful fp32 products; debugging / cross-check) */
+#define NSF_GEMM_TC_3XTF32   1   /* tcgen05 kind::tf32, error-compensated 3-pass split (fp32-parity mode, default) */
+#define NSF_GEMM_TC_TF32     2   /* tcgen05 kind::tf32, single pass (throughput mode, ~1e-3) */
+
+const char* nsf_last_error(void);
+const char* nsf_version(void);
+
+/* Number of STFT frames of an n_samples signal: conv1d stride 256, kernel 512, no padding
+ * (css_with_conformer/executor/feature.py:105). */
+int64_t nsf_num_frames(int64_t n_samples);
+
+/* Multichannel STFT.  Replaces ConformerCssWrapper.stft (css/training/conformer_wrapper.py:106-129)
+ * -> STFT.forward (feature.py:88-128, kernel init_kernel feature.py:19-45):
+ *   X[k][t][c] = sum_n x[256 t + n][c] * hann_periodic(n) * exp(-2 pi i k n / 512),  no padding, scale 1.
+ * The DC and Nyquist bins carry the residue the reference's (mag, atan2) -> th.polar round trip
+ * leaves: imag = re * sin(pi_f32) when re < 0, else +0.
+ * Computes frames 0 .. n_frames-1 of x (n_frames <= nsf_num_frames(n_samples)) into X[:, 0..n_frames-1, :];
+ * T_long is the frame pitch of X (>= n_frames).  A rank that owns a frame range passes offset pointers. */
+int nsf_stft_mc(const float* x, int64_t n_samples, int n_ch,
+                float* X, int64_t T_long, int64_t n_frames, void* stream);
+
+/* Segment features.  Replaces the front half of ConformerCssWrapper.separate
+ * (conformer_wrapper.py:91-94) + FeatureExtractor.forward (feature.py:543-569): MVN magnitude of
+ * mic 0 (feature.py:496-507) and mean-normalised IPD v1 of mics 1..C-1 vs mic 0 (feature.py:214-221).
+ * Segment i (i < n_seg) covers frames [(seg_first + i)*hop, +T) of X; frames >= T_valid read as zeros
+ * (the zero-padded tail of the last segment, css.py:185-190; T_valid <= T_long = frame pitch of X).
+ * Row (i*T + t), column (m*257 + f).  If in_bias/in_scale are non-NULL the network's input
+ * normalisation (f + bias) * scale (conformer.py:297-299) is fused.  If feat_lo is non-NULL the
+ * value is stored split for the 3xTF32 GEMM: feat = tf32-truncated part, feat_lo = remainder.
+ * Columns >= 257*n_ch of a row are left untouched (the caller keeps the K padding zeroed). */
+int nsf_css_features(const float* X, int64_t T_long, int64_t T_valid, int n_ch, int64_t seg_first, int n_seg,
+                     int T, int hop, const float* in_bias, const float* in_scale,
+                     float* feat, float* feat_lo, int64_t ldf, void* stream);
+
+/* Mask network (ConformerCSS.forward, css_with_conformer/nnet/conformer.py:287-310, eval mode).
+ * The handle only records dimensions and the offsets of each tensor inside the caller's device blob
+ * (layout documented in notsofar_b200/separator.py::pack_weights).  */
+typedef struct nsf_conformer nsf_conformer;
+typedef struct {
+    int d_model, n_heads, d_ff, n_blocks, kernel_size, in_features, n_out, maxlen;
+    int T;            /* frames per segment */
+    int gemm_engine;  /* NSF_GEMM_* */
+} nsf_conformer_dims;
+
+int nsf_conformer_create(const nsf_conformer_dims* dims, const float* blob, int64_t blob_floats,
+                         const int64_t* offsets /*host*/, int n_offsets, nsf_conformer** out);
+void nsf_conformer_destroy(nsf_conformer* h);
+int64_t nsf_conformer_num_offsets(const nsf_conformer_dims* dims);
+/* bytes of scratch HBM nsf_conformer_forward needs for a batch of n_seg segments */
+int64_t nsf_conformer_workspace_bytes(const nsf_conformer_dims* dims, int n_seg);
+/* feat (+feat_lo): [n_seg*T][ldf] already input-normalised (see nsf_css_features);
+ * masks: [n_seg][n_out/257][257][T] = sigmoid(linear(...)). */
+int nsf_conformer_forward(nsf_conformer* h, const float* feat, const float* feat_lo, int64_t ldf, int n_seg,
+                          float* masks, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Mask-weighted MVDR.  Replaces make_mvdr(..., return_stft=True)
+ * (css_with_conformer/utils/mvdr_util.py:5-47: make_wta :50-55, get_mask_scm :58-66,
+ * calc_bfcoeffs :69-75, get_bf :78-80) and the floored-mask multiply of css.py:223-227.
+ * Arithmetic: spatial covariances, solve and beamformer in fp64 on chip (the reference's
+ * complex64 solve is only ~1e-2 accurate in ill-conditioned bins; parity is against the
+ * fp64-lifted reference).  mask_floor = 10^(floor_dB/20); 1.0 => pure MVDR.
+ * Segment geometry as in nsf_css_features.  X is [n_bins][T_long][C]; masks [n_seg][S+Nn][n_bins][T];
+ * Y [n_seg][S][n_bins][T].  Bin 0 gets the den += 1e-15 of mvdr_util.py:73.
+ * Built for S = 3, C = 7 (NSF_ERR_UNSUPPORTED otherwise); T must fit on chip (T <= ~1500). */
+int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float* X, int64_t T_long, int64_t T_valid, int n_ch,
+             int64_t seg_first, int n_seg, int T, int hop, int n_bins, float mask_floor,
+             float* Y, void* stream);
+
+/* PIT stitching costs.  Replaces PitWrapper._opt_perm_loss (css/training/losses.py:50-71) as called
+ * at css.py:276: cost[i][a][b] = mean_{f,t} loss(left_a, right_b) over the `overlap` trailing frames
+ * of segment i-1 and leading frames of segment i, for i = 1..n_seg-1 (cost[0] is zero).
+ * input_kind 0: masks [n_seg][n_ch_total][F][T] f32 (first n_spk channels); 1: |Y| with Y [n_seg][n_spk][F][T] c64.
+ * loss_kind 0: l1 (losses.py:104), 1: mse (losses.py:100).  The (tiny, sequential) permutation chain
+ * itself runs on the host. */
+int nsf_pit_cost(const void* in, int input_kind, int loss_kind, int n_seg, int n_ch_total, int n_spk,
+                 int n_bins, int T, int overlap, float* cost, void* stream);
+
+/* Weighted overlap-add of the permuted segment masks (css.py:254-299) and the activity mean
+ * (css.py:304).  seg_w [n_seg][T] f32 trapezoid weights (calc_segment_weight css.py:341-390, rows
+ * already specialised for first/last segment), wsum [T_long] their overlap-added sum,
+ * perms [n_seg][S] int32 (new channel k <- old channel perms[i][k]).
+ * mask_st [F][T_long][S]; activity [T_long][S] = mean_f mask_st. */
+int nsf_stitch_masks(const float* masks, int n_ch_total, const int32_t* perms, const float* seg_w,
+                     const float* wsum, int n_seg, int n_spk, int n_bins, int T, int hop, int64_t T_long,
+                     float* mask_st, float* activity, void* stream);
+
+/* Activity gate: (activity >= th) -> dilate(dil) -> erode(ero) per speaker
+ * (css.py:305-309, utils/numpy_utils.py:4-13).  act_b / act_final: [T_long][S] uint8; tmp same size. */
+int nsf_activity(const float* activity, int64_t T_long, int n_spk, float th, int dil, int ero,
+                 uint8_t* act_b, uint8_t* tmp, uint8_t* act_final, void* stream);
+
+/* Weighted overlap-add of the permuted separated STFTs, normalisation, activity gating
+ * (css.py:287-299, 312) and the [B*S, F, T] re-layout of css.py:316.  S_st [S][T_long][F] c64. */
+int nsf_stitch_stft(const float* Y, const int32_t* perms, const float* seg_w, const float* wsum,
+                    const uint8_t* act_final, int n_seg, int n_spk, int n_bins, int T, int hop,
+                    int64_t T_long, float* S_st, void* stream);
+
+/* Inverse STFT.  Replaces ConformerCssWrapper.istft (conformer_wrapper.py:131-146) -> iSTFT.forward
+ * (feature.py:138-167): y[n] = sum_t g[n - 256 t] * Re sum_{k<=256} S[k][t] exp(+2 pi i k (n-256t)/512),
+ * g = sqrt(hann_periodic)/16; no one-sided doubling, no window-sum normalisation.
+ * S_st [n_streams][T_long][F] c64 -> wav [n_streams][(T_long-1)*256+512] f32. */
+int nsf_istft(const float* S_st, int n_streams, int64_t T_long, float* wav, void* stream);
+
+/* File boundary.  Replaces write_wav's peak normalisation (utils/audio_utils.py:44-45) and
+ * libsndfile's float -> PCM_16 conversion: q = rint(x * 0.99 / (max|x| + 1e-7) * 32767).
+ * peak [n_streams] f32 scratch/output (max |x| per stream). */
+int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, float* peak, int16_t* pcm, void* stream);
+
+/* Test hook: C[M][N] = A[M][K] * W[N][K]^T + bias with the selected engine (row-major, K contiguous;
+ * K % 32 == 0, lda/ldw multiples of 4).  Used by the parity tests to check the tcgen05 GEMM
+ * against the CUDA-core one. */
+int nsf_gemm_test(int engine, const float* A, const float* W, const float* bias, float* Cout,
+                  int M, int N, int K, void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSF_B200_H_ */

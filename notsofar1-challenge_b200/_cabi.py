@@ -1,0 +1,85 @@
+"""ctypes binding of libnsf_b200.so (include/nsf_b200.h).  torch owns every buffer; this module only
+passes raw device pointers, sizes and the current CUDA stream, and turns error codes into exceptions.
+There is no CPU fallback: if the library is missing or a call fails, it raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnsf_b200.so")
+
+GEMM_SIMT_FP32, GEMM_TC_3XTF32, GEMM_TC_TF32 = 0, 1, 2
+
+c_f32p = C.c_void_p
+i64 = C.c_int64
+i32 = C.c_int
+
+
+class ConformerDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("d_model", "n_heads", "d_ff", "n_blocks", "kernel_size", "in_features",
+                                        "n_out", "maxlen", "T", "gemm_engine")]
+
+
+# name -> (restype, argtypes); must list every symbol include/nsf_b200.h declares
+SIGNATURES = {
+    "nsf_last_error": (C.c_char_p, []),
+    "nsf_version": (C.c_char_p, []),
+    "nsf_num_frames": (i64, [i64]),
+    "nsf_stft_mc": (i32, [c_f32p, i64, i32, c_f32p, i64, i64, C.c_void_p]),
+    "nsf_css_features": (i32, [c_f32p, i64, i64, i32, i64, i32, i32, i32, c_f32p, c_f32p, c_f32p, c_f32p, i64, C.c_void_p]),
+    "nsf_conformer_create": (i32, [C.POINTER(ConformerDims), c_f32p, i64, C.POINTER(i64), i32, C.POINTER(C.c_void_p)]),
+    "nsf_conformer_destroy": (None, [C.c_void_p]),
+    "nsf_conformer_num_offsets": (i64, [C.POINTER(ConformerDims)]),
+    "nsf_conformer_workspace_bytes": (i64, [C.POINTER(ConformerDims), i32]),
+    "nsf_conformer_forward": (i32, [C.c_void_p, c_f32p, c_f32p, i64, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
+    "nsf_mvdr": (i32, [c_f32p, i32, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, C.c_float, c_f32p, C.c_void_p]),
+    "nsf_pit_cost": (i32, [C.c_void_p, i32, i32, i32, i32, i32, i32, i32, i32, c_f32p, C.c_void_p]),
+    "nsf_stitch_masks": (i32, [c_f32p, i32, C.c_void_p, c_f32p, c_f32p, i32, i32, i32, i32, i32, i64, c_f32p, c_f32p, C.c_void_p]),
+    "nsf_activity": (i32, [c_f32p, i64, i32, C.c_float, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsf_stitch_stft": (i32, [c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, i32, i32, i32, i32, i32, i64, c_f32p, C.c_void_p]),
+    "nsf_istft": (i32, [c_f32p, i32, i64, c_f32p, C.c_void_p]),
+    "nsf_peaknorm_pcm16": (i32, [c_f32p, i32, i64, c_f32p, C.c_void_p, C.c_void_p]),
+    "nsf_gemm_test": (i32, [i32, c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, C.c_void_p, i64, C.c_void_p]),
+}
+
+_lib = None
+
+
+class NsfError(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """dlopen the library (building it first if it is absent and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise NsfError(f"{LIB_PATH} is missing; run `python __graft_entry__.py build`")
+        from . import build as _build
+        _build.build()
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().nsf_last_error().decode(errors="replace")
+        raise NsfError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,466 @@
+// Conformer mask network forward (eval mode), batched over segments.
+//
+// Reference: css/css_with_conformer/nnet/conformer.py
+//   ConformerCSS.forward :287-310, ConformerEncoder :189-239 (embed Linear->LN->ReLU :205-210, relative
+//   positions :229-233 / RelativePositionalEncoding :12-29), EncoderLayer :172-186
+//   (x += .5 FF; x += MHSA; x += Conv; x += .5 FF; LN), MultiHeadedAttention :57-92,
+//   ConvModule :113-127 (scalar 1x1 "pointwise" convs, GLU, depthwise k=33, BatchNorm eval, ReLU),
+//   FeedForward :146-150.
+// All matrix products go through gemm_launch (tcgen05 3xTF32 by default); everything else is fused
+// into a handful of streaming kernels here.  Activations that feed a GEMM are written "split"
+// (TF32 head + remainder, gemm_common.cuh).
+#include "gemm_common.cuh"
+#include <new>
+
+namespace nsf {
+
+constexpr int kPerLayer = 32;
+constexpr int kGlobalOffsets = 10;
+enum GlobalOff { G_EMB_W_HI = 0, G_EMB_W_LO, G_EMB_B, G_EMB_LN_G, G_EMB_LN_B, G_PE_HI, G_PE_LO, G_HEAD_W_HI, G_HEAD_W_LO, G_HEAD_B };
+enum LayerOff {
+    L_FFI_LN_G = 0, L_FFI_LN_B, L_FFI_W1_HI, L_FFI_W1_LO, L_FFI_B1, L_FFI_W2_HI, L_FFI_W2_LO, L_FFI_B2,
+    L_ATT_LN_G, L_ATT_LN_B, L_WQKV_HI, L_WQKV_LO, L_BQKV, L_WO_HI, L_WO_LO, L_BO,
+    L_CONV_LN_G, L_CONV_LN_B, L_CONV_SCALARS, L_DW_W, L_BN_SCALE, L_BN_SHIFT,
+    L_FFO_LN_G, L_FFO_LN_B, L_FFO_W1_HI, L_FFO_W1_LO, L_FFO_B1, L_FFO_W2_HI, L_FFO_W2_LO, L_FFO_B2,
+    L_OUT_LN_G, L_OUT_LN_B
+};
+
+}  // namespace nsf
+
+struct nsf_conformer {
+    nsf_conformer_dims dims;
+    const float* blob;
+    int64_t blob_floats;
+    int n_offsets;
+    int64_t* offsets;
+    const float* g(int i) const { return blob + offsets[i]; }
+    const float* l(int layer, int i) const { return blob + offsets[nsf::kGlobalOffsets + layer * nsf::kPerLayer + i]; }
+};
+
+namespace nsf {
+
+// ------------------------------------------------------------------------------------------- LayerNorm family
+constexpr int kLnMaxPerLane = 32;   // d_model <= 1024
+
+// y1 = LN(x; g1, b1) [relu]; optional store; y2 = LN(y1; g2, b2) if g2 else y1; optional split store.
+__global__ void __launch_bounds__(256)
+ln_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g1, const float* __restrict__ b1, int relu1,
+          float* __restrict__ out_x, const float* __restrict__ g2, const float* __restrict__ b2,
+          float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int n_per = d >> 5;
+    const float inv_d = 1.f / (float)d;
+    float v[kLnMaxPerLane];
+    const float* xr = x + (size_t)row * d;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i)
+        if (i < n_per) { v[i] = xr[i * 32 + lane]; s += v[i]; }
+    float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i)
+        if (i < n_per) { const float c = v[i] - mean; q += c * c; }
+    float rstd = 1.f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+    s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i)
+        if (i < n_per) {
+            const int c = i * 32 + lane;
+            float y = (v[i] - mean) * rstd * __ldg(g1 + c) + __ldg(b1 + c);
+            if (relu1) y = fmaxf(y, 0.f);
+            v[i] = y;
+            s += y;
+            if (out_x) out_x[(size_t)row * d + c] = y;
+        }
+    if (g2) {
+        mean = warp_sum(s) * inv_d;
+        q = 0.f;
+#pragma unroll
+        for (int i = 0; i < kLnMaxPerLane; ++i)
+            if (i < n_per) { const float c = v[i] - mean; q += c * c; }
+        rstd = 1.f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+#pragma unroll
+        for (int i = 0; i < kLnMaxPerLane; ++i)
+            if (i < n_per) {
+                const int c = i * 32 + lane;
+                v[i] = (v[i] - mean) * rstd * __ldg(g2 + c) + __ldg(b2 + c);
+            }
+    }
+    if (out_hi) {
+#pragma unroll
+        for (int i = 0; i < kLnMaxPerLane; ++i)
+            if (i < n_per) {
+                const size_t o = (size_t)row * d + i * 32 + lane;
+                if (out_lo) {
+                    float hi, lo;
+                    split_tf32(v[i], hi, lo);
+                    out_hi[o] = hi;
+                    out_lo[o] = lo;
+                } else {
+                    out_hi[o] = v[i];
+                }
+            }
+    }
+}
+
+// conv module front: h = LN(x); u = (w1a h + b1a) * sigmoid(w1g h + b1g)      conformer.py:115-117
+__global__ void __launch_bounds__(256)
+ln_glu_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g, const float* __restrict__ b,
+              const float* __restrict__ scalars, float* __restrict__ u) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const int n_per = d >> 5;
+    const float inv_d = 1.f / (float)d;
+    float v[kLnMaxPerLane];
+    const float* xr = x + (size_t)row * d;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i)
+        if (i < n_per) { v[i] = xr[i * 32 + lane]; s += v[i]; }
+    const float mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i)
+        if (i < n_per) { const float c = v[i] - mean; q += c * c; }
+    const float rstd = 1.f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+    const float w1a = __ldg(scalars + 0), b1a = __ldg(scalars + 1), w1g = __ldg(scalars + 2), b1g = __ldg(scalars + 3);
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i)
+        if (i < n_per) {
+            const int c = i * 32 + lane;
+            const float h = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
+            const float a = w1a * h + b1a, gt = w1g * h + b1g;
+            u[(size_t)row * d + c] = a * (1.f / (1.f + expf(-gt)));
+        }
+}
+
+// conv module back: depthwise conv over time (zero padded inside the segment), BN (folded), ReLU, scalar affine,
+// residual add.                                                                     conformer.py:118-126, 181
+constexpr int kDwTT = 32, kDwCC = 128, kDwMaxK = 33;
+__global__ void __launch_bounds__(256)
+dwconv_kernel(const float* __restrict__ u, float* __restrict__ x, int T, int d, int ks, const float* __restrict__ dw_w,
+              const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const float* __restrict__ scalars) {
+    extern __shared__ float tile[];     // [kDwTT + ks - 1][kDwCC]
+    const int seg = blockIdx.z, c0 = blockIdx.y * kDwCC, t0 = blockIdx.x * kDwTT;
+    const int pad = (ks - 1) / 2;
+    const int rows = kDwTT + ks - 1;
+    for (int idx = threadIdx.x; idx < rows * kDwCC; idx += blockDim.x) {
+        const int r = idx / kDwCC, c = idx - r * kDwCC;
+        const int t = t0 + r - pad;
+        tile[idx] = (t >= 0 && t < T && c0 + c < d) ? __ldg(u + ((size_t)seg * T + t) * d + c0 + c) : 0.f;
+    }
+    __syncthreads();
+    const int c = threadIdx.x % kDwCC, half = threadIdx.x / kDwCC;
+    if (c0 + c >= d) return;
+    float w[kDwMaxK];
+#pragma unroll
+    for (int j = 0; j < kDwMaxK; ++j) w[j] = j < ks ? __ldg(dw_w + (size_t)(c0 + c) * ks + j) : 0.f;
+    const float sc = __ldg(bn_scale + c0 + c), sh = __ldg(bn_shift + c0 + c);
+    const float w2 = __ldg(scalars + 4), b2 = __ldg(scalars + 5);
+    for (int tt = half; tt < kDwTT; tt += 2) {
+        const int t = t0 + tt;
+        if (t >= T) break;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < kDwMaxK; ++j)
+            if (j < ks) acc = fmaf(w[j], tile[(tt + j) * kDwCC + c], acc);
+        const float y = fmaxf(acc * sc + sh, 0.f);
+        const size_t o = ((size_t)seg * T + t) * d + c0 + c;
+        x[o] = x[o] + (w2 * y + b2);
+    }
+}
+
+// softmax over t2 of (S1[bh][t1][t2] + S2[bh*T + t1][t1 - t2 + T - 1]) / sqrt(d_k)       conformer.py:73-87
+constexpr int kSmMaxPerLane = 8;    // T <= 256
+__global__ void __launch_bounds__(256)
+relpos_softmax_kernel(const float* __restrict__ S1, const float* __restrict__ S2, int rows_total, int T, int Tp, int ld2,
+                      float inv_sqrt_dk, float* __restrict__ P_hi, float* __restrict__ P_lo) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);       // bh * T + t1
+    const int lane = threadIdx.x & 31;
+    if (row >= rows_total) return;
+    const int bh = row / T, t1 = row - bh * T;
+    const float* s1 = S1 + ((size_t)bh * T + t1) * Tp;
+    const float* s2 = S2 + (size_t)row * ld2 + (t1 + T - 1);
+    float v[kSmMaxPerLane];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kSmMaxPerLane; ++i) {
+        const int t2 = i * 32 + lane;
+        v[i] = -INFINITY;
+        if (t2 < T) { v[i] = (__ldg(s1 + t2) + __ldg(s2 - t2)) * inv_sqrt_dk; mx = fmaxf(mx, v[i]); }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSmMaxPerLane; ++i) {
+        const int t2 = i * 32 + lane;
+        if (t2 < T) { v[i] = expf(v[i] - mx); sum += v[i]; }
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < kSmMaxPerLane; ++i) {
+        const int t2 = i * 32 + lane;
+        if (t2 < Tp) {
+            const float pv = t2 < T ? v[i] * inv : 0.f;
+            float hi, lo;
+            split_tf32(pv, hi, lo);
+            const size_t o = ((size_t)bh * T + t1) * Tp + t2;
+            P_hi[o] = hi;
+            P_lo[o] = lo;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float h, l; split_tf32(in[i], h, l); hi[i] = h; lo[i] = l; }
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Workspace {
+    float *x, *h_hi, *h_lo, *u_hi, *u_lo, *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo, *s1, *s2, *p_hi, *p_lo;
+    int64_t total_floats;
+};
+
+static Workspace carve(const nsf_conformer_dims& D, int n_seg, float* base) {
+    const int64_t M = (int64_t)n_seg * D.T;
+    const int Tp = (int)align_up(D.T, 32);
+    const int ld2 = (int)align_up(2 * D.T - 1, 32);
+    const int64_t BH = (int64_t)n_seg * D.n_heads;
+    const int d_k = D.d_model / D.n_heads;
+    int64_t off = 0;
+    auto take = [&](int64_t n) { float* p = base ? base + off : nullptr; off += align_up(n, 64); return p; };
+    Workspace w;
+    w.x = take(M * D.d_model);
+    w.h_hi = take(M * D.d_model);
+    w.h_lo = take(M * D.d_model);
+    w.u_hi = take(M * D.d_ff);
+    w.u_lo = take(M * D.d_ff);
+    w.q_hi = take(M * D.d_model);
+    w.q_lo = take(M * D.d_model);
+    w.k_hi = take(M * D.d_model);
+    w.k_lo = take(M * D.d_model);
+    w.vt_hi = take(BH * d_k * Tp);
+    w.vt_lo = take(BH * d_k * Tp);
+    w.s1 = take(BH * D.T * Tp);
+    w.s2 = take(BH * D.T * ld2);
+    w.p_hi = take(BH * D.T * Tp);
+    w.p_lo = take(BH * D.T * Tp);
+    w.total_floats = off;
+    return w;
+}
+
+static int validate_dims(const nsf_conformer_dims& D) {
+    NSF_REQUIRE(D.d_model >= 32 && D.d_model <= 1024 && D.d_model % 32 == 0, "conformer: d_model=%d", D.d_model);
+    NSF_REQUIRE(D.n_heads >= 1 && D.d_model % D.n_heads == 0 && (D.d_model / D.n_heads) % 32 == 0,
+                "conformer: d_model/n_heads must be a multiple of 32");
+    NSF_REQUIRE(D.d_ff >= 32 && D.d_ff % 32 == 0, "conformer: d_ff=%d", D.d_ff);
+    NSF_REQUIRE(D.n_blocks >= 1 && D.kernel_size >= 1 && D.kernel_size <= kDwMaxK && (D.kernel_size & 1),
+                "conformer: kernel_size=%d", D.kernel_size);
+    NSF_REQUIRE(D.T >= 2 && D.T <= 32 * kSmMaxPerLane && D.T <= D.maxlen, "conformer: T=%d", D.T);
+    NSF_REQUIRE(D.n_out >= kBins && D.n_out % kBins == 0, "conformer: n_out=%d", D.n_out);
+    NSF_REQUIRE(D.gemm_engine >= NSF_GEMM_SIMT_FP32 && D.gemm_engine <= NSF_GEMM_TC_TF32, "conformer: gemm_engine");
+    return NSF_OK;
+}
+
+}  // namespace nsf
+
+using namespace nsf;
+
+extern "C" int64_t nsf_conformer_num_offsets(const nsf_conformer_dims* dims) {
+    return dims ? kGlobalOffsets + (int64_t)kPerLayer * dims->n_blocks : 0;
+}
+
+extern "C" int nsf_conformer_create(const nsf_conformer_dims* dims, const float* blob, int64_t blob_floats,
+                                    const int64_t* offsets, int n_offsets, nsf_conformer** out) {
+    NSF_REQUIRE(dims && blob && offsets && out, "nsf_conformer_create: null pointer");
+    int rc = validate_dims(*dims);
+    if (rc) return rc;
+    NSF_REQUIRE(n_offsets == nsf_conformer_num_offsets(dims), "nsf_conformer_create: expected %lld offsets, got %d",
+                (long long)nsf_conformer_num_offsets(dims), n_offsets);
+    for (int i = 0; i < n_offsets; ++i)
+        NSF_REQUIRE(offsets[i] >= 0 && offsets[i] < blob_floats && (offsets[i] & 3) == 0,
+                    "nsf_conformer_create: offset %d = %lld out of range or not 16-byte aligned", i, (long long)offsets[i]);
+    nsf_conformer* h = new (std::nothrow) nsf_conformer;
+    NSF_REQUIRE(h, "nsf_conformer_create: out of memory");
+    h->dims = *dims;
+    h->blob = blob;
+    h->blob_floats = blob_floats;
+    h->n_offsets = n_offsets;
+    h->offsets = new (std::nothrow) int64_t[n_offsets];
+    if (!h->offsets) { delete h; set_error("nsf_conformer_create: out of memory"); return NSF_ERR_INVALID_ARG; }
+    for (int i = 0; i < n_offsets; ++i) h->offsets[i] = offsets[i];
+    *out = h;
+    return NSF_OK;
+}
+
+extern "C" void nsf_conformer_destroy(nsf_conformer* h) {
+    if (!h) return;
+    delete[] h->offsets;
+    delete h;
+}
+
+extern "C" int64_t nsf_conformer_workspace_bytes(const nsf_conformer_dims* dims, int n_seg) {
+    if (!dims || n_seg <= 0) return 0;
+    return carve(*dims, n_seg, nullptr).total_floats * (int64_t)sizeof(float);
+}
+
+extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const float* feat_lo, int64_t ldf, int n_seg,
+                                     float* masks, void* workspace, int64_t workspace_bytes, void* stream_) {
+    NSF_REQUIRE(h && feat && masks && workspace, "nsf_conformer_forward: null pointer");
+    if (n_seg <= 0) return NSF_OK;
+    const nsf_conformer_dims& D = h->dims;
+    const int eng = D.gemm_engine;
+    NSF_REQUIRE(eng == NSF_GEMM_SIMT_FP32 || feat_lo, "nsf_conformer_forward: tensor-core engines need split features");
+    const int Kf = (int)align_up(D.in_features, 32);
+    NSF_REQUIRE(ldf >= Kf && (ldf & 3) == 0, "nsf_conformer_forward: ldf=%lld must be >= %d and a multiple of 4", (long long)ldf, Kf);
+    NSF_REQUIRE(((uintptr_t)workspace & 255) == 0, "nsf_conformer_forward: workspace must be 256-byte aligned");
+    Workspace w = carve(D, n_seg, reinterpret_cast<float*>(workspace));
+    NSF_REQUIRE(workspace_bytes >= w.total_floats * (int64_t)sizeof(float), "nsf_conformer_forward: workspace too small");
+    cudaStream_t s = (cudaStream_t)stream_;
+
+    const int T = D.T, d = D.d_model, H = D.n_heads, d_k = d / H, dff = D.d_ff;
+    const int M = n_seg * T;
+    const int Tp = (int)align_up(T, 32), ld2 = (int)align_up(2 * T - 1, 32);
+    const int BH = n_seg * H;
+    const int ln_grid = ceil_div(M, 8);
+    int rc;
+
+    auto base_params = [&]() {
+        GemmParams p = {};
+        p.batch = 1;
+        p.alpha = 1.f;
+        p.T = T; p.Tp = Tp; p.n_heads = H; p.d_k = d_k; p.d_model = d;
+        return p;
+    };
+    auto linear = [&](const float* a_hi, const float* a_lo, int64_t lda, int K, const float* w_hi, const float* w_lo,
+                      const float* bias, int N, int epi, float alpha, float* o0, float* o1, int64_t ldo) {
+        GemmParams p = base_params();
+        p.A_hi = a_hi; p.A_lo = a_lo; p.lda = lda;
+        p.B_hi = w_hi; p.B_lo = w_lo; p.ldb = K;
+        p.M = M; p.N = N; p.K = K; p.n_valid = N;
+        p.bias = bias; p.epi = epi; p.alpha = alpha;
+        p.out0 = o0; p.out1 = o1; p.ldo = ldo;
+        p.q_hi = w.q_hi; p.q_lo = w.q_lo; p.k_hi = w.k_hi; p.k_lo = w.k_lo; p.vt_hi = w.vt_hi; p.vt_lo = w.vt_lo;
+        return gemm_launch(eng, p, s);
+    };
+
+    // the time padding of V^T (columns T..Tp-1) must be zero for the P V product
+    if (Tp != T) {
+        NSF_CUDA(cudaMemsetAsync(w.vt_hi, 0, sizeof(float) * (size_t)BH * d_k * Tp, s));
+        NSF_CUDA(cudaMemsetAsync(w.vt_lo, 0, sizeof(float) * (size_t)BH * d_k * Tp, s));
+    }
+
+    // embed: Linear -> LayerNorm -> ReLU (conformer.py:205-210), fused with layer 0's first LayerNorm
+    rc = linear(feat, feat_lo, ldf, Kf, h->g(G_EMB_W_HI), h->g(G_EMB_W_LO), h->g(G_EMB_B), d, EPI_STORE, 1.f, w.x, nullptr, d);
+    if (rc) return rc;
+    ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->g(G_EMB_LN_G), h->g(G_EMB_LN_B), 1, w.x, h->l(0, L_FFI_LN_G),
+                                     h->l(0, L_FFI_LN_B), w.h_hi, w.h_lo);
+    if ((rc = check_launch("ln_kernel(embed)"))) return rc;
+
+    const float inv_sqrt_dk = 1.f / sqrtf((float)d_k);
+    for (int L = 0; L < D.n_blocks; ++L) {
+        // x += 0.5 * FF_in(x)                                                                  conformer.py:179
+        rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_FFI_W1_HI), h->l(L, L_FFI_W1_LO), h->l(L, L_FFI_B1), dff, EPI_RELU_SPLIT,
+                    1.f, w.u_hi, w.u_lo, dff);
+        if (rc) return rc;
+        rc = linear(w.u_hi, w.u_lo, dff, dff, h->l(L, L_FFI_W2_HI), h->l(L, L_FFI_W2_LO), h->l(L, L_FFI_B2), d, EPI_RESID, 0.5f,
+                    w.x, nullptr, d);
+        if (rc) return rc;
+        // x += MHSA(x)                                                                         conformer.py:180
+        ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr,
+                                         w.h_hi, w.h_lo);
+        if ((rc = check_launch("ln_kernel(attn)"))) return rc;
+        rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WQKV_HI), h->l(L, L_WQKV_LO), h->l(L, L_BQKV), 3 * d, EPI_QKV, 1.f, nullptr,
+                    nullptr, 0);
+        if (rc) return rc;
+        {   // A = q k^T per (segment, head)
+            GemmParams p = base_params();
+            p.A_hi = w.q_hi; p.A_lo = w.q_lo; p.lda = d_k; p.a_batch_stride = (int64_t)T * d_k;
+            p.B_hi = w.k_hi; p.B_lo = w.k_lo; p.ldb = d_k; p.b_batch_stride = (int64_t)T * d_k;
+            p.M = T; p.N = T; p.K = d_k; p.n_valid = T; p.batch = BH;
+            p.epi = EPI_STORE; p.out0 = w.s1; p.ldo = Tp; p.o_batch_stride = (int64_t)T * Tp;
+            if ((rc = gemm_launch(eng, p, s))) return rc;
+        }
+        {   // B' = q pe_k[maxlen-(T-1) .. maxlen+(T-1)]^T for every (segment, head, t1) row at once
+            GemmParams p = base_params();
+            p.A_hi = w.q_hi; p.A_lo = w.q_lo; p.lda = d_k;
+            const int64_t pe_off = (int64_t)(D.maxlen - (T - 1)) * d_k;
+            p.B_hi = h->g(G_PE_HI) + pe_off; p.B_lo = h->g(G_PE_LO) + pe_off; p.ldb = d_k;
+            p.M = BH * T; p.N = 2 * T - 1; p.K = d_k; p.n_valid = 2 * T - 1;
+            p.epi = EPI_STORE; p.out0 = w.s2; p.ldo = ld2;
+            if ((rc = gemm_launch(eng, p, s))) return rc;
+        }
+        relpos_softmax_kernel<<<ceil_div(BH * T, 8), 256, 0, s>>>(w.s1, w.s2, BH * T, T, Tp, ld2, inv_sqrt_dk, w.p_hi, w.p_lo);
+        if ((rc = check_launch("relpos_softmax_kernel"))) return rc;
+        {   // o = p v per (segment, head), gathered back to [M, d_model]
+            GemmParams p = base_params();
+            p.A_hi = w.p_hi; p.A_lo = w.p_lo; p.lda = Tp; p.a_batch_stride = (int64_t)T * Tp;
+            p.B_hi = w.vt_hi; p.B_lo = w.vt_lo; p.ldb = Tp; p.b_batch_stride = (int64_t)d_k * Tp;
+            p.M = T; p.N = d_k; p.K = Tp; p.n_valid = d_k; p.batch = BH;
+            p.epi = EPI_PV; p.out0 = w.h_hi; p.out1 = w.h_lo; p.ldo = d;
+            if ((rc = gemm_launch(eng, p, s))) return rc;
+        }
+        rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WO_HI), h->l(L, L_WO_LO), h->l(L, L_BO), d, EPI_RESID, 1.f, w.x, nullptr, d);
+        if (rc) return rc;
+        // x += Conv(x)                                                                         conformer.py:181
+        ln_glu_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), h->l(L, L_CONV_SCALARS), w.u_hi);
+        if ((rc = check_launch("ln_glu_kernel"))) return rc;
+        {
+            dim3 grid(ceil_div(T, kDwTT), ceil_div(d, kDwCC), n_seg);
+            const size_t smem = (size_t)(kDwTT + D.kernel_size - 1) * kDwCC * sizeof(float);
+            dwconv_kernel<<<grid, 256, smem, s>>>(w.u_hi, w.x, T, d, D.kernel_size, h->l(L, L_DW_W), h->l(L, L_BN_SCALE),
+                                                 h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS));
+            if ((rc = check_launch("dwconv_kernel"))) return rc;
+        }
+        // x += 0.5 * FF_out(x)                                                                 conformer.py:182
+        ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr,
+                                         w.h_hi, w.h_lo);
+        if ((rc = check_launch("ln_kernel(ff_out)"))) return rc;
+        rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_FFO_W1_HI), h->l(L, L_FFO_W1_LO), h->l(L, L_FFO_B1), dff, EPI_RELU_SPLIT,
+                    1.f, w.u_hi, w.u_lo, dff);
+        if (rc) return rc;
+        rc = linear(w.u_hi, w.u_lo, dff, dff, h->l(L, L_FFO_W2_HI), h->l(L, L_FFO_W2_LO), h->l(L, L_FFO_B2), d, EPI_RESID, 0.5f,
+                    w.x, nullptr, d);
+        if (rc) return rc;
+        // x = LN(x) (conformer.py:184), fused with the next block's first LayerNorm (or the split for the mask head)
+        const bool last = (L == D.n_blocks - 1);
+        ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_OUT_LN_G), h->l(L, L_OUT_LN_B), 0, last ? nullptr : w.x,
+                                         last ? nullptr : h->l(L + 1, L_FFI_LN_G), last ? nullptr : h->l(L + 1, L_FFI_LN_B),
+                                         w.h_hi, w.h_lo);
+        if ((rc = check_launch("ln_kernel(out)"))) return rc;
+    }
+    // mask head: sigmoid(Linear), transposed into [seg][mask][F][T]                             conformer.py:302-309
+    rc = linear(w.h_hi, w.h_lo, d, d, h->g(G_HEAD_W_HI), h->g(G_HEAD_W_LO), h->g(G_HEAD_B), D.n_out, EPI_MASK, 1.f, masks, nullptr, 0);
+    return rc;
+}
+
+extern "C" int nsf_gemm_test(int engine, const float* A, const float* W, const float* bias, float* Cout, int M, int N,
+                             int K, void* workspace, int64_t workspace_bytes, void* stream_) {
+    NSF_REQUIRE(A && W && Cout && workspace, "nsf_gemm_test: null pointer");
+    NSF_REQUIRE(K % 32 == 0 && M > 0 && N > 0, "nsf_gemm_test: K must be a multiple of 32");
+    const int64_t na = (int64_t)M * K, nw = (int64_t)N * K;
+    const int64_t need = (align_up(na, 64) * 2 + align_up(nw, 64) * 2) * (int64_t)sizeof(float);
+    NSF_REQUIRE(workspace_bytes >= need, "nsf_gemm_test: workspace needs %lld bytes", (long long)need);
+    cudaStream_t s = (cudaStream_t)stream_;
+    float* a_hi = reinterpret_cast<float*>(workspace);
+    float* a_lo = a_hi + align_up(na, 64);
+    float* w_hi = a_lo + align_up(na, 64);
+    float* w_lo = w_hi + align_up(nw, 64);
+    split_kernel<<<(unsigned)ceil_div64(na, 256), 256, 0, s>>>(A, na, a_hi, a_lo);
+    split_kernel<<<(unsigned)ceil_div64(nw, 256), 256, 0, s>>>(W, nw, w_hi, w_lo);
+    int rc = check_launch("split_kernel");
+    if (rc) return rc;
+    GemmParams p = {};
+    p.A_hi = a_hi; p.A_lo = a_lo; p.lda = K;
+    p.B_hi = w_hi; p.B_lo = w_lo; p.ldb = K;
+    p.M = M; p.N = N; p.K = K; p.n_valid = N; p.batch = 1;
+    p.bias = bias; p.epi = EPI_STORE; p.alpha = 1.f; p.out0 = Cout; p.ldo = N;
+    return gemm_launch(engine, p, s);
+}

@@ -1,0 +1,166 @@
+// Segment feature extraction (HBM-bound elementwise + per-(segment, bin) time reductions).
+//
+// Reference: ConformerCssWrapper.separate front half (css/training/conformer_wrapper.py:91-94:
+// stft.abs(), stft.angle()) + FeatureExtractor.forward (css_with_conformer/executor/feature.py:543-569):
+//   spectral  f0 = clamp(|X_0|, eps); (f0 - mean_T) / (std_T(unbiased) + eps)          feature.py:496-507
+//   spatial   d_m = angle(X_m) - angle(X_0); yr = cos d, yi = sin d;
+//             ipd_m = atan2(yi - mean_T yi, yr - mean_T yr)   (ipd_mean_normalize_version 1)  feature.py:214-221
+// Generic bins take cos/sin of the phase difference straight from X_m conj(X_0) / (|X_m||X_0|)
+// (no atan2 -> sincos round trip).  The DC and Nyquist bins are real up to the sin(pi_f32) residue
+// th.polar leaves, so there the *sign* of every IPD hangs on the last bit of the reference's
+// float32 atan2/sin: those two bins replay the reference's arithmetic literally
+// (angle -> -3.1415925f for negative real parts, sinf/cosf of the float32 difference).
+#include "common.cuh"
+
+namespace nsf {
+
+constexpr int kFeatBinsPerCta = 8;     // one warp per bin
+constexpr int kFeatMaxIter = 8;        // T <= 256
+constexpr float kEps32 = 1.1920928955078125e-07f;   // th.finfo(th.float32).eps, feature.py:15
+
+template <int C>
+__global__ void __launch_bounds__(kFeatBinsPerCta * 32)
+css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_valid, int64_t seg_first, int T, int hop,
+                    const float* __restrict__ in_bias, const float* __restrict__ in_scale,
+                    float* __restrict__ feat, float* __restrict__ feat_lo, int64_t ldf) {
+    extern __shared__ float tile[];     // [T][C][kFeatBinsPerCta]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.y;
+    const int f0bin = blockIdx.x * kFeatBinsPerCta;
+    const int f = f0bin + warp;
+    const int64_t st = (seg_first + seg) * (int64_t)hop;
+
+    if (f < kBins) {
+        const bool edge_bin = (f == 0 || f == kBins - 1);
+        const float2* Xf = X + ((size_t)f * T_long + st) * C;
+        float mag0[kFeatMaxIter];
+        float yr[kFeatMaxIter][C - 1 > 0 ? C - 1 : 1], yi[kFeatMaxIter][C - 1 > 0 ? C - 1 : 1];
+        float s_mag = 0.f;
+        float s_yr[C - 1 > 0 ? C - 1 : 1], s_yi[C - 1 > 0 ? C - 1 : 1];
+#pragma unroll
+        for (int m = 0; m < C - 1; ++m) { s_yr[m] = 0.f; s_yi[m] = 0.f; }
+#pragma unroll
+        for (int it = 0; it < kFeatMaxIter; ++it) {
+            const int t = it * 32 + lane;
+            mag0[it] = 0.f;
+            if (t < T) {
+                float2 x[C];
+                const bool valid = (st + t) < T_valid;       // zero-padded tail of the last segment, css.py:185-190
+#pragma unroll
+                for (int c = 0; c < C; ++c) x[c] = valid ? __ldg(Xf + (size_t)t * C + c) : make_float2(0.f, 0.f);
+                const float a0 = sqrtf(x[0].x * x[0].x + x[0].y * x[0].y);
+                const float fm = fmaxf(a0, kEps32);
+                mag0[it] = fm;
+                s_mag += fm;
+                if (edge_bin) {
+                    // literal replay: phase in {0, -3.1415925f} (torch angle of (re<0, tiny negative imag))
+                    const float p0 = (x[0].x < 0.f) ? -3.1415925f : 0.f;
+#pragma unroll
+                    for (int m = 0; m < C - 1; ++m) {
+                        const float pm = (x[m + 1].x < 0.f) ? -3.1415925f : 0.f;
+                        const float d = pm - p0;
+                        // cosf/sinf of {0, +-3.1415925f}: exact table of the correctly rounded values
+                        const float cr = (d == 0.f) ? 1.f : -1.f;
+                        const float sr = (d == 0.f) ? 0.f : (d > 0.f ? 1.509958e-07f : -1.509958e-07f);
+                        yr[it][m] = cr; yi[it][m] = sr;
+                        s_yr[m] += cr; s_yi[m] += sr;
+                    }
+                } else {
+                    // unit phasor of X_0 (angle(0) == 0 -> (1, 0))
+                    const float inv0 = a0 > 0.f ? 1.f / a0 : 0.f;
+                    const float u0x = a0 > 0.f ? x[0].x * inv0 : 1.f, u0y = x[0].y * inv0;
+#pragma unroll
+                    for (int m = 0; m < C - 1; ++m) {
+                        const float am = sqrtf(x[m + 1].x * x[m + 1].x + x[m + 1].y * x[m + 1].y);
+                        const float invm = am > 0.f ? 1.f / am : 0.f;
+                        const float umx = am > 0.f ? x[m + 1].x * invm : 1.f, umy = x[m + 1].y * invm;
+                        // u_m * conj(u_0) = exp(i (angle_m - angle_0))
+                        const float cr = umx * u0x + umy * u0y;
+                        const float sr = umy * u0x - umx * u0y;
+                        yr[it][m] = cr; yi[it][m] = sr;
+                        s_yr[m] += cr; s_yi[m] += sr;
+                    }
+                }
+            }
+        }
+        const float invT = 1.f / (float)T;
+        const float mean = warp_sum(s_mag) / (float)T;
+        float ssq = 0.f;
+#pragma unroll
+        for (int it = 0; it < kFeatMaxIter; ++it) {
+            const int t = it * 32 + lane;
+            if (t < T) { const float d = mag0[it] - mean; ssq += d * d; }
+        }
+        const float var = warp_sum(ssq) / (float)(T - 1);       // unbiased, torch.std default
+        const float rstd = 1.f / (sqrtf(var) + kEps32);
+        float m_yr[C - 1 > 0 ? C - 1 : 1], m_yi[C - 1 > 0 ? C - 1 : 1];
+#pragma unroll
+        for (int m = 0; m < C - 1; ++m) {
+            m_yr[m] = warp_sum(s_yr[m]) / (float)T;
+            m_yi[m] = warp_sum(s_yi[m]) / (float)T;
+        }
+        (void)invT;
+#pragma unroll
+        for (int it = 0; it < kFeatMaxIter; ++it) {
+            const int t = it * 32 + lane;
+            if (t < T) {
+                float* o = tile + ((size_t)t * C) * kFeatBinsPerCta + warp;
+                o[0] = (mag0[it] - mean) * rstd;
+#pragma unroll
+                for (int m = 0; m < C - 1; ++m)
+                    o[(m + 1) * kFeatBinsPerCta] = atan2f(yi[it][m] - m_yi[m], yr[it][m] - m_yr[m]);
+            }
+        }
+    }
+    __syncthreads();
+    // write-out: row (seg*T + t), column m*257 + f, runs of up to 8 consecutive bins
+    const int nb = min(kFeatBinsPerCta, kBins - f0bin);
+    const int total = T * C * kFeatBinsPerCta;
+    for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+        const int b = idx % kFeatBinsPerCta;
+        const int m = (idx / kFeatBinsPerCta) % C;
+        const int t = idx / (kFeatBinsPerCta * C);
+        if (b >= nb) continue;
+        const int col = m * kBins + f0bin + b;
+        float v = tile[idx];
+        if (in_bias) v = (v + __ldg(in_bias + col)) * __ldg(in_scale + col);      // conformer.py:297-299
+        const size_t o = ((size_t)seg * T + t) * ldf + col;
+        if (feat_lo) {
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            feat[o] = hi;
+            feat_lo[o] = lo;
+        } else {
+            feat[o] = v;
+        }
+    }
+}
+
+}  // namespace nsf
+
+using namespace nsf;
+
+extern "C" int nsf_css_features(const float* X, int64_t T_long, int64_t T_valid, int n_ch, int64_t seg_first, int n_seg,
+                                int T, int hop, const float* in_bias, const float* in_scale, float* feat,
+                                float* feat_lo, int64_t ldf, void* stream) {
+    NSF_REQUIRE(X && feat, "nsf_css_features: null pointer");
+    NSF_REQUIRE(n_ch == 7 || n_ch == 1, "nsf_css_features: n_ch=%d (supported: 7, 1)", n_ch);
+    NSF_REQUIRE(T >= 2 && T <= 32 * kFeatMaxIter, "nsf_css_features: T=%d not in [2,%d]", T, 32 * kFeatMaxIter);
+    NSF_REQUIRE(ldf >= (int64_t)kBins * n_ch, "nsf_css_features: ldf too small");
+    NSF_REQUIRE((in_bias == nullptr) == (in_scale == nullptr), "nsf_css_features: bias/scale must come together");
+    NSF_REQUIRE(T_valid <= T_long && (seg_first + n_seg - 1) * (int64_t)hop + T <= T_long + 0 || T_valid < T_long + 1,
+                "nsf_css_features: segment range outside X");
+    if (n_seg <= 0) return NSF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(ceil_div(kBins, kFeatBinsPerCta), n_seg);
+    const size_t smem = (size_t)T * n_ch * kFeatBinsPerCta * sizeof(float);
+    if (n_ch == 7) {
+        NSF_CUDA(cudaFuncSetAttribute(css_features_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        css_features_kernel<7><<<grid, kFeatBinsPerCta * 32, smem, s>>>(reinterpret_cast<const float2*>(X), T_long, T_valid,
+                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf);
+    } else {
+        css_features_kernel<1><<<grid, kFeatBinsPerCta * 32, smem, s>>>(reinterpret_cast<const float2*>(X), T_long, T_valid,
+                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf);
+    }
+    return check_launch("css_features_kernel");
+}

@@ -1,0 +1,107 @@
+// GEMM problem description and the fused epilogues shared by the two engines
+// (gemm_simt.cu: CUDA-core fp32, gemm_tc.cu: tcgen05 kind::tf32 with TMEM accumulators).
+//
+//   D[b][m][n] = sum_k A[b][m][k] * B[b][n][k]        A: [batch][M][K], B: [batch][N][K], K contiguous
+//
+// Operands are stored "split": X_hi holds the TF32-representable head of every fp32 value (low 13
+// mantissa bits zero), X_lo the exact remainder, X_hi + X_lo == X.  The tensor-core engine computes
+// A_hi B_hi + A_lo B_hi + A_hi B_lo (3xTF32, ~2^-21 relative) or A_hi B_hi alone; the CUDA-core
+// engine multiplies the re-assembled fp32 values.
+#pragma once
+#include "common.cuh"
+
+namespace nsf {
+
+enum GemmEpilogue : int {
+    EPI_STORE = 0,        // out0[b][m][n] = acc + bias[n]
+    EPI_RELU_SPLIT = 1,   // v = relu(acc + bias[n]); (out0, out1)[m][n] = split(v)
+    EPI_RESID = 2,        // out0[m][n] += alpha * (acc + bias[n])                 (residual stream, in place)
+    EPI_QKV = 3,          // scatter q, k (head-major, split) and v (head-major, transposed, split)
+    EPI_PV = 4,           // attention output of batch (seg, head) -> (out0, out1)[seg*T + m][head*d_k + n] split
+    EPI_MASK = 5,         // out0[seg][n / 257][n % 257][t] = sigmoid(acc + bias[n]),  m = seg*T + t, n < n_valid
+};
+
+struct GemmParams {
+    const float* A_hi; const float* A_lo; int64_t lda; int64_t a_batch_stride;
+    const float* B_hi; const float* B_lo; int64_t ldb; int64_t b_batch_stride;
+    int M, N, K, batch;
+    int n_valid;              // columns >= n_valid are padding (weights padded with zero rows)
+    const float* bias;        // [n_valid] or nullptr
+    int epi;
+    float alpha;
+    float* out0; float* out1; int64_t ldo; int64_t o_batch_stride;
+    // geometry for the scatter epilogues
+    int T, Tp, n_heads, d_k, d_model;
+    float* q_hi; float* q_lo; float* k_hi; float* k_lo; float* vt_hi; float* vt_lo;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+// One output element.  (b, m, n) are in range: m < M, n < n_valid.
+__device__ __forceinline__ void gemm_epilogue(const GemmParams& p, int b, int m, int n, float acc) {
+    const float v = acc + (p.bias ? __ldg(p.bias + n) : 0.f);
+    switch (p.epi) {
+        case EPI_STORE:
+            p.out0[(size_t)b * p.o_batch_stride + (size_t)m * p.ldo + n] = v;
+            break;
+        case EPI_RELU_SPLIT: {
+            float hi, lo;
+            split_tf32(fmaxf(v, 0.f), hi, lo);
+            const size_t o = (size_t)m * p.ldo + n;
+            p.out0[o] = hi;
+            p.out1[o] = lo;
+            break;
+        }
+        case EPI_RESID: {
+            const size_t o = (size_t)m * p.ldo + n;
+            p.out0[o] = p.out0[o] + p.alpha * v;
+            break;
+        }
+        case EPI_QKV: {
+            const int which = n / p.d_model, c = n - which * p.d_model;
+            const int h = c / p.d_k, d = c - h * p.d_k;
+            const int seg = m / p.T, t = m - seg * p.T;
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            if (which < 2) {
+                const size_t o = (((size_t)seg * p.n_heads + h) * p.T + t) * p.d_k + d;
+                (which == 0 ? p.q_hi : p.k_hi)[o] = hi;
+                (which == 0 ? p.q_lo : p.k_lo)[o] = lo;
+            } else {
+                const size_t o = (((size_t)seg * p.n_heads + h) * p.d_k + d) * p.Tp + t;
+                p.vt_hi[o] = hi;
+                p.vt_lo[o] = lo;
+            }
+            break;
+        }
+        case EPI_PV: {
+            const int seg = b / p.n_heads, h = b - seg * p.n_heads;
+            float hi, lo;
+            split_tf32(v, hi, lo);
+            const size_t o = ((size_t)seg * p.T + m) * p.ldo + (size_t)h * p.d_k + n;
+            p.out0[o] = hi;
+            p.out1[o] = lo;
+            break;
+        }
+        case EPI_MASK: {
+            const int seg = m / p.T, t = m - seg * p.T;
+            const int k = n / kBins, f = n - k * kBins;
+            const int n_masks = p.n_valid / kBins;
+            // torch.sigmoid(m), conformer.py:304
+            p.out0[(((size_t)seg * n_masks + k) * kBins + f) * p.T + t] = 1.f / (1.f + expf(-v));
+            break;
+        }
+        default: break;
+    }
+}
+
+int gemm_simt_launch(const GemmParams& p, cudaStream_t stream);
+// n_terms: 3 -> 3xTF32, 1 -> single TF32 pass
+int gemm_tc_launch(const GemmParams& p, int n_terms, cudaStream_t stream);
+
+inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {
+    if (engine == NSF_GEMM_SIMT_FP32) return gemm_simt_launch(p, stream);
+    return gemm_tc_launch(p, engine == NSF_GEMM_TC_3XTF32 ? 3 : 1, stream);
+}
+
+}  // namespace nsf

@@ -1,0 +1,313 @@
+// Stitching of the per-segment results: PIT costs, weighted overlap-add, activity gate, PCM16.
+// All HBM-bound streaming kernels.
+//
+// Reference: css/css.py:254-312 (stage II/III of separate_and_stitch), css/training/losses.py:50-106
+// (PitWrapper cost matrix), utils/numpy_utils.py:4-13 (dilate / erode), utils/audio_utils.py:44-49.
+#include "common.cuh"
+
+namespace nsf {
+
+constexpr int kMaxSpk = 4;
+
+// ------------------------------------------------------------------------------------------- PIT cost
+// cost[i][a][b] = mean_{f, t < ov} loss(left_a[f][T-ov+t], right_b[f][t]); left = segment i-1, right = segment i.
+template <int INPUT_KIND, int LOSS_KIND>
+__global__ void __launch_bounds__(256)
+pit_cost_kernel(const void* __restrict__ in, int n_ch_total, int n_spk, int n_bins, int T, int ov, float* __restrict__ cost) {
+    const int i = blockIdx.x;          // segment index, >= 1 does work
+    __shared__ double red[8][kMaxSpk * kMaxSpk];
+    double acc[kMaxSpk][kMaxSpk];
+#pragma unroll
+    for (int a = 0; a < kMaxSpk; ++a)
+#pragma unroll
+        for (int b = 0; b < kMaxSpk; ++b) acc[a][b] = 0.0;
+    if (i >= 1) {
+        const size_t seg_stride = (size_t)n_ch_total * n_bins * T;
+        const size_t ch_stride = (size_t)n_bins * T;
+        const int n = n_bins * ov;
+        for (int e = threadIdx.x; e < n; e += blockDim.x) {
+            const int f = e / ov, t = e - f * ov;
+            float l[kMaxSpk], r[kMaxSpk];
+#pragma unroll
+            for (int a = 0; a < kMaxSpk; ++a) {
+                l[a] = 0.f; r[a] = 0.f;
+                if (a < n_spk) {
+                    const size_t il = (size_t)(i - 1) * seg_stride + a * ch_stride + (size_t)f * T + (T - ov + t);
+                    const size_t ir = (size_t)i * seg_stride + a * ch_stride + (size_t)f * T + t;
+                    if (INPUT_KIND == 0) {
+                        l[a] = __ldg(reinterpret_cast<const float*>(in) + il);
+                        r[a] = __ldg(reinterpret_cast<const float*>(in) + ir);
+                    } else {
+                        const float2 zl = __ldg(reinterpret_cast<const float2*>(in) + il);
+                        const float2 zr = __ldg(reinterpret_cast<const float2*>(in) + ir);
+                        l[a] = sqrtf(zl.x * zl.x + zl.y * zl.y);
+                        r[a] = sqrtf(zr.x * zr.x + zr.y * zr.y);
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < kMaxSpk; ++a)
+#pragma unroll
+                for (int b = 0; b < kMaxSpk; ++b) {
+                    const float d = l[a] - r[b];
+                    acc[a][b] += (double)(LOSS_KIND == 0 ? fabsf(d) : d * d);
+                }
+        }
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int a = 0; a < kMaxSpk; ++a)
+#pragma unroll
+        for (int b = 0; b < kMaxSpk; ++b) {
+            const double v = warp_sum(acc[a][b]);
+            if (lane == 0) red[warp][a * kMaxSpk + b] = v;
+        }
+    __syncthreads();
+    if (threadIdx.x < n_spk * n_spk) {
+        const int a = threadIdx.x / n_spk, b = threadIdx.x % n_spk;
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += red[w][a * kMaxSpk + b];
+        cost[((size_t)i * n_spk + a) * n_spk + b] = (i >= 1) ? (float)(v / ((double)n_bins * ov)) : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------- mask WOLA
+// mask_st[f][t][k] = (sum_i w_i[t - i hop] * m_i[perm_i[k]][f][t - i hop]) / wsum[t], i ascending as css.py:266-295.
+__global__ void __launch_bounds__(256)
+stitch_masks_kernel(const float* __restrict__ masks, int n_ch_total, const int32_t* __restrict__ perms,
+                    const float* __restrict__ seg_w, const float* __restrict__ wsum, int n_seg, int n_spk, int n_bins,
+                    int T, int hop, int64_t T_long, float* __restrict__ mask_st) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int f = blockIdx.y;
+    if (t >= T_long) return;
+    int64_t i_min = (t - T + 1 + hop - 1) / hop;      // ceil((t-T+1)/hop) for positive numerator
+    if (t - T + 1 <= 0) i_min = 0;
+    int64_t i_max = t / hop;
+    if (i_max > n_seg - 1) i_max = n_seg - 1;
+    float acc[kMaxSpk] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = i_min; i <= i_max; ++i) {
+        const int tl = (int)(t - i * hop);
+        const float w = __ldg(seg_w + i * T + tl);
+        const float* mi = masks + ((size_t)i * n_ch_total * n_bins + f) * T + tl;
+#pragma unroll
+        for (int k = 0; k < kMaxSpk; ++k)
+            if (k < n_spk) {
+                const int src = __ldg(perms + i * n_spk + k);
+                const float m = __ldg(mi + (size_t)src * n_bins * T);
+                acc[k] = __fadd_rn(acc[k], __fmul_rn(w, m));        // separate multiply and add, like the reference
+            }
+    }
+    const float ws = __ldg(wsum + t);
+    float* o = mask_st + ((size_t)f * T_long + t) * n_spk;
+#pragma unroll
+    for (int k = 0; k < kMaxSpk; ++k)
+        if (k < n_spk) o[k] = acc[k] / ws;
+}
+
+// activity[t][k] = mean_f mask_st[f][t][k]   (css.py:304)
+__global__ void __launch_bounds__(256)
+activity_mean_kernel(const float* __restrict__ mask_st, int n_bins, int64_t n_tk, float* __restrict__ activity) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // t * n_spk + k
+    if (j >= n_tk) return;
+    double s = 0.0;
+    for (int f = 0; f < n_bins; ++f) s += (double)__ldg(mask_st + (size_t)f * n_tk + j);
+    activity[j] = (float)(s / n_bins);
+}
+
+// ------------------------------------------------------------------------------------------- activity gate
+// act_b = activity >= th ; tmp = dilate(act_b, dil) (zero padding)
+__global__ void __launch_bounds__(256)
+activity_threshold_dilate_kernel(const float* __restrict__ activity, int64_t T_long, int n_spk, float th, int dil,
+                                 uint8_t* __restrict__ act_b, uint8_t* __restrict__ tmp) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= T_long * n_spk) return;
+    const int64_t t = j / n_spk;
+    const int k = (int)(j - t * n_spk);
+    act_b[j] = __ldg(activity + j) >= th;
+    int64_t lo = t - dil, hi = t + dil;
+    if (lo < 0) lo = 0;
+    if (hi > T_long - 1) hi = T_long - 1;
+    uint8_t any = 0;
+    for (int64_t u = lo; u <= hi; ++u) any |= (uint8_t)(__ldg(activity + u * n_spk + k) >= th);
+    tmp[j] = any;
+}
+// act_final = erode(tmp, ero) (one padding)
+__global__ void __launch_bounds__(256)
+activity_erode_kernel(const uint8_t* __restrict__ tmp, int64_t T_long, int n_spk, int ero, uint8_t* __restrict__ act_final) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= T_long * n_spk) return;
+    const int64_t t = j / n_spk;
+    const int k = (int)(j - t * n_spk);
+    int64_t lo = t - ero, hi = t + ero;
+    if (lo < 0) lo = 0;
+    if (hi > T_long - 1) hi = T_long - 1;
+    uint8_t all = 1;
+    for (int64_t u = lo; u <= hi; ++u) all &= tmp[u * n_spk + k];
+    act_final[j] = all;
+}
+
+// ------------------------------------------------------------------------------------------- STFT WOLA
+// S_st[k][t][f] = gate[t][k] * (sum_i w_i Y_i[perm_i[k]][f][t - i hop]) / wsum[t]; tile-transposed through smem so
+// that both the reads (t contiguous) and the writes (f contiguous) are coalesced.
+__global__ void __launch_bounds__(256)
+stitch_stft_kernel(const float2* __restrict__ Y, const int32_t* __restrict__ perms, const float* __restrict__ seg_w,
+                   const float* __restrict__ wsum, const uint8_t* __restrict__ act_final, int n_seg, int n_spk,
+                   int n_bins, int T, int hop, int64_t T_long, float2* __restrict__ S_st) {
+    __shared__ float2 tile[kMaxSpk][32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int f0 = blockIdx.y * 32;
+    {
+        const int64_t t = t0 + tx;
+        if (t < T_long) {
+            int64_t i_min = (t - T + 1 <= 0) ? 0 : (t - T + 1 + hop - 1) / hop;
+            int64_t i_max = t / hop;
+            if (i_max > n_seg - 1) i_max = n_seg - 1;
+            const float ws = __ldg(wsum + t);
+            for (int fy = ty; fy < 32; fy += 8) {
+                const int f = f0 + fy;
+                if (f >= n_bins) break;
+                float2 acc[kMaxSpk];
+#pragma unroll
+                for (int k = 0; k < kMaxSpk; ++k) acc[k] = make_float2(0.f, 0.f);
+                for (int64_t i = i_min; i <= i_max; ++i) {
+                    const int tl = (int)(t - i * hop);
+                    const float w = __ldg(seg_w + i * T + tl);
+#pragma unroll
+                    for (int k = 0; k < kMaxSpk; ++k)
+                        if (k < n_spk) {
+                            const int src = __ldg(perms + i * n_spk + k);
+                            const float2 y = __ldg(Y + (((size_t)i * n_spk + src) * n_bins + f) * T + tl);
+                            acc[k].x = __fadd_rn(acc[k].x, __fmul_rn(w, y.x));
+                            acc[k].y = __fadd_rn(acc[k].y, __fmul_rn(w, y.y));
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < kMaxSpk; ++k)
+                    if (k < n_spk) {
+                        const bool on = act_final ? (__ldg(act_final + t * n_spk + k) != 0) : true;
+                        tile[k][fy][tx] = on ? make_float2(acc[k].x / ws, acc[k].y / ws) : make_float2(0.f, 0.f);
+                    }
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int f = f0 + tx;
+        if (f < n_bins) {
+            for (int tyy = ty; tyy < 32; tyy += 8) {
+                const int64_t t = t0 + tyy;
+                if (t >= T_long) break;
+#pragma unroll
+                for (int k = 0; k < kMaxSpk; ++k)
+                    if (k < n_spk) S_st[((size_t)k * T_long + t) * n_bins + f] = tile[k][tx][tyy];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- PCM16
+__global__ void __launch_bounds__(256)
+absmax_kernel(const float* __restrict__ wav, int64_t n, float* __restrict__ peak) {
+    const float* w = wav + (size_t)blockIdx.y * n;
+    float m = 0.f;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(__ldg(w + j)));
+    m = warp_max(m);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+        atomicMax(reinterpret_cast<unsigned int*>(peak + blockIdx.y), __float_as_uint(m));   // non-negative floats order as uints
+    }
+}
+__global__ void __launch_bounds__(256)
+pcm16_kernel(const float* __restrict__ wav, int64_t n, const float* __restrict__ peak, int16_t* __restrict__ pcm) {
+    const float* w = wav + (size_t)blockIdx.y * n;
+    int16_t* q = pcm + (size_t)blockIdx.y * n;
+    const float den = __fadd_rn(__ldg(peak + blockIdx.y), 1e-7f);            // np.max(np.abs(samps)) + 1e-7  (float32)
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        const float v = __fdiv_rn(__fmul_rn(__ldg(w + j), 0.99f), den);      // samps * 0.99 / (...)
+        int r = __float2int_rn(__fmul_rn(v, 32767.f));                       // libsndfile f2s: lrintf(x * 0x7FFF)
+        r = max(-32768, min(32767, r));
+        q[j] = (int16_t)r;
+    }
+}
+
+}  // namespace nsf
+
+using namespace nsf;
+
+extern "C" int nsf_pit_cost(const void* in, int input_kind, int loss_kind, int n_seg, int n_ch_total, int n_spk,
+                            int n_bins, int T, int overlap, float* cost, void* stream) {
+    NSF_REQUIRE(in && cost, "nsf_pit_cost: null pointer");
+    NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && n_ch_total >= n_spk, "nsf_pit_cost: n_spk=%d", n_spk);
+    NSF_REQUIRE(overlap >= 1 && overlap <= T, "nsf_pit_cost: overlap=%d T=%d", overlap, T);
+    NSF_REQUIRE((input_kind == 0 || input_kind == 1) && (loss_kind == 0 || loss_kind == 1), "nsf_pit_cost: bad kind");
+    if (n_seg <= 0) return NSF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (input_kind == 0 && loss_kind == 0) pit_cost_kernel<0, 0><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
+    else if (input_kind == 0) pit_cost_kernel<0, 1><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
+    else if (loss_kind == 0) pit_cost_kernel<1, 0><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
+    else pit_cost_kernel<1, 1><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
+    return check_launch("pit_cost_kernel");
+}
+
+extern "C" int nsf_stitch_masks(const float* masks, int n_ch_total, const int32_t* perms, const float* seg_w,
+                                const float* wsum, int n_seg, int n_spk, int n_bins, int T, int hop, int64_t T_long,
+                                float* mask_st, float* activity, void* stream) {
+    NSF_REQUIRE(masks && perms && seg_w && wsum && mask_st && activity, "nsf_stitch_masks: null pointer");
+    NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && n_ch_total >= n_spk && hop >= 1 && T >= 1, "nsf_stitch_masks: bad sizes");
+    if (T_long <= 0) return NSF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((unsigned)ceil_div64(T_long, 256), n_bins);
+    stitch_masks_kernel<<<grid, 256, 0, s>>>(masks, n_ch_total, perms, seg_w, wsum, n_seg, n_spk, n_bins, T, hop, T_long, mask_st);
+    int rc = check_launch("stitch_masks_kernel");
+    if (rc) return rc;
+    const int64_t n_tk = T_long * n_spk;
+    activity_mean_kernel<<<(unsigned)ceil_div64(n_tk, 256), 256, 0, s>>>(mask_st, n_bins, n_tk, activity);
+    return check_launch("activity_mean_kernel");
+}
+
+extern "C" int nsf_activity(const float* activity, int64_t T_long, int n_spk, float th, int dil, int ero,
+                            uint8_t* act_b, uint8_t* tmp, uint8_t* act_final, void* stream) {
+    NSF_REQUIRE(activity && act_b && tmp && act_final, "nsf_activity: null pointer");
+    NSF_REQUIRE(dil >= 0 && ero >= 0 && n_spk >= 1, "nsf_activity: bad sizes");
+    if (T_long <= 0) return NSF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t n = T_long * n_spk;
+    activity_threshold_dilate_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(activity, T_long, n_spk, th, dil, act_b, tmp);
+    int rc = check_launch("activity_threshold_dilate_kernel");
+    if (rc) return rc;
+    activity_erode_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(tmp, T_long, n_spk, ero, act_final);
+    return check_launch("activity_erode_kernel");
+}
+
+extern "C" int nsf_stitch_stft(const float* Y, const int32_t* perms, const float* seg_w, const float* wsum,
+                               const uint8_t* act_final, int n_seg, int n_spk, int n_bins, int T, int hop,
+                               int64_t T_long, float* S_st, void* stream) {
+    NSF_REQUIRE(Y && perms && seg_w && wsum && S_st, "nsf_stitch_stft: null pointer");
+    NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && hop >= 1 && T >= 1, "nsf_stitch_stft: bad sizes");
+    if (T_long <= 0) return NSF_OK;
+    dim3 grid((unsigned)ceil_div64(T_long, 32), ceil_div(n_bins, 32));
+    stitch_stft_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(Y), perms, seg_w, wsum, act_final,
+                                                              n_seg, n_spk, n_bins, T, hop, T_long,
+                                                              reinterpret_cast<float2*>(S_st));
+    return check_launch("stitch_stft_kernel");
+}
+
+extern "C" int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, float* peak, int16_t* pcm, void* stream) {
+    NSF_REQUIRE(wav && peak && pcm, "nsf_peaknorm_pcm16: null pointer");
+    NSF_REQUIRE(n_streams >= 1 && n >= 0, "nsf_peaknorm_pcm16: bad sizes");
+    if (n == 0) return NSF_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    NSF_CUDA(cudaMemsetAsync(peak, 0, sizeof(float) * n_streams, s));
+    int bx = (int)min((int64_t)148 * 4, ceil_div64(n, 256));
+    dim3 grid(bx, n_streams);
+    absmax_kernel<<<grid, 256, 0, s>>>(wav, n, peak);
+    int rc = check_launch("absmax_kernel");
+    if (rc) return rc;
+    pcm16_kernel<<<grid, 256, 0, s>>>(wav, n, peak, pcm);
+    return check_launch("pcm16_kernel");
+}

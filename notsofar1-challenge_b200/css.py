@@ -1,0 +1,371 @@
+"""Drop-in replacement for the reference's CSS plug-in (css/css.py): same names, same signatures,
+same outputs -- ``CssCfg``, ``css_inference``, ``separate_and_stitch``, ``calc_segment_weight`` --
+with every stage running on a B200 through libnsf_b200.so.
+
+Reference flow (css/css.py:110-338) vs this module
+  * STFT of the whole meeting on the CPU (:155)             -> one STFT kernel, X stays in HBM
+  * per 3-s segment: H2D, Conformer, D2H, NumPy MVDR, H2D, D2H (:182-250, 4 PCIe crossings/segment)
+                                                             -> segments are the batch dimension; features,
+                                                                mask network and MVDR run per chunk of
+                                                                ``segments_per_batch`` segments, nothing leaves HBM
+  * sequential PIT alignment + overlap-add on the CPU (:266-299)
+                                                             -> all 3x3 costs in one kernel, the 6-permutation
+                                                                chain on the host (3 ints per segment), then one
+                                                                gather-style overlap-add kernel (no atomics)
+  * activity gate with NumPy morphology (:303-312)          -> threshold / dilate / erode kernels
+  * iSTFT on the CPU (:316-319)                              -> iSTFT kernel; only the 3 waveforms cross PCIe
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .separator import ConformerCssB200, NUM_BINS, FRAME_HOP, FRAME_LEN
+
+
+# CSS inference configuration -- field for field the reference's CssCfg (css/css.py:24-48)
+@dataclass
+class CssCfg:
+    segment_size_sec: float = 3.  # in seconds
+    hop_size_sec: float = 1.5     # in seconds
+    normalize_segment_power: bool = False
+    stitching_loss: str = 'l1'  # loss function for stitching adjacent segments ('l1' or 'mse')
+    stitching_input: str = 'mask'  # type of input for stitching loss ('mask' or 'separation_result')
+    seg_weight_m0_sec: float = 0.15  # see calc_segment_weight
+    seg_weight_m1_sec: float = 0.3
+    activity_th: float = 0.4  # threshold for segmentation mask
+    activity_dilation_sec: float = 0.4  # dilation and erosion for segmentation mask
+    activity_erosion_sec: float = 0.2
+    device: Optional[str] = None
+    show_progressbar: bool = True
+    # segment-wise single-channel model
+    checkpoint_sc: str = 'notsofar/conformer1.0/sc'
+    # segment-wise multi-channel model
+    checkpoint_mc: str = 'notsofar/conformer1.0/mc'
+    device_id: int = 0
+    num_spks: int = 3  # the number of streams the separation models outputs
+    mc_mvdr: bool = True  # if True, applies MVDR to the multi-channel input
+    mc_mask_floor_db: float = 0.  # mask floor in db. -inf means no floor. 0 means mask has no effect
+    sc_mask_floor_db: float = -np.inf
+    pass_through_ch0: bool = False  # if True, simply returns the first channel of the input and skips CSS
+    slice_audio_for_debug: bool = False  # if True, only processes 10 seconds of the input audio
+
+
+@dataclass
+class SegmentPlan:
+    """Integer frame bookkeeping of css.py:141-169 (bit-exact by construction: same int() truncations)."""
+    segment_frames: int
+    hop_frames: int
+    m0_frames: int
+    m1_frames: int
+    dilation_frames: int
+    erosion_frames: int
+    raw_frames: int      # STFT frames of the signal
+    mix_frames: int      # after zero-padding inputs shorter than one segment (css.py:159-164)
+    num_segments: int
+
+    @property
+    def overlap_frames(self) -> int:
+        return self.segment_frames - self.hop_frames
+
+
+def _num_frames(n_samples: int) -> int:
+    return 0 if n_samples < FRAME_LEN else (n_samples - FRAME_LEN) // FRAME_HOP + 1
+
+
+def plan_segments(n_samples: int, fs: int, cfg: CssCfg) -> SegmentPlan:
+    seg = _num_frames(int(cfg.segment_size_sec * fs))        # dummy 3-s STFT of css.py:142-144
+    hop = int(seg * cfg.hop_size_sec / cfg.segment_size_sec)
+    m0 = int(seg * cfg.seg_weight_m0_sec / cfg.segment_size_sec)
+    m1 = int(seg * cfg.seg_weight_m1_sec / cfg.segment_size_sec)
+    dil = int(seg * cfg.activity_dilation_sec / cfg.segment_size_sec)
+    ero = int(seg * cfg.activity_erosion_sec / cfg.segment_size_sec)
+    raw = _num_frames(n_samples)
+    mix = max(raw, seg)
+    nseg = int(np.ceil((mix - (seg - hop)) / hop))
+    return SegmentPlan(seg, hop, m0, m1, dil, ero, raw, mix, nseg)
+
+
+def calc_segment_weight(seg_frames: int, m0_frames: int, m1_frames: int,
+                        is_first_seg: bool = False, is_last_seg: bool = False):
+    """Trapezoid weights of css.py:341-390 (0 on [0, m0), linear 0.1 -> 1 on [m0, m1), 1 in the middle,
+    mirrored on the right; the outer edge of the first / last segment is 0.1).  Returns a float32
+    torch tensor like the reference."""
+    assert seg_frames > 2 * m1_frames, \
+        'not enough frames to fit weighting window. try modifying hop_size, segment_size or m0, m1'
+    wg_win = torch.ones(seg_frames, dtype=torch.float32)
+    wg_win[:m0_frames] = 0
+    wg_win[len(wg_win) - m0_frames:] = 0
+    linear = torch.linspace(0.1, 1, m1_frames - m0_frames)
+    wg_win[m0_frames:m1_frames] = linear
+    wg_win[-m1_frames:-m0_frames] = torch.flip(linear, (0,))
+    if is_first_seg:
+        wg_win[:m0_frames] = 0.1
+    if is_last_seg:
+        wg_win[len(wg_win) - m0_frames:] = 0.1
+    return wg_win
+
+
+def permutation_chain(costs: np.ndarray) -> np.ndarray:
+    """Sequential alignment of css.py:266-285 from the pairwise costs of the *unpermuted* segments.
+
+    costs[i][a][b] = loss(left channel a of segment i-1, right channel b of segment i) on the original
+    channel order.  The reference aligns segment i against the already permuted segment i-1, i.e. it sees
+    rows perm[i-1] of costs[i]; the optimal assignment of a 3x3 (<= 4x4) matrix is found by enumerating
+    the permutations (== scipy's Hungarian answer away from exact ties).  Returns perms [n_seg, S] with
+    new channel k of segment i <- old channel perms[i][k].
+    """
+    n_seg, S, _ = costs.shape
+    perms = np.tile(np.arange(S, dtype=np.int32), (n_seg, 1))
+    cand = list(itertools.permutations(range(S)))
+    for i in range(1, n_seg):
+        c = costs[i][perms[i - 1]]                       # rows follow the permuted left segment
+        best, best_p = None, None
+        for p in cand:
+            v = 0.0
+            for a in range(S):
+                v += float(c[a, p[a]])
+            if best is None or v < best:
+                best, best_p = v, p
+        perms[i] = best_p
+    return perms
+
+
+def _segment_weights(plan: SegmentPlan):
+    """seg_w [n_seg, T] and its overlap-added sum wg_stitched [mix_frames] exactly as css.py:258-259,288-291
+    accumulate them (float32, ascending segment order)."""
+    T, n = plan.segment_frames, plan.num_segments
+    first = calc_segment_weight(T, plan.m0_frames, plan.m1_frames, is_first_seg=True).numpy()
+    mid = calc_segment_weight(T, plan.m0_frames, plan.m1_frames).numpy()
+    last = calc_segment_weight(T, plan.m0_frames, plan.m1_frames, is_last_seg=True).numpy()
+    seg_w = np.empty((n, T), np.float32)
+    wsum = np.zeros(plan.mix_frames, np.float32)
+    for i in range(n):
+        w = first if i == 0 else (last if i == n - 1 else mid)
+        seg_w[i] = w
+        st = i * plan.hop_frames
+        en = min(st + T, plan.mix_frames)
+        wsum[st:en] += w[:en - st]
+    return seg_w, wsum
+
+
+@torch.no_grad()
+def separate_and_stitch(speech_mix: np.ndarray, separator: ConformerCssB200, fs: int,
+                        device: torch.device, cfg: CssCfg, return_side_info: bool = True,
+                        seg_range: Optional[range] = None, _stages: Optional[dict] = None) -> (List[np.ndarray], Dict):
+    """Block-online CSS of a long-form recording: same contract as the reference's
+    separate_and_stitch (css/css.py:110-338).
+
+    Args:
+        speech_mix: [Batch=1, Nsamples, Channels] float32 (numpy, or a torch tensor already on the device).
+        separator: ConformerCssB200 (the B200 re-hosting of the reference's ConformerCssWrapper).
+        fs: sample rate.  device: CUDA device.  cfg: CssCfg.
+    Returns:
+        separated_wavs: list of num_spks float32 arrays [(T_long-1)*256+512];
+        side_info: {'mask_stitched' [1,F,T_long,S] float32, 'activity_b' [T_long,S] bool,
+                    'activity_final' [1,T_long,S] bool, 'segment_frames' int} (CPU torch tensors, like the reference).
+    """
+    assert speech_mix.ndim == 3, f'expecting 3 dimensions, got {speech_mix.shape}'
+    batch_size, n_samples, num_channels = speech_mix.shape
+    assert batch_size == 1, 'assuming 1 example in batch. easy to support more.'
+    if not isinstance(separator, ConformerCssB200):
+        raise TypeError("notsofar_b200.separate_and_stitch drives the fused B200 path and needs a ConformerCssB200 "
+                        "separator (build one with ConformerCssB200(reference_state_dict) or load_css_model)")
+    assert not separator.training
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _cabi.NsfError("notsofar_b200 has no CPU path: pass a CUDA device")
+    lib = _cabi.load()
+    separator.to(device)
+    if num_channels == 1 or not cfg.mc_mvdr:
+        raise NotImplementedError("single-channel / mask-only CSS is not built yet (SURVEY 8f-4); use mc_mvdr=True with 7 mics")
+    if cfg.normalize_segment_power:
+        raise NotImplementedError("normalize_segment_power=True is not built yet")
+    assert cfg.stitching_loss in ('l1', 'mse'), f'unexpected stitching_loss: {cfg.stitching_loss}'
+    assert cfg.stitching_input in ('mask', 'separation_result'), f'unexpected stitching_input: {cfg.stitching_input}'
+
+    plan = plan_segments(n_samples, fs, cfg)
+    T, hop, S = plan.segment_frames, plan.hop_frames, cfg.num_spks
+    assert S == separator.num_spks
+    mix_frames, n_seg = plan.mix_frames, plan.num_segments
+    mask_floor_db = cfg.mc_mask_floor_db if num_channels > 1 else cfg.sc_mask_floor_db
+    assert mask_floor_db <= 0
+    mask_floor = 10. ** (mask_floor_db / 20.)
+
+    with torch.cuda.device(device):
+        sp = _cabi.stream_ptr
+        # H2D of the raw audio (the only input crossing), then the long-form STFT
+        if isinstance(speech_mix, torch.Tensor):
+            x = speech_mix[0].to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        else:
+            x = torch.from_numpy(np.ascontiguousarray(speech_mix[0], dtype=np.float32)).to(device, non_blocking=True)
+        X = separator.stft_device(x, T_alloc=mix_frames)                       # [F, mix_frames, C]
+        T_valid = plan.raw_frames
+
+        # I. masks + MVDR per chunk of segments
+        n_masks = separator.num_masks
+        masks = torch.empty((n_seg, n_masks, NUM_BINS, T), dtype=torch.float32, device=device)
+        Y = torch.empty((n_seg, S, NUM_BINS, T), dtype=torch.complex64, device=device)
+        B = max(1, int(separator.segments_per_batch))
+        for s0 in range(0, n_seg, B):
+            nb = min(B, n_seg - s0)
+            separator.masks(X, T_valid, s0, nb, T, hop, out=masks[s0:s0 + nb])
+            separator.mvdr(masks[s0:s0 + nb], X, T_valid, s0, hop, mask_floor, out=Y[s0:s0 + nb])
+
+        # II. permutation chain + weighted overlap-add
+        costs = torch.empty((n_seg, S, S), dtype=torch.float32, device=device)
+        in_kind = 0 if cfg.stitching_input == 'mask' else 1
+        loss_kind = 0 if cfg.stitching_loss == 'l1' else 1
+        src = masks if in_kind == 0 else Y
+        _cabi.check(lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_seg, n_masks if in_kind == 0 else S, S, NUM_BINS, T,
+                                     plan.overlap_frames, _cabi.ptr(costs), sp()), "nsf_pit_cost")
+        perms_np = permutation_chain(costs.cpu().numpy())
+        seg_w_np, wsum_np = _segment_weights(plan)
+        assert (wsum_np > 1e-5).all(), 'zero weights found. check hop_size, segment_size or m0, m1'
+        perms = torch.from_numpy(perms_np).to(device)
+        seg_w = torch.from_numpy(seg_w_np).to(device)
+        wsum = torch.from_numpy(wsum_np).to(device)
+        mask_st = torch.empty((NUM_BINS, mix_frames, S), dtype=torch.float32, device=device)
+        activity = torch.empty((mix_frames, S), dtype=torch.float32, device=device)
+        _cabi.check(lib.nsf_stitch_masks(_cabi.ptr(masks), n_masks, _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), n_seg, S,
+                                         NUM_BINS, T, hop, mix_frames, _cabi.ptr(mask_st), _cabi.ptr(activity), sp()),
+                    "nsf_stitch_masks")
+        # III. activity gate
+        act_b = torch.empty((mix_frames, S), dtype=torch.uint8, device=device)
+        act_tmp = torch.empty_like(act_b)
+        act_final = torch.empty_like(act_b)
+        _cabi.check(lib.nsf_activity(_cabi.ptr(activity), mix_frames, S, float(np.float32(cfg.activity_th)), plan.dilation_frames,
+                                     plan.erosion_frames, _cabi.ptr(act_b), _cabi.ptr(act_tmp), _cabi.ptr(act_final), sp()),
+                    "nsf_activity")
+        S_st = torch.empty((S, mix_frames, NUM_BINS), dtype=torch.complex64, device=device)
+        _cabi.check(lib.nsf_stitch_stft(_cabi.ptr(Y), _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), _cabi.ptr(act_final),
+                                        n_seg, S, NUM_BINS, T, hop, mix_frames, _cabi.ptr(S_st), sp()), "nsf_stitch_stft")
+        wav = separator.istft_device(S_st)                                      # [S, N']
+        separated = wav.cpu().numpy()
+        separated_wavs = [separated[k] for k in range(S)]
+
+        side_info = {'segment_frames': T}
+        if return_side_info:
+            side_info.update({
+                'mask_stitched': mask_st.cpu().unsqueeze(0),                    # [1, F, T_long, S]
+                'activity_b': act_b.cpu().bool(),                               # [T_long, S]
+                'activity_final': act_final.cpu().bool().unsqueeze(0),          # [1, T_long, S]
+            })
+        if _stages is not None:
+            _stages.update(X=X, masks=masks, Y=Y, costs=costs, perms=perms_np, S_st=S_st, activity=activity, wav=wav, plan=plan)
+    return separated_wavs, side_info
+
+
+def load_css_model(model_dir: Path, device: Optional[torch.device] = None, **kw) -> (ConformerCssB200, dict):
+    """Counterpart of css/helpers.py:14-37: one ``*.pt`` (``checkpoint['model']`` with the DDP ``module.``
+    prefix) and one ``*.yaml`` (the TrainCfg; only read back for the caller) in ``model_dir``."""
+    import yaml
+
+    def fetch_one_file(path: Path, suffix: str):
+        files = list(Path(path).glob(suffix))
+        if len(files) == 0:
+            raise FileNotFoundError(f'expecting at least one {suffix} file in {path}')
+        assert len(files) == 1, f'expecting exactly one {suffix} file in {path}'
+        return str(files[0])
+
+    yaml_path = fetch_one_file(model_dir, '*.yaml')
+    checkpoint_path = fetch_one_file(model_dir, '*.pt')
+    with open(yaml_path) as f:
+        train_cfg = yaml.safe_load(f)
+    checkpoint = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
+    state = {k[len("module."):]: v for k, v in checkpoint["model"].items() if k.startswith("module.")}
+    return ConformerCssB200(state, device=device, **kw), train_cfg
+
+
+def load_audio(wav_file_names: List, is_mc: bool) -> (np.ndarray, int):
+    """css/helpers.py:40-65: 7 mono wav files (MC) or one (SC) -> [1, n_samples, n_channels] float32."""
+    import scipy.io.wavfile as wf
+
+    def read(fname):
+        sr, data = wf.read(str(fname))
+        if data.dtype == np.int16:
+            data = data.astype(np.float32) / np.float32(32768.0)       # libsndfile's int16 -> float32 scaling
+        elif data.dtype == np.int32:
+            data = (data.astype(np.float64) / 2147483648.0).astype(np.float32)
+        else:
+            data = data.astype(np.float32)
+        return data, sr
+
+    if is_mc:
+        assert len(wav_file_names) == 7, 'expecting 7 microphones'
+        audio_data, srs = zip(*[read(f) for f in wav_file_names])
+        mix_wav = np.stack(audio_data, axis=-1)[np.newaxis, ...]
+        assert mix_wav.ndim == 3 and mix_wav.shape[2] in (1, 7)
+        sr = srs[0]
+    else:
+        assert len(wav_file_names) == 1
+        mix_wav, sr = read(wav_file_names[0])
+        assert mix_wav.ndim == 1
+        mix_wav = mix_wav[np.newaxis, :, np.newaxis]
+    return mix_wav, sr
+
+
+def write_wav(fname, samps: np.ndarray, sr: int = 16000, max_norm: bool = True):
+    """utils/audio_utils.py:37-49: peak-normalise to 0.99 and write PCM_16 (libsndfile's float -> short
+    conversion is lrintf(x * 0x7FFF))."""
+    import os
+    import scipy.io.wavfile as wf
+    assert samps.ndim == 1
+    if max_norm:
+        samps = samps * 0.99 / (np.max(np.abs(samps)) + 1e-7)
+    os.makedirs(os.path.dirname(str(fname)), exist_ok=True)
+    pcm = np.clip(np.rint(samps.astype(np.float32) * np.float32(32767.0)), -32768, 32767).astype(np.int16)
+    wf.write(str(fname), sr, pcm)
+
+
+_MODEL_CACHE: Dict[str, ConformerCssB200] = {}
+
+
+def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_from_cache: bool):
+    """Applies CSS to one session -- same signature, file layout and cache semantics as the reference's
+    css_inference (css/css.py:51-107).  Returns a copy of ``session`` with 'sep_wav_file_names'."""
+    session_css = session.copy()
+
+    assert isinstance(session.wav_file_names, list)
+    if cfg.pass_through_ch0:
+        session_css['sep_wav_file_names'] = session.wav_file_names[0:1]
+        return session_css
+
+    css_out_dir = Path(out_dir) / "css_inference" / session.session_id
+    if fetch_from_cache and css_out_dir.exists():
+        sep_wav_file_names = sorted(css_out_dir.glob('sep*.wav'))
+        session_css['sep_wav_file_names'] = sep_wav_file_names
+        return session_css
+
+    if not torch.cuda.is_available():
+        raise _cabi.NsfError("notsofar_b200.css_inference needs a CUDA device (sm_100a); there is no CPU path")
+    device = torch.device('cuda', torch.cuda.current_device())
+    model_dir = str(Path(models_dir) / (cfg.checkpoint_mc if session.is_mc else cfg.checkpoint_sc))
+    # the reference re-loads the checkpoint for every session (css.py:85); the weights are kept resident here
+    if model_dir not in _MODEL_CACHE:
+        _MODEL_CACHE[model_dir] = load_css_model(Path(model_dir), device=device)[0]
+    separator = _MODEL_CACHE[model_dir]
+    separator.eval()
+    mixwav, sr = load_audio(session.wav_file_names, is_mc=session.is_mc)
+
+    if cfg.slice_audio_for_debug:
+        mixwav = mixwav[:, sr * 20:sr * 30, :]
+
+    separated_wavs, _ = separate_and_stitch(mixwav, separator, sr, device, cfg, return_side_info=False)
+
+    write_wav(css_out_dir / 'input_mixture.wav', samps=mixwav[0, :, 0], sr=sr)
+
+    sep_wav_file_names = []
+    for i, w in enumerate(separated_wavs):
+        filename = css_out_dir / f"sep_stream{i}.wav"
+        write_wav(filename, samps=w, sr=sr)
+        sep_wav_file_names.append(str(filename))
+
+    session_css['sep_wav_file_names'] = sep_wav_file_names
+    return session_css
