@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds per second (xRT) of the CSS + MVDR hot path on a synthetic 7-channel 16 kHz meeting.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--seconds 1800]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): continuous speech separation of a 30-minute 7-channel meeting -- multichannel
+STFT, 1 209 overlapping 3-s segments through the v1.0-MC Conformer mask network (d=512, 8 heads, 18 blocks, seeded
+random weights: no checkpoints offline) in fp32-parity (3xTF32) mode, fp64 mask-weighted MVDR, permutation-aligned
+overlap-add, activity gate, iSTFT.  One "step" = one pass of that path over the whole meeting.
+
+  value : audio-seconds / wall-second with the raw audio already resident in HBM (device-timed, CUDA events,
+          max over ranks).  N > 1: every rank separates its own meeting (sessions are independent by rule,
+          inference_pipeline/inference.py:58) -> weak scaling, no data-path collective.
+  e2e   : the same through the public API notsofar_b200.separate_and_stitch with HOST buffers -- H2D of the pinned
+          raw audio and D2H of the three separated waveforms inside the timed region.
+  roofline     : the dominant kernel class of the step (the tcgen05 GEMM), algorithmic flops / event-timed duration
+                 vs MEASURED_PEAKS.json; the other classes are listed in "kernels".
+  cpu_baseline : the numpy port of the reference's path (oracle/, same algorithm, all host cores) on a bounded slice.
+
+--impl reference times that CPU port alone (rank 0 only), same metric / unit / config.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 16000
+METRIC = "audio-sec/sec (xRT) CSS+MVDR 7-ch 16kHz"
+UNIT = "audio-s/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_burst=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    which="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, which="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi SM clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_meeting(seconds: float, seed: int):
+    """5-minute seeded pattern (notsofar_b200.synth.synthetic_meeting) tiled to the requested length."""
+    from notsofar_b200 import synth
+    n = int(round(seconds * FS))
+    base_s = min(seconds, 300.0)
+    base = synth.synthetic_meeting(base_s, seed=seed)
+    reps = -(-n // len(base))
+    return np.tile(base, (reps, 1))[:n] if reps > 1 else base[:n]
+
+
+def cpu_port_xrt(x_slice: np.ndarray, weights, repeats: int = 1):
+    """Times the numpy port of the reference path on x_slice [n, 7]; returns (xRT, seconds of CPU work)."""
+    from oracle import css_oracle as O
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        O.separate_and_stitch(x_slice[None], weights, FS, O.OracleCfg(activity_th=0.3), dtype=np.float32)
+    dt = (time.perf_counter() - t0) / repeats
+    return len(x_slice) / FS / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (numpy port under oracle/) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from notsofar_b200 import synth
+    cores = os.cpu_count() or 1
+    sample_s = args.ref_seconds
+    x = make_meeting(sample_s, seed=0)
+    w = synth.random_state_dict(0)
+    from oracle import css_oracle as O
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        O.separate_and_stitch(x[None], w, FS, O.OracleCfg(activity_th=0.3), dtype=np.float32)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    val = sample_s / (ms / 1e3)
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": f"CSS Conformer v1.0-MC (random init) + MVDR, 7-ch 16 kHz, {sample_s:.0f}-s slice of the synthetic meeting per step",
+                       "segments_per_step": int(O.plan_segments(len(x), FS, O.OracleCfg()).num_segments)},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample_s:.0f} s of the synthetic 7-ch meeting per step, numpy/BLAS on all host threads"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import notsofar_b200 as N
+    from notsofar_b200 import synth, _cabi
+    from notsofar_b200.css import css_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+
+    seconds = args.seconds
+    x_np = make_meeting(seconds, seed=rank)                   # every rank its own meeting (sessions are independent)
+    n = len(x_np)
+    x_pinned = torch.from_numpy(x_np).pin_memory()
+    weights = synth.random_state_dict(0)
+    engine = {"3xtf32": N.GEMM_TC_3XTF32, "tf32": N.GEMM_TC_TF32, "simt": N.GEMM_SIMT_FP32}[args.engine]
+    sep = N.ConformerCssB200(weights, device=dev, gemm_engine=engine, segments_per_batch=args.segments_per_batch)
+    cfg = N.CssCfg(activity_th=0.3, show_progressbar=False)   # inference_v1.yaml:17
+    plan = N.plan_segments(n, FS, cfg)
+    x_dev = x_pinned.to(dev)
+    h2d_bytes = x_pinned.numel() * 4
+    n_out = (plan.mix_frames - 1) * 256 + 512
+    d2h_bytes = 3 * n_out * 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return css_device(x_dev, sep, FS, cfg)
+
+    def step_e2e():
+        return N.separate_and_stitch(x_pinned[None], sep, FS, dev, cfg, return_side_info=False)
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+
+    # ---- timed: device-resident input.  Inputs + intermediates (> 5 GB per step) far exceed the 126 MB L2.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.nsf_launch_count()
+    lib.nsf_prof_enable(1)
+    _cabi.prof_collect()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    prof = _cabi.prof_collect()
+    lib.nsf_prof_enable(0)
+    launches = (lib.nsf_launch_count() - launches0) // args.steps
+    clocks = sampler.stop()
+    del out
+
+    # ---- timed: end to end through the public API with host buffers
+    for _ in range(min(2, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        wavs, _ = step_e2e()
+    ev1.record()
+    barrier()
+    e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3) / args.steps
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = t.tolist()
+
+    if rank == 0:
+        peaks = _peaks()
+        value = world * seconds / (dev_ms / 1e3)
+        e2e_val = world * seconds / (e2e_ms / 1e3)
+        kernels = {}
+        for name, (ms, work, cnt) in prof.items():
+            if cnt == 0:
+                continue
+            per = {"ms_per_step": ms / args.steps, "brackets_per_step": cnt / args.steps}
+            if name.startswith("gemm"):
+                per.update(bound="tensor", achieved=work / (ms * 1e-3) / 1e12 if ms > 0 else None, unit="TFLOP/s")
+            elif name != "net_other":
+                per.update(bound="hbm", achieved=work / (ms * 1e-3) / 1e9 if ms > 0 else None, unit="GB/s")
+            kernels[name] = per
+        dom = max((k for k in kernels if "achieved" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+        d = kernels[dom]
+        if d["bound"] == "tensor":
+            # 3xTF32 issues three tf32 MMAs per algorithmic product; dense tf32 peak is half the bf16 peak.  The
+            # fraction is reported against the measured sustained bf16 GEMM peak (the only measured tensor number).
+            peak = peaks["bf16_sustained"]
+            note = f"algorithmic fp32 flops (3 tf32 passes count once) vs sustained bf16 cuBLAS peak, {peaks['which']}"
+        else:
+            peak = peaks["hbm_gbs"]
+            note = f"algorithmic bytes vs copy bandwidth, {peaks['which']}"
+        roofline = {"kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": peak, "unit": d["unit"],
+                    "frac": d["achieved"] / peak, "traffic": None, "share_of_step": d["ms_per_step"] / dev_ms, "note": note}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": {"3xtf32": "f32 (3xTF32 tensor-core GEMMs, fp64 MVDR)", "tf32": "tf32", "simt": "f32"}[args.engine],
+                "data": "synthetic (seeded 5-min 7-ch pattern tiled; random-init v1.0-MC weights)",
+                "config": {"workload": f"CSS Conformer v1.0-MC + MVDR, 7-ch 16 kHz, {seconds / 60:.0f}-min synthetic meeting per GPU "
+                                       f"({plan.num_segments} segments of 186 frames)",
+                           "segments_per_batch": args.segments_per_batch, "gemm_engine": args.engine,
+                           "parallelism": f"{world} independent meetings (one per GPU)",
+                           "l2": "inputs and intermediates exceed L2 (>5 GB touched per step)"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes + plan.num_segments * 36},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "kernels": kernels}
+        if world == 1 and not args.no_cpu_baseline:
+            sl = x_np[: int(args.cpu_seconds * FS)]
+            xrt, dt = cpu_port_xrt(sl, weights)
+            line["cpu_baseline"] = {"value": xrt, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"first {args.cpu_seconds:.0f} s of the same meeting ({dt:.1f} s of CPU work), numpy port of the "
+                                              f"reference path on all host threads; cost is linear in segments"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seconds", type=float, default=1800.0, help="meeting length per GPU")
+    ap.add_argument("--engine", default="3xtf32", choices=["3xtf32", "tf32", "simt"])
+    ap.add_argument("--segments-per-batch", type=int, default=128)
+    ap.add_argument("--cpu-seconds", type=float, default=30.0, help="slice of the meeting the CPU baseline leg runs")
+    ap.add_argument("--ref-seconds", type=float, default=15.0, help="--impl reference: audio seconds per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1 and args.gpus > 1 and args.impl == "b200":
+        # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29511", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,17 @@ extern "C" {
 
 const char* nsf_last_error(void);
 const char* nsf_version(void);
+/* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
+int64_t nsf_launch_count(void);
+
+/* Optional kernel-class profiler (bench.py's roofline): when enabled, every entry point brackets its launches
+ * with CUDA events on the launching stream.  nsf_prof_collect synchronises the device and returns, per class,
+ * the summed event time [ms], the summed algorithmic work (bytes for HBM-bound classes, flops for GEMMs) and
+ * the number of brackets since the previous collect. */
+int nsf_prof_enable(int on);
+int nsf_prof_num_classes(void);
+const char* nsf_prof_class_name(int cls);
+int nsf_prof_collect(double* ms /*host*/, double* work /*host*/, int64_t* count /*host*/, int n_classes);
 
 /* Number of STFT frames of an n_samples signal: conv1d stride 256, kernel 512, no padding
  * (css_with_conformer/executor/feature.py:105). */

@@ -25,6 +25,11 @@ class ConformerDims(C.Structure):
 SIGNATURES = {
     "nsf_last_error": (C.c_char_p, []),
     "nsf_version": (C.c_char_p, []),
+    "nsf_launch_count": (i64, []),
+    "nsf_prof_enable": (i32, [i32]),
+    "nsf_prof_num_classes": (i32, []),
+    "nsf_prof_class_name": (C.c_char_p, [i32]),
+    "nsf_prof_collect": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]),
     "nsf_num_frames": (i64, [i64]),
     "nsf_stft_mc": (i32, [c_f32p, i64, i32, c_f32p, i64, i64, C.c_void_p]),
     "nsf_css_features": (i32, [c_f32p, i64, i64, i32, i64, i32, i32, i32, c_f32p, c_f32p, c_f32p, c_f32p, i64, C.c_void_p]),
@@ -83,3 +88,12 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_collect():
+    """{class name: (ms, work, brackets)} since the previous collect (synchronises the device)."""
+    lib = load()
+    n = lib.nsf_prof_num_classes()
+    ms, work, cnt = (C.c_double * n)(), (C.c_double * n)(), (i64 * n)()
+    check(lib.nsf_prof_collect(ms, work, cnt, n), "nsf_prof_collect")
+    return {lib.nsf_prof_class_name(i).decode(): (ms[i], work[i], cnt[i]) for i in range(n)}

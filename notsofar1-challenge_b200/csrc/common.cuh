@@ -13,6 +13,7 @@ constexpr int kFrame = NSF_FRAME_LEN;   // 512
 constexpr int kHop = NSF_FRAME_HOP;     // 256
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
@@ -20,8 +21,25 @@ inline int check_launch(const char* what) {
         set_error("%s: %s", what, cudaGetErrorString(e));
         return NSF_ERR_CUDA;
     }
+    count_launch();
     return NSF_OK;
 }
+
+// Optional per-kernel-class timing with CUDA events on the launching stream (nsf_prof_* in the C ABI).
+// A ProfScope brackets the launches of one class; `work` is the algorithmic work of the bracket
+// (bytes for the HBM-bound classes, flops for the GEMM classes).
+enum ProfClass : int {
+    PROF_STFT = 0, PROF_FEATURES, PROF_GEMM_TC, PROF_GEMM_SIMT, PROF_NET_OTHER, PROF_MVDR, PROF_PIT, PROF_STITCH,
+    PROF_ACTIVITY, PROF_ISTFT, PROF_PCM16, PROF_NUM_CLASSES
+};
+bool prof_enabled();
+void prof_begin(int cls, double work, cudaStream_t stream);
+void prof_end(int cls, cudaStream_t stream);
+struct ProfScope {
+    int cls; cudaStream_t stream; bool on;
+    ProfScope(int c, double work, cudaStream_t s) : cls(c), stream(s), on(prof_enabled()) { if (on) prof_begin(cls, work, stream); }
+    ~ProfScope() { if (on) prof_end(cls, stream); }
+};
 
 #define NSF_REQUIRE(cond, ...)                                   \
     do {                                                         \

@@ -360,8 +360,9 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
     // embed: Linear -> LayerNorm -> ReLU (conformer.py:205-210), fused with layer 0's first LayerNorm
     rc = linear(feat, feat_lo, ldf, Kf, h->g(G_EMB_W_HI), h->g(G_EMB_W_LO), h->g(G_EMB_B), d, EPI_STORE, 1.f, w.x, nullptr, d);
     if (rc) return rc;
+    { ProfScope prof(PROF_NET_OTHER, 0.0, s);
     ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->g(G_EMB_LN_G), h->g(G_EMB_LN_B), 1, w.x, h->l(0, L_FFI_LN_G),
-                                     h->l(0, L_FFI_LN_B), w.h_hi, w.h_lo);
+                                     h->l(0, L_FFI_LN_B), w.h_hi, w.h_lo); }
     if ((rc = check_launch("ln_kernel(embed)"))) return rc;
 
     const float inv_sqrt_dk = 1.f / sqrtf((float)d_k);
@@ -374,8 +375,8 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                     w.x, nullptr, d);
         if (rc) return rc;
         // x += MHSA(x)                                                                         conformer.py:180
-        ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr,
-                                         w.h_hi, w.h_lo);
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr,
+                                         w.h_hi, w.h_lo); }
         if ((rc = check_launch("ln_kernel(attn)"))) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WQKV_HI), h->l(L, L_WQKV_LO), h->l(L, L_BQKV), 3 * d, EPI_QKV, 1.f, nullptr,
                     nullptr, 0);
@@ -397,7 +398,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
             p.epi = EPI_STORE; p.out0 = w.s2; p.ldo = ld2;
             if ((rc = gemm_launch(eng, p, s))) return rc;
         }
-        relpos_softmax_kernel<<<ceil_div(BH * T, 8), 256, 0, s>>>(w.s1, w.s2, BH * T, T, Tp, ld2, inv_sqrt_dk, w.p_hi, w.p_lo);
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s); relpos_softmax_kernel<<<ceil_div(BH * T, 8), 256, 0, s>>>(w.s1, w.s2, BH * T, T, Tp, ld2, inv_sqrt_dk, w.p_hi, w.p_lo); }
         if ((rc = check_launch("relpos_softmax_kernel"))) return rc;
         {   // o = p v per (segment, head), gathered back to [M, d_model]
             GemmParams p = base_params();
@@ -410,18 +411,18 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WO_HI), h->l(L, L_WO_LO), h->l(L, L_BO), d, EPI_RESID, 1.f, w.x, nullptr, d);
         if (rc) return rc;
         // x += Conv(x)                                                                         conformer.py:181
-        ln_glu_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), h->l(L, L_CONV_SCALARS), w.u_hi);
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_glu_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), h->l(L, L_CONV_SCALARS), w.u_hi); }
         if ((rc = check_launch("ln_glu_kernel"))) return rc;
         {
             dim3 grid(ceil_div(T, kDwTT), ceil_div(d, kDwCC), n_seg);
             const size_t smem = (size_t)(kDwTT + D.kernel_size - 1) * kDwCC * sizeof(float);
-            dwconv_kernel<<<grid, 256, smem, s>>>(w.u_hi, w.x, T, d, D.kernel_size, h->l(L, L_DW_W), h->l(L, L_BN_SCALE),
-                                                 h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS));
+            { ProfScope prof(PROF_NET_OTHER, 0.0, s); dwconv_kernel<<<grid, 256, smem, s>>>(w.u_hi, w.x, T, d, D.kernel_size, h->l(L, L_DW_W), h->l(L, L_BN_SCALE),
+                                                 h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS)); }
             if ((rc = check_launch("dwconv_kernel"))) return rc;
         }
         // x += 0.5 * FF_out(x)                                                                 conformer.py:182
-        ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr,
-                                         w.h_hi, w.h_lo);
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr,
+                                         w.h_hi, w.h_lo); }
         if ((rc = check_launch("ln_kernel(ff_out)"))) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_FFO_W1_HI), h->l(L, L_FFO_W1_LO), h->l(L, L_FFO_B1), dff, EPI_RELU_SPLIT,
                     1.f, w.u_hi, w.u_lo, dff);
@@ -431,9 +432,9 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         if (rc) return rc;
         // x = LN(x) (conformer.py:184), fused with the next block's first LayerNorm (or the split for the mask head)
         const bool last = (L == D.n_blocks - 1);
-        ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_OUT_LN_G), h->l(L, L_OUT_LN_B), 0, last ? nullptr : w.x,
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_OUT_LN_G), h->l(L, L_OUT_LN_B), 0, last ? nullptr : w.x,
                                          last ? nullptr : h->l(L + 1, L_FFI_LN_G), last ? nullptr : h->l(L + 1, L_FFI_LN_B),
-                                         w.h_hi, w.h_lo);
+                                         w.h_hi, w.h_lo); }
         if ((rc = check_launch("ln_kernel(out)"))) return rc;
     }
     // mask head: sigmoid(Linear), transposed into [seg][mask][F][T]                             conformer.py:302-309

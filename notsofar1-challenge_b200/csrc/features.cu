@@ -153,6 +153,7 @@ extern "C" int nsf_css_features(const float* X, int64_t T_long, int64_t T_valid,
     if (n_seg <= 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(ceil_div(kBins, kFeatBinsPerCta), n_seg);
+    ProfScope prof(PROF_FEATURES, (double)n_seg * T * kBins * n_ch * (8.0 + (feat_lo ? 8.0 : 4.0)), s);
     const size_t smem = (size_t)T * n_ch * kFeatBinsPerCta * sizeof(float);
     if (n_ch == 7) {
         NSF_CUDA(cudaFuncSetAttribute(css_features_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

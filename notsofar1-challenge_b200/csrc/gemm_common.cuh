@@ -100,6 +100,8 @@ int gemm_simt_launch(const GemmParams& p, cudaStream_t stream);
 int gemm_tc_launch(const GemmParams& p, int n_terms, cudaStream_t stream);
 
 inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {
+    // algorithmic flops: 2 M N K per batch entry (the three TF32 passes of 3xTF32 count once)
+    ProfScope prof(engine == NSF_GEMM_SIMT_FP32 ? PROF_GEMM_SIMT : PROF_GEMM_TC, 2.0 * p.M * p.N * p.K * p.batch, stream);
     if (engine == NSF_GEMM_SIMT_FP32) return gemm_simt_launch(p, stream);
     return gemm_tc_launch(p, engine == NSF_GEMM_TC_3XTF32 ? 3 : 1, stream);
 }

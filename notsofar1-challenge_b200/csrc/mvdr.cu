@@ -231,6 +231,8 @@ extern "C" int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float*
     }
     NSF_CUDA(cudaFuncSetAttribute(mvdr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(n_bins, kMvdrWarps), n_seg);
+    // algorithmic bytes: 7*8 mix + (S+Nn)*4 masks + S*8 out per (bin, frame)  (96 B for S = 3, Nn = 1)
+    ProfScope prof(PROF_MVDR, (double)n_seg * n_bins * T * (kMvdrC * 8.0 + (kMvdrS + n_noise) * 4.0 + kMvdrS * 8.0), (cudaStream_t)stream);
     mvdr_kernel<<<grid, kMvdrWarps * 32, smem, (cudaStream_t)stream>>>(masks, n_noise, reinterpret_cast<const float2*>(X), T_long,
                                                                       T_valid, seg_first, T, hop, n_bins, mask_floor,
                                                                       reinterpret_cast<float2*>(Y));

@@ -239,6 +239,7 @@ extern "C" int nsf_stft_mc(const float* x, int64_t n_samples, int n_ch, float* X
     const size_t smem = sizeof(StftSmem) + (size_t)kBins * kStftTT * n_ch * sizeof(float2);
     NSF_CUDA(cudaFuncSetAttribute(stft_mc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t grid = ceil_div64(n_frames, kStftTT);
+    ProfScope prof(PROF_STFT, (double)n_frames * n_ch * (kHop * 4.0 + kBins * 8.0), s);
     stft_mc_kernel<<<(unsigned)grid, kStftThreads, smem, s>>>(x, n_ch, reinterpret_cast<float2*>(X), T_long, n_frames);
     return check_launch("stft_mc_kernel");
 }
@@ -251,6 +252,7 @@ extern "C" int nsf_istft(const float* S_st, int n_streams, int64_t T_long, float
     if (rc) return rc;
     const int64_t n_out = (T_long - 1) * kHop + kFrame;
     dim3 grid((unsigned)ceil_div64(T_long + 1, kIstftTT), (unsigned)n_streams);
+    ProfScope prof(PROF_ISTFT, (double)T_long * n_streams * (kBins * 8.0 + kHop * 4.0), s);
     istft_kernel<<<grid, kIstftThreads, 0, s>>>(reinterpret_cast<const float2*>(S_st), T_long, wav, n_out);
     return check_launch("istft_kernel");
 }

@@ -247,6 +247,7 @@ extern "C" int nsf_pit_cost(const void* in, int input_kind, int loss_kind, int n
     NSF_REQUIRE((input_kind == 0 || input_kind == 1) && (loss_kind == 0 || loss_kind == 1), "nsf_pit_cost: bad kind");
     if (n_seg <= 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    ProfScope prof(PROF_PIT, (double)(n_seg - 1) * n_bins * overlap * 2.0 * n_spk * (input_kind == 0 ? 4.0 : 8.0), s);
     if (input_kind == 0 && loss_kind == 0) pit_cost_kernel<0, 0><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
     else if (input_kind == 0) pit_cost_kernel<0, 1><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
     else if (loss_kind == 0) pit_cost_kernel<1, 0><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
@@ -262,6 +263,8 @@ extern "C" int nsf_stitch_masks(const float* masks, int n_ch_total, const int32_
     if (T_long <= 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)ceil_div64(T_long, 256), n_bins);
+    const double contrib = (double)T / hop;      // segments contributing to one output frame
+    ProfScope prof(PROF_STITCH, (double)T_long * n_bins * n_spk * 4.0 * (contrib + 2.0), s);
     stitch_masks_kernel<<<grid, 256, 0, s>>>(masks, n_ch_total, perms, seg_w, wsum, n_seg, n_spk, n_bins, T, hop, T_long, mask_st);
     int rc = check_launch("stitch_masks_kernel");
     if (rc) return rc;
@@ -277,6 +280,7 @@ extern "C" int nsf_activity(const float* activity, int64_t T_long, int n_spk, fl
     if (T_long <= 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n = T_long * n_spk;
+    ProfScope prof(PROF_ACTIVITY, (double)n * 7.0, s);
     activity_threshold_dilate_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(activity, T_long, n_spk, th, dil, act_b, tmp);
     int rc = check_launch("activity_threshold_dilate_kernel");
     if (rc) return rc;
@@ -291,6 +295,7 @@ extern "C" int nsf_stitch_stft(const float* Y, const int32_t* perms, const float
     NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && hop >= 1 && T >= 1, "nsf_stitch_stft: bad sizes");
     if (T_long <= 0) return NSF_OK;
     dim3 grid((unsigned)ceil_div64(T_long, 32), ceil_div(n_bins, 32));
+    ProfScope prof(PROF_STITCH, (double)T_long * n_bins * n_spk * 8.0 * ((double)T / hop + 1.0), (cudaStream_t)stream);
     stitch_stft_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(Y), perms, seg_w, wsum, act_final,
                                                               n_seg, n_spk, n_bins, T, hop, T_long,
                                                               reinterpret_cast<float2*>(S_st));
@@ -303,6 +308,7 @@ extern "C" int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, fl
     if (n == 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     NSF_CUDA(cudaMemsetAsync(peak, 0, sizeof(float) * n_streams, s));
+    ProfScope prof(PROF_PCM16, (double)n * n_streams * 10.0, s);
     int bx = (int)min((int64_t)148 * 4, ceil_div64(n, 256));
     dim3 grid(bx, n_streams);
     absmax_kernel<<<grid, 256, 0, s>>>(wav, n, peak);

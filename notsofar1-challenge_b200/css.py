@@ -156,33 +156,19 @@ def _segment_weights(plan: SegmentPlan):
 
 
 @torch.no_grad()
-def separate_and_stitch(speech_mix: np.ndarray, separator: ConformerCssB200, fs: int,
-                        device: torch.device, cfg: CssCfg, return_side_info: bool = True,
-                        seg_range: Optional[range] = None, _stages: Optional[dict] = None) -> (List[np.ndarray], Dict):
-    """Block-online CSS of a long-form recording: same contract as the reference's
-    separate_and_stitch (css/css.py:110-338).
+def css_device(x: torch.Tensor, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_info: bool = True) -> Dict:
+    """The whole CSS path on tensors that already live in HBM.
 
-    Args:
-        speech_mix: [Batch=1, Nsamples, Channels] float32 (numpy, or a torch tensor already on the device).
-        separator: ConformerCssB200 (the B200 re-hosting of the reference's ConformerCssWrapper).
-        fs: sample rate.  device: CUDA device.  cfg: CssCfg.
-    Returns:
-        separated_wavs: list of num_spks float32 arrays [(T_long-1)*256+512];
-        side_info: {'mask_stitched' [1,F,T_long,S] float32, 'activity_b' [T_long,S] bool,
-                    'activity_final' [1,T_long,S] bool, 'segment_frames' int} (CPU torch tensors, like the reference).
+    x: [Nsamples, Channels] float32 on the CUDA device.  Returns a dict of device tensors:
+    'wav' [S, N'], 'mask_stitched' [F, T_long, S], 'activity' [T_long, S] float, 'activity_b' / 'activity_final'
+    [T_long, S] uint8, plus the per-segment 'masks' [n_seg, S+Nn, F, T], 'Y' [n_seg, S, F, T], 'X' [F, T_long, C],
+    'perms' (numpy [n_seg, S]) and 'plan'.  The only host round trip inside is the [n_seg, S, S] cost matrix of
+    the permutation chain (css.py:266-285), 36 bytes per segment.
     """
-    assert speech_mix.ndim == 3, f'expecting 3 dimensions, got {speech_mix.shape}'
-    batch_size, n_samples, num_channels = speech_mix.shape
-    assert batch_size == 1, 'assuming 1 example in batch. easy to support more.'
-    if not isinstance(separator, ConformerCssB200):
-        raise TypeError("notsofar_b200.separate_and_stitch drives the fused B200 path and needs a ConformerCssB200 "
-                        "separator (build one with ConformerCssB200(reference_state_dict) or load_css_model)")
-    assert not separator.training
-    device = torch.device(device)
-    if device.type != "cuda":
-        raise _cabi.NsfError("notsofar_b200 has no CPU path: pass a CUDA device")
+    assert x.dim() == 2 and x.is_cuda and x.dtype == torch.float32
+    n_samples, num_channels = x.shape
+    device = x.device
     lib = _cabi.load()
-    separator.to(device)
     if num_channels == 1 or not cfg.mc_mvdr:
         raise NotImplementedError("single-channel / mask-only CSS is not built yet (SURVEY 8f-4); use mc_mvdr=True with 7 mics")
     if cfg.normalize_segment_power:
@@ -200,15 +186,10 @@ def separate_and_stitch(speech_mix: np.ndarray, separator: ConformerCssB200, fs:
 
     with torch.cuda.device(device):
         sp = _cabi.stream_ptr
-        # H2D of the raw audio (the only input crossing), then the long-form STFT
-        if isinstance(speech_mix, torch.Tensor):
-            x = speech_mix[0].to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
-        else:
-            x = torch.from_numpy(np.ascontiguousarray(speech_mix[0], dtype=np.float32)).to(device, non_blocking=True)
-        X = separator.stft_device(x, T_alloc=mix_frames)                       # [F, mix_frames, C]
+        X = separator.stft_device(x.contiguous(), T_alloc=mix_frames)          # [F, mix_frames, C]
         T_valid = plan.raw_frames
 
-        # I. masks + MVDR per chunk of segments
+        # I. masks + MVDR per chunk of segments (css.py:182-250; segments are the batch dimension here)
         n_masks = separator.num_masks
         masks = torch.empty((n_seg, n_masks, NUM_BINS, T), dtype=torch.float32, device=device)
         Y = torch.empty((n_seg, S, NUM_BINS, T), dtype=torch.complex64, device=device)
@@ -218,7 +199,7 @@ def separate_and_stitch(speech_mix: np.ndarray, separator: ConformerCssB200, fs:
             separator.masks(X, T_valid, s0, nb, T, hop, out=masks[s0:s0 + nb])
             separator.mvdr(masks[s0:s0 + nb], X, T_valid, s0, hop, mask_floor, out=Y[s0:s0 + nb])
 
-        # II. permutation chain + weighted overlap-add
+        # II. permutation chain + weighted overlap-add (css.py:254-299)
         costs = torch.empty((n_seg, S, S), dtype=torch.float32, device=device)
         in_kind = 0 if cfg.stitching_input == 'mask' else 1
         loss_kind = 0 if cfg.stitching_loss == 'l1' else 1
@@ -236,7 +217,7 @@ def separate_and_stitch(speech_mix: np.ndarray, separator: ConformerCssB200, fs:
         _cabi.check(lib.nsf_stitch_masks(_cabi.ptr(masks), n_masks, _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), n_seg, S,
                                          NUM_BINS, T, hop, mix_frames, _cabi.ptr(mask_st), _cabi.ptr(activity), sp()),
                     "nsf_stitch_masks")
-        # III. activity gate
+        # III. activity gate (css.py:303-312)
         act_b = torch.empty((mix_frames, S), dtype=torch.uint8, device=device)
         act_tmp = torch.empty_like(act_b)
         act_final = torch.empty_like(act_b)
@@ -247,18 +228,53 @@ def separate_and_stitch(speech_mix: np.ndarray, separator: ConformerCssB200, fs:
         _cabi.check(lib.nsf_stitch_stft(_cabi.ptr(Y), _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), _cabi.ptr(act_final),
                                         n_seg, S, NUM_BINS, T, hop, mix_frames, _cabi.ptr(S_st), sp()), "nsf_stitch_stft")
         wav = separator.istft_device(S_st)                                      # [S, N']
-        separated = wav.cpu().numpy()
-        separated_wavs = [separated[k] for k in range(S)]
+    return dict(wav=wav, mask_stitched=mask_st, activity=activity, activity_b=act_b, activity_final=act_final, masks=masks,
+                Y=Y, X=X, S_st=S_st, costs=costs, perms=perms_np, plan=plan)
 
-        side_info = {'segment_frames': T}
-        if return_side_info:
-            side_info.update({
-                'mask_stitched': mask_st.cpu().unsqueeze(0),                    # [1, F, T_long, S]
-                'activity_b': act_b.cpu().bool(),                               # [T_long, S]
-                'activity_final': act_final.cpu().bool().unsqueeze(0),          # [1, T_long, S]
-            })
-        if _stages is not None:
-            _stages.update(X=X, masks=masks, Y=Y, costs=costs, perms=perms_np, S_st=S_st, activity=activity, wav=wav, plan=plan)
+
+@torch.no_grad()
+def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device: torch.device, cfg: CssCfg,
+                        return_side_info: bool = True, _stages: Optional[dict] = None) -> (List[np.ndarray], Dict):
+    """Block-online CSS of a long-form recording: same contract as the reference's
+    separate_and_stitch (css/css.py:110-338).
+
+    Args:
+        speech_mix: [Batch=1, Nsamples, Channels] float32 numpy array (or a CPU / pinned / CUDA torch tensor).
+        separator: ConformerCssB200 (the B200 re-hosting of the reference's ConformerCssWrapper).
+        fs: sample rate.  device: CUDA device.  cfg: CssCfg.
+    Returns:
+        separated_wavs: list of num_spks float32 arrays [(T_long-1)*256+512];
+        side_info: {'mask_stitched' [1,F,T_long,S] float32, 'activity_b' [T_long,S] bool,
+                    'activity_final' [1,T_long,S] bool, 'segment_frames' int} (CPU torch tensors, like the reference).
+    """
+    assert speech_mix.ndim == 3, f'expecting 3 dimensions, got {speech_mix.shape}'
+    batch_size = speech_mix.shape[0]
+    assert batch_size == 1, 'assuming 1 example in batch. easy to support more.'
+    if not isinstance(separator, ConformerCssB200):
+        raise TypeError("notsofar_b200.separate_and_stitch drives the fused B200 path and needs a ConformerCssB200 "
+                        "separator (build one with ConformerCssB200(reference_state_dict) or load_css_model)")
+    assert not separator.training
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _cabi.NsfError("notsofar_b200 has no CPU path: pass a CUDA device")
+    separator.to(device)
+    # H2D of the raw audio: the only input that crosses PCIe
+    if isinstance(speech_mix, torch.Tensor):
+        x = speech_mix[0].to(device=device, dtype=torch.float32, non_blocking=True)
+    else:
+        x = torch.from_numpy(np.ascontiguousarray(speech_mix[0], dtype=np.float32)).to(device, non_blocking=True)
+    out = css_device(x.contiguous(), separator, fs, cfg)
+    separated = out["wav"].cpu().numpy()                                        # D2H of the separated streams
+    separated_wavs = [separated[k] for k in range(cfg.num_spks)]
+    side_info = {'segment_frames': out["plan"].segment_frames}
+    if return_side_info:
+        side_info.update({
+            'mask_stitched': out["mask_stitched"].cpu().unsqueeze(0),           # [1, F, T_long, S]
+            'activity_b': out["activity_b"].cpu().bool(),                       # [T_long, S]
+            'activity_final': out["activity_final"].cpu().bool().unsqueeze(0),  # [1, T_long, S]
+        })
+    if _stages is not None:
+        _stages.update(out)
     return separated_wavs, side_info
 
 

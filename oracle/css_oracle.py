@@ -235,6 +235,7 @@ def conformer_masks(w: Dict[str, np.ndarray], feat: np.ndarray, dtype=np.float32
     maxlen = pe.shape[0] // 2
     rel = np.clip(np.arange(t_)[:, None] - np.arange(t_)[None, :], -maxlen, maxlen - 1) + maxlen
     pos_k = pe[rel]                                                                   # [T, T, d_k]
+    pos_kT = np.ascontiguousarray(pos_k.transpose(0, 2, 1))
     inv_sqrt_dk = dtype(1.0 / math.sqrt(d.d_k))
     pad = (d.kernel_size - 1) // 2
     for l in range(d.n_blocks):
@@ -253,7 +254,9 @@ def conformer_masks(w: Dict[str, np.ndarray], feat: np.ndarray, dtype=np.float32
         kh = (h @ W[q_ + "linear_k.weight"].T + W[q_ + "linear_k.bias"]).reshape(b_, t_, d.n_heads, d.d_k).transpose(0, 2, 1, 3)
         vh = (h @ W[q_ + "linear_v.weight"].T + W[q_ + "linear_v.bias"]).reshape(b_, t_, d.n_heads, d.d_k).transpose(0, 2, 1, 3)
         A = qh @ kh.transpose(0, 1, 3, 2)                                             # [B, H, T, T]
-        Bm = np.einsum("bhtd,tsd->bhts", qh, pos_k).astype(dtype)                     # conformer.py:74-77
+        # conformer.py:74-77: reshape_q [T, B*H, d_k] @ pos_k^T [T, d_k, T] -> [T, B*H, T] -> [B, H, T, T]
+        rq = qh.reshape(b_ * d.n_heads, t_, d.d_k).transpose(1, 0, 2)
+        Bm = np.matmul(rq, pos_kT).transpose(1, 0, 2).reshape(b_, d.n_heads, t_, t_)
         s = (A + Bm) * inv_sqrt_dk
         s = s - s.max(axis=-1, keepdims=True)
         e = np.exp(s)
@@ -481,13 +484,15 @@ def plan_segments(n_samples: int, fs: int, cfg) -> SegmentPlan:
 def separate_and_stitch(speech_mix: np.ndarray, weights: Dict[str, np.ndarray], fs: int = 16000,
                         cfg: Optional[OracleCfg] = None, dtype=np.float32, mvdr_dtype=None,
                         masks_override: Optional[np.ndarray] = None, batch: int = 8,
-                        return_stages: bool = False):
+                        return_stages: bool = False, stft_override: Optional[np.ndarray] = None):
     """css.py:110-338 restated.  speech_mix [1, N, C] float.  Returns (list of num_spks
     waveforms, side_info) like the reference; with return_stages also the per-segment tensors.
 
     mvdr_dtype: arithmetic of the MVDR stage (default = dtype).  np.float64 with
     dtype=np.float32 is "fp32 masks, fp64-lifted beamformer" (SURVEY 8c protocol).
     masks_override: [num_segments, 4, F, T] masks to use instead of the network's.
+    stft_override: [F, T_long, C] long-form STFT to use instead of stft(x) (stage isolation in the
+    parity tests: the ill-conditioned MVDR amplifies even 1e-7 differences of its input).
     """
     cfg = cfg or OracleCfg()
     mvdr_dtype = mvdr_dtype or dtype
@@ -497,7 +502,7 @@ def separate_and_stitch(speech_mix: np.ndarray, weights: Dict[str, np.ndarray], 
     n, c = x.shape
     plan = plan_segments(n, fs, cfg)
     T, hop = plan.segment_frames, plan.hop_frames
-    stft_mix = stft(x, dtype)                                        # [F, T_long, C]
+    stft_mix = stft(x, dtype) if stft_override is None else np.asarray(stft_override)[:, :plan.raw_frames].astype(cd)
     if plan.raw_frames < T:                                          # css.py:159-164
         stft_mix = np.pad(stft_mix, ((0, 0), (0, T - plan.raw_frames), (0, 0)))
     mix_frames = plan.mix_frames
