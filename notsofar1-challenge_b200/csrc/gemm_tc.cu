@@ -1,31 +1,39 @@
-// tcgen05 GEMM engine for sm_100a: TMA (SWIZZLE_128B) -> shared memory -> tcgen05.mma kind::tf32 with the
-// fp32 accumulator in TMEM -> tcgen05.ld epilogue with the fused ops of gemm_common.cuh.
+// tcgen05 GEMM engine for sm_100a: persistent, warp-specialised.
 //
 //   D[b][m][n] = sum_k A[b][m][k] B[b][n][k]          both operands K-major fp32 (tf32 inputs)
 //
-// 3xTF32 (n_terms == 3): D = A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in the same TMEM tile; the
-// operands arrive pre-split (X_hi has its 13 low mantissa bits clear, X_lo = X - X_hi exactly), so the
-// tensor core's truncation of X_hi is a no-op and the result is fp32-grade (~2^-21 relative).
+// TMA (SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma kind::tf32 with two fp32 accumulators in TMEM
+// (double buffered, 2 x 256 columns) -> tcgen05.ld epilogue staged through shared memory so that every
+// global store is a full 128-byte row segment, with the fused ops of gemm_common.cuh.
 //
-// CTA = 6 warps: warp 0 lane 0 TMA producer | warp 1 TMEM allocator + lane 0 MMA issuer | warps 2..5 epilogue
-// (each owns the 32 TMEM lanes of its warp-id % 4 quarter).  One 128x128 output tile per CTA,
-// BLOCK_K = 32 floats = one 128-byte swizzle row, 3- or 4-stage mbarrier ring.
+// 3xTF32 (NTERMS == 3): D = A_lo B_hi + A_hi B_lo + A_hi B_hi accumulated in the same TMEM tile; the operands
+// arrive pre-split (X_hi has its 13 low mantissa bits clear, X_lo = X - X_hi exactly), so the tensor core's
+// truncation of X_hi is a no-op and the result is fp32-grade (~2^-21 relative).
+//
+// CTA = 10 warps, one CTA per SM, grid = min(#tiles, #SMs), tiles handed out round-robin (n fastest, so the
+// CTAs of a wave share A row-blocks through L2):
+//   warp 0 lane 0  TMA producer            warp 1  TMEM allocator + lane 0 MMA issuer
+//   warps 2..9     epilogue (warp w reads the 32 TMEM lanes of quarter w % 4; w and w + 4 split the columns)
+// Tile 128 x 256, BLOCK_K = 32 floats = one 128-byte swizzle row; 2 stages of 96 KB for 3xTF32, 4 of 48 KB
+// for single-pass TF32.  While the epilogue warps drain accumulator `acc`, the MMA warp already fills `acc^1`.
 #include "gemm_common.cuh"
 #include <cuda.h>
 #include <mutex>
 
 namespace nsf {
 
-constexpr int TBM = 128, TBN = 128, TBK = 32;
-constexpr int kTileBytes = TBM * TBK * 4;          // 16 KB, same for A and B tiles (TBM == TBN)
-constexpr int kTcThreads = 192;
-constexpr uint32_t kTmemCols = 128;
+constexpr int TBM = 128, TBN = 256, TBK = 32;
+constexpr int kATileBytes = TBM * TBK * 4;         // 16 KB
+constexpr int kBTileBytes = TBN * TBK * 4;         // 32 KB
+constexpr int kTcThreads = 320;                   // 1 TMA + 1 MMA + 8 epilogue warps
+constexpr uint32_t kTmemCols = 512;                // two 128 x 256 fp32 accumulators
+constexpr int kEpiPitch = 33;                      // staging row pitch (floats): conflict-free both ways
+constexpr int kEpiBytes = 8 * 32 * kEpiPitch * 4;  // one 32 x 32 staging tile per epilogue warp
 
 template <int NTERMS> struct TcCfg {
-    static constexpr int kTilesPerStage = NTERMS == 3 ? 4 : 2;
-    static constexpr int kStages = NTERMS == 3 ? 3 : 4;
-    static constexpr int kStageBytes = kTilesPerStage * kTileBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+    static constexpr int kStageBytes = (NTERMS == 3 ? 2 : 1) * (kATileBytes + kBTileBytes);
+    static constexpr int kStages = NTERMS == 3 ? 2 : 4;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
 // ------------------------------------------------------------------------------------------- PTX wrappers
@@ -36,6 +44,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -52,7 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000LL) {
-            printf("nsf gemm_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+            printf("nsf gemm_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
             __trap();
         }
     }
@@ -74,6 +85,18 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t desc_
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 // K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), LBO unused (=1).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -83,30 +106,160 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
 }
 
+
+
+// ------------------------------------------------------------------------------------------- fused epilogue
+// One 32 (rows r0..) x 32 (columns nc..) chunk of the accumulator, r[j] = D[r0 + lane][nc + j].
+// Outputs whose fastest index is the column (row-major activations) go through a shared-memory transpose so
+// that each store instruction writes one full 128-byte row segment; outputs whose fastest index is the row
+// (V^T, the [F][T] masks) are stored straight from the TMEM register layout.  All loops are fully unrolled:
+// a single warp per scheduler has to cover its own latencies.
+struct RowWalker {      // (segment, frame) of consecutive rows m = seg * T + t without divisions in the loop
+    int seg, t, T;
+    __device__ __forceinline__ RowWalker(int m, int T_) : seg(m / T_), t(m - (m / T_) * T_), T(T_) {}
+    __device__ __forceinline__ void next() { if (++t == T) { t = 0; ++seg; } }
+};
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
+                                               float* stage, int lane) {
+    const bool lane_is_row = p.epi == EPI_MASK || (p.epi == EPI_QKV && nc >= 2 * p.d_model);
+    if (lane_is_row) {
+        const int m = r0 + lane;
+        if (m >= p.M) return;
+        const int seg = m / p.T, t = m - seg * p.T;
+        if (p.epi == EPI_MASK) {
+            const int n_masks = p.n_valid / kBins;
+            int k = nc / kBins, f = nc - k * kBins;
+            float* base = p.out0 + (size_t)seg * n_masks * kBins * p.T + t;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (nc + j < p.N) {
+                    const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + nc + j) : 0.f);
+                    base[((size_t)k * kBins + f) * p.T] = 1.f / (1.f + expf(-v));       // torch.sigmoid, conformer.py:304
+                }
+                if (++f == kBins) { f = 0; ++k; }
+            }
+        } else {    // V^T of EPI_QKV: [seg][head][d][Tp]; a 32-column chunk stays inside one head (d_k % 32 == 0)
+            const int c = nc - 2 * p.d_model;
+            const int h = c / p.d_k, d0 = c - h * p.d_k;
+            const size_t o = (((size_t)seg * p.n_heads + h) * p.d_k + d0) * p.Tp + t;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float hi, lo;
+                split_tf32(__uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + nc + j) : 0.f), hi, lo);
+                p.vt_hi[o + (size_t)j * p.Tp] = hi;
+                p.vt_lo[o + (size_t)j * p.Tp] = lo;
+            }
+        }
+        return;
+    }
+    // lane == column
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[lane * kEpiPitch + j] = __uint_as_float(r[j]);
+    __syncwarp();
+    const int n = nc + lane;
+    const int rows = min(32, p.M - r0);
+    if (n < p.N) {
+        const float bs = p.bias ? __ldg(p.bias + n) : 0.f;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = stage[i * kEpiPitch + lane] + bs;
+        switch (p.epi) {
+            case EPI_STORE: {
+                float* o = p.out0 + (size_t)b * p.o_batch_stride + (size_t)r0 * p.ldo + n;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < rows) o[(size_t)i * p.ldo] = v[i];
+                break;
+            }
+            case EPI_RELU_SPLIT: {
+                const size_t o = (size_t)r0 * p.ldo + n;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < rows) {
+                        float hi, lo;
+                        split_tf32(fmaxf(v[i], 0.f), hi, lo);
+                        p.out0[o + (size_t)i * p.ldo] = hi;
+                        p.out1[o + (size_t)i * p.ldo] = lo;
+                    }
+                break;
+            }
+            case EPI_RESID: {
+                // in-place residual stream: all loads of the chunk are issued before the first store
+                float* o = p.out0 + (size_t)r0 * p.ldo + n;
+                float old[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) old[i] = (i < rows) ? o[(size_t)i * p.ldo] : 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < rows) o[(size_t)i * p.ldo] = old[i] + p.alpha * v[i];
+                break;
+            }
+            case EPI_QKV: {     // q, k: [seg][head][t][d_k]
+                const int which = nc / p.d_model, c = n - which * p.d_model;
+                const int h = c / p.d_k, d = c - h * p.d_k;
+                float* o_hi = which ? p.k_hi : p.q_hi;
+                float* o_lo = which ? p.k_lo : p.q_lo;
+                RowWalker w(r0, p.T);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    if (i < rows) {
+                        float hi, lo;
+                        split_tf32(v[i], hi, lo);
+                        const size_t o = (((size_t)w.seg * p.n_heads + h) * p.T + w.t) * p.d_k + d;
+                        o_hi[o] = hi;
+                        o_lo[o] = lo;
+                    }
+                    w.next();
+                }
+                break;
+            }
+            case EPI_PV: {      // batch = (seg, head); rows are frames of that segment
+                const int seg = b / p.n_heads, h = b - seg * p.n_heads;
+                const size_t o = ((size_t)seg * p.T + r0) * p.ldo + (size_t)h * p.d_k + n;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < rows) {
+                        float hi, lo;
+                        split_tf32(v[i], hi, lo);
+                        p.out0[o + (size_t)i * p.ldo] = hi;
+                        p.out1[o + (size_t)i * p.ldo] = lo;
+                    }
+                break;
+            }
+            default: break;
+        }
+    }
+    __syncwarp();
+}
+
 template <int NTERMS>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
-               const GemmParams p) {
+               const GemmParams p, const int tiles_m, const int tiles_n, const int total_tiles) {
     using Cfg = TcCfg<NTERMS>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-byte alignment
     unsigned char* gen_tiles = smem_raw + (tiles - raw);
-    const uint32_t bars = tiles + Cfg::kStages * Cfg::kStageBytes;       // full[S], empty[S], tmem_full, tmem_ptr
+    float* epi_stage = reinterpret_cast<float*>(gen_tiles + Cfg::kStages * Cfg::kStageBytes);
+    const uint32_t bars = tiles + Cfg::kStages * Cfg::kStageBytes + kEpiBytes;
+    // full[S], empty[S], tmem_full[2], tmem_empty[2], tmem_ptr
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (Cfg::kStages + s); };
-    const uint32_t tmem_full_bar = bars + 8u * (2 * Cfg::kStages);
-    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_tiles + Cfg::kStages * Cfg::kStageBytes + 8 * (2 * Cfg::kStages + 1));
-    const uint32_t tmem_ptr_addr = bars + 8u * (2 * Cfg::kStages + 1);
+    auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * Cfg::kStages + a); };
+    auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * Cfg::kStages + 2 + a); };
+    const uint32_t tmem_ptr_addr = bars + 8u * (2 * Cfg::kStages + 4);
+    volatile uint32_t* tmem_ptr_gen =
+        reinterpret_cast<volatile uint32_t*>(gen_tiles + Cfg::kStages * Cfg::kStageBytes + kEpiBytes + 8 * (2 * Cfg::kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * TBN, m0 = blockIdx.y * TBM, b = blockIdx.z;
     const int nkb = p.K / TBK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -121,20 +274,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % Cfg::kStages;
-                const uint32_t ph = (kb / Cfg::kStages) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1);
-                mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
-                const uint32_t st = tiles + s * Cfg::kStageBytes;
-                const int k0 = kb * TBK;
-                tma_load_3d(st, &map_a_hi, k0, m0, b, full_bar(s));
-                if (NTERMS == 3) {
-                    tma_load_3d(st + kTileBytes, &map_a_lo, k0, m0, b, full_bar(s));
-                    tma_load_3d(st + 2 * kTileBytes, &map_b_hi, k0, n0, b, full_bar(s));
-                    tma_load_3d(st + 3 * kTileBytes, &map_b_lo, k0, n0, b, full_bar(s));
-                } else {
-                    tma_load_3d(st + kTileBytes, &map_b_hi, k0, n0, b, full_bar(s));
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int n_blk = tile % tiles_n, rest = tile / tiles_n;
+                const int m_blk = rest % tiles_m, b = rest / tiles_m;
+                const int m0 = m_blk * TBM, n0 = n_blk * TBN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (it / Cfg::kStages) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
+                    const uint32_t st = tiles + s * Cfg::kStageBytes;
+                    const int k0 = kb * TBK;
+                    tma_load_3d(st, &map_a_hi, k0, m0, b, full_bar(s));
+                    if (NTERMS == 3) {
+                        tma_load_3d(st + kATileBytes, &map_a_lo, k0, m0, b, full_bar(s));
+                        tma_load_3d(st + 2 * kATileBytes, &map_b_hi, k0, n0, b, full_bar(s));
+                        tma_load_3d(st + 2 * kATileBytes + kBTileBytes, &map_b_lo, k0, n0, b, full_bar(s));
+                    } else {
+                        tma_load_3d(st + kATileBytes, &map_b_hi, k0, n0, b, full_bar(s));
+                    }
                 }
             }
         }
@@ -142,58 +301,73 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (lane == 0) {
             // ===== MMA issuer
             const uint32_t idesc = make_idesc();
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % Cfg::kStages;
-                const uint32_t ph = (kb / Cfg::kStages) & 1;
-                mbar_wait(full_bar(s), ph);
+            uint32_t it = 0, tl = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+                const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+                mbar_wait(tmem_empty_bar(acc), aph ^ 1);       // epilogue has drained this accumulator
                 tcgen05_fence_after();
-                const uint32_t st = tiles + s * Cfg::kStageBytes;
-                const uint32_t a_hi = st, a_lo = st + kTileBytes;
-                const uint32_t b_hi = st + (NTERMS == 3 ? 2 : 1) * kTileBytes, b_lo = st + 3 * kTileBytes;
+                const uint32_t d_tmem = tmem_base + acc * TBN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % Cfg::kStages;
+                    const uint32_t ph = (it / Cfg::kStages) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t st = tiles + s * Cfg::kStageBytes;
+                    const uint32_t a_hi = st, a_lo = st + kATileBytes;
+                    const uint32_t b_hi = st + (NTERMS == 3 ? 2 : 1) * kATileBytes, b_lo = b_hi + kBTileBytes;
 #pragma unroll
-                for (int ks = 0; ks < TBK / 8; ++ks) {                    // UMMA_K = 8 tf32 = 32 bytes
-                    const uint32_t koff = ks * 32;
-                    const uint64_t da_hi = make_smem_desc(a_hi + koff), db_hi = make_smem_desc(b_hi + koff);
-                    if (NTERMS == 3) {
-                        const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
-                        tcgen05_mma_tf32(tmem_base, da_lo, db_hi, idesc, (kb | ks) != 0);    // small terms first
-                        tcgen05_mma_tf32(tmem_base, da_hi, db_lo, idesc, 1);
-                        tcgen05_mma_tf32(tmem_base, da_hi, db_hi, idesc, 1);
-                    } else {
-                        tcgen05_mma_tf32(tmem_base, da_hi, db_hi, idesc, (kb | ks) != 0);
+                    for (int ks = 0; ks < TBK / 8; ++ks) {                    // UMMA_K = 8 tf32 = 32 bytes
+                        const uint32_t koff = ks * 32;
+                        const uint64_t da_hi = make_smem_desc(a_hi + koff), db_hi = make_smem_desc(b_hi + koff);
+                        if (NTERMS == 3) {
+                            const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
+                            tcgen05_mma_tf32(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);    // small terms first
+                            tcgen05_mma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
+                            tcgen05_mma_tf32(d_tmem, da_hi, db_hi, idesc, 1);
+                        } else {
+                            tcgen05_mma_tf32(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
+                        }
                     }
+                    tcgen05_commit(empty_bar(s));          // frees the stage once the MMAs above have read it
                 }
-                tcgen05_commit(empty_bar(s));          // frees the stage once the MMAs above have read it
+                tcgen05_commit(tmem_full_bar(acc));        // accumulator complete
             }
-            tcgen05_commit(tmem_full_bar);             // accumulator complete
         }
     } else {
-        // ===== epilogue warps: TMEM -> registers -> fused epilogue -> global
-        const int q = warp & 3;                        // TMEM lane quarter this warp may access
-        mbar_wait(tmem_full_bar, 0);
-        tcgen05_fence_after();
-        const int m = m0 + q * 32 + lane;
+        // ===== epilogue warps: TMEM -> registers -> (shared-memory transpose) -> fused epilogue -> global.
+        // Warps w and w + 4 share TMEM lane quarter w % 4 and take alternate 32-column chunks.
+        const int q = warp & 3;                            // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                  // 0: chunks 0, 2, 4, ...   1: chunks 1, 3, 5, ...
+        float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
+        uint32_t tl = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
+            const int n_blk = tile % tiles_n, rest = tile / tiles_n;
+            const int m_blk = rest % tiles_m, b = rest / tiles_m;
+            const int n0 = n_blk * TBN;
+            const int r0 = m_blk * TBM + q * 32;           // first row of this warp's quarter
+            const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            mbar_wait(tmem_full_bar(acc), aph);
+            tcgen05_fence_after();
+            const int n_end = min(p.N - n0, TBN);           // valid columns of this tile (> 0)
+            const int c_first = half * 32;
+            if (c_first >= n_end) {                         // nothing to read for this warp
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                continue;
+            }
 #pragma unroll 1
-        for (int c0 = 0; c0 < TBN; c0 += 32) {
-            if (n0 + c0 >= p.N) break;                 // warp-uniform
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (m < p.M) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < p.N) gemm_epilogue(p, b, m, n, __uint_as_float(r[j]));
+            for (int c0 = c_first; c0 < n_end; c0 += 64) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + (uint32_t)c0, r);
+                if (c0 + 64 >= n_end) {
+                    // last read of this accumulator by this warp: hand it back to the MMA warp before the stores
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
                 }
+                if (r0 >= p.M) continue;                    // warp-uniform: quarter entirely out of range
+                epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane);
             }
         }
     }
@@ -223,24 +397,35 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// [batch][rows][K] fp32, K contiguous; box = 32 x 128 x 1, 128-byte swizzle, zero fill out of bounds
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int64_t batch, int64_t batch_stride) {
+// [batch][rows][K] fp32, K contiguous; box = 32 x box_rows x 1, 128-byte swizzle, zero fill out of bounds
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t K, int64_t ld, int64_t batch, int64_t batch_stride,
+                    int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("gemm_tc: cuTensorMapEncodeTiled is not available from the driver"); return NSF_ERR_CUDA; }
     if (batch_stride == 0) batch_stride = rows * ld;
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)batch_stride * 4};
-    cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)TBM, 1};
+    cuuint32_t box[3] = {(cuuint32_t)TBK, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15)) {
         set_error("gemm_tc: operand base/strides must be 16-byte aligned (ld=%lld, batch_stride=%lld)", (long long)ld, (long long)batch_stride);
         return NSF_ERR_INVALID_ARG;
     }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("gemm_tc: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return NSF_ERR_CUDA; }
     return NSF_OK;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
 }
 
 template <int NTERMS>
@@ -248,19 +433,22 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
     using Cfg = TcCfg<NTERMS>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_map(&ma_hi, p.A_hi, p.M, p.K, p.lda, p.batch, p.a_batch_stride))) return rc;
-    if ((rc = make_map(&mb_hi, p.B_hi, p.N, p.K, p.ldb, p.batch, p.b_batch_stride))) return rc;
+    if ((rc = make_map(&ma_hi, p.A_hi, p.M, p.K, p.lda, p.batch, p.a_batch_stride, TBM))) return rc;
+    if ((rc = make_map(&mb_hi, p.B_hi, p.N, p.K, p.ldb, p.batch, p.b_batch_stride, TBN))) return rc;
     if (NTERMS == 3) {
         if (!p.A_lo || !p.B_lo) { set_error("gemm_tc: 3xTF32 needs split operands"); return NSF_ERR_INVALID_ARG; }
-        if ((rc = make_map(&ma_lo, p.A_lo, p.M, p.K, p.lda, p.batch, p.a_batch_stride))) return rc;
-        if ((rc = make_map(&mb_lo, p.B_lo, p.N, p.K, p.ldb, p.batch, p.b_batch_stride))) return rc;
+        if ((rc = make_map(&ma_lo, p.A_lo, p.M, p.K, p.lda, p.batch, p.a_batch_stride, TBM))) return rc;
+        if ((rc = make_map(&mb_lo, p.B_lo, p.N, p.K, p.ldb, p.batch, p.b_batch_stride, TBN))) return rc;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
     NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    dim3 grid(ceil_div(p.N, TBN), ceil_div(p.M, TBM), p.batch);
-    gemm_tc_kernel<NTERMS><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p);
+    const int tiles_m = ceil_div(p.M, TBM), tiles_n = ceil_div(p.N, TBN);
+    const int64_t total = (int64_t)tiles_m * tiles_n * p.batch;
+    if (total > 0x7fffffff) { set_error("gemm_tc: too many tiles"); return NSF_ERR_INVALID_ARG; }
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    gemm_tc_kernel<NTERMS><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, tiles_m, tiles_n, (int)total);
     return check_launch("gemm_tc_kernel");
 }
 
