@@ -155,9 +155,49 @@ def _segment_weights(plan: SegmentPlan):
     return seg_w, wsum
 
 
+class HostFeeder:
+    """Streams a pinned (or pageable) host recording [Nsamples, Channels] into HBM in chunks on a side stream, so the
+    STFT / mask network of the first segments run while the rest of the meeting is still crossing PCIe.
+    ``ready(n)`` makes the *current* stream wait until samples [0, n) have landed."""
+
+    def __init__(self, x_host: torch.Tensor, device: torch.device, chunk_samples: int):
+        assert x_host.dim() == 2 and x_host.dtype == torch.float32 and not x_host.is_cuda
+        n = x_host.shape[0]
+        self.x_dev = torch.empty(x_host.shape, dtype=torch.float32, device=device)
+        self.stream = _side_stream(device)
+        self.stream.wait_stream(torch.cuda.current_stream(device))     # x_dev may recycle memory still in use upstream
+        self.bounds, self.events = [], []
+        chunk_samples = max(int(chunk_samples), FRAME_LEN)
+        with torch.cuda.stream(self.stream):
+            for s0 in range(0, n, chunk_samples):
+                s1 = min(n, s0 + chunk_samples)
+                self.x_dev[s0:s1].copy_(x_host[s0:s1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                self.bounds.append(s1)
+                self.events.append(ev)
+        self._next = 0
+
+    def ready(self, n_samples: int):
+        cur = torch.cuda.current_stream(self.x_dev.device)
+        while self._next < len(self.bounds) and (self._next == 0 or self.bounds[self._next - 1] < n_samples):
+            cur.wait_event(self.events[self._next])
+            self._next += 1
+
+
+_SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _side_stream(device: torch.device):
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SIDE_STREAMS:
+        _SIDE_STREAMS[idx] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[idx]
+
+
 @torch.no_grad()
-def css_device(x: torch.Tensor, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_info: bool = True) -> Dict:
-    """The whole CSS path on tensors that already live in HBM.
+def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_info: bool = True) -> Dict:
+    """The whole CSS path on tensors that already live in HBM (or are on their way there: x may be a HostFeeder).
 
     x: [Nsamples, Channels] float32 on the CUDA device.  Returns a dict of device tensors:
     'wav' [S, N'], 'mask_stitched' [F, T_long, S], 'activity' [T_long, S] float, 'activity_b' / 'activity_final'
@@ -165,7 +205,10 @@ def css_device(x: torch.Tensor, separator: ConformerCssB200, fs: int, cfg: CssCf
     'perms' (numpy [n_seg, S]) and 'plan'.  The only host round trip inside is the [n_seg, S, S] cost matrix of
     the permutation chain (css.py:266-285), 36 bytes per segment.
     """
-    assert x.dim() == 2 and x.is_cuda and x.dtype == torch.float32
+    feeder = x if isinstance(x, HostFeeder) else None
+    if feeder is not None:
+        x = feeder.x_dev
+    assert x.dim() == 2 and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
     n_samples, num_channels = x.shape
     device = x.device
     lib = _cabi.load()
@@ -186,8 +229,9 @@ def css_device(x: torch.Tensor, separator: ConformerCssB200, fs: int, cfg: CssCf
 
     with torch.cuda.device(device):
         sp = _cabi.stream_ptr
-        X = separator.stft_device(x.contiguous(), T_alloc=mix_frames)          # [F, mix_frames, C]
         T_valid = plan.raw_frames
+        X = separator.stft_alloc(num_channels, mix_frames, T_valid, device)   # [F, mix_frames, C], padding frames zeroed
+        frames_done = 0
 
         # I. masks + MVDR per chunk of segments (css.py:182-250; segments are the batch dimension here)
         n_masks = separator.num_masks
@@ -196,8 +240,18 @@ def css_device(x: torch.Tensor, separator: ConformerCssB200, fs: int, cfg: CssCf
         B = max(1, int(separator.segments_per_batch))
         for s0 in range(0, n_seg, B):
             nb = min(B, n_seg - s0)
+            # STFT of the frames this chunk of segments needs (and, when streaming from the host, only once they landed)
+            f_need = min(T_valid, (s0 + nb - 1) * hop + T)
+            if f_need > frames_done:
+                if feeder is not None:
+                    feeder.ready((f_need - 1) * FRAME_HOP + FRAME_LEN)
+                separator.stft_frames(x, X, frames_done, f_need)
+                frames_done = f_need
             separator.masks(X, T_valid, s0, nb, T, hop, out=masks[s0:s0 + nb])
             separator.mvdr(masks[s0:s0 + nb], X, T_valid, s0, hop, mask_floor, out=Y[s0:s0 + nb])
+
+        if feeder is not None:
+            feeder.ready(n_samples)       # every copy has been ordered before the buffers can be recycled
 
         # II. permutation chain + weighted overlap-add (css.py:254-299)
         costs = torch.empty((n_seg, S, S), dtype=torch.float32, device=device)
@@ -258,13 +312,24 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
     if device.type != "cuda":
         raise _cabi.NsfError("notsofar_b200 has no CPU path: pass a CUDA device")
     separator.to(device)
-    # H2D of the raw audio: the only input that crosses PCIe
-    if isinstance(speech_mix, torch.Tensor):
-        x = speech_mix[0].to(device=device, dtype=torch.float32, non_blocking=True)
+    # H2D of the raw audio -- the only input that crosses PCIe -- streamed in chunks behind the compute
+    if isinstance(speech_mix, torch.Tensor) and speech_mix.is_cuda:
+        x = speech_mix[0].to(device=device, dtype=torch.float32).contiguous()
     else:
-        x = torch.from_numpy(np.ascontiguousarray(speech_mix[0], dtype=np.float32)).to(device, non_blocking=True)
-    out = css_device(x.contiguous(), separator, fs, cfg)
-    separated = out["wav"].cpu().numpy()                                        # D2H of the separated streams
+        x_host = speech_mix[0] if isinstance(speech_mix, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(speech_mix[0], dtype=np.float32))
+        x_host = x_host.to(torch.float32).contiguous()
+        plan0 = plan_segments(x_host.shape[0], fs, cfg)
+        chunk = max(1, int(separator.segments_per_batch)) * plan0.hop_frames * FRAME_HOP
+        with torch.cuda.device(device):
+            x = HostFeeder(x_host, device, chunk)
+    out = css_device(x, separator, fs, cfg)
+    # D2H of the separated streams into a (recycled) pinned buffer
+    wav = out["wav"]
+    with torch.cuda.device(device):
+        host = _pinned_out(tuple(wav.shape))
+        host.copy_(wav, non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+    separated = host.numpy()
     separated_wavs = [separated[k] for k in range(cfg.num_spks)]
     side_info = {'segment_frames': out["plan"].segment_frames}
     if return_side_info:
@@ -276,6 +341,25 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
     if _stages is not None:
         _stages.update(out)
     return separated_wavs, side_info
+
+
+_PINNED_POOL: Dict[tuple, list] = {}
+_PINNED_SLOTS = 2
+
+
+def _pinned_out(shape: tuple) -> torch.Tensor:
+    """Page-locked float32 host buffer for the separated waveforms.  Buffers are recycled round-robin over
+    _PINNED_SLOTS slots per shape (pinning 345 MB costs more than the whole separation), so the arrays a call
+    returns stay valid until _PINNED_SLOTS later calls with the same output length; copy them to keep them longer."""
+    slot = _PINNED_POOL.setdefault(shape, [0, []])
+    idx, bufs = slot
+    if len(bufs) < _PINNED_SLOTS:
+        bufs.append(torch.empty(shape, dtype=torch.float32, pin_memory=True))
+        buf = bufs[-1]
+    else:
+        buf = bufs[idx % _PINNED_SLOTS]
+    slot[0] = idx + 1
+    return buf
 
 
 def load_css_model(model_dir: Path, device: Optional[torch.device] = None, **kw) -> (ConformerCssB200, dict):

@@ -240,6 +240,25 @@ class ConformerCssB200:
         _cabi.check(self._lib.nsf_stft_mc(_cabi.ptr(x), n, c, _cabi.ptr(X), T_alloc, nf, _cabi.stream_ptr()), "nsf_stft_mc")
         return X
 
+    def stft_alloc(self, n_ch: int, T_alloc: int, T_valid: int, device) -> torch.Tensor:
+        """X [F, T_alloc, C] complex64 with the frames >= T_valid (zero padding of short inputs, css.py:159-164) cleared."""
+        X = torch.empty((NUM_BINS, T_alloc, n_ch), dtype=torch.complex64, device=device)
+        if T_alloc > T_valid:
+            X[:, T_valid:, :].zero_()
+        return X
+
+    def stft_frames(self, x: torch.Tensor, X: torch.Tensor, f0: int, f1: int):
+        """Frames [f0, f1) of x [N, C] into X[:, f0:f1, :] (the rest of X is untouched)."""
+        self._require_cuda()
+        n, c = x.shape
+        assert x.is_contiguous() and X.is_contiguous() and X.shape[2] == c and 0 <= f0 <= f1 <= int(self._lib.nsf_num_frames(n))
+        if f1 == f0:
+            return
+        xo = x[f0 * FRAME_HOP:]
+        Xo = X[:, f0:, :]
+        _cabi.check(self._lib.nsf_stft_mc(_cabi.ptr(xo), n - f0 * FRAME_HOP, c, _cabi.ptr(Xo), X.shape[1], f1 - f0,
+                                          _cabi.stream_ptr()), "nsf_stft_mc")
+
     def features(self, X: torch.Tensor, T_valid: int, seg_first: int, n_seg: int, T: int, hop: int,
                  normalize_input: bool = False, split: bool = False):
         """feat [n_seg*T, ldf] (and its TF32 remainder when split) for segments seg_first.. of X."""
