@@ -173,6 +173,14 @@ int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, float* peak, 
 int nsf_gemm_test(int engine, const float* A, const float* W, const float* bias, float* Cout,
                   int M, int N, int K, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Test hook: the fused relative-position attention of the mask network (conformer.py:66-92) on plain fp32 inputs.
+ * q, k, v [n_seg*n_heads][T][64], pe [2*maxlen][64] (Embedding table of RelativePositionalEncoding, conformer.py:18)
+ *   out[seg*T + t1][head*64 + d] = sum_t2 softmax_t2((q[t1].k[t2] + q[t1].pe[maxlen + t1 - t2]) / 8) v[t2][d].
+ * T <= 192.  Used by the parity tests to check the tcgen05 attention kernel against a float64 restatement. */
+int64_t nsf_attention_test_workspace_bytes(int n_seg, int n_heads, int T, int maxlen);
+int nsf_attention_test(const float* q, const float* k, const float* v, const float* pe, int maxlen, int n_seg, int n_heads,
+                       int T, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

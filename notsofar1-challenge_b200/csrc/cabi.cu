@@ -63,7 +63,7 @@ extern "C" int nsf_prof_enable(int on) {
 extern "C" int nsf_prof_num_classes(void) { return PROF_NUM_CLASSES; }
 
 extern "C" const char* nsf_prof_class_name(int cls) {
-    static const char* names[PROF_NUM_CLASSES] = {"stft", "features", "gemm_tc", "gemm_simt", "net_other", "mvdr", "pit_cost",
+    static const char* names[PROF_NUM_CLASSES] = {"stft", "features", "gemm_tc", "gemm_simt", "attention", "net_other", "mvdr", "pit_cost",
                                                   "stitch", "activity", "istft", "pcm16"};
     return (cls >= 0 && cls < PROF_NUM_CLASSES) ? names[cls] : "?";
 }

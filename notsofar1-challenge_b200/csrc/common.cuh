@@ -29,7 +29,7 @@ inline int check_launch(const char* what) {
 // A ProfScope brackets the launches of one class; `work` is the algorithmic work of the bracket
 // (bytes for the HBM-bound classes, flops for the GEMM classes).
 enum ProfClass : int {
-    PROF_STFT = 0, PROF_FEATURES, PROF_GEMM_TC, PROF_GEMM_SIMT, PROF_NET_OTHER, PROF_MVDR, PROF_PIT, PROF_STITCH,
+    PROF_STFT = 0, PROF_FEATURES, PROF_GEMM_TC, PROF_GEMM_SIMT, PROF_ATTN, PROF_NET_OTHER, PROF_MVDR, PROF_PIT, PROF_STITCH,
     PROF_ACTIVITY, PROF_ISTFT, PROF_PCM16, PROF_NUM_CLASSES
 };
 bool prof_enabled();

@@ -248,10 +248,11 @@ static Workspace carve(const nsf_conformer_dims& D, int n_seg, float* base) {
     w.k_lo = take(M * D.d_model);
     w.vt_hi = take(BH * d_k * Tp);
     w.vt_lo = take(BH * d_k * Tp);
-    w.s1 = take(BH * D.T * Tp);
-    w.s2 = take(BH * D.T * ld2);
-    w.p_hi = take(BH * D.T * Tp);
-    w.p_lo = take(BH * D.T * Tp);
+    const bool unfused = !attn_fused_supported(D.T, d_k) || D.gemm_engine == NSF_GEMM_SIMT_FP32;   // score buffers of the unfused path
+    w.s1 = take(unfused ? BH * D.T * Tp : 0);
+    w.s2 = take(unfused ? BH * D.T * ld2 : 0);
+    w.p_hi = take(unfused ? BH * D.T * Tp : 0);
+    w.p_lo = take(unfused ? BH * D.T * Tp : 0);
     w.total_floats = off;
     return w;
 }
@@ -381,32 +382,39 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WQKV_HI), h->l(L, L_WQKV_LO), h->l(L, L_BQKV), 3 * d, EPI_QKV, 1.f, nullptr,
                     nullptr, 0);
         if (rc) return rc;
-        {   // A = q k^T per (segment, head)
-            GemmParams p = base_params();
-            p.A_hi = w.q_hi; p.A_lo = w.q_lo; p.lda = d_k; p.a_batch_stride = (int64_t)T * d_k;
-            p.B_hi = w.k_hi; p.B_lo = w.k_lo; p.ldb = d_k; p.b_batch_stride = (int64_t)T * d_k;
-            p.M = T; p.N = T; p.K = d_k; p.n_valid = T; p.batch = BH;
-            p.epi = EPI_STORE; p.out0 = w.s1; p.ldo = Tp; p.o_batch_stride = (int64_t)T * Tp;
-            if ((rc = gemm_launch(eng, p, s))) return rc;
-        }
-        {   // B' = q pe_k[maxlen-(T-1) .. maxlen+(T-1)]^T for every (segment, head, t1) row at once
-            GemmParams p = base_params();
-            p.A_hi = w.q_hi; p.A_lo = w.q_lo; p.lda = d_k;
-            const int64_t pe_off = (int64_t)(D.maxlen - (T - 1)) * d_k;
-            p.B_hi = h->g(G_PE_HI) + pe_off; p.B_lo = h->g(G_PE_LO) + pe_off; p.ldb = d_k;
-            p.M = BH * T; p.N = 2 * T - 1; p.K = d_k; p.n_valid = 2 * T - 1;
-            p.epi = EPI_STORE; p.out0 = w.s2; p.ldo = ld2;
-            if ((rc = gemm_launch(eng, p, s))) return rc;
-        }
-        { ProfScope prof(PROF_NET_OTHER, 0.0, s); relpos_softmax_kernel<<<ceil_div(BH * T, 8), 256, 0, s>>>(w.s1, w.s2, BH * T, T, Tp, ld2, inv_sqrt_dk, w.p_hi, w.p_lo); }
-        if ((rc = check_launch("relpos_softmax_kernel"))) return rc;
-        {   // o = p v per (segment, head), gathered back to [M, d_model]
-            GemmParams p = base_params();
-            p.A_hi = w.p_hi; p.A_lo = w.p_lo; p.lda = Tp; p.a_batch_stride = (int64_t)T * Tp;
-            p.B_hi = w.vt_hi; p.B_lo = w.vt_lo; p.ldb = Tp; p.b_batch_stride = (int64_t)d_k * Tp;
-            p.M = T; p.N = d_k; p.K = Tp; p.n_valid = d_k; p.batch = BH;
-            p.epi = EPI_PV; p.out0 = w.h_hi; p.out1 = w.h_lo; p.ldo = d;
-            if ((rc = gemm_launch(eng, p, s))) return rc;
+        if (attn_fused_supported(T, d_k) && eng != NSF_GEMM_SIMT_FP32) {
+            // scores, relative-position skew, softmax and P V in one tcgen05 kernel (attention.cu)
+            ProfScope prof(PROF_ATTN, 6.0 * T * T * d_k * (double)BH, s);
+            if ((rc = attn_fused_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE_HI), h->g(G_PE_LO), D.maxlen,
+                                        n_seg, H, T, Tp, w.h_hi, w.h_lo, d, s))) return rc;
+        } else {
+            {   // A = q k^T per (segment, head)
+                GemmParams p = base_params();
+                p.A_hi = w.q_hi; p.A_lo = w.q_lo; p.lda = d_k; p.a_batch_stride = (int64_t)T * d_k;
+                p.B_hi = w.k_hi; p.B_lo = w.k_lo; p.ldb = d_k; p.b_batch_stride = (int64_t)T * d_k;
+                p.M = T; p.N = T; p.K = d_k; p.n_valid = T; p.batch = BH;
+                p.epi = EPI_STORE; p.out0 = w.s1; p.ldo = Tp; p.o_batch_stride = (int64_t)T * Tp;
+                if ((rc = gemm_launch(eng, p, s))) return rc;
+            }
+            {   // B' = q pe_k[maxlen-(T-1) .. maxlen+(T-1)]^T for every (segment, head, t1) row at once
+                GemmParams p = base_params();
+                p.A_hi = w.q_hi; p.A_lo = w.q_lo; p.lda = d_k;
+                const int64_t pe_off = (int64_t)(D.maxlen - (T - 1)) * d_k;
+                p.B_hi = h->g(G_PE_HI) + pe_off; p.B_lo = h->g(G_PE_LO) + pe_off; p.ldb = d_k;
+                p.M = BH * T; p.N = 2 * T - 1; p.K = d_k; p.n_valid = 2 * T - 1;
+                p.epi = EPI_STORE; p.out0 = w.s2; p.ldo = ld2;
+                if ((rc = gemm_launch(eng, p, s))) return rc;
+            }
+            { ProfScope prof(PROF_NET_OTHER, 0.0, s); relpos_softmax_kernel<<<ceil_div(BH * T, 8), 256, 0, s>>>(w.s1, w.s2, BH * T, T, Tp, ld2, inv_sqrt_dk, w.p_hi, w.p_lo); }
+            if ((rc = check_launch("relpos_softmax_kernel"))) return rc;
+            {   // o = p v per (segment, head), gathered back to [M, d_model]
+                GemmParams p = base_params();
+                p.A_hi = w.p_hi; p.A_lo = w.p_lo; p.lda = Tp; p.a_batch_stride = (int64_t)T * Tp;
+                p.B_hi = w.vt_hi; p.B_lo = w.vt_lo; p.ldb = Tp; p.b_batch_stride = (int64_t)d_k * Tp;
+                p.M = T; p.N = d_k; p.K = Tp; p.n_valid = d_k; p.batch = BH;
+                p.epi = EPI_PV; p.out0 = w.h_hi; p.out1 = w.h_lo; p.ldo = d;
+                if ((rc = gemm_launch(eng, p, s))) return rc;
+            }
         }
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WO_HI), h->l(L, L_WO_LO), h->l(L, L_BO), d, EPI_RESID, 1.f, w.x, nullptr, d);
         if (rc) return rc;

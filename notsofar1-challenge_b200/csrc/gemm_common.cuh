@@ -99,6 +99,12 @@ int gemm_simt_launch(const GemmParams& p, cudaStream_t stream);
 // n_terms: 3 -> 3xTF32, 1 -> single TF32 pass
 int gemm_tc_launch(const GemmParams& p, int n_terms, cudaStream_t stream);
 
+// fused relative-position attention (attention.cu); q, k: [n_seg*heads][T][64], vt: [n_seg*heads][64][Tp], all split
+int attn_fused_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
+                      const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
+                      float* out_hi, float* out_lo, int64_t ldo, cudaStream_t stream);
+inline bool attn_fused_supported(int T, int d_k) { return T >= 2 && T <= 192 && d_k == 64; }
+
 inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {
     // algorithmic flops: 2 M N K per batch entry (the three TF32 passes of 3xTF32 count once)
     ProfScope prof(engine == NSF_GEMM_SIMT_FP32 ? PROF_GEMM_SIMT : PROF_GEMM_TC, 2.0 * p.M * p.N * p.K * p.batch, stream);

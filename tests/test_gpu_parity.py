@@ -190,6 +190,41 @@ def test_gemm_engines_vs_fp64(nb, dev, M, N, K):
     assert errs["tf32"] < 3e-3
 
 
+# ----------------------------------------------------------------------------------------------- fused attention
+@pytest.mark.parametrize("n_seg,n_heads,T,maxlen", [(2, 2, 186, 1000), (1, 1, 50, 1000), (1, 2, 128, 200), (1, 1, 129, 300),
+                                                      (2, 1, 192, 1000), (1, 1, 2, 1000), (3, 8, 186, 1000)])
+def test_fused_attention_vs_fp64(nb, dev, n_seg, n_heads, T, maxlen):
+    """tcgen05 attention kernel (scores + relative-position skew + softmax + P V) vs a float64 restatement of
+    MultiHeadedAttention.forward (conformer.py:66-92)."""
+    lib = nb._cabi.load()
+    rng = np.random.default_rng(T * 13 + n_heads)
+    bh = n_seg * n_heads
+    q, k, v = (rng.standard_normal((bh, T, 64)).astype(np.float32) for _ in range(3))
+    pe = rng.standard_normal((2 * maxlen, 64)).astype(np.float32)
+    qd, kd, vd, ped = (a.astype(np.float64) for a in (q, k, v, pe))
+    idx = np.arange(T)[:, None] - np.arange(T)[None, :] + maxlen          # pe_k row of (t1, t2)
+    A = np.einsum("btd,bsd->bts", qd, kd)
+    B = np.einsum("btd,tsd->bts", qd, ped[idx])
+    sc = (A + B) / 8.0
+    sc -= sc.max(-1, keepdims=True)
+    P = np.exp(sc)
+    P /= P.sum(-1, keepdims=True)
+    o = np.einsum("bts,bsd->btd", P, vd)                                   # [bh, T, 64]
+    ref = o.reshape(n_seg, n_heads, T, 64).transpose(0, 2, 1, 3).reshape(n_seg * T, n_heads * 64)
+    tq, tk, tv, tpe = (torch.from_numpy(a).to(dev) for a in (q, k, v, pe))
+    out = torch.full((n_seg * T, n_heads * 64), float("nan"), dtype=torch.float32, device=dev)
+    need = int(lib.nsf_attention_test_workspace_bytes(n_seg, n_heads, T, maxlen))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    nb._cabi.check(lib.nsf_attention_test(nb._cabi.ptr(tq), nb._cabi.ptr(tk), nb._cabi.ptr(tv), nb._cabi.ptr(tpe), maxlen, n_seg, n_heads,
+                                          T, nb._cabi.ptr(out), nb._cabi.ptr(ws), need, nb._cabi.stream_ptr()), "nsf_attention_test")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = rel_l2(got, ref)
+    print("fused attention rel err", (n_seg, n_heads, T), err)
+    assert err < 2e-5
+
+
 # ----------------------------------------------------------------------------------------------- mask network
 @pytest.mark.parametrize("engine_name", ["simt", "3xtf32"])
 def test_masks_vs_reference_golden(nb, dev, golden, small_weights, engine_name):
