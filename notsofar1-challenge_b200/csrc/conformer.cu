@@ -40,9 +40,84 @@ struct nsf_conformer {
 namespace nsf {
 
 // ------------------------------------------------------------------------------------------- LayerNorm family
-constexpr int kLnMaxPerLane = 32;   // d_model <= 1024
+// One warp per row, the row held in registers as float4s (d = 128 * NV, or the scalar tail kernel for other
+// multiples of 32); all loads of a row are in flight before the first reduction.  HBM-bound streaming kernels.
+constexpr int kLnMaxPerLane = 32;   // scalar kernels: d_model <= 1024
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+template <int NV>
+__device__ __forceinline__ void ln_stats(const float4 (&v)[NV], float inv_d, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    mean = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
+        q += (a * a + b * b) + (c * c + e * e);
+    }
+    rstd = 1.f / sqrtf(warp_sum(q) * inv_d + 1e-5f);
+}
+__device__ __forceinline__ float4 ln_apply(float4 v, float mean, float rstd, float4 g, float4 b) {
+    return make_float4((v.x - mean) * rstd * g.x + b.x, (v.y - mean) * rstd * g.y + b.y, (v.z - mean) * rstd * g.z + b.z,
+                       (v.w - mean) * rstd * g.w + b.w);
+}
 
 // y1 = LN(x; g1, b1) [relu]; optional store; y2 = LN(y1; g2, b2) if g2 else y1; optional split store.
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_vec_kernel(const float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1, int relu1,
+              float* __restrict__ out_x, const float* __restrict__ g2, const float* __restrict__ b2,
+              float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    constexpr int d = 128 * NV;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float inv_d = 1.f / (float)d;
+    const size_t ro = (size_t)row * d;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = ld4(x + ro + (i * 32 + lane) * 4);
+    float mean, rstd;
+    ln_stats<NV>(v, inv_d, mean, rstd);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        float4 y = ln_apply(v[i], mean, rstd, ldg4(g1 + c), ldg4(b1 + c));
+        if (relu1) y = make_float4(fmaxf(y.x, 0.f), fmaxf(y.y, 0.f), fmaxf(y.z, 0.f), fmaxf(y.w, 0.f));
+        v[i] = y;
+        if (out_x) st4(out_x + ro + c, y);
+    }
+    if (g2) {
+        ln_stats<NV>(v, inv_d, mean, rstd);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = (i * 32 + lane) * 4;
+            v[i] = ln_apply(v[i], mean, rstd, ldg4(g2 + c), ldg4(b2 + c));
+        }
+    }
+    if (out_hi) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const size_t o = ro + (i * 32 + lane) * 4;
+            if (out_lo) {
+                float4 hi, lo;
+                split_tf32(v[i].x, hi.x, lo.x); split_tf32(v[i].y, hi.y, lo.y);
+                split_tf32(v[i].z, hi.z, lo.z); split_tf32(v[i].w, hi.w, lo.w);
+                st4(out_hi + o, hi);
+                st4(out_lo + o, lo);
+            } else {
+                st4(out_hi + o, v[i]);
+            }
+        }
+    }
+}
+
+// scalar variant for d not a multiple of 128
 __global__ void __launch_bounds__(256)
 ln_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g1, const float* __restrict__ b1, int relu1,
           float* __restrict__ out_x, const float* __restrict__ g2, const float* __restrict__ b2,
@@ -106,7 +181,47 @@ ln_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g
     }
 }
 
+static int ln_launch(const float* x, int M, int d, const float* g1, const float* b1, int relu1, float* out_x, const float* g2,
+                     const float* b2, float* out_hi, float* out_lo, cudaStream_t s) {
+    const int grid = ceil_div(M, 8);
+    switch ((d % 128 == 0) ? d / 128 : 0) {
+        case 1: ln_vec_kernel<1><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
+        case 2: ln_vec_kernel<2><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
+        case 4: ln_vec_kernel<4><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
+        case 8: ln_vec_kernel<8><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
+        default: ln_kernel<<<grid, 256, 0, s>>>(x, M, d, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
+    }
+    return check_launch("ln_kernel");
+}
+
 // conv module front: h = LN(x); u = (w1a h + b1a) * sigmoid(w1g h + b1g)      conformer.py:115-117
+__device__ __forceinline__ float glu1(float h, float w1a, float b1a, float w1g, float b1g) {
+    const float a = w1a * h + b1a, gt = w1g * h + b1g;
+    return a * (1.f / (1.f + expf(-gt)));
+}
+template <int NV>
+__global__ void __launch_bounds__(256)
+ln_glu_vec_kernel(const float* __restrict__ x, int M, const float* __restrict__ g, const float* __restrict__ b,
+                  const float* __restrict__ scalars, float* __restrict__ u) {
+    constexpr int d = 128 * NV;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const size_t ro = (size_t)row * d;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = ld4(x + ro + (i * 32 + lane) * 4);
+    float mean, rstd;
+    ln_stats<NV>(v, 1.f / (float)d, mean, rstd);
+    const float w1a = __ldg(scalars + 0), b1a = __ldg(scalars + 1), w1g = __ldg(scalars + 2), b1g = __ldg(scalars + 3);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 h = ln_apply(v[i], mean, rstd, ldg4(g + c), ldg4(b + c));
+        st4(u + ro + c, make_float4(glu1(h.x, w1a, b1a, w1g, b1g), glu1(h.y, w1a, b1a, w1g, b1g), glu1(h.z, w1a, b1a, w1g, b1g),
+                                    glu1(h.w, w1a, b1a, w1g, b1g)));
+    }
+}
 __global__ void __launch_bounds__(256)
 ln_glu_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g, const float* __restrict__ b,
               const float* __restrict__ scalars, float* __restrict__ u) {
@@ -132,45 +247,65 @@ ln_glu_kernel(const float* __restrict__ x, int M, int d, const float* __restrict
     for (int i = 0; i < kLnMaxPerLane; ++i)
         if (i < n_per) {
             const int c = i * 32 + lane;
-            const float h = (v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c);
-            const float a = w1a * h + b1a, gt = w1g * h + b1g;
-            u[(size_t)row * d + c] = a * (1.f / (1.f + expf(-gt)));
+            u[(size_t)row * d + c] = glu1((v[i] - mean) * rstd * __ldg(g + c) + __ldg(b + c), w1a, b1a, w1g, b1g);
         }
+}
+static int ln_glu_launch(const float* x, int M, int d, const float* g, const float* b, const float* scalars, float* u, cudaStream_t s) {
+    const int grid = ceil_div(M, 8);
+    switch ((d % 128 == 0) ? d / 128 : 0) {
+        case 1: ln_glu_vec_kernel<1><<<grid, 256, 0, s>>>(x, M, g, b, scalars, u); break;
+        case 2: ln_glu_vec_kernel<2><<<grid, 256, 0, s>>>(x, M, g, b, scalars, u); break;
+        case 4: ln_glu_vec_kernel<4><<<grid, 256, 0, s>>>(x, M, g, b, scalars, u); break;
+        case 8: ln_glu_vec_kernel<8><<<grid, 256, 0, s>>>(x, M, g, b, scalars, u); break;
+        default: ln_glu_kernel<<<grid, 256, 0, s>>>(x, M, d, g, b, scalars, u); break;
+    }
+    return check_launch("ln_glu_kernel");
 }
 
 // conv module back: depthwise conv over time (zero padded inside the segment), BN (folded), ReLU, scalar affine,
 // residual add.                                                                     conformer.py:118-126, 181
-constexpr int kDwTT = 32, kDwCC = 128, kDwMaxK = 33;
+// One CTA stages a whole segment of 64 channels in shared memory (coalesced float4 rows); each thread then slides a
+// 48-value register window down its channel and produces 16 outputs per window (33 taps from registers).
+constexpr int kDwCh = 64, kDwOut = 16, kDwMaxK = 33;
 __global__ void __launch_bounds__(256)
 dwconv_kernel(const float* __restrict__ u, float* __restrict__ x, int T, int d, int ks, const float* __restrict__ dw_w,
               const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const float* __restrict__ scalars) {
-    extern __shared__ float tile[];     // [kDwTT + ks - 1][kDwCC]
-    const int seg = blockIdx.z, c0 = blockIdx.y * kDwCC, t0 = blockIdx.x * kDwTT;
+    extern __shared__ __align__(16) float tile[];     // [T + ks - 1][kDwCh], row r <-> frame r - pad
+    const int seg = blockIdx.y, c0 = blockIdx.x * kDwCh;
     const int pad = (ks - 1) / 2;
-    const int rows = kDwTT + ks - 1;
-    for (int idx = threadIdx.x; idx < rows * kDwCC; idx += blockDim.x) {
-        const int r = idx / kDwCC, c = idx - r * kDwCC;
-        const int t = t0 + r - pad;
-        tile[idx] = (t >= 0 && t < T && c0 + c < d) ? __ldg(u + ((size_t)seg * T + t) * d + c0 + c) : 0.f;
+    const int rows = T + ks - 1;
+    for (int idx = threadIdx.x; idx < rows * (kDwCh / 4); idx += blockDim.x) {
+        const int r = idx / (kDwCh / 4), c4 = idx - r * (kDwCh / 4);
+        const int t = r - pad;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < T && c0 + c4 * 4 < d) v = ldg4(u + ((size_t)seg * T + t) * d + c0 + c4 * 4);
+        st4(tile + r * kDwCh + c4 * 4, v);
     }
     __syncthreads();
-    const int c = threadIdx.x % kDwCC, half = threadIdx.x / kDwCC;
+    const int c = threadIdx.x & (kDwCh - 1), grp = threadIdx.x / kDwCh;       // 4 frame groups
     if (c0 + c >= d) return;
     float w[kDwMaxK];
 #pragma unroll
     for (int j = 0; j < kDwMaxK; ++j) w[j] = j < ks ? __ldg(dw_w + (size_t)(c0 + c) * ks + j) : 0.f;
     const float sc = __ldg(bn_scale + c0 + c), sh = __ldg(bn_shift + c0 + c);
     const float w2 = __ldg(scalars + 4), b2 = __ldg(scalars + 5);
-    for (int tt = half; tt < kDwTT; tt += 2) {
-        const int t = t0 + tt;
-        if (t >= T) break;
-        float acc = 0.f;
+    const int per = ceil_div(ceil_div(T, 4), kDwOut) * kDwOut;
+    const int t_end = min(T, (grp + 1) * per);
+    for (int t0 = grp * per; t0 < t_end; t0 += kDwOut) {
+        float win[kDwOut + kDwMaxK - 1];
 #pragma unroll
-        for (int j = 0; j < kDwMaxK; ++j)
-            if (j < ks) acc = fmaf(w[j], tile[(tt + j) * kDwCC + c], acc);
-        const float y = fmaxf(acc * sc + sh, 0.f);
-        const size_t o = ((size_t)seg * T + t) * d + c0 + c;
-        x[o] = x[o] + (w2 * y + b2);
+        for (int i = 0; i < kDwOut + kDwMaxK - 1; ++i) win[i] = (t0 + i < rows) ? tile[(t0 + i) * kDwCh + c] : 0.f;
+        float xo[kDwOut];
+#pragma unroll
+        for (int o = 0; o < kDwOut; ++o) xo[o] = (t0 + o < t_end) ? x[((size_t)seg * T + t0 + o) * d + c0 + c] : 0.f;
+#pragma unroll
+        for (int o = 0; o < kDwOut; ++o) {
+            float acc = 0.f;
+#pragma unroll
+            for (int j = 0; j < kDwMaxK; ++j) acc = fmaf(w[j], win[o + j], acc);
+            const float y = fmaxf(acc * sc + sh, 0.f);
+            if (t0 + o < t_end) x[((size_t)seg * T + t0 + o) * d + c0 + c] = xo[o] + (w2 * y + b2);
+        }
     }
 }
 
@@ -330,7 +465,6 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
     const int M = n_seg * T;
     const int Tp = (int)align_up(T, 32), ld2 = (int)align_up(2 * T - 1, 32);
     const int BH = n_seg * H;
-    const int ln_grid = ceil_div(M, 8);
     int rc;
 
     auto base_params = [&]() {
@@ -362,9 +496,8 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
     rc = linear(feat, feat_lo, ldf, Kf, h->g(G_EMB_W_HI), h->g(G_EMB_W_LO), h->g(G_EMB_B), d, EPI_STORE, 1.f, w.x, nullptr, d);
     if (rc) return rc;
     { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-    ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->g(G_EMB_LN_G), h->g(G_EMB_LN_B), 1, w.x, h->l(0, L_FFI_LN_G),
-                                     h->l(0, L_FFI_LN_B), w.h_hi, w.h_lo); }
-    if ((rc = check_launch("ln_kernel(embed)"))) return rc;
+    rc = ln_launch(w.x, M, d, h->g(G_EMB_LN_G), h->g(G_EMB_LN_B), 1, w.x, h->l(0, L_FFI_LN_G), h->l(0, L_FFI_LN_B), w.h_hi, w.h_lo, s); }
+    if (rc) return rc;
 
     const float inv_sqrt_dk = 1.f / sqrtf((float)d_k);
     for (int L = 0; L < D.n_blocks; ++L) {
@@ -376,9 +509,9 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                     w.x, nullptr, d);
         if (rc) return rc;
         // x += MHSA(x)                                                                         conformer.py:180
-        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr,
-                                         w.h_hi, w.h_lo); }
-        if ((rc = check_launch("ln_kernel(attn)"))) return rc;
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s);
+          rc = ln_launch(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, s); }
+        if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WQKV_HI), h->l(L, L_WQKV_LO), h->l(L, L_BQKV), 3 * d, EPI_QKV, 1.f, nullptr,
                     nullptr, 0);
         if (rc) return rc;
@@ -419,19 +552,21 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WO_HI), h->l(L, L_WO_LO), h->l(L, L_BO), d, EPI_RESID, 1.f, w.x, nullptr, d);
         if (rc) return rc;
         // x += Conv(x)                                                                         conformer.py:181
-        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_glu_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), h->l(L, L_CONV_SCALARS), w.u_hi); }
-        if ((rc = check_launch("ln_glu_kernel"))) return rc;
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s);
+          rc = ln_glu_launch(w.x, M, d, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), h->l(L, L_CONV_SCALARS), w.u_hi, s); }
+        if (rc) return rc;
         {
-            dim3 grid(ceil_div(T, kDwTT), ceil_div(d, kDwCC), n_seg);
-            const size_t smem = (size_t)(kDwTT + D.kernel_size - 1) * kDwCC * sizeof(float);
+            dim3 grid(ceil_div(d, kDwCh), n_seg);
+            const size_t smem = (size_t)(T + D.kernel_size - 1) * kDwCh * sizeof(float);
+            NSF_CUDA(cudaFuncSetAttribute(dwconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             { ProfScope prof(PROF_NET_OTHER, 0.0, s); dwconv_kernel<<<grid, 256, smem, s>>>(w.u_hi, w.x, T, d, D.kernel_size, h->l(L, L_DW_W), h->l(L, L_BN_SCALE),
                                                  h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS)); }
             if ((rc = check_launch("dwconv_kernel"))) return rc;
         }
         // x += 0.5 * FF_out(x)                                                                 conformer.py:182
-        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr,
-                                         w.h_hi, w.h_lo); }
-        if ((rc = check_launch("ln_kernel(ff_out)"))) return rc;
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s);
+          rc = ln_launch(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, s); }
+        if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_FFO_W1_HI), h->l(L, L_FFO_W1_LO), h->l(L, L_FFO_B1), dff, EPI_RELU_SPLIT,
                     1.f, w.u_hi, w.u_lo, dff);
         if (rc) return rc;
@@ -440,10 +575,10 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         if (rc) return rc;
         // x = LN(x) (conformer.py:184), fused with the next block's first LayerNorm (or the split for the mask head)
         const bool last = (L == D.n_blocks - 1);
-        { ProfScope prof(PROF_NET_OTHER, 0.0, s); ln_kernel<<<ln_grid, 256, 0, s>>>(w.x, M, d, h->l(L, L_OUT_LN_G), h->l(L, L_OUT_LN_B), 0, last ? nullptr : w.x,
-                                         last ? nullptr : h->l(L + 1, L_FFI_LN_G), last ? nullptr : h->l(L + 1, L_FFI_LN_B),
-                                         w.h_hi, w.h_lo); }
-        if ((rc = check_launch("ln_kernel(out)"))) return rc;
+        { ProfScope prof(PROF_NET_OTHER, 0.0, s);
+          rc = ln_launch(w.x, M, d, h->l(L, L_OUT_LN_G), h->l(L, L_OUT_LN_B), 0, last ? nullptr : w.x, last ? nullptr : h->l(L + 1, L_FFI_LN_G),
+                         last ? nullptr : h->l(L + 1, L_FFI_LN_B), w.h_hi, w.h_lo, s); }
+        if (rc) return rc;
     }
     // mask head: sigmoid(Linear), transposed into [seg][mask][F][T]                             conformer.py:302-309
     rc = linear(w.h_hi, w.h_lo, d, d, h->g(G_HEAD_W_HI), h->g(G_HEAD_W_LO), h->g(G_HEAD_B), D.n_out, EPI_MASK, 1.f, masks, nullptr, 0);

@@ -8,9 +8,10 @@
 //   get_bf     :78-80   y_i[f,t] = sum_c conj(W[f,c]) x[c,f,t]
 // and the floored-mask multiply of css/css.py:223-227.
 //
-// The whole bin lives on chip: the [T, 7] complex slab is staged once in shared memory (10.4 KB for
-// T = 186), the four covariance matrices are accumulated in fp64 by 28 lanes (one per upper-triangle
-// entry), the three 7x7 complex systems are solved by Gauss-Jordan with partial pivoting on 21 lanes
+// The whole bin lives on chip: the [T, 7] complex slab is staged once in shared memory, converted to fp64
+// on the way in (20.8 KB for T = 186; fp32 -> fp64 conversions are a slow pipe, so they are done once per
+// sample instead of once per covariance entry), the four covariance matrices are accumulated in fp64 by
+// 28 lanes (one per upper-triangle entry; only the winner-take-all winner of a frame gets its own update), the three 7x7 complex systems are solved by Gauss-Jordan with partial pivoting on 21 lanes
 // (one matrix row per lane, pivot rows broadcast by warp shuffles), and the beamformer is applied
 // from the staged slab.  fp64 because the noise covariances have condition numbers of 1e5..1e7
 // (the reference's own complex64 result is only ~1e-2 accurate there): parity is
@@ -35,8 +36,18 @@ __device__ __forceinline__ double2 zinv(double2 a) {
     return make_double2(a.x * d, -a.y * d);
 }
 
-struct MvdrWarpSmem {
-    // sizes depend on T; carved manually
+// per-warp shared-memory carve-up (bytes), all 16-byte aligned
+struct MvdrLayout {
+    size_t x_off, r_off, c_off, we_off, wm_off, total;
+    __host__ __device__ MvdrLayout(int T) {
+        size_t o = 0;
+        x_off = o;  o += (size_t)T * kMvdrC * sizeof(double2);                       // slab, already converted to fp64
+        r_off = o;  o += (size_t)(kMvdrS + 1) * kMvdrC * kMvdrC * sizeof(double2);   // the four covariance matrices
+        c_off = o;  o += (size_t)kMvdrS * 8 * sizeof(double2);                       // beamformer coefficients
+        we_off = o; o += (((size_t)T * sizeof(double)) + 15) & ~(size_t)15;          // winner weight - 1e-10 per frame
+        wm_off = o; o += (((size_t)T * sizeof(int)) + 15) & ~(size_t)15;             // winner bit mask per frame
+        total = o;
+    }
 };
 
 __global__ void __launch_bounds__(kMvdrWarps * 32)
@@ -50,30 +61,32 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
     const int seg = blockIdx.y;
     if (f >= n_bins) return;                 // warp-uniform; no block-level barriers below
 
-    // per-warp carve-up: weights (double4 per frame) | R matrices | W coefficients | x slab (float2)
-    const size_t w_bytes = (size_t)T * 4 * sizeof(double);
-    const size_t r_bytes = (size_t)(S + 1) * C * C * sizeof(double2);
-    const size_t c_bytes = (size_t)S * 8 * sizeof(double2);
-    const size_t x_bytes = (((size_t)T * C * sizeof(float2)) + 15) & ~(size_t)15;
-    const size_t per_warp = w_bytes + r_bytes + c_bytes + x_bytes;
-    unsigned char* base = smem_raw + (size_t)warp * per_warp;
-    double* wts = reinterpret_cast<double*>(base);                                   // [T][4]
-    double2* Rm = reinterpret_cast<double2*>(base + w_bytes);                        // [4][C][C]
-    double2* Wc = reinterpret_cast<double2*>(base + w_bytes + r_bytes);              // [S][8]
-    float2* xs = reinterpret_cast<float2*>(base + w_bytes + r_bytes + c_bytes);      // [T][C]
+    const MvdrLayout L(T);
+    unsigned char* base = smem_raw + (size_t)warp * L.total;
+    double2* xs = reinterpret_cast<double2*>(base + L.x_off);                        // [T][C]
+    double2* Rm = reinterpret_cast<double2*>(base + L.r_off);                        // [4][C][C]
+    double2* Wc = reinterpret_cast<double2*>(base + L.c_off);                        // [S][8]
+    double* wext = reinterpret_cast<double*>(base + L.we_off);                       // [T]
+    int* wmsk = reinterpret_cast<int*>(base + L.wm_off);                             // [T]
 
     const int64_t st = (seg_first + seg) * (int64_t)hop;
     const int n_ch_total = S + n_noise;
     const float* mseg = masks + ((size_t)seg * n_ch_total * n_bins + f) * T;        // + k * n_bins * T
     const size_t mstride = (size_t)n_bins * T;
 
-    // ---- A. stage the slab and the winner-take-all weights
+    // ---- A. stage the slab (converted to fp64 once) and the winner-take-all weights.
+    // make_wta keeps a mask where it equals the maximum over {speakers, summed noise} and puts 1e-10 elsewhere, so
+    //   R_k = sum_t w_k(t) P(t) = 1e-10 * sum_t P(t) + sum_{t: k wins} (m_k(t) - 1e-10) P(t),   P(t) = x(t) x(t)^H:
+    // per frame only the winner (ties: every mask equal to the maximum) needs its own accumulation.
     {
         const float2* Xf = X + ((size_t)f * T_long + st) * C;
         const int n = T * C;
         int64_t n_valid = (T_valid - st) * C;
         if (n_valid > n) n_valid = n;
-        for (int j = lane; j < n; j += 32) xs[j] = (j < n_valid) ? __ldg(Xf + j) : make_float2(0.f, 0.f);
+        for (int j = lane; j < n; j += 32) {
+            const float2 v = (j < n_valid) ? __ldg(Xf + j) : make_float2(0.f, 0.f);
+            xs[j] = make_double2((double)v.x, (double)v.y);
+        }
         for (int t = lane; t < T; t += 32) {
             float m[S + 1];
 #pragma unroll
@@ -84,8 +97,11 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
             float mx = m[0];
 #pragma unroll
             for (int k = 1; k <= S; ++k) mx = fmaxf(mx, m[k]);
+            int bits = 0;
 #pragma unroll
-            for (int k = 0; k <= S; ++k) wts[t * 4 + k] = (m[k] == mx) ? (double)m[k] : 1e-10;   // np.where(mask==mask_max, mask, 1e-10)
+            for (int k = 0; k <= S; ++k) bits |= (m[k] == mx) ? (1 << k) : 0;               // np.where(mask == mask_max, mask, 1e-10)
+            wext[t] = (double)mx - 1e-10;
+            wmsk[t] = bits;
         }
     }
     __syncwarp();
@@ -97,26 +113,29 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
         while (l >= rowlen) { l -= rowlen; ++ei; --rowlen; }
         ej = ei + l;
     }
-    double ar[S + 1], ai[S + 1];
-#pragma unroll
-    for (int k = 0; k <= S; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
     if (lane < 28) {
+        double ar[S + 1], ai[S + 1], tr = 0.0, ti = 0.0;
+#pragma unroll
+        for (int k = 0; k <= S; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+#pragma unroll 2
         for (int t = 0; t < T; ++t) {
-            const float2 xi = xs[t * C + ei], xj = xs[t * C + ej];
-            const double4 w = *reinterpret_cast<const double4*>(wts + t * 4);
-            const double xir = xi.x, xii = xi.y, xjr = xj.x, xji = xj.y;
-            const double pr = xir * xjr + xii * xji;         // x_i conj(x_j)
-            const double pi = xii * xjr - xir * xji;
-            ar[0] += w.x * pr; ai[0] += w.x * pi;
-            ar[1] += w.y * pr; ai[1] += w.y * pi;
-            ar[2] += w.z * pr; ai[2] += w.z * pi;
-            ar[3] += w.w * pr; ai[3] += w.w * pi;
+            const double2 xi = xs[t * C + ei], xj = xs[t * C + ej];
+            const double pr = xi.x * xj.x + xi.y * xj.y;         // x_i conj(x_j)
+            const double pi = xi.y * xj.x - xi.x * xj.y;
+            tr += pr; ti += pi;
+            const int bits = wmsk[t];                             // warp-uniform
+            const double we = wext[t];
+            if (bits & 1) { ar[0] += we * pr; ai[0] += we * pi; }
+            if (bits & 2) { ar[1] += we * pr; ai[1] += we * pi; }
+            if (bits & 4) { ar[2] += we * pr; ai[2] += we * pi; }
+            if (bits & 8) { ar[3] += we * pr; ai[3] += we * pi; }
         }
 #pragma unroll
         for (int k = 0; k <= S; ++k) {
-            if (ei == ej) { ar[k] += 1e-15; ai[k] = 0.0; }   // Ri += 1e-15 * I
-            Rm[(k * C + ei) * C + ej] = make_double2(ar[k], ai[k]);
-            if (ei != ej) Rm[(k * C + ej) * C + ei] = make_double2(ar[k], -ai[k]);
+            double rr = ar[k] + 1e-10 * tr, ri = ai[k] + 1e-10 * ti;
+            if (ei == ej) { rr += 1e-15; ri = 0.0; }             // Ri += 1e-15 * I
+            Rm[(k * C + ei) * C + ej] = make_double2(rr, ri);
+            if (ei != ej) Rm[(k * C + ej) * C + ei] = make_double2(rr, -ri);
         }
     }
     __syncwarp();
@@ -190,7 +209,7 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
         for (int s = 0; s < S; ++s) { yr[s] = 0.0; yi[s] = 0.0; }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const float2 x = xs[t * C + c];
+            const double2 x = xs[t * C + c];
             const double xr = x.x, xi = x.y;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
@@ -222,9 +241,7 @@ extern "C" int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float*
     NSF_REQUIRE(n_noise >= 1 && n_noise <= 4, "nsf_mvdr: n_noise=%d", n_noise);
     NSF_REQUIRE(T >= 1 && n_bins >= 1 && hop >= 1 && T_valid <= T_long, "nsf_mvdr: bad sizes");
     if (n_seg <= 0) return NSF_OK;
-    const size_t per_warp = (size_t)T * 4 * sizeof(double) + (size_t)(kMvdrS + 1) * kMvdrC * kMvdrC * sizeof(double2) +
-                            (size_t)kMvdrS * 8 * sizeof(double2) + ((((size_t)T * kMvdrC * sizeof(float2)) + 15) & ~(size_t)15);
-    const size_t smem = per_warp * kMvdrWarps;
+    const size_t smem = MvdrLayout(T).total * kMvdrWarps;
     if (smem > 220 * 1024) {
         set_error("nsf_mvdr: T=%d frames per covariance does not fit on chip (long-utterance path not built yet)", T);
         return NSF_ERR_UNSUPPORTED;

@@ -1,0 +1,40 @@
+#!/usr/bin/env python
+"""BASELINE.json config 5: MVDR kernel sweep -- 257 bins x {1k ... 100k} frames x 7 mics as batches of 186-frame segments
+(the pipeline shape), achieved algorithmic GB/s (96 B per bin-frame) against the measured HBM copy bandwidth.
+Inputs follow SURVEY 8d: mix ~ CN(0,1) with a per-bin rank-1 + identity spatial structure, masks = softmax(3 N(0,1)).
+Run on a B200: python tools/bench_mvdr.py"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from notsofar_b200 import _cabi
+
+def main():
+    lib = _cabi.load()
+    dev = torch.device("cuda", 0)
+    peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
+        if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0}
+    T, hop, F, C, S = 186, 186, 257, 7, 3
+    g = torch.Generator(device=dev).manual_seed(0)
+    for frames in (1000, 3000, 10000, 30000, 100000):
+        n_seg = -(-frames // T)
+        T_long = n_seg * T
+        a = torch.randn(F, 1, C, 2, device=dev, generator=g)
+        s = torch.randn(F, T_long, 1, 2, device=dev, generator=g)
+        steer = torch.view_as_complex(a.contiguous()) * torch.view_as_complex(s.contiguous())
+        X = (steer + torch.view_as_complex(torch.randn(F, T_long, C, 2, device=dev, generator=g))).contiguous()
+        masks = torch.softmax(3 * torch.randn(n_seg, S + 1, F, T, device=dev, generator=g), dim=1).contiguous()
+        Y = torch.empty(n_seg, S, F, T, dtype=torch.complex64, device=dev)
+        for i in range(8):
+            if i == 3:
+                lib.nsf_prof_enable(1); _cabi.prof_collect()
+            _cabi.check(lib.nsf_mvdr(_cabi.ptr(masks), S, 1, _cabi.ptr(X), T_long, T_long, C, 0, n_seg, T, hop, F, 1.0, _cabi.ptr(Y),
+                                     _cabi.stream_ptr()), "nsf_mvdr")
+        prof = _cabi.prof_collect(); lib.nsf_prof_enable(0)
+        ms, work, cnt = prof["mvdr"]
+        gbs = work / (ms * 1e-3) / 1e9
+        print(json.dumps({"frames": frames, "segments": n_seg, "us_per_launch": ms / cnt * 1e3, "GB/s": gbs,
+                          "frac_of_measured_hbm": gbs / peaks["hbm_gbs"]}), flush=True)
+
+if __name__ == "__main__":
+    main()
