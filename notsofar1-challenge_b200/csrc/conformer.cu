@@ -265,9 +265,9 @@ static int ln_glu_launch(const float* x, int M, int d, const float* g, const flo
 // conv module back: depthwise conv over time (zero padded inside the segment), BN (folded), ReLU, scalar affine,
 // residual add.                                                                     conformer.py:118-126, 181
 // One CTA stages a whole segment of 64 channels in shared memory (coalesced float4 rows); each thread then slides a
-// 48-value register window down its channel and produces 16 outputs per window (33 taps from registers).
-constexpr int kDwCh = 64, kDwOut = 16, kDwMaxK = 33;
-__global__ void __launch_bounds__(256)
+// 40-value register window down its channel and produces 8 outputs per window (33 taps from registers).
+constexpr int kDwCh = 64, kDwOut = 8, kDwMaxK = 33;
+__global__ void __launch_bounds__(256, 2)
 dwconv_kernel(const float* __restrict__ u, float* __restrict__ x, int T, int d, int ks, const float* __restrict__ dw_w,
               const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const float* __restrict__ scalars) {
     extern __shared__ __align__(16) float tile[];     // [T + ks - 1][kDwCh], row r <-> frame r - pad

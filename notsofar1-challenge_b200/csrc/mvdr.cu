@@ -8,10 +8,10 @@
 //   get_bf     :78-80   y_i[f,t] = sum_c conj(W[f,c]) x[c,f,t]
 // and the floored-mask multiply of css/css.py:223-227.
 //
-// The whole bin lives on chip: the [T, 7] complex slab is staged once in shared memory, converted to fp64
-// on the way in (20.8 KB for T = 186; fp32 -> fp64 conversions are a slow pipe, so they are done once per
-// sample instead of once per covariance entry), the four covariance matrices are accumulated in fp64 by
-// 28 lanes (one per upper-triangle entry; only the winner-take-all winner of a frame gets its own update), the three 7x7 complex systems are solved by Gauss-Jordan with partial pivoting on 21 lanes
+// The [T, 7] complex slab of a bin streams through shared memory 32 frames at a time, converted to fp64 on the
+// way in (fp32 -> fp64 conversions are a slow pipe, so they are done once per sample instead of once per
+// covariance entry), the four covariance matrices are accumulated in fp64 by 28 lanes (one per upper-triangle
+// entry; only the winner-take-all winner of a frame gets its own update), the three 7x7 complex systems are solved by Gauss-Jordan with partial pivoting on 21 lanes
 // (one matrix row per lane, pivot rows broadcast by warp shuffles), and the beamformer is applied
 // from the staged slab.  fp64 because the noise covariances have condition numbers of 1e5..1e7
 // (the reference's own complex64 result is only ~1e-2 accurate there): parity is
@@ -36,18 +36,15 @@ __device__ __forceinline__ double2 zinv(double2 a) {
     return make_double2(a.x * d, -a.y * d);
 }
 
-// per-warp shared-memory carve-up (bytes), all 16-byte aligned
-struct MvdrLayout {
-    size_t x_off, r_off, c_off, we_off, wm_off, total;
-    __host__ __device__ MvdrLayout(int T) {
-        size_t o = 0;
-        x_off = o;  o += (size_t)T * kMvdrC * sizeof(double2);                       // slab, already converted to fp64
-        r_off = o;  o += (size_t)(kMvdrS + 1) * kMvdrC * kMvdrC * sizeof(double2);   // the four covariance matrices
-        c_off = o;  o += (size_t)kMvdrS * 8 * sizeof(double2);                       // beamformer coefficients
-        we_off = o; o += (((size_t)T * sizeof(double)) + 15) & ~(size_t)15;          // winner weight - 1e-10 per frame
-        wm_off = o; o += (((size_t)T * sizeof(int)) + 15) & ~(size_t)15;             // winner bit mask per frame
-        total = o;
-    }
+// per-warp shared memory: one 32-frame chunk of the slab in fp64 + its winner-take-all weights, the four covariance
+// matrices and the beamformer coefficients (7.5 KB, independent of T: occupancy is set by registers, not by T)
+constexpr int kMvdrChunk = 32;
+struct MvdrWarpSmem {
+    double2 xs[kMvdrChunk * kMvdrC];                     // chunk of the slab, converted to fp64 once per sample
+    double wext[kMvdrChunk];                             // winner weight - 1e-10 per frame
+    int wmsk[kMvdrChunk];                                // winner bit mask per frame
+    double2 Rm[(kMvdrS + 1) * kMvdrC * kMvdrC];          // covariance matrices
+    double2 Wc[kMvdrS * 8];                              // beamformer coefficients
 };
 
 __global__ void __launch_bounds__(kMvdrWarps * 32)
@@ -55,90 +52,103 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
             int64_t T_valid, int64_t seg_first, int T, int hop, int n_bins, float mask_floor,
             float2* __restrict__ Y) {
     constexpr int C = kMvdrC, S = kMvdrS;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ __align__(16) MvdrWarpSmem smem_all[kMvdrWarps];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * kMvdrWarps + warp;
     const int seg = blockIdx.y;
     if (f >= n_bins) return;                 // warp-uniform; no block-level barriers below
-
-    const MvdrLayout L(T);
-    unsigned char* base = smem_raw + (size_t)warp * L.total;
-    double2* xs = reinterpret_cast<double2*>(base + L.x_off);                        // [T][C]
-    double2* Rm = reinterpret_cast<double2*>(base + L.r_off);                        // [4][C][C]
-    double2* Wc = reinterpret_cast<double2*>(base + L.c_off);                        // [S][8]
-    double* wext = reinterpret_cast<double*>(base + L.we_off);                       // [T]
-    int* wmsk = reinterpret_cast<int*>(base + L.wm_off);                             // [T]
+    MvdrWarpSmem& sm = smem_all[warp];
 
     const int64_t st = (seg_first + seg) * (int64_t)hop;
     const int n_ch_total = S + n_noise;
     const float* mseg = masks + ((size_t)seg * n_ch_total * n_bins + f) * T;        // + k * n_bins * T
     const size_t mstride = (size_t)n_bins * T;
+    const float2* Xf = X + ((size_t)f * T_long + st) * C;                            // [T][C] slab of this (segment, bin)
+    int64_t n_valid64 = (T_valid - st) * C;                                          // samples beyond are the zero padding
+    const int n_valid = (int)(n_valid64 < 0 ? 0 : (n_valid64 > (int64_t)T * C ? (int64_t)T * C : n_valid64));
 
-    // ---- A. stage the slab (converted to fp64 once) and the winner-take-all weights.
+    // ---- A + B. covariance accumulation, 32 frames at a time.
     // make_wta keeps a mask where it equals the maximum over {speakers, summed noise} and puts 1e-10 elsewhere, so
     //   R_k = sum_t w_k(t) P(t) = 1e-10 * sum_t P(t) + sum_{t: k wins} (m_k(t) - 1e-10) P(t),   P(t) = x(t) x(t)^H:
     // per frame only the winner (ties: every mask equal to the maximum) needs its own accumulation.
-    {
-        const float2* Xf = X + ((size_t)f * T_long + st) * C;
-        const int n = T * C;
-        int64_t n_valid = (T_valid - st) * C;
-        if (n_valid > n) n_valid = n;
-        for (int j = lane; j < n; j += 32) {
-            const float2 v = (j < n_valid) ? __ldg(Xf + j) : make_float2(0.f, 0.f);
-            xs[j] = make_double2((double)v.x, (double)v.y);
-        }
-        for (int t = lane; t < T; t += 32) {
-            float m[S + 1];
-#pragma unroll
-            for (int k = 0; k < S; ++k) m[k] = __ldg(mseg + k * mstride + t);
-            float nz = 0.f;
-            for (int k = 0; k < n_noise; ++k) nz += __ldg(mseg + (S + k) * mstride + t);   // noise_masks.sum(axis=0)
-            m[S] = nz;
-            float mx = m[0];
-#pragma unroll
-            for (int k = 1; k <= S; ++k) mx = fmaxf(mx, m[k]);
-            int bits = 0;
-#pragma unroll
-            for (int k = 0; k <= S; ++k) bits |= (m[k] == mx) ? (1 << k) : 0;               // np.where(mask == mask_max, mask, 1e-10)
-            wext[t] = (double)mx - 1e-10;
-            wmsk[t] = bits;
-        }
-    }
-    __syncwarp();
-
-    // ---- B. covariance accumulation: lane l < 28 owns upper-triangle entry (i, j), i <= j
+    // Lane l < 28 owns upper-triangle entry (i, j), i <= j.  The next chunk's samples and masks are fetched into
+    // registers while the current chunk is being accumulated.
     int ei = 0, ej = 0;
     {
         int l = lane < 28 ? lane : 0, rowlen = C;
         while (l >= rowlen) { l -= rowlen; ++ei; --rowlen; }
         ej = ei + l;
     }
-    if (lane < 28) {
-        double ar[S + 1], ai[S + 1], tr = 0.0, ti = 0.0;
+    double ar[S + 1], ai[S + 1], tr = 0.0, ti = 0.0;
 #pragma unroll
-        for (int k = 0; k <= S; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
-#pragma unroll 2
-        for (int t = 0; t < T; ++t) {
-            const double2 xi = xs[t * C + ei], xj = xs[t * C + ej];
-            const double pr = xi.x * xj.x + xi.y * xj.y;         // x_i conj(x_j)
-            const double pi = xi.y * xj.x - xi.x * xj.y;
-            tr += pr; ti += pi;
-            const int bits = wmsk[t];                             // warp-uniform
-            const double we = wext[t];
-            if (bits & 1) { ar[0] += we * pr; ai[0] += we * pi; }
-            if (bits & 2) { ar[1] += we * pr; ai[1] += we * pi; }
-            if (bits & 4) { ar[2] += we * pr; ai[2] += we * pi; }
-            if (bits & 8) { ar[3] += we * pr; ai[3] += we * pi; }
+    for (int k = 0; k <= S; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
+
+    float2 px[C];          // prefetched samples: element lane + 32 q of the chunk's [32][C] block
+    float pm[S + 1];       // prefetched masks of frame t0 + lane (noise already summed)
+    auto prefetch = [&](int t0) {
+#pragma unroll
+        for (int q = 0; q < C; ++q) {
+            const int j = t0 * C + q * 32 + lane;
+            px[q] = (j < n_valid && (q * 32 + lane) < kMvdrChunk * C) ? __ldg(Xf + j) : make_float2(0.f, 0.f);
         }
+        const int t = t0 + lane;
+#pragma unroll
+        for (int k = 0; k <= S; ++k) pm[k] = 0.f;
+        if (t < T) {
+#pragma unroll
+            for (int k = 0; k < S; ++k) pm[k] = __ldg(mseg + k * mstride + t);
+            float nz = 0.f;
+            for (int k = 0; k < n_noise; ++k) nz += __ldg(mseg + (S + k) * mstride + t);   // noise_masks.sum(axis=0)
+            pm[S] = nz;
+        }
+    };
+    prefetch(0);
+    for (int t0 = 0; t0 < T; t0 += kMvdrChunk) {
+        // stage the prefetched chunk
+#pragma unroll
+        for (int q = 0; q < C; ++q) sm.xs[q * 32 + lane] = make_double2((double)px[q].x, (double)px[q].y);
+        {
+            float mx = pm[0];
+#pragma unroll
+            for (int k = 1; k <= S; ++k) mx = fmaxf(mx, pm[k]);
+            int bits = 0;
+#pragma unroll
+            for (int k = 0; k <= S; ++k) bits |= (pm[k] == mx) ? (1 << k) : 0;               // np.where(mask == mask_max, mask, 1e-10)
+            sm.wext[lane] = (double)mx - 1e-10;
+            sm.wmsk[lane] = bits;
+        }
+        __syncwarp();
+        if (t0 + kMvdrChunk < T) prefetch(t0 + kMvdrChunk);
+        const int nt = min(kMvdrChunk, T - t0);
+        if (lane < 28) {
+#pragma unroll 4
+            for (int t = 0; t < nt; ++t) {
+                const double2 xi = sm.xs[t * C + ei], xj = sm.xs[t * C + ej];
+                const double pr = xi.x * xj.x + xi.y * xj.y;         // x_i conj(x_j)
+                const double pi = xi.y * xj.x - xi.x * xj.y;
+                tr += pr; ti += pi;
+                const int bits = sm.wmsk[t];                          // warp-uniform
+                const double we = sm.wext[t];
+                if (bits & 1) { ar[0] += we * pr; ai[0] += we * pi; }
+                if (bits & 2) { ar[1] += we * pr; ai[1] += we * pi; }
+                if (bits & 4) { ar[2] += we * pr; ai[2] += we * pi; }
+                if (bits & 8) { ar[3] += we * pr; ai[3] += we * pi; }
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 28) {
 #pragma unroll
         for (int k = 0; k <= S; ++k) {
             double rr = ar[k] + 1e-10 * tr, ri = ai[k] + 1e-10 * ti;
             if (ei == ej) { rr += 1e-15; ri = 0.0; }             // Ri += 1e-15 * I
-            Rm[(k * C + ei) * C + ej] = make_double2(rr, ri);
-            if (ei != ej) Rm[(k * C + ej) * C + ei] = make_double2(rr, -ri);
+            sm.Rm[(k * C + ei) * C + ej] = make_double2(rr, ri);
+            if (ei != ej) sm.Rm[(k * C + ej) * C + ei] = make_double2(rr, -ri);
         }
     }
     __syncwarp();
+    double2* Rm = sm.Rm;
+    double2* Wc = sm.Wc;
 
     // ---- C. three Gauss-Jordan solves, lane = (speaker s = lane / 8, row r = lane % 8)
     {
@@ -202,20 +212,25 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
     }
     __syncwarp();
 
-    // ---- D. apply: y_s[t] = sum_c conj(W_s[c]) x_c[t], then the floored-mask multiply (css.py:223-227)
+    // ---- D. apply: y_s[t] = sum_c conj(W_s[c]) x_c[t], then the floored-mask multiply (css.py:223-227).
+    // The slab is read a second time (L2-resident: it was fetched microseconds ago), one frame per lane.
+    double2 wc[S][C];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int c = 0; c < C; ++c) wc[s][c] = Wc[s * 8 + c];
     for (int t = lane; t < T; t += 32) {
         double yr[S], yi[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) { yr[s] = 0.0; yi[s] = 0.0; }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-            const double2 x = xs[t * C + c];
+            const float2 x = (t * C + c < n_valid) ? __ldg(Xf + t * C + c) : make_float2(0.f, 0.f);
             const double xr = x.x, xi = x.y;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                const double2 w = Wc[s * 8 + c];
-                yr[s] += w.x * xr + w.y * xi;
-                yi[s] += w.x * xi - w.y * xr;
+                yr[s] += wc[s][c].x * xr + wc[s][c].y * xi;
+                yi[s] += wc[s][c].x * xi - wc[s][c].y * xr;
             }
         }
 #pragma unroll
@@ -241,16 +256,10 @@ extern "C" int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float*
     NSF_REQUIRE(n_noise >= 1 && n_noise <= 4, "nsf_mvdr: n_noise=%d", n_noise);
     NSF_REQUIRE(T >= 1 && n_bins >= 1 && hop >= 1 && T_valid <= T_long, "nsf_mvdr: bad sizes");
     if (n_seg <= 0) return NSF_OK;
-    const size_t smem = MvdrLayout(T).total * kMvdrWarps;
-    if (smem > 220 * 1024) {
-        set_error("nsf_mvdr: T=%d frames per covariance does not fit on chip (long-utterance path not built yet)", T);
-        return NSF_ERR_UNSUPPORTED;
-    }
-    NSF_CUDA(cudaFuncSetAttribute(mvdr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(n_bins, kMvdrWarps), n_seg);
     // algorithmic bytes: 7*8 mix + (S+Nn)*4 masks + S*8 out per (bin, frame)  (96 B for S = 3, Nn = 1)
     ProfScope prof(PROF_MVDR, (double)n_seg * n_bins * T * (kMvdrC * 8.0 + (kMvdrS + n_noise) * 4.0 + kMvdrS * 8.0), (cudaStream_t)stream);
-    mvdr_kernel<<<grid, kMvdrWarps * 32, smem, (cudaStream_t)stream>>>(masks, n_noise, reinterpret_cast<const float2*>(X), T_long,
+    mvdr_kernel<<<grid, kMvdrWarps * 32, 0, (cudaStream_t)stream>>>(masks, n_noise, reinterpret_cast<const float2*>(X), T_long,
                                                                       T_valid, seg_first, T, hop, n_bins, mask_floor,
                                                                       reinterpret_cast<float2*>(Y));
     return check_launch("mvdr_kernel");
