@@ -137,6 +137,28 @@ def permutation_chain(costs: np.ndarray) -> np.ndarray:
     return perms
 
 
+def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batch: int = 128):
+    """Chunks of segments the mask network / MVDR run on: [(first segment, count), ...].
+
+    Large, equal chunks keep the persistent GEMMs' last wave full (a 128 x 256 tile grid over 148 SMs quantises badly for
+    small M); when the audio is still streaming in from the host the first chunk is kept short so that compute starts
+    after the first few MB have landed."""
+    max_batch = max(1, max_batch)
+    out, s0 = [], 0
+    if streaming and n_seg > first_batch and max_batch > first_batch:
+        out.append((0, first_batch))
+        s0 = first_batch
+    rest = n_seg - s0
+    if rest > 0:
+        parts = -(-rest // max_batch)
+        base, extra = divmod(rest, parts)
+        for i in range(parts):
+            nb = base + (1 if i < extra else 0)
+            out.append((s0, nb))
+            s0 += nb
+    return out
+
+
 def _segment_weights(plan: SegmentPlan):
     """seg_w [n_seg, T] and its overlap-added sum wg_stitched [mix_frames] exactly as css.py:258-259,288-291
     accumulate them (float32, ascending segment order)."""
@@ -237,9 +259,7 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
         n_masks = separator.num_masks
         masks = torch.empty((n_seg, n_masks, NUM_BINS, T), dtype=torch.float32, device=device)
         Y = torch.empty((n_seg, S, NUM_BINS, T), dtype=torch.complex64, device=device)
-        B = max(1, int(separator.segments_per_batch))
-        for s0 in range(0, n_seg, B):
-            nb = min(B, n_seg - s0)
+        for s0, nb in plan_batches(n_seg, int(separator.segments_per_batch), streaming=feeder is not None):
             # STFT of the frames this chunk of segments needs (and, when streaming from the host, only once they landed)
             f_need = min(T_valid, (s0 + nb - 1) * hop + T)
             if f_need > frames_done:
@@ -319,7 +339,8 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
         x_host = speech_mix[0] if isinstance(speech_mix, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(speech_mix[0], dtype=np.float32))
         x_host = x_host.to(torch.float32).contiguous()
         plan0 = plan_segments(x_host.shape[0], fs, cfg)
-        chunk = max(1, int(separator.segments_per_batch)) * plan0.hop_frames * FRAME_HOP
+        # copy granularity: the first (short) chunk of segments, so that the STFT of chunk 0 can start early
+        chunk = min(128, max(1, int(separator.segments_per_batch))) * plan0.hop_frames * FRAME_HOP
         with torch.cuda.device(device):
             x = HostFeeder(x_host, device, chunk)
     out = css_device(x, separator, fs, cfg)
