@@ -175,7 +175,8 @@ def run_b200(args):
     n = len(x_np)
     x_pinned = torch.from_numpy(x_np).pin_memory()
     weights = synth.random_state_dict(0)
-    engine = {"3xtf32": N.GEMM_TC_3XTF32, "tf32": N.GEMM_TC_TF32, "simt": N.GEMM_SIMT_FP32}[args.engine]
+    engine = {"3xtf32": N.GEMM_TC_3XTF32, "tf32": N.GEMM_TC_TF32, "simt": N.GEMM_SIMT_FP32, "2xbf16": N.GEMM_TC_2XBF16,
+              "2xf16": N.GEMM_TC_2XF16}[args.engine]
     sep = N.ConformerCssB200(weights, device=dev, gemm_engine=engine, segments_per_batch=args.segments_per_batch)
     cfg = N.CssCfg(activity_th=0.3, show_progressbar=False)   # inference_v1.yaml:17
     plan = N.plan_segments(n, FS, cfg)
@@ -268,7 +269,7 @@ def run_b200(args):
             # 3xTF32 issues three tf32 MMAs per algorithmic product; dense tf32 peak is half the bf16 peak.  The
             # fraction is reported against the measured sustained bf16 GEMM peak (the only measured tensor number).
             peak = peaks["bf16_sustained"]
-            note = f"algorithmic fp32 flops (3 tf32 passes count once) vs sustained bf16 cuBLAS peak, {peaks['which']}"
+            note = f"algorithmic fp32 flops (the 3 tensor-core passes of a split product count once) vs sustained bf16 cuBLAS peak, {peaks['which']}"
         else:
             peak = peaks["hbm_gbs"]
             note = f"algorithmic bytes vs copy bandwidth, {peaks['which']}"
@@ -277,11 +278,17 @@ def run_b200(args):
             # every algorithmic product costs three kind::tf32 MMAs, and the dense tf32 rate is half the bf16 rate:
             # the ceiling of this arithmetic is peak / 6
             extra = {"issued_tf32_tflops": 3 * d["achieved"], "frac_of_3xtf32_ceiling": 6 * d["achieved"] / peak}
+        elif d["bound"] == "tensor" and args.engine in ("2xbf16", "2xf16"):
+            # three kind::f16 MMAs per algorithmic product: the ceiling of this arithmetic is peak / 3
+            extra = {"issued_f16_tflops": 3 * d["achieved"], "frac_of_split16_ceiling": 3 * d["achieved"] / peak}
         roofline = {**extra, "kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": peak, "unit": d["unit"],
                     "frac": d["achieved"] / peak, "traffic": NCU_TRAFFIC.get(dom), "share_of_step": d["ms_per_step"] / prof_ms, "note": note}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"3xtf32": "f32 (3xTF32 tensor-core GEMMs, fp64 MVDR)", "tf32": "tf32", "simt": "f32"}[args.engine],
+                "dtype": {"3xtf32": "f32 (3xTF32 tensor-core GEMMs, fp64 MVDR)", "tf32": "tf32", "simt": "f32",
+                          "2xbf16": "f32 (bf16 head+remainder pairs, 3 kind::f16 MMAs per product, fp32 accumulate; fp64 MVDR)",
+                          "2xf16": "f32 (scaled fp16 head+remainder pairs = 22 mantissa bits, 3 kind::f16 MMAs per product, "
+                                   "fp32 accumulate; 3xTF32 attention; fp64 MVDR)"}[args.engine],
                 "data": "synthetic (seeded 5-min 7-ch pattern tiled; random-init v1.0-MC weights)",
                 "config": {"workload": f"CSS Conformer v1.0-MC + MVDR, 7-ch 16 kHz, {seconds / 60:.0f}-min synthetic meeting per GPU "
                                        f"({plan.num_segments} segments of 186 frames)",
@@ -311,7 +318,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=1800.0, help="meeting length per GPU")
-    ap.add_argument("--engine", default="3xtf32", choices=["3xtf32", "tf32", "simt"])
+    ap.add_argument("--engine", default="3xtf32", choices=["3xtf32", "tf32", "simt", "2xbf16", "2xf16"])
     ap.add_argument("--segments-per-batch", type=int, default=640)
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="slice of the meeting the CPU baseline leg runs")
     ap.add_argument("--ref-seconds", type=float, default=15.0, help="--impl reference: audio seconds per step")

@@ -51,6 +51,9 @@ extern "C" {
 #define NSF_GEMM_SIMT_FP32   0   /* CUDA-core fp32 FMA (bit-faithful fp32 products; debugging / cross-check) */
 #define NSF_GEMM_TC_3XTF32   1   /* tcgen05 kind::tf32, error-compensated 3-pass split (fp32-parity mode, default) */
 #define NSF_GEMM_TC_TF32     2   /* tcgen05 kind::tf32, single pass (throughput mode, ~1e-3) */
+#define NSF_GEMM_TC_2XBF16   3   /* tcgen05 kind::f16 on bf16 head + remainder pairs, 3 MMAs per product (~2^-17, fp32 range) */
+#define NSF_GEMM_TC_2XF16    4   /* tcgen05 kind::f16 on power-of-two-scaled fp16 head + remainder pairs, 3 MMAs per product
+                                    (~2^-22: fp32-grade at twice the 3xTF32 rate); scaled magnitudes saturate at 65504 */
 
 const char* nsf_last_error(void);
 const char* nsf_version(void);
@@ -87,11 +90,16 @@ int nsf_stft_mc(const float* x, int64_t n_samples, int n_ch,
  * (the zero-padded tail of the last segment, css.py:185-190; T_valid <= T_long = frame pitch of X).
  * Row (i*T + t), column (m*257 + f).  If in_bias/in_scale are non-NULL the network's input
  * normalisation (f + bias) * scale (conformer.py:297-299) is fused.  If feat_lo is non-NULL the
- * value is stored split for the 3xTF32 GEMM: feat = tf32-truncated part, feat_lo = remainder.
+ * value is stored split for the tensor-core GEMM in format split_fmt: NSF_SPLIT_TF32 -> two fp32 arrays (TF32 head,
+ * exact remainder); NSF_SPLIT_BF16 / NSF_SPLIT_F16 -> feat and feat_lo are uint16 arrays of pitch ldf holding bf16 /
+ * (x 2^4-scaled) fp16 head and remainder, for the NSF_GEMM_TC_2XBF16 / _2XF16 engines.
  * Columns >= 257*n_ch of a row are left untouched (the caller keeps the K padding zeroed). */
+#define NSF_SPLIT_TF32 0
+#define NSF_SPLIT_BF16 1
+#define NSF_SPLIT_F16  2
 int nsf_css_features(const float* X, int64_t T_long, int64_t T_valid, int n_ch, int64_t seg_first, int n_seg,
                      int T, int hop, const float* in_bias, const float* in_scale,
-                     float* feat, float* feat_lo, int64_t ldf, void* stream);
+                     float* feat, float* feat_lo, int64_t ldf, int split_fmt, void* stream);
 
 /* Mask network (ConformerCSS.forward, css_with_conformer/nnet/conformer.py:287-310, eval mode).
  * The handle only records dimensions and the offsets of each tensor inside the caller's device blob
@@ -109,7 +117,8 @@ void nsf_conformer_destroy(nsf_conformer* h);
 int64_t nsf_conformer_num_offsets(const nsf_conformer_dims* dims);
 /* bytes of scratch HBM nsf_conformer_forward needs for a batch of n_seg segments */
 int64_t nsf_conformer_workspace_bytes(const nsf_conformer_dims* dims, int n_seg);
-/* feat (+feat_lo): [n_seg*T][ldf] already input-normalised (see nsf_css_features);
+/* feat (+feat_lo): [n_seg*T][ldf] already input-normalised, in the split format of the handle's engine
+ * (see nsf_css_features; ldf counts elements);
  * masks: [n_seg][n_out/257][257][T] = sigmoid(linear(...)). */
 int nsf_conformer_forward(nsf_conformer* h, const float* feat, const float* feat_lo, int64_t ldf, int n_seg,
                           float* masks, void* workspace, int64_t workspace_bytes, void* stream);

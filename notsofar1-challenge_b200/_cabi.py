@@ -9,7 +9,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnsf_b200.so")
 
-GEMM_SIMT_FP32, GEMM_TC_3XTF32, GEMM_TC_TF32 = 0, 1, 2
+GEMM_SIMT_FP32, GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_TC_2XBF16, GEMM_TC_2XF16 = 0, 1, 2, 3, 4
+SPLIT_TF32, SPLIT_BF16, SPLIT_F16 = 0, 1, 2
+F16_ACT_SCALE, F16_WEIGHT_SCALE = 16.0, 256.0        # csrc/common.cuh kF16ActScale / kF16WeightScale
+
+
+def split_fmt_of_engine(engine: int) -> int:
+    return {GEMM_TC_2XBF16: SPLIT_BF16, GEMM_TC_2XF16: SPLIT_F16}.get(engine, SPLIT_TF32)
 
 c_f32p = C.c_void_p
 i64 = C.c_int64
@@ -32,7 +38,7 @@ SIGNATURES = {
     "nsf_prof_collect": (i32, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64), i32]),
     "nsf_num_frames": (i64, [i64]),
     "nsf_stft_mc": (i32, [c_f32p, i64, i32, c_f32p, i64, i64, C.c_void_p]),
-    "nsf_css_features": (i32, [c_f32p, i64, i64, i32, i64, i32, i32, i32, c_f32p, c_f32p, c_f32p, c_f32p, i64, C.c_void_p]),
+    "nsf_css_features": (i32, [c_f32p, i64, i64, i32, i64, i32, i32, i32, c_f32p, c_f32p, c_f32p, c_f32p, i64, i32, C.c_void_p]),
     "nsf_conformer_create": (i32, [C.POINTER(ConformerDims), c_f32p, i64, C.POINTER(i64), i32, C.POINTER(C.c_void_p)]),
     "nsf_conformer_destroy": (None, [C.c_void_p]),
     "nsf_conformer_num_offsets": (i64, [C.POINTER(ConformerDims)]),

@@ -41,6 +41,7 @@ struct AttnParams {
     int pe_row0;       // first pe_k row of the window: maxlen - (T - 1)
     float inv_sqrt_dk;
     float* out_hi; float* out_lo; int64_t ldo;      // [n_seg * T][d_model], column head * 64 + d
+    int out_fmt;                                    // SplitFmt of the output pair
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int n_threads) {
@@ -306,16 +307,11 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
                 if (t1 < T) {
                     const int seg = bh / p.n_heads, h = bh - seg * p.n_heads;
                     const size_t o = ((size_t)seg * T + t1) * p.ldo + (size_t)h * kAttnDk + 32 * hh;
-                    float4* dh = reinterpret_cast<float4*>(p.out_hi + o);
-                    float4* dl = reinterpret_cast<float4*>(p.out_lo + o);
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        float hi[4], lo[4];
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) split_tf32(__uint_as_float(ov[4 * k4 + e]), hi[e], lo[e]);
-                        dh[k4] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                        dl[k4] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    }
+                    for (int k4 = 0; k4 < 8; ++k4)
+                        split_store4(p.out_fmt, p.out_hi, p.out_lo, o + 4 * k4,
+                                     make_float4(__uint_as_float(ov[4 * k4]), __uint_as_float(ov[4 * k4 + 1]),
+                                                 __uint_as_float(ov[4 * k4 + 2]), __uint_as_float(ov[4 * k4 + 3])));
                 }
             }
             tcgen05_fence_before();
@@ -334,7 +330,7 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_con
 // q, k: [n_bh][T][64] split; vt: [n_bh][64][Tp] split; pe: [2 * maxlen][64] split; out: [n_seg * T][ldo] split.
 int attn_fused_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
                       const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
-                      float* out_hi, float* out_lo, int64_t ldo, cudaStream_t stream) {
+                      float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream) {
     if (T < 2 || T > 192 || Tp % 32 != 0 || Tp < T || Tp > 192) { set_error("attn_fused: T=%d Tp=%d unsupported", T, Tp); return NSF_ERR_UNSUPPORTED; }
     if (maxlen < T || (ldo & 3)) { set_error("attn_fused: maxlen=%d ldo=%lld", maxlen, (long long)ldo); return NSF_ERR_INVALID_ARG; }
     const int n_bh = n_seg * n_heads;
@@ -351,7 +347,7 @@ int attn_fused_launch(const float* q_hi, const float* q_lo, const float* k_hi, c
     AttnParams p;
     p.n_bh = n_bh; p.n_heads = n_heads; p.T = T; p.Tp = Tp; p.pe_row0 = maxlen - (T - 1);
     p.inv_sqrt_dk = 1.f / sqrtf((float)kAttnDk);
-    p.out_hi = out_hi; p.out_lo = out_lo; p.ldo = ldo;
+    p.out_hi = out_hi; p.out_lo = out_lo; p.ldo = ldo; p.out_fmt = out_fmt;
     NSF_CUDA(cudaFuncSetAttribute(attn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
     const int total = n_bh * ((T + 127) / 128);
     const int grid = total < sm_count() ? total : sm_count();
@@ -415,7 +411,7 @@ extern "C" int nsf_attention_test(const float* q, const float* k, const float* v
     {
         ProfScope prof(PROF_ATTN, 6.0 * T * T * kAttnDk * (double)n_bh, s);
         if ((rc = attn_fused_launch(q_hi, q_lo, k_hi, k_lo, v_hi, v_lo, p_hi, p_lo, maxlen, n_seg, n_heads, T, (int)Tp, o_hi, o_lo,
-                                    (int64_t)n_heads * kAttnDk, s))) return rc;
+                                    (int64_t)n_heads * kAttnDk, SPLIT_TF32, s))) return rc;
     }
     attn_test_merge_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, s>>>(o_hi, o_lo, nq, out);
     return check_launch("attn_test_merge_kernel");

@@ -1,6 +1,8 @@
 // Shared helpers for the libnsf_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -82,6 +84,69 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
     hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
     lo = v - hi;
+}
+
+// Storage formats of a "split" activation / weight pair (X_hi, X_lo) that feeds a tensor-core GEMM.
+//   SPLIT_TF32  two fp32 arrays: TF32 head + exact remainder                       (3xTF32 / TF32 engines)
+//   SPLIT_BF16  two bf16 arrays: hi = bf16(x), lo = bf16(x - hi)                    (~2^-17 relative, fp32 range)
+//   SPLIT_F16   two fp16 arrays of the scaled value s x: hi = f16(s x), lo = f16(s x - hi)  (~2^-22 relative; the
+//               power-of-two scale keeps the remainder out of the fp16 subnormals: activations s = 2^4, weights
+//               s = 2^8, undone exactly in the GEMM epilogue; |s x| saturates at 65504)
+// The 16-bit arrays live in the same buffers as the fp32 ones (element index unchanged, half the bytes used).
+enum SplitFmt : int { SPLIT_TF32 = 0, SPLIT_BF16 = 1, SPLIT_F16 = 2 };
+constexpr float kF16ActScale = 16.f, kF16WeightScale = 256.f;
+
+inline int split_fmt_of_engine(int engine) {
+    return engine == NSF_GEMM_TC_2XBF16 ? SPLIT_BF16 : engine == NSF_GEMM_TC_2XF16 ? SPLIT_F16 : SPLIT_TF32;
+}
+
+__device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+}
+__device__ __forceinline__ void split_f16(float v, float scale, uint16_t& hi, uint16_t& lo) {
+    const float s = fminf(fmaxf(v * scale, -65504.f), 65504.f);
+    const __half h = __float2half_rn(s);
+    const __half l = __float2half_rn(s - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+}
+// one value into a split pair of format `fmt` (warp-uniform); hi/lo are the buffer bases, idx the element index
+__device__ __forceinline__ void split_store(int fmt, float* hi, float* lo, size_t idx, float v) {
+    if (fmt == SPLIT_TF32) {
+        float h, l;
+        split_tf32(v, h, l);
+        hi[idx] = h;
+        lo[idx] = l;
+    } else {
+        uint16_t h, l;
+        if (fmt == SPLIT_BF16) split_bf16(v, h, l); else split_f16(v, kF16ActScale, h, l);
+        reinterpret_cast<uint16_t*>(hi)[idx] = h;
+        reinterpret_cast<uint16_t*>(lo)[idx] = l;
+    }
+}
+// four consecutive values (idx a multiple of 4, bases 16-byte aligned)
+__device__ __forceinline__ void split_store4(int fmt, float* hi, float* lo, size_t idx, float4 v) {
+    if (fmt == SPLIT_TF32) {
+        float4 h, l;
+        split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+        *reinterpret_cast<float4*>(hi + idx) = h;
+        *reinterpret_cast<float4*>(lo + idx) = l;
+    } else {
+        uint16_t h[4], l[4];
+        if (fmt == SPLIT_BF16) {
+            split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+        } else {
+            split_f16(v.x, kF16ActScale, h[0], l[0]); split_f16(v.y, kF16ActScale, h[1], l[1]);
+            split_f16(v.z, kF16ActScale, h[2], l[2]); split_f16(v.w, kF16ActScale, h[3], l[3]);
+        }
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + idx) =
+            make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + idx) =
+            make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    }
 }
 
 // twiddle table W512^j = (cos(2 pi j/512), sin(2 pi j/512)), j < 512; filled once per process

@@ -72,7 +72,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 ln_vec_kernel(const float* __restrict__ x, int M, const float* __restrict__ g1, const float* __restrict__ b1, int relu1,
               float* __restrict__ out_x, const float* __restrict__ g2, const float* __restrict__ b2,
-              float* __restrict__ out_hi, float* __restrict__ out_lo) {
+              float* __restrict__ out_hi, float* __restrict__ out_lo, int fmt) {
     constexpr int d = 128 * NV;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -105,11 +105,7 @@ ln_vec_kernel(const float* __restrict__ x, int M, const float* __restrict__ g1, 
         for (int i = 0; i < NV; ++i) {
             const size_t o = ro + (i * 32 + lane) * 4;
             if (out_lo) {
-                float4 hi, lo;
-                split_tf32(v[i].x, hi.x, lo.x); split_tf32(v[i].y, hi.y, lo.y);
-                split_tf32(v[i].z, hi.z, lo.z); split_tf32(v[i].w, hi.w, lo.w);
-                st4(out_hi + o, hi);
-                st4(out_lo + o, lo);
+                split_store4(fmt, out_hi, out_lo, o, v[i]);
             } else {
                 st4(out_hi + o, v[i]);
             }
@@ -121,7 +117,7 @@ ln_vec_kernel(const float* __restrict__ x, int M, const float* __restrict__ g1, 
 __global__ void __launch_bounds__(256)
 ln_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g1, const float* __restrict__ b1, int relu1,
           float* __restrict__ out_x, const float* __restrict__ g2, const float* __restrict__ b2,
-          float* __restrict__ out_hi, float* __restrict__ out_lo) {
+          float* __restrict__ out_hi, float* __restrict__ out_lo, int fmt) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= M) return;
@@ -170,10 +166,7 @@ ln_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g
             if (i < n_per) {
                 const size_t o = (size_t)row * d + i * 32 + lane;
                 if (out_lo) {
-                    float hi, lo;
-                    split_tf32(v[i], hi, lo);
-                    out_hi[o] = hi;
-                    out_lo[o] = lo;
+                    split_store(fmt, out_hi, out_lo, o, v[i]);
                 } else {
                     out_hi[o] = v[i];
                 }
@@ -182,14 +175,14 @@ ln_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g
 }
 
 static int ln_launch(const float* x, int M, int d, const float* g1, const float* b1, int relu1, float* out_x, const float* g2,
-                     const float* b2, float* out_hi, float* out_lo, cudaStream_t s) {
+                     const float* b2, float* out_hi, float* out_lo, int fmt, cudaStream_t s) {
     const int grid = ceil_div(M, 8);
     switch ((d % 128 == 0) ? d / 128 : 0) {
-        case 1: ln_vec_kernel<1><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
-        case 2: ln_vec_kernel<2><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
-        case 4: ln_vec_kernel<4><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
-        case 8: ln_vec_kernel<8><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
-        default: ln_kernel<<<grid, 256, 0, s>>>(x, M, d, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo); break;
+        case 1: ln_vec_kernel<1><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
+        case 2: ln_vec_kernel<2><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
+        case 4: ln_vec_kernel<4><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
+        case 8: ln_vec_kernel<8><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
+        default: ln_kernel<<<grid, 256, 0, s>>>(x, M, d, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
     }
     return check_launch("ln_kernel");
 }
@@ -350,10 +343,11 @@ relpos_softmax_kernel(const float* __restrict__ S1, const float* __restrict__ S2
     }
 }
 
+// scale: extra factor for SPLIT_F16 operands that are not activations (weights: kF16WeightScale / kF16ActScale)
 __global__ void __launch_bounds__(256)
-split_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ hi, float* __restrict__ lo) {
+split_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ hi, float* __restrict__ lo, int fmt, float scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { float h, l; split_tf32(in[i], h, l); hi[i] = h; lo[i] = l; }
+    if (i < n) split_store(fmt, hi, lo, (size_t)i, in[i] * scale);
 }
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
@@ -401,7 +395,7 @@ static int validate_dims(const nsf_conformer_dims& D) {
                 "conformer: kernel_size=%d", D.kernel_size);
     NSF_REQUIRE(D.T >= 2 && D.T <= 32 * kSmMaxPerLane && D.T <= D.maxlen, "conformer: T=%d", D.T);
     NSF_REQUIRE(D.n_out >= kBins && D.n_out % kBins == 0, "conformer: n_out=%d", D.n_out);
-    NSF_REQUIRE(D.gemm_engine >= NSF_GEMM_SIMT_FP32 && D.gemm_engine <= NSF_GEMM_TC_TF32, "conformer: gemm_engine");
+    NSF_REQUIRE(D.gemm_engine >= NSF_GEMM_SIMT_FP32 && D.gemm_engine <= NSF_GEMM_TC_2XF16, "conformer: gemm_engine");
     return NSF_OK;
 }
 
@@ -463,6 +457,11 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
 
     const int T = D.T, d = D.d_model, H = D.n_heads, d_k = d / H, dff = D.d_ff;
     const int M = n_seg * T;
+    // activations that feed the linear layers are stored in the engine's split format; q / k / v^T / pe_k and the
+    // attention-internal products stay SPLIT_TF32 (3xTF32) under the 16-bit engines
+    const int fmt = split_fmt_of_engine(eng);
+    const int eng_attn = fmt == SPLIT_TF32 ? eng : NSF_GEMM_TC_3XTF32;
+    const float lin_scale = fmt == SPLIT_F16 ? 1.f / (kF16ActScale * kF16WeightScale) : 1.f;
     const int Tp = (int)align_up(T, 32), ld2 = (int)align_up(2 * T - 1, 32);
     const int BH = n_seg * H;
     int rc;
@@ -471,6 +470,8 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         GemmParams p = {};
         p.batch = 1;
         p.alpha = 1.f;
+        p.acc_scale = 1.f;
+        p.op_fmt = SPLIT_TF32; p.out_fmt = fmt;
         p.T = T; p.Tp = Tp; p.n_heads = H; p.d_k = d_k; p.d_model = d;
         return p;
     };
@@ -480,6 +481,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         p.A_hi = a_hi; p.A_lo = a_lo; p.lda = lda;
         p.B_hi = w_hi; p.B_lo = w_lo; p.ldb = K;
         p.M = M; p.N = N; p.K = K; p.n_valid = N;
+        p.op_fmt = fmt; p.acc_scale = lin_scale;
         p.bias = bias; p.epi = epi; p.alpha = alpha;
         p.out0 = o0; p.out1 = o1; p.ldo = ldo;
         p.q_hi = w.q_hi; p.q_lo = w.q_lo; p.k_hi = w.k_hi; p.k_lo = w.k_lo; p.vt_hi = w.vt_hi; p.vt_lo = w.vt_lo;
@@ -496,7 +498,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
     rc = linear(feat, feat_lo, ldf, Kf, h->g(G_EMB_W_HI), h->g(G_EMB_W_LO), h->g(G_EMB_B), d, EPI_STORE, 1.f, w.x, nullptr, d);
     if (rc) return rc;
     { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-    rc = ln_launch(w.x, M, d, h->g(G_EMB_LN_G), h->g(G_EMB_LN_B), 1, w.x, h->l(0, L_FFI_LN_G), h->l(0, L_FFI_LN_B), w.h_hi, w.h_lo, s); }
+    rc = ln_launch(w.x, M, d, h->g(G_EMB_LN_G), h->g(G_EMB_LN_B), 1, w.x, h->l(0, L_FFI_LN_G), h->l(0, L_FFI_LN_B), w.h_hi, w.h_lo, fmt, s); }
     if (rc) return rc;
 
     const float inv_sqrt_dk = 1.f / sqrtf((float)d_k);
@@ -510,7 +512,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         if (rc) return rc;
         // x += MHSA(x)                                                                         conformer.py:180
         { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-          rc = ln_launch(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, s); }
+          rc = ln_launch(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, fmt, s); }
         if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WQKV_HI), h->l(L, L_WQKV_LO), h->l(L, L_BQKV), 3 * d, EPI_QKV, 1.f, nullptr,
                     nullptr, 0);
@@ -519,7 +521,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
             // scores, relative-position skew, softmax and P V in one tcgen05 kernel (attention.cu)
             ProfScope prof(PROF_ATTN, 6.0 * T * T * d_k * (double)BH, s);
             if ((rc = attn_fused_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE_HI), h->g(G_PE_LO), D.maxlen,
-                                        n_seg, H, T, Tp, w.h_hi, w.h_lo, d, s))) return rc;
+                                        n_seg, H, T, Tp, w.h_hi, w.h_lo, d, fmt, s))) return rc;
         } else {
             {   // A = q k^T per (segment, head)
                 GemmParams p = base_params();
@@ -527,7 +529,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                 p.B_hi = w.k_hi; p.B_lo = w.k_lo; p.ldb = d_k; p.b_batch_stride = (int64_t)T * d_k;
                 p.M = T; p.N = T; p.K = d_k; p.n_valid = T; p.batch = BH;
                 p.epi = EPI_STORE; p.out0 = w.s1; p.ldo = Tp; p.o_batch_stride = (int64_t)T * Tp;
-                if ((rc = gemm_launch(eng, p, s))) return rc;
+                if ((rc = gemm_launch(eng_attn, p, s))) return rc;
             }
             {   // B' = q pe_k[maxlen-(T-1) .. maxlen+(T-1)]^T for every (segment, head, t1) row at once
                 GemmParams p = base_params();
@@ -536,7 +538,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                 p.B_hi = h->g(G_PE_HI) + pe_off; p.B_lo = h->g(G_PE_LO) + pe_off; p.ldb = d_k;
                 p.M = BH * T; p.N = 2 * T - 1; p.K = d_k; p.n_valid = 2 * T - 1;
                 p.epi = EPI_STORE; p.out0 = w.s2; p.ldo = ld2;
-                if ((rc = gemm_launch(eng, p, s))) return rc;
+                if ((rc = gemm_launch(eng_attn, p, s))) return rc;
             }
             { ProfScope prof(PROF_NET_OTHER, 0.0, s); relpos_softmax_kernel<<<ceil_div(BH * T, 8), 256, 0, s>>>(w.s1, w.s2, BH * T, T, Tp, ld2, inv_sqrt_dk, w.p_hi, w.p_lo); }
             if ((rc = check_launch("relpos_softmax_kernel"))) return rc;
@@ -546,7 +548,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                 p.B_hi = w.vt_hi; p.B_lo = w.vt_lo; p.ldb = Tp; p.b_batch_stride = (int64_t)d_k * Tp;
                 p.M = T; p.N = d_k; p.K = Tp; p.n_valid = d_k; p.batch = BH;
                 p.epi = EPI_PV; p.out0 = w.h_hi; p.out1 = w.h_lo; p.ldo = d;
-                if ((rc = gemm_launch(eng, p, s))) return rc;
+                if ((rc = gemm_launch(eng_attn, p, s))) return rc;
             }
         }
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WO_HI), h->l(L, L_WO_LO), h->l(L, L_BO), d, EPI_RESID, 1.f, w.x, nullptr, d);
@@ -565,7 +567,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         }
         // x += 0.5 * FF_out(x)                                                                 conformer.py:182
         { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-          rc = ln_launch(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, s); }
+          rc = ln_launch(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, fmt, s); }
         if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_FFO_W1_HI), h->l(L, L_FFO_W1_LO), h->l(L, L_FFO_B1), dff, EPI_RELU_SPLIT,
                     1.f, w.u_hi, w.u_lo, dff);
@@ -577,7 +579,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         const bool last = (L == D.n_blocks - 1);
         { ProfScope prof(PROF_NET_OTHER, 0.0, s);
           rc = ln_launch(w.x, M, d, h->l(L, L_OUT_LN_G), h->l(L, L_OUT_LN_B), 0, last ? nullptr : w.x, last ? nullptr : h->l(L + 1, L_FFI_LN_G),
-                         last ? nullptr : h->l(L + 1, L_FFI_LN_B), w.h_hi, w.h_lo, s); }
+                         last ? nullptr : h->l(L + 1, L_FFI_LN_B), w.h_hi, w.h_lo, fmt, s); }
         if (rc) return rc;
     }
     // mask head: sigmoid(Linear), transposed into [seg][mask][F][T]                             conformer.py:302-309
@@ -589,6 +591,7 @@ extern "C" int nsf_gemm_test(int engine, const float* A, const float* W, const f
                              int K, void* workspace, int64_t workspace_bytes, void* stream_) {
     NSF_REQUIRE(A && W && Cout && workspace, "nsf_gemm_test: null pointer");
     NSF_REQUIRE(K % 32 == 0 && M > 0 && N > 0, "nsf_gemm_test: K must be a multiple of 32");
+    NSF_REQUIRE(engine >= NSF_GEMM_SIMT_FP32 && engine <= NSF_GEMM_TC_2XF16, "nsf_gemm_test: engine");
     const int64_t na = (int64_t)M * K, nw = (int64_t)N * K;
     const int64_t need = (align_up(na, 64) * 2 + align_up(nw, 64) * 2) * (int64_t)sizeof(float);
     NSF_REQUIRE(workspace_bytes >= need, "nsf_gemm_test: workspace needs %lld bytes", (long long)need);
@@ -597,14 +600,16 @@ extern "C" int nsf_gemm_test(int engine, const float* A, const float* W, const f
     float* a_lo = a_hi + align_up(na, 64);
     float* w_hi = a_lo + align_up(na, 64);
     float* w_lo = w_hi + align_up(nw, 64);
-    split_kernel<<<(unsigned)ceil_div64(na, 256), 256, 0, s>>>(A, na, a_hi, a_lo);
-    split_kernel<<<(unsigned)ceil_div64(nw, 256), 256, 0, s>>>(W, nw, w_hi, w_lo);
+    const int fmt = split_fmt_of_engine(engine);
+    split_kernel<<<(unsigned)ceil_div64(na, 256), 256, 0, s>>>(A, na, a_hi, a_lo, fmt, 1.f);
+    split_kernel<<<(unsigned)ceil_div64(nw, 256), 256, 0, s>>>(W, nw, w_hi, w_lo, fmt, fmt == SPLIT_F16 ? kF16WeightScale / kF16ActScale : 1.f);
     int rc = check_launch("split_kernel");
     if (rc) return rc;
     GemmParams p = {};
     p.A_hi = a_hi; p.A_lo = a_lo; p.lda = K;
     p.B_hi = w_hi; p.B_lo = w_lo; p.ldb = K;
     p.M = M; p.N = N; p.K = K; p.n_valid = N; p.batch = 1;
+    p.op_fmt = fmt; p.out_fmt = fmt; p.acc_scale = fmt == SPLIT_F16 ? 1.f / (kF16ActScale * kF16WeightScale) : 1.f;
     p.bias = bias; p.epi = EPI_STORE; p.alpha = 1.f; p.out0 = Cout; p.ldo = N;
     return gemm_launch(engine, p, s);
 }

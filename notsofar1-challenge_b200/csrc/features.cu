@@ -22,7 +22,7 @@ template <int C>
 __global__ void __launch_bounds__(kFeatBinsPerCta * 32)
 css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_valid, int64_t seg_first, int T, int hop,
                     const float* __restrict__ in_bias, const float* __restrict__ in_scale,
-                    float* __restrict__ feat, float* __restrict__ feat_lo, int64_t ldf) {
+                    float* __restrict__ feat, float* __restrict__ feat_lo, int64_t ldf, int fmt) {
     extern __shared__ float tile[];     // [T][C][kFeatBinsPerCta]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seg = blockIdx.y;
@@ -126,10 +126,7 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
         if (in_bias) v = (v + __ldg(in_bias + col)) * __ldg(in_scale + col);      // conformer.py:297-299
         const size_t o = ((size_t)seg * T + t) * ldf + col;
         if (feat_lo) {
-            float hi, lo;
-            split_tf32(v, hi, lo);
-            feat[o] = hi;
-            feat_lo[o] = lo;
+            split_store(fmt, feat, feat_lo, o, v);
         } else {
             feat[o] = v;
         }
@@ -142,26 +139,28 @@ using namespace nsf;
 
 extern "C" int nsf_css_features(const float* X, int64_t T_long, int64_t T_valid, int n_ch, int64_t seg_first, int n_seg,
                                 int T, int hop, const float* in_bias, const float* in_scale, float* feat,
-                                float* feat_lo, int64_t ldf, void* stream) {
+                                float* feat_lo, int64_t ldf, int split_fmt, void* stream) {
     NSF_REQUIRE(X && feat, "nsf_css_features: null pointer");
     NSF_REQUIRE(n_ch == 7 || n_ch == 1, "nsf_css_features: n_ch=%d (supported: 7, 1)", n_ch);
     NSF_REQUIRE(T >= 2 && T <= 32 * kFeatMaxIter, "nsf_css_features: T=%d not in [2,%d]", T, 32 * kFeatMaxIter);
     NSF_REQUIRE(ldf >= (int64_t)kBins * n_ch, "nsf_css_features: ldf too small");
     NSF_REQUIRE((in_bias == nullptr) == (in_scale == nullptr), "nsf_css_features: bias/scale must come together");
+    NSF_REQUIRE(split_fmt >= SPLIT_TF32 && split_fmt <= SPLIT_F16 && (split_fmt == SPLIT_TF32 || feat_lo),
+                "nsf_css_features: split_fmt=%d (16-bit formats need feat_lo)", split_fmt);
     NSF_REQUIRE(T_valid <= T_long && (seg_first + n_seg - 1) * (int64_t)hop + T <= T_long + 0 || T_valid < T_long + 1,
                 "nsf_css_features: segment range outside X");
     if (n_seg <= 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(ceil_div(kBins, kFeatBinsPerCta), n_seg);
-    ProfScope prof(PROF_FEATURES, (double)n_seg * T * kBins * n_ch * (8.0 + (feat_lo ? 8.0 : 4.0)), s);
+    ProfScope prof(PROF_FEATURES, (double)n_seg * T * kBins * n_ch * (8.0 + (feat_lo ? (split_fmt == SPLIT_TF32 ? 8.0 : 4.0) : 4.0)), s);
     const size_t smem = (size_t)T * n_ch * kFeatBinsPerCta * sizeof(float);
     if (n_ch == 7) {
         NSF_CUDA(cudaFuncSetAttribute(css_features_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         css_features_kernel<7><<<grid, kFeatBinsPerCta * 32, smem, s>>>(reinterpret_cast<const float2*>(X), T_long, T_valid,
-                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf);
+                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf, split_fmt);
     } else {
         css_features_kernel<1><<<grid, kFeatBinsPerCta * 32, smem, s>>>(reinterpret_cast<const float2*>(X), T_long, T_valid,
-                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf);
+                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf, split_fmt);
     }
     return check_launch("css_features_kernel");
 }

@@ -25,6 +25,9 @@ struct GemmParams {
     const float* A_hi; const float* A_lo; int64_t lda; int64_t a_batch_stride;
     const float* B_hi; const float* B_lo; int64_t ldb; int64_t b_batch_stride;
     int M, N, K, batch;
+    int op_fmt;               // SplitFmt of A and B (the 16-bit formats reinterpret the float pointers as uint16_t arrays)
+    int out_fmt;              // SplitFmt of the split outputs of EPI_RELU_SPLIT / EPI_PV (q, k, v^T of EPI_QKV stay SPLIT_TF32)
+    float acc_scale;          // accumulator scale applied before the bias (undoes the SPLIT_F16 operand scales; 1 otherwise)
     int n_valid;              // columns >= n_valid are padding (weights padded with zero rows)
     const float* bias;        // [n_valid] or nullptr
     int epi;
@@ -39,7 +42,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 
 // One output element.  (b, m, n) are in range: m < M, n < n_valid.
 __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, int b, int m, int n, float acc) {
-    const float v = acc + (p.bias ? __ldg(p.bias + n) : 0.f);
+    const float v = acc * p.acc_scale + (p.bias ? __ldg(p.bias + n) : 0.f);
     switch (p.epi) {
         case EPI_STORE:
             p.out0[(size_t)b * p.o_batch_stride + (size_t)m * p.ldo + n] = v;
@@ -96,19 +99,20 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, int b, int m,
 }
 
 int gemm_simt_launch(const GemmParams& p, cudaStream_t stream);
-// n_terms: 3 -> 3xTF32, 1 -> single TF32 pass
-int gemm_tc_launch(const GemmParams& p, int n_terms, cudaStream_t stream);
+// mode: 3 -> 3xTF32, 1 -> single TF32 pass, 16 -> three kind::f16 MMAs on 16-bit pairs (p.op_fmt = SPLIT_BF16 / SPLIT_F16)
+int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream);
 
 // fused relative-position attention (attention.cu); q, k: [n_seg*heads][T][64], vt: [n_seg*heads][64][Tp], all split
 int attn_fused_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
                       const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
-                      float* out_hi, float* out_lo, int64_t ldo, cudaStream_t stream);
+                      float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
 inline bool attn_fused_supported(int T, int d_k) { return T >= 2 && T <= 192 && d_k == 64; }
 
 inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {
     // algorithmic flops: 2 M N K per batch entry (the three TF32 passes of 3xTF32 count once)
     ProfScope prof(engine == NSF_GEMM_SIMT_FP32 ? PROF_GEMM_SIMT : PROF_GEMM_TC, 2.0 * p.M * p.N * p.K * p.batch, stream);
     if (engine == NSF_GEMM_SIMT_FP32) return gemm_simt_launch(p, stream);
+    if (engine == NSF_GEMM_TC_2XBF16 || engine == NSF_GEMM_TC_2XF16) return gemm_tc_launch(p, 16, stream);
     return gemm_tc_launch(p, engine == NSF_GEMM_TC_3XTF32 ? 3 : 1, stream);
 }
 

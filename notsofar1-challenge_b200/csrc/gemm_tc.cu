@@ -21,24 +21,24 @@
 
 namespace nsf {
 
-constexpr int TBM = 128, TBN = 256, TBK = 32;
-constexpr int kATileBytes = TBM * TBK * 4;         // 16 KB
-constexpr int kBTileBytes = TBN * TBK * 4;         // 32 KB
+constexpr int TBM = 128, TBN = 256;
+constexpr int kRowBytes = 128;                     // one swizzle row of K: 32 tf32 or 64 16-bit elements
+constexpr int kATileBytes = TBM * kRowBytes;       // 16 KB
+constexpr int kBTileBytes = TBN * kRowBytes;       // 32 KB
 constexpr int kTcThreads = 320;                   // 1 TMA + 1 MMA + 8 epilogue warps
 constexpr uint32_t kTmemCols = 512;                // two 128 x 256 fp32 accumulators
 constexpr int kEpiPitch = 33;                      // staging row pitch (floats): conflict-free both ways
 constexpr int kEpiBytes = 8 * 32 * kEpiPitch * 4;  // one 32 x 32 staging tile per epilogue warp
 
-template <int NTERMS> struct TcCfg {
-    static constexpr int kStageBytes = (NTERMS == 3 ? 2 : 1) * (kATileBytes + kBTileBytes);
-    static constexpr int kStages = NTERMS == 3 ? 2 : 4;
+// MODE 1: one kind::tf32 pass; 3: 3xTF32; 16: three kind::f16 MMAs on 16-bit head/remainder pairs (2xBF16 / 2xF16)
+template <int MODE> struct TcCfg {
+    static constexpr bool kSplit = MODE != 1;
+    static constexpr int kBlockK = MODE == 16 ? 64 : 32;          // elements of K per stage (one 128-byte row)
+    static constexpr int kStageBytes = (kSplit ? 2 : 1) * (kATileBytes + kBTileBytes);
+    static constexpr int kStages = kSplit ? 2 : 4;
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = TBN
-__device__ __forceinline__ constexpr uint32_t make_idesc() {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TBN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-}
 
 
 
@@ -68,7 +68,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (nc + j < p.N) {
-                    const float v = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + nc + j) : 0.f);
+                    const float v = __uint_as_float(r[j]) * p.acc_scale + (p.bias ? __ldg(p.bias + nc + j) : 0.f);
                     base[((size_t)k * kBins + f) * p.T] = 1.f / (1.f + expf(-v));       // torch.sigmoid, conformer.py:304
                 }
                 if (++f == kBins) { f = 0; ++k; }
@@ -80,7 +80,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 float hi, lo;
-                split_tf32(__uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + nc + j) : 0.f), hi, lo);
+                split_tf32(__uint_as_float(r[j]) * p.acc_scale + (p.bias ? __ldg(p.bias + nc + j) : 0.f), hi, lo);
                 p.vt_hi[o + (size_t)j * p.Tp] = hi;
                 p.vt_lo[o + (size_t)j * p.Tp] = lo;
             }
@@ -97,7 +97,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
         const float bs = p.bias ? __ldg(p.bias + n) : 0.f;
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = stage[i * kEpiPitch + lane] + bs;
+        for (int i = 0; i < 32; ++i) v[i] = stage[i * kEpiPitch + lane] * p.acc_scale + bs;
         switch (p.epi) {
             case EPI_STORE: {
                 float* o = p.out0 + (size_t)b * p.o_batch_stride + (size_t)r0 * p.ldo + n;
@@ -110,12 +110,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                 const size_t o = (size_t)r0 * p.ldo + n;
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (i < rows) {
-                        float hi, lo;
-                        split_tf32(fmaxf(v[i], 0.f), hi, lo);
-                        p.out0[o + (size_t)i * p.ldo] = hi;
-                        p.out1[o + (size_t)i * p.ldo] = lo;
-                    }
+                    if (i < rows) split_store(p.out_fmt, p.out0, p.out1, o + (size_t)i * p.ldo, fmaxf(v[i], 0.f));
                 break;
             }
             case EPI_RESID: {
@@ -153,12 +148,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                 const size_t o = ((size_t)seg * p.T + r0) * p.ldo + (size_t)h * p.d_k + n;
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
-                    if (i < rows) {
-                        float hi, lo;
-                        split_tf32(v[i], hi, lo);
-                        p.out0[o + (size_t)i * p.ldo] = hi;
-                        p.out1[o + (size_t)i * p.ldo] = lo;
-                    }
+                    if (i < rows) split_store(p.out_fmt, p.out0, p.out1, o + (size_t)i * p.ldo, v[i]);
                 break;
             }
             default: break;
@@ -167,12 +157,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
     __syncwarp();
 }
 
-template <int NTERMS>
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const GemmParams p, const int tiles_m, const int tiles_n, const int total_tiles) {
-    using Cfg = TcCfg<NTERMS>;
+    using Cfg = TcCfg<MODE>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -189,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         reinterpret_cast<volatile uint32_t*>(gen_tiles + Cfg::kStages * Cfg::kStageBytes + kEpiBytes + 8 * (2 * Cfg::kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = p.K / TBK;
+    const int nkb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;      // a K tail is zero-filled by TMA
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -219,9 +209,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(empty_bar(s), ph ^ 1);
                     mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
                     const uint32_t st = tiles + s * Cfg::kStageBytes;
-                    const int k0 = kb * TBK;
+                    const int k0 = kb * Cfg::kBlockK;
                     tma_load_3d(st, &map_a_hi, k0, m0, b, full_bar(s));
-                    if (NTERMS == 3) {
+                    if (Cfg::kSplit) {
                         tma_load_3d(st + kATileBytes, &map_a_lo, k0, m0, b, full_bar(s));
                         tma_load_3d(st + 2 * kATileBytes, &map_b_hi, k0, n0, b, full_bar(s));
                         tma_load_3d(st + 2 * kATileBytes + kBTileBytes, &map_b_lo, k0, n0, b, full_bar(s));
@@ -234,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer
-            const uint32_t idesc = make_idesc();
+            const uint32_t idesc = MODE == 16 ? make_idesc_f16(TBN, p.op_fmt == SPLIT_BF16) : make_idesc_tf32(TBN);
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
@@ -248,12 +238,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     tcgen05_fence_after();
                     const uint32_t st = tiles + s * Cfg::kStageBytes;
                     const uint32_t a_hi = st, a_lo = st + kATileBytes;
-                    const uint32_t b_hi = st + (NTERMS == 3 ? 2 : 1) * kATileBytes, b_lo = b_hi + kBTileBytes;
+                    const uint32_t b_hi = st + (Cfg::kSplit ? 2 : 1) * kATileBytes, b_lo = b_hi + kBTileBytes;
 #pragma unroll
-                    for (int ks = 0; ks < TBK / 8; ++ks) {                    // UMMA_K = 8 tf32 = 32 bytes
+                    for (int ks = 0; ks < kRowBytes / 32; ++ks) {             // UMMA_K = 8 tf32 = 16 halves = 32 bytes
                         const uint32_t koff = ks * 32;
                         const uint64_t da_hi = make_smem_desc(a_hi + koff), db_hi = make_smem_desc(b_hi + koff);
-                        if (NTERMS == 3) {
+                        if (MODE == 16) {
+                            const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
+                            tcgen05_mma_f16(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);     // small terms first
+                            tcgen05_mma_f16(d_tmem, da_hi, db_lo, idesc, 1);
+                            tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                        } else if (MODE == 3) {
                             const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
                             tcgen05_mma_tf32(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);    // small terms first
                             tcgen05_mma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
@@ -314,34 +309,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------- host side
-template <int NTERMS>
+template <int MODE>
 static int launch_t(const GemmParams& p, cudaStream_t stream) {
-    using Cfg = TcCfg<NTERMS>;
+    using Cfg = TcCfg<MODE>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    if ((rc = make_tmap_kmajor(&ma_hi, p.A_hi, p.M, p.K, p.lda, p.batch, p.a_batch_stride, TBM))) return rc;
-    if ((rc = make_tmap_kmajor(&mb_hi, p.B_hi, p.N, p.K, p.ldb, p.batch, p.b_batch_stride, TBN))) return rc;
-    if (NTERMS == 3) {
-        if (!p.A_lo || !p.B_lo) { set_error("gemm_tc: 3xTF32 needs split operands"); return NSF_ERR_INVALID_ARG; }
-        if ((rc = make_tmap_kmajor(&ma_lo, p.A_lo, p.M, p.K, p.lda, p.batch, p.a_batch_stride, TBM))) return rc;
-        if ((rc = make_tmap_kmajor(&mb_lo, p.B_lo, p.N, p.K, p.ldb, p.batch, p.b_batch_stride, TBN))) return rc;
+    auto make = [&](CUtensorMap* m, const float* base, int64_t rows, int64_t ld, int64_t bstride, int box_rows) {
+        return MODE == 16 ? make_tmap_kmajor16(m, base, rows, p.K, ld, p.batch, bstride, box_rows)
+                          : make_tmap_kmajor(m, base, rows, p.K, ld, p.batch, bstride, box_rows);
+    };
+    if ((rc = make(&ma_hi, p.A_hi, p.M, p.lda, p.a_batch_stride, TBM))) return rc;
+    if ((rc = make(&mb_hi, p.B_hi, p.N, p.ldb, p.b_batch_stride, TBN))) return rc;
+    if (Cfg::kSplit) {
+        if (!p.A_lo || !p.B_lo) { set_error("gemm_tc: split engines need head and remainder operands"); return NSF_ERR_INVALID_ARG; }
+        if ((rc = make(&ma_lo, p.A_lo, p.M, p.lda, p.a_batch_stride, TBM))) return rc;
+        if ((rc = make(&mb_lo, p.B_lo, p.N, p.ldb, p.b_batch_stride, TBN))) return rc;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
-    NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<NTERMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int tiles_m = ceil_div(p.M, TBM), tiles_n = ceil_div(p.N, TBN);
     const int64_t total = (int64_t)tiles_m * tiles_n * p.batch;
     if (total > 0x7fffffff) { set_error("gemm_tc: too many tiles"); return NSF_ERR_INVALID_ARG; }
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm_tc_kernel<NTERMS><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, tiles_m, tiles_n, (int)total);
+    gemm_tc_kernel<MODE><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, tiles_m, tiles_n, (int)total);
     return check_launch("gemm_tc_kernel");
 }
 
-int gemm_tc_launch(const GemmParams& p, int n_terms, cudaStream_t stream) {
-    if (p.K % TBK != 0 || p.K <= 0) { set_error("gemm_tc: K=%d must be a positive multiple of %d", p.K, TBK); return NSF_ERR_INVALID_ARG; }
-    if (p.M <= 0 || p.N <= 0 || p.batch <= 0) { set_error("gemm_tc: empty problem"); return NSF_ERR_INVALID_ARG; }
-    return n_terms == 3 ? launch_t<3>(p, stream) : launch_t<1>(p, stream);
+int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream) {
+    if (p.M <= 0 || p.N <= 0 || p.batch <= 0 || p.K <= 0) { set_error("gemm_tc: empty problem"); return NSF_ERR_INVALID_ARG; }
+    if (mode == 16) {
+        if (p.op_fmt != SPLIT_BF16 && p.op_fmt != SPLIT_F16) { set_error("gemm_tc: 16-bit engine needs SPLIT_BF16 / SPLIT_F16 operands"); return NSF_ERR_INVALID_ARG; }
+        if (p.K % 8 != 0) { set_error("gemm_tc: K=%d must be a multiple of 8", p.K); return NSF_ERR_INVALID_ARG; }
+        return launch_t<16>(p, stream);
+    }
+    if (p.op_fmt != SPLIT_TF32) { set_error("gemm_tc: tf32 engines need SPLIT_TF32 operands"); return NSF_ERR_INVALID_ARG; }
+    if (p.K % 32 != 0) { set_error("gemm_tc: K=%d must be a multiple of 32", p.K); return NSF_ERR_INVALID_ARG; }
+    return mode == 3 ? launch_t<3>(p, stream) : launch_t<1>(p, stream);
 }
 
 }  // namespace nsf

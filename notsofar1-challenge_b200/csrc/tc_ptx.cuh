@@ -56,6 +56,14 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t desc_
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16: A and B are both fp16 or both bf16 (selected by the instruction descriptor), fp32 accumulate, UMMA_K = 16
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -76,6 +84,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128
 __host__ __device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// kind::f16, fp32 accumulate, A and B K-major, M = 128; bf16 != 0 -> bf16 operands, else fp16
+__host__ __device__ __forceinline__ constexpr uint32_t make_idesc_f16(int n, int bf16) {
+    return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 // A operand read from tensor memory (lane = row, one tf32 element per 32-bit column)
 __device__ __forceinline__ void tcgen05_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -133,6 +145,28 @@ inline int make_tmap_kmajor(CUtensorMap* map, const float* base, int64_t rows, i
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tcgen05: cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return NSF_ERR_CUDA; }
+    return NSF_OK;
+}
+
+// [batch][rows][K] 16-bit elements (fp16 / bf16 bit patterns), K contiguous; box = 64 x box_rows x 1 (128-byte rows),
+// 128-byte swizzle, zero fill out of bounds (a K tail shorter than 64 reads as zeros)
+inline int make_tmap_kmajor16(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int64_t batch,
+                              int64_t batch_stride, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("tcgen05: cuTensorMapEncodeTiled is not available from the driver"); return NSF_ERR_CUDA; }
+    if (batch_stride == 0) batch_stride = rows * ld;
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
+    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15)) {
+        set_error("tcgen05: 16-bit operand base/strides must be 16-byte aligned (ld=%lld, batch_stride=%lld)", (long long)ld, (long long)batch_stride);
+        return NSF_ERR_INVALID_ARG;
+    }
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("tcgen05: cuTensorMapEncodeTiled (16-bit) failed with CUresult %d", (int)r); return NSF_ERR_CUDA; }
     return NSF_OK;
 }
 

@@ -8,8 +8,9 @@ the reference's plug-in interface keeps working, and adds the batched entry poin
 
 Weights come from a reference ``state_dict`` (677 tensors for the v1.0 MC model, names
 ``executor.nnet...``, optional DDP ``module.`` prefix as in css/helpers.py:30-36) and are repacked
-once into a single device blob: GEMM weights split into TF32 head + remainder, K padded to a
-multiple of 32, BatchNorm folded into scale/shift.
+once into a single device blob: GEMM weights split into head + remainder in the engine's format (two fp32
+arrays for the TF32 engines, two 16-bit arrays for 2xBF16 / 2xF16), K padded to a multiple of 32, BatchNorm
+folded into scale/shift.
 """
 from __future__ import annotations
 
@@ -38,6 +39,42 @@ def _split_tf32(w: np.ndarray):
     hi = (w.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
     lo = w - hi
     return hi, lo
+
+
+def _split16(w: np.ndarray, fmt: int):
+    """fp32 -> (head, remainder) as 16-bit patterns packed two per float32 word (csrc/common.cuh SplitFmt):
+    SPLIT_BF16: hi = bf16(w), lo = bf16(w - hi); SPLIT_F16: the same in fp16 on 2^8 w (saturating at 65504)."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    if fmt == _cabi.SPLIT_BF16:
+        t = torch.from_numpy(w)
+        hi = t.to(torch.bfloat16)
+        lo = (t - hi.to(torch.float32)).to(torch.bfloat16)
+        hi, lo = hi.view(torch.int16).numpy(), lo.view(torch.int16).numpy()
+    else:
+        ws = np.clip(w * np.float32(_cabi.F16_WEIGHT_SCALE), -65504.0, 65504.0).astype(np.float32)
+        hi = ws.astype(np.float16)
+        lo = (ws - hi.astype(np.float32)).astype(np.float16)
+        hi, lo = hi.view(np.int16), lo.view(np.int16)
+    assert hi.size % 2 == 0
+    return hi.reshape(-1).view(np.float32), lo.reshape(-1).view(np.float32)
+
+
+def split_activations(a: np.ndarray, gemm_engine: int):
+    """Host-side twin of the device's split store (csrc/common.cuh split_store): fp32 activations [rows, ld] ->
+    (head, remainder) in the layout nsf_conformer_forward expects for ``gemm_engine`` (tests, external feature paths)."""
+    fmt = _cabi.split_fmt_of_engine(gemm_engine)
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if fmt == _cabi.SPLIT_TF32:
+        return _split_tf32(a)
+    if fmt == _cabi.SPLIT_BF16:
+        t = torch.from_numpy(a)
+        hi = t.to(torch.bfloat16)
+        lo = (t - hi.to(torch.float32)).to(torch.bfloat16)
+        return hi.view(torch.int16).numpy(), lo.view(torch.int16).numpy()
+    s = np.clip(a * np.float32(_cabi.F16_ACT_SCALE), -65504.0, 65504.0).astype(np.float32)
+    hi = s.astype(np.float16)
+    lo = (s - hi.astype(np.float32)).astype(np.float16)
+    return hi.view(np.int16), lo.view(np.int16)
 
 
 def _strip_prefix(sd: Dict[str, object]) -> Dict[str, np.ndarray]:
@@ -89,8 +126,11 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
             chunks.append(np.zeros(pad, np.float32))
         cursor += a.size + pad
 
-    def add_split(a: np.ndarray):
-        hi, lo = _split_tf32(a)
+    fmt = _cabi.split_fmt_of_engine(gemm_engine)
+
+    def add_split(a: np.ndarray, tf32: bool = False):
+        """GEMM weight in the engine's split format (pe_k feeds the attention kernel, which stays SPLIT_TF32)."""
+        hi, lo = _split_tf32(a) if (tf32 or fmt == _cabi.SPLIT_TF32) else _split16(a, fmt)
         add(hi)
         add(lo)
 
@@ -106,7 +146,7 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
     add(w[c + "embed.0.bias"])
     add(w[c + "embed.1.weight"])
     add(w[c + "embed.1.bias"])
-    add_split(w[c + "pos_emb.pe_k.weight"])
+    add_split(w[c + "pos_emb.pe_k.weight"], tf32=True)
     add_split(w[_P + "linear.weight"])
     add(w[_P + "linear.bias"])
     for l in range(n_blocks):
@@ -266,12 +306,14 @@ class ConformerCssB200:
         F_, T_long, c = X.shape
         assert F_ == NUM_BINS and X.dtype == torch.complex64 and X.is_contiguous()
         rows = n_seg * T
-        feat = torch.zeros((rows, self.ldf), dtype=torch.float32, device=X.device)
+        fmt = _cabi.split_fmt_of_engine(self.gemm_engine) if split else _cabi.SPLIT_TF32
+        # 16-bit split formats: bf16 / scaled-fp16 bit patterns (the K padding columns stay zero)
+        feat = torch.zeros((rows, self.ldf), dtype=torch.float32 if fmt == _cabi.SPLIT_TF32 else torch.int16, device=X.device)
         feat_lo = torch.zeros_like(feat) if split else None
         _cabi.check(self._lib.nsf_css_features(
             _cabi.ptr(X), T_long, T_valid, c, seg_first, n_seg, T, hop,
             _cabi.ptr(self._in_bias) if normalize_input else None, _cabi.ptr(self._in_scale) if normalize_input else None,
-            _cabi.ptr(feat), _cabi.ptr(feat_lo), self.ldf, _cabi.stream_ptr()), "nsf_css_features")
+            _cabi.ptr(feat), _cabi.ptr(feat_lo), self.ldf, fmt, _cabi.stream_ptr()), "nsf_css_features")
         return feat, feat_lo
 
     def masks_from_features(self, feat: torch.Tensor, feat_lo: Optional[torch.Tensor], n_seg: int, T: int,

@@ -164,6 +164,29 @@ def test_features_batched_and_padded_tail_vs_oracle(nb, dev, golden, small_weigh
     assert np.all(hi & 0x1FFF == 0)          # TF32 heads have the 13 low mantissa bits clear
 
 
+@pytest.mark.parametrize("engine_name", ["2xbf16", "2xf16"])
+def test_features_16bit_split_formats(nb, dev, golden, small_weights, engine_name):
+    """The 16-bit head + remainder pairs the 2xBF16 / 2xF16 engines read decode back to the fp32 features."""
+    eng = {"2xbf16": nb.GEMM_TC_2XBF16, "2xf16": nb.GEMM_TC_2XF16}[engine_name]
+    sep = _sep(nb, small_weights, dev, engine=eng)
+    plan, segs = _golden_segments(golden)
+    T, hop = plan.segment_frames, plan.hop_frames
+    X = torch.from_numpy(golden["stft"]).to(dev)
+    hi, lo = sep.features(X, T_valid=plan.raw_frames, seg_first=0, n_seg=plan.num_segments, T=T, hop=hop, split=True)
+    assert hi.dtype == torch.int16 and lo.dtype == torch.int16
+    dt, scale = (torch.bfloat16, 1.0) if engine_name == "2xbf16" else (torch.float16, 16.0)
+    f = ((hi.view(dt).float() + lo.view(dt).float()) / scale).cpu().numpy()
+    assert np.all(f[:, 1799:] == 0)
+    f = f[:, :1799].reshape(plan.num_segments, T, 1799)
+    tol = 2e-4 if engine_name == "2xbf16" else 1e-4       # bf16 pairs keep 16 mantissa bits: |ipd| <= pi -> 5e-5
+    for i in range(plan.num_segments):
+        assert np.abs(f[i] - O.css_features(segs[i])).max() < tol, f"segment {i}"
+    from notsofar_b200.separator import split_activations
+    ref32, _ = sep.features(X, T_valid=plan.raw_frames, seg_first=0, n_seg=plan.num_segments, T=T, hop=hop)
+    h2, l2 = split_activations(ref32.cpu().numpy(), eng)
+    assert np.array_equal(h2, hi.cpu().numpy()) and np.array_equal(l2, lo.cpu().numpy())   # host twin is bit-identical
+
+
 # ----------------------------------------------------------------------------------------------- GEMM engines
 @pytest.mark.parametrize("M,N,K", [(128, 128, 32), (186, 186, 64), (300, 1028, 512), (1000, 512, 1824), (77, 371, 64)])
 def test_gemm_engines_vs_fp64(nb, dev, M, N, K):
@@ -176,7 +199,8 @@ def test_gemm_engines_vs_fp64(nb, dev, M, N, K):
     tA, tW, tb = (torch.from_numpy(a).to(dev) for a in (A, W, bias))
     ws = torch.empty(8 * (M * K + N * K) + 4096, dtype=torch.uint8, device=dev)
     errs = {}
-    for name, eng in (("simt", nb.GEMM_SIMT_FP32), ("3xtf32", nb.GEMM_TC_3XTF32), ("tf32", nb.GEMM_TC_TF32)):
+    for name, eng in (("simt", nb.GEMM_SIMT_FP32), ("3xtf32", nb.GEMM_TC_3XTF32), ("tf32", nb.GEMM_TC_TF32),
+                      ("2xbf16", nb.GEMM_TC_2XBF16), ("2xf16", nb.GEMM_TC_2XF16)):
         out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
         nb._cabi.check(lib.nsf_gemm_test(eng, nb._cabi.ptr(tA), nb._cabi.ptr(tW), nb._cabi.ptr(tb), nb._cabi.ptr(out), M, N, K,
                                          nb._cabi.ptr(ws), ws.numel(), nb._cabi.stream_ptr()), "nsf_gemm_test")
@@ -188,6 +212,10 @@ def test_gemm_engines_vs_fp64(nb, dev, M, N, K):
     # round to nearest: the error grows with K (7e-7 at K = 64, 1.3e-5 at K = 1824 [measured])
     assert errs["3xtf32"] < 3e-5
     assert errs["tf32"] < 3e-3
+    # 16-bit head + remainder pairs, three kind::f16 MMAs: bf16 keeps 16 mantissa bits (~2^-17 per element),
+    # power-of-two-scaled fp16 keeps 22 (fp32-grade, same accumulator floor as 3xTF32)
+    assert errs["2xbf16"] < 3e-5
+    assert errs["2xf16"] < 3e-5
 
 
 # ----------------------------------------------------------------------------------------------- fused attention
@@ -226,17 +254,20 @@ def test_fused_attention_vs_fp64(nb, dev, n_seg, n_heads, T, maxlen):
 
 
 # ----------------------------------------------------------------------------------------------- mask network
-@pytest.mark.parametrize("engine_name", ["simt", "3xtf32"])
+ENGINES = {"simt": 0, "3xtf32": 1, "tf32": 2, "2xbf16": 3, "2xf16": 4}
+
+
+@pytest.mark.parametrize("engine_name", ["simt", "3xtf32", "2xbf16", "2xf16"])
 def test_masks_vs_reference_golden(nb, dev, golden, small_weights, engine_name):
-    eng = {"simt": nb.GEMM_SIMT_FP32, "3xtf32": nb.GEMM_TC_3XTF32}[engine_name]
+    eng = ENGINES[engine_name]
     sep = _sep(nb, small_weights, dev, engine=eng)
     T = int(golden["segment_frames"])
     feat = np.zeros((T, sep.ldf), np.float32)
     ib = small_weights["executor.nnet.input_bias"].reshape(-1)
     isc = small_weights["executor.nnet.input_scale"].reshape(-1)
     feat[:, :1799] = (golden["feat0"] + ib) * isc                              # conformer.py:297-299
-    hi = (feat.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
-    lo = feat - hi
+    from notsofar_b200.separator import split_activations
+    hi, lo = split_activations(feat, eng)
     m = sep.masks_from_features(torch.from_numpy(hi).to(dev), torch.from_numpy(lo).to(dev), 1, T).cpu().numpy()[0]
     ref = golden["masks"][0]
     err = rel_l2(m, ref)
@@ -244,10 +275,11 @@ def test_masks_vs_reference_golden(nb, dev, golden, small_weights, engine_name):
     assert err < TOL
 
 
-def test_masks_production_net_vs_oracle(nb, dev):
+@pytest.mark.parametrize("engine_name", ["3xtf32", "2xbf16", "2xf16"])
+def test_masks_production_net_vs_oracle(nb, dev, engine_name):
     """v1.0-MC architecture (d=512, 8 heads, 18 blocks, 59 M parameters), 2 segments of 186 frames."""
     w = O.random_weights(seed=0, gain=0.5)
-    sep = _sep(nb, w, dev)
+    sep = _sep(nb, w, dev, engine=ENGINES[engine_name])
     rng = np.random.default_rng(3)
     x = (rng.standard_normal((48128 + 93 * 256, 7)) * 0.05).astype(np.float32)
     X = sep.stft_device(torch.from_numpy(x).to(dev))
@@ -256,8 +288,10 @@ def test_masks_production_net_vs_oracle(nb, dev):
     raw, _ = sep.features(X, X.shape[1], 0, 2, 186, 93)                          # un-normalised features for the oracle
     ref = O.conformer_masks(w, raw.cpu().numpy()[:, :1799].reshape(2, 186, 1799))
     err = rel_l2(m, ref)
-    print(f"production net masks rel_l2 vs oracle = {err:.3e}, max abs = {np.abs(m - ref).max():.3e}, mask std {ref.std():.3f}")
+    print(f"production net masks[{engine_name}] rel_l2 vs oracle = {err:.3e}, max abs = {np.abs(m - ref).max():.3e}, mask std {ref.std():.3f}")
     assert err < TOL
+    if engine_name != "3xtf32":
+        return
     sep_simt = _sep(nb, w, dev, engine=nb.GEMM_SIMT_FP32)
     m2 = sep_simt.masks_from_features(feat, lo, 2, 186).cpu().numpy()
     print(f"   simt engine: {rel_l2(m2, ref):.3e}")
