@@ -153,6 +153,164 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def roofline_of(prof, prof_ms, steps, engine):
+    """Per-kernel-class durations (library CUDA-event brackets on the launching stream) -> (kernels, roofline of the
+    class that takes the largest share of the step)."""
+    peaks = _peaks()
+    kernels = {}
+    for name, (ms, work, cnt) in prof.items():
+        if cnt == 0:
+            continue
+        per = {"ms_per_step": ms / steps, "brackets_per_step": cnt / steps}
+        if name.startswith("gemm") or name == "attention":
+            per.update(bound="tensor", achieved=work / (ms * 1e-3) / 1e12 if ms > 0 else None, unit="TFLOP/s")
+        elif name != "net_other":
+            per.update(bound="hbm", achieved=work / (ms * 1e-3) / 1e9 if ms > 0 else None, unit="GB/s")
+        kernels[name] = per
+    dom = max((k for k in kernels if "achieved" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
+    d = kernels[dom]
+    if d["bound"] == "tensor":
+        # the fraction is reported against the measured sustained bf16 GEMM peak (the only measured tensor number)
+        peak = peaks["bf16_sustained"]
+        note = f"algorithmic fp32 flops (the 3 tensor-core passes of a split product count once) vs sustained bf16 cuBLAS peak, {peaks['which']}"
+    else:
+        peak = peaks["hbm_gbs"]
+        note = f"algorithmic bytes vs copy bandwidth, {peaks['which']}"
+    extra = {}
+    if d["bound"] == "tensor" and engine == "3xtf32":
+        # every algorithmic product costs three kind::tf32 MMAs, and the dense tf32 rate is half the bf16 rate:
+        # the ceiling of this arithmetic is peak / 6
+        extra = {"issued_tf32_tflops": 3 * d["achieved"], "frac_of_3xtf32_ceiling": 6 * d["achieved"] / peak}
+    elif d["bound"] == "tensor" and engine in ("2xbf16", "2xf16"):
+        # three kind::f16 MMAs per algorithmic product: the ceiling of this arithmetic is peak / 3
+        extra = {"issued_f16_tflops": 3 * d["achieved"], "frac_of_split16_ceiling": 3 * d["achieved"] / peak}
+    roofline = {**extra, "kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": peak, "unit": d["unit"],
+                "frac": d["achieved"] / peak, "traffic": NCU_TRAFFIC.get((dom, engine)), "share_of_step": d["ms_per_step"] / prof_ms, "note": note}
+    return kernels, roofline
+
+
+def run_b200_sharded(args, world, rank, local_rank, dev, lib):
+    """N > 1: ONE synthetic meeting of N x --seconds, segments sharded over the ranks in contiguous blocks with a
+    one-segment halo; exchanges: all-gather of the 3x3 stitching costs and of the per-frame mask means, gather of the
+    separated waveforms to rank 0 (NCCL over NVLink).  Per-rank work is fixed as N grows -> weak scaling."""
+    import torch
+    import torch.distributed as dist
+    import notsofar_b200 as N
+    from notsofar_b200 import synth, _cabi
+    from notsofar_b200.css import HostFeeder
+    from notsofar_b200.sharded import css_device_sharded, make_shard
+
+    seconds = args.seconds
+    total_s = seconds * world
+    n_total = int(round(total_s * FS))
+    cfg = N.CssCfg(activity_th=0.3, show_progressbar=False)
+    plan = N.plan_segments(n_total, FS, cfg)
+    sh = make_shard(plan, rank, world)
+    # the 5-min seeded pattern tiles the long meeting; every rank materialises only its own sample range
+    base = synth.synthetic_meeting(min(total_s, 300.0), seed=0)
+    idx0, idx1 = sh.sample_lo, sh.sample_hi
+    reps = -(-idx1 // len(base))
+    x_np = np.ascontiguousarray(np.tile(base, (reps - idx0 // len(base), 1))[idx0 % len(base): idx0 % len(base) + (idx1 - idx0)])
+    x_pinned = torch.from_numpy(x_np).pin_memory()
+    weights = synth.random_state_dict(0)
+    engine = {"3xtf32": N.GEMM_TC_3XTF32, "tf32": N.GEMM_TC_TF32, "simt": N.GEMM_SIMT_FP32, "2xbf16": N.GEMM_TC_2XBF16,
+              "2xf16": N.GEMM_TC_2XF16}[args.engine]
+    sep = N.ConformerCssB200(weights, device=dev, gemm_engine=engine, segments_per_batch=args.segments_per_batch)
+    x_dev = x_pinned.to(dev)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        return css_device_sharded(x_dev, sep, FS, cfg, n_total)
+
+    def step_e2e():
+        chunk = 128 * plan.hop_frames * 256
+        feeder = HostFeeder(x_pinned, dev, chunk)
+        out = css_device_sharded(feeder, sep, FS, cfg, n_total)
+        if rank == 0:
+            from notsofar_b200.css import _pinned_out
+            host = _pinned_out(tuple(out["wav"].shape))
+            host.copy_(out["wav"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out
+
+    for _ in range(args.warmup):
+        out = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.nsf_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    launches = (lib.nsf_launch_count() - launches0) // args.steps
+    clocks = sampler.stop()
+    # rank 0's per-kernel-class brackets (same second pass as the single-GPU arm)
+    lib.nsf_prof_enable(1)
+    _cabi.prof_collect()
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        out = step_device()
+    ev1.record()
+    barrier()
+    prof_ms = ev0.elapsed_time(ev1) / args.steps
+    prof = _cabi.prof_collect()
+    lib.nsf_prof_enable(0)
+    del out
+    e2e_ms = float("nan")
+    if not args.skip_e2e:
+        for _ in range(min(2, args.warmup)):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        ev0.record()
+        for _ in range(args.steps):
+            step_e2e()
+        ev1.record()
+        barrier()
+        e2e_ms = max(ev0.elapsed_time(ev1), (time.perf_counter() - t0) * 1e3) / args.steps
+    t = torch.tensor([dev_ms, e2e_ms, float(launches)], device=dev, dtype=torch.float64)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms = tmax[0].item(), tmax[1].item()
+    if rank == 0:
+        n_out = (plan.mix_frames - 1) * 256 + 512
+        kernels, roofline = roofline_of(prof, prof_ms, args.steps, args.engine)
+        line = {"metric": METRIC, "value": total_s / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": DTYPES[args.engine],
+                "data": "synthetic (seeded 5-min 7-ch pattern tiled; random-init v1.0-MC weights)",
+                "config": {"workload": f"CSS Conformer v1.0-MC + MVDR, 7-ch 16 kHz, ONE {total_s / 60:.0f}-min synthetic meeting "
+                                       f"({plan.num_segments} segments of 186 frames) sharded over {world} GPUs = {seconds / 60:.0f} min per GPU",
+                           "segments_per_batch": args.segments_per_batch, "gemm_engine": args.engine,
+                           "parallelism": f"segment-sharded x{world}: contiguous blocks + 1-segment halo; NCCL all-gather of stitching costs "
+                                          f"(36 B/segment) and mask means (12 B/frame), gather of the separated streams to rank 0",
+                           "l2": "inputs and intermediates exceed L2 (>5 GB touched per step per GPU)"},
+                "clocks": clocks,
+                "e2e": {"value": total_s / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": int(n_total * 7 * 4 + (world - 1) * (plan.segment_frames + 1) * 256 * 7 * 4),
+                        "d2h_bytes_per_step": int(3 * n_out * 4 + plan.num_segments * 36 * world)},
+                "gpu_launches": int(t[2].item()),
+                "roofline": roofline, "kernels": kernels}
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+DTYPES = {"3xtf32": "f32 (3xTF32 tensor-core GEMMs, fp64 MVDR)", "tf32": "tf32", "simt": "f32",
+          "2xbf16": "f32 (bf16 head+remainder pairs, 3 kind::f16 MMAs per product, fp32 accumulate; fp64 MVDR)",
+          "2xf16": "f32 (scaled fp16 head+remainder pairs = 22 mantissa bits, 3 kind::f16 MMAs per product, "
+                   "fp32 accumulate; fp64 MVDR)"}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -171,6 +329,11 @@ def run_b200(args):
     lib = _cabi.load()
 
     seconds = args.seconds
+    sharded = world > 1 and args.multi == "shard"
+    if sharded:
+        # one meeting of world x `seconds`, its segments sharded over the ranks (notsofar_b200.sharded): every rank
+        # separates `seconds` of audio (weak scaling) and the separated streams are gathered on rank 0
+        return run_b200_sharded(args, world, rank, local_rank, dev, lib)
     x_np = make_meeting(seconds, seed=rank)                   # every rank its own meeting (sessions are independent)
     n = len(x_np)
     x_pinned = torch.from_numpy(x_np).pin_memory()
@@ -250,45 +413,12 @@ def run_b200(args):
         dev_ms, e2e_ms = t.tolist()
 
     if rank == 0:
-        peaks = _peaks()
         value = world * seconds / (dev_ms / 1e3)
         e2e_val = world * seconds / (e2e_ms / 1e3)
-        kernels = {}
-        for name, (ms, work, cnt) in prof.items():
-            if cnt == 0:
-                continue
-            per = {"ms_per_step": ms / args.steps, "brackets_per_step": cnt / args.steps}
-            if name.startswith("gemm") or name == "attention":
-                per.update(bound="tensor", achieved=work / (ms * 1e-3) / 1e12 if ms > 0 else None, unit="TFLOP/s")
-            elif name != "net_other":
-                per.update(bound="hbm", achieved=work / (ms * 1e-3) / 1e9 if ms > 0 else None, unit="GB/s")
-            kernels[name] = per
-        dom = max((k for k in kernels if "achieved" in kernels[k]), key=lambda k: kernels[k]["ms_per_step"])
-        d = kernels[dom]
-        if d["bound"] == "tensor":
-            # 3xTF32 issues three tf32 MMAs per algorithmic product; dense tf32 peak is half the bf16 peak.  The
-            # fraction is reported against the measured sustained bf16 GEMM peak (the only measured tensor number).
-            peak = peaks["bf16_sustained"]
-            note = f"algorithmic fp32 flops (the 3 tensor-core passes of a split product count once) vs sustained bf16 cuBLAS peak, {peaks['which']}"
-        else:
-            peak = peaks["hbm_gbs"]
-            note = f"algorithmic bytes vs copy bandwidth, {peaks['which']}"
-        extra = {}
-        if d["bound"] == "tensor" and args.engine == "3xtf32":
-            # every algorithmic product costs three kind::tf32 MMAs, and the dense tf32 rate is half the bf16 rate:
-            # the ceiling of this arithmetic is peak / 6
-            extra = {"issued_tf32_tflops": 3 * d["achieved"], "frac_of_3xtf32_ceiling": 6 * d["achieved"] / peak}
-        elif d["bound"] == "tensor" and args.engine in ("2xbf16", "2xf16"):
-            # three kind::f16 MMAs per algorithmic product: the ceiling of this arithmetic is peak / 3
-            extra = {"issued_f16_tflops": 3 * d["achieved"], "frac_of_split16_ceiling": 3 * d["achieved"] / peak}
-        roofline = {**extra, "kernel": dom, "bound": d["bound"], "achieved": d["achieved"], "peak": peak, "unit": d["unit"],
-                    "frac": d["achieved"] / peak, "traffic": NCU_TRAFFIC.get(dom), "share_of_step": d["ms_per_step"] / prof_ms, "note": note}
+        kernels, roofline = roofline_of(prof, prof_ms, args.steps, args.engine)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": {"3xtf32": "f32 (3xTF32 tensor-core GEMMs, fp64 MVDR)", "tf32": "tf32", "simt": "f32",
-                          "2xbf16": "f32 (bf16 head+remainder pairs, 3 kind::f16 MMAs per product, fp32 accumulate; fp64 MVDR)",
-                          "2xf16": "f32 (scaled fp16 head+remainder pairs = 22 mantissa bits, 3 kind::f16 MMAs per product, "
-                                   "fp32 accumulate; 3xTF32 attention; fp64 MVDR)"}[args.engine],
+                "dtype": DTYPES[args.engine],
                 "data": "synthetic (seeded 5-min 7-ch pattern tiled; random-init v1.0-MC weights)",
                 "config": {"workload": f"CSS Conformer v1.0-MC + MVDR, 7-ch 16 kHz, {seconds / 60:.0f}-min synthetic meeting per GPU "
                                        f"({plan.num_segments} segments of 186 frames)",
@@ -318,11 +448,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=1800.0, help="meeting length per GPU")
-    ap.add_argument("--engine", default="3xtf32", choices=["3xtf32", "tf32", "simt", "2xbf16", "2xf16"])
+    ap.add_argument("--engine", default="2xbf16", choices=["3xtf32", "tf32", "simt", "2xbf16", "2xf16"])
     ap.add_argument("--segments-per-batch", type=int, default=640)
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="slice of the meeting the CPU baseline leg runs")
     ap.add_argument("--ref-seconds", type=float, default=15.0, help="--impl reference: audio seconds per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--multi", default="shard", choices=["shard", "replicas"],
+                    help="N > 1: shard ONE N x --seconds meeting by segments over the ranks (default), or give every rank its own meeting")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: device-resident loop alone")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,303 @@
+"""One meeting across the GPUs of a box: contiguous blocks of segments per rank, three small exchanges.
+
+The reference separates a session on one device, segment after segment (css/css.py:182-250).  Loop I has no
+cross-segment dependency; only the permutation chain (css.py:266-285), the 50 %-overlap weighted overlap-add
+(:287-299) and the activity morphology (:303-312) couple neighbours.  Rank r therefore owns the segments
+[lo_r, hi_r) plus a one-segment halo on the left (recomputed, not communicated), and the ranks meet three times:
+
+  1. all-gather of the 3x3 stitching costs of the owned segments (36 B / segment) -> every rank replays the
+     6-permutation chain on the host and knows the global channel order of its block;
+  2. all-gather of the per-frame mask means (12 B / frame) -> every rank runs the (global) dilate / erode gate;
+  3. gather of the separated waveforms of the owned frames to the rank that hands the streams to ASR /
+     diarization (3 x 4 B / sample; 345 MB per 30 min), where the 256-sample seams are overlap-added.
+
+Everything else (STFT of the rank's sample range, features, mask network, MVDR, local WOLA, iSTFT) is the
+single-GPU path of css.py on the rank's slice.  torch.distributed (NCCL over NVLink on the GPUs, gloo in the
+CPU tests of the exchange logic) carries the three exchanges; there is no CPU compute path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .css import (CssCfg, SegmentPlan, plan_segments, plan_batches, permutation_chain, _segment_weights, HostFeeder)
+from .separator import NUM_BINS, FRAME_HOP, FRAME_LEN
+
+
+@dataclass
+class Shard:
+    """Segment / frame / sample ranges of one rank (all global indices; *_hi exclusive)."""
+    rank: int
+    world: int
+    seg_lo: int
+    seg_hi: int
+    halo: int            # 1 if the block has a left neighbour (segment seg_lo - 1 is recomputed locally)
+    frame0: int          # global index of local frame 0
+    n_frames: int        # local frames (pitch of the local X / stitched arrays)
+    valid_frames: int    # local frames that exist in the signal (the rest is the zero padding of css.py:159-164,185-190)
+    own_lo: int          # owned output frames [own_lo, own_hi)
+    own_hi: int
+    sample_lo: int       # samples of the recording this rank needs: [sample_lo, sample_hi)
+    sample_hi: int
+
+    @property
+    def n_own_seg(self) -> int:
+        return self.seg_hi - self.seg_lo
+
+    @property
+    def n_loc_seg(self) -> int:
+        return self.seg_hi - self.seg_lo + self.halo if self.seg_hi > self.seg_lo else 0
+
+    @property
+    def n_own_frames(self) -> int:
+        return self.own_hi - self.own_lo
+
+
+def shard_bounds(n_seg: int, world: int) -> List[int]:
+    """Balanced contiguous blocks: rank r owns segments [b[r], b[r+1])."""
+    base, extra = divmod(n_seg, world)
+    b = [0]
+    for r in range(world):
+        b.append(b[-1] + base + (1 if r < extra else 0))
+    return b
+
+
+def make_shard(plan: SegmentPlan, rank: int, world: int) -> Shard:
+    T, hop = plan.segment_frames, plan.hop_frames
+    b = shard_bounds(plan.num_segments, world)
+    lo, hi = b[rank], b[rank + 1]
+    if hi == lo:           # more ranks than segments: nothing to do, nothing owned
+        return Shard(rank, world, lo, hi, 0, 0, 0, 0, 0, 0, 0, 0)
+    halo = 1 if lo > 0 else 0
+    frame0 = (lo - halo) * hop
+    n_frames = min(plan.mix_frames, (hi - 1) * hop + T) - frame0
+    valid = max(0, min(plan.raw_frames - frame0, n_frames))
+    own_lo = lo * hop
+    own_hi = hi * hop if hi < plan.num_segments else plan.mix_frames
+    s_lo = frame0 * FRAME_HOP
+    s_hi = (frame0 + valid - 1) * FRAME_HOP + FRAME_LEN if valid > 0 else s_lo
+    return Shard(rank, world, lo, hi, halo, frame0, n_frames, valid, own_lo, own_hi, s_lo, s_hi)
+
+
+# ------------------------------------------------------------------------------------------- exchanges
+def allgather_varlen(own: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+    """All-gather along dim 0 of per-rank tensors with counts[r] rows (known to every rank from the plan)."""
+    import torch.distributed as dist
+    world = len(counts)
+    assert own.shape[0] == counts[dist.get_rank(group)]
+    mx = max(max(counts), 1)
+    pad = torch.zeros((mx,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+    pad[:own.shape[0]] = own
+    out = torch.empty((world * mx,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    out = out.view((world, mx) + tuple(own.shape[1:]))
+    return torch.cat([out[r, :counts[r]] for r in range(world)], dim=0)
+
+
+def gather_varlen(own: torch.Tensor, counts: Sequence[int], dst: int = 0, group=None, dim: int = 0) -> Optional[List[torch.Tensor]]:
+    """Gather per-rank tensors whose size along ``dim`` is counts[r] to rank ``dst``; returns the list there, None elsewhere."""
+    import torch.distributed as dist
+    world = len(counts)
+    rank = dist.get_rank(group)
+    assert own.shape[dim] == counts[rank]
+    mx = max(max(counts), 1)
+    shape = list(own.shape)
+    shape[dim] = mx
+    pad = torch.zeros(shape, dtype=own.dtype, device=own.device)
+    pad.narrow(dim, 0, own.shape[dim]).copy_(own)
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return [bufs[r].narrow(dim, 0, counts[r]) for r in range(world)]
+
+
+def assemble_waveforms(pieces: Sequence[torch.Tensor], shards: Sequence[Shard], mix_frames: int) -> torch.Tensor:
+    """Overlap-adds the per-rank waveform pieces [S, n_own_frames*256 + 256] (piece r starts at sample own_lo*256;
+    its last 256 samples are the tail of its last frame, which lands on the head of rank r+1's first frame)."""
+    n_out = (mix_frames - 1) * FRAME_HOP + FRAME_LEN
+    S = pieces[0].shape[0]
+    out = torch.zeros((S, n_out), dtype=pieces[0].dtype, device=pieces[0].device)
+    for p, sh in zip(pieces, shards):
+        if sh.n_own_frames == 0:
+            continue
+        n = sh.n_own_frames * FRAME_HOP + FRAME_HOP
+        assert p.shape[1] == n
+        out[:, sh.own_lo * FRAME_HOP: sh.own_lo * FRAME_HOP + n] += p
+    return out
+
+
+# ------------------------------------------------------------------------------------------- per-rank work
+class ShardWorker:
+    """The work of one rank, split at the three exchange points so that the same code runs under torch.distributed
+    (css_device_sharded) and, rank after rank on one device, in the single-GPU parity test of the sharding logic."""
+
+    def __init__(self, separator, fs: int, cfg: CssCfg, n_samples_total: int, rank: int, world: int):
+        self.sep, self.fs, self.cfg = separator, fs, cfg
+        self.plan = plan_segments(n_samples_total, fs, cfg)
+        self.world = world
+        self.shards = [make_shard(self.plan, r, world) for r in range(world)]
+        self.sh = self.shards[rank]
+        self.lib = _cabi.load()
+        if cfg.normalize_segment_power:
+            raise NotImplementedError("normalize_segment_power=True is not built yet")
+        assert cfg.stitching_loss in ('l1', 'mse') and cfg.stitching_input in ('mask', 'separation_result')
+
+    # ---- phase 1: STFT, mask network, MVDR and stitching costs of the local block --------------------------------
+    @torch.no_grad()
+    def phase1(self, x_local) -> torch.Tensor:
+        """x_local: samples [sample_lo, sample_hi) of the recording, [n, C] float32 on the device (or a HostFeeder
+        over that slice).  Returns the costs of the owned segments [n_own_seg, S, S] (device)."""
+        sh, plan, cfg, sep = self.sh, self.plan, self.cfg, self.sep
+        feeder = x_local if isinstance(x_local, HostFeeder) else None
+        x = feeder.x_dev if feeder is not None else x_local
+        device = x.device
+        self.device = device
+        T, hop, S = plan.segment_frames, plan.hop_frames, cfg.num_spks
+        n_masks = sep.num_masks
+        n_loc = sh.n_loc_seg
+        if n_loc == 0:
+            self.masks = self.Y = None
+            return torch.zeros((0, S, S), dtype=torch.float32, device=device)
+        assert x.shape[0] == sh.sample_hi - sh.sample_lo, (x.shape, sh)
+        num_channels = x.shape[1]
+        if num_channels == 1 or not cfg.mc_mvdr:
+            raise NotImplementedError("single-channel / mask-only CSS is not built yet")
+        mask_floor = 10. ** (cfg.mc_mask_floor_db / 20.)
+        with torch.cuda.device(device):
+            X = sep.stft_alloc(num_channels, sh.n_frames, sh.valid_frames, device)
+            self.masks = torch.empty((n_loc, n_masks, NUM_BINS, T), dtype=torch.float32, device=device)
+            self.Y = torch.empty((n_loc, S, NUM_BINS, T), dtype=torch.complex64, device=device)
+            frames_done = 0
+            for s0, nb in plan_batches(n_loc, int(sep.segments_per_batch), streaming=feeder is not None):
+                f_need = min(sh.valid_frames, (s0 + nb - 1) * hop + T)
+                if f_need > frames_done:
+                    if feeder is not None:
+                        feeder.ready((f_need - 1) * FRAME_HOP + FRAME_LEN)
+                    sep.stft_frames(x, X, frames_done, f_need)
+                    frames_done = f_need
+                sep.masks(X, sh.valid_frames, s0, nb, T, hop, out=self.masks[s0:s0 + nb])
+                sep.mvdr(self.masks[s0:s0 + nb], X, sh.valid_frames, s0, hop, mask_floor, out=self.Y[s0:s0 + nb])
+            if feeder is not None:
+                feeder.ready(x.shape[0])
+            costs = torch.empty((n_loc, S, S), dtype=torch.float32, device=device)
+            in_kind = 0 if cfg.stitching_input == 'mask' else 1
+            loss_kind = 0 if cfg.stitching_loss == 'l1' else 1
+            src = self.masks if in_kind == 0 else self.Y
+            _cabi.check(self.lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_loc, n_masks if in_kind == 0 else S, S, NUM_BINS,
+                                              T, plan.overlap_frames, _cabi.ptr(costs), _cabi.stream_ptr()), "nsf_pit_cost")
+        self.X = X
+        return costs[sh.halo:]
+
+    # ---- phase 2: permutation chain (host, replicated), local mask WOLA -> owned rows of the activity mean --------
+    @torch.no_grad()
+    def phase2(self, costs_all: np.ndarray) -> torch.Tensor:
+        sh, plan, cfg = self.sh, self.plan, self.cfg
+        S = cfg.num_spks
+        assert costs_all.shape == (plan.num_segments, S, S)
+        self.perms = permutation_chain(costs_all)
+        device = self.device
+        if sh.n_loc_seg == 0:
+            return torch.zeros((0, S), dtype=torch.float32, device=device)
+        seg_w_np, wsum_np = _segment_weights(plan)
+        assert (wsum_np > 1e-5).all(), 'zero weights found. check hop_size, segment_size or m0, m1'
+        loc0 = sh.seg_lo - sh.halo
+        with torch.cuda.device(device):
+            self.perms_loc = torch.from_numpy(np.ascontiguousarray(self.perms[loc0:sh.seg_hi])).to(device)
+            self.seg_w = torch.from_numpy(np.ascontiguousarray(seg_w_np[loc0:sh.seg_hi])).to(device)
+            self.wsum = torch.from_numpy(np.ascontiguousarray(wsum_np[sh.frame0:sh.frame0 + sh.n_frames])).to(device)
+            self.mask_st = torch.empty((NUM_BINS, sh.n_frames, S), dtype=torch.float32, device=device)
+            activity = torch.empty((sh.n_frames, S), dtype=torch.float32, device=device)
+            _cabi.check(self.lib.nsf_stitch_masks(_cabi.ptr(self.masks), self.sep.num_masks, _cabi.ptr(self.perms_loc), _cabi.ptr(self.seg_w),
+                                                  _cabi.ptr(self.wsum), sh.n_loc_seg, S, NUM_BINS, plan.segment_frames, plan.hop_frames,
+                                                  sh.n_frames, _cabi.ptr(self.mask_st), _cabi.ptr(activity), _cabi.stream_ptr()),
+                        "nsf_stitch_masks")
+        return activity[sh.own_lo - sh.frame0: sh.own_hi - sh.frame0]
+
+    # ---- phase 3: global activity gate (replicated, tiny), local STFT WOLA + iSTFT -> waveform of the owned frames --
+    @torch.no_grad()
+    def phase3(self, activity_all: torch.Tensor) -> Dict[str, torch.Tensor]:
+        sh, plan, cfg = self.sh, self.plan, self.cfg
+        S = cfg.num_spks
+        device = self.device
+        mix = plan.mix_frames
+        assert tuple(activity_all.shape) == (mix, S)
+        with torch.cuda.device(device):
+            activity_all = activity_all.contiguous()
+            act_b = torch.empty((mix, S), dtype=torch.uint8, device=device)
+            act_tmp = torch.empty_like(act_b)
+            act_final = torch.empty_like(act_b)
+            _cabi.check(self.lib.nsf_activity(_cabi.ptr(activity_all), mix, S, float(np.float32(cfg.activity_th)), plan.dilation_frames,
+                                              plan.erosion_frames, _cabi.ptr(act_b), _cabi.ptr(act_tmp), _cabi.ptr(act_final),
+                                              _cabi.stream_ptr()), "nsf_activity")
+            out = dict(activity=activity_all, activity_b=act_b, activity_final=act_final)
+            if sh.n_loc_seg == 0:
+                out["wav_piece"] = torch.zeros((S, 0), dtype=torch.float32, device=device)
+                out["mask_piece"] = torch.zeros((NUM_BINS, 0, S), dtype=torch.float32, device=device)
+                return out
+            act_loc = act_final[sh.frame0: sh.frame0 + sh.n_frames]            # contiguous rows
+            S_st = torch.empty((S, sh.n_frames, NUM_BINS), dtype=torch.complex64, device=device)
+            _cabi.check(self.lib.nsf_stitch_stft(_cabi.ptr(self.Y), _cabi.ptr(self.perms_loc), _cabi.ptr(self.seg_w), _cabi.ptr(self.wsum),
+                                                 _cabi.ptr(act_loc), sh.n_loc_seg, S, NUM_BINS, plan.segment_frames, plan.hop_frames,
+                                                 sh.n_frames, _cabi.ptr(S_st), _cabi.stream_ptr()), "nsf_stitch_stft")
+            # frames outside the owned range are incomplete here (their other segment lives on a neighbour): they
+            # contribute nothing to this rank's piece
+            a, b = sh.own_lo - sh.frame0, sh.own_hi - sh.frame0
+            if a > 0:
+                S_st[:, :a].zero_()
+            if b < sh.n_frames:
+                S_st[:, b:].zero_()
+            wav = self.sep.istft_device(S_st)                                   # [S, (n_frames-1)*256+512]
+            out["wav_piece"] = wav[:, a * FRAME_HOP: b * FRAME_HOP + FRAME_HOP].contiguous()
+            out["mask_piece"] = self.mask_st[:, a:b]
+        return out
+
+
+@torch.no_grad()
+def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total: int, group=None, dst: int = 0,
+                       want_side_info: bool = False) -> Dict:
+    """One meeting sharded over the ranks of ``group`` (default: the world).  x_local is this rank's sample range
+    (``make_shard(plan, rank, world).sample_lo/hi``), on the device or behind a HostFeeder.  Returns on rank ``dst``
+    {'wav' [S, N'], 'activity_b', 'activity_final', 'perms', 'plan' (+ 'mask_stitched' if want_side_info)}; on the
+    other ranks the dict has no 'wav'."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    wk = ShardWorker(separator, fs, cfg, n_samples_total, rank, world)
+    S = cfg.num_spks
+    own_costs = wk.phase1(x_local)
+    costs_all = allgather_varlen(own_costs, [s.n_own_seg for s in wk.shards], group)
+    own_act = wk.phase2(costs_all.cpu().numpy())
+    activity_all = allgather_varlen(own_act, [s.n_own_frames for s in wk.shards], group)
+    out = wk.phase3(activity_all)
+    counts = [s.n_own_frames * FRAME_HOP + FRAME_HOP if s.n_own_frames else 0 for s in wk.shards]
+    pieces = gather_varlen(out["wav_piece"], counts, dst, group, dim=1)
+    res = dict(activity_b=out["activity_b"], activity_final=out["activity_final"], perms=wk.perms, plan=wk.plan, shard=wk.sh)
+    mask_pieces = None
+    if want_side_info:
+        mask_pieces = gather_varlen(out["mask_piece"].contiguous(), [s.n_own_frames for s in wk.shards], dst, group, dim=1)
+    if rank == dst:
+        res["wav"] = assemble_waveforms(pieces, wk.shards, wk.plan.mix_frames)
+        if mask_pieces is not None:
+            res["mask_stitched"] = torch.cat(mask_pieces, dim=1)
+    return res
+
+
+@torch.no_grad()
+def css_sharded_on_one_device(x: torch.Tensor, separator, fs: int, cfg: CssCfg, world: int) -> Dict:
+    """The sharded algorithm with all ``world`` ranks played by one device, one after the other (exchanges become
+    concatenations).  Used to check the sharding logic against css_device on a single GPU."""
+    n = x.shape[0]
+    wks = [ShardWorker(separator, fs, cfg, n, r, world) for r in range(world)]
+    costs = [w.phase1(x[w.sh.sample_lo:w.sh.sample_hi].contiguous()) for w in wks]
+    costs_all = torch.cat(costs, 0).cpu().numpy()
+    acts = [w.phase2(costs_all) for w in wks]
+    activity_all = torch.cat(acts, 0)
+    outs = [w.phase3(activity_all) for w in wks]
+    wav = assemble_waveforms([o["wav_piece"] for o in outs], [w.sh for w in wks], wks[0].plan.mix_frames)
+    return dict(wav=wav, mask_stitched=torch.cat([o["mask_piece"] for o in outs], 1), activity=activity_all,
+                activity_b=outs[0]["activity_b"], activity_final=outs[0]["activity_final"], perms=wks[0].perms,
+                plan=wks[0].plan, masks=[w.masks for w in wks], Y=[w.Y for w in wks], shards=[w.sh for w in wks])
