@@ -190,6 +190,10 @@ int64_t nsf_attention_test_workspace_bytes(int n_seg, int n_heads, int T, int ma
 int nsf_attention_test(const float* q, const float* k, const float* v, const float* pe, int maxlen, int n_seg, int n_heads,
                        int T, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* The same test hook for the bf16-pair attention kernel of the NSF_GEMM_TC_2XBF16 engine (attention16.cu); workspace as above. */
+int nsf_attention16_test(const float* q, const float* k, const float* v, const float* pe, int maxlen, int n_seg, int n_heads,
+                         int T, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

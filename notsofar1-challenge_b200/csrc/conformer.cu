@@ -461,6 +461,9 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
     // attention-internal products stay SPLIT_TF32 (3xTF32) under the 16-bit engines
     const int fmt = split_fmt_of_engine(eng);
     const int eng_attn = fmt == SPLIT_TF32 ? eng : NSF_GEMM_TC_3XTF32;
+    // 2xBF16 runs the attention on bf16 pairs too (attention16.cu); 2xF16 keeps the 3xTF32 attention (fp32-grade throughout)
+    const bool attn16 = eng == NSF_GEMM_TC_2XBF16 && attn_fused_supported(T, d_k);
+    const int qkv_fmt = attn16 ? SPLIT_BF16 : SPLIT_TF32;
     const float lin_scale = fmt == SPLIT_F16 ? 1.f / (kF16ActScale * kF16WeightScale) : 1.f;
     const int Tp = (int)align_up(T, 32), ld2 = (int)align_up(2 * T - 1, 32);
     const int BH = n_seg * H;
@@ -471,7 +474,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         p.batch = 1;
         p.alpha = 1.f;
         p.acc_scale = 1.f;
-        p.op_fmt = SPLIT_TF32; p.out_fmt = fmt;
+        p.op_fmt = SPLIT_TF32; p.out_fmt = fmt; p.qkv_fmt = qkv_fmt;
         p.T = T; p.Tp = Tp; p.n_heads = H; p.d_k = d_k; p.d_model = d;
         return p;
     };
@@ -520,7 +523,10 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         if (attn_fused_supported(T, d_k) && eng != NSF_GEMM_SIMT_FP32) {
             // scores, relative-position skew, softmax and P V in one tcgen05 kernel (attention.cu)
             ProfScope prof(PROF_ATTN, 6.0 * T * T * d_k * (double)BH, s);
-            if ((rc = attn_fused_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE_HI), h->g(G_PE_LO), D.maxlen,
+            if (attn16) {
+                if ((rc = attn16_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE_HI), h->g(G_PE_LO), D.maxlen,
+                                        n_seg, H, T, Tp, w.h_hi, w.h_lo, d, fmt, s))) return rc;
+            } else if ((rc = attn_fused_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE_HI), h->g(G_PE_LO), D.maxlen,
                                         n_seg, H, T, Tp, w.h_hi, w.h_lo, d, fmt, s))) return rc;
         } else {
             {   // A = q k^T per (segment, head)

@@ -26,7 +26,8 @@ struct GemmParams {
     const float* B_hi; const float* B_lo; int64_t ldb; int64_t b_batch_stride;
     int M, N, K, batch;
     int op_fmt;               // SplitFmt of A and B (the 16-bit formats reinterpret the float pointers as uint16_t arrays)
-    int out_fmt;              // SplitFmt of the split outputs of EPI_RELU_SPLIT / EPI_PV (q, k, v^T of EPI_QKV stay SPLIT_TF32)
+    int out_fmt;              // SplitFmt of the split outputs of EPI_RELU_SPLIT / EPI_PV
+    int qkv_fmt;              // SplitFmt of q, k, v^T written by EPI_QKV (SPLIT_TF32 for attention.cu, SPLIT_BF16 for attention16.cu)
     float acc_scale;          // accumulator scale applied before the bias (undoes the SPLIT_F16 operand scales; 1 otherwise)
     int n_valid;              // columns >= n_valid are padding (weights padded with zero rows)
     const float* bias;        // [n_valid] or nullptr
@@ -64,16 +65,12 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, int b, int m,
             const int which = n / p.d_model, c = n - which * p.d_model;
             const int h = c / p.d_k, d = c - h * p.d_k;
             const int seg = m / p.T, t = m - seg * p.T;
-            float hi, lo;
-            split_tf32(v, hi, lo);
             if (which < 2) {
                 const size_t o = (((size_t)seg * p.n_heads + h) * p.T + t) * p.d_k + d;
-                (which == 0 ? p.q_hi : p.k_hi)[o] = hi;
-                (which == 0 ? p.q_lo : p.k_lo)[o] = lo;
+                split_store(p.qkv_fmt, which == 0 ? p.q_hi : p.k_hi, which == 0 ? p.q_lo : p.k_lo, o, v);
             } else {
                 const size_t o = (((size_t)seg * p.n_heads + h) * p.d_k + d) * p.Tp + t;
-                p.vt_hi[o] = hi;
-                p.vt_lo[o] = lo;
+                split_store(p.qkv_fmt, p.vt_hi, p.vt_lo, o, v);
             }
             break;
         }
@@ -106,6 +103,10 @@ int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream);
 int attn_fused_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
                       const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
                       float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
+// the same on bf16 head + remainder pairs (attention16.cu); the float pointers are reinterpreted as uint16_t arrays
+int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
+                  const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
+                  float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
 inline bool attn_fused_supported(int T, int d_k) { return T >= 2 && T <= 192 && d_k == 64; }
 
 inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {

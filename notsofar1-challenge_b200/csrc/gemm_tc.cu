@@ -78,12 +78,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             const int h = c / p.d_k, d0 = c - h * p.d_k;
             const size_t o = (((size_t)seg * p.n_heads + h) * p.d_k + d0) * p.Tp + t;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                float hi, lo;
-                split_tf32(__uint_as_float(r[j]) * p.acc_scale + (p.bias ? __ldg(p.bias + nc + j) : 0.f), hi, lo);
-                p.vt_hi[o + (size_t)j * p.Tp] = hi;
-                p.vt_lo[o + (size_t)j * p.Tp] = lo;
-            }
+            for (int j = 0; j < 32; ++j)
+                split_store(p.qkv_fmt, p.vt_hi, p.vt_lo, o + (size_t)j * p.Tp,
+                            __uint_as_float(r[j]) * p.acc_scale + (p.bias ? __ldg(p.bias + nc + j) : 0.f));
         }
         return;
     }
@@ -132,13 +129,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                 RowWalker w(r0, p.T);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    if (i < rows) {
-                        float hi, lo;
-                        split_tf32(v[i], hi, lo);
-                        const size_t o = (((size_t)w.seg * p.n_heads + h) * p.T + w.t) * p.d_k + d;
-                        o_hi[o] = hi;
-                        o_lo[o] = lo;
-                    }
+                    if (i < rows)
+                        split_store(p.qkv_fmt, o_hi, o_lo, (((size_t)w.seg * p.n_heads + h) * p.T + w.t) * p.d_k + d, v[i]);
                     w.next();
                 }
                 break;

@@ -146,7 +146,13 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
     add(w[c + "embed.0.bias"])
     add(w[c + "embed.1.weight"])
     add(w[c + "embed.1.bias"])
-    add_split(w[c + "pos_emb.pe_k.weight"], tf32=True)
+    # pe_k feeds the attention kernel: bf16 pairs for the 2xBF16 engine (attention16.cu), TF32 pairs otherwise
+    pe = w[c + "pos_emb.pe_k.weight"]
+    if gemm_engine == _cabi.GEMM_TC_2XBF16 and d_k == 64:
+        hi, lo = _split16(pe, _cabi.SPLIT_BF16)
+        add(hi); add(lo)
+    else:
+        add_split(pe, tf32=True)
     add_split(w[_P + "linear.weight"])
     add(w[_P + "linear.bias"])
     for l in range(n_blocks):
