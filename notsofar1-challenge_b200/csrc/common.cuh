@@ -149,6 +149,38 @@ __device__ __forceinline__ void split_store4(int fmt, float* hi, float* lo, size
     }
 }
 
+// eight consecutive values (idx a multiple of 8, bases 16-byte aligned): one 16-byte store per plane for the 16-bit formats
+__device__ __forceinline__ void split_store8(int fmt, float* hi, float* lo, size_t idx, const float (&v)[8]) {
+    if (fmt == SPLIT_TF32) {
+        split_store4(fmt, hi, lo, idx, make_float4(v[0], v[1], v[2], v[3]));
+        split_store4(fmt, hi, lo, idx + 4, make_float4(v[4], v[5], v[6], v[7]));
+    } else if (fmt == SPLIT_BF16) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * e] - __low2float(hp), v[2 * e + 1] - __high2float(hp));
+            h[e] = *reinterpret_cast<const uint32_t*>(&hp);
+            l[e] = *reinterpret_cast<const uint32_t*>(&lp);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(hi) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lo) + idx) = make_uint4(l[0], l[1], l[2], l[3]);
+    } else {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float a = fminf(fmaxf(v[2 * e] * kF16ActScale, -65504.f), 65504.f);
+            const float b = fminf(fmaxf(v[2 * e + 1] * kF16ActScale, -65504.f), 65504.f);
+            const __half2 hp = __floats2half2_rn(a, b);
+            const __half2 lp = __floats2half2_rn(a - __low2float(hp), b - __high2float(hp));
+            h[e] = *reinterpret_cast<const uint32_t*>(&hp);
+            l[e] = *reinterpret_cast<const uint32_t*>(&lp);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(hi) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(lo) + idx) = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
 // twiddle table W512^j = (cos(2 pi j/512), sin(2 pi j/512)), j < 512; filled once per process
 // from float64 on the host (exact to the last bit of fp32).
 const float2* twiddle_table_device();      // returns device pointer (initialises on first use), nullptr on error

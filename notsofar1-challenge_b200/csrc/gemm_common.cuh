@@ -28,6 +28,7 @@ struct GemmParams {
     int op_fmt;               // SplitFmt of A and B (the 16-bit formats reinterpret the float pointers as uint16_t arrays)
     int out_fmt;              // SplitFmt of the split outputs of EPI_RELU_SPLIT / EPI_PV
     int qkv_fmt;              // SplitFmt of q, k, v^T written by EPI_QKV (SPLIT_TF32 for attention.cu, SPLIT_BF16 for attention16.cu)
+    int vec8;                 // set by the tensor-core launcher: N, leading dimensions and bases allow 8-column vector epilogues
     float acc_scale;          // accumulator scale applied before the bias (undoes the SPLIT_F16 operand scales; 1 otherwise)
     int n_valid;              // columns >= n_valid are padding (weights padded with zero rows)
     const float* bias;        // [n_valid] or nullptr

@@ -84,7 +84,79 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
         }
         return;
     }
-    // lane == column
+    if (p.vec8) {
+        // ---- vector path: swizzled 32 x 32 staging (float4 group g of row l at group g ^ (l & 7): conflict-free both
+        // ways), then every lane owns 8 consecutive columns (cg) of rows rq, rq + 8, rq + 16, rq + 24: 16-byte accesses
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+            *reinterpret_cast<float4*>(stage + lane * 32 + 4 * (jj ^ (lane & 7))) =
+                make_float4(__uint_as_float(r[4 * jj]), __uint_as_float(r[4 * jj + 1]), __uint_as_float(r[4 * jj + 2]),
+                            __uint_as_float(r[4 * jj + 3]));
+        __syncwarp();
+        const int cg = lane & 3, rq = lane >> 2;
+        const int n0 = nc + 8 * cg;
+        if (n0 < p.N) {
+            float bs[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) bs[e] = 0.f;
+            if (p.bias) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
+                bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+            }
+            const int g0 = (2 * cg) ^ rq, g1 = (2 * cg + 1) ^ rq;
+            // EPI_QKV geometry (a 32-column chunk stays inside q or k and inside one head)
+            const int which = p.epi == EPI_QKV ? nc / p.d_model : 0;
+            const int cq = n0 - which * p.d_model;
+            const int hq = p.epi == EPI_QKV ? cq / p.d_k : 0, dq = cq - hq * p.d_k;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rr = rq + 8 * k;
+                const int m = r0 + rr;
+                if (m >= p.M) break;
+                const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 32 + 4 * g0);
+                const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 32 + 4 * g1);
+                float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = v[e] * p.acc_scale + bs[e];
+                switch (p.epi) {
+                    case EPI_STORE: {
+                        float* o = p.out0 + (size_t)b * p.o_batch_stride + (size_t)m * p.ldo + n0;
+                        *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        break;
+                    }
+                    case EPI_RELU_SPLIT: {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                        split_store8(p.out_fmt, p.out0, p.out1, (size_t)m * p.ldo + n0, v);
+                        break;
+                    }
+                    case EPI_RESID: {
+                        float* o = p.out0 + (size_t)m * p.ldo + n0;
+                        const float4 x0 = *reinterpret_cast<const float4*>(o), x1 = *reinterpret_cast<const float4*>(o + 4);
+                        *reinterpret_cast<float4*>(o) = make_float4(x0.x + p.alpha * v[0], x0.y + p.alpha * v[1], x0.z + p.alpha * v[2], x0.w + p.alpha * v[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(x1.x + p.alpha * v[4], x1.y + p.alpha * v[5], x1.z + p.alpha * v[6], x1.w + p.alpha * v[7]);
+                        break;
+                    }
+                    case EPI_QKV: {     // q, k: [seg][head][t][d_k]
+                        const int seg = m / p.T, t = m - seg * p.T;
+                        split_store8(p.qkv_fmt, which ? p.k_hi : p.q_hi, which ? p.k_lo : p.q_lo,
+                                     (((size_t)seg * p.n_heads + hq) * p.T + t) * p.d_k + dq, v);
+                        break;
+                    }
+                    case EPI_PV: {      // batch = (seg, head); rows are frames of that segment
+                        const int seg = b / p.n_heads, h = b - seg * p.n_heads;
+                        split_store8(p.out_fmt, p.out0, p.out1, ((size_t)seg * p.T + m) * p.ldo + (size_t)h * p.d_k + n0, v);
+                        break;
+                    }
+                    default: break;
+                }
+            }
+        }
+        __syncwarp();
+        return;
+    }
+    // lane == column (scalar fallback for shapes that do not allow 16-byte accesses)
 #pragma unroll
     for (int j = 0; j < 32; ++j) stage[lane * kEpiPitch + j] = __uint_as_float(r[j]);
     __syncwarp();
@@ -320,12 +392,29 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
         ma_lo = ma_hi;
         mb_lo = mb_hi;
     }
+    GemmParams pv = p;
+    {
+        auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+        const int osz = 2;      // strictest element size of the outputs (16-bit planes): 8 elements = 16 bytes
+        (void)osz;
+        bool ok = p.N % 8 == 0 && (!p.bias || al16(p.bias));
+        switch (p.epi) {
+            case EPI_STORE: case EPI_RESID:
+                ok = ok && p.ldo % 4 == 0 && p.o_batch_stride % 4 == 0 && al16(p.out0); break;
+            case EPI_RELU_SPLIT: case EPI_PV:
+                ok = ok && p.ldo % 8 == 0 && al16(p.out0) && al16(p.out1) && p.d_k % 8 == 0; break;
+            case EPI_QKV:
+                ok = ok && p.d_k % 8 == 0 && p.d_model % 32 == 0 && al16(p.q_hi) && al16(p.q_lo) && al16(p.k_hi) && al16(p.k_lo); break;
+            default: ok = false; break;     // EPI_MASK writes along rows
+        }
+        pv.vec8 = ok ? 1 : 0;
+    }
     NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int tiles_m = ceil_div(p.M, TBM), tiles_n = ceil_div(p.N, TBN);
     const int64_t total = (int64_t)tiles_m * tiles_n * p.batch;
     if (total > 0x7fffffff) { set_error("gemm_tc: too many tiles"); return NSF_ERR_INVALID_ARG; }
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm_tc_kernel<MODE><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, p, tiles_m, tiles_n, (int)total);
+    gemm_tc_kernel<MODE><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total);
     return check_launch("gemm_tc_kernel");
 }
 
