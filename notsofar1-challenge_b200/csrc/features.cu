@@ -18,8 +18,9 @@ constexpr int kFeatBinsPerCta = 8;     // one warp per bin
 constexpr int kFeatMaxIter = 8;        // T <= 256
 constexpr float kEps32 = 1.1920928955078125e-07f;   // th.finfo(th.float32).eps, feature.py:15
 
-template <int C>
-__global__ void __launch_bounds__(kFeatBinsPerCta * 32)
+// NITER = ceil(T / 32) register slots per lane (6 for the pipeline's T = 186: two CTAs per SM instead of one)
+template <int C, int NITER>
+__global__ void __launch_bounds__(kFeatBinsPerCta * 32, NITER <= 6 ? 2 : 1)
 css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_valid, int64_t seg_first, int T, int hop,
                     const float* __restrict__ in_bias, const float* __restrict__ in_scale,
                     float* __restrict__ feat, float* __restrict__ feat_lo, int64_t ldf, int fmt) {
@@ -33,14 +34,14 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
     if (f < kBins) {
         const bool edge_bin = (f == 0 || f == kBins - 1);
         const float2* Xf = X + ((size_t)f * T_long + st) * C;
-        float mag0[kFeatMaxIter];
-        float yr[kFeatMaxIter][C - 1 > 0 ? C - 1 : 1], yi[kFeatMaxIter][C - 1 > 0 ? C - 1 : 1];
+        float mag0[NITER];
+        float yr[NITER][C - 1 > 0 ? C - 1 : 1], yi[NITER][C - 1 > 0 ? C - 1 : 1];
         float s_mag = 0.f;
         float s_yr[C - 1 > 0 ? C - 1 : 1], s_yi[C - 1 > 0 ? C - 1 : 1];
 #pragma unroll
         for (int m = 0; m < C - 1; ++m) { s_yr[m] = 0.f; s_yi[m] = 0.f; }
 #pragma unroll
-        for (int it = 0; it < kFeatMaxIter; ++it) {
+        for (int it = 0; it < NITER; ++it) {
             const int t = it * 32 + lane;
             mag0[it] = 0.f;
             if (t < T) {
@@ -87,7 +88,7 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
         const float mean = warp_sum(s_mag) / (float)T;
         float ssq = 0.f;
 #pragma unroll
-        for (int it = 0; it < kFeatMaxIter; ++it) {
+        for (int it = 0; it < NITER; ++it) {
             const int t = it * 32 + lane;
             if (t < T) { const float d = mag0[it] - mean; ssq += d * d; }
         }
@@ -101,7 +102,7 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
         }
         (void)invT;
 #pragma unroll
-        for (int it = 0; it < kFeatMaxIter; ++it) {
+        for (int it = 0; it < NITER; ++it) {
             const int t = it * 32 + lane;
             if (t < T) {
                 float* o = tile + ((size_t)t * C) * kFeatBinsPerCta + warp;
@@ -154,13 +155,15 @@ extern "C" int nsf_css_features(const float* X, int64_t T_long, int64_t T_valid,
     dim3 grid(ceil_div(kBins, kFeatBinsPerCta), n_seg);
     ProfScope prof(PROF_FEATURES, (double)n_seg * T * kBins * n_ch * (8.0 + (feat_lo ? (split_fmt == SPLIT_TF32 ? 8.0 : 4.0) : 4.0)), s);
     const size_t smem = (size_t)T * n_ch * kFeatBinsPerCta * sizeof(float);
-    if (n_ch == 7) {
-        NSF_CUDA(cudaFuncSetAttribute(css_features_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        css_features_kernel<7><<<grid, kFeatBinsPerCta * 32, smem, s>>>(reinterpret_cast<const float2*>(X), T_long, T_valid,
-                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf, split_fmt);
-    } else {
-        css_features_kernel<1><<<grid, kFeatBinsPerCta * 32, smem, s>>>(reinterpret_cast<const float2*>(X), T_long, T_valid,
-                                                                       seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf, split_fmt);
-    }
+#define NSF_FEAT_LAUNCH(CH, NI)                                                                                              \
+    do {                                                                                                                     \
+        NSF_CUDA(cudaFuncSetAttribute(css_features_kernel<CH, NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        css_features_kernel<CH, NI><<<grid, kFeatBinsPerCta * 32, smem, s>>>(reinterpret_cast<const float2*>(X), T_long,       \
+            T_valid, seg_first, T, hop, in_bias, in_scale, feat, feat_lo, ldf, split_fmt);                                   \
+    } while (0)
+    const bool small = T <= 32 * 6;
+    if (n_ch == 7) { if (small) NSF_FEAT_LAUNCH(7, 6); else NSF_FEAT_LAUNCH(7, 8); }
+    else           { if (small) NSF_FEAT_LAUNCH(1, 6); else NSF_FEAT_LAUNCH(1, 8); }
+#undef NSF_FEAT_LAUNCH
     return check_launch("css_features_kernel");
 }
