@@ -53,6 +53,11 @@ __device__ __forceinline__ void a2_barrel_stage(uint32_t (&w)[128], int lane) {
 #pragma unroll
     for (int i = 0; i < kA2Slots + SH - 1; ++i) w[i] = on ? w[i + SH] : w[i];
 }
+__device__ __forceinline__ float ex2_approx(float x) {          // MUFU.EX2, 2 ulp; ex2(-inf) = +0
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);       // .x (low half) = lo_elem
     return *reinterpret_cast<const uint32_t*>(&v);
@@ -227,7 +232,7 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             if (warp_valid) {
 #pragma unroll
                 for (int i = 0; i < kA2Slots; ++i) {
-                    const float e = exp2f(__uint_as_float(w[i]) - mx);
+                    const float e = ex2_approx(__uint_as_float(w[i]) - mx);
                     w[i] = __float_as_uint(e);
                     sum += e;
                 }

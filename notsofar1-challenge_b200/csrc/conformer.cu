@@ -192,6 +192,11 @@ __device__ __forceinline__ float glu1(float h, float w1a, float b1a, float w1g, 
     const float a = w1a * h + b1a, gt = w1g * h + b1g;
     return a * (1.f / (1.f + expf(-gt)));
 }
+// the same with MUFU-based exp and reciprocal (2 ulp): the fused conv kernel evaluates 57 M sigmoids per block
+__device__ __forceinline__ float glu1_fast(float h, float w1a, float b1a, float w1g, float b1g) {
+    const float a = w1a * h + b1a, gt = w1g * h + b1g;
+    return a * __fdividef(1.f, 1.f + __expf(-gt));
+}
 template <int NV>
 __global__ void __launch_bounds__(256)
 ln_glu_vec_kernel(const float* __restrict__ x, int M, const float* __restrict__ g, const float* __restrict__ b,
@@ -333,18 +338,31 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
         const bool c_ok = c0 + c4 * 4 < d;
         const float4 g4 = c_ok ? ldg4(ln_g + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 b4 = c_ok ? ldg4(ln_b + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = threadIdx.x / (kDwCh / 4); r < rows; r += blockDim.x / (kDwCh / 4)) {
-            const int t = r - pad;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t >= 0 && t < T && c_ok) {
-                const size_t row = (size_t)seg * T + t;
-                const float4 xv = ld4(x + row * d + c0 + c4 * 4);
-                const float2 st = __ldg(stats + row);
-                const float4 h = ln_apply(xv, st.x, st.y, g4, b4);
-                v = make_float4(glu1(h.x, w1a, b1a, w1g, b1g), glu1(h.y, w1a, b1a, w1g, b1g), glu1(h.z, w1a, b1a, w1g, b1g),
-                                glu1(h.w, w1a, b1a, w1g, b1g));
+        // four rows per trip: all global loads of a trip are in flight before the first use
+        constexpr int kRowStep = 256 / (kDwCh / 4);
+        for (int rb = threadIdx.x / (kDwCh / 4); rb < rows; rb += 4 * kRowStep) {
+            float4 xv[4];
+            float2 st[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = rb + u * kRowStep - pad;
+                const bool ok = t >= 0 && t < T && c_ok;
+                const size_t row = (size_t)seg * T + (ok ? t : 0);
+                xv[u] = ok ? ld4(x + row * d + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                st[u] = ok ? __ldg(stats + row) : make_float2(0.f, 0.f);
             }
-            st4(tile + r * kDwCh + c4 * 4, v);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = rb + u * kRowStep, t = r - pad;
+                if (r >= rows) break;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (t >= 0 && t < T && c_ok) {
+                    const float4 h = ln_apply(xv[u], st[u].x, st[u].y, g4, b4);
+                    v = make_float4(glu1_fast(h.x, w1a, b1a, w1g, b1g), glu1_fast(h.y, w1a, b1a, w1g, b1g),
+                                    glu1_fast(h.z, w1a, b1a, w1g, b1g), glu1_fast(h.w, w1a, b1a, w1g, b1g));
+                }
+                st4(tile + r * kDwCh + c4 * 4, v);
+            }
         }
     }
     __syncthreads();
