@@ -176,6 +176,14 @@ int nsf_istft(const float* S_st, int n_streams, int64_t T_long, float* wav, void
  * peak [n_streams] f32 scratch/output (max |x| per stream). */
 int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, float* peak, int16_t* pcm, void* stream);
 
+/* CSS -> diarization hand-off without the disk round trip.  Replaces read_wav(normalize=True) (utils/audio_utils.py:10-34:
+ * int16 / 32767) + the per-(word, scale) slicing and pad_sequence of extract_speaker_embedding_for_words
+ * (diarization/word_based_diarization.py:78-104): out[i][j] = pcm[stream_id[i]][start[i] + j] / 32767 for j < len[i], else 0.
+ * pcm [n_streams][n] int16 (the output of nsf_peaknorm_pcm16), stream_id / start / len [n_crops] on the device,
+ * out [n_crops][max_len] f32.  The integer crop plan itself is host logic (notsofar_b200.diarization.word_crop_plan). */
+int nsf_gather_crops(const int16_t* pcm, int n_streams, int64_t n, const int32_t* stream_id, const int64_t* start,
+                     const int32_t* len, int n_crops, int64_t max_len, float* out, void* stream);
+
 /* Test hook: C[M][N] = A[M][K] * W[N][K]^T + bias with the selected engine (row-major, K contiguous;
  * K % 32 == 0, lda/ldw multiples of 4).  Used by the parity tests to check the tcgen05 GEMM
  * against the CUDA-core one. */

@@ -1,0 +1,81 @@
+"""Drop-in counterpart of the reference's ASR plug-in (asr/asr.py): ``WhisperAsrCfg`` and ``asr_inference`` with the
+reference's signature, cache file, per-stream loop and segments_df layout (asr.py:31-101).
+
+The transcription itself is openai-whisper in the reference (``whisper.load_model`` / ``model.transcribe``, asr.py:69-74):
+a third-party package that is absent offline together with its weights and tokenizer (parity unpinned).
+It is reached through one plug-in point, ``set_transcriber``; a transcriber gets a stream (a WAV path, or -- extension --
+the device-resident PCM16 stream the CSS stage produced) and returns whisper's result dict
+``{'segments': [{'start', 'end', 'text', 'words': [{'word', 'start', 'end'}, ...]}, ...]}``.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Callable, Optional
+
+import pandas as pd
+
+
+@dataclass
+class WhisperAsrCfg:
+    """asr.py:15-28, field for field."""
+    model_name: str = 'large-v2'  # use 'large-v2' for experiments, use 'tiny' for fast debugging
+    language: Optional[str] = 'en'  # language that the speech is in (if None, whisper runs language ID)
+    word_level_time_stamps: bool = True
+    beam_size: Optional[int] = 5
+    hallucination_silence_threshold: Optional[float] = 2.
+
+    def text_normalizer(self):
+        raise NotImplementedError("the chime8 text normaliser (utils/text_norm_whisper_like) belongs to scoring, outside the hot path")
+
+    def assert_valid(self):
+        assert self.model_name in ['tiny.en', 'tiny', 'base.en', 'base', 'small.en', 'small', 'medium.en',
+                                   'medium', 'large-v1', 'large-v2', 'large-v3', 'large']
+
+
+_TRANSCRIBER: Optional[Callable] = None     # (stream, cfg: WhisperAsrCfg, options: dict) -> whisper result dict
+
+
+def set_transcriber(fn: Optional[Callable]):
+    global _TRANSCRIBER
+    _TRANSCRIBER = fn
+
+
+def segments_frame(results: dict, session, wav_file) -> Optional[pd.DataFrame]:
+    """asr.py:75-96: whisper's per-stream result -> the segments_df rows of that stream (None when empty)."""
+    if len(results['segments']) == 0:
+        return None
+    raw = pd.DataFrame(results['segments'])
+    word_start_end = raw['words'].apply(lambda x: [[w['word'], w['start'], w['end']] for w in x])
+    df = pd.DataFrame({'start_time': raw['start'], 'end_time': raw['end'], 'text': raw['text'], 'word_timing': word_start_end})
+    df['meeting_id'] = session.meeting_id
+    df['session_id'] = session.session_id
+    df['wav_file_name'] = wav_file
+    return df
+
+
+def asr_inference(out_dir: str, session: pd.Series, cfg: WhisperAsrCfg, fetch_from_cache: bool, streams=None):
+    """Same contract as the reference's asr_inference (asr.py:31-101).  ``streams`` (optional, extension): one
+    device-resident stream per entry of session.sep_wav_file_names, handed to the transcriber instead of the path."""
+    cfg.assert_valid()
+    options = dict(task="transcribe", language=cfg.language, word_timestamps=cfg.word_level_time_stamps,
+                   beam_size=cfg.beam_size, hallucination_silence_threshold=cfg.hallucination_silence_threshold)
+    wav_files = session.sep_wav_file_names
+    assert isinstance(wav_files, list)
+    out_file = Path(out_dir) / 'asr' / session.session_id / cfg.model_name / "all_segments_df.pkl"
+    if fetch_from_cache and out_file.exists():
+        return pd.read_pickle(out_file)
+    if _TRANSCRIBER is None:
+        from ._cabi import NsfError
+        raise NsfError("asr_inference needs a transcriber (the reference's is openai-whisper, absent offline: SURVEY 8c); "
+                       "register one with notsofar_b200.asr.set_transcriber")
+    dfs = []
+    for i, wav_file in enumerate(wav_files):
+        results = _TRANSCRIBER(streams[i] if streams is not None else str(wav_file), cfg, options)
+        df = segments_frame(results, session, wav_file)
+        if df is not None:
+            dfs.append(df)
+    all_segments_df = pd.concat(dfs, ignore_index=True)
+    out_file.parent.mkdir(parents=True, exist_ok=True)
+    all_segments_df.to_pickle(out_file)
+    return all_segments_df

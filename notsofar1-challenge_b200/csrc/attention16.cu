@@ -198,12 +198,10 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 const int u_lo = (T - 1) - (kA2Slots * hh + kA2Slots - 1);
                 const uint32_t wcol = (uint32_t)(kA2ColB + 32 * q + u_lo);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t tmp[32];
-                    tmem_ld_32x32(tmem_base + lane_sel + wcol + 32 * k, tmp);
+                for (int k = 0; k < 4; ++k) tmem_ld_32x32_nowait(tmem_base + lane_sel + wcol + 32 * k, w + 32 * k);
+                tmem_ld_wait();                         // the four window loads overlap
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) w[32 * k + j] = tmp[j];
-                }
+                for (int k = 0; k < 4; ++k) tmem_ld_fence(w + 32 * k);
                 a2_barrel_stage<16>(w, lane);
                 a2_barrel_stage<8>(w, lane);
                 a2_barrel_stage<4>(w, lane);
@@ -251,9 +249,8 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                         const int j = 16 * cc + jj;
                         const float p0 = __uint_as_float(w[kA2Slots - 1 - 2 * j]) * inv;
                         const float p1 = __uint_as_float(w[kA2Slots - 2 - 2 * j]) * inv;
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
-                        ph[jj] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                        pl[jj] = pack_bf16(p0 - __bfloat162float(h0), p1 - __bfloat162float(h1));
+                        ph[jj] = pack_bf16(p0, p1);                                   // one packed convert (F2FP)
+                        pl[jj] = pack_bf16(p0 - __uint_as_float(ph[jj] << 16), p1 - __uint_as_float(ph[jj] & 0xffff0000u));
                     }
                     tmem_st_32x16(tmem_base + lane_sel + (uint32_t)(48 * hh + 16 * cc), ph);
                     tmem_st_32x16(tmem_base + lane_sel + (uint32_t)(kA2ColPlo + 48 * hh + 16 * cc), pl);

@@ -137,7 +137,15 @@ __device__ __forceinline__ void split_store4(int fmt, float* hi, float* lo, size
     } else {
         uint16_t h[4], l[4];
         if (fmt == SPLIT_BF16) {
-            split_bf16(v.x, h[0], l[0]); split_bf16(v.y, h[1], l[1]); split_bf16(v.z, h[2], l[2]); split_bf16(v.w, h[3], l[3]);
+            // packed converts (F2FP) instead of four scalar F2F pairs
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - __low2float(h01), v.y - __high2float(h01));
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - __low2float(h23), v.w - __high2float(h23));
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + idx) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(lo) + idx) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            return;
         } else {
             split_f16(v.x, kF16ActScale, h[0], l[0]); split_f16(v.y, kF16ActScale, h[1], l[1]);
             split_f16(v.z, kF16ActScale, h[2], l[2]); split_f16(v.w, kF16ActScale, h[3], l[3]);

@@ -317,3 +317,34 @@ extern "C" int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, fl
     pcm16_kernel<<<grid, 256, 0, s>>>(wav, n, peak, pcm);
     return check_launch("pcm16_kernel");
 }
+
+// ------------------------------------------------------------------------------------------- word crops (CSS -> diarization hand-off)
+// The reference re-reads the 16-bit WAVs the CSS stage wrote (read_wav(normalize=True): int16 / 32767,
+// utils/audio_utils.py:10-34), cuts wavs[channel][start:end] per (word, scale) and zero-pads the batch
+// (pad_sequence, diarization/word_based_diarization.py:98-104).  Here the PCM16 streams never leave HBM.
+namespace nsf {
+__global__ void __launch_bounds__(256)
+gather_crops_kernel(const int16_t* __restrict__ pcm, int64_t n, const int32_t* __restrict__ stream_id,
+                    const int64_t* __restrict__ start, const int32_t* __restrict__ len, int64_t max_len,
+                    float* __restrict__ out) {
+    const int crop = blockIdx.y;
+    const int16_t* src = pcm + (size_t)stream_id[crop] * n + start[crop];
+    const int l = len[crop];
+    float* dst = out + (size_t)crop * max_len;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < max_len; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = i < l ? (float)src[i] / 32767.f : 0.f;
+}
+}  // namespace nsf
+
+extern "C" int nsf_gather_crops(const int16_t* pcm, int n_streams, int64_t n, const int32_t* stream_id, const int64_t* start,
+                                const int32_t* len, int n_crops, int64_t max_len, float* out, void* stream) {
+    NSF_REQUIRE(pcm && stream_id && start && len && out, "nsf_gather_crops: null pointer");
+    NSF_REQUIRE(n_streams >= 1 && n >= 0 && n_crops >= 0 && max_len >= 0, "nsf_gather_crops: bad sizes");
+    if (n_crops == 0 || max_len == 0) return NSF_OK;
+    NSF_REQUIRE(n_crops <= 65535, "nsf_gather_crops: at most 65535 crops per call");
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid((unsigned)nsf::ceil_div64(max_len, 256 * 4) > 64 ? 64 : (unsigned)nsf::ceil_div64(max_len, 256 * 4), (unsigned)n_crops);
+    if (grid.x == 0) grid.x = 1;
+    nsf::gather_crops_kernel<<<grid, 256, 0, s>>>(pcm, n, stream_id, start, len, max_len, out);
+    return nsf::check_launch("gather_crops_kernel");
+}
