@@ -62,7 +62,7 @@ def _golden_segments(g):
 
 
 def _sep(N, weights, dev, engine=None, **kw):
-    return N.ConformerCssB200(weights, device=dev, gemm_engine=N.GEMM_TC_3XTF32 if engine is None else engine, **kw)
+    return N.ConformerCssB200(weights, device=dev, **({} if engine is None else {'gemm_engine': engine}), **kw)
 
 
 # ----------------------------------------------------------------------------------------------- STFT / iSTFT
@@ -151,7 +151,7 @@ def test_features_vs_reference_golden(nb, dev, golden, small_weights):
 
 def test_features_batched_and_padded_tail_vs_oracle(nb, dev, golden, small_weights):
     """All segments in one launch from the long-form X, incl. the zero-padded last segment (css.py:185-190)."""
-    sep = _sep(nb, small_weights, dev)
+    sep = _sep(nb, small_weights, dev, engine=nb.GEMM_TC_3XTF32)
     plan, segs = _golden_segments(golden)
     T, hop = plan.segment_frames, plan.hop_frames
     X = torch.from_numpy(golden["stft"]).to(dev)
