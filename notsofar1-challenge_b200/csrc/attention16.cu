@@ -19,7 +19,8 @@
 
 namespace nsf {
 
-constexpr int kA2Threads = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 softmax / epilogue
+constexpr int kA2Split = 3;                      // softmax threads per query row (one TMEM lane quarter each: 4 * kA2Split warps)
+constexpr int kA2Threads = 64 + 128 * kA2Split; // warp 0 TMA, warp 1 MMA, warps 2..13 softmax / epilogue
 constexpr int kA2Dk = 64;
 constexpr int kA2QHalf = 128 * 128;             // one plane of Q: 128 rows x 128 B
 constexpr int kA2KHalf = 192 * 128;             // one plane of K: 192 rows
@@ -33,8 +34,10 @@ constexpr int kA2TileBytes = kA2PeOff + 2 * kA2PeHalf;          // 208 KB
 constexpr int kA2ColB = 192;                    // first TMEM column of Bm
 constexpr int kA2ColPlo = 96;                   // first TMEM column of the remainder plane of P (head plane at 0)
 constexpr int kA2ColO = 384;                    // first TMEM column of O
-constexpr int kA2Slots = 96;                    // key positions per softmax thread (two threads per row)
-constexpr int kA2SmemBytes = kA2TileBytes + 2048 /*pair exchange*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+constexpr int kA2Slots = 192 / kA2Split;         // key positions per softmax thread: 64
+constexpr int kA2XchBytes = 2 * kA2Split * 128 * 4;             // (max, sum) exchange between the threads of a row
+constexpr int kA2SmemBytes = kA2TileBytes + kA2XchBytes + 256 /*barriers*/ + 1024 /*alignment*/;
+static_assert(kA2Slots % 32 == 0 && kA2Slots + 32 <= 96, "softmax thread geometry");
 
 struct Attn16Params {
     int n_bh, n_heads, T, Tp;
@@ -48,7 +51,7 @@ __device__ __forceinline__ void a2_named_bar_sync(int id, int n_threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n_threads) : "memory");
 }
 template <int SH>
-__device__ __forceinline__ void a2_barrel_stage(uint32_t (&w)[128], int lane) {
+__device__ __forceinline__ void a2_barrel_stage(uint32_t (&w)[kA2Slots + 32], int lane) {
     const bool on = (lane & SH) != 0;
 #pragma unroll
     for (int i = 0; i < kA2Slots + SH - 1; ++i) w[i] = on ? w[i + SH] : w[i];
@@ -74,8 +77,8 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     const uint32_t base = (raw + 1023u) & ~1023u;
     unsigned char* gen = smem_raw + (base - raw);
     const uint32_t q_smem = base + kA2QOff, k_smem = base + kA2KOff, v_smem = base + kA2VOff, pe_smem = base + kA2PeOff;
-    float* xch = reinterpret_cast<float*>(gen + kA2TileBytes);                 // [2 (max, sum)][2 (half)][128]
-    const uint32_t bars = base + kA2TileBytes + 2048;
+    float* xch = reinterpret_cast<float*>(gen + kA2TileBytes);                 // [2 (max, sum)][kA2Split][128]
+    const uint32_t bars = base + kA2TileBytes + kA2XchBytes;
     const uint32_t qk_full = bars, qk_empty = bars + 8, v_full = bars + 16, v_empty = bars + 24, pe_full = bars + 32;
     const uint32_t s_ready = bars + 40, p_ready = bars + 48, o_ready = bars + 56, o_drained = bars + 64;
     const uint32_t tmem_ptr_addr = bars + 72;
@@ -96,7 +99,7 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
 
     if (threadIdx.x == 0) {
         mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(pe_full, 1);
-        mbar_init(s_ready, 1); mbar_init(p_ready, 8); mbar_init(o_ready, 1); mbar_init(o_drained, 8);
+        mbar_init(s_ready, 1); mbar_init(p_ready, 4 * kA2Split); mbar_init(o_ready, 1); mbar_init(o_drained, 4 * kA2Split);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -178,38 +181,39 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             }
         }
     } else {
-        // ===== softmax / epilogue warps
+        // ===== softmax / epilogue warps: kA2Split threads per query row, kA2Slots keys each
         const int q = warp & 3;                          // TMEM lane quarter
-        const int hh = (warp - 2) >> 2;                  // which half of the key positions
+        const int hh = (warp - 2) >> 2;                  // which part of the key positions
         const int r = 32 * q + lane;                     // row inside the block
         const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
-        float* xch_max = xch;                            // [2][128]
-        float* xch_sum = xch + 256;
+        float* xch_max = xch;                            // [kA2Split][128]
+        float* xch_sum = xch + kA2Split * 128;
         const bool warp_valid = (R0 + 32 * q) < T;       // warp-uniform, fixed for the CTA's row block
         uint32_t it = 0;
         for (int bh = first; bh < p.n_bh; bh += stride, ++it) {
             mbar_wait(s_ready, it & 1);
             tcgen05_fence_after();
 
-            uint32_t w[128];                             // fp32 bit patterns
+            uint32_t w[kA2Slots + 32];                   // fp32 bit patterns
             float mx = -INFINITY;
             if (warp_valid) {
-                // window of Bm: columns kA2ColB + 32 q + u_lo + [0, 128); the thread needs element lane + 95 - slot
+                // window of Bm: columns kA2ColB + 32 q + u_lo + [0, kA2Slots + 32); the thread needs element
+                // lane + (kA2Slots - 1) - slot
                 const int u_lo = (T - 1) - (kA2Slots * hh + kA2Slots - 1);
                 const uint32_t wcol = (uint32_t)(kA2ColB + 32 * q + u_lo);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tmem_ld_32x32_nowait(tmem_base + lane_sel + wcol + 32 * k, w + 32 * k);
-                tmem_ld_wait();                         // the four window loads overlap
+                for (int k = 0; k < kA2Slots / 32 + 1; ++k) tmem_ld_32x32_nowait(tmem_base + lane_sel + wcol + 32 * k, w + 32 * k);
+                tmem_ld_wait();                         // the window loads overlap
 #pragma unroll
-                for (int k = 0; k < 4; ++k) tmem_ld_fence(w + 32 * k);
+                for (int k = 0; k < kA2Slots / 32 + 1; ++k) tmem_ld_fence(w + 32 * k);
                 a2_barrel_stage<16>(w, lane);
                 a2_barrel_stage<8>(w, lane);
                 a2_barrel_stage<4>(w, lane);
                 a2_barrel_stage<2>(w, lane);
                 a2_barrel_stage<1>(w, lane);
-                // scores in the log2 domain: slot s <-> key t2 = 96 hh + s uses w[95 - s]
+                // scores in the log2 domain: slot s <-> key t2 = kA2Slots hh + s uses w[kA2Slots - 1 - s]
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
+                for (int cc = 0; cc < kA2Slots / 32; ++cc) {
                     uint32_t sv[32];
                     tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)(kA2Slots * hh + 32 * cc), sv);
 #pragma unroll
@@ -224,8 +228,9 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 }
             }
             xch_max[hh * 128 + r] = mx;
-            a2_named_bar_sync(1 + q, 64);
-            mx = fmaxf(mx, xch_max[(hh ^ 1) * 128 + r]);
+            a2_named_bar_sync(1 + q, 32 * kA2Split);
+#pragma unroll
+            for (int o = 1; o < kA2Split; ++o) mx = fmaxf(mx, xch_max[((hh + o) % kA2Split) * 128 + r]);
             float sum = 0.f;
             if (warp_valid) {
 #pragma unroll
@@ -236,13 +241,19 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 }
             }
             xch_sum[hh * 128 + r] = sum;
-            a2_named_bar_sync(1 + q, 64);
-            sum += xch_sum[(hh ^ 1) * 128 + r];
+            a2_named_bar_sync(1 + q, 32 * kA2Split);
+            {
+                // every thread of the row adds the partial sums in the same (part) order: identical totals
+                float tot = 0.f;
+#pragma unroll
+                for (int o = 0; o < kA2Split; ++o) tot += xch_sum[o * 128 + r];
+                sum = tot;
+            }
             if (warp_valid) {
                 const float inv = 1.f / sum;
-                // packed column j of this half holds keys 96 hh + 2j (low half) and 2j + 1 (high half)
+                // packed column j of this part holds keys kA2Slots hh + 2j (low half) and 2j + 1 (high half)
 #pragma unroll
-                for (int cc = 0; cc < 3; ++cc) {
+                for (int cc = 0; cc < kA2Slots / 32; ++cc) {
                     uint32_t ph[16], pl[16];
 #pragma unroll
                     for (int jj = 0; jj < 16; ++jj) {
@@ -252,8 +263,8 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                         ph[jj] = pack_bf16(p0, p1);                                   // one packed convert (F2FP)
                         pl[jj] = pack_bf16(p0 - __uint_as_float(ph[jj] << 16), p1 - __uint_as_float(ph[jj] & 0xffff0000u));
                     }
-                    tmem_st_32x16(tmem_base + lane_sel + (uint32_t)(48 * hh + 16 * cc), ph);
-                    tmem_st_32x16(tmem_base + lane_sel + (uint32_t)(kA2ColPlo + 48 * hh + 16 * cc), pl);
+                    tmem_st_32x16(tmem_base + lane_sel + (uint32_t)(kA2Slots / 2 * hh + 16 * cc), ph);
+                    tmem_st_32x16(tmem_base + lane_sel + (uint32_t)(kA2ColPlo + kA2Slots / 2 * hh + 16 * cc), pl);
                 }
                 tmem_st_wait();
             }
@@ -261,10 +272,10 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(p_ready);
 
-            // ---- O = P V: 32 columns per warp, split and stored to the [M][d_model] activation
+            // ---- O = P V: 32 columns per warp (parts 0 and 1), split and stored to the [M][d_model] activation
             mbar_wait(o_ready, it & 1);
             tcgen05_fence_after();
-            if (warp_valid) {
+            if (warp_valid && hh < 2) {
                 uint32_t ov[32];
                 tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)(kA2ColO + 32 * hh), ov);
                 const int t1 = R0 + r;
@@ -272,10 +283,12 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                     const int seg = bh / p.n_heads, h = bh - seg * p.n_heads;
                     const size_t o = ((size_t)seg * T + t1) * p.ldo + (size_t)h * kA2Dk + 32 * hh;
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4)
-                        split_store4(p.out_fmt, p.out_hi, p.out_lo, o + 4 * k4,
-                                     make_float4(__uint_as_float(ov[4 * k4]), __uint_as_float(ov[4 * k4 + 1]),
-                                                 __uint_as_float(ov[4 * k4 + 2]), __uint_as_float(ov[4 * k4 + 3])));
+                    for (int k8 = 0; k8 < 4; ++k8) {
+                        float v8[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v8[e] = __uint_as_float(ov[8 * k8 + e]);
+                        split_store8(p.out_fmt, p.out_hi, p.out_lo, o + 8 * k8, v8);
+                    }
                 }
             }
             tcgen05_fence_before();
@@ -297,7 +310,10 @@ int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const
                   const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
                   float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream) {
     if (T < 2 || T > 192 || Tp % 32 != 0 || Tp < T || Tp > 192) { set_error("attn16: T=%d Tp=%d unsupported", T, Tp); return NSF_ERR_UNSUPPORTED; }
-    if (maxlen < T || (ldo & 3)) { set_error("attn16: maxlen=%d ldo=%lld", maxlen, (long long)ldo); return NSF_ERR_INVALID_ARG; }
+    if (maxlen < T || (ldo & 7) || ((uintptr_t)out_hi & 15) || ((uintptr_t)out_lo & 15)) {
+        set_error("attn16: maxlen=%d ldo=%lld (ldo must be a multiple of 8, outputs 16-byte aligned)", maxlen, (long long)ldo);
+        return NSF_ERR_INVALID_ARG;
+    }
     const int n_bh = n_seg * n_heads;
     CUtensorMap mq_hi, mq_lo, mk_hi, mk_lo, mp_hi, mp_lo, mv_hi, mv_lo;
     int rc;
