@@ -136,6 +136,18 @@ int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float* X, int64_t
              int64_t seg_first, int n_seg, int T, int hop, int n_bins, float mask_floor,
              float* Y, void* stream);
 
+/* Separation without the beamformer (single-channel input, or CssCfg.mc_mvdr = False): css.py:218-227,
+ *   Y[seg][s][f][t] = X[f][(seg_first+seg)*hop + t][channel 0] * max(masks[seg][s][f][t], mask_floor).
+ * Layouts and segment geometry as in nsf_mvdr; X may have any number of channels (the reference channel is 0). */
+int nsf_mask_apply(const float* masks, int n_spk, int n_noise, const float* X, int64_t T_long, int64_t T_valid, int n_ch,
+                   int64_t seg_first, int n_seg, int T, int hop, int n_bins, float mask_floor, float* Y, void* stream);
+
+/* CssCfg.normalize_segment_power (css.py:233-247): every segment of Y [n_seg][S][n_bins][T] is scaled in place by
+ *   sqrt(mean_{f,t<t_seg} |X_ref|^2) / sqrt(mean_{f,t<t_seg} |sum_s Y_s|^2),   t_seg = min(T, mix_frames - segment start),
+ * mix_frames = frames of the (possibly zero-padded) long-form STFT (css.py:159-169).  ratio [n_seg] f32 scratch / output. */
+int nsf_segment_power_norm(float* Y, int n_spk, const float* X, int64_t T_long, int64_t T_valid, int n_ch, int64_t seg_first,
+                           int n_seg, int T, int hop, int n_bins, int64_t mix_frames, float* ratio, void* stream);
+
 /* PIT stitching costs.  Replaces PitWrapper._opt_perm_loss (css/training/losses.py:50-71) as called
  * at css.py:276: cost[i][a][b] = mean_{f,t} loss(left_a, right_b) over the `overlap` trailing frames
  * of segment i-1 and leading frames of segment i, for i = 1..n_seg-1 (cost[0] is zero).

@@ -53,6 +53,8 @@ SIGNATURES = {
     "nsf_peaknorm_pcm16": (i32, [c_f32p, i32, i64, c_f32p, C.c_void_p, C.c_void_p]),
     "nsf_attention_test_workspace_bytes": (i64, [i32, i32, i32, i32]),
     "nsf_attention_test": (i32, [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
+    "nsf_mask_apply": (i32, [c_f32p, i32, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, C.c_float, c_f32p, C.c_void_p]),
+    "nsf_segment_power_norm": (i32, [c_f32p, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, i64, c_f32p, C.c_void_p]),
     "nsf_gather_crops": (i32, [C.c_void_p, i32, i64, C.c_void_p, C.c_void_p, C.c_void_p, i32, i64, c_f32p, C.c_void_p]),
     "nsf_attention16_test": (i32, [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_gemm_test": (i32, [i32, c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, C.c_void_p, i64, C.c_void_p]),

@@ -234,10 +234,8 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
     n_samples, num_channels = x.shape
     device = x.device
     lib = _cabi.load()
-    if num_channels == 1 or not cfg.mc_mvdr:
-        raise NotImplementedError("single-channel / mask-only CSS is not built yet (SURVEY 8f-4); use mc_mvdr=True with 7 mics")
-    if cfg.normalize_segment_power:
-        raise NotImplementedError("normalize_segment_power=True is not built yet")
+    assert num_channels == separator.num_mics, f'the model expects {separator.num_mics} channel(s), got {num_channels}'
+    use_mvdr = num_channels > 1 and cfg.mc_mvdr              # css.py:209
     assert cfg.stitching_loss in ('l1', 'mse'), f'unexpected stitching_loss: {cfg.stitching_loss}'
     assert cfg.stitching_input in ('mask', 'separation_result'), f'unexpected stitching_input: {cfg.stitching_input}'
 
@@ -268,7 +266,12 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
                 separator.stft_frames(x, X, frames_done, f_need)
                 frames_done = f_need
             separator.masks(X, T_valid, s0, nb, T, hop, out=masks[s0:s0 + nb])
-            separator.mvdr(masks[s0:s0 + nb], X, T_valid, s0, hop, mask_floor, out=Y[s0:s0 + nb])
+            if use_mvdr:
+                separator.mvdr(masks[s0:s0 + nb], X, T_valid, s0, hop, mask_floor, out=Y[s0:s0 + nb])
+            else:
+                separator.mask_apply(masks[s0:s0 + nb], X, T_valid, s0, hop, mask_floor, out=Y[s0:s0 + nb])
+            if cfg.normalize_segment_power:
+                separator.power_norm(Y[s0:s0 + nb], X, T_valid, s0, hop, mix_frames)
 
         if feeder is not None:
             feeder.ready(n_samples)       # every copy has been ordered before the buffers can be recycled

@@ -353,6 +353,30 @@ class ConformerCssB200:
                                        _cabi.stream_ptr()), "nsf_mvdr")
         return out
 
+    def mask_apply(self, masks: torch.Tensor, X: torch.Tensor, T_valid: int, seg_first: int, hop: int, mask_floor: float,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Separation without the beamformer (css.py:218-227): reference channel x floored mask -> Y [n_seg, S, F, T]."""
+        self._require_cuda()
+        n_seg, n_m, n_bins, T = masks.shape
+        assert masks.dtype == torch.float32 and masks.is_contiguous() and X.is_contiguous()
+        if out is None:
+            out = torch.empty((n_seg, self.num_spks, n_bins, T), dtype=torch.complex64, device=masks.device)
+        _cabi.check(self._lib.nsf_mask_apply(_cabi.ptr(masks), self.num_spks, n_m - self.num_spks, _cabi.ptr(X), X.shape[1], T_valid,
+                                             X.shape[2], seg_first, n_seg, T, hop, n_bins, float(mask_floor), _cabi.ptr(out),
+                                             _cabi.stream_ptr()), "nsf_mask_apply")
+        return out
+
+    def power_norm(self, Y: torch.Tensor, X: torch.Tensor, T_valid: int, seg_first: int, hop: int, mix_frames: int) -> torch.Tensor:
+        """CssCfg.normalize_segment_power (css.py:233-247), in place on Y [n_seg, S, F, T]; returns the per-segment ratios."""
+        self._require_cuda()
+        n_seg, S, n_bins, T = Y.shape
+        assert Y.dtype == torch.complex64 and Y.is_contiguous() and X.is_contiguous()
+        ratio = torch.empty((n_seg,), dtype=torch.float32, device=Y.device)
+        _cabi.check(self._lib.nsf_segment_power_norm(_cabi.ptr(Y), S, _cabi.ptr(X), X.shape[1], T_valid, X.shape[2], seg_first, n_seg,
+                                                     T, hop, n_bins, mix_frames, _cabi.ptr(ratio), _cabi.stream_ptr()),
+                    "nsf_segment_power_norm")
+        return ratio
+
     def istft_device(self, S_st: torch.Tensor) -> torch.Tensor:
         """S_st [n_streams, T_long, F] complex64 (frame-major) -> wav [n_streams, (T_long-1)*256+512]."""
         self._require_cuda()
@@ -380,7 +404,8 @@ class ConformerCssB200:
         """[Batch, F, T, Mics] complex -> {'spk_masks': [Batch, F, T, S], 'noise_masks': [Batch, F, T, Nn]}."""
         self._require_cuda()
         assert torch.is_complex(stft)
-        assert stft.dim() == 4, "single-channel model is not built yet"
+        if stft.dim() == 3:                                 # single-channel model: [Batch, F, T]
+            stft = stft.unsqueeze(-1)
         stft = stft.to(self.device)
         B, F_, T, c = stft.shape
         outs = []

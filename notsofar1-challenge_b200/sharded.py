@@ -143,8 +143,6 @@ class ShardWorker:
         self.shards = [make_shard(self.plan, r, world) for r in range(world)]
         self.sh = self.shards[rank]
         self.lib = _cabi.load()
-        if cfg.normalize_segment_power:
-            raise NotImplementedError("normalize_segment_power=True is not built yet")
         assert cfg.stitching_loss in ('l1', 'mse') and cfg.stitching_input in ('mask', 'separation_result')
 
     # ---- phase 1: STFT, mask network, MVDR and stitching costs of the local block --------------------------------
@@ -165,9 +163,8 @@ class ShardWorker:
             return torch.zeros((0, S, S), dtype=torch.float32, device=device)
         assert x.shape[0] == sh.sample_hi - sh.sample_lo, (x.shape, sh)
         num_channels = x.shape[1]
-        if num_channels == 1 or not cfg.mc_mvdr:
-            raise NotImplementedError("single-channel / mask-only CSS is not built yet")
-        mask_floor = 10. ** (cfg.mc_mask_floor_db / 20.)
+        use_mvdr = num_channels > 1 and cfg.mc_mvdr
+        mask_floor = 10. ** ((cfg.mc_mask_floor_db if num_channels > 1 else cfg.sc_mask_floor_db) / 20.)
         with torch.cuda.device(device):
             X = sep.stft_alloc(num_channels, sh.n_frames, sh.valid_frames, device)
             self.masks = torch.empty((n_loc, n_masks, NUM_BINS, T), dtype=torch.float32, device=device)
@@ -181,7 +178,13 @@ class ShardWorker:
                     sep.stft_frames(x, X, frames_done, f_need)
                     frames_done = f_need
                 sep.masks(X, sh.valid_frames, s0, nb, T, hop, out=self.masks[s0:s0 + nb])
-                sep.mvdr(self.masks[s0:s0 + nb], X, sh.valid_frames, s0, hop, mask_floor, out=self.Y[s0:s0 + nb])
+                if use_mvdr:
+                    sep.mvdr(self.masks[s0:s0 + nb], X, sh.valid_frames, s0, hop, mask_floor, out=self.Y[s0:s0 + nb])
+                else:
+                    sep.mask_apply(self.masks[s0:s0 + nb], X, sh.valid_frames, s0, hop, mask_floor, out=self.Y[s0:s0 + nb])
+                if cfg.normalize_segment_power:
+                    # the reference's t = en - st counts frames up to mix_frames (global): local pitch ends there too
+                    sep.power_norm(self.Y[s0:s0 + nb], X, sh.valid_frames, s0, hop, plan.mix_frames - sh.frame0)
             if feeder is not None:
                 feeder.ready(x.shape[0])
             costs = torch.empty((n_loc, S, S), dtype=torch.float32, device=device)

@@ -61,7 +61,9 @@ def build_separator(weights: Dict[str, np.ndarray]):
     from .css_oracle import net_dims
     ns = load()
     d = net_dims(weights)
-    cfg = ns.cw.ConformerCssCfg(nnet_conf=ns.cw.NnetCfg(conformer_conf=ns.cw.ConformerCfg(
+    # single-channel models have no IPD pairs (conformer_v1.0_sc.yaml: extractor_conf.ipd_index = '')
+    ext = ns.cw.ExtractorCfg(ipd_index='') if d.in_features == 257 else ns.cw.ExtractorCfg()
+    cfg = ns.cw.ConformerCssCfg(extractor_conf=ext, nnet_conf=ns.cw.NnetCfg(conformer_conf=ns.cw.ConformerCfg(
         attention_dim=d.d_model, attention_heads=d.n_heads, num_blocks=d.n_blocks,
         linear_units=d.d_ff, kernel_size=d.kernel_size, dropout_rate=0.0),
         in_features=d.in_features))

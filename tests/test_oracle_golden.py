@@ -1,5 +1,7 @@
 """The oracle (oracle/css_oracle.py) against golden vectors produced by the reference itself
 (tests/golden/make_golden.py) and against the reference's own known-answer tests.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -135,3 +137,37 @@ def test_stitch_chain_vs_reference(golden, small_weights):
     wavs32, _ = O.separate_and_stitch(x, small_weights, 16000, _cfg(golden), masks_override=golden["masks"])
     for k in range(3):
         assert rel_l2(wavs32[k], golden["wavs"][k]) < max(5 * floor, 1e-3)
+
+
+# ----------------------------------------------------------------------------------------------- no-beamformer modes
+@pytest.fixture(scope="module")
+def golden_sc():
+    return dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "css_golden_sc.npz")))
+
+
+@pytest.mark.parametrize("mode", ["sc", "mc_nobf"])
+def test_oracle_no_beamformer_modes_vs_reference(golden, golden_sc, mode):
+    """Single-channel CSS with normalize_segment_power, and 7-channel CSS with mc_mvdr=False and a clipping mask floor
+    (css.py:218-247), against the reference's own run (tests/golden/make_golden_sc.py)."""
+    x = (golden["mixture_int16"].astype(np.float32) / np.float32(golden["mixture_scale"]))[None]
+    g = {k[len(mode) + 1:]: v for k, v in golden_sc.items() if k.startswith(mode + "_")}
+    if mode == "sc":
+        x = x[:, :, :1]
+        w = O.random_weights(seed=2, d_model=128, n_heads=2, d_ff=256, n_blocks=2, in_features=257)
+        cfg = O.OracleCfg(activity_th=float(g["th"]), segment_size_sec=1.0, hop_size_sec=0.5, normalize_segment_power=True)
+    else:
+        w = O.random_weights(seed=1, d_model=128, n_heads=2, d_ff=256, n_blocks=2)
+        cfg = O.OracleCfg(activity_th=float(g["th"]), segment_size_sec=1.0, hop_size_sec=0.5, mc_mvdr=False, mc_mask_floor_db=-20.0)
+    if mode == "sc":
+        wavs, side = O.separate_and_stitch(x, w, 16000, cfg, return_stages=True)
+        assert rel_l2(side["masks"], g["masks"]) < 1e-4
+    else:
+        # 7-channel features recomputed outside torch flip IPD signs in the real-valued DC / Nyquist bins (1e-3-level mask
+        # differences, see test_separate_protocol): the stages after the network are checked on the reference's masks
+        wavs, side = O.separate_and_stitch(x, w, 16000, cfg, return_stages=True, masks_override=g["masks"])
+    assert np.array_equal(np.squeeze(side["activity_b"]), np.squeeze(g["activity_b"]))
+    assert np.array_equal(np.squeeze(side["activity_final"]), np.squeeze(g["activity_final"]))
+    assert not np.squeeze(g["activity_b"]).all() and np.squeeze(g["activity_b"]).any()
+    assert rel_l2(np.squeeze(side["mask_stitched"]), np.squeeze(g["mask_stitched"])) < 1e-4
+    for k in range(3):
+        assert rel_l2(wavs[k], g["wavs"][k]) < 1e-4
