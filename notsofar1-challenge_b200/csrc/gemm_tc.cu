@@ -108,6 +108,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             const int which = p.epi == EPI_QKV ? nc / p.d_model : 0;
             const int cq = n0 - which * p.d_model;
             const int hq = p.epi == EPI_QKV ? cq / p.d_k : 0, dq = cq - hq * p.d_k;
+            // in-place residual stream: the four rows' old values are all in flight before the first store (a store to
+            // x would otherwise fence the next row's loads and expose one HBM round trip per row)
+            float4 xo[4][2];
+            if (p.epi == EPI_RESID) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int m = r0 + rq + 8 * k;
+                    const float* o = p.out0 + (size_t)(m < p.M ? m : r0) * p.ldo + n0;
+                    xo[k][0] = *reinterpret_cast<const float4*>(o);
+                    xo[k][1] = *reinterpret_cast<const float4*>(o + 4);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int rr = rq + 8 * k;
@@ -133,7 +145,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                     }
                     case EPI_RESID: {
                         float* o = p.out0 + (size_t)m * p.ldo + n0;
-                        const float4 x0 = *reinterpret_cast<const float4*>(o), x1 = *reinterpret_cast<const float4*>(o + 4);
+                        const float4 x0 = xo[k][0], x1 = xo[k][1];
                         *reinterpret_cast<float4*>(o) = make_float4(x0.x + p.alpha * v[0], x0.y + p.alpha * v[1], x0.z + p.alpha * v[2], x0.w + p.alpha * v[3]);
                         *reinterpret_cast<float4*>(o + 4) = make_float4(x1.x + p.alpha * v[4], x1.y + p.alpha * v[5], x1.z + p.alpha * v[6], x1.w + p.alpha * v[7]);
                         break;
