@@ -112,6 +112,17 @@ def calc_segment_weight(seg_frames: int, m0_frames: int, m1_frames: int,
     return wg_win
 
 
+_PERM_TABLES: Dict[int, tuple] = {}
+
+
+def _perm_tables(S: int):
+    """All S! channel orders, and next-state bookkeeping for the chain: cand [P, S]."""
+    if S not in _PERM_TABLES:
+        cand = np.asarray(list(itertools.permutations(range(S))), dtype=np.int64)
+        _PERM_TABLES[S] = (cand,)
+    return _PERM_TABLES[S]
+
+
 def permutation_chain(costs: np.ndarray) -> np.ndarray:
     """Sequential alignment of css.py:266-285 from the pairwise costs of the *unpermuted* segments.
 
@@ -120,20 +131,29 @@ def permutation_chain(costs: np.ndarray) -> np.ndarray:
     rows perm[i-1] of costs[i]; the optimal assignment of a 3x3 (<= 4x4) matrix is found by enumerating
     the permutations (== scipy's Hungarian answer away from exact ties).  Returns perms [n_seg, S] with
     new channel k of segment i <- old channel perms[i][k].
+
+    The enumeration is vectorised over segments: total[i][q][p] = sum_a costs[i][cand[q][a]][cand[p][a]] (float64,
+    summed in channel order) for every possible previous order q, best[i][q] = first arg-min over p; the chain
+    itself is then a table walk (0.3 ms instead of 14 ms of Python for a 30-minute meeting, during which the GPU
+    would sit idle behind the cost read-back).
     """
     n_seg, S, _ = costs.shape
-    perms = np.tile(np.arange(S, dtype=np.int32), (n_seg, 1))
-    cand = list(itertools.permutations(range(S)))
+    (cand,) = _perm_tables(S)
+    P = len(cand)
+    c = np.asarray(costs, dtype=np.float64)
+    total = np.zeros((n_seg, P, P), np.float64)
+    for a in range(S):                                   # ((0 + c_0) + c_1) + c_2: the order of the scalar loop it replaces
+        total += c[:, cand[:, a][:, None], cand[:, a][None, :]]
+    best = total.argmin(axis=2)                          # first minimum wins, like the strict '<' of the scalar loop
+    perms = np.empty((n_seg, S), dtype=np.int32)
+    perms[0] = np.arange(S)
+    q = 0                                                # identity is cand[0]
+    best_l = best.tolist()
+    states = [0] * n_seg
     for i in range(1, n_seg):
-        c = costs[i][perms[i - 1]]                       # rows follow the permuted left segment
-        best, best_p = None, None
-        for p in cand:
-            v = 0.0
-            for a in range(S):
-                v += float(c[a, p[a]])
-            if best is None or v < best:
-                best, best_p = v, p
-        perms[i] = best_p
+        q = best_l[i][q]
+        states[i] = q
+    perms[:] = cand[np.asarray(states)]
     return perms
 
 
@@ -159,21 +179,42 @@ def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batc
     return out
 
 
+_SEG_W_CACHE: Dict[tuple, tuple] = {}
+
+
 def _segment_weights(plan: SegmentPlan):
     """seg_w [n_seg, T] and its overlap-added sum wg_stitched [mix_frames] exactly as css.py:258-259,288-291
-    accumulate them (float32, ascending segment order)."""
-    T, n = plan.segment_frames, plan.num_segments
+    accumulate them (float32, ascending segment order).  Cached per plan: callers must not modify the arrays."""
+    key = (plan.segment_frames, plan.hop_frames, plan.m0_frames, plan.m1_frames, plan.num_segments, plan.mix_frames)
+    if key in _SEG_W_CACHE:
+        return _SEG_W_CACHE[key]
+    T, n, hop = plan.segment_frames, plan.num_segments, plan.hop_frames
     first = calc_segment_weight(T, plan.m0_frames, plan.m1_frames, is_first_seg=True).numpy()
     mid = calc_segment_weight(T, plan.m0_frames, plan.m1_frames).numpy()
     last = calc_segment_weight(T, plan.m0_frames, plan.m1_frames, is_last_seg=True).numpy()
     seg_w = np.empty((n, T), np.float32)
+    seg_w[:] = mid
+    seg_w[n - 1] = last
+    seg_w[0] = first                                     # a lone segment is a "first" one (css.py:257-259 before :283-284)
     wsum = np.zeros(plan.mix_frames, np.float32)
-    for i in range(n):
-        w = first if i == 0 else (last if i == n - 1 else mid)
-        seg_w[i] = w
-        st = i * plan.hop_frames
-        en = min(st + T, plan.mix_frames)
-        wsum[st:en] += w[:en - st]
+    if T <= 2 * hop:
+        # at most two segments meet in a frame: even and odd segments tile the axis without overlap, and a + b is
+        # the same float32 whichever comes first
+        for parity in (0, 1):
+            part = np.zeros(plan.mix_frames + T, np.float32)
+            idx = np.arange(parity, n, 2)
+            if len(idx):
+                pos = (idx[:, None] * hop + np.arange(T)[None, :]).reshape(-1)
+                part[pos] = seg_w[idx].reshape(-1)
+            wsum += part[:plan.mix_frames]
+    else:
+        for i in range(n):
+            st = i * hop
+            en = min(st + T, plan.mix_frames)
+            wsum[st:en] += seg_w[i][:en - st]
+    _SEG_W_CACHE[key] = (seg_w, wsum)
+    if len(_SEG_W_CACHE) > 16:
+        _SEG_W_CACHE.pop(next(iter(_SEG_W_CACHE)))
     return seg_w, wsum
 
 
@@ -283,14 +324,15 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
         src = masks if in_kind == 0 else Y
         _cabi.check(lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_seg, n_masks if in_kind == 0 else S, S, NUM_BINS, T,
                                      plan.overlap_frames, _cabi.ptr(costs), sp()), "nsf_pit_cost")
-        perms_np = permutation_chain(costs.cpu().numpy())
+        # host work that does not depend on the costs runs while the GPU is still busy with the segments
         seg_w_np, wsum_np = _segment_weights(plan)
         assert (wsum_np > 1e-5).all(), 'zero weights found. check hop_size, segment_size or m0, m1'
-        perms = torch.from_numpy(perms_np).to(device)
         seg_w = torch.from_numpy(seg_w_np).to(device)
         wsum = torch.from_numpy(wsum_np).to(device)
         mask_st = torch.empty((NUM_BINS, mix_frames, S), dtype=torch.float32, device=device)
         activity = torch.empty((mix_frames, S), dtype=torch.float32, device=device)
+        perms_np = permutation_chain(costs.cpu().numpy())            # the only device -> host sync of the path
+        perms = torch.from_numpy(perms_np).to(device)
         _cabi.check(lib.nsf_stitch_masks(_cabi.ptr(masks), n_masks, _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), n_seg, S,
                                          NUM_BINS, T, hop, mix_frames, _cabi.ptr(mask_st), _cabi.ptr(activity), sp()),
                     "nsf_stitch_masks")
