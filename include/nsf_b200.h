@@ -55,6 +55,8 @@ extern "C" {
 #define NSF_GEMM_TC_2XF16    4   /* tcgen05 kind::f16 on power-of-two-scaled fp16 head + remainder pairs, 3 MMAs per product
                                     (~2^-22: fp32-grade at twice the 3xTF32 rate); scaled magnitudes saturate at 65504 */
 
+#define NSF_GEMM_TC_BF16     5   /* tcgen05 kind::f16, plain bf16 operands, one MMA per product (the Whisper encoder's engine) */
+
 const char* nsf_last_error(void);
 const char* nsf_version(void);
 /* number of kernels this library has launched in the process so far (bench.py's gpu_launches) */
@@ -213,6 +215,13 @@ int nsf_attention_test(const float* q, const float* k, const float* v, const flo
 /* The same test hook for the bf16-pair attention kernel of the NSF_GEMM_TC_2XBF16 engine (attention16.cu); workspace as above. */
 int nsf_attention16_test(const float* q, const float* k, const float* v, const float* pe, int maxlen, int n_seg, int n_heads,
                          int T, float* out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Test hook: non-causal multi-head attention with online softmax (flash_attn.cu, the Whisper encoder's attention) on fp32
+ * inputs that are rounded to bf16 inside.  q, k, v [n_batch*n_heads][T][64] (already scaled), out [n_batch*T][n_heads*64] f32:
+ *   out[b*T + t1][h*64 + d] = sum_t2 softmax_t2(q[t1].k[t2]) v[t2][d]. */
+int64_t nsf_flash_attention_test_workspace_bytes(int n_batch, int n_heads, int T);
+int nsf_flash_attention_test(const float* q, const float* k, const float* v, int n_batch, int n_heads, int T, float* out,
+                             void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,13 +9,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libnsf_b200.so")
 
-GEMM_SIMT_FP32, GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_TC_2XBF16, GEMM_TC_2XF16 = 0, 1, 2, 3, 4
-SPLIT_TF32, SPLIT_BF16, SPLIT_F16 = 0, 1, 2
+GEMM_SIMT_FP32, GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_TC_2XBF16, GEMM_TC_2XF16, GEMM_TC_BF16 = 0, 1, 2, 3, 4, 5
+SPLIT_TF32, SPLIT_BF16, SPLIT_F16, SPLIT_BF16_1, SPLIT_FP32 = 0, 1, 2, 3, 4
 F16_ACT_SCALE, F16_WEIGHT_SCALE = 16.0, 256.0        # csrc/common.cuh kF16ActScale / kF16WeightScale
 
 
 def split_fmt_of_engine(engine: int) -> int:
-    return {GEMM_TC_2XBF16: SPLIT_BF16, GEMM_TC_2XF16: SPLIT_F16}.get(engine, SPLIT_TF32)
+    return {GEMM_TC_2XBF16: SPLIT_BF16, GEMM_TC_2XF16: SPLIT_F16, GEMM_TC_BF16: SPLIT_BF16_1}.get(engine, SPLIT_TF32)
 
 c_f32p = C.c_void_p
 i64 = C.c_int64
@@ -56,6 +56,8 @@ SIGNATURES = {
     "nsf_mask_apply": (i32, [c_f32p, i32, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, C.c_float, c_f32p, C.c_void_p]),
     "nsf_segment_power_norm": (i32, [c_f32p, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, i64, c_f32p, C.c_void_p]),
     "nsf_gather_crops": (i32, [C.c_void_p, i32, i64, C.c_void_p, C.c_void_p, C.c_void_p, i32, i64, c_f32p, C.c_void_p]),
+    "nsf_flash_attention_test_workspace_bytes": (i64, [i32, i32, i32]),
+    "nsf_flash_attention_test": (i32, [c_f32p, c_f32p, c_f32p, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_attention16_test": (i32, [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_gemm_test": (i32, [i32, c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, C.c_void_p, i64, C.c_void_p]),
 }

@@ -93,11 +93,14 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 //               power-of-two scale keeps the remainder out of the fp16 subnormals: activations s = 2^4, weights
 //               s = 2^8, undone exactly in the GEMM epilogue; |s x| saturates at 65504)
 // The 16-bit arrays live in the same buffers as the fp32 ones (element index unchanged, half the bytes used).
-enum SplitFmt : int { SPLIT_TF32 = 0, SPLIT_BF16 = 1, SPLIT_F16 = 2 };
+//   SPLIT_BF16_1 one bf16 array (head only): the plain bf16 operand of the single-pass NSF_GEMM_TC_BF16 engine
+//   SPLIT_FP32   one fp32 array (no split): plain outputs written through the same store helpers
+enum SplitFmt : int { SPLIT_TF32 = 0, SPLIT_BF16 = 1, SPLIT_F16 = 2, SPLIT_BF16_1 = 3, SPLIT_FP32 = 4 };
 constexpr float kF16ActScale = 16.f, kF16WeightScale = 256.f;
 
 inline int split_fmt_of_engine(int engine) {
-    return engine == NSF_GEMM_TC_2XBF16 ? SPLIT_BF16 : engine == NSF_GEMM_TC_2XF16 ? SPLIT_F16 : SPLIT_TF32;
+    return engine == NSF_GEMM_TC_2XBF16 ? SPLIT_BF16 : engine == NSF_GEMM_TC_2XF16 ? SPLIT_F16
+         : engine == NSF_GEMM_TC_BF16 ? SPLIT_BF16_1 : SPLIT_TF32;
 }
 
 __device__ __forceinline__ void split_bf16(float v, uint16_t& hi, uint16_t& lo) {
@@ -120,6 +123,10 @@ __device__ __forceinline__ void split_store(int fmt, float* hi, float* lo, size_
         split_tf32(v, h, l);
         hi[idx] = h;
         lo[idx] = l;
+    } else if (fmt == SPLIT_BF16_1) {
+        reinterpret_cast<uint16_t*>(hi)[idx] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    } else if (fmt == SPLIT_FP32) {
+        hi[idx] = v;
     } else {
         uint16_t h, l;
         if (fmt == SPLIT_BF16) split_bf16(v, h, l); else split_f16(v, kF16ActScale, h, l);
@@ -134,6 +141,12 @@ __device__ __forceinline__ void split_store4(int fmt, float* hi, float* lo, size
         split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
         *reinterpret_cast<float4*>(hi + idx) = h;
         *reinterpret_cast<float4*>(lo + idx) = l;
+    } else if (fmt == SPLIT_BF16_1) {
+        const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + idx) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    } else if (fmt == SPLIT_FP32) {
+        *reinterpret_cast<float4*>(hi + idx) = v;
     } else {
         uint16_t h[4], l[4];
         if (fmt == SPLIT_BF16) {
@@ -162,6 +175,17 @@ __device__ __forceinline__ void split_store8(int fmt, float* hi, float* lo, size
     if (fmt == SPLIT_TF32) {
         split_store4(fmt, hi, lo, idx, make_float4(v[0], v[1], v[2], v[3]));
         split_store4(fmt, hi, lo, idx + 4, make_float4(v[4], v[5], v[6], v[7]));
+    } else if (fmt == SPLIT_FP32) {
+        *reinterpret_cast<float4*>(hi + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(hi + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    } else if (fmt == SPLIT_BF16_1) {
+        uint32_t h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            h[e] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(hi) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
     } else if (fmt == SPLIT_BF16) {
         uint32_t h[4], l[4];
 #pragma unroll

@@ -706,7 +706,7 @@ extern "C" int nsf_gemm_test(int engine, const float* A, const float* W, const f
                              int K, void* workspace, int64_t workspace_bytes, void* stream_) {
     NSF_REQUIRE(A && W && Cout && workspace, "nsf_gemm_test: null pointer");
     NSF_REQUIRE(K % 32 == 0 && M > 0 && N > 0, "nsf_gemm_test: K must be a multiple of 32");
-    NSF_REQUIRE(engine >= NSF_GEMM_SIMT_FP32 && engine <= NSF_GEMM_TC_2XF16, "nsf_gemm_test: engine");
+    NSF_REQUIRE(engine >= NSF_GEMM_SIMT_FP32 && engine <= NSF_GEMM_TC_BF16, "nsf_gemm_test: engine");
     const int64_t na = (int64_t)M * K, nw = (int64_t)N * K;
     const int64_t need = (align_up(na, 64) * 2 + align_up(nw, 64) * 2) * (int64_t)sizeof(float);
     NSF_REQUIRE(workspace_bytes >= need, "nsf_gemm_test: workspace needs %lld bytes", (long long)need);

@@ -19,7 +19,11 @@ enum GemmEpilogue : int {
     EPI_QKV = 3,          // scatter q, k (head-major, split) and v (head-major, transposed, split)
     EPI_PV = 4,           // attention output of batch (seg, head) -> (out0, out1)[seg*T + m][head*d_k + n] split
     EPI_MASK = 5,         // out0[seg][n / 257][n % 257][t] = sigmoid(acc + bias[n]),  m = seg*T + t, n < n_valid
+    EPI_GELU_SPLIT = 6,   // v = gelu(acc + bias[n]) (exact, erf); (out0, out1)[b][m][n] = split(v), batch stride o_batch_stride
+    EPI_GELU_POS = 7,     // out0[b*M + m][n] = gelu(acc + bias[n]) + pos[m][n]   (fp32; pos = out1, row pitch ldo)
 };
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 struct GemmParams {
     const float* A_hi; const float* A_lo; int64_t lda; int64_t a_batch_stride;
@@ -84,6 +88,12 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, int b, int m,
             p.out1[o] = lo;
             break;
         }
+        case EPI_GELU_SPLIT:
+            split_store(p.out_fmt, p.out0, p.out1, (size_t)b * p.o_batch_stride + (size_t)m * p.ldo + n, gelu_erf(v));
+            break;
+        case EPI_GELU_POS:
+            p.out0[((size_t)b * p.M + m) * p.ldo + n] = gelu_erf(v) + __ldg(p.out1 + (size_t)m * p.ldo + n);
+            break;
         case EPI_MASK: {
             const int seg = m / p.T, t = m - seg * p.T;
             const int k = n / kBins, f = n - k * kBins;
@@ -97,7 +107,8 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, int b, int m,
 }
 
 int gemm_simt_launch(const GemmParams& p, cudaStream_t stream);
-// mode: 3 -> 3xTF32, 1 -> single TF32 pass, 16 -> three kind::f16 MMAs on 16-bit pairs (p.op_fmt = SPLIT_BF16 / SPLIT_F16)
+// mode: 3 -> 3xTF32, 1 -> single TF32 pass, 16 -> three kind::f16 MMAs on 16-bit pairs (p.op_fmt = SPLIT_BF16 / SPLIT_F16),
+//       116 -> one kind::f16 MMA on plain bf16 operands (p.op_fmt = SPLIT_BF16_1)
 int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream);
 
 // fused relative-position attention (attention.cu); q, k: [n_seg*heads][T][64], vt: [n_seg*heads][64][Tp], all split
@@ -108,6 +119,9 @@ int attn_fused_launch(const float* q_hi, const float* q_lo, const float* k_hi, c
 int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
                   const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
                   float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
+// non-causal attention with online softmax on plain bf16 operands (flash_attn.cu); q, k [n_bh][T][64], vt [n_bh][64][Tp]
+int flash_attn_launch(const void* q, const void* k, const void* vt, int n_batch, int n_heads, int T, int Tp,
+                      float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
 inline bool attn_fused_supported(int T, int d_k) { return T >= 2 && T <= 192 && d_k == 64; }
 
 inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {
@@ -115,6 +129,7 @@ inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {
     ProfScope prof(engine == NSF_GEMM_SIMT_FP32 ? PROF_GEMM_SIMT : PROF_GEMM_TC, 2.0 * p.M * p.N * p.K * p.batch, stream);
     if (engine == NSF_GEMM_SIMT_FP32) return gemm_simt_launch(p, stream);
     if (engine == NSF_GEMM_TC_2XBF16 || engine == NSF_GEMM_TC_2XF16) return gemm_tc_launch(p, 16, stream);
+    if (engine == NSF_GEMM_TC_BF16) return gemm_tc_launch(p, 116, stream);
     return gemm_tc_launch(p, engine == NSF_GEMM_TC_3XTF32 ? 3 : 1, stream);
 }
 

@@ -32,8 +32,8 @@ constexpr int kEpiBytes = 8 * 32 * kEpiPitch * 4;  // one 32 x 32 staging tile p
 
 // MODE 1: one kind::tf32 pass; 3: 3xTF32; 16: three kind::f16 MMAs on 16-bit head/remainder pairs (2xBF16 / 2xF16)
 template <int MODE> struct TcCfg {
-    static constexpr bool kSplit = MODE != 1;
-    static constexpr int kBlockK = MODE == 16 ? 64 : 32;          // elements of K per stage (one 128-byte row)
+    static constexpr bool kSplit = MODE == 3 || MODE == 16;
+    static constexpr int kBlockK = MODE >= 16 ? 64 : 32;          // elements of K per stage (one 128-byte row)
     static constexpr int kStageBytes = (kSplit ? 2 : 1) * (kATileBytes + kBTileBytes);
     static constexpr int kStages = kSplit ? 2 : 4;
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
@@ -143,6 +143,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                         split_store8(p.out_fmt, p.out0, p.out1, (size_t)m * p.ldo + n0, v);
                         break;
                     }
+                    case EPI_GELU_SPLIT: {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = gelu_erf(v[e]);
+                        split_store8(p.out_fmt, p.out0, p.out1, (size_t)b * p.o_batch_stride + (size_t)m * p.ldo + n0, v);
+                        break;
+                    }
+                    case EPI_GELU_POS: {
+                        float* o = p.out0 + ((size_t)b * p.M + m) * p.ldo + n0;
+                        const float* ps = p.out1 + (size_t)m * p.ldo + n0;
+                        const float4 p0 = __ldg(reinterpret_cast<const float4*>(ps)), p1 = __ldg(reinterpret_cast<const float4*>(ps + 4));
+                        *reinterpret_cast<float4*>(o) = make_float4(gelu_erf(v[0]) + p0.x, gelu_erf(v[1]) + p0.y, gelu_erf(v[2]) + p0.z, gelu_erf(v[3]) + p0.w);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(gelu_erf(v[4]) + p1.x, gelu_erf(v[5]) + p1.y, gelu_erf(v[6]) + p1.z, gelu_erf(v[7]) + p1.w);
+                        break;
+                    }
                     case EPI_RESID: {
                         float* o = p.out0 + (size_t)m * p.ldo + n0;
                         const float4 x0 = xo[k][0], x1 = xo[k][1];
@@ -185,6 +199,20 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                     if (i < rows) o[(size_t)i * p.ldo] = v[i];
+                break;
+            }
+            case EPI_GELU_SPLIT: {
+                const size_t o = (size_t)b * p.o_batch_stride + (size_t)r0 * p.ldo + n;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < rows) split_store(p.out_fmt, p.out0, p.out1, o + (size_t)i * p.ldo, gelu_erf(v[i]));
+                break;
+            }
+            case EPI_GELU_POS: {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (i < rows)
+                        p.out0[((size_t)b * p.M + r0 + i) * p.ldo + n] = gelu_erf(v[i]) + __ldg(p.out1 + (size_t)(r0 + i) * p.ldo + n);
                 break;
             }
             case EPI_RELU_SPLIT: {
@@ -300,7 +328,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer
-            const uint32_t idesc = MODE == 16 ? make_idesc_f16(TBN, p.op_fmt == SPLIT_BF16) : make_idesc_tf32(TBN);
+            const uint32_t idesc = MODE >= 16 ? make_idesc_f16(TBN, p.op_fmt != SPLIT_F16) : make_idesc_tf32(TBN);
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
@@ -324,6 +352,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                             tcgen05_mma_f16(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);     // small terms first
                             tcgen05_mma_f16(d_tmem, da_hi, db_lo, idesc, 1);
                             tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
+                        } else if (MODE == 116) {
+                            tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
                         } else if (MODE == 3) {
                             const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
                             tcgen05_mma_tf32(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);    // small terms first
@@ -391,7 +421,7 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
     auto make = [&](CUtensorMap* m, const float* base, int64_t rows, int64_t ld, int64_t bstride, int box_rows) {
-        return MODE == 16 ? make_tmap_kmajor16(m, base, rows, p.K, ld, p.batch, bstride, box_rows)
+        return MODE >= 16 ? make_tmap_kmajor16(m, base, rows, p.K, ld, p.batch, bstride, box_rows)
                           : make_tmap_kmajor(m, base, rows, p.K, ld, p.batch, bstride, box_rows);
     };
     if ((rc = make(&ma_hi, p.A_hi, p.M, p.lda, p.a_batch_stride, TBM))) return rc;
@@ -415,6 +445,10 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
                 ok = ok && p.ldo % 4 == 0 && p.o_batch_stride % 4 == 0 && al16(p.out0); break;
             case EPI_RELU_SPLIT: case EPI_PV:
                 ok = ok && p.ldo % 8 == 0 && al16(p.out0) && al16(p.out1) && p.d_k % 8 == 0; break;
+            case EPI_GELU_SPLIT:
+                ok = ok && p.ldo % 8 == 0 && p.o_batch_stride % 8 == 0 && al16(p.out0) && (p.out_fmt == SPLIT_BF16_1 || al16(p.out1)); break;
+            case EPI_GELU_POS:
+                ok = ok && p.ldo % 4 == 0 && al16(p.out0) && al16(p.out1); break;
             case EPI_QKV:
                 ok = ok && p.d_k % 8 == 0 && p.d_model % 32 == 0 && al16(p.q_hi) && al16(p.q_lo) && al16(p.k_hi) && al16(p.k_lo); break;
             default: ok = false; break;     // EPI_MASK writes along rows
@@ -436,6 +470,11 @@ int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream) {
         if (p.op_fmt != SPLIT_BF16 && p.op_fmt != SPLIT_F16) { set_error("gemm_tc: 16-bit engine needs SPLIT_BF16 / SPLIT_F16 operands"); return NSF_ERR_INVALID_ARG; }
         if (p.K % 8 != 0) { set_error("gemm_tc: K=%d must be a multiple of 8", p.K); return NSF_ERR_INVALID_ARG; }
         return launch_t<16>(p, stream);
+    }
+    if (mode == 116) {
+        if (p.op_fmt != SPLIT_BF16_1) { set_error("gemm_tc: the bf16 engine needs SPLIT_BF16_1 operands"); return NSF_ERR_INVALID_ARG; }
+        if (p.K % 8 != 0) { set_error("gemm_tc: K=%d must be a multiple of 8", p.K); return NSF_ERR_INVALID_ARG; }
+        return launch_t<116>(p, stream);
     }
     if (p.op_fmt != SPLIT_TF32) { set_error("gemm_tc: tf32 engines need SPLIT_TF32 operands"); return NSF_ERR_INVALID_ARG; }
     if (p.K % 32 != 0) { set_error("gemm_tc: K=%d must be a multiple of 32", p.K); return NSF_ERR_INVALID_ARG; }

@@ -613,3 +613,55 @@ def test_no_beamformer_modes_vs_reference_golden(nb, dev, golden, mode):
         assert X.dim() == 3
         out = sep.separate(X)
         assert out["spk_masks"].shape == (1, 257, X.shape[2], 3) and out["noise_masks"].shape[-1] == 1
+
+
+# ----------------------------------------------------------------------------------------------- Whisper-path kernels
+@pytest.mark.parametrize("n_batch,n_heads,T", [(1, 1, 50), (1, 2, 128), (2, 1, 129), (1, 2, 300), (1, 3, 1500)])
+def test_flash_attention_vs_fp64(nb, dev, n_batch, n_heads, T):
+    """tcgen05 online-softmax attention (flash_attn.cu) vs float64 softmax(q k^T) v on the bf16-rounded inputs."""
+    lib = nb._cabi.load()
+    rng = np.random.default_rng(T + n_heads)
+    bh = n_batch * n_heads
+    q, k, v = (rng.standard_normal((bh, T, 64)).astype(np.float32) for _ in range(3))
+    q *= 0.35; k *= 0.35                                                    # the d_k^-0.25 scale whisper folds into q and k
+    k[:, : T // 3] += 1.5 * rng.standard_normal((bh, 1, 64)).astype(np.float32)   # a moving maximum across key tiles
+    rb = lambda a: torch.from_numpy(a).to(torch.bfloat16).to(torch.float64).numpy()
+    qd, kd, vd = rb(q), rb(k), rb(v)
+    sc = np.einsum("btd,bsd->bts", qd, kd)
+    sc -= sc.max(-1, keepdims=True)
+    P = np.exp(sc)
+    P /= P.sum(-1, keepdims=True)
+    o = np.einsum("bts,bsd->btd", P, vd)
+    ref = o.reshape(n_batch, n_heads, T, 64).transpose(0, 2, 1, 3).reshape(n_batch * T, n_heads * 64)
+    tq, tk, tv = (torch.from_numpy(a).to(dev) for a in (q, k, v))
+    out = torch.full((n_batch * T, n_heads * 64), float("nan"), dtype=torch.float32, device=dev)
+    need = int(lib.nsf_flash_attention_test_workspace_bytes(n_batch, n_heads, T))
+    ws = torch.empty(need, dtype=torch.uint8, device=dev)
+    nb._cabi.check(lib.nsf_flash_attention_test(nb._cabi.ptr(tq), nb._cabi.ptr(tk), nb._cabi.ptr(tv), n_batch, n_heads, T, nb._cabi.ptr(out),
+                                                nb._cabi.ptr(ws), need, nb._cabi.stream_ptr()), "nsf_flash_attention_test")
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    assert np.isfinite(got).all()
+    err = rel_l2(got, ref)
+    print("flash attention rel err", (n_batch, n_heads, T), err)
+    assert err < 5e-3                                                       # probabilities are rounded to bf16 (2^-9) for P V
+
+
+def test_gemm_bf16_engine_vs_fp64(nb, dev):
+    lib = nb._cabi.load()
+    rng = np.random.default_rng(11)
+    M, N, K = 700, 1280, 1280
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    rb = lambda a: torch.from_numpy(a).to(torch.bfloat16).to(torch.float64).numpy()
+    ref = rb(A) @ rb(W).T + bias
+    tA, tW, tb = (torch.from_numpy(a).to(dev) for a in (A, W, bias))
+    ws = torch.empty(8 * (M * K + N * K) + 4096, dtype=torch.uint8, device=dev)
+    out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
+    nb._cabi.check(lib.nsf_gemm_test(nb.GEMM_TC_BF16, nb._cabi.ptr(tA), nb._cabi.ptr(tW), nb._cabi.ptr(tb), nb._cabi.ptr(out), M, N, K,
+                                     nb._cabi.ptr(ws), ws.numel(), nb._cabi.stream_ptr()), "nsf_gemm_test")
+    torch.cuda.synchronize()
+    err = rel_l2(out.cpu().numpy(), ref)
+    print("gemm bf16 rel err vs fp64 on rounded operands", err)
+    assert err < 1e-5
