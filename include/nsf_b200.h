@@ -216,6 +216,27 @@ int nsf_attention_test(const float* q, const float* k, const float* v, const flo
 int nsf_attention16_test(const float* q, const float* k, const float* v, const float* pe, int maxlen, int n_seg, int n_heads,
                          int T, float* out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- Whisper audio encoder (row a15: asr/asr.py:69-74 calls openai-whisper, third-party and unpinned; the published
+ * algorithm of whisper/audio.py::log_mel_spectrogram and whisper/model.py::AudioEncoder is restated here, parity against
+ * the transformers implementation of the same model -- see csrc/whisper.cu).  30-s chunks of 480 000 samples. */
+typedef struct nsf_whisper_encoder nsf_whisper_encoder;
+typedef struct { int n_mels, n_ctx, d_model, n_heads, n_layers, d_ff; } nsf_whisper_dims;
+int64_t nsf_whisper_encoder_num_offsets(const nsf_whisper_dims* dims);
+/* blob layout: notsofar_b200/whisper.py::pack_whisper_encoder (bf16 planes packed two per float word, fp32 biases / LN / pos) */
+int nsf_whisper_encoder_create(const nsf_whisper_dims* dims, const float* blob, int64_t blob_floats, const int64_t* offsets /*host*/,
+                               int n_offsets, nsf_whisper_encoder** out);
+void nsf_whisper_encoder_destroy(nsf_whisper_encoder* h);
+int64_t nsf_whisper_encoder_workspace_bytes(const nsf_whisper_dims* dims, int n_batch);
+/* elements of one bf16 plane of the time-major, zero-framed log-mel input: n_batch * 3002 * n_mels */
+int64_t nsf_whisper_mel_plane_elems(int n_mels, int n_batch);
+/* audio [n_batch][480000] f32 -> log-mel as bf16 head / remainder planes [n_batch][3002][n_mels] (row 0 and 3001 zero).
+ * filters [n_mels][201] f32 (slaney mel filterbank); log_spec [n_batch][n_mels][3000] f32 and gmax [n_batch] u32 are scratch. */
+int nsf_whisper_logmel(const float* audio, int n_batch, int64_t n_samples, const float* filters, int n_mels, float* log_spec,
+                       uint32_t* gmax, void* mel_hi, void* mel_lo, void* stream);
+/* out [n_batch * 1500][d_model] f32 = ln_post(encoder(mel)) */
+int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* mel_hi, const void* mel_lo, int n_batch, float* out,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Test hook: non-causal multi-head attention with online softmax (flash_attn.cu, the Whisper encoder's attention) on fp32
  * inputs that are rounded to bf16 inside.  q, k, v [n_batch*n_heads][T][64] (already scaled), out [n_batch*T][n_heads*64] f32:
  *   out[b*T + t1][h*64 + d] = sum_t2 softmax_t2(q[t1].k[t2]) v[t2][d]. */

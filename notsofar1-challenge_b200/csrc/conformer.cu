@@ -174,16 +174,18 @@ ln_kernel(const float* __restrict__ x, int M, int d, const float* __restrict__ g
     }
 }
 
-static int ln_launch(const float* x, int M, int d, const float* g1, const float* b1, int relu1, float* out_x, const float* g2,
-                     const float* b2, float* out_hi, float* out_lo, int fmt, cudaStream_t s) {
+int ln_launch(const float* x, int M, int d, const float* g1, const float* b1, int relu1, float* out_x, const float* g2,
+              const float* b2, float* out_hi, float* out_lo, int fmt, cudaStream_t s) {
     const int grid = ceil_div(M, 8);
+#define NSF_LN_CASE(NV) case NV: ln_vec_kernel<NV><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
     switch ((d % 128 == 0) ? d / 128 : 0) {
-        case 1: ln_vec_kernel<1><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
-        case 2: ln_vec_kernel<2><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
-        case 4: ln_vec_kernel<4><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
-        case 8: ln_vec_kernel<8><<<grid, 256, 0, s>>>(x, M, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
-        default: ln_kernel<<<grid, 256, 0, s>>>(x, M, d, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt); break;
+        NSF_LN_CASE(1) NSF_LN_CASE(2) NSF_LN_CASE(3) NSF_LN_CASE(4) NSF_LN_CASE(5) NSF_LN_CASE(6) NSF_LN_CASE(8) NSF_LN_CASE(10)
+        default:
+            if (d > 32 * kLnMaxPerLane || d % 32 != 0) { set_error("ln_launch: d=%d unsupported", d); return NSF_ERR_UNSUPPORTED; }
+            ln_kernel<<<grid, 256, 0, s>>>(x, M, d, g1, b1, relu1, out_x, g2, b2, out_hi, out_lo, fmt);
+            break;
     }
+#undef NSF_LN_CASE
     return check_launch("ln_kernel");
 }
 

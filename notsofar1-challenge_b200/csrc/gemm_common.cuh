@@ -32,6 +32,7 @@ struct GemmParams {
     int op_fmt;               // SplitFmt of A and B (the 16-bit formats reinterpret the float pointers as uint16_t arrays)
     int out_fmt;              // SplitFmt of the split outputs of EPI_RELU_SPLIT / EPI_PV
     int qkv_fmt;              // SplitFmt of q, k, v^T written by EPI_QKV (SPLIT_TF32 for attention.cu, SPLIT_BF16 for attention16.cu)
+    int b_shared;             // batched A against one B (weights): every batch entry reads B[0]
     int vec8;                 // set by the tensor-core launcher: N, leading dimensions and bases allow 8-column vector epilogues
     float acc_scale;          // accumulator scale applied before the bias (undoes the SPLIT_F16 operand scales; 1 otherwise)
     int n_valid;              // columns >= n_valid are padding (weights padded with zero rows)
@@ -122,6 +123,10 @@ int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const
 // non-causal attention with online softmax on plain bf16 operands (flash_attn.cu); q, k [n_bh][T][64], vt [n_bh][64][Tp]
 int flash_attn_launch(const void* q, const void* k, const void* vt, int n_batch, int n_heads, int T, int Tp,
                       float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
+// y1 = LN(x; g1, b1) [relu]; optional fp32 store to out_x; y2 = LN(y1; g2, b2) if g2; optional split store in fmt
+// (conformer.cu; one warp per row, d a multiple of 32, vector path for d = 128 * {1,2,3,4,5,6,8,10})
+int ln_launch(const float* x, int M, int d, const float* g1, const float* b1, int relu1, float* out_x, const float* g2,
+              const float* b2, float* out_hi, float* out_lo, int fmt, cudaStream_t s);
 inline bool attn_fused_supported(int T, int d_k) { return T >= 2 && T <= 192 && d_k == 64; }
 
 inline int gemm_launch(int engine, const GemmParams& p, cudaStream_t stream) {

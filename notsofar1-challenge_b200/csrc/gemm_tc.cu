@@ -314,13 +314,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_expect_tx(full_bar(s), Cfg::kStageBytes);
                     const uint32_t st = tiles + s * Cfg::kStageBytes;
                     const int k0 = kb * Cfg::kBlockK;
+                    const int bb = p.b_shared ? 0 : b;
                     tma_load_3d(st, &map_a_hi, k0, m0, b, full_bar(s));
                     if (Cfg::kSplit) {
                         tma_load_3d(st + kATileBytes, &map_a_lo, k0, m0, b, full_bar(s));
-                        tma_load_3d(st + 2 * kATileBytes, &map_b_hi, k0, n0, b, full_bar(s));
-                        tma_load_3d(st + 2 * kATileBytes + kBTileBytes, &map_b_lo, k0, n0, b, full_bar(s));
+                        tma_load_3d(st + 2 * kATileBytes, &map_b_hi, k0, n0, bb, full_bar(s));
+                        tma_load_3d(st + 2 * kATileBytes + kBTileBytes, &map_b_lo, k0, n0, bb, full_bar(s));
                     } else {
-                        tma_load_3d(st + kATileBytes, &map_b_hi, k0, n0, b, full_bar(s));
+                        tma_load_3d(st + kATileBytes, &map_b_hi, k0, n0, bb, full_bar(s));
                     }
                 }
             }
@@ -420,16 +421,17 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
     using Cfg = TcCfg<MODE>;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
-    auto make = [&](CUtensorMap* m, const float* base, int64_t rows, int64_t ld, int64_t bstride, int box_rows) {
-        return MODE >= 16 ? make_tmap_kmajor16(m, base, rows, p.K, ld, p.batch, bstride, box_rows)
-                          : make_tmap_kmajor(m, base, rows, p.K, ld, p.batch, bstride, box_rows);
+    auto make = [&](CUtensorMap* m, const float* base, int64_t rows, int64_t ld, int64_t bstride, int box_rows, int64_t batch) {
+        return MODE >= 16 ? make_tmap_kmajor16(m, base, rows, p.K, ld, batch, bstride, box_rows)
+                          : make_tmap_kmajor(m, base, rows, p.K, ld, batch, bstride, box_rows);
     };
-    if ((rc = make(&ma_hi, p.A_hi, p.M, p.lda, p.a_batch_stride, TBM))) return rc;
-    if ((rc = make(&mb_hi, p.B_hi, p.N, p.ldb, p.b_batch_stride, TBN))) return rc;
+    const int64_t b_batch = p.b_shared ? 1 : p.batch;
+    if ((rc = make(&ma_hi, p.A_hi, p.M, p.lda, p.a_batch_stride, TBM, p.batch))) return rc;
+    if ((rc = make(&mb_hi, p.B_hi, p.N, p.ldb, p.b_shared ? 0 : p.b_batch_stride, TBN, b_batch))) return rc;
     if (Cfg::kSplit) {
         if (!p.A_lo || !p.B_lo) { set_error("gemm_tc: split engines need head and remainder operands"); return NSF_ERR_INVALID_ARG; }
-        if ((rc = make(&ma_lo, p.A_lo, p.M, p.lda, p.a_batch_stride, TBM))) return rc;
-        if ((rc = make(&mb_lo, p.B_lo, p.N, p.ldb, p.b_batch_stride, TBN))) return rc;
+        if ((rc = make(&ma_lo, p.A_lo, p.M, p.lda, p.a_batch_stride, TBM, p.batch))) return rc;
+        if ((rc = make(&mb_lo, p.B_lo, p.N, p.ldb, p.b_shared ? 0 : p.b_batch_stride, TBN, b_batch))) return rc;
     } else {
         ma_lo = ma_hi;
         mb_lo = mb_hi;

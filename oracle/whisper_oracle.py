@@ -1,0 +1,86 @@
+"""CPU restatement of the Whisper log-mel front end and audio encoder  --  TEST INFRASTRUCTURE (numpy).
+
+Only tests/ may import this module; it is the checker for csrc/whisper.cu, never the thing shipped.
+
+The algorithm lives in a third-party dependency that is absent from /root/reference: openai-whisper, installed by the
+reference from ``git+https://github.com/openai/whisper.git`` at an unpinned HEAD (requirements.txt:2; call site
+asr/asr.py:69-74).  What is restated here is its published algorithm [upstream]:
+  whisper/audio.py  log_mel_spectrogram: torch.stft(n_fft 400, hop 160, hann(400), centred, reflect), |.|^2 of frames [:-1],
+                    mel filterbank (librosa slaney), log10(clamp(1e-10)), max(., max - 8), (. + 4) / 4
+  whisper/model.py  AudioEncoder / ResidualAttentionBlock / MultiHeadAttention (see csrc/whisper.cu header)
+**Parity unpinned** with respect to openai-whisper itself: the pin available offline is the transformers implementation of
+the same model (WhisperFeatureExtractor, WhisperModel.encoder), checked in tests/test_whisper.py.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import numpy as np
+
+
+def log_mel(audio: np.ndarray, filters: np.ndarray) -> np.ndarray:
+    """audio [480000] -> [n_mels, 3000] float32."""
+    x = np.asarray(audio, np.float64)
+    n_fft, hop = 400, 160
+    xp = np.pad(x, (n_fft // 2, n_fft // 2), mode="reflect")
+    win = 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(n_fft) / n_fft)
+    n_frames = 1 + (len(xp) - n_fft) // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(n_frames)[:, None]
+    spec = np.fft.rfft(xp[idx] * win, axis=1)[:-1]                       # drop the last frame (stft[..., :-1])
+    power = (np.abs(spec) ** 2).T                                        # [201, 3000]
+    mel = filters.astype(np.float64) @ power
+    log_spec = np.log10(np.maximum(mel, 1e-10))
+    log_spec = np.maximum(log_spec, log_spec.max() - 8.0)
+    return ((log_spec + 4.0) / 4.0).astype(np.float32)
+
+
+def _ln(x, g, b):
+    mu = x.mean(-1, keepdims=True)
+    var = ((x - mu) ** 2).mean(-1, keepdims=True)
+    return (x - mu) / np.sqrt(var + 1e-5) * g + b
+
+
+def _gelu(x):
+    from scipy.special import erf
+    return 0.5 * x * (1.0 + erf(x / math.sqrt(2.0)))
+
+
+def encoder(w: Dict[str, np.ndarray], mel: np.ndarray, dtype=np.float64) -> np.ndarray:
+    """w: openai-whisper encoder names (see notsofar_b200.whisper._canon); mel [n_mels, 3000] -> [1500, d]."""
+    W = {k: np.asarray(v, dtype) for k, v in w.items()}
+    x = np.asarray(mel, dtype)
+    d = W["conv1.weight"].shape[0]
+
+    def conv1d(x, wt, b, stride):
+        c_out, c_in, k = wt.shape
+        xp = np.pad(x, ((0, 0), (1, 1)))
+        t_out = (x.shape[1] + 2 - k) // stride + 1
+        cols = np.stack([xp[:, kk:kk + stride * t_out:stride] for kk in range(k)], axis=1)     # [c_in, k, t_out]
+        return np.einsum("ock,ckt->ot", wt, cols) + b[:, None]
+
+    x = _gelu(conv1d(x, W["conv1.weight"], W["conv1.bias"], 1))
+    x = _gelu(conv1d(x, W["conv2.weight"], W["conv2.bias"], 2))
+    x = x.T + W["positional_embedding"]
+    n_heads = d // 64
+    l = 0
+    while f"blocks.{l}.attn.query.weight" in W:
+        p = f"blocks.{l}."
+        h = _ln(x, W[p + "attn_ln.weight"], W[p + "attn_ln.bias"])
+        q = h @ W[p + "attn.query.weight"].T + W[p + "attn.query.bias"]
+        k = h @ W[p + "attn.key.weight"].T
+        v = h @ W[p + "attn.value.weight"].T + W[p + "attn.value.bias"]
+        T = x.shape[0]
+        q = q.reshape(T, n_heads, 64).transpose(1, 0, 2) * 64 ** -0.25
+        k = k.reshape(T, n_heads, 64).transpose(1, 0, 2) * 64 ** -0.25
+        v = v.reshape(T, n_heads, 64).transpose(1, 0, 2)
+        s = q @ k.transpose(0, 2, 1)
+        s = s - s.max(-1, keepdims=True)
+        pr = np.exp(s)
+        pr /= pr.sum(-1, keepdims=True)
+        o = (pr @ v).transpose(1, 0, 2).reshape(T, d)
+        x = x + o @ W[p + "attn.out.weight"].T + W[p + "attn.out.bias"]
+        h = _ln(x, W[p + "mlp_ln.weight"], W[p + "mlp_ln.bias"])
+        x = x + _gelu(h @ W[p + "mlp.0.weight"].T + W[p + "mlp.0.bias"]) @ W[p + "mlp.2.weight"].T + W[p + "mlp.2.bias"]
+        l += 1
+    return _ln(x, W["ln_post.weight"], W["ln_post.bias"])
