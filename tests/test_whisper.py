@@ -10,6 +10,18 @@ from oracle import whisper_oracle as WO
 from conftest import rel_l2
 
 
+@pytest.fixture(autouse=True)
+def _drop_reference_import_stubs():
+    """oracle/reference_shim.py leaves spec-less stand-ins for librosa / soundfile in sys.modules (earlier tests of the same
+    process); transformers probes optional packages with importlib.util.find_spec, which rejects those."""
+    import sys
+    for name in ("librosa", "soundfile", "sounddevice"):
+        mod = sys.modules.get(name)
+        if mod is not None and getattr(mod, "__spec__", None) is None:
+            del sys.modules[name]
+    yield
+
+
 def _hf_encoder(d_model, layers, heads, ffn, n_mels, seed=0, gain=1.0):
     from transformers import WhisperConfig
     from transformers.models.whisper.modeling_whisper import WhisperEncoder
