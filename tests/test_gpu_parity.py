@@ -665,3 +665,81 @@ def test_gemm_bf16_engine_vs_fp64(nb, dev):
     err = rel_l2(out.cpu().numpy(), ref)
     print("gemm bf16 rel err vs fp64 on rounded operands", err)
     assert err < 1e-5
+
+
+# ----------------------------------------------------------------------------------------------- edge cases of the plug-in
+@pytest.mark.parametrize("n_samples,kw", [
+    (48000 + 256, {}),                               # one frame more than a segment: a second, almost empty segment
+    (70001, dict(stitching_loss="mse")),             # truncated last segment, MSE stitching cost
+    (90000, dict(stitching_input="separation_result", hop_size_sec=1.0)),   # cost on |separated|, 2/3 overlap ratio
+])
+def test_edge_lengths_and_stitch_options_vs_oracle(nb, dev, small_weights, n_samples, kw):
+    from notsofar_b200 import synth
+    x = synth.synthetic_meeting(n_samples / 16000 + 0.1, seed=5)[:n_samples][None]
+    sep = _sep(nb, small_weights, dev, segments_per_batch=2)
+    cfg = nb.CssCfg(activity_th=0.5, show_progressbar=False, **kw)
+    stages = {}
+    wavs, side = nb.separate_and_stitch(x, sep, 16000, dev, cfg, _stages=stages)
+    plan = stages["plan"]
+    ocfg = O.OracleCfg(activity_th=0.5, **kw)
+    oplan = O.plan_segments(n_samples, 16000, ocfg)
+    assert (plan.num_segments, plan.mix_frames, plan.raw_frames) == (oplan.num_segments, oplan.mix_frames, oplan.raw_frames)
+    masks = stages["masks"].cpu().numpy()
+    X_dev = stages["X"].cpu().numpy()[:, :max(plan.raw_frames, 1)]
+    wavs_o, so = O.separate_and_stitch(x, small_weights, 16000, ocfg, masks_override=masks, mvdr_dtype=np.float64,
+                                       return_stages=True, stft_override=X_dev)
+    assert np.array_equal(stages["perms"], so["perms"])
+    assert np.array_equal(side["activity_b"].numpy(), np.squeeze(so["activity_b"]).reshape(side["activity_b"].shape))
+    assert np.array_equal(side["activity_final"].numpy()[0], np.squeeze(so["activity_final"]).reshape(side["activity_b"].shape))
+    assert len(wavs) == 3 and wavs[0].shape == wavs_o[0].shape == ((plan.mix_frames - 1) * 256 + 512,)
+    for k in range(3):
+        assert rel_l2(wavs[k], wavs_o[k]) < TOL
+
+
+@pytest.mark.parametrize("n_samples", [19000, 48000])
+def test_single_segment_inputs_fail_like_the_reference(nb, dev, small_weights, n_samples):
+    """Inputs of at most one segment leave the trailing m0 frames with zero stitching weight; the reference then stops at
+    its 'zero weights found' assertion (css.py:297, the first-segment window of :257-259 has no right edge) -- same here."""
+    x = (np.random.default_rng(0).standard_normal((1, n_samples, 7)) * 0.01).astype(np.float32)
+    with pytest.raises(AssertionError, match="zero weights found"):
+        O.separate_and_stitch(x, small_weights, 16000, O.OracleCfg(activity_th=0.5))
+    sep = _sep(nb, small_weights, dev)
+    with pytest.raises(AssertionError, match="zero weights found"):
+        nb.separate_and_stitch(x, sep, 16000, dev, nb.CssCfg(activity_th=0.5, show_progressbar=False))
+    torch.cuda.synchronize()
+
+
+def test_css_inference_files_cache_and_passthrough(nb, dev, small_weights, tmp_path):
+    """css_inference (css/css.py:51-107): checkpoint layout of helpers.py:14-37, 7 mono WAVs in, css_inference/<session>/ out,
+    fetch_from_cache, pass_through_ch0; the session row is copied, not mutated."""
+    import pandas as pd
+    import scipy.io.wavfile as wf
+    from notsofar_b200 import synth
+    from notsofar_b200 import css as css_mod
+    model_dir = tmp_path / "models" / "notsofar" / "conformer1.0" / "mc"
+    model_dir.mkdir(parents=True)
+    torch.save({"model": {"module." + k: torch.from_numpy(np.asarray(v)) for k, v in small_weights.items()}}, model_dir / "model.pt")
+    (model_dir / "cfg.yaml").write_text("single_channel: false\n")
+    x = synth.synthetic_meeting(5.0, seed=9)
+    wav_dir = tmp_path / "wavs"
+    wav_dir.mkdir()
+    names = []
+    for c in range(7):
+        f = wav_dir / f"ch{c}.wav"
+        wf.write(str(f), 16000, np.clip(np.rint(x[:, c] * 32768.0 * 8), -32768, 32767).astype(np.int16))
+        names.append(str(f))
+    session = pd.Series(dict(session_id="multichannel/MTG_1_dev", meeting_id="MTG_1", is_mc=True, wav_file_names=names))
+    css_mod._MODEL_CACHE.clear()
+    cfg = nb.CssCfg(show_progressbar=False, activity_th=0.3)
+    out = nb.css_inference(str(tmp_path / "out"), str(tmp_path / "models"), session, cfg, fetch_from_cache=False)
+    assert "sep_wav_file_names" not in session and len(out.sep_wav_file_names) == 3
+    d = tmp_path / "out" / "css_inference" / "multichannel/MTG_1_dev"
+    assert (d / "input_mixture.wav").exists()
+    for k, f in enumerate(out.sep_wav_file_names):
+        sr, pcm = wf.read(f)
+        assert f.endswith(f"sep_stream{k}.wav") and sr == 16000 and pcm.dtype == np.int16
+        assert np.abs(pcm).max() in (32438, 32439)                                    # 0.99 peak normalisation
+    again = nb.css_inference(str(tmp_path / "out"), str(tmp_path / "models"), session, cfg, fetch_from_cache=True)
+    assert [str(f) for f in again.sep_wav_file_names] == sorted(out.sep_wav_file_names)
+    thru = nb.css_inference(str(tmp_path / "out2"), str(tmp_path / "models"), session, nb.CssCfg(pass_through_ch0=True), False)
+    assert thru.sep_wav_file_names == names[:1] and not (tmp_path / "out2").exists()
