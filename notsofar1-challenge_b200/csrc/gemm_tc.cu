@@ -1,21 +1,24 @@
 // tcgen05 GEMM engine for sm_100a: persistent, warp-specialised.
 //
-//   D[b][m][n] = sum_k A[b][m][k] B[b][n][k]          both operands K-major fp32 (tf32 inputs)
+//   D[b][m][n] = sum_k A[b][m][k] B[b][n][k]          both operands K-major
 //
-// TMA (SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma kind::tf32 with two fp32 accumulators in TMEM
-// (double buffered, 2 x 256 columns) -> tcgen05.ld epilogue staged through shared memory so that every
-// global store is a full 128-byte row segment, with the fused ops of gemm_common.cuh.
+// TMA (SWIZZLE_128B) -> shared-memory ring -> tcgen05.mma with two fp32 accumulators in TMEM (double buffered,
+// 2 x 256 columns) -> tcgen05.ld epilogue staged through a swizzled shared-memory transpose so that every lane
+// owns 8 consecutive output columns (16-byte global accesses), with the fused ops of gemm_common.cuh.
 //
-// 3xTF32 (NTERMS == 3): D = A_lo B_hi + A_hi B_lo + A_hi B_hi accumulated in the same TMEM tile; the operands
-// arrive pre-split (X_hi has its 13 low mantissa bits clear, X_lo = X - X_hi exactly), so the tensor core's
-// truncation of X_hi is a no-op and the result is fp32-grade (~2^-21 relative).
+// MODE selects the arithmetic (template parameter; operands arrive pre-split by the producing kernels):
+//   16   2xBF16 / 2xF16: D = A_lo B_hi + A_hi B_lo + A_hi B_hi, three kind::f16 MMAs on 16-bit head / remainder planes
+//        (bf16: 16 mantissa bits, fp32 range; fp16: 22 bits on power-of-two-scaled values), BLOCK_K = 64
+//   116  plain bf16, one kind::f16 MMA (the Whisper encoder), BLOCK_K = 64, 4 stages
+//   3    3xTF32: the same three-term form on kind::tf32 (TF32 head with 13 cleared bits + exact fp32 remainder), BLOCK_K = 32
+//   1    single-pass TF32
 //
 // CTA = 10 warps, one CTA per SM, grid = min(#tiles, #SMs), tiles handed out round-robin (n fastest, so the
 // CTAs of a wave share A row-blocks through L2):
 //   warp 0 lane 0  TMA producer            warp 1  TMEM allocator + lane 0 MMA issuer
 //   warps 2..9     epilogue (warp w reads the 32 TMEM lanes of quarter w % 4; w and w + 4 split the columns)
-// Tile 128 x 256, BLOCK_K = 32 floats = one 128-byte swizzle row; 2 stages of 96 KB for 3xTF32, 4 of 48 KB
-// for single-pass TF32.  While the epilogue warps drain accumulator `acc`, the MMA warp already fills `acc^1`.
+// Tile 128 x 256, one 128-byte swizzle row of K per stage; 2 stages of 96 KB for the split modes, 4 of 48 KB for the
+// single-pass ones.  While the epilogue warps drain accumulator `acc`, the MMA warp already fills `acc^1`.
 #include "gemm_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -439,8 +442,6 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
     GemmParams pv = p;
     {
         auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
-        const int osz = 2;      // strictest element size of the outputs (16-bit planes): 8 elements = 16 bytes
-        (void)osz;
         bool ok = p.N % 8 == 0 && (!p.bias || al16(p.bias));
         switch (p.epi) {
             case EPI_STORE: case EPI_RESID:
