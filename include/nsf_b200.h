@@ -233,9 +233,27 @@ int64_t nsf_whisper_mel_plane_elems(int n_mels, int n_batch);
  * filters [n_mels][201] f32 (slaney mel filterbank); log_spec [n_batch][n_mels][3000] f32 and gmax [n_batch] u32 are scratch. */
 int nsf_whisper_logmel(const float* audio, int n_batch, int64_t n_samples, const float* filters, int n_mels, float* log_spec,
                        uint32_t* gmax, void* mel_hi, void* mel_lo, void* stream);
-/* out [n_batch * 1500][d_model] f32 = ln_post(encoder(mel)) */
-int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* mel_hi, const void* mel_lo, int n_batch, float* out,
+/* out [n_batch * 1500][d_model] f32 = ln_post(encoder(mel)); out_bf16 (optional): the same as a bf16 plane, the operand
+ * nsf_whisper_decoder_prefill_cross reads */
+int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* mel_hi, const void* mel_lo, int n_batch, float* out, void* out_bf16,
                                 void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- Whisper text decoder, greedy step (csrc/whisper_dec.cu; whisper/model.py TextDecoder [upstream, unpinned]).
+ * state: one caller-owned device buffer of nsf_whisper_decoder_state_bytes (cross / self key-value caches in bf16,
+ * activations).  prefill_cross projects the audio features (bf16 plane [n_batch*n_audio_ctx][d_model], written by
+ * nsf_whisper_encoder_forward) into every layer's cross-attention caches; step consumes one token per sequence at
+ * position pos (0-based, the initial prompt is fed token by token) and returns the arg-max next tokens
+ * (and, if logits_out != NULL, the fp32 logits [n_batch][vocab]). */
+typedef struct nsf_whisper_decoder nsf_whisper_decoder;
+typedef struct { int vocab, n_text_ctx, d_model, n_heads, n_layers, d_ff, n_audio_ctx; } nsf_whisper_dec_dims;
+int64_t nsf_whisper_decoder_num_offsets(const nsf_whisper_dec_dims* dims);
+int nsf_whisper_decoder_create(const nsf_whisper_dec_dims* dims, const float* blob, int64_t blob_floats, const int64_t* offsets /*host*/,
+                               int n_offsets, nsf_whisper_decoder** out);
+void nsf_whisper_decoder_destroy(nsf_whisper_decoder* h);
+int64_t nsf_whisper_decoder_state_bytes(const nsf_whisper_dec_dims* dims, int n_batch);
+int nsf_whisper_decoder_prefill_cross(nsf_whisper_decoder* h, const void* enc_bf16, int n_batch, void* state, int64_t state_bytes, void* stream);
+int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* tokens, int pos, int n_batch, void* state, int64_t state_bytes,
+                             float* logits_out, int32_t* next_tokens, void* stream);
 
 /* Test hook: non-causal multi-head attention with online softmax (flash_attn.cu, the Whisper encoder's attention) on fp32
  * inputs that are rounded to bf16 inside.  q, k, v [n_batch*n_heads][T][64] (already scaled), out [n_batch*T][n_heads*64] f32:

@@ -214,7 +214,7 @@ extern "C" int nsf_whisper_logmel(const float* audio, int n_batch, int64_t n_sam
 }
 
 extern "C" int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* mel_hi, const void* mel_lo, int n_batch, float* out,
-                                           void* workspace, int64_t workspace_bytes, void* stream_) {
+                                           void* out_bf16, void* workspace, int64_t workspace_bytes, void* stream_) {
     NSF_REQUIRE(h && mel_hi && mel_lo && out && workspace, "nsf_whisper_encoder_forward: null pointer");
     if (n_batch <= 0) return NSF_OK;
     const nsf_whisper_dims& D = h->dims;
@@ -282,6 +282,7 @@ extern "C" int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* m
         if ((rc = linear(w.u, dff, h->l(L, WL_W2), h->l(L, WL_B2), d, EPI_RESID, w.x, d))) return rc;
     }
     { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-      rc = ln_launch(w.x, M, d, h->g(WG_LNP_G), h->g(WG_LNP_B), 0, out, nullptr, nullptr, nullptr, nullptr, SPLIT_FP32, s); }
+      rc = ln_launch(w.x, M, d, h->g(WG_LNP_G), h->g(WG_LNP_B), 0, out, nullptr, nullptr, reinterpret_cast<float*>(out_bf16),
+                     reinterpret_cast<float*>(out_bf16), SPLIT_BF16_1, s); }
     return rc;
 }

@@ -1,0 +1,280 @@
+// Whisper text decoder, greedy step (bf16 tensor-core GEMMs, fp32 residual stream, bf16 key / value caches).
+//
+// Algorithm [upstream openai-whisper, unpinned -- whisper/model.py TextDecoder / ResidualAttentionBlock; see whisper.cu]:
+//   x = token_embedding[tok] + positional_embedding[pos]
+//   n_layer x { x += self_attn(ln(x), causal, kv cache); x += cross_attn(ln(x), audio features); x += mlp(ln(x)) }
+//   logits = ln(x) @ token_embedding^T;  greedy: next token = argmax(logits)
+// The d_k^-0.25 scales of q and k are folded into the packed weights.  Cross-attention keys / values of all layers are
+// projected once per batch of chunks (nsf_whisper_decoder_prefill_cross); every decode step then is a fixed sequence of
+// small-M tcgen05 GEMMs (M = sequences in flight) and two bandwidth-bound cache-attention kernels.
+// Not built: beam search, temperature fallback, the logit filters of whisper/decoding.py (SuppressBlank, SuppressTokens,
+// timestamp rules) and word timestamps -- the host loop is plain greedy arg-max.
+#include "gemm_common.cuh"
+#include <new>
+
+namespace nsf {
+
+enum WdGlobal { WD_TOK_EMB = 0, WD_POS, WD_LN_G, WD_LN_B, WD_NUM };
+enum WdLayer { WDL_LN1_G = 0, WDL_LN1_B, WDL_WQKV, WDL_BQKV, WDL_WO, WDL_BO, WDL_LNC_G, WDL_LNC_B, WDL_WCQ, WDL_BCQ, WDL_WCKV, WDL_BCKV,
+               WDL_WCO, WDL_BCO, WDL_LN2_G, WDL_LN2_B, WDL_W1, WDL_B1, WDL_W2, WDL_B2, WDL_NUM };
+
+__global__ void __launch_bounds__(256)
+wd_embed_kernel(const int32_t* __restrict__ tokens, const uint16_t* __restrict__ emb, const float* __restrict__ pos_row, int d, int vocab,
+                float* __restrict__ x) {
+    const int b = blockIdx.x;
+    int tok = tokens[b];
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+    for (int c = threadIdx.x; c < d; c += blockDim.x)
+        x[(size_t)b * d + c] = __bfloat162float(__ushort_as_bfloat16(emb[(size_t)tok * d + c])) + __ldg(pos_row + c);
+}
+
+// One CTA per (sequence, head): optional append of the new key / value to the cache, scores against n_keys cached keys,
+// softmax, weighted sum of the cached values.  q / k_new / v_new: fp32 rows of pitch ldq (column head * 64 + d).
+// Kc, Vc: [n_bh][t_max][64] bf16.  out: bf16 plane [n_batch][d_model].
+template <bool APPEND>
+__global__ void __launch_bounds__(256)
+wd_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_new, const float* __restrict__ v_new, int64_t ldq,
+               uint16_t* __restrict__ Kc, uint16_t* __restrict__ Vc, int n_keys, int t_max, int n_heads, uint16_t* __restrict__ out, int d_model) {
+    extern __shared__ float sm[];                     // q[64] | p[n_keys] | red[32] | acc[4][64]
+    float* qs = sm;
+    float* p = sm + 64;
+    float* red = p + ((n_keys + 31) & ~31);
+    float* accs = red + 32;
+    const int bh = blockIdx.x, b = bh / n_heads, h = bh - b * n_heads;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint16_t* K = Kc + (size_t)bh * t_max * 64;
+    uint16_t* V = Vc + (size_t)bh * t_max * 64;
+    if (tid < 64) {
+        qs[tid] = q[(size_t)b * ldq + h * 64 + tid];
+        if (APPEND) {
+            K[(size_t)(n_keys - 1) * 64 + tid] = __bfloat16_as_ushort(__float2bfloat16_rn(k_new[(size_t)b * ldq + h * 64 + tid]));
+            V[(size_t)(n_keys - 1) * 64 + tid] = __bfloat16_as_ushort(__float2bfloat16_rn(v_new[(size_t)b * ldq + h * 64 + tid]));
+        }
+    }
+    __syncthreads();
+    const float q0 = qs[2 * lane], q1 = qs[2 * lane + 1];
+    float mx = -INFINITY;
+    for (int t = warp; t < n_keys; t += 8) {
+        const uint32_t kk = *reinterpret_cast<const uint32_t*>(K + (size_t)t * 64 + 2 * lane);
+        float s = q0 * __uint_as_float(kk << 16) + q1 * __uint_as_float(kk & 0xffff0000u);
+        s = warp_sum(s);
+        if (lane == 0) p[t] = s;
+        mx = fmaxf(mx, s);
+    }
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int t = tid; t < n_keys; t += 256) {
+        const float e = __expf(p[t] - mx);
+        p[t] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[w];
+    const int dcol = tid & 63, grp = tid >> 6;
+    float acc = 0.f;
+    for (int t = grp; t < n_keys; t += 4)
+        acc = fmaf(p[t], __bfloat162float(__ushort_as_bfloat16(V[(size_t)t * 64 + dcol])), acc);
+    accs[grp * 64 + dcol] = acc;
+    __syncthreads();
+    if (tid < 64) {
+        const float o = (accs[tid] + accs[64 + tid] + accs[128 + tid] + accs[192 + tid]) / sum;
+        out[(size_t)b * d_model + h * 64 + tid] = __bfloat16_as_ushort(__float2bfloat16_rn(o));
+    }
+}
+
+// first maximum of every row (torch.argmax)
+__global__ void __launch_bounds__(1024)
+wd_argmax_kernel(const float* __restrict__ logits, int vocab, int32_t* __restrict__ next) {
+    __shared__ float bv[32];
+    __shared__ int bi[32];
+    const float* row = logits + (size_t)blockIdx.x * vocab;
+    float best = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < vocab; i += blockDim.x) {
+        const float v = row[i];
+        if (v > best) { best = v; idx = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
+        next[blockIdx.x] = idx;
+    }
+}
+
+}  // namespace nsf
+
+struct nsf_whisper_decoder {
+    nsf_whisper_dec_dims dims;
+    const float* blob;
+    int64_t* offsets;
+    const float* g(int i) const { return blob + offsets[i]; }
+    const float* l(int layer, int i) const { return blob + offsets[nsf::WD_NUM + layer * nsf::WDL_NUM + i]; }
+};
+
+namespace nsf {
+
+static inline int64_t wd_align(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct WdState {
+    uint16_t *ck, *cv, *sk, *sv;       // cross / self caches: [L][n_bh][t][64]
+    float *x, *qkv, *qc, *logits;
+    float *h, *u;                      // bf16 planes
+    int32_t* next;
+    int64_t total_bytes;
+};
+static WdState wd_carve(const nsf_whisper_dec_dims& D, int n_batch, unsigned char* base) {
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { unsigned char* p = base ? base + off : nullptr; off += wd_align(bytes, 256); return p; };
+    const int64_t bh = (int64_t)n_batch * D.n_heads;
+    WdState s;
+    s.ck = (uint16_t*)take(D.n_layers * bh * D.n_audio_ctx * 64 * 2);
+    s.cv = (uint16_t*)take(D.n_layers * bh * D.n_audio_ctx * 64 * 2);
+    s.sk = (uint16_t*)take(D.n_layers * bh * D.n_text_ctx * 64 * 2);
+    s.sv = (uint16_t*)take(D.n_layers * bh * D.n_text_ctx * 64 * 2);
+    s.x = (float*)take((int64_t)n_batch * D.d_model * 4);
+    s.qkv = (float*)take((int64_t)n_batch * 3 * D.d_model * 4);
+    s.qc = (float*)take((int64_t)n_batch * D.d_model * 4);
+    s.logits = (float*)take((int64_t)n_batch * D.vocab * 4);
+    s.h = (float*)take((int64_t)n_batch * D.d_model * 2);
+    s.u = (float*)take((int64_t)n_batch * D.d_ff * 2);
+    s.next = (int32_t*)take((int64_t)n_batch * 4);
+    s.total_bytes = off;
+    return s;
+}
+
+}  // namespace nsf
+
+using namespace nsf;
+
+extern "C" int64_t nsf_whisper_decoder_num_offsets(const nsf_whisper_dec_dims* d) { return d ? WD_NUM + (int64_t)WDL_NUM * d->n_layers : 0; }
+
+extern "C" int nsf_whisper_decoder_create(const nsf_whisper_dec_dims* dims, const float* blob, int64_t blob_floats, const int64_t* offsets,
+                                          int n_offsets, nsf_whisper_decoder** out) {
+    NSF_REQUIRE(dims && blob && offsets && out, "nsf_whisper_decoder_create: null pointer");
+    NSF_REQUIRE(dims->d_model % 128 == 0 && dims->d_model == dims->n_heads * 64 && dims->d_ff % 8 == 0 && dims->n_layers >= 1 &&
+                dims->vocab >= 2 && dims->n_text_ctx >= 1 && dims->n_audio_ctx >= 1, "nsf_whisper_decoder_create: bad dims");
+    NSF_REQUIRE(n_offsets == nsf_whisper_decoder_num_offsets(dims), "nsf_whisper_decoder_create: expected %lld offsets",
+                (long long)nsf_whisper_decoder_num_offsets(dims));
+    for (int i = 0; i < n_offsets; ++i)
+        NSF_REQUIRE(offsets[i] >= 0 && offsets[i] < blob_floats && (offsets[i] & 3) == 0, "nsf_whisper_decoder_create: offset %d", i);
+    nsf_whisper_decoder* h = new (std::nothrow) nsf_whisper_decoder;
+    NSF_REQUIRE(h, "out of memory");
+    h->dims = *dims; h->blob = blob;
+    h->offsets = new (std::nothrow) int64_t[n_offsets];
+    if (!h->offsets) { delete h; set_error("out of memory"); return NSF_ERR_INVALID_ARG; }
+    for (int i = 0; i < n_offsets; ++i) h->offsets[i] = offsets[i];
+    *out = h;
+    return NSF_OK;
+}
+
+extern "C" void nsf_whisper_decoder_destroy(nsf_whisper_decoder* h) {
+    if (!h) return;
+    delete[] h->offsets;
+    delete h;
+}
+
+extern "C" int64_t nsf_whisper_decoder_state_bytes(const nsf_whisper_dec_dims* dims, int n_batch) {
+    if (!dims || n_batch <= 0) return 0;
+    return wd_carve(*dims, n_batch, nullptr).total_bytes;
+}
+
+static GemmParams wd_base(const nsf_whisper_dec_dims& D, int M) {
+    GemmParams p = {};
+    p.batch = 1; p.alpha = 1.f; p.acc_scale = 1.f;
+    p.op_fmt = SPLIT_BF16_1; p.out_fmt = SPLIT_BF16_1; p.qkv_fmt = SPLIT_BF16_1;
+    p.n_heads = D.n_heads; p.d_k = 64; p.d_model = D.d_model;
+    p.M = M;
+    return p;
+}
+
+extern "C" int nsf_whisper_decoder_prefill_cross(nsf_whisper_decoder* h, const void* enc_bf16, int n_batch, void* state, int64_t state_bytes,
+                                                 void* stream_) {
+    NSF_REQUIRE(h && enc_bf16 && state, "nsf_whisper_decoder_prefill_cross: null pointer");
+    const nsf_whisper_dec_dims& D = h->dims;
+    NSF_REQUIRE(((uintptr_t)state & 255) == 0, "nsf_whisper_decoder_prefill_cross: state must be 256-byte aligned");
+    WdState st = wd_carve(D, n_batch, reinterpret_cast<unsigned char*>(state));
+    NSF_REQUIRE(state_bytes >= st.total_bytes, "nsf_whisper_decoder_prefill_cross: state too small");
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int d = D.d_model, Ta = D.n_audio_ctx;
+    const int64_t per_layer = (int64_t)n_batch * D.n_heads * Ta * 64;
+    for (int L = 0; L < D.n_layers; ++L) {
+        // [Wk; Wv] against the audio features; the q / k slots of the QKV scatter are the layer's cross key / value caches
+        GemmParams p = wd_base(D, n_batch * Ta);
+        p.A_hi = reinterpret_cast<const float*>(enc_bf16); p.lda = d;
+        p.B_hi = h->l(L, WDL_WCKV); p.ldb = d;
+        p.N = 2 * d; p.K = d; p.n_valid = 2 * d;
+        p.bias = h->l(L, WDL_BCKV); p.epi = EPI_QKV;
+        p.T = Ta; p.Tp = Ta;
+        p.q_hi = p.q_lo = reinterpret_cast<float*>(st.ck + L * per_layer);
+        p.k_hi = p.k_lo = reinterpret_cast<float*>(st.cv + L * per_layer);
+        p.vt_hi = p.vt_lo = nullptr;
+        int rc = gemm_launch(NSF_GEMM_TC_BF16, p, s);
+        if (rc) return rc;
+    }
+    return NSF_OK;
+}
+
+extern "C" int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* tokens, int pos, int n_batch, void* state, int64_t state_bytes,
+                                        float* logits_out, int32_t* next_tokens, void* stream_) {
+    NSF_REQUIRE(h && tokens && state && next_tokens, "nsf_whisper_decoder_step: null pointer");
+    const nsf_whisper_dec_dims& D = h->dims;
+    NSF_REQUIRE(pos >= 0 && pos < D.n_text_ctx, "nsf_whisper_decoder_step: pos=%d outside the text context %d", pos, D.n_text_ctx);
+    NSF_REQUIRE(((uintptr_t)state & 255) == 0, "nsf_whisper_decoder_step: state must be 256-byte aligned");
+    WdState st = wd_carve(D, n_batch, reinterpret_cast<unsigned char*>(state));
+    NSF_REQUIRE(state_bytes >= st.total_bytes, "nsf_whisper_decoder_step: state too small");
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int d = D.d_model, H = D.n_heads, B = n_batch, dff = D.d_ff;
+    const int64_t bh = (int64_t)B * H;
+    int rc;
+    uint16_t* hb = reinterpret_cast<uint16_t*>(st.h);
+
+    wd_embed_kernel<<<B, 256, 0, s>>>(tokens, reinterpret_cast<const uint16_t*>(h->g(WD_TOK_EMB)), h->g(WD_POS) + (size_t)pos * d, d, D.vocab, st.x);
+    if ((rc = check_launch("wd_embed_kernel"))) return rc;
+    auto linear = [&](const float* a, int K, const float* wt, const float* bias, int N, int epi, float* o0, int64_t ldo) {
+        GemmParams p = wd_base(D, B);
+        p.A_hi = a; p.lda = K; p.B_hi = wt; p.ldb = K;
+        p.N = N; p.K = K; p.n_valid = N;
+        p.bias = bias; p.epi = epi; p.out0 = o0; p.out1 = o0; p.ldo = ldo;
+        return gemm_launch(NSF_GEMM_TC_BF16, p, s);
+    };
+    auto attn_smem = [](int n_keys) { return (size_t)(64 + ((n_keys + 31) & ~31) + 32 + 256) * sizeof(float); };
+    for (int L = 0; L < D.n_layers; ++L) {
+        if ((rc = ln_launch(st.x, B, d, h->l(L, WDL_LN1_G), h->l(L, WDL_LN1_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
+        if ((rc = linear(st.h, d, h->l(L, WDL_WQKV), h->l(L, WDL_BQKV), 3 * d, EPI_STORE, st.qkv, 3 * d))) return rc;
+        wd_attn_kernel<true><<<(unsigned)bh, 256, attn_smem(pos + 1), s>>>(st.qkv, st.qkv + d, st.qkv + 2 * d, 3 * d,
+            st.sk + (size_t)L * bh * D.n_text_ctx * 64, st.sv + (size_t)L * bh * D.n_text_ctx * 64, pos + 1, D.n_text_ctx, H, hb, d);
+        if ((rc = check_launch("wd_attn_kernel<self>"))) return rc;
+        if ((rc = linear(st.h, d, h->l(L, WDL_WO), h->l(L, WDL_BO), d, EPI_RESID, st.x, d))) return rc;
+        if ((rc = ln_launch(st.x, B, d, h->l(L, WDL_LNC_G), h->l(L, WDL_LNC_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
+        if ((rc = linear(st.h, d, h->l(L, WDL_WCQ), h->l(L, WDL_BCQ), d, EPI_STORE, st.qc, d))) return rc;
+        wd_attn_kernel<false><<<(unsigned)bh, 256, attn_smem(D.n_audio_ctx), s>>>(st.qc, nullptr, nullptr, d,
+            st.ck + (size_t)L * bh * D.n_audio_ctx * 64, st.cv + (size_t)L * bh * D.n_audio_ctx * 64, D.n_audio_ctx, D.n_audio_ctx, H, hb, d);
+        if ((rc = check_launch("wd_attn_kernel<cross>"))) return rc;
+        if ((rc = linear(st.h, d, h->l(L, WDL_WCO), h->l(L, WDL_BCO), d, EPI_RESID, st.x, d))) return rc;
+        if ((rc = ln_launch(st.x, B, d, h->l(L, WDL_LN2_G), h->l(L, WDL_LN2_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
+        if ((rc = linear(st.h, d, h->l(L, WDL_W1), h->l(L, WDL_B1), dff, EPI_GELU_SPLIT, st.u, dff))) return rc;
+        if ((rc = linear(st.u, dff, h->l(L, WDL_W2), h->l(L, WDL_B2), d, EPI_RESID, st.x, d))) return rc;
+    }
+    if ((rc = ln_launch(st.x, B, d, h->g(WD_LN_G), h->g(WD_LN_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
+    float* lg = logits_out ? logits_out : st.logits;
+    if ((rc = linear(st.h, d, h->g(WD_TOK_EMB), nullptr, D.vocab, EPI_STORE, lg, D.vocab))) return rc;
+    wd_argmax_kernel<<<B, 1024, 0, s>>>(lg, D.vocab, next_tokens);
+    return check_launch("wd_argmax_kernel");
+}

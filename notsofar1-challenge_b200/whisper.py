@@ -191,7 +191,7 @@ class WhisperEncoderB200:
             self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         out = torch.empty((B, self.dims.n_ctx, self.dims.d_model), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _cabi.check(self._lib.nsf_whisper_encoder_forward(self._handle, _cabi.ptr(mel_hi), _cabi.ptr(mel_lo), B, _cabi.ptr(out),
+            _cabi.check(self._lib.nsf_whisper_encoder_forward(self._handle, _cabi.ptr(mel_hi), _cabi.ptr(mel_lo), B, _cabi.ptr(out), None,
                                                               _cabi.ptr(self._ws), need, _cabi.stream_ptr()), "nsf_whisper_encoder_forward")
         return out
 
@@ -208,3 +208,186 @@ class WhisperEncoderB200:
     def encode_audio(self, audio: torch.Tensor) -> torch.Tensor:
         hi, lo, _ = self.log_mel(audio)
         return self.encode_mel(hi, lo)
+
+
+# ------------------------------------------------------------------------------------------- text decoder (greedy)
+class WhisperDecDims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("vocab", "n_text_ctx", "d_model", "n_heads", "n_layers", "d_ff", "n_audio_ctx")]
+
+
+def _canon_decoder(sd: Dict[str, object]) -> Dict[str, np.ndarray]:
+    """-> openai-whisper decoder names (token_embedding.weight, positional_embedding, blocks.N.attn.query.weight, ...,
+    blocks.N.cross_attn.*, ln.weight) from either naming."""
+    hf = {"self_attn.q_proj": "attn.query", "self_attn.k_proj": "attn.key", "self_attn.v_proj": "attn.value",
+          "self_attn.out_proj": "attn.out", "self_attn_layer_norm": "attn_ln",
+          "encoder_attn.q_proj": "cross_attn.query", "encoder_attn.k_proj": "cross_attn.key", "encoder_attn.v_proj": "cross_attn.value",
+          "encoder_attn.out_proj": "cross_attn.out", "encoder_attn_layer_norm": "cross_attn_ln",
+          "fc1": "mlp.0", "fc2": "mlp.2", "final_layer_norm": "mlp_ln"}
+    out = {}
+    for k, v in sd.items():
+        for pre in ("model.decoder.", "decoder."):
+            if k.startswith(pre):
+                k = k[len(pre):]
+                break
+        else:
+            continue
+        if isinstance(v, torch.Tensor):
+            v = v.detach().float().cpu().numpy()
+        v = np.asarray(v)
+        if k.startswith("layers."):
+            _, n, rest = k.split(".", 2)
+            for a, b in hf.items():
+                if rest.startswith(a + "."):
+                    rest = b + rest[len(a):]
+                    break
+            k = f"blocks.{n}.{rest}"
+        elif k.startswith("layer_norm."):
+            k = "ln." + k[len("layer_norm."):]
+        elif k == "embed_tokens.weight":
+            k = "token_embedding.weight"
+        elif k == "embed_positions.weight":
+            k = "positional_embedding"
+        out[k] = v
+    return out
+
+
+def pack_whisper_decoder(state_dict: Dict[str, object], n_audio_ctx: int = 1500):
+    """-> (WhisperDecDims, blob, offsets); entry order: csrc/whisper_dec.cu WdGlobal / WdLayer."""
+    w = _canon_decoder(state_dict)
+    vocab, d = w["token_embedding.weight"].shape
+    n_text_ctx = w["positional_embedding"].shape[0]
+    n_layers = 0
+    while f"blocks.{n_layers}.attn.query.weight" in w:
+        n_layers += 1
+    d_ff = w["blocks.0.mlp.0.weight"].shape[0]
+    chunks, offsets, cursor = [], [], 0
+
+    def add(a32):
+        nonlocal cursor
+        a32 = np.ascontiguousarray(a32).reshape(-1)
+        assert a32.dtype == np.float32
+        offsets.append(cursor)
+        chunks.append(a32)
+        pad = (-a32.size) % 64
+        if pad:
+            chunks.append(np.zeros(pad, np.float32))
+        cursor += a32.size + pad
+
+    def add_bf16(a):
+        bits = _bf16_bits(a).reshape(-1)
+        if bits.size % 2:
+            bits = np.concatenate([bits, np.zeros(1, bits.dtype)])
+        add(bits.view(np.float32))
+
+    f32 = lambda a: np.asarray(a, np.float32)
+    add_bf16(w["token_embedding.weight"]); add(f32(w["positional_embedding"])); add(f32(w["ln.weight"])); add(f32(w["ln.bias"]))
+    sc = np.float32(64 ** -0.25)
+    z = np.zeros(d, np.float32)
+    for l in range(n_layers):
+        p = f"blocks.{l}."
+        add(f32(w[p + "attn_ln.weight"])); add(f32(w[p + "attn_ln.bias"]))
+        add_bf16(np.concatenate([w[p + "attn.query.weight"] * sc, w[p + "attn.key.weight"] * sc, w[p + "attn.value.weight"]], 0))
+        add(f32(np.concatenate([w[p + "attn.query.bias"] * sc, z, w[p + "attn.value.bias"]])))
+        add_bf16(w[p + "attn.out.weight"]); add(f32(w[p + "attn.out.bias"]))
+        add(f32(w[p + "cross_attn_ln.weight"])); add(f32(w[p + "cross_attn_ln.bias"]))
+        add_bf16(w[p + "cross_attn.query.weight"] * sc); add(f32(w[p + "cross_attn.query.bias"] * sc))
+        add_bf16(np.concatenate([w[p + "cross_attn.key.weight"] * sc, w[p + "cross_attn.value.weight"]], 0))
+        add(f32(np.concatenate([z, w[p + "cross_attn.value.bias"]])))
+        add_bf16(w[p + "cross_attn.out.weight"]); add(f32(w[p + "cross_attn.out.bias"]))
+        add(f32(w[p + "mlp_ln.weight"])); add(f32(w[p + "mlp_ln.bias"]))
+        add_bf16(w[p + "mlp.0.weight"]); add(f32(w[p + "mlp.0.bias"]))
+        add_bf16(w[p + "mlp.2.weight"]); add(f32(w[p + "mlp.2.bias"]))
+    dims = WhisperDecDims(vocab=vocab, n_text_ctx=n_text_ctx, d_model=d, n_heads=d // 64, n_layers=n_layers, d_ff=d_ff, n_audio_ctx=n_audio_ctx)
+    assert len(offsets) == 4 + 20 * n_layers
+    return dims, np.concatenate(chunks), np.asarray(offsets, np.int64)
+
+
+class WhisperB200:
+    """Encoder + greedy decoder of one Whisper model on one B200: audio chunks in, token ids out.
+
+    Plain greedy arg-max decoding (whisper/decoding.py GreedyDecoder with temperature 0) from a caller-given prompt
+    (e.g. <|startoftranscript|><|en|><|transcribe|><|notimestamps|>); the logit filters, beam search, temperature
+    fallback and word timestamps of openai-whisper's DecodingTask are not built."""
+
+    def __init__(self, state_dict: Dict[str, object], device: Optional[torch.device] = None):
+        self.encoder = WhisperEncoderB200(state_dict, device=device)
+        self.device = self.encoder.device
+        self._lib = self.encoder._lib
+        dims, blob, offsets = pack_whisper_decoder(state_dict, self.encoder.dims.n_ctx)
+        self.dec_dims = dims
+        self._dblob = torch.from_numpy(blob).to(self.device)
+        self._dh = C.c_void_p()
+        offs = (C.c_int64 * len(offsets))(*offsets.tolist())
+        _cabi.check(self._lib.nsf_whisper_decoder_create(C.byref(dims), _cabi.ptr(self._dblob), self._dblob.numel(), offs, len(offsets),
+                                                         C.byref(self._dh)), "nsf_whisper_decoder_create")
+        self._state = None
+
+    def __del__(self):
+        try:
+            self._lib.nsf_whisper_decoder_destroy(self._dh)
+        except Exception:
+            pass
+
+    def encode(self, mel_hi: torch.Tensor, mel_lo: torch.Tensor):
+        """-> (encoder output fp32 [B, 1500, d], the same as a bf16 plane int16 [B, 1500, d])"""
+        enc = self.encoder
+        B = mel_hi.shape[0]
+        need = int(self._lib.nsf_whisper_encoder_workspace_bytes(C.byref(enc.dims), B))
+        if enc._ws is None or enc._ws.numel() < need:
+            enc._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty((B, enc.dims.n_ctx, enc.dims.d_model), dtype=torch.float32, device=self.device)
+        out16 = torch.empty((B, enc.dims.n_ctx, enc.dims.d_model), dtype=torch.int16, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.nsf_whisper_encoder_forward(enc._handle, _cabi.ptr(mel_hi), _cabi.ptr(mel_lo), B, _cabi.ptr(out),
+                                                              _cabi.ptr(out16), _cabi.ptr(enc._ws), need, _cabi.stream_ptr()),
+                        "nsf_whisper_encoder_forward")
+        return out, out16
+
+    def _ensure_state(self, B: int):
+        need = int(self._lib.nsf_whisper_decoder_state_bytes(C.byref(self.dec_dims), B))
+        if self._state is None or self._state.numel() < need:
+            self._state = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return need
+
+    @torch.no_grad()
+    def decode_greedy(self, enc_bf16: torch.Tensor, prompt, max_new_tokens: int = 224, eot: Optional[int] = None,
+                      forced_tokens: Optional[torch.Tensor] = None, return_logits: bool = False):
+        """enc_bf16 int16 [B, 1500, d] (from ``encode``).  prompt: list of token ids fed first.  Returns tokens int32
+        [B, len(prompt) + n_new] (and the fp32 logits of every step if return_logits).  forced_tokens [B, n]: teacher forcing
+        (the arg-max is still computed and returned, the forced token is fed) -- used by the parity tests."""
+        B = enc_bf16.shape[0]
+        D = self.dec_dims
+        need = self._ensure_state(B)
+        lib, st = self._lib, self._state
+        with torch.cuda.device(self.device):
+            _cabi.check(lib.nsf_whisper_decoder_prefill_cross(self._dh, _cabi.ptr(enc_bf16), B, _cabi.ptr(st), need, _cabi.stream_ptr()),
+                        "nsf_whisper_decoder_prefill_cross")
+            n_prompt = len(prompt)
+            total = min(D.n_text_ctx, n_prompt + max_new_tokens)
+            tokens = torch.zeros((B, total), dtype=torch.int32, device=self.device)
+            tokens[:, :n_prompt] = torch.tensor(prompt, dtype=torch.int32, device=self.device)
+            nxt = torch.empty((B,), dtype=torch.int32, device=self.device)
+            argmaxes = torch.zeros((B, total), dtype=torch.int32, device=self.device)
+            logits_all = torch.empty((total, B, D.vocab), dtype=torch.float32, device=self.device) if return_logits else None
+            done = torch.zeros((B,), dtype=torch.bool, device=self.device)
+            n_done_check = 16
+            for pos in range(total - 1):
+                cur = tokens[:, pos].contiguous()
+                lg = logits_all[pos] if return_logits else None
+                _cabi.check(lib.nsf_whisper_decoder_step(self._dh, _cabi.ptr(cur), pos, B, _cabi.ptr(st), need, _cabi.ptr(lg), _cabi.ptr(nxt),
+                                                         _cabi.stream_ptr()), "nsf_whisper_decoder_step")
+                argmaxes[:, pos + 1] = nxt
+                if pos + 1 >= n_prompt:
+                    if forced_tokens is not None:
+                        tokens[:, pos + 1] = forced_tokens[:, pos + 1 - n_prompt]
+                    else:
+                        tokens[:, pos + 1] = torch.where(done, torch.full_like(nxt, eot if eot is not None else 0), nxt)
+                        if eot is not None:
+                            done |= nxt == eot
+                            if (pos + 1) % n_done_check == 0 and bool(done.all()):
+                                tokens = tokens[:, :pos + 2]
+                                argmaxes = argmaxes[:, :pos + 2]
+                                break
+        if return_logits:
+            return tokens, argmaxes, logits_all
+        return tokens

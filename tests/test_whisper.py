@@ -113,3 +113,86 @@ def test_encoder_kernel_vs_oracle(d_model, layers, heads, ffn, n_mels, batch):
         err = rel_l2(out[b], ref)
         print(f"whisper encoder d={d_model} L={layers}: rel_l2 vs oracle = {err:.3e}")
         assert err < 2e-2                                        # bf16 operands (2^-9 per element), fp32 accumulate / residual
+
+
+def _hf_full(d_model, layers, heads, ffn, n_mels, vocab, seed=0, gain=2.0):
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+    cfg = WhisperConfig(d_model=d_model, encoder_layers=layers, decoder_layers=layers, encoder_attention_heads=heads,
+                        decoder_attention_heads=heads, encoder_ffn_dim=ffn, decoder_ffn_dim=ffn, num_mel_bins=n_mels, vocab_size=vocab,
+                        pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=3)
+    torch.manual_seed(seed)
+    m = WhisperForConditionalGeneration(cfg).eval()
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "embed_positions" in n:
+                continue
+            if p.dim() >= 2:
+                p.mul_(gain)
+            elif "bias" in n:
+                p.normal_(0, 0.1)
+            elif "layer_norm" in n and "weight" in n:
+                p.add_(0.1 * torch.randn_like(p))
+    return m
+
+
+def test_decoder_packing_accepts_both_namings():
+    from notsofar_b200.whisper import pack_whisper_decoder, _canon_decoder
+    m = _hf_full(128, 2, 2, 256, 80, 1000)
+    dims, blob, offs = pack_whisper_decoder(m.state_dict())
+    assert (dims.vocab, dims.n_text_ctx, dims.d_model, dims.n_heads, dims.n_layers, dims.d_ff, dims.n_audio_ctx) == (1000, 448, 128, 2, 2, 256, 1500)
+    oa = {"decoder." + k: v for k, v in _canon_decoder(m.state_dict()).items()}
+    _, blob2, offs2 = pack_whisper_decoder(oa)
+    assert np.array_equal(blob.view(np.uint32), blob2.view(np.uint32)) and np.array_equal(offs, offs2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d_model,layers,heads,ffn,vocab", [(128, 2, 2, 256, 1000), (384, 3, 6, 1536, 1003)])
+def test_decoder_logits_and_greedy_vs_transformers(d_model, layers, heads, ffn, vocab):
+    """Teacher-forced logits of every step against the transformers decoder (fp32, same weights, the encoder output the
+    device produced), then free-running greedy decoding: token ids must agree wherever the reference's top-2 margin is
+    not within the bf16 noise."""
+    from notsofar_b200.whisper import WhisperB200
+    dev = torch.device("cuda", 0)
+    m = _hf_full(d_model, layers, heads, ffn, 80, vocab)
+    wb = WhisperB200(m.state_dict(), device=dev)
+    rng = np.random.default_rng(vocab)
+    B, n_new = 2, 10
+    mel = (rng.standard_normal((B, 80, 3000)) * 0.5).astype(np.float32)
+    t = torch.zeros((B, 3002, 80), dtype=torch.float32, device=dev)
+    t[:, 1:3001] = torch.from_numpy(mel).to(dev).transpose(1, 2)
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    enc32, enc16 = wb.encode(hi.view(torch.int16).contiguous(), lo.view(torch.int16).contiguous())
+    prompt = [3, 5, 7]
+    forced = torch.from_numpy(rng.integers(4, vocab, size=(B, n_new)).astype(np.int32)).to(dev)
+    tokens, argmaxes, logits = wb.decode_greedy(enc16, prompt, max_new_tokens=n_new, forced_tokens=forced, return_logits=True)
+    torch.cuda.synchronize()
+    tok = tokens.cpu().long()
+    with torch.no_grad():
+        ref = m.proj_out(m.model.decoder(input_ids=tok[:, :-1], encoder_hidden_states=enc32.cpu()).last_hidden_state).numpy()   # [B, n, vocab]
+    got = logits[: tok.shape[1] - 1].permute(1, 0, 2).cpu().numpy()
+    assert np.isfinite(got).all()
+    err = rel_l2(got, ref)
+    print(f"whisper decoder d={d_model}: teacher-forced logits rel_l2 = {err:.3e}")
+    assert err < 2e-2
+    assert np.array_equal(argmaxes.cpu().numpy()[:, 1:], got.argmax(-1))                 # device arg-max == arg-max of its logits
+    # free-running greedy against a plain fp32 greedy loop on the transformers model
+    eot = 2
+    mine = wb.decode_greedy(enc16, prompt, max_new_tokens=n_new, eot=eot).cpu().numpy()
+    cur = torch.tensor([prompt] * B)
+    margins = []
+    with torch.no_grad():
+        for _ in range(n_new):
+            lg = m.proj_out(m.model.decoder(input_ids=cur, encoder_hidden_states=enc32.cpu()).last_hidden_state)[:, -1]
+            top2 = lg.topk(2, dim=-1).values
+            margins.append(((top2[:, 0] - top2[:, 1]) / lg.std(dim=-1)).numpy())
+            cur = torch.cat([cur, lg.argmax(-1, keepdim=True)], 1)
+    hf = cur.numpy()
+    margins = np.stack(margins, 1)                                                        # [B, n_new]
+    for b in range(B):
+        n = min(mine.shape[1], hf.shape[1])
+        diff = np.nonzero(mine[b, :n] != hf[b, :n])[0]
+        if len(diff):
+            first = diff[0] - len(prompt)
+            print(f"sequence {b}: first difference at new token {first}, reference margin {margins[b, first]:.3e} sigma")
+            assert margins[b, first] < 5e-2, "greedy ids differ where the reference's decision is not marginal"
