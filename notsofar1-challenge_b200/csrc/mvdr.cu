@@ -213,30 +213,31 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
     __syncwarp();
 
     // ---- D. apply: y_s[t] = sum_c conj(W_s[c]) x_c[t], then the floored-mask multiply (css.py:223-227).
-    // The slab is read a second time (L2-resident: it was fetched microseconds ago), one frame per lane.
-    double2 wc[S][C];
+    // The coefficients come out of the fp64 solve and are rounded to fp32 once; the 7-term sums run on the fp32 pipe
+    // (the reference applies in complex64 too, mvdr_util.py:78-80), which keeps the fp64 pipe -- the kernel's bottleneck --
+    // for the covariances and the solves.  The slab is read a second time (L2-resident), one frame per lane.
+    float2 wc[S][C];
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
-        for (int c = 0; c < C; ++c) wc[s][c] = Wc[s * 8 + c];
+        for (int c = 0; c < C; ++c) wc[s][c] = make_float2((float)Wc[s * 8 + c].x, (float)Wc[s * 8 + c].y);
     for (int t = lane; t < T; t += 32) {
-        double yr[S], yi[S];
+        float yr[S], yi[S];
 #pragma unroll
-        for (int s = 0; s < S; ++s) { yr[s] = 0.0; yi[s] = 0.0; }
+        for (int s = 0; s < S; ++s) { yr[s] = 0.f; yi[s] = 0.f; }
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const float2 x = (t * C + c < n_valid) ? __ldg(Xf + t * C + c) : make_float2(0.f, 0.f);
-            const double xr = x.x, xi = x.y;
 #pragma unroll
             for (int s = 0; s < S; ++s) {
-                yr[s] += wc[s][c].x * xr + wc[s][c].y * xi;
-                yi[s] += wc[s][c].x * xi - wc[s][c].y * xr;
+                yr[s] = fmaf(wc[s][c].x, x.x, fmaf(wc[s][c].y, x.y, yr[s]));
+                yi[s] = fmaf(wc[s][c].x, x.y, fmaf(-wc[s][c].y, x.x, yi[s]));
             }
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             const float mk = fmaxf(__ldg(mseg + s * mstride + t), mask_floor);      // torch.clip(mask, min=floor)
-            Y[(((size_t)seg * S + s) * n_bins + f) * T + t] = make_float2((float)yr[s] * mk, (float)yi[s] * mk);
+            Y[(((size_t)seg * S + s) * n_bins + f) * T + t] = make_float2(yr[s] * mk, yi[s] * mk);
         }
     }
 }
