@@ -7,8 +7,10 @@
 // Work item = (batch x head, block of 128 query rows).  Per 128-key tile j:
 //   MMA warp      S_j = Q K_j^T into one of two TMEM score buffers (so S_{j+1} is computed while the softmax of tile j
 //                 runs), then O_j = P_j V_j (P as the A operand from tensor memory) into a 64-column TMEM tile;
-//   softmax warps one thread per query row: running max / sum in the log2 domain, P_j written back to TMEM as packed
-//                 bf16x2, the output accumulator kept in registers: acc = (acc + O_{j-1}) * 2^(m_old - m_new);
+//   softmax warps two threads per query row (64 keys and 32 output columns each; the row maximum is exchanged through
+//                 shared memory once per tile, the row sums only at the end): running max / sum in the log2 domain, P_j
+//                 written back to TMEM as packed bf16x2, the output accumulator kept in registers:
+//                 acc = (acc + O_{j-1}) * 2^(m_old - m_new);
 //   TMA warp      Q once per item, K_j / V_j^T through two 3-slot rings.
 // q, k: [n_bh][T][64] bf16; v^T: [n_bh][64][Tp] bf16 with keys >= T zero; out: [batch * T][ldo] at column head * 64.
 #include "gemm_common.cuh"
@@ -17,7 +19,7 @@
 
 namespace nsf {
 
-constexpr int kFaThreads = 192;                 // warp 0 TMA, warp 1 MMA, warps 2..5 softmax
+constexpr int kFaThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 softmax (two per TMEM lane quarter)
 constexpr int kFaDk = 64;
 constexpr int kFaQBytes = 128 * 128;            // 128 rows x 64 bf16
 constexpr int kFaKBytes = 128 * 128;            // 128 keys x 64 bf16
@@ -27,7 +29,8 @@ constexpr int kFaTileBytes = kFaQBytes + kFaRing * (kFaKBytes + kFaVBytes);
 constexpr int kFaColS = 0;                      // two 128-column score buffers
 constexpr int kFaColP = 256;                    // 64 packed columns = 128 keys
 constexpr int kFaColO = 320;                    // 64 columns
-constexpr int kFaSmemBytes = kFaTileBytes + 256 + 1024;
+constexpr int kFaXchBytes = 2 * 128 * 4;        // row maxima (and, at the end, row sums) of the two key halves
+constexpr int kFaSmemBytes = kFaTileBytes + kFaXchBytes + 256 + 1024;
 
 struct FaParams {
     int n_bh, n_heads, T;
@@ -54,7 +57,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     const uint32_t q_smem = base;
     auto k_smem = [&](int s) { return base + kFaQBytes + s * kFaKBytes; };
     auto v_smem = [&](int s) { return base + kFaQBytes + kFaRing * kFaKBytes + s * kFaVBytes; };
-    const uint32_t bars = base + kFaTileBytes;
+    float* xch = reinterpret_cast<float*>(gen + kFaTileBytes);     // [2][128]
+    const uint32_t bars = base + kFaTileBytes + kFaXchBytes;
     const uint32_t q_full = bars, q_empty = bars + 8;
     auto k_full = [&](int s) { return bars + 16u + 8u * s; };
     auto k_empty = [&](int s) { return bars + 16u + 8u * (kFaRing + s); };
@@ -74,8 +78,8 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1); mbar_init(q_empty, 1);
         for (int s = 0; s < kFaRing; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 4); }
-        mbar_init(p_full, 4); mbar_init(o_full, 1); mbar_init(o_empty, 4);
+        for (int b = 0; b < 2; ++b) { mbar_init(s_full(b), 1); mbar_init(s_empty(b), 8); }
+        mbar_init(p_full, 8); mbar_init(o_full, 1); mbar_init(o_empty, 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -155,45 +159,47 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
             }
         }
     } else {
-        // ===== softmax / accumulate warps: one thread per query row
+        // ===== softmax / accumulate warps: two threads per query row (key half hh, output columns 32 hh ..)
         const int q = warp & 3;
+        const int hh = (warp - 2) >> 2;
         const int r = 32 * q + lane;
         const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
         const float c = 1.4426950408889634f;                       // scores are natural-log logits
         uint32_t st_cnt = 0, o_cnt = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
             const int bh = item / n_qb, qb = item - bh * n_qb;
-            float m = -INFINITY, l = 0.f;
-            float acc[kFaDk];
+            float m = -INFINITY, l = 0.f;                           // l: this thread's half of the row sum
+            float acc[32];
 #pragma unroll
-            for (int d = 0; d < kFaDk; ++d) acc[d] = 0.f;
+            for (int d = 0; d < 32; ++d) acc[d] = 0.f;
             for (int j = 0; j < n_kt; ++j, ++st_cnt) {
                 const uint32_t b = st_cnt & 1;
                 mbar_wait(s_full(b), (st_cnt >> 1) & 1);
                 tcgen05_fence_after();
-                uint32_t sv[128];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tmem_ld_32x32_nowait(tmem_base + lane_sel + kFaColS + 128 * b + 32 * k, sv + 32 * k);
+                uint32_t sv[64];
+                tmem_ld_32x32_nowait(tmem_base + lane_sel + kFaColS + 128 * b + 64 * hh, sv);
+                tmem_ld_32x32_nowait(tmem_base + lane_sel + kFaColS + 128 * b + 64 * hh + 32, sv + 32);
                 tmem_ld_wait();
-#pragma unroll
-                for (int k = 0; k < 4; ++k) tmem_ld_fence(sv + 32 * k);
+                tmem_ld_fence(sv); tmem_ld_fence(sv + 32);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(s_empty(b));             // the score buffer can be refilled
-                const int n_valid = min(128, T - j * 128);
+                const int n_valid = min(64, T - j * 128 - 64 * hh);
                 float mt = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 128; ++i) {
+                for (int i = 0; i < 64; ++i) {
                     const float v = i < n_valid ? __uint_as_float(sv[i]) * c : -INFINITY;
                     sv[i] = __float_as_uint(v);
                     mt = fmaxf(mt, v);
                 }
-                const float m_new = fmaxf(m, mt);
+                xch[hh * 128 + r] = mt;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                const float m_new = fmaxf(m, fmaxf(mt, xch[(hh ^ 1) * 128 + r]));
                 const float alpha = fa_ex2(m - m_new);              // 0 on the first tile (m = -inf)
                 float sum = 0.f;
-                uint32_t pk[64];
+                uint32_t pk[32];
 #pragma unroll
-                for (int i = 0; i < 64; ++i) {
+                for (int i = 0; i < 32; ++i) {
                     const float p0 = fa_ex2(__uint_as_float(sv[2 * i]) - m_new), p1 = fa_ex2(__uint_as_float(sv[2 * i + 1]) - m_new);
                     pk[i] = fa_pack_bf16(p0, p1);
                     // the row sum uses the rounded probabilities the tensor core will see
@@ -205,52 +211,48 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     // O_{j-1} = P_{j-1} V_{j-1} is relative to the previous maximum, like acc
                     mbar_wait(o_full, o_cnt & 1);
                     tcgen05_fence_after();
-                    uint32_t ov[64];
-                    tmem_ld_32x32_nowait(tmem_base + lane_sel + kFaColO, ov);
-                    tmem_ld_32x32_nowait(tmem_base + lane_sel + kFaColO + 32, ov + 32);
-                    tmem_ld_wait();
-                    tmem_ld_fence(ov); tmem_ld_fence(ov + 32);
+                    uint32_t ov[32];
+                    tmem_ld_32x32(tmem_base + lane_sel + kFaColO + 32 * hh, ov);
                     tcgen05_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(o_empty);
                     ++o_cnt;
 #pragma unroll
-                    for (int d = 0; d < kFaDk; ++d) acc[d] = (acc[d] + __uint_as_float(ov[d])) * alpha;
+                    for (int d = 0; d < 32; ++d) acc[d] = (acc[d] + __uint_as_float(ov[d])) * alpha;
                 }
-                // P_j -> TMEM (the previous P V product has completed: o_full above, or nothing was issued yet)
-                {
-                    uint32_t* pp = pk;
-                    tmem_st_32x32(tmem_base + lane_sel + kFaColP, *reinterpret_cast<uint32_t(*)[32]>(pp));
-                    tmem_st_32x32(tmem_base + lane_sel + kFaColP + 32, *reinterpret_cast<uint32_t(*)[32]>(pp + 32));
-                    tmem_st_wait();
-                }
+                // P_j -> TMEM (the previous P V product has completed: o_full above, or nothing was issued yet).  The
+                // exchange slot is reused next tile: the barrier above orders this tile's reads before those writes
+                // because every thread passes it again only after its partner has read.
+                tmem_st_32x32(tmem_base + lane_sel + kFaColP + 32 * hh, pk);
+                tmem_st_wait();
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");       // partner has read xch: safe to overwrite
             }
-            // last tile's product
+            // last tile's product and the other half of the row sum
             mbar_wait(o_full, o_cnt & 1);
             tcgen05_fence_after();
             {
-                uint32_t ov[64];
-                tmem_ld_32x32_nowait(tmem_base + lane_sel + kFaColO, ov);
-                tmem_ld_32x32_nowait(tmem_base + lane_sel + kFaColO + 32, ov + 32);
-                tmem_ld_wait();
-                tmem_ld_fence(ov); tmem_ld_fence(ov + 32);
+                uint32_t ov[32];
+                tmem_ld_32x32(tmem_base + lane_sel + kFaColO + 32 * hh, ov);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(o_empty);
                 ++o_cnt;
-                const float inv = 1.f / l;
+                xch[hh * 128 + r] = l;
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                const float inv = 1.f / (l + xch[(hh ^ 1) * 128 + r]);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
 #pragma unroll
-                for (int d = 0; d < kFaDk; ++d) acc[d] = (acc[d] + __uint_as_float(ov[d])) * inv;
+                for (int d = 0; d < 32; ++d) acc[d] = (acc[d] + __uint_as_float(ov[d])) * inv;
             }
             const int t1 = qb * 128 + r;
             if (t1 < T) {
                 const int bidx = bh / p.n_heads, h = bh - bidx * p.n_heads;
-                const size_t o = ((size_t)bidx * T + t1) * p.ldo + (size_t)h * kFaDk;
+                const size_t o = ((size_t)bidx * T + t1) * p.ldo + (size_t)h * kFaDk + 32 * hh;
 #pragma unroll
-                for (int k8 = 0; k8 < 8; ++k8) {
+                for (int k8 = 0; k8 < 4; ++k8) {
                     float v8[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) v8[e] = acc[8 * k8 + e];
