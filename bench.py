@@ -236,10 +236,12 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
         chunk = 128 * plan.hop_frames * 256
         feeder = HostFeeder(x_pinned, dev, chunk)
         out = css_device_sharded(feeder, sep, FS, cfg, n_total)
-        if rank == 0:
-            from notsofar_b200.css import _pinned_out
-            host = _pinned_out(tuple(out["wav"].shape))
-            host.copy_(out["wav"], non_blocking=True)
+        # the assembled streams stay on rank 0's GPU (the ASR / diarization hand-off); the host copy of the result is read
+        # by every rank for its own samples in parallel (each over its own PCIe link), seams included in the pieces
+        from notsofar_b200.css import _pinned_out
+        piece = out["wav_piece"]
+        host = _pinned_out(tuple(piece.shape))
+        host.copy_(piece, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
         return out
 
@@ -305,7 +307,8 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
                 "clocks": clocks,
                 "e2e": {"value": total_s / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(n_total * 7 * 4 + (world - 1) * (plan.segment_frames + 1) * 256 * 7 * 4),
-                        "d2h_bytes_per_step": int(3 * n_out * 4 + plan.num_segments * 36 * world)},
+                        "d2h_bytes_per_step": int(3 * (n_out + 256 * (world - 1)) * 4 + plan.num_segments * 36 * world),
+                        "d2h": "every rank reads its own samples (pieces overlap by one 256-sample seam); the NVLink gather to rank 0 is inside the step"},
                 "gpu_launches": int(t[2].item()),
                 "roofline": roofline, "kernels": kernels}
         print(json.dumps(line), flush=True)

@@ -278,7 +278,8 @@ def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total
     out = wk.phase3(activity_all)
     counts = [s.n_own_frames * FRAME_HOP + FRAME_HOP if s.n_own_frames else 0 for s in wk.shards]
     pieces = gather_varlen(out["wav_piece"], counts, dst, group, dim=1)
-    res = dict(activity_b=out["activity_b"], activity_final=out["activity_final"], perms=wk.perms, plan=wk.plan, shard=wk.sh)
+    res = dict(activity_b=out["activity_b"], activity_final=out["activity_final"], perms=wk.perms, plan=wk.plan, shard=wk.sh,
+               wav_piece=out["wav_piece"])        # this rank's own samples [S, n_own_frames*256 + 256], first sample own_lo*256
     mask_pieces = None
     if want_side_info:
         mask_pieces = gather_varlen(out["mask_piece"].contiguous(), [s.n_own_frames for s in wk.shards], dst, group, dim=1)
