@@ -148,7 +148,13 @@ def permutation_chain(costs: np.ndarray) -> np.ndarray:
             np.copyto(acc, c[cand[qi, 0], cand[pi, 0]])   # ((0 + c_0) + c_1) + c_2: the order of the scalar loop it replaces
             for a in range(1, S):
                 acc += c[cand[qi, a], cand[pi, a]]
-    best = np.ascontiguousarray(total.argmin(axis=1).T).astype(np.int64)     # [n_seg, P]; first minimum wins ('<' of the scalar loop)
+    bval = total[:, 0].copy()                              # [P (previous order), n_seg]
+    bidx = np.zeros((P, n_seg), np.int64)
+    for pi in range(1, P):                                 # strict '<': the first minimum wins, like the scalar loop
+        better = total[:, pi] < bval
+        bidx[better] = pi
+        np.minimum(bval, total[:, pi], out=bval)
+    best = np.ascontiguousarray(bidx.T)                    # [n_seg, P]
     best[0] = np.arange(P)                               # segment 0 keeps its order
     # state_i = best[i][state_{i-1}], state_{-1} = 0 (identity = cand[0]).  The maps compose associatively: blocked prefix
     # composition -- inside blocks of ~sqrt(n) segments vectorised across blocks, then one short carry walk over the
