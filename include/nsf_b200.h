@@ -255,6 +255,15 @@ int nsf_whisper_decoder_prefill_cross(nsf_whisper_decoder* h, const void* enc_bf
 int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* tokens, int pos, int n_batch, void* state, int64_t state_bytes,
                              float* logits_out, int32_t* next_tokens, void* stream);
 
+/* The same step with all loop state on the device, so that one captured CUDA graph can be replayed for every position:
+ * consumes cur_tokens [n_batch] at position *pos_dev, then (one bookkeeping kernel) records the arg-max in
+ * argmaxes[b][pos+1], chooses the token fed next -- forced[b][pos+1] if >= 0 (prompt / teacher forcing), eot once the
+ * sequence is done, else the arg-max -- into out_tokens[b][pos+1] and cur_tokens, marks sequences that produced eot in
+ * done, and increments *pos_dev.  forced / out_tokens / argmaxes: [n_batch][total_len] int32. */
+int nsf_whisper_decoder_step_dev(nsf_whisper_decoder* h, int32_t* cur_tokens, int32_t* pos_dev, int n_batch, void* state, int64_t state_bytes,
+                                 const int32_t* forced, int total_len, int eot, int32_t* out_tokens, int32_t* argmaxes, uint8_t* done,
+                                 void* stream);
+
 /* Test hook: non-causal multi-head attention with online softmax (flash_attn.cu, the Whisper encoder's attention) on fp32
  * inputs that are rounded to bf16 inside.  q, k, v [n_batch*n_heads][T][64] (already scaled), out [n_batch*T][n_heads*64] f32:
  *   out[b*T + t1][h*64 + d] = sum_t2 softmax_t2(q[t1].k[t2]) v[t2][d]. */

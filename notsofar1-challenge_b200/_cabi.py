@@ -68,6 +68,8 @@ SIGNATURES = {
     "nsf_whisper_decoder_destroy": (None, [C.c_void_p]),
     "nsf_whisper_decoder_state_bytes": (i64, [C.c_void_p, i32]),
     "nsf_whisper_decoder_prefill_cross": (i32, [C.c_void_p, C.c_void_p, i32, C.c_void_p, i64, C.c_void_p]),
+    "nsf_whisper_decoder_step_dev": (i32, [C.c_void_p, C.c_void_p, C.c_void_p, i32, C.c_void_p, i64, C.c_void_p, i32, i32, C.c_void_p,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsf_whisper_decoder_step": (i32, [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, i64, c_f32p, C.c_void_p, C.c_void_p]),
     "nsf_flash_attention_test_workspace_bytes": (i64, [i32, i32, i32]),
     "nsf_flash_attention_test": (i32, [c_f32p, c_f32p, c_f32p, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),

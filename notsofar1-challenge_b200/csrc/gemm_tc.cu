@@ -24,21 +24,21 @@
 
 namespace nsf {
 
-constexpr int TBM = 128, TBN = 256;
+constexpr int TBM = 128;                           // tile rows; tile columns TN = 256 (default) or 32 (small-M GEMMs, see gemm_tc_launch)
 constexpr int kRowBytes = 128;                     // one swizzle row of K: 32 tf32 or 64 16-bit elements
 constexpr int kATileBytes = TBM * kRowBytes;       // 16 KB
-constexpr int kBTileBytes = TBN * kRowBytes;       // 32 KB
 constexpr int kTcThreads = 320;                   // 1 TMA + 1 MMA + 8 epilogue warps
 constexpr uint32_t kTmemCols = 512;                // two 128 x 256 fp32 accumulators
 constexpr int kEpiPitch = 33;                      // staging row pitch (floats): conflict-free both ways
 constexpr int kEpiBytes = 8 * 32 * kEpiPitch * 4;  // one 32 x 32 staging tile per epilogue warp
 
 // MODE 1: one kind::tf32 pass; 3: 3xTF32; 16: three kind::f16 MMAs on 16-bit head/remainder pairs (2xBF16 / 2xF16)
-template <int MODE> struct TcCfg {
+template <int MODE, int TN> struct TcCfg {
     static constexpr bool kSplit = MODE == 3 || MODE == 16;
     static constexpr int kBlockK = MODE >= 16 ? 64 : 32;          // elements of K per stage (one 128-byte row)
+    static constexpr int kBTileBytes = TN * kRowBytes;            // 32 KB (TN = 256) or 4 KB (TN = 32)
     static constexpr int kStageBytes = (kSplit ? 2 : 1) * (kATileBytes + kBTileBytes);
-    static constexpr int kStages = kSplit ? 2 : 4;
+    static constexpr int kStages = TN == 32 ? 8 : (kSplit ? 2 : 4);
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
@@ -264,12 +264,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
     __syncwarp();
 }
 
-template <int MODE>
+template <int MODE, int TN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const GemmParams p, const int tiles_m, const int tiles_n, const int total_tiles) {
-    using Cfg = TcCfg<MODE>;
+    using Cfg = TcCfg<MODE, TN>;
+    constexpr int TBN = TN;
+    constexpr int kBTileBytes = Cfg::kBTileBytes;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -419,9 +421,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------- host side
-template <int MODE>
+template <int MODE, int TN>
 static int launch_t(const GemmParams& p, cudaStream_t stream) {
-    using Cfg = TcCfg<MODE>;
+    using Cfg = TcCfg<MODE, TN>;
+    constexpr int TBN = TN;
+    constexpr int kBTileBytes = Cfg::kBTileBytes;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
     auto make = [&](CUtensorMap* m, const float* base, int64_t rows, int64_t ld, int64_t bstride, int box_rows, int64_t batch) {
@@ -458,12 +462,12 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
         }
         pv.vec8 = ok ? 1 : 0;
     }
-    NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int tiles_m = ceil_div(p.M, TBM), tiles_n = ceil_div(p.N, TBN);
     const int64_t total = (int64_t)tiles_m * tiles_n * p.batch;
     if (total > 0x7fffffff) { set_error("gemm_tc: too many tiles"); return NSF_ERR_INVALID_ARG; }
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm_tc_kernel<MODE><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total);
+    gemm_tc_kernel<MODE, TN><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total);
     return check_launch("gemm_tc_kernel");
 }
 
@@ -472,16 +476,19 @@ int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream) {
     if (mode == 16) {
         if (p.op_fmt != SPLIT_BF16 && p.op_fmt != SPLIT_F16) { set_error("gemm_tc: 16-bit engine needs SPLIT_BF16 / SPLIT_F16 operands"); return NSF_ERR_INVALID_ARG; }
         if (p.K % 8 != 0) { set_error("gemm_tc: K=%d must be a multiple of 8", p.K); return NSF_ERR_INVALID_ARG; }
-        return launch_t<16>(p, stream);
+        return launch_t<16, 256>(p, stream);
     }
     if (mode == 116) {
         if (p.op_fmt != SPLIT_BF16_1) { set_error("gemm_tc: the bf16 engine needs SPLIT_BF16_1 operands"); return NSF_ERR_INVALID_ARG; }
         if (p.K % 8 != 0) { set_error("gemm_tc: K=%d must be a multiple of 8", p.K); return NSF_ERR_INVALID_ARG; }
-        return launch_t<116>(p, stream);
+        // small M (the Whisper decode step: M = sequences in flight): 128 x 32 tiles spread the weight stream over N / 32 CTAs
+        // instead of N / 256, with an 8-deep TMA ring per CTA
+        if (p.M <= 256 && p.batch == 1) return launch_t<116, 32>(p, stream);
+        return launch_t<116, 256>(p, stream);
     }
     if (p.op_fmt != SPLIT_TF32) { set_error("gemm_tc: tf32 engines need SPLIT_TF32 operands"); return NSF_ERR_INVALID_ARG; }
     if (p.K % 32 != 0) { set_error("gemm_tc: K=%d must be a multiple of 32", p.K); return NSF_ERR_INVALID_ARG; }
-    return mode == 3 ? launch_t<3>(p, stream) : launch_t<1>(p, stream);
+    return mode == 3 ? launch_t<3, 256>(p, stream) : launch_t<1, 256>(p, stream);
 }
 
 }  // namespace nsf

@@ -18,10 +18,13 @@ enum WdGlobal { WD_TOK_EMB = 0, WD_POS, WD_LN_G, WD_LN_B, WD_NUM };
 enum WdLayer { WDL_LN1_G = 0, WDL_LN1_B, WDL_WQKV, WDL_BQKV, WDL_WO, WDL_BO, WDL_LNC_G, WDL_LNC_B, WDL_WCQ, WDL_BCQ, WDL_WCKV, WDL_BCKV,
                WDL_WCO, WDL_BCO, WDL_LN2_G, WDL_LN2_B, WDL_W1, WDL_B1, WDL_W2, WDL_B2, WDL_NUM };
 
+__global__ void wd_set_int_kernel(int32_t* p, int v) { *p = v; }
+
 __global__ void __launch_bounds__(256)
-wd_embed_kernel(const int32_t* __restrict__ tokens, const uint16_t* __restrict__ emb, const float* __restrict__ pos_row, int d, int vocab,
-                float* __restrict__ x) {
+wd_embed_kernel(const int32_t* __restrict__ tokens, const uint16_t* __restrict__ emb, const float* __restrict__ pos_emb,
+                const int32_t* __restrict__ pos_ptr, int d, int vocab, float* __restrict__ x) {
     const int b = blockIdx.x;
+    const float* pos_row = pos_emb + (size_t)(*pos_ptr) * d;
     int tok = tokens[b];
     tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
     for (int c = threadIdx.x; c < d; c += blockDim.x)
@@ -34,11 +37,13 @@ wd_embed_kernel(const int32_t* __restrict__ tokens, const uint16_t* __restrict__
 template <bool APPEND>
 __global__ void __launch_bounds__(256)
 wd_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_new, const float* __restrict__ v_new, int64_t ldq,
-               uint16_t* __restrict__ Kc, uint16_t* __restrict__ Vc, int n_keys, int t_max, int n_heads, uint16_t* __restrict__ out, int d_model) {
-    extern __shared__ float sm[];                     // q[64] | p[n_keys] | red[32] | acc[4][64]
+               uint16_t* __restrict__ Kc, uint16_t* __restrict__ Vc, int n_keys_host, const int32_t* __restrict__ pos_ptr, int t_max,
+               int n_heads, uint16_t* __restrict__ out, int d_model) {
+    extern __shared__ float sm[];                     // q[64] | p[t_max rounded] | red[32] | acc[8][64]
+    const int n_keys = APPEND ? (*pos_ptr + 1) : n_keys_host;       // self-attention: keys 0 .. pos (the position lives on the device)
     float* qs = sm;
     float* p = sm + 64;
-    float* red = p + ((n_keys + 31) & ~31);
+    float* red = p + ((t_max + 31) & ~31);
     float* accs = red + 32;
     const int bh = blockIdx.x, b = bh / n_heads, h = bh - b * n_heads;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -52,15 +57,31 @@ wd_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_new, con
         }
     }
     __syncthreads();
-    const float q0 = qs[2 * lane], q1 = qs[2 * lane + 1];
+    // scores: 8 lanes per key (16 bytes = 8 dims each), 4 keys per warp instruction, 32 keys per CTA pass
+    const int sub = lane & 7, krow = lane >> 3;
+    float qv[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qv[e] = qs[8 * sub + e];
     float mx = -INFINITY;
-    for (int t = warp; t < n_keys; t += 8) {
-        const uint32_t kk = *reinterpret_cast<const uint32_t*>(K + (size_t)t * 64 + 2 * lane);
-        float s = q0 * __uint_as_float(kk << 16) + q1 * __uint_as_float(kk & 0xffff0000u);
-        s = warp_sum(s);
-        if (lane == 0) p[t] = s;
-        mx = fmaxf(mx, s);
+    for (int t0 = 0; t0 < n_keys; t0 += 32) {
+        const int t = t0 + 4 * warp + krow;
+        float s = 0.f;
+        if (t < n_keys) {
+            const uint4 kk = *reinterpret_cast<const uint4*>(K + (size_t)t * 64 + 8 * sub);
+            const uint32_t w4[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                s = fmaf(qv[2 * e], __uint_as_float(w4[e] << 16), fmaf(qv[2 * e + 1], __uint_as_float(w4[e] & 0xffff0000u), s));
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (t < n_keys) {
+            if (sub == 0) p[t] = s;
+            mx = fmaxf(mx, s);
+        }
     }
+    mx = warp_max(mx);
     if (lane == 0) red[warp] = mx;
     __syncthreads();
     mx = red[0];
@@ -79,15 +100,38 @@ wd_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_new, con
     sum = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) sum += red[w];
-    const int dcol = tid & 63, grp = tid >> 6;
-    float acc = 0.f;
-    for (int t = grp; t < n_keys; t += 4)
-        acc = fmaf(p[t], __bfloat162float(__ushort_as_bfloat16(V[(size_t)t * 64 + dcol])), acc);
-    accs[grp * 64 + dcol] = acc;
+    // weighted values: thread = (key slot tid / 8 of 32, 8 dims tid % 8), 16-byte loads, partial sums reduced through smem
+    const int vsub = tid & 7, vrow = tid >> 3;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int t = vrow; t < n_keys; t += 32) {
+        const uint4 vv = *reinterpret_cast<const uint4*>(V + (size_t)t * 64 + 8 * vsub);
+        const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+        const float pt = p[t];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            acc[2 * e] = fmaf(pt, __uint_as_float(w4[e] << 16), acc[2 * e]);
+            acc[2 * e + 1] = fmaf(pt, __uint_as_float(w4[e] & 0xffff0000u), acc[2 * e + 1]);
+        }
+    }
+    // reduce the 4 key slots that share a lane group inside each warp, then the 8 warps through shared memory
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    __syncthreads();                                   // p[] is no longer needed by anyone: accs may alias nothing, but order the phases
+    if (lane < 8) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) accs[warp * 64 + 8 * lane + e] = acc[e];
+    }
     __syncthreads();
     if (tid < 64) {
-        const float o = (accs[tid] + accs[64 + tid] + accs[128 + tid] + accs[192 + tid]) / sum;
-        out[(size_t)b * d_model + h * 64 + tid] = __bfloat16_as_ushort(__float2bfloat16_rn(o));
+        float o = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) o += accs[w * 64 + tid];
+        out[(size_t)b * d_model + h * 64 + tid] = __bfloat16_as_ushort(__float2bfloat16_rn(o / sum));
     }
 }
 
@@ -118,6 +162,33 @@ wd_argmax_kernel(const float* __restrict__ logits, int vocab, int32_t* __restric
     }
 }
 
+// Bookkeeping of one greedy step, one block: which token is fed next (the prompt / teacher-forced token if forced >= 0, the
+// end-of-text token once a sequence is done, else the arg-max), the record of fed tokens and arg-maxes, the position.
+__global__ void __launch_bounds__(1024)
+wd_advance_kernel(const int32_t* __restrict__ next, const int32_t* __restrict__ forced, int total_len, int eot, int32_t* __restrict__ cur,
+                  int32_t* __restrict__ out_tokens, int32_t* __restrict__ argmaxes, uint8_t* __restrict__ done, int32_t* __restrict__ pos_ptr,
+                  int n_batch) {
+    const int p = *pos_ptr;
+    __syncthreads();
+    for (int b = threadIdx.x; b < n_batch; b += blockDim.x) {
+        const int a = next[b];
+        int fed = a;
+        const int f = (forced && p + 1 < total_len) ? forced[(size_t)b * total_len + p + 1] : -1;
+        if (f >= 0) fed = f;
+        else {
+            if (done[b]) fed = eot;
+            else if (eot >= 0 && a == eot) done[b] = 1;
+        }
+        if (p + 1 < total_len) {
+            out_tokens[(size_t)b * total_len + p + 1] = fed;
+            argmaxes[(size_t)b * total_len + p + 1] = a;
+        }
+        cur[b] = fed;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *pos_ptr = p + 1;
+}
+
 }  // namespace nsf
 
 struct nsf_whisper_decoder {
@@ -137,6 +208,7 @@ struct WdState {
     float *x, *qkv, *qc, *logits;
     float *h, *u;                      // bf16 planes
     int32_t* next;
+    int32_t* pos;                      // device-side position of nsf_whisper_decoder_step (host-position entry point)
     int64_t total_bytes;
 };
 static WdState wd_carve(const nsf_whisper_dec_dims& D, int n_batch, unsigned char* base) {
@@ -155,6 +227,7 @@ static WdState wd_carve(const nsf_whisper_dec_dims& D, int n_batch, unsigned cha
     s.h = (float*)take((int64_t)n_batch * D.d_model * 2);
     s.u = (float*)take((int64_t)n_batch * D.d_ff * 2);
     s.next = (int32_t*)take((int64_t)n_batch * 4);
+    s.pos = (int32_t*)take(256);
     s.total_bytes = off;
     return s;
 }
@@ -231,21 +304,18 @@ extern "C" int nsf_whisper_decoder_prefill_cross(nsf_whisper_decoder* h, const v
     return NSF_OK;
 }
 
-extern "C" int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* tokens, int pos, int n_batch, void* state, int64_t state_bytes,
-                                        float* logits_out, int32_t* next_tokens, void* stream_) {
-    NSF_REQUIRE(h && tokens && state && next_tokens, "nsf_whisper_decoder_step: null pointer");
+static int wd_step_impl(nsf_whisper_decoder* h, const int32_t* tokens, const int32_t* pos_dev, int n_batch, void* state, int64_t state_bytes,
+                        float* logits_out, int32_t* next_tokens, cudaStream_t s) {
     const nsf_whisper_dec_dims& D = h->dims;
-    NSF_REQUIRE(pos >= 0 && pos < D.n_text_ctx, "nsf_whisper_decoder_step: pos=%d outside the text context %d", pos, D.n_text_ctx);
     NSF_REQUIRE(((uintptr_t)state & 255) == 0, "nsf_whisper_decoder_step: state must be 256-byte aligned");
     WdState st = wd_carve(D, n_batch, reinterpret_cast<unsigned char*>(state));
     NSF_REQUIRE(state_bytes >= st.total_bytes, "nsf_whisper_decoder_step: state too small");
-    cudaStream_t s = (cudaStream_t)stream_;
     const int d = D.d_model, H = D.n_heads, B = n_batch, dff = D.d_ff;
     const int64_t bh = (int64_t)B * H;
     int rc;
     uint16_t* hb = reinterpret_cast<uint16_t*>(st.h);
 
-    wd_embed_kernel<<<B, 256, 0, s>>>(tokens, reinterpret_cast<const uint16_t*>(h->g(WD_TOK_EMB)), h->g(WD_POS) + (size_t)pos * d, d, D.vocab, st.x);
+    wd_embed_kernel<<<B, 256, 0, s>>>(tokens, reinterpret_cast<const uint16_t*>(h->g(WD_TOK_EMB)), h->g(WD_POS), pos_dev, d, D.vocab, st.x);
     if ((rc = check_launch("wd_embed_kernel"))) return rc;
     auto linear = [&](const float* a, int K, const float* wt, const float* bias, int N, int epi, float* o0, int64_t ldo) {
         GemmParams p = wd_base(D, B);
@@ -254,18 +324,20 @@ extern "C" int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* t
         p.bias = bias; p.epi = epi; p.out0 = o0; p.out1 = o0; p.ldo = ldo;
         return gemm_launch(NSF_GEMM_TC_BF16, p, s);
     };
-    auto attn_smem = [](int n_keys) { return (size_t)(64 + ((n_keys + 31) & ~31) + 32 + 256) * sizeof(float); };
+    auto attn_smem = [](int t_max) { return (size_t)(64 + ((t_max + 31) & ~31) + 32 + 512) * sizeof(float); };
     for (int L = 0; L < D.n_layers; ++L) {
         if ((rc = ln_launch(st.x, B, d, h->l(L, WDL_LN1_G), h->l(L, WDL_LN1_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
         if ((rc = linear(st.h, d, h->l(L, WDL_WQKV), h->l(L, WDL_BQKV), 3 * d, EPI_STORE, st.qkv, 3 * d))) return rc;
-        wd_attn_kernel<true><<<(unsigned)bh, 256, attn_smem(pos + 1), s>>>(st.qkv, st.qkv + d, st.qkv + 2 * d, 3 * d,
-            st.sk + (size_t)L * bh * D.n_text_ctx * 64, st.sv + (size_t)L * bh * D.n_text_ctx * 64, pos + 1, D.n_text_ctx, H, hb, d);
+        { ProfScope prof(PROF_ATTN, 0.0, s);
+        wd_attn_kernel<true><<<(unsigned)bh, 256, attn_smem(D.n_text_ctx), s>>>(st.qkv, st.qkv + d, st.qkv + 2 * d, 3 * d,
+            st.sk + (size_t)L * bh * D.n_text_ctx * 64, st.sv + (size_t)L * bh * D.n_text_ctx * 64, 0, pos_dev, D.n_text_ctx, H, hb, d); }
         if ((rc = check_launch("wd_attn_kernel<self>"))) return rc;
         if ((rc = linear(st.h, d, h->l(L, WDL_WO), h->l(L, WDL_BO), d, EPI_RESID, st.x, d))) return rc;
         if ((rc = ln_launch(st.x, B, d, h->l(L, WDL_LNC_G), h->l(L, WDL_LNC_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
         if ((rc = linear(st.h, d, h->l(L, WDL_WCQ), h->l(L, WDL_BCQ), d, EPI_STORE, st.qc, d))) return rc;
+        { ProfScope prof(PROF_MVDR, 4.0 * bh * D.n_audio_ctx * 64 * 2.0 / 2.0, s);       // cross-attention cache reads (bytes), reported under "mvdr"
         wd_attn_kernel<false><<<(unsigned)bh, 256, attn_smem(D.n_audio_ctx), s>>>(st.qc, nullptr, nullptr, d,
-            st.ck + (size_t)L * bh * D.n_audio_ctx * 64, st.cv + (size_t)L * bh * D.n_audio_ctx * 64, D.n_audio_ctx, D.n_audio_ctx, H, hb, d);
+            st.ck + (size_t)L * bh * D.n_audio_ctx * 64, st.cv + (size_t)L * bh * D.n_audio_ctx * 64, D.n_audio_ctx, nullptr, D.n_audio_ctx, H, hb, d); }
         if ((rc = check_launch("wd_attn_kernel<cross>"))) return rc;
         if ((rc = linear(st.h, d, h->l(L, WDL_WCO), h->l(L, WDL_BCO), d, EPI_RESID, st.x, d))) return rc;
         if ((rc = ln_launch(st.x, B, d, h->l(L, WDL_LN2_G), h->l(L, WDL_LN2_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
@@ -277,4 +349,31 @@ extern "C" int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* t
     if ((rc = linear(st.h, d, h->g(WD_TOK_EMB), nullptr, D.vocab, EPI_STORE, lg, D.vocab))) return rc;
     wd_argmax_kernel<<<B, 1024, 0, s>>>(lg, D.vocab, next_tokens);
     return check_launch("wd_argmax_kernel");
+}
+
+extern "C" int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* tokens, int pos, int n_batch, void* state, int64_t state_bytes,
+                                        float* logits_out, int32_t* next_tokens, void* stream_) {
+    NSF_REQUIRE(h && tokens && state && next_tokens, "nsf_whisper_decoder_step: null pointer");
+    NSF_REQUIRE(pos >= 0 && pos < h->dims.n_text_ctx, "nsf_whisper_decoder_step: pos=%d outside the text context %d", pos, h->dims.n_text_ctx);
+    NSF_REQUIRE(((uintptr_t)state & 255) == 0, "nsf_whisper_decoder_step: state must be 256-byte aligned");
+    WdState st = wd_carve(h->dims, n_batch, reinterpret_cast<unsigned char*>(state));
+    NSF_REQUIRE(state_bytes >= st.total_bytes, "nsf_whisper_decoder_step: state too small");
+    cudaStream_t s = (cudaStream_t)stream_;
+    wd_set_int_kernel<<<1, 1, 0, s>>>(st.pos, pos);
+    int rc = check_launch("wd_set_int_kernel");
+    if (rc) return rc;
+    return wd_step_impl(h, tokens, st.pos, n_batch, state, state_bytes, logits_out, next_tokens, s);
+}
+
+extern "C" int nsf_whisper_decoder_step_dev(nsf_whisper_decoder* h, int32_t* cur_tokens, int32_t* pos_dev, int n_batch, void* state,
+                                            int64_t state_bytes, const int32_t* forced, int total_len, int eot, int32_t* out_tokens,
+                                            int32_t* argmaxes, uint8_t* done, void* stream_) {
+    NSF_REQUIRE(h && cur_tokens && pos_dev && state && out_tokens && argmaxes && done, "nsf_whisper_decoder_step_dev: null pointer");
+    NSF_REQUIRE(n_batch >= 1 && total_len >= 1 && total_len <= h->dims.n_text_ctx, "nsf_whisper_decoder_step_dev: bad sizes");
+    WdState st = wd_carve(h->dims, n_batch, reinterpret_cast<unsigned char*>(state));
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = wd_step_impl(h, cur_tokens, pos_dev, n_batch, state, state_bytes, nullptr, st.next, s);
+    if (rc) return rc;
+    wd_advance_kernel<<<1, 1024, 0, s>>>(st.next, forced, total_len, eot, cur_tokens, out_tokens, argmaxes, done, pos_dev, n_batch);
+    return check_launch("wd_advance_kernel");
 }

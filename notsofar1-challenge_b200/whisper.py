@@ -364,6 +364,8 @@ class WhisperB200:
                         "nsf_whisper_decoder_prefill_cross")
             n_prompt = len(prompt)
             total = min(D.n_text_ctx, n_prompt + max_new_tokens)
+            if not return_logits:
+                return self._decode_graph(B, need, prompt, total, eot, forced_tokens)
             tokens = torch.zeros((B, total), dtype=torch.int32, device=self.device)
             tokens[:, :n_prompt] = torch.tensor(prompt, dtype=torch.int32, device=self.device)
             nxt = torch.empty((B,), dtype=torch.int32, device=self.device)
@@ -391,3 +393,54 @@ class WhisperB200:
         if return_logits:
             return tokens, argmaxes, logits_all
         return tokens
+
+    def _decode_graph(self, B: int, need: int, prompt, total: int, eot: Optional[int], forced_tokens: Optional[torch.Tensor]):
+        """The decode loop as replays of ONE captured CUDA graph: position, current tokens, done flags and the token record
+        live on the device (nsf_whisper_decoder_step_dev), so every step launches the same ~450 kernels with the same
+        arguments."""
+        dev = self.device
+        n_prompt = len(prompt)
+        key = (B, total, self._state.data_ptr())
+        if getattr(self, "_graphs", None) is None:
+            self._graphs = {}
+        if key not in self._graphs:
+            bufs = dict(cur=torch.zeros((B,), dtype=torch.int32, device=dev), pos=torch.zeros((1,), dtype=torch.int32, device=dev),
+                        forced=torch.full((B, total), -1, dtype=torch.int32, device=dev),
+                        out=torch.zeros((B, total), dtype=torch.int32, device=dev), arg=torch.zeros((B, total), dtype=torch.int32, device=dev),
+                        done=torch.zeros((B,), dtype=torch.uint8, device=dev), eot=torch.zeros((), dtype=torch.int32))
+
+            def launch(eot_val):
+                _cabi.check(self._lib.nsf_whisper_decoder_step_dev(
+                    self._dh, _cabi.ptr(bufs["cur"]), _cabi.ptr(bufs["pos"]), B, _cabi.ptr(self._state), need, _cabi.ptr(bufs["forced"]), total,
+                    eot_val, _cabi.ptr(bufs["out"]), _cabi.ptr(bufs["arg"]), _cabi.ptr(bufs["done"]), _cabi.stream_ptr()),
+                    "nsf_whisper_decoder_step_dev")
+            self._graphs[key] = (bufs, {}, launch)
+        bufs, graphs, launch = self._graphs[key]
+        eot_val = -1 if eot is None else int(eot)
+        if eot_val not in graphs:
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                launch(eot_val)                      # warm-up outside the capture (lazy attribute / table initialisation)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch(eot_val)
+            graphs[eot_val] = g
+        g = graphs[eot_val]
+        bufs["forced"].fill_(-1)
+        bufs["forced"][:, :n_prompt] = torch.tensor(prompt, dtype=torch.int32, device=dev)
+        if forced_tokens is not None:
+            n = min(forced_tokens.shape[1], total - n_prompt)
+            bufs["forced"][:, n_prompt:n_prompt + n] = forced_tokens[:, :n]
+        bufs["out"].zero_(); bufs["arg"].zero_(); bufs["done"].zero_(); bufs["pos"].zero_()
+        bufs["out"][:, 0] = prompt[0]
+        bufs["cur"].fill_(prompt[0])
+        steps = total - 1
+        for i in range(steps):
+            g.replay()
+            if eot is not None and forced_tokens is None and (i + 1) % 16 == 0 and i + 1 >= n_prompt and bool(bufs["done"].all()):
+                steps = i + 1
+                break
+        return bufs["out"][:, :steps + 1].clone()

@@ -35,8 +35,17 @@ def main():
     hi, lo, _ = wb.encoder.log_mel(audio)
     _, enc16 = wb.encode(hi, lo)
     prompt = [50258, 50259, 50360, 50364]
-    wb.decode_greedy(enc16, prompt, max_new_tokens=4)
+    wb.decode_greedy(enc16, prompt, max_new_tokens=steps)          # warm-up: captures the step graph
     torch.cuda.synchronize()
+    # one un-captured, teacher-forced pass of a few steps with the library's event brackets: where a step goes
+    lib = _cabi.load()
+    lib.nsf_prof_enable(1); _cabi.prof_collect()
+    forced = torch.zeros((B, 8), dtype=torch.int32, device=dev)
+    wb.decode_greedy(enc16, prompt, max_new_tokens=8, forced_tokens=forced, return_logits=True)
+    torch.cuda.synchronize()
+    prof = _cabi.prof_collect(); lib.nsf_prof_enable(0)
+    n_prof = len(prompt) + 8 - 1
+    classes = {("cross_attn_cache" if k == "mvdr" else ("self_attn_cache" if k == "attention" else k)): round(v[0] / n_prof, 3) for k, v in prof.items() if v[2]}
     t0 = time.perf_counter()
     _, enc16 = wb.encode(hi, lo)
     torch.cuda.synchronize()
@@ -49,7 +58,8 @@ def main():
     print(json.dumps({"workload": f"Whisper-large-v3-shaped encoder + greedy decode, {B} x 30-s chunks, bf16", "encoder_ms": t_enc * 1e3,
                       "decode_ms_total": t_dec * 1e3, "decode_steps": n_steps, "ms_per_step": t_dec * 1e3 / n_steps,
                       "tokens_per_s": B * n_steps / t_dec,
-                      "audio_s_per_s_at_224_tokens": 30.0 * B / (t_enc + t_dec / n_steps * 228)}))
+                      "audio_s_per_s_at_224_tokens": 30.0 * B / (t_enc + t_dec / n_steps * 228),
+                      "ms_per_step_by_class (incl. prefill GEMMs / steps)": classes}))
 
 if __name__ == "__main__":
     main()
