@@ -148,8 +148,9 @@ extern "C" int nsf_css_features(const float* X, int64_t T_long, int64_t T_valid,
     NSF_REQUIRE((in_bias == nullptr) == (in_scale == nullptr), "nsf_css_features: bias/scale must come together");
     NSF_REQUIRE(split_fmt >= SPLIT_TF32 && split_fmt <= SPLIT_F16 && (split_fmt == SPLIT_TF32 || feat_lo),
                 "nsf_css_features: split_fmt=%d (16-bit formats need feat_lo)", split_fmt);
-    NSF_REQUIRE(T_valid <= T_long && (seg_first + n_seg - 1) * (int64_t)hop + T <= T_long + 0 || T_valid < T_long + 1,
-                "nsf_css_features: segment range outside X");
+    // frames >= T_valid are never read (they are the zero padding of the last segment), so segments may extend past X
+    NSF_REQUIRE(T_valid >= 0 && T_valid <= T_long && seg_first >= 0 && hop >= 1, "nsf_css_features: T_valid=%lld T_long=%lld seg_first=%lld hop=%d",
+                (long long)T_valid, (long long)T_long, (long long)seg_first, hop);
     if (n_seg <= 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid(ceil_div(kBins, kFeatBinsPerCta), n_seg);

@@ -343,8 +343,9 @@ extern "C" int nsf_gather_crops(const int16_t* pcm, int n_streams, int64_t n, co
     if (n_crops == 0 || max_len == 0) return NSF_OK;
     NSF_REQUIRE(n_crops <= 65535, "nsf_gather_crops: at most 65535 crops per call");
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 grid((unsigned)nsf::ceil_div64(max_len, 256 * 4) > 64 ? 64 : (unsigned)nsf::ceil_div64(max_len, 256 * 4), (unsigned)n_crops);
-    if (grid.x == 0) grid.x = 1;
+    int64_t gx = nsf::ceil_div64(max_len, 256 * 4);           // four samples per thread and pass, at most 64 CTAs per crop
+    gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
+    dim3 grid((unsigned)gx, (unsigned)n_crops);
     nsf::gather_crops_kernel<<<grid, 256, 0, s>>>(pcm, n, stream_id, start, len, max_len, out);
     return nsf::check_launch("gather_crops_kernel");
 }

@@ -14,6 +14,7 @@
 // row in front, the operand row of output frame t is the contiguous run of 3 input rows starting at row t (conv1) or
 // 2t (conv2); the TMA tensor map simply uses a row pitch smaller than the row length.
 #include "gemm_common.cuh"
+#include <mutex>
 #include <new>
 
 namespace nsf {
@@ -148,14 +149,21 @@ static WhWorkspace wh_carve(const nsf_whisper_dims& D, int n_batch, unsigned cha
     return w;
 }
 
+static std::mutex g_wh_tab_mutex;
+static bool g_wh_tab_ready[64] = {};
+
+// the DFT twiddles and the window live in __device__ globals: one initialisation per device of the process
 static int wh_ensure_tables(cudaStream_t s) {
-    static bool done = false;
-    if (!done) {
-        wh_init_tables_kernel<<<2, 256, 0, s>>>();
-        int rc = check_launch("wh_init_tables_kernel");
-        if (rc) return rc;
-        done = true;
-    }
+    int dev = 0;
+    NSF_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index %d out of range", dev); return NSF_ERR_INVALID_ARG; }
+    std::lock_guard<std::mutex> lock(g_wh_tab_mutex);
+    if (g_wh_tab_ready[dev]) return NSF_OK;
+    wh_init_tables_kernel<<<2, 256, 0, s>>>();
+    int rc = check_launch("wh_init_tables_kernel");
+    if (rc) return rc;
+    NSF_CUDA(cudaStreamSynchronize(s));
+    g_wh_tab_ready[dev] = true;
     return NSF_OK;
 }
 
