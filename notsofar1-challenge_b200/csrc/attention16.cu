@@ -24,7 +24,7 @@ constexpr int kA2Threads = 64 + 128 * kA2Split; // warp 0 TMA, warp 1 MMA, warps
 constexpr int kA2Dk = 64;
 constexpr int kA2QHalf = 128 * 128;             // one plane of Q: 128 rows x 128 B
 constexpr int kA2KHalf = 192 * 128;             // one plane of K: 192 rows
-constexpr int kA2VHalf = 3 * 64 * 128;          // one plane of V^T: 3 k-blocks of 64 frames, 64 rows (d) each
+constexpr int kA2VHalf = 192 * 128;             // one plane of V: 192 key rows x 64 d (MN-major B operand of P V: no transposed copy)
 constexpr int kA2PeHalf = 320 * 128;            // one plane of the pe_k window
 constexpr int kA2QOff = 0;
 constexpr int kA2KOff = kA2QOff + 2 * kA2QHalf;
@@ -94,7 +94,6 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     const int rows_valid = min(128, T - R0);
     const int nBh = (((rows_valid + T - 1) + 31) / 32) * 16;        // half of the pe_k window columns (multiple of 16)
     const int nPe = (2 * nBh + 63) / 64;                            // 64-row boxes of the window
-    const int n_kb_v = (p.Tp + 63) / 64;                            // 64-frame k-blocks of V^T
     const int nks_pv = (T + 15) / 16;                               // 16-key k-steps of P V
 
     if (threadIdx.x == 0) {
@@ -128,17 +127,15 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 tma_load_3d(k_smem, &map_k_hi, 0, 0, bh, qk_full);
                 tma_load_3d(k_smem + kA2KHalf, &map_k_lo, 0, 0, bh, qk_full);
                 mbar_wait(v_empty, (it & 1) ^ 1);
-                mbar_expect_tx(v_full, (uint32_t)n_kb_v * 2u * 8192u);
-                for (int kb = 0; kb < n_kb_v; ++kb) {
-                    tma_load_3d(v_smem + kb * 8192, &map_v_hi, 64 * kb, 0, bh, v_full);
-                    tma_load_3d(v_smem + kA2VHalf + kb * 8192, &map_v_lo, 64 * kb, 0, bh, v_full);
-                }
+                mbar_expect_tx(v_full, 2u * kA2VHalf);
+                tma_load_3d(v_smem, &map_v_hi, 0, 0, bh, v_full);
+                tma_load_3d(v_smem + kA2VHalf, &map_v_lo, 0, 0, bh, v_full);
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && first < p.n_bh) {
             // ===== MMA issuer
-            const uint32_t idesc_s = make_idesc_f16(192, 1), idesc_b = make_idesc_f16(nBh, 1), idesc_o = make_idesc_f16(64, 1);
+            const uint32_t idesc_s = make_idesc_f16(192, 1), idesc_b = make_idesc_f16(nBh, 1), idesc_o = make_idesc_f16_bmn(64, 1);
             mbar_wait(pe_full, 0);
             uint32_t it = 0;
             for (int bh = first; bh < p.n_bh; bh += stride, ++it) {
@@ -169,7 +166,7 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 mbar_wait(v_full, it & 1);
                 tcgen05_fence_after();
                 for (int j = 0; j < nks_pv; ++j) {
-                    const uint32_t vo = (uint32_t)(j >> 2) * 8192u + (uint32_t)(j & 3) * 32u;
+                    const uint32_t vo = (uint32_t)j * 2048u;                         // 16 key rows of 128 bytes
                     const uint64_t bv_hi = make_smem_desc(v_smem + vo), bv_lo = make_smem_desc(v_smem + kA2VHalf + vo);
                     const uint32_t a_col = tmem_base + 8u * j;                       // 16 keys = 8 packed columns
                     tcgen05_mma_f16_ts(tmem_base + kA2ColO, a_col + kA2ColPlo, bv_hi, idesc_o, j != 0);
@@ -304,7 +301,7 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     }
 }
 
-// q, k: [n_bh][T][64] bf16 pairs; vt: [n_bh][64][Tp] bf16 pairs (frames >= T zero); pe: [2 * maxlen][64] bf16 pairs;
+// q, k, v: [n_bh][T][64] bf16 pairs (v row-major like k: the P V product reads it as an MN-major operand); pe: [2 * maxlen][64] bf16 pairs;
 // out: [n_seg * T][ldo] split in out_fmt.  The float pointers are reinterpreted as uint16_t arrays (SplitFmt).
 int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
                   const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
@@ -323,8 +320,8 @@ int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const
     if ((rc = make_tmap_kmajor16(&mk_lo, k_lo, T, kA2Dk, kA2Dk, n_bh, 0, 192))) return rc;
     if ((rc = make_tmap_kmajor16(&mp_hi, pe_hi, 2 * (int64_t)maxlen, kA2Dk, kA2Dk, 1, 0, 64))) return rc;
     if ((rc = make_tmap_kmajor16(&mp_lo, pe_lo, 2 * (int64_t)maxlen, kA2Dk, kA2Dk, 1, 0, 64))) return rc;
-    if ((rc = make_tmap_kmajor16(&mv_hi, vt_hi, kA2Dk, Tp, Tp, n_bh, 0, 64))) return rc;
-    if ((rc = make_tmap_kmajor16(&mv_lo, vt_lo, kA2Dk, Tp, Tp, n_bh, 0, 64))) return rc;
+    if ((rc = make_tmap_kmajor16(&mv_hi, vt_hi, T, kA2Dk, kA2Dk, n_bh, 0, 192))) return rc;
+    if ((rc = make_tmap_kmajor16(&mv_lo, vt_lo, T, kA2Dk, kA2Dk, n_bh, 0, 192))) return rc;
     Attn16Params p;
     p.n_bh = n_bh; p.n_heads = n_heads; p.T = T; p.Tp = Tp; p.pe_row0 = maxlen - (T - 1);
     p.n_rb = (T + 127) / 128;
@@ -352,16 +349,6 @@ attn16_test_split_kernel(const float* __restrict__ in, int64_t n, float* __restr
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) split_store(SPLIT_BF16, hi, lo, (size_t)i, in[i]);
 }
-// v [n_bh][T][64] -> vt [n_bh][64][Tp] bf16 pairs (frames >= T zero)
-__global__ void __launch_bounds__(256)
-attn16_test_vt_kernel(const float* __restrict__ v, int n_bh, int T, int Tp, float* __restrict__ hi, float* __restrict__ lo) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_bh * kA2Dk * Tp) return;
-    const int t = (int)(i % Tp);
-    const int d = (int)((i / Tp) % kA2Dk);
-    const int64_t bh = i / ((int64_t)Tp * kA2Dk);
-    split_store(SPLIT_BF16, hi, lo, (size_t)i, t < T ? v[(bh * T + t) * kA2Dk + d] : 0.f);
-}
 __global__ void __launch_bounds__(256)
 attn16_test_merge_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int64_t n, float* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -388,7 +375,7 @@ extern "C" int nsf_attention16_test(const float* q, const float* k, const float*
     attn16_test_split_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, s>>>(q, nq, q_hi, q_lo);
     attn16_test_split_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, s>>>(k, nq, k_hi, k_lo);
     attn16_test_split_kernel<<<(unsigned)ceil_div64(np, 256), 256, 0, s>>>(pe, np, p_hi, p_lo);
-    attn16_test_vt_kernel<<<(unsigned)ceil_div64(nv, 256), 256, 0, s>>>(v, (int)n_bh, T, (int)Tp, v_hi, v_lo);
+    attn16_test_split_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, s>>>(v, nq, v_hi, v_lo);
     int rc = check_launch("attn16_test_split_kernel");
     if (rc) return rc;
     {

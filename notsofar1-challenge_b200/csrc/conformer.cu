@@ -567,7 +567,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         p.batch = 1;
         p.alpha = 1.f;
         p.acc_scale = 1.f;
-        p.op_fmt = SPLIT_TF32; p.out_fmt = fmt; p.qkv_fmt = qkv_fmt;
+        p.op_fmt = SPLIT_TF32; p.out_fmt = fmt; p.qkv_fmt = qkv_fmt; p.v_rowmajor = attn16 ? 1 : 0;
         p.T = T; p.Tp = Tp; p.n_heads = H; p.d_k = d_k; p.d_model = d;
         return p;
     };
@@ -585,7 +585,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
     };
 
     // the time padding of V^T (columns T..Tp-1) must be zero for the P V product
-    if (Tp != T) {
+    if (Tp != T && !attn16) {
         NSF_CUDA(cudaMemsetAsync(w.vt_hi, 0, sizeof(float) * (size_t)BH * d_k * Tp, s));
         NSF_CUDA(cudaMemsetAsync(w.vt_lo, 0, sizeof(float) * (size_t)BH * d_k * Tp, s));
     }

@@ -32,6 +32,7 @@ struct GemmParams {
     int op_fmt;               // SplitFmt of A and B (the 16-bit formats reinterpret the float pointers as uint16_t arrays)
     int out_fmt;              // SplitFmt of the split outputs of EPI_RELU_SPLIT / EPI_PV
     int qkv_fmt;              // SplitFmt of q, k, v^T written by EPI_QKV (SPLIT_TF32 for attention.cu, SPLIT_BF16 for attention16.cu)
+    int v_rowmajor;           // EPI_QKV: v is written like q and k ([seg][head][t][d_k], into vt_hi / vt_lo) instead of transposed
     int b_shared;             // batched A against one B (weights): every batch entry reads B[0]
     int vec8;                 // set by the tensor-core launcher: N, leading dimensions and bases allow 8-column vector epilogues
     float acc_scale;          // accumulator scale applied before the bias (undoes the SPLIT_F16 operand scales; 1 otherwise)
@@ -71,9 +72,9 @@ __device__ __forceinline__ void gemm_epilogue(const GemmParams& p, int b, int m,
             const int which = n / p.d_model, c = n - which * p.d_model;
             const int h = c / p.d_k, d = c - h * p.d_k;
             const int seg = m / p.T, t = m - seg * p.T;
-            if (which < 2) {
+            if (which < 2 || p.v_rowmajor) {
                 const size_t o = (((size_t)seg * p.n_heads + h) * p.T + t) * p.d_k + d;
-                split_store(p.qkv_fmt, which == 0 ? p.q_hi : p.k_hi, which == 0 ? p.q_lo : p.k_lo, o, v);
+                split_store(p.qkv_fmt, which == 0 ? p.q_hi : which == 1 ? p.k_hi : p.vt_hi, which == 0 ? p.q_lo : which == 1 ? p.k_lo : p.vt_lo, o, v);
             } else {
                 const size_t o = (((size_t)seg * p.n_heads + h) * p.d_k + d) * p.Tp + t;
                 split_store(p.qkv_fmt, p.vt_hi, p.vt_lo, o, v);

@@ -59,7 +59,7 @@ struct RowWalker {      // (segment, frame) of consecutive rows m = seg * T + t 
 
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
                                                float* stage, int lane) {
-    const bool lane_is_row = p.epi == EPI_MASK || (p.epi == EPI_QKV && nc >= 2 * p.d_model);
+    const bool lane_is_row = p.epi == EPI_MASK || (p.epi == EPI_QKV && nc >= 2 * p.d_model && !p.v_rowmajor);
     if (lane_is_row) {
         const int m = r0 + lane;
         if (m >= p.M) return;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                     }
                     case EPI_QKV: {     // q, k: [seg][head][t][d_k]
                         const int seg = m / p.T, t = m - seg * p.T;
-                        split_store8(p.qkv_fmt, which ? p.k_hi : p.q_hi, which ? p.k_lo : p.q_lo,
+                        split_store8(p.qkv_fmt, which == 0 ? p.q_hi : which == 1 ? p.k_hi : p.vt_hi, which == 0 ? p.q_lo : which == 1 ? p.k_lo : p.vt_lo,
                                      (((size_t)seg * p.n_heads + hq) * p.T + t) * p.d_k + dq, v);
                         break;
                     }
@@ -239,8 +239,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             case EPI_QKV: {     // q, k: [seg][head][t][d_k]
                 const int which = nc / p.d_model, c = n - which * p.d_model;
                 const int h = c / p.d_k, d = c - h * p.d_k;
-                float* o_hi = which ? p.k_hi : p.q_hi;
-                float* o_lo = which ? p.k_lo : p.q_lo;
+                float* o_hi = which == 0 ? p.q_hi : which == 1 ? p.k_hi : p.vt_hi;
+                float* o_lo = which == 0 ? p.q_lo : which == 1 ? p.k_lo : p.vt_lo;
                 RowWalker w(r0, p.T);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -457,7 +457,8 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
             case EPI_GELU_POS:
                 ok = ok && p.ldo % 4 == 0 && al16(p.out0) && al16(p.out1); break;
             case EPI_QKV:
-                ok = ok && p.d_k % 8 == 0 && p.d_model % 32 == 0 && al16(p.q_hi) && al16(p.q_lo) && al16(p.k_hi) && al16(p.k_lo); break;
+                ok = ok && p.d_k % 8 == 0 && p.d_model % 32 == 0 && al16(p.q_hi) && al16(p.q_lo) && al16(p.k_hi) && al16(p.k_lo) &&
+                     (!p.v_rowmajor || (al16(p.vt_hi) && al16(p.vt_lo))); break;
             default: ok = false; break;     // EPI_MASK writes along rows
         }
         pv.vec8 = ok ? 1 : 0;

@@ -111,6 +111,10 @@ __host__ __device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int n) {
 __host__ __device__ __forceinline__ constexpr uint32_t make_idesc_f16(int n, int bf16) {
     return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
+// the same with an MN-major B operand (rows of the shared-memory tile are K, the 128-byte row holds 64 N elements)
+__host__ __device__ __forceinline__ constexpr uint32_t make_idesc_f16_bmn(int n, int bf16) {
+    return make_idesc_f16(n, bf16) | (1u << 16);
+}
 // A operand read from tensor memory (lane = row, one tf32 element per 32-bit column)
 __device__ __forceinline__ void tcgen05_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
