@@ -12,7 +12,7 @@
 //                 written back to TMEM as packed bf16x2, the output accumulator kept in registers:
 //                 acc = (acc + O_{j-1}) * 2^(m_old - m_new);
 //   TMA warp      Q once per item, K_j / V_j^T through two 3-slot rings.
-// q, k: [n_bh][T][64] bf16; v^T: [n_bh][64][Tp] bf16 with keys >= T zero; out: [batch * T][ldo] at column head * 64.
+// q, k, v: [n_bh][T][64] bf16 (rows beyond T are zero-filled by TMA); out: [batch * T][ldo] at column head * 64.
 #include "gemm_common.cuh"
 #include "tc_ptx.cuh"
 #include <math.h>
@@ -23,7 +23,7 @@ constexpr int kFaThreads = 320;                 // warp 0 TMA, warp 1 MMA, warps
 constexpr int kFaDk = 64;
 constexpr int kFaQBytes = 128 * 128;            // 128 rows x 64 bf16
 constexpr int kFaKBytes = 128 * 128;            // 128 keys x 64 bf16
-constexpr int kFaVBytes = 2 * 64 * 128;         // V^T tile: 2 k-blocks of [64 (d)][64 keys]
+constexpr int kFaVBytes = 128 * 128;            // V tile: 128 keys x 64 d, read by the P V product as an MN-major operand
 constexpr int kFaRing = 3;
 constexpr int kFaTileBytes = kFaQBytes + kFaRing * (kFaKBytes + kFaVBytes);
 constexpr int kFaColS = 0;                      // two 128-column score buffers
@@ -108,15 +108,14 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     tma_load_3d(k_smem(s), &map_k, 0, j * 128, bh, k_full(s));
                     mbar_wait(v_empty(s), ph ^ 1);
                     mbar_expect_tx(v_full(s), kFaVBytes);
-                    tma_load_3d(v_smem(s), &map_v, j * 128, 0, bh, v_full(s));
-                    tma_load_3d(v_smem(s) + 8192, &map_v, j * 128 + 64, 0, bh, v_full(s));
+                    tma_load_3d(v_smem(s), &map_v, 0, j * 128, bh, v_full(s));
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer
-            const uint32_t idesc_s = make_idesc_f16(128, 1), idesc_o = make_idesc_f16(64, 1);
+            const uint32_t idesc_s = make_idesc_f16(128, 1), idesc_o = make_idesc_f16_bmn(64, 1);
             uint32_t it = 0, kt = 0, st_cnt = 0, pv_cnt = 0;      // kt: K tiles issued; st_cnt: S buffers used; pv_cnt: P V products issued
             auto issue_s = [&](uint32_t ktile) {
                 const int s = ktile % kFaRing;
@@ -141,7 +140,7 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
                     tcgen05_mma_f16_ts(tmem_base + kFaColO, tmem_base + kFaColP + 8 * i,
-                                       make_smem_desc(v_smem(s) + (i >> 2) * 8192 + (i & 3) * 32), idesc_o, i != 0);
+                                       make_smem_desc(v_smem(s) + i * 2048), idesc_o, i != 0);      // 16 key rows of 128 bytes
                 tcgen05_commit(v_empty(s));
                 tcgen05_commit(o_full);
                 ++pv_cnt;
@@ -269,17 +268,17 @@ flash_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     }
 }
 
-// q, k: [n_bh][T][64] bf16; vt: [n_bh][64][Tp] bf16 (keys >= T zero); out [batch * T][ldo] in out_fmt at column head * 64
-int flash_attn_launch(const void* q, const void* k, const void* vt, int n_batch, int n_heads, int T, int Tp,
+// q, k, v: [n_bh][T][64] bf16; out [batch * T][ldo] in out_fmt at column head * 64
+int flash_attn_launch(const void* q, const void* k, const void* vt, int n_batch, int n_heads, int T,
                       float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream) {
-    if (T < 1 || Tp < T || Tp % 8 != 0) { set_error("flash_attn: T=%d Tp=%d", T, Tp); return NSF_ERR_INVALID_ARG; }
+    if (T < 1) { set_error("flash_attn: T=%d", T); return NSF_ERR_INVALID_ARG; }
     if ((ldo & 7) || ((uintptr_t)out_hi & 15)) { set_error("flash_attn: ldo=%lld / output alignment", (long long)ldo); return NSF_ERR_INVALID_ARG; }
     const int n_bh = n_batch * n_heads;
     CUtensorMap mq, mk, mv;
     int rc;
     if ((rc = make_tmap_kmajor16(&mq, q, T, kFaDk, kFaDk, n_bh, 0, 128))) return rc;
     if ((rc = make_tmap_kmajor16(&mk, k, T, kFaDk, kFaDk, n_bh, 0, 128))) return rc;
-    if ((rc = make_tmap_kmajor16(&mv, vt, kFaDk, Tp, Tp, n_bh, 0, 64))) return rc;
+    if ((rc = make_tmap_kmajor16(&mv, vt, T, kFaDk, kFaDk, n_bh, 0, 128))) return rc;
     FaParams p;
     p.n_bh = n_bh; p.n_heads = n_heads; p.T = T;
     p.out_hi = out_hi; p.out_lo = out_lo; p.ldo = ldo; p.out_fmt = out_fmt;
@@ -296,23 +295,13 @@ fa_test_cvt_kernel(const float* __restrict__ in, int64_t n, uint16_t* __restrict
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = __bfloat16_as_ushort(__float2bfloat16_rn(in[i]));
 }
-__global__ void __launch_bounds__(256)
-fa_test_vt_kernel(const float* __restrict__ v, int n_bh, int T, int Tp, uint16_t* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_bh * kFaDk * Tp) return;
-    const int t = (int)(i % Tp);
-    const int d = (int)((i / Tp) % kFaDk);
-    const int64_t bh = i / ((int64_t)Tp * kFaDk);
-    out[i] = t < T ? __bfloat16_as_ushort(__float2bfloat16_rn(v[(bh * T + t) * kFaDk + d])) : (uint16_t)0;
-}
-
 }  // namespace nsf
 
 using namespace nsf;
 
 extern "C" int64_t nsf_flash_attention_test_workspace_bytes(int n_batch, int n_heads, int T) {
-    const int64_t n_bh = (int64_t)n_batch * n_heads, Tp = (T + 7) / 8 * 8;
-    return (2 * n_bh * T * kFaDk + n_bh * kFaDk * Tp) * 2 + 1024;
+    const int64_t n_bh = (int64_t)n_batch * n_heads;
+    return 3 * n_bh * T * kFaDk * 2 + 1024;
 }
 
 extern "C" int nsf_flash_attention_test(const float* q, const float* k, const float* v, int n_batch, int n_heads, int T, float* out,
@@ -322,16 +311,16 @@ extern "C" int nsf_flash_attention_test(const float* q, const float* k, const fl
     NSF_REQUIRE(workspace_bytes >= nsf_flash_attention_test_workspace_bytes(n_batch, n_heads, T) && ((uintptr_t)workspace & 255) == 0,
                 "nsf_flash_attention_test: workspace too small or not 256-byte aligned");
     cudaStream_t s = (cudaStream_t)stream_;
-    const int64_t n_bh = (int64_t)n_batch * n_heads, Tp = (T + 7) / 8 * 8;
-    const int64_t nq = n_bh * T * kFaDk, nv = n_bh * kFaDk * Tp;
+    const int64_t n_bh = (int64_t)n_batch * n_heads;
+    const int64_t nq = n_bh * T * kFaDk;
     uint16_t* qb = reinterpret_cast<uint16_t*>(workspace);
     uint16_t* kb = qb + nq;
     uint16_t* vb = kb + nq;
     fa_test_cvt_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, s>>>(q, nq, qb);
     fa_test_cvt_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, s>>>(k, nq, kb);
-    fa_test_vt_kernel<<<(unsigned)ceil_div64(nv, 256), 256, 0, s>>>(v, (int)n_bh, T, (int)Tp, vb);
+    fa_test_cvt_kernel<<<(unsigned)ceil_div64(nq, 256), 256, 0, s>>>(v, nq, vb);
     int rc = check_launch("fa_test_cvt_kernel");
     if (rc) return rc;
     ProfScope prof(PROF_ATTN, 4.0 * T * T * kFaDk * (double)n_bh, s);
-    return flash_attn_launch(qb, kb, vb, n_batch, n_heads, T, (int)Tp, out, nullptr, (int64_t)n_heads * kFaDk, SPLIT_FP32, s);
+    return flash_attn_launch(qb, kb, vb, n_batch, n_heads, T, out, nullptr, (int64_t)n_heads * kFaDk, SPLIT_FP32, s);
 }

@@ -121,8 +121,8 @@ int attn_fused_launch(const float* q_hi, const float* q_lo, const float* k_hi, c
 int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const float* k_lo, const float* vt_hi,
                   const float* vt_lo, const float* pe_hi, const float* pe_lo, int maxlen, int n_seg, int n_heads, int T, int Tp,
                   float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
-// non-causal attention with online softmax on plain bf16 operands (flash_attn.cu); q, k [n_bh][T][64], vt [n_bh][64][Tp]
-int flash_attn_launch(const void* q, const void* k, const void* vt, int n_batch, int n_heads, int T, int Tp,
+// non-causal attention with online softmax on plain bf16 operands (flash_attn.cu); q, k, v [n_bh][T][64]
+int flash_attn_launch(const void* q, const void* k, const void* vt, int n_batch, int n_heads, int T,
                       float* out_hi, float* out_lo, int64_t ldo, int out_fmt, cudaStream_t stream);
 // y1 = LN(x; g1, b1) [relu]; optional fp32 store to out_x; y2 = LN(y1; g2, b2) if g2; optional split store in fmt
 // (conformer.cu; one warp per row, d a multiple of 32, vector path for d = 128 * {1,2,3,4,5,6,8,10})

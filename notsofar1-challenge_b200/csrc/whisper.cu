@@ -238,14 +238,13 @@ extern "C" int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* m
     auto base = [&]() {
         GemmParams p = {};
         p.batch = 1; p.alpha = 1.f; p.acc_scale = 1.f;
-        p.op_fmt = SPLIT_BF16_1; p.out_fmt = SPLIT_BF16_1; p.qkv_fmt = SPLIT_BF16_1;
+        p.op_fmt = SPLIT_BF16_1; p.out_fmt = SPLIT_BF16_1; p.qkv_fmt = SPLIT_BF16_1; p.v_rowmajor = 1;
         p.T = T; p.Tp = Tp; p.n_heads = H; p.d_k = 64; p.d_model = d;
         p.q_hi = w.q; p.q_lo = w.q; p.k_hi = w.k; p.k_lo = w.k; p.vt_hi = w.vt; p.vt_lo = w.vt;
         return p;
     };
-    // zero row in front of every chunk of the conv1 output, zero key padding of V^T
+    // zero row in front of every chunk of the conv1 output
     NSF_CUDA(cudaMemsetAsync(w.x1p, 0, (size_t)n_batch * kWhPadRows * d * 2, s));
-    if (Tp != T) NSF_CUDA(cudaMemsetAsync(w.vt, 0, (size_t)n_batch * d * Tp * 2, s));
 
     {   // conv1 (k = 3, pad 1) + GELU: rows t .. t+2 of the zero-framed time-major mel, 2xBF16 engine (K = 3 n_mels is tiny)
         GemmParams p = base();
@@ -281,7 +280,7 @@ extern "C" int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* m
         if (rc) return rc;
         if ((rc = linear(w.h, d, h->l(L, WL_WQKV), h->l(L, WL_BQKV), 3 * d, EPI_QKV, nullptr, 0))) return rc;
         { ProfScope prof(PROF_ATTN, 4.0 * T * T * 64 * (double)n_batch * H, s);
-          if ((rc = flash_attn_launch(w.q, w.k, w.vt, n_batch, H, T, Tp, w.h, w.h, d, SPLIT_BF16_1, s))) return rc; }
+          if ((rc = flash_attn_launch(w.q, w.k, w.vt, n_batch, H, T, w.h, w.h, d, SPLIT_BF16_1, s))) return rc; }
         if ((rc = linear(w.h, d, h->l(L, WL_WO), h->l(L, WL_BO), d, EPI_RESID, w.x, d))) return rc;
         { ProfScope prof(PROF_NET_OTHER, 0.0, s);
           rc = ln_launch(w.x, M, d, h->l(L, WL_LN2_G), h->l(L, WL_LN2_B), 0, nullptr, nullptr, nullptr, w.h, w.h, SPLIT_BF16_1, s); }
