@@ -179,3 +179,51 @@ def test_sharded_equals_single_device(N, small_weights, world, seconds):
     print(f"sharded (world {world}) vs single device: waveform rel_l2 = {err:.2e}, max abs = {np.abs(a - b).max():.2e}")
     assert err < 1e-6
     assert one["activity_final"].any() and not one["activity_final"].all(), "test input must exercise the gate"
+
+
+# ----------------------------------------------------------------------------------------------- sessions over ranks
+def test_assign_sessions_balances_and_covers():
+    from notsofar_b200.scheduler import assign_sessions
+    rng = np.random.default_rng(0)
+    d = rng.uniform(300, 900, size=37).tolist()
+    for world in (1, 2, 8):
+        shares = assign_sessions(d, world)
+        flat = sorted(i for s in shares for i in s)
+        assert flat == list(range(37))
+        loads = [sum(d[i] for i in s) for s in shares]
+        assert max(loads) - min(loads) <= max(d)                      # LPT bound
+    assert assign_sessions([], 4) == [[], [], [], []]
+    assert assign_sessions([5.0, 5.0], 4) == [[0], [1], [], []]
+
+
+def _sched_worker(rank, world, port, ret):
+    import pandas as pd
+    import torch.distributed as dist
+    from notsofar_b200.scheduler import css_inference_distributed
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sessions = [pd.Series(dict(session_id=f"multichannel/MTG_{i}", wav_file_names=[f"/x/{i}.wav"])) for i in range(5)]
+        calls = []
+
+        def fake_css(out_dir, models_dir, session, cfg, fetch):
+            calls.append(session.session_id)
+            s = session.copy()
+            s["sep_wav_file_names"] = [f"{out_dir}/{session.session_id}/sep_stream{k}.wav" for k in range(3)]
+            return s
+        out = css_inference_distributed("/out", "/models", sessions, None, False, css_fn=fake_css, durations=[10, 50, 20, 40, 30])
+        assert [o.session_id for o in out] == [s.session_id for s in sessions]
+        assert all(len(o.sep_wav_file_names) == 3 for o in out)
+        ret[f"calls{rank}"] = calls
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sessions_distributed_under_gloo_world2():
+    import torch.multiprocessing as mp
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_sched_worker, args=(2, port, ret), nprocs=2, join=True)
+        c0, c1 = ret["calls0"], ret["calls1"]
+        assert sorted(c0 + c1) == [f"multichannel/MTG_{i}" for i in range(5)] and c0 and c1
