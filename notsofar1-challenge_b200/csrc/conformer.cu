@@ -15,8 +15,11 @@
 namespace nsf {
 
 constexpr int kPerLayer = 32;
-constexpr int kGlobalOffsets = 10;
-enum GlobalOff { G_EMB_W_HI = 0, G_EMB_W_LO, G_EMB_B, G_EMB_LN_G, G_EMB_LN_B, G_PE_HI, G_PE_LO, G_HEAD_W_HI, G_HEAD_W_LO, G_HEAD_B };
+constexpr int kGlobalOffsets = 12;
+// pe_k is packed twice: TF32 pairs for attention.cu / the unfused path, bf16 pairs for attention16.cu (which one is used
+// depends on the engine AND on the segment length, which the handle only learns at forward time)
+enum GlobalOff { G_EMB_W_HI = 0, G_EMB_W_LO, G_EMB_B, G_EMB_LN_G, G_EMB_LN_B, G_PE_HI, G_PE_LO, G_HEAD_W_HI, G_HEAD_W_LO, G_HEAD_B,
+                 G_PE16_HI, G_PE16_LO };
 enum LayerOff {
     L_FFI_LN_G = 0, L_FFI_LN_B, L_FFI_W1_HI, L_FFI_W1_LO, L_FFI_B1, L_FFI_W2_HI, L_FFI_W2_LO, L_FFI_B2,
     L_ATT_LN_G, L_ATT_LN_B, L_WQKV_HI, L_WQKV_LO, L_BQKV, L_WO_HI, L_WO_LO, L_BO,
@@ -617,7 +620,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
             // scores, relative-position skew, softmax and P V in one tcgen05 kernel (attention.cu)
             ProfScope prof(PROF_ATTN, 6.0 * T * T * d_k * (double)BH, s);
             if (attn16) {
-                if ((rc = attn16_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE_HI), h->g(G_PE_LO), D.maxlen,
+                if ((rc = attn16_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE16_HI), h->g(G_PE16_LO), D.maxlen,
                                         n_seg, H, T, Tp, w.h_hi, w.h_lo, d, fmt, s))) return rc;
             } else if ((rc = attn_fused_launch(w.q_hi, w.q_lo, w.k_hi, w.k_lo, w.vt_hi, w.vt_lo, h->g(G_PE_HI), h->g(G_PE_LO), D.maxlen,
                                         n_seg, H, T, Tp, w.h_hi, w.h_lo, d, fmt, s))) return rc;

@@ -91,9 +91,9 @@ def _strip_prefix(sd: Dict[str, object]) -> Dict[str, np.ndarray]:
 def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
     """Returns (dims: _cabi.ConformerDims, blob: np.float32[...], offsets: np.int64[...]).
 
-    Blob order (offsets index): 10 global entries
-      0 embed.W hi [d][Kf] | 1 embed.W lo | 2 embed.b | 3 embed LN g | 4 embed LN b | 5 pe_k hi [2*maxlen][d_k] | 6 pe_k lo
-      7 head.W hi [n_out][d] | 8 head.W lo | 9 head.b
+    Blob order (offsets index): 12 global entries
+      0 embed.W hi [d][Kf] | 1 embed.W lo | 2 embed.b | 3 embed LN g | 4 embed LN b | 5 pe_k hi [2*maxlen][d_k] | 6 pe_k lo (TF32 pairs)
+      7 head.W hi [n_out][d] | 8 head.W lo | 9 head.b | 10 pe_k hi | 11 pe_k lo (bf16 pairs)
     then 32 per encoder block
       0-7   feed_forward_in : LN g, LN b, W1 hi, W1 lo, b1, W2 hi, W2 lo, b2
       8-15  self_attn       : LN g, LN b, Wqkv hi [3d][d], Wqkv lo, bqkv, Wo hi, Wo lo, bo
@@ -146,15 +146,14 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
     add(w[c + "embed.0.bias"])
     add(w[c + "embed.1.weight"])
     add(w[c + "embed.1.bias"])
-    # pe_k feeds the attention kernel: bf16 pairs for the 2xBF16 engine (attention16.cu), TF32 pairs otherwise
+    # pe_k feeds the attention kernels: TF32 pairs here (attention.cu and the unfused path), bf16 pairs at the end
+    # (attention16.cu); which kernel runs depends on the engine and on the segment length
     pe = w[c + "pos_emb.pe_k.weight"]
-    if gemm_engine == _cabi.GEMM_TC_2XBF16 and d_k == 64:
-        hi, lo = _split16(pe, _cabi.SPLIT_BF16)
-        add(hi); add(lo)
-    else:
-        add_split(pe, tf32=True)
+    add_split(pe, tf32=True)
     add_split(w[_P + "linear.weight"])
     add(w[_P + "linear.bias"])
+    pe16_hi, pe16_lo = _split16(pe, _cabi.SPLIT_BF16)
+    add(pe16_hi); add(pe16_lo)
     for l in range(n_blocks):
         p = c + f"encoders.{l}."
         add_ffn(p + "feed_forward_in.")
@@ -180,7 +179,7 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
 
     dims = _cabi.ConformerDims(d_model=d_model, n_heads=n_heads, d_ff=d_ff, n_blocks=n_blocks, kernel_size=ks,
                                in_features=in_features, n_out=n_out, maxlen=two_maxlen // 2, T=T, gemm_engine=gemm_engine)
-    assert len(offsets) == 10 + 32 * n_blocks, len(offsets)
+    assert len(offsets) == 12 + 32 * n_blocks, len(offsets)
     return dims, np.concatenate(chunks), np.asarray(offsets, dtype=np.int64), \
         dict(input_bias=w[_P + "input_bias"].reshape(-1).astype(np.float32),
              input_scale=w[_P + "input_scale"].reshape(-1).astype(np.float32))

@@ -743,3 +743,26 @@ def test_css_inference_files_cache_and_passthrough(nb, dev, small_weights, tmp_p
     assert [str(f) for f in again.sep_wav_file_names] == sorted(out.sep_wav_file_names)
     thru = nb.css_inference(str(tmp_path / "out2"), str(tmp_path / "models"), session, nb.CssCfg(pass_through_ch0=True), False)
     assert thru.sep_wav_file_names == names[:1] and not (tmp_path / "out2").exists()
+
+
+def test_long_segments_take_the_unfused_attention_path(nb, dev, small_weights):
+    """4-s segments (249 frames > 192): the fused attention kernels do not apply, the network falls back to score / softmax /
+    P V GEMMs (3xTF32 inside the 2xBF16 engine); masks and the whole path still match the oracle."""
+    from notsofar_b200 import synth
+    x = synth.synthetic_meeting(9.0, seed=11)[None]
+    sep = _sep(nb, small_weights, dev)
+    kw = dict(segment_size_sec=4.0, hop_size_sec=2.0)
+    cfg = nb.CssCfg(activity_th=0.5, show_progressbar=False, **kw)
+    stages = {}
+    wavs, side = nb.separate_and_stitch(x, sep, 16000, dev, cfg, _stages=stages)
+    plan = stages["plan"]
+    assert plan.segment_frames == 249 and plan.num_segments >= 3
+    masks = stages["masks"].cpu().numpy()
+    feat, _ = sep.features(stages["X"], plan.raw_frames, 0, 1, plan.segment_frames, plan.hop_frames)
+    m_ref = O.conformer_masks(small_weights, feat.cpu().numpy()[:, :1799].reshape(1, plan.segment_frames, 1799))
+    assert rel_l2(masks[:1], m_ref) < TOL
+    wavs_o, so = O.separate_and_stitch(x, small_weights, 16000, O.OracleCfg(activity_th=0.5, **kw), masks_override=masks, mvdr_dtype=np.float64,
+                                       return_stages=True, stft_override=stages["X"].cpu().numpy()[:, :plan.raw_frames])
+    assert np.array_equal(stages["perms"], so["perms"])
+    for k in range(3):
+        assert rel_l2(wavs[k], wavs_o[k]) < TOL

@@ -147,6 +147,26 @@ def test_exchanges_under_gloo_world2(N):
 
 # ----------------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
+def test_sharded_no_beamformer_power_norm_equals_single_device(N):
+    """Single-channel model, no MVDR, normalize_segment_power: the per-segment power ratios use the global frame count."""
+    from notsofar_b200.css import css_device
+    from notsofar_b200.sharded import css_sharded_on_one_device
+    from notsofar_b200 import synth
+    dev = torch.device("cuda", 0)
+    w = O.random_weights(seed=2, d_model=128, n_heads=2, d_ff=256, n_blocks=2, in_features=257)
+    sep = N.ConformerCssB200(w, device=dev)
+    x = torch.from_numpy(np.ascontiguousarray(synth.synthetic_meeting(10.3, seed=4)[:, :1])).to(dev)
+    cfg = N.CssCfg(activity_th=0.5, show_progressbar=False, normalize_segment_power=True)
+    one = css_device(x, sep, 16000, cfg)
+    sh = css_sharded_on_one_device(x, sep, 16000, cfg, 3)
+    torch.cuda.synchronize()
+    assert np.array_equal(sh["perms"], one["perms"]) and torch.equal(sh["mask_stitched"], one["mask_stitched"])
+    for w_Y, s in zip(sh["Y"], sh["shards"]):
+        assert torch.equal(w_Y.view(torch.float32), one["Y"][s.seg_lo - s.halo:s.seg_hi].view(torch.float32))
+    assert rel_l2(sh["wav"].cpu().numpy(), one["wav"].cpu().numpy()) < 1e-6
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("world,seconds", [(2, 14.0), (3, 21.7), (5, 6.1)])
 def test_sharded_equals_single_device(N, small_weights, world, seconds):
     """All ranks of the sharded algorithm played on one GPU vs css_device: integers and everything up to the stitched
