@@ -766,3 +766,20 @@ def test_long_segments_take_the_unfused_attention_path(nb, dev, small_weights):
     assert np.array_equal(stages["perms"], so["perms"])
     for k in range(3):
         assert rel_l2(wavs[k], wavs_o[k]) < TOL
+
+
+@pytest.mark.parametrize("d_model,n_heads,engine_name", [(192, 3, "2xbf16"), (128, 4, "2xbf16"), (192, 3, "3xtf32"), (128, 4, "2xf16")])
+def test_masks_odd_network_shapes_vs_oracle(nb, dev, d_model, n_heads, engine_name):
+    """Shapes off the production fast paths: d_model not a multiple of 128 (scalar LayerNorm kernels, unfused conv module)
+    and d_k = 32 (no fused attention kernel: score / softmax / P V GEMMs)."""
+    w = O.random_weights(seed=7, d_model=d_model, n_heads=n_heads, d_ff=160, n_blocks=2)
+    sep = _sep(nb, w, dev, engine=ENGINES[engine_name])
+    rng = np.random.default_rng(d_model)
+    x = (rng.standard_normal((48128 + 93 * 256, 7)) * 0.05).astype(np.float32)
+    X = sep.stft_device(torch.from_numpy(x).to(dev))
+    m = sep.masks(X, X.shape[1], 0, 2, 186, 93).cpu().numpy()
+    raw, _ = sep.features(X, X.shape[1], 0, 2, 186, 93)
+    ref = O.conformer_masks(w, raw.cpu().numpy()[:, :1799].reshape(2, 186, 1799))
+    err = rel_l2(m, ref)
+    print(f"masks d_model={d_model} heads={n_heads} [{engine_name}]: rel_l2 vs oracle = {err:.3e}")
+    assert err < TOL
