@@ -511,6 +511,23 @@ def write_wav(fname, samps: np.ndarray, sr: int = 16000, max_norm: bool = True):
 
 
 _MODEL_CACHE: Dict[str, ConformerCssB200] = {}
+# CSS -> ASR / diarization hand-off without the disk round trip: the separated streams of the most recent sessions as the
+# PCM16 the WAV files hold (peak-normalised to 0.99, utils/audio_utils.py:44-45), still in HBM, keyed by session_id.
+DEVICE_STREAMS: Dict[str, "torch.Tensor"] = {}
+_DEVICE_STREAMS_KEEP = 2
+
+
+def streams_to_pcm16(wav: "torch.Tensor") -> "torch.Tensor":
+    """wav [S, N] float32 on the device -> int16 [S, N]: write_wav's 0.99 peak normalisation + libsndfile's PCM_16 rounding
+    (nsf_peaknorm_pcm16), i.e. exactly the samples read_wav would read back from the files css_inference writes."""
+    lib = _cabi.load()
+    assert wav.is_cuda and wav.dtype == torch.float32 and wav.dim() == 2 and wav.is_contiguous()
+    peak = torch.empty((wav.shape[0],), dtype=torch.float32, device=wav.device)
+    pcm = torch.empty(wav.shape, dtype=torch.int16, device=wav.device)
+    with torch.cuda.device(wav.device):
+        _cabi.check(lib.nsf_peaknorm_pcm16(_cabi.ptr(wav), wav.shape[0], wav.shape[1], _cabi.ptr(peak), _cabi.ptr(pcm), _cabi.stream_ptr()),
+                    "nsf_peaknorm_pcm16")
+    return pcm
 
 
 def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_from_cache: bool):
@@ -543,7 +560,13 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
     if cfg.slice_audio_for_debug:
         mixwav = mixwav[:, sr * 20:sr * 30, :]
 
-    separated_wavs, _ = separate_and_stitch(mixwav, separator, sr, device, cfg, return_side_info=False)
+    stages: dict = {}
+    separated_wavs, _ = separate_and_stitch(mixwav, separator, sr, device, cfg, return_side_info=False, _stages=stages)
+    # keep the streams of this session on the device for the stages downstream (diarization_inference(..., pcm=...))
+    DEVICE_STREAMS[session.session_id] = streams_to_pcm16(stages["wav"])
+    while len(DEVICE_STREAMS) > _DEVICE_STREAMS_KEEP:
+        DEVICE_STREAMS.pop(next(iter(DEVICE_STREAMS)))
+    del stages
 
     write_wav(css_out_dir / 'input_mixture.wav', samps=mixwav[0, :, 0], sr=sr)
 

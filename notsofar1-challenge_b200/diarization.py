@@ -236,6 +236,12 @@ def diarization_inference(out_dir: str, segments_df: pd.DataFrame, cfg: Diarizat
 
     if cfg.method == "word_nmesc":
         if pcm is None:
+            # streams the CSS stage of this process left in HBM (same sample values as the WAV files), else the files
+            from .css import DEVICE_STREAMS
+            cached = DEVICE_STREAMS.get(session_name)
+            if cached is not None and len(wav_files) == cached.shape[0] and all(f"sep_stream{k}.wav" in str(f) for k, f in enumerate(wav_files)):
+                pcm = cached
+        if pcm is None:
             pcm = _load_streams_as_pcm(wav_files, device)
         out = word_based_clustering(pcm, sr, segments_df, cfg)
     else:

@@ -739,6 +739,10 @@ def test_css_inference_files_cache_and_passthrough(nb, dev, small_weights, tmp_p
         sr, pcm = wf.read(f)
         assert f.endswith(f"sep_stream{k}.wav") and sr == 16000 and pcm.dtype == np.int16
         assert np.abs(pcm).max() in (32438, 32439)                                    # 0.99 peak normalisation
+    # the hand-off copy left in HBM holds exactly the samples of the files
+    dev_pcm = css_mod.DEVICE_STREAMS["multichannel/MTG_1_dev"].cpu().numpy()
+    for k, f in enumerate(out.sep_wav_file_names):
+        assert np.array_equal(dev_pcm[k], wf.read(f)[1])
     again = nb.css_inference(str(tmp_path / "out"), str(tmp_path / "models"), session, cfg, fetch_from_cache=True)
     assert [str(f) for f in again.sep_wav_file_names] == sorted(out.sep_wav_file_names)
     thru = nb.css_inference(str(tmp_path / "out2"), str(tmp_path / "models"), session, nb.CssCfg(pass_through_ch0=True), False)
