@@ -72,7 +72,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             for (int j = 0; j < 32; ++j) {
                 if (nc + j < p.N) {
                     const float v = __uint_as_float(r[j]) * p.acc_scale + (p.bias ? __ldg(p.bias + nc + j) : 0.f);
-                    base[((size_t)k * kBins + f) * p.T] = 1.f / (1.f + expf(-v));       // torch.sigmoid, conformer.py:304
+                    base[((size_t)k * kBins + f) * p.T] = __fdividef(1.f, 1.f + __expf(-v));   // torch.sigmoid (conformer.py:304), MUFU exp / rcp (2 ulp)
                 }
                 if (++f == kBins) { f = 0; ++k; }
             }
