@@ -17,6 +17,7 @@ CPU tests of the exchange logic) carries the three exchanges; there is no CPU co
 """
 from __future__ import annotations
 
+import sys
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence
 
@@ -271,13 +272,32 @@ def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     wk = ShardWorker(separator, fs, cfg, n_samples_total, rank, world)
     S = cfg.num_spks
+    import os
+    import time
+    timing = os.environ.get("NSF_SHARD_TIMING") == "1"
+
+    def mark(label, _t=[None]):
+        if timing:
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            if _t[0] is not None and rank == dst:
+                print(f"[shard timing] {label}: {(now - _t[0]) * 1e3:.2f} ms", file=sys.stderr, flush=True)
+            _t[0] = now
+    mark("start")
     own_costs = wk.phase1(x_local)
+    mark("phase1 (segments)")
     costs_all = allgather_varlen(own_costs, [s.n_own_seg for s in wk.shards], group)
-    own_act = wk.phase2(costs_all.cpu().numpy())
+    costs_np = costs_all.cpu().numpy()
+    mark("all-gather costs + read-back")
+    own_act = wk.phase2(costs_np)
+    mark("phase2 (chain + mask WOLA)")
     activity_all = allgather_varlen(own_act, [s.n_own_frames for s in wk.shards], group)
+    mark("all-gather activity")
     out = wk.phase3(activity_all)
+    mark("phase3 (gate + STFT WOLA + iSTFT)")
     counts = [s.n_own_frames * FRAME_HOP + FRAME_HOP if s.n_own_frames else 0 for s in wk.shards]
     pieces = gather_varlen(out["wav_piece"], counts, dst, group, dim=1)
+    mark("gather waveforms")
     res = dict(activity_b=out["activity_b"], activity_final=out["activity_final"], perms=wk.perms, plan=wk.plan, shard=wk.sh,
                wav_piece=out["wav_piece"])        # this rank's own samples [S, n_own_frames*256 + 256], first sample own_lo*256
     mask_pieces = None
@@ -285,6 +305,7 @@ def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total
         mask_pieces = gather_varlen(out["mask_piece"].contiguous(), [s.n_own_frames for s in wk.shards], dst, group, dim=1)
     if rank == dst:
         res["wav"] = assemble_waveforms(pieces, wk.shards, wk.plan.mix_frames)
+        mark("assemble")
         if mask_pieces is not None:
             res["mask_stitched"] = torch.cat(mask_pieces, dim=1)
     return res
