@@ -43,6 +43,7 @@ struct MvdrWarpSmem {
     double2 xs[kMvdrChunk * kMvdrC];                     // chunk of the slab, converted to fp64 once per sample
     double wext[kMvdrChunk];                             // winner weight - 1e-10 per frame
     int wmsk[kMvdrChunk];                                // winner bit mask per frame
+    uint8_t wlist[kMvdrS + 1][kMvdrChunk];               // per mask: the chunk's frames it wins (bit 7: this list also adds the frame to the total)
     double2 Rm[(kMvdrS + 1) * kMvdrC * kMvdrC];          // covariance matrices
     double2 Wc[kMvdrS * 8];                              // beamformer coefficients
 };
@@ -80,6 +81,7 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
         ej = ei + l;
     }
     double ar[S + 1], ai[S + 1], tr = 0.0, ti = 0.0;
+    int wcnt[S + 1] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k <= S; ++k) { ar[k] = 0.0; ai[k] = 0.0; }
 
@@ -116,23 +118,37 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
             for (int k = 0; k <= S; ++k) bits |= (pm[k] == mx) ? (1 << k) : 0;               // np.where(mask == mask_max, mask, 1e-10)
             sm.wext[lane] = (double)mx - 1e-10;
             sm.wmsk[lane] = bits;
+            // frames sorted by winner: the accumulation below runs one branch-free loop per mask over the frames it wins
+            // (a predicated update of all four masks per frame would issue 8 fp64 instructions of which 2 do work)
+            if (t0 + lane >= T) bits = 0;
+            const int lowest = bits & -bits;
+#pragma unroll
+            for (int k = 0; k <= S; ++k) {
+                const unsigned m = __ballot_sync(0xffffffffu, (bits >> k) & 1);
+                if ((bits >> k) & 1) sm.wlist[k][__popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane | ((lowest == (1 << k)) ? 0x80 : 0));
+                wcnt[k] = __popc(m);
+            }
         }
         __syncwarp();
         if (t0 + kMvdrChunk < T) prefetch(t0 + kMvdrChunk);
         const int nt = min(kMvdrChunk, T - t0);
+        (void)nt;
         if (lane < 28) {
+#pragma unroll
+            for (int k = 0; k <= S; ++k) {
+                const int cnt = wcnt[k];                              // warp-uniform trip count
 #pragma unroll 4
-            for (int t = 0; t < nt; ++t) {
-                const double2 xi = sm.xs[t * C + ei], xj = sm.xs[t * C + ej];
-                const double pr = xi.x * xj.x + xi.y * xj.y;         // x_i conj(x_j)
-                const double pi = xi.y * xj.x - xi.x * xj.y;
-                tr += pr; ti += pi;
-                const int bits = sm.wmsk[t];                          // warp-uniform
-                const double we = sm.wext[t];
-                if (bits & 1) { ar[0] += we * pr; ai[0] += we * pi; }
-                if (bits & 2) { ar[1] += we * pr; ai[1] += we * pi; }
-                if (bits & 4) { ar[2] += we * pr; ai[2] += we * pi; }
-                if (bits & 8) { ar[3] += we * pr; ai[3] += we * pi; }
+                for (int n = 0; n < cnt; ++n) {
+                    const int e = sm.wlist[k][n];
+                    const int t = e & 31;
+                    const double2 xi = sm.xs[t * C + ei], xj = sm.xs[t * C + ej];
+                    const double pr = xi.x * xj.x + xi.y * xj.y;     // x_i conj(x_j)
+                    const double pi = xi.y * xj.x - xi.x * xj.y;
+                    const double we = sm.wext[t];
+                    ar[k] += we * pr; ai[k] += we * pi;
+                    const double first = (e & 0x80) ? 1.0 : 0.0;     // exact ties: the frame enters the total once
+                    tr += first * pr; ti += first * pi;
+                }
             }
         }
         __syncwarp();
