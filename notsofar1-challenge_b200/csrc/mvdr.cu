@@ -187,7 +187,7 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
         }
         bool done = !act;
         int mycol = -1;
-        const int gbase = lane & ~7;
+        double2 mypiv = make_double2(1.0, 0.0);
 #pragma unroll
         for (int k = 0; k < C; ++k) {
             // partial pivoting inside the 8-lane group
@@ -199,24 +199,23 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
                 const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
                 if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
             }
-            (void)gbase;
+            // Gauss-Jordan without normalising the pivot row: row_i -= (row_i[k] / piv) row_p for every other row (rows that
+            // were pivots before included), 6 fp64 operations per entry; the division by the pivots happens once at the end
             const double2 piv = shfl_d2(row[k], bidx);
-            const double2 pinv = zinv(piv);
             const bool is_p = (lane == bidx);
-            const double2 fk = row[k];
+            const double2 g = zmul(row[k], zinv(piv));
 #pragma unroll
             for (int c = k + 1; c < 2 * C; ++c) {
-                const double2 pr_ = zmul(shfl_d2(row[c], bidx), pinv);   // normalised pivot row entry
-                if (is_p) row[c] = pr_;
-                else { const double2 q = zmul(fk, pr_); row[c].x -= q.x; row[c].y -= q.y; }
+                const double2 prc = shfl_d2(row[c], bidx);
+                if (!is_p) { const double2 q = zmul(g, prc); row[c].x -= q.x; row[c].y -= q.y; }
             }
-            row[k] = is_p ? make_double2(1.0, 0.0) : make_double2(0.0, 0.0);
-            if (is_p) { done = true; mycol = k; }
+            if (is_p) { done = true; mycol = k; mypiv = row[k]; }
         }
-        // lane holding pivot column k has row k of G = N^-1 R in row[C..2C)
+        // the lane that was the pivot of column k holds row k of N^-1 R, still scaled by its pivot, in row[C..2C)
+        const double2 minv = zinv(mypiv);
         double2 gd = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int c = 0; c < C; ++c) if (act && mycol == c) gd = row[C + c];
+        for (int c = 0; c < C; ++c) if (act && mycol == c) gd = zmul(row[C + c], minv);
         double2 tr = gd;
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
@@ -224,7 +223,7 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
             tr.y += __shfl_xor_sync(0xffffffffu, tr.y, o);
         }
         if (f == 0) tr.x += 1e-15;                               // den[0] += 1e-15, mvdr_util.py:73
-        if (act) Wc[s * 8 + mycol] = zmul(row[C], zinv(tr));     // W[c] = G[c][0] / trace(G)
+        if (act) Wc[s * 8 + mycol] = zmul(zmul(row[C], minv), zinv(tr));     // W[c] = G[c][0] / trace(G)
     }
     __syncwarp();
 
