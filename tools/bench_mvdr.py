@@ -25,7 +25,8 @@ def main():
         if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0}
     T, hop, F, C, S = 186, 186, 257, 7, 3
     g = torch.Generator(device=dev).manual_seed(0)
-    for frames in (1000, 3000, 10000, 30000, 100000):
+    sizes = [int(a) for a in sys.argv[1:]] or [1000, 3000, 10000, 30000, 100000]      # python tools/bench_mvdr.py [frames ...]
+    for frames in sizes:
         n_seg = -(-frames // T)
         T_long = n_seg * T
         a = torch.randn(F, 1, C, 2, device=dev, generator=g)
