@@ -264,6 +264,34 @@ int nsf_whisper_decoder_step_dev(nsf_whisper_decoder* h, int32_t* cur_tokens, in
                                  const int32_t* forced, int total_len, int eot, int32_t* out_tokens, int32_t* argmaxes, uint8_t* done,
                                  void* stream);
 
+/* ---- TitaNet speaker-embedding forward + multi-scale cosine affinity (row a16: diarization/word_based_diarization.py:26
+ * loads NeMo's EncDecSpeakerLabelModel "titanet_large", :105 calls spk_model.forward(input_signal, input_signal_length) under
+ * autocast, :171-177 build the per-scale affinity with NeMo's getCosAffinityMatrix and average it.  NeMo is third-party and
+ * unpinned; the published architecture is restated in oracle/titanet_oracle.py -- see csrc/titanet.cu).
+ * dims: Jasper blocks (filters / repeat / kernel / residual per block), attention channels, embedding size.
+ * blob layout: notsofar_b200/titanet.py::pack_titanet (BatchNorms folded; GEMM weights as bf16 head / remainder planes). */
+typedef struct nsf_titanet nsf_titanet;
+typedef struct { int feat_in, n_blocks, att_ch, emb; int filters[8], repeat[8], kernel[8], residual[8]; } nsf_titanet_dims;
+int64_t nsf_titanet_num_offsets(const nsf_titanet_dims* dims);
+int nsf_titanet_create(const nsf_titanet_dims* dims, const float* blob, int64_t blob_floats, const int64_t* offsets /*host*/,
+                       int n_offsets, nsf_titanet** out);
+void nsf_titanet_destroy(nsf_titanet* h);
+int64_t nsf_titanet_workspace_bytes(const nsf_titanet_dims* dims, int n_crops, int t_pad);
+/* crops [n_crops][max_len] f32 zero padded (the output of nsf_gather_crops), lengths [n_crops] -> normalised log-mel features
+ * as bf16 head / remainder planes [n_crops][t_pad][n_mels] (frames >= n_frames zero) and n_frames [n_crops] = len / 160 + 1.
+ * mel_filters [n_mels][257] f32, lm_scratch [n_crops][t_pad][n_mels] f32, t_pad >= max_len / 160 + 1. */
+int nsf_titanet_features(const float* crops, const int32_t* lengths, int n_crops, int64_t max_len, int t_pad,
+                         const float* mel_filters, int n_mels, float* lm_scratch, void* feat_hi, void* feat_lo, int32_t* n_frames,
+                         void* stream);
+/* features -> emb [n_crops][dims.emb] f32 (the second output of spk_model.forward) */
+int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const void* feat_lo, const int32_t* n_frames, int n_crops, int t_pad,
+                        float* emb, void* workspace, int64_t workspace_bytes, void* stream);
+/* acc [n][n] += scale * minmax(cos_similarity(emb)) for one scale: rows of emb (pitch row_pitch floats) normalised by
+ * (norm + 3.5e-4), unit diagonal, global min-max scaling (getCosAffinityMatrix [upstream]); scale = 1 / n_scales gives the mean
+ * of word_based_diarization.py:177.  en_scratch [n][dim], sim_scratch [n][n], minmax [2] u32. */
+int nsf_cos_affinity_accum(const float* emb, int64_t row_pitch, int dim, int n, float scale, float* en_scratch, float* sim_scratch,
+                           uint32_t* minmax, float* acc, void* stream);
+
 /* Test hook: non-causal multi-head attention with online softmax (flash_attn.cu, the Whisper encoder's attention) on fp32
  * inputs that are rounded to bf16 inside.  q, k, v [n_batch*n_heads][T][64] (already scaled), out [n_batch*T][n_heads*64] f32:
  *   out[b*T + t1][h*64 + d] = sum_t2 softmax_t2(q[t1].k[t2]) v[t2][d]. */

@@ -74,6 +74,13 @@ SIGNATURES = {
     "nsf_flash_attention_test_workspace_bytes": (i64, [i32, i32, i32]),
     "nsf_flash_attention_test": (i32, [c_f32p, c_f32p, c_f32p, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_attention16_test": (i32, [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
+    "nsf_titanet_num_offsets": (i64, [C.c_void_p]),
+    "nsf_titanet_create": (i32, [C.c_void_p, c_f32p, i64, C.POINTER(i64), i32, C.POINTER(C.c_void_p)]),
+    "nsf_titanet_destroy": (None, [C.c_void_p]),
+    "nsf_titanet_workspace_bytes": (i64, [C.c_void_p, i32, i32]),
+    "nsf_titanet_features": (i32, [c_f32p, C.c_void_p, i32, i64, i32, c_f32p, i32, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsf_titanet_forward": (i32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
+    "nsf_cos_affinity_accum": (i32, [c_f32p, i64, i32, i32, C.c_float, c_f32p, c_f32p, C.c_void_p, c_f32p, C.c_void_p]),
     "nsf_gemm_test": (i32, [i32, c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, C.c_void_p, i64, C.c_void_p]),
 }
 

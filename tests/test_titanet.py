@@ -1,0 +1,182 @@
+"""TitaNet speaker-embedding forward + multi-scale cosine affinity.
+
+NeMo is absent offline and the reference holds no vectors for this path: **parity unpinned**.  The CUDA path is compared,
+through the C ABI, with the numpy restatement of the published architecture (oracle/titanet_oracle.py); the CPU tests pin the
+restatement's own invariants (parameter count of titanet-large, front-end closed forms, masking == cropping)."""
+import numpy as np
+import pytest
+
+from oracle import titanet_oracle as O
+from conftest import rel_l2
+
+SMALL = ((64, 1, 3, False), (64, 2, 7, True), (128, 2, 5, True), (192, 1, 1, False))
+
+
+def _crops(rng, lens):
+    out = []
+    for n in lens:
+        t = np.arange(n) / 16000.0
+        f0 = rng.uniform(90, 250)
+        x = sum(np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 6.28)) / h for h in range(1, 12))
+        x = x * (0.5 + 0.5 * np.sin(2 * np.pi * 3.1 * t)) * 0.05 + 0.01 * rng.standard_normal(n)
+        out.append(x.astype(np.float32))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU: the restatement itself
+def test_titanet_large_parameter_count():
+    """encoder + pooling + embedding layer of titanet-large: 25.3 M published minus the 192 x 16681 classifier."""
+    w = O.random_weights(0)
+    n = sum(v.size for k, v in w.items() if "running" not in k)
+    assert 21.9e6 < n < 22.3e6, n
+    assert O.block_plan()[-1][:2] == (1024, 3072)
+
+
+def test_frontend_closed_forms():
+    rng = np.random.default_rng(0)
+    x = _crops(rng, [16000])[0]
+    f = O.features(x)
+    assert f.shape == (O.seq_len(16000), 80) == (101, 80)
+    np.testing.assert_allclose(f.mean(0), 0, atol=1e-9)
+    np.testing.assert_allclose(f.std(0, ddof=1), 1, atol=1e-4)          # unbiased std + 1e-5
+    fb = O.mel_filterbank()
+    assert fb.shape == (80, 257) and (fb >= 0).all() and (fb.sum(1) > 0).all()
+    # slaney normalisation: every triangle has unit area in Hz (up to the discretisation of the 31.25-Hz grid)
+    np.testing.assert_allclose(fb.sum(1) * 31.25, 1.0, atol=0.2)
+
+
+def test_pack_matches_plan():
+    import notsofar_b200.titanet as T
+    w = O.random_weights(3, blocks=SMALL, att_ch=32, emb=16)
+    assert T.infer_blocks(w) == SMALL
+    dims, blob, offsets = T.pack_titanet(w, SMALL)
+    lib = T._cabi.load()
+    import ctypes as C
+    assert lib.nsf_titanet_num_offsets(C.byref(dims)) == len(offsets)
+    assert blob.dtype == np.float32 and (offsets % 64 == 0).all()
+    assert lib.nsf_titanet_workspace_bytes(C.byref(dims), 4, 32) > 0
+
+
+def test_cos_affinity_oracle():
+    rng = np.random.default_rng(1)
+    e = rng.standard_normal((7, 16))
+    a = O.cos_affinity(e)
+    assert a.shape == (7, 7) and np.allclose(a, a.T) and a.max() == 1.0 and a.min() == 0.0
+    assert O.cos_affinity(e[:1]).tolist() == [[1.0]]
+
+
+# ------------------------------------------------------------------------------------------------ GPU parity
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    return torch.device("cuda", 0)
+
+
+def _run(model, crops, dev):
+    import torch
+    n, L = len(crops), max(len(c) for c in crops)
+    buf = np.zeros((n, L), np.float32)
+    for i, c in enumerate(crops):
+        buf[i, :len(c)] = c
+    lens = torch.tensor([len(c) for c in crops], dtype=torch.int32, device=dev)
+    return model, torch.from_numpy(buf).to(dev), lens
+
+
+@pytest.mark.gpu
+def test_titanet_features_vs_oracle(dev):
+    import torch
+    import notsofar_b200.titanet as T
+    w = O.random_weights(3, blocks=SMALL, att_ch=32, emb=16)
+    model = T.TitaNetB200(w, dev)
+    rng = np.random.default_rng(2)
+    crops = _crops(rng, [8000, 48000, 4321, 24000, 16001])
+    _, x, lens = _run(model, crops, dev)
+    hi, lo, nf, t_pad = model.features(x, lens)
+    assert t_pad % 16 == 0 and nf.cpu().tolist() == [O.seq_len(len(c)) for c in crops]          # integer frame counts: exact
+    feat = (hi.float() + lo.float()).cpu().numpy()
+    for i, c in enumerate(crops):
+        ref = O.features(c)
+        T_i = ref.shape[0]
+        assert rel_l2(feat[i, :T_i], ref) < 2e-4, (i, rel_l2(feat[i, :T_i], ref))
+        assert not feat[i, T_i:].any()                                                           # masked beyond the length
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("blocks,att,emb,lens,tol", [
+    (SMALL, 32, 16, [8000, 48000, 4321, 24000, 16001, 12000], 2e-4),
+    (O.BLOCKS, 128, 192, [8000, 24000, 40000], 5e-4),                     # titanet-large dims
+])
+def test_titanet_embedding_vs_oracle(dev, blocks, att, emb, lens, tol):
+    import notsofar_b200.titanet as T
+    w = O.random_weights(5, blocks=blocks, att_ch=att, emb=emb)
+    model = T.TitaNetB200(w, dev)
+    rng = np.random.default_rng(4)
+    crops = _crops(rng, lens)
+    _, x, l = _run(model, crops, dev)
+    e = model.embed(x, l).cpu().numpy()
+    ref = O.embed(w, crops, blocks)
+    assert e.shape == ref.shape == (len(lens), emb)
+    errs = [rel_l2(e[i], ref[i]) for i in range(len(lens))]
+    print("titanet embedding rel err vs fp64 oracle", errs)
+    assert max(errs) < tol, errs
+    # batching must not change a crop's embedding (padding is masked everywhere): the same crop alone
+    _, x1, l1 = _run(model, crops[:1], dev)
+    e1 = model.embed(x1, l1).cpu().numpy()
+    assert rel_l2(e1[0], e[0]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_multiscale_affinity_vs_oracle(dev):
+    import torch
+    import notsofar_b200.titanet as T
+    rng = np.random.default_rng(6)
+    emb = rng.standard_normal((37, 6, 192)).astype(np.float32)
+    a = T.multiscale_affinity(torch.from_numpy(emb).to(dev)).cpu().numpy()
+    ref = np.mean([O.cos_affinity(emb[:, s]) for s in range(6)], axis=0)
+    assert np.abs(a - ref).max() < 2e-6
+    assert T.multiscale_affinity(torch.from_numpy(emb[:1]).to(dev)).cpu().tolist() == [[1.0]]
+
+
+@pytest.mark.gpu
+def test_word_based_clustering_with_titanet_backend(dev):
+    """The a16 pipeline end to end on device-resident streams: crop plan -> gather -> TitaNet embeddings -> affinity ->
+    a clustering backend (NMESC itself is NeMo: plug-in point)."""
+    import pandas as pd
+    import torch
+    import notsofar_b200.diarization as D
+    import notsofar_b200.titanet as T
+    w = O.random_weights(3, blocks=SMALL, att_ch=32, emb=16)
+    model = T.TitaNetB200(w, dev)
+    rng = np.random.default_rng(8)
+    sr, n = 16000, 16000 * 20
+    pcm = torch.from_numpy((rng.standard_normal((3, n)) * 3000).astype(np.int16)).to(dev)
+    words = [[f"w{i}", 1.0 + 0.9 * i, 1.0 + 0.9 * i + 0.2 + 0.1 * (i % 5)] for i in range(18)]
+    df = pd.DataFrame({"start_time": [1.0, 9.0], "end_time": [9.0, 19.0], "text": ["a", "b"], "word_timing": [words[:9], words[9:]],
+                       "meeting_id": ["m", "m"], "session_id": ["s", "s"], "wav_file_name": ["s0.wav", "s1.wav"],
+                       "wav_file_name_ind": [0, 1]})
+    df["wav_file_name"] = df["wav_file_name"].astype("category")          # as diarization_inference prepares it (diarization.py:94-97)
+    cfg = D.DiarizationCfg(method="word_nmesc", min_embedding_windows=[1.5, 1.0, 0.5])
+    seen = {}
+
+    def cluster(emb, cfg_):
+        seen["emb"] = emb
+        aff = T.multiscale_affinity(emb.float())
+        seen["aff"] = aff
+        return (aff[0] < aff[0].median()).int().cpu().numpy()
+
+    D.set_embedding_backend(model.as_embedding_backend())
+    D.set_clustering_backend(cluster)
+    try:
+        out = D.word_based_clustering(pcm, sr, df, cfg)
+    finally:
+        D.set_embedding_backend(None)
+        D.set_clustering_backend(None)
+    assert seen["emb"].shape == (18, 3, 16) and torch.isfinite(seen["emb"]).all()
+    assert seen["aff"].shape == (18, 18)
+    assert set(out["speaker_id"]) <= {"spk0", "spk1"} and len(out) >= 2
+    # embeddings equal the oracle's on the same crops (first word, all scales)
+    plan = D.word_crop_plan(df, n, sr, cfg.min_embedding_windows, cfg.max_allowed_word_duration)
+    x = pcm.cpu().numpy().astype(np.float32) / 32767.0
+    ref = O.embed(w, [x[plan.stream_id[i], plan.start[i]:plan.start[i] + plan.length[i]] for i in range(3)], SMALL)
+    got = seen["emb"][0].cpu().numpy()
+    assert rel_l2(got, ref) < 2e-4
