@@ -279,7 +279,7 @@ void nsf_titanet_destroy(nsf_titanet* h);
 int64_t nsf_titanet_workspace_bytes(const nsf_titanet_dims* dims, int n_crops, int t_pad);
 /* crops [n_crops][max_len] f32 zero padded (the output of nsf_gather_crops), lengths [n_crops] -> normalised log-mel features
  * as bf16 head / remainder planes [n_crops][t_pad][n_mels] (frames >= n_frames zero) and n_frames [n_crops] = len / 160 + 1.
- * mel_filters [n_mels][257] f32, lm_scratch [n_crops][t_pad][n_mels] f32, t_pad >= max_len / 160 + 1. */
+ * mel_filters [257][n_mels] f32 (bin major), lm_scratch [n_crops][t_pad][n_mels] f32, t_pad >= max_len / 160 + 1. */
 int nsf_titanet_features(const float* crops, const int32_t* lengths, int n_crops, int64_t max_len, int t_pad,
                          const float* mel_filters, int n_mels, float* lm_scratch, void* feat_hi, void* feat_lo, int32_t* n_frames,
                          void* stream);

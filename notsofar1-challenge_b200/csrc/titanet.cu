@@ -14,6 +14,7 @@
 // Activations are time-major [n * t_pad][C]: every 1x1 convolution is one GEMM over all crops of the batch; frames beyond a
 // crop's length are carried along as finite values and masked wherever the reference masks (conv inputs, pooling).
 #include "gemm_common.cuh"
+#include "fft512.cuh"
 
 namespace nsf {
 
@@ -21,52 +22,73 @@ constexpr int kTnNfft = 512, kTnWin = 400, kTnHop = 160, kTnBins = 257;
 constexpr int kTnMaxBlocks = 8;
 
 // ------------------------------------------------------------------------------------------- front end
-// One CTA per (crop, frame): pre-emphasised, reflect-padded, windowed frame in shared memory, direct DFT (one bin per thread,
-// only the 400 window samples are non-zero), power, mel filterbank, log.  lm [n][t_pad][n_mels] f32.
+// One CTA per (crop, 8 frames): four groups of 64 threads, each transforming two real frames packed as the real and
+// imaginary part of one 512-point complex FFT (fft512.cuh, shared-memory radix 8x8x8).  A frame is the pre-emphasised,
+// reflect-padded signal under the 400-sample symmetric hann window centred in the 512-point transform; its power spectrum
+// goes through the mel filterbank and the log.  lm [n][t_pad][n_mels] f32 (frames >= n_frames are not written).
+constexpr int kTnFramesPerCta = 8;
+struct TnLogmelSmem {
+    float2 tw[kTnNfft];
+    float scratch[4][kFftScratchFloats];
+    float pw[kTnFramesPerCta][kTnBins + 3];
+};
+
 __global__ void __launch_bounds__(256)
 tn_logmel_kernel(const float* __restrict__ crops, const int* __restrict__ lengths, int64_t max_len, int t_pad,
                  const float* __restrict__ filters, int n_mels, float* __restrict__ lm,
                  int* __restrict__ n_frames) {
-    __shared__ float xw[kTnWin];
-    __shared__ float2 tw[kTnNfft];
-    __shared__ float pw[kTnBins];
-    const int b = blockIdx.y, t = blockIdx.x;
+    __shared__ __align__(16) TnLogmelSmem sm;
+    const int b = blockIdx.y, t0 = blockIdx.x * kTnFramesPerCta;
     const int len = lengths[b];
     const int nf = len > 0 ? len / kTnHop + 1 : 0;                     // FilterbankFeatures.get_seq_len, centred frames
-    if (t == 0 && threadIdx.x == 0) n_frames[b] = nf;
-    if (t >= nf) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) n_frames[b] = nf;
+    if (t0 >= nf) return;
     const float* x = crops + (size_t)b * max_len;
     constexpr int off = (kTnNfft - kTnWin) / 2;
     for (int i = threadIdx.x; i < kTnNfft; i += blockDim.x) {
-        { float sn, cs; sincospif((float)i / 256.f, &sn, &cs); tw[i] = make_float2(cs, sn); }     // (cos, sin)(2 pi i / 512)
-        if (i < kTnWin) {
-            int j = t * kTnHop + i + off - kTnNfft / 2;                 // centred frame, reflect padding (torch.stft center=True)
-            if (j < 0) j = -j;
-            if (j >= len) j = 2 * (len - 1) - j;
-            j = max(0, min(j, len - 1));
-            const float v = j > 0 ? x[j] - 0.97f * x[j - 1] : x[0];    // pre-emphasis happens before the padding
-            const float w = 0.5f - 0.5f * cospif(2.f * (float)i / (float)(kTnWin - 1));   // hann_window(400, periodic=False)
-            xw[i] = v * w;
-        }
+        float sn, cs;
+        sincospif((float)i / 256.f, &sn, &cs);                          // (cos, sin)(2 pi i / 512)
+        sm.tw[i] = make_float2(cs, sn);
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < kTnBins; k += blockDim.x) {
-        float re = 0.f, im = 0.f;
-        int idx = (k * off) & (kTnNfft - 1);
-        for (int i = 0; i < kTnWin; ++i) {
-            const float2 w = tw[idx];
-            re = fmaf(xw[i], w.x, re);
-            im = fmaf(-xw[i], w.y, im);
-            idx = (idx + k) & (kTnNfft - 1);
-        }
-        pw[k] = re * re + im * im;
+    const int group = threadIdx.x >> 6, lane64 = threadIdx.x & 63;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory"); };
+    auto sample = [&](int t, int n) -> float {
+        if (n < off || n >= off + kTnWin) return 0.f;
+        int j = t * kTnHop + n - kTnNfft / 2;                           // centred frame, reflect padding (torch.stft center=True)
+        if (j < 0) j = -j;
+        if (j >= len) j = 2 * (len - 1) - j;
+        j = max(0, min(j, len - 1));
+        const float v = j > 0 ? x[j] - 0.97f * x[j - 1] : x[0];        // pre-emphasis happens before the padding
+        return v * (0.5f - 0.5f * cospif(2.f * (float)(n - off) / (float)(kTnWin - 1)));   // hann_window(400, periodic=False)
+    };
+    const int ta = t0 + 2 * group, tb = ta + 1;
+    float2 v[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) v[a] = make_float2(sample(ta, 64 * a + lane64), sample(tb, 64 * a + lane64));
+    float* scratch = sm.scratch[group];
+    fft512_group<-1>(v, lane64, scratch, sm.tw, group_sync);
+    float* zre = scratch;
+    float* zim = scratch + 8 * 72;
+    {
+        const int k0 = lane64 >> 3, k1 = lane64 & 7;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) { zre[k0 + 8 * k1 + 64 * k2] = v[k2].x; zim[k0 + 8 * k1 + 64 * k2] = v[k2].y; }
+    }
+    group_sync();
+    for (int k = lane64; k < kTnBins; k += 64) {      // A[k] = (Z[k] + conj(Z[-k])) / 2,  B[k] = (Z[k] - conj(Z[-k])) / (2i)
+        const int kn = (kTnNfft - k) & (kTnNfft - 1);
+        const float ar = zre[k] + zre[kn], ai = zim[k] - zim[kn], br = zim[k] + zim[kn], bi = zre[kn] - zre[k];
+        sm.pw[2 * group][k] = 0.25f * (ar * ar + ai * ai);
+        sm.pw[2 * group + 1][k] = 0.25f * (br * br + bi * bi);
     }
     __syncthreads();
-    for (int m = threadIdx.x; m < n_mels; m += blockDim.x) {
-        const float* f = filters + (size_t)m * kTnBins;
+    for (int e = threadIdx.x; e < n_mels * kTnFramesPerCta; e += blockDim.x) {
+        const int m = e % n_mels, fr = e / n_mels;
+        if (t0 + fr >= nf) continue;
         float acc = 0.f;
-        for (int k = 0; k < kTnBins; ++k) acc = fmaf(__ldg(f + k), pw[k], acc);
-        lm[((size_t)b * t_pad + t) * n_mels + m] = logf(acc + 5.9604644775390625e-08f);     // log(x + 2^-24)
+        for (int k = 0; k < kTnBins; ++k) acc = fmaf(__ldg(filters + (size_t)k * n_mels + m), sm.pw[fr][k], acc);   // filters [257][n_mels]: coalesced over m
+        lm[((size_t)b * t_pad + t0 + fr) * n_mels + m] = logf(acc + 5.9604644775390625e-08f);     // log(x + 2^-24)
     }
 }
 
@@ -99,35 +121,59 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, fl
     }
 }
 
-// depthwise convolution over time ('same' padding, cross-correlation), input masked beyond the crop's length (MaskedConv1d):
-// thread = (crop, frame, 8 channels); in / out: bf16 head + remainder planes [n * t_pad][C]; w [k][C] f32
-__global__ void __launch_bounds__(256)
+// depthwise convolution over time ('same' padding, cross-correlation), input masked beyond the crop's length (MaskedConv1d).
+// CTA = (crop, 64 frames, 64 channels), 128 threads: the 64 + k - 1 input rows are staged once in shared memory as fp32 (each
+// input element crosses L2 1.0 - 1.5 times instead of k times; two planes of 4-channel halves so that the 16-byte reads of a
+// quarter warp are contiguous), thread = (4 frames, 8 channels) so that a tap's weights are fetched once per four outputs.
+// With k = 15 the kernel issues 1.9 FMA per HBM byte: bound by instruction issue unless the overhead per FMA stays small.
+// in / out: bf16 head + remainder planes [n * t_pad][C]; w [k][C] f32.
+constexpr int kDwFrames = 64, kDwCh = 64, kDwMaxK = 31, kDwRowsMax = kDwFrames + kDwMaxK - 1;
+__global__ void __launch_bounds__(128)
 tn_dwconv_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo, const int* __restrict__ n_frames, int t_pad,
-                 int C, int k, const float* __restrict__ w, float* __restrict__ out_hi, float* __restrict__ out_lo, int64_t total) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= total) return;
-    const int c8 = C >> 3;
-    const int cg = (int)(e % c8);
-    const int64_t row = e / c8;
-    const int b = (int)(row / t_pad), t = (int)(row - (int64_t)b * t_pad);
+                 int C, int k, const float* __restrict__ w, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+    __shared__ __align__(16) float4 tile[2][kDwRowsMax][8];
+    const int b = blockIdx.z, t0 = blockIdx.y * kDwFrames, c0 = blockIdx.x * kDwCh;
     const int nf = n_frames[b];
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const int half = k >> 1;
-    for (int j = 0; j < k; ++j) {
-        const int tt = t + j - half;
-        if (tt < 0 || tt >= nf) continue;
-        const size_t o = ((size_t)b * t_pad + tt) * C + (size_t)cg * 8;
-        const uint4 h = *reinterpret_cast<const uint4*>(in_hi + o), l = *reinterpret_cast<const uint4*>(in_lo + o);
+    const int half = k >> 1, rows = kDwFrames + k - 1;
+    const int nvec = min(kDwCh, C - c0) >> 3;                         // 8-channel vectors in this CTA's channel slice
+    for (int e = threadIdx.x; e < rows * 8; e += blockDim.x) {
+        const int r = e >> 3, v8 = e & 7;
+        const int tt = t0 + r - half;
         float v[8];
-        bf16x8_to_f32(h, l, v);
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)j * C + cg * 8));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)j * C + cg * 8 + 4));
-        acc[0] = fmaf(w0.x, v[0], acc[0]); acc[1] = fmaf(w0.y, v[1], acc[1]); acc[2] = fmaf(w0.z, v[2], acc[2]); acc[3] = fmaf(w0.w, v[3], acc[3]);
-        acc[4] = fmaf(w1.x, v[4], acc[4]); acc[5] = fmaf(w1.y, v[5], acc[5]); acc[6] = fmaf(w1.z, v[6], acc[6]); acc[7] = fmaf(w1.w, v[7], acc[7]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+        if (v8 < nvec && tt >= 0 && tt < nf) {
+            const size_t o = ((size_t)b * t_pad + tt) * C + c0 + v8 * 8;
+            bf16x8_to_f32(*reinterpret_cast<const uint4*>(in_hi + o), *reinterpret_cast<const uint4*>(in_lo + o), v);
+        }
+        tile[0][r][v8] = make_float4(v[0], v[1], v[2], v[3]);
+        tile[1][r][v8] = make_float4(v[4], v[5], v[6], v[7]);
     }
-    split_store8(SPLIT_BF16, out_hi, out_lo, (size_t)row * C + (size_t)cg * 8, acc);
+    __syncthreads();
+    const int fg = threadIdx.x >> 3, v8 = threadIdx.x & 7;
+    if (v8 >= nvec) return;
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
+    for (int j = 0; j < k; ++j) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + (size_t)j * C + c0 + v8 * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + (size_t)j * C + c0 + v8 * 8 + 4));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 x0 = tile[0][fg + 16 * i + j][v8], x1 = tile[1][fg + 16 * i + j][v8];
+            acc[i][0] = fmaf(w0.x, x0.x, acc[i][0]); acc[i][1] = fmaf(w0.y, x0.y, acc[i][1]);
+            acc[i][2] = fmaf(w0.z, x0.z, acc[i][2]); acc[i][3] = fmaf(w0.w, x0.w, acc[i][3]);
+            acc[i][4] = fmaf(w1.x, x1.x, acc[i][4]); acc[i][5] = fmaf(w1.y, x1.y, acc[i][5]);
+            acc[i][6] = fmaf(w1.z, x1.z, acc[i][6]); acc[i][7] = fmaf(w1.w, x1.w, acc[i][7]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = t0 + fg + 16 * i;
+        if (t < t_pad) split_store8(SPLIT_BF16, out_hi, out_lo, ((size_t)b * t_pad + t) * C + c0 + v8 * 8, acc[i]);
+    }
 }
 
 // masked statistics over time per (crop, channel): mean (and optionally std = sqrt(max(mean((x - mean)^2), 1e-10))) of
@@ -181,6 +227,18 @@ tn_fc_kernel(const float* __restrict__ in, int K, const float* __restrict__ W, c
         s += bias ? bias[j] : 0.f;
         out[(size_t)b * N + j] = act == 1 ? fmaxf(s, 0.f) : act == 2 ? 1.f / (1.f + expf(-s)) : s;
     }
+}
+
+// the same for short rows (K <= 512: the squeeze-excite expansion), one thread per output on transposed weights Wt [K][N]
+__global__ void __launch_bounds__(256)
+tn_fc_t_kernel(const float* __restrict__ in, int K, const float* __restrict__ Wt, int N, int n, int act, float* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * N) return;
+    const int b = (int)(e / N), j = (int)(e - (int64_t)b * N);
+    const float* a = in + (size_t)b * K;
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s = fmaf(__ldg(Wt + (size_t)k * N + j), a[k], s);
+    out[e] = act == 1 ? fmaxf(s, 0.f) : act == 2 ? 1.f / (1.f + expf(-s)) : s;
 }
 
 // y = relu(pre * gate[crop][c] + res), zero beyond the crop's length; bf16 planes for the next block, optionally fp32 in place
@@ -348,7 +406,7 @@ struct TnPlan {                      // offset indices, in the order notsofar_b2
 bool tn_dims_ok(const nsf_titanet_dims& d) {
     if (d.n_blocks < 1 || d.n_blocks > kTnMaxBlocks || d.feat_in < 8 || d.feat_in % 8 || d.att_ch < 8 || d.att_ch % 8 || d.emb < 1) return false;
     for (int b = 0; b < d.n_blocks; ++b)
-        if (d.filters[b] < 64 || d.filters[b] % 64 || d.repeat[b] < 1 || d.repeat[b] > 8 || d.kernel[b] < 1 || !(d.kernel[b] & 1)) return false;
+        if (d.filters[b] < 64 || d.filters[b] % 64 || d.repeat[b] < 1 || d.repeat[b] > 8 || d.kernel[b] < 1 || d.kernel[b] > kDwMaxK || !(d.kernel[b] & 1)) return false;
     return true;
 }
 
@@ -402,7 +460,7 @@ extern "C" int64_t nsf_titanet_num_offsets(const nsf_titanet_dims* d) { return d
 extern "C" int nsf_titanet_create(const nsf_titanet_dims* dims, const float* blob, int64_t blob_floats, const int64_t* offsets,
                                   int n_offsets, nsf_titanet** out) {
     NSF_REQUIRE(dims && blob && offsets && out, "nsf_titanet_create: null pointer");
-    NSF_REQUIRE(tn_dims_ok(*dims), "nsf_titanet_create: unsupported dims (feat_in / att_ch multiples of 8, filters multiples of 64, odd kernels, <= 8 blocks)");
+    NSF_REQUIRE(tn_dims_ok(*dims), "nsf_titanet_create: unsupported dims (feat_in / att_ch multiples of 8, filters multiples of 64, odd kernels <= 31, <= 8 blocks)");
     NSF_REQUIRE(n_offsets == tn_plan(*dims).num, "nsf_titanet_create: expected %d offsets, got %d", tn_plan(*dims).num, n_offsets);
     for (int i = 0; i < n_offsets; ++i)
         NSF_REQUIRE(offsets[i] >= 0 && offsets[i] < blob_floats && offsets[i] % 4 == 0, "nsf_titanet_create: offset %d out of range / unaligned", i);
@@ -435,7 +493,7 @@ extern "C" int nsf_titanet_features(const float* crops, const int32_t* lengths, 
     NSF_REQUIRE(t_pad >= max_len / kTnHop + 1, "nsf_titanet_features: t_pad=%d cannot hold %lld frames", t_pad, (long long)(max_len / kTnHop + 1));
     cudaStream_t s = (cudaStream_t)stream_;
     ProfScope prof(PROF_FEATURES, (double)n_crops * max_len * 4.0, s);
-    tn_logmel_kernel<<<dim3(t_pad, n_crops), 256, 0, s>>>(crops, lengths, max_len, t_pad, mel_filters, n_mels, lm_scratch, n_frames);
+    tn_logmel_kernel<<<dim3((t_pad + kTnFramesPerCta - 1) / kTnFramesPerCta, n_crops), 256, 0, s>>>(crops, lengths, max_len, t_pad, mel_filters, n_mels, lm_scratch, n_frames);
     int rc = check_launch("tn_logmel_kernel");
     if (rc) return rc;
     tn_featnorm_kernel<<<n_crops, (n_mels + 31) / 32 * 32, 0, s>>>(lm_scratch, n_frames, t_pad, n_mels, reinterpret_cast<float*>(feat_hi),
@@ -489,9 +547,8 @@ extern "C" int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const vo
         int c = c_in;
         for (int r = 0; r < rep; ++r) {
             { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-              const int64_t total = M64 * (c / 8);
-              tn_dwconv_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(x_hi), reinterpret_cast<const uint16_t*>(x_lo),
-                                                                               n_frames, t_pad, c, k, g(P.dw[b][r]), w.d_hi, w.d_lo, total);
+              tn_dwconv_kernel<<<dim3((c + kDwCh - 1) / kDwCh, (t_pad + kDwFrames - 1) / kDwFrames, n_crops), 128, 0, s>>>(
+                  reinterpret_cast<const uint16_t*>(x_hi), reinterpret_cast<const uint16_t*>(x_lo), n_frames, t_pad, c, k, g(P.dw[b][r]), w.d_hi, w.d_lo);
               if ((rc = check_launch("tn_dwconv_kernel"))) return rc; }
             if (r < rep - 1) {       // pointwise conv + BatchNorm + ReLU -> planes (the block's scratch output buffer)
                 if ((rc = gemm(w.d_hi, w.d_lo, c, P.pw_hi[b][r], P.pw_lo[b][r], g(P.pw_b[b][r]), co, EPI_RELU_SPLIT, y_hi, y_lo, SPLIT_BF16))) return rc;
@@ -507,7 +564,9 @@ extern "C" int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const vo
           tn_masked_stats_kernel<<<dim3((co + 31) / 32, n_crops), 256, 0, s>>>(w.pre, n_frames, t_pad, co, w.pooled, nullptr, co);
           if ((rc = check_launch("tn_masked_stats_kernel"))) return rc;
           if ((rc = fc(w.pooled, co, g(P.fc0[b]), nullptr, co / 8, 1, w.hid))) return rc;
-          if ((rc = fc(w.hid, co / 8, g(P.fc2[b]), nullptr, co, 2, w.gate))) return rc;
+          { const int64_t outs = (int64_t)n_crops * co;               // fc.2, stored transposed [co / 8][co]
+            tn_fc_t_kernel<<<(unsigned)((outs + 255) / 256), 256, 0, s>>>(w.hid, co / 8, g(P.fc2[b]), co, n_crops, 2, w.gate);
+            if ((rc = check_launch("tn_fc_t_kernel"))) return rc; }
           const int64_t total = M64 * (co / 8);
           tn_se_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.pre, w.gate, D.residual[b] ? w.res : nullptr, n_frames, t_pad, co,
                                                                              y_hi, y_lo, last_block ? 1 : 0, total);

@@ -179,7 +179,7 @@ def set_clustering_backend(fn: Optional[Callable]):
     _CLUSTERING_BACKEND = fn
 
 
-def word_based_clustering(pcm, sr: int, segments_df: pd.DataFrame, cfg: DiarizationCfg, batch_words: int = 32):
+def word_based_clustering(pcm, sr: int, segments_df: pd.DataFrame, cfg: DiarizationCfg, batch_words: int = 256):
     """word_based_diarization.py:135-189 on device-resident streams: crops -> embeddings (backend) -> labels (backend)
     -> prepare_diarized_data_frame.  ``pcm`` int16 CUDA tensor [n_streams, n]."""
     from . import _cabi

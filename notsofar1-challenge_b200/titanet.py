@@ -91,7 +91,7 @@ def pack_titanet(w: Dict[str, object], blocks: Sequence[Tuple[int, int, int, boo
             i += 3 if r == rep - 1 else 5
             c = co
         add(_np(w[p + f"mconv.{i}.fc.0.weight"]))
-        add(_np(w[p + f"mconv.{i}.fc.2.weight"]))
+        add(_np(w[p + f"mconv.{i}.fc.2.weight"]).T)                                # transposed [co / 8][co]
         if res:
             a, c0 = _bn_fold(w, p + "res.0.1", BN_EPS_ENC)
             add_split(_np(w[p + "res.0.0.conv.weight"])[:, :, 0] * a[:, None])
@@ -132,7 +132,7 @@ class TitaNetB200:
         self.dims, blob, offsets = pack_titanet(state_dict, self.blocks)
         self._blob = torch.from_numpy(blob).to(self.device)
         self._offsets = offsets
-        self._filters = torch.from_numpy(mel_filterbank(self.dims.feat_in, SR, N_FFT)).to(self.device).contiguous()
+        self._filters = torch.from_numpy(np.ascontiguousarray(mel_filterbank(self.dims.feat_in, SR, N_FFT).T)).to(self.device)   # [257][n_mels]
         self._handle = C.c_void_p()
         _cabi.check(self._lib.nsf_titanet_create(C.byref(self.dims), _cabi.ptr(self._blob), self._blob.numel(),
                                                  offsets.ctypes.data_as(C.POINTER(C.c_int64)), len(offsets), C.byref(self._handle)),
@@ -179,10 +179,26 @@ class TitaNetB200:
                                                       _cabi.ptr(self._ws), self._ws.numel(), _cabi.stream_ptr()), "nsf_titanet_forward")
         return emb
 
-    def embed(self, crops: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
-        """-> [n, emb] float32 embeddings (spk_model.forward(input_signal=crops, input_signal_length=lengths)[1])."""
-        hi, lo, nf, t_pad = self.features(crops, lengths)
-        return self.forward_features(hi, lo, nf, t_pad)
+    def embed(self, crops: torch.Tensor, lengths: torch.Tensor, bucket: bool = True) -> torch.Tensor:
+        """-> [n, emb] float32 embeddings (spk_model.forward(input_signal=crops, input_signal_length=lengths)[1]).
+
+        Padding is masked everywhere, so a crop's embedding does not depend on what it is batched with: with ``bucket`` the
+        crops are grouped by padded frame count (the six window scales of a word batch give six groups) and every group runs
+        at its own length instead of the longest crop's."""
+        if not bucket or crops.shape[0] < 2:
+            hi, lo, nf, t_pad = self.features(crops, lengths)
+            return self.forward_features(hi, lo, nf, t_pad)
+        lens_h = lengths.detach().cpu().numpy().astype(np.int64)
+        t_pads = (lens_h // HOP + 1 + 15) // 16 * 16
+        out = torch.empty((crops.shape[0], self.emb_dim), dtype=torch.float32, device=crops.device)
+        for tp in np.unique(t_pads):
+            idx = np.nonzero(t_pads == tp)[0]
+            idx_t = torch.from_numpy(idx).to(crops.device)
+            L = max(int(lens_h[idx].max()), 1)
+            sub = crops.index_select(0, idx_t)[:, :L].contiguous()
+            hi, lo, nf, t_pad = self.features(sub, lengths.index_select(0, idx_t))
+            out.index_copy_(0, idx_t, self.forward_features(hi, lo, nf, t_pad))
+        return out
 
     def as_embedding_backend(self):
         return lambda crops, lens, cfg: self.embed(crops, lens)
