@@ -12,9 +12,12 @@ What the reference computes itself, and is mirrored here with the same names, ar
     stay in HBM and ``gather_word_crops`` cuts / pads the batches there (libnsf_b200.so: nsf_gather_crops)
   * diarization_inference                           diarization.py:15-109 (modes, cache file, category codes)
 
-What lives in third-party packages that are absent offline (NeMo's TitaNet ``EncDecSpeakerLabelModel``, NMESC /
-spectral clustering -- SURVEY 8c: unpinned) is reached through two plug-in points, ``set_embedding_backend`` and
-``set_clustering_backend``; without them ``word_nmesc`` raises.  There is no CPU fallback for the GPU pieces.
+What the reference takes from NeMo (third-party, unpinned, absent offline -- SURVEY 8c) is built from the published
+algorithms and checked against this repository's own restatements only (**parity unpinned**):
+  * TitaNet ``EncDecSpeakerLabelModel.forward``     titanet.py / csrc/titanet.cu (weights: NSF_TITANET_CKPT -> .nemo archive)
+  * getCosAffinityMatrix + mean over scales         titanet.multiscale_affinity (CUDA)
+  * NMESC + SpectralClustering (``run_clustering``)  clustering.py (torch; eigendecompositions are library calls)
+``set_embedding_backend`` / ``set_clustering_backend`` replace either stage.  There is no CPU fallback for the GPU pieces.
 """
 from __future__ import annotations
 
@@ -179,13 +182,36 @@ def set_clustering_backend(fn: Optional[Callable]):
     _CLUSTERING_BACKEND = fn
 
 
-def word_based_clustering(pcm, sr: int, segments_df: pd.DataFrame, cfg: DiarizationCfg, batch_words: int = 256):
-    """word_based_diarization.py:135-189 on device-resident streams: crops -> embeddings (backend) -> labels (backend)
-    -> prepare_diarized_data_frame.  ``pcm`` int16 CUDA tensor [n_streams, n]."""
+def _embedding_backend(cfg: DiarizationCfg, device):
+    """The registered backend, else TitaNetB200 on the checkpoint named by NSF_TITANET_CKPT (the reference downloads
+    ``cfg.embedding_model_name`` from NGC, word_based_diarization.py:21-29; there is no network here)."""
+    if _EMBEDDING_BACKEND is not None:
+        return _EMBEDDING_BACKEND
     from . import _cabi
-    if _EMBEDDING_BACKEND is None or _CLUSTERING_BACKEND is None:
-        raise _cabi.NsfError("word_nmesc needs a speaker-embedding and a clustering backend (the reference's live in NeMo, "
-                             "absent offline: SURVEY 8c); register them with set_embedding_backend / set_clustering_backend")
+    path = os.environ.get("NSF_TITANET_CKPT")
+    if not path:
+        raise _cabi.NsfError(f"word_nmesc needs the weights of '{cfg.embedding_model_name}': set NSF_TITANET_CKPT to its .nemo archive "
+                             "(or a torch state_dict file), or register a backend with set_embedding_backend")
+    global _TITANET
+    if _TITANET is None or _TITANET[0] != (path, str(device)):
+        from .titanet import load_titanet
+        _TITANET = ((path, str(device)), load_titanet(path, device))
+    return _TITANET[1].as_embedding_backend()
+
+
+_TITANET = None
+
+
+def word_based_clustering(pcm, sr: int, segments_df: pd.DataFrame, cfg: DiarizationCfg, batch_words: int = 256):
+    """word_based_diarization.py:135-189 on device-resident streams: crops -> TitaNet embeddings (csrc/titanet.cu) -> multi-scale
+    cosine affinity -> NMESC + spectral clustering (clustering.py) -> prepare_diarized_data_frame.  ``pcm`` int16 CUDA tensor
+    [n_streams, n].  Both stages can be replaced through set_embedding_backend / set_clustering_backend.  Embeddings do not
+    depend on the batch composition (padding is masked), so batches are larger than the reference's 32 words."""
+    embed_fn = _embedding_backend(cfg, getattr(pcm, "device", None))
+    if _CLUSTERING_BACKEND is not None:
+        cluster_fn = _CLUSTERING_BACKEND
+    else:
+        from .clustering import nmesc_backend as cluster_fn
     import torch
     n_scales = len(cfg.min_embedding_windows)
     plan = word_crop_plan(segments_df, pcm.shape[1], sr, cfg.min_embedding_windows, cfg.max_allowed_word_duration)
@@ -193,10 +219,10 @@ def word_based_clustering(pcm, sr: int, segments_df: pd.DataFrame, cfg: Diarizat
     step = batch_words * n_scales
     for first in range(0, len(plan.start), step):
         crops, lens = gather_word_crops(pcm, plan, first, min(step, len(plan.start) - first))
-        embs.append(_EMBEDDING_BACKEND(crops, lens, cfg))
+        embs.append(embed_fn(crops, lens, cfg))
     emb = torch.cat(embs, 0).view(len(plan.words), n_scales, -1)
     keep = ~plan.too_long
-    labels = _CLUSTERING_BACKEND(emb[torch.from_numpy(keep).to(emb.device)], cfg)
+    labels = cluster_fn(emb[torch.from_numpy(keep).to(emb.device)], cfg)
     kept_words = [w for w, k in zip(plan.words, keep) if k]
     all_words = [w + [f"spk{int(l)}"] for w, l in zip(kept_words, labels)]
     return prepare_diarized_data_frame(all_words, segments_df, cfg.apply_deduplication)

@@ -224,3 +224,25 @@ def multiscale_affinity(emb: torch.Tensor) -> torch.Tensor:
                                                    _cabi.ptr(sim), _cabi.ptr(mm), _cabi.ptr(acc), _cabi.stream_ptr()),
                         "nsf_cos_affinity_accum")
     return acc
+
+
+def load_titanet_state_dict(path: str) -> Dict[str, torch.Tensor]:
+    """State dict of a NeMo speaker model from a ``.nemo`` archive (a tar file holding ``model_weights.ckpt``) or from a file
+    written by ``torch.save(model.state_dict())`` -- what EncDecSpeakerLabelModel.from_pretrained would have downloaded
+    (word_based_diarization.py:26)."""
+    import io
+    import tarfile
+    if tarfile.is_tarfile(path):
+        with tarfile.open(path, "r:*") as tar:
+            names = [m for m in tar.getmembers() if m.name.endswith(".ckpt")]
+            if not names:
+                raise _cabi.NsfError(f"{path}: no *.ckpt member in the archive")
+            sd = torch.load(io.BytesIO(tar.extractfile(names[0]).read()), map_location="cpu", weights_only=True)
+    else:
+        sd = torch.load(path, map_location="cpu", weights_only=True)
+    sd = sd.get("state_dict", sd)
+    return {k: v for k, v in sd.items() if k.startswith(("encoder.", "decoder."))}
+
+
+def load_titanet(path: str, device) -> TitaNetB200:
+    return TitaNetB200(load_titanet_state_dict(path), device)

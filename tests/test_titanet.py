@@ -65,6 +65,44 @@ def test_cos_affinity_oracle():
     assert O.cos_affinity(e[:1]).tolist() == [[1.0]]
 
 
+def _blob_affinity(rng, sizes, d=24, noise=0.25):
+    centers = 3.0 * np.eye(len(sizes), d)                                  # orthogonal 'voices'
+    emb = np.concatenate([c + noise * rng.standard_normal((n, d)) for c, n in zip(centers, sizes)])
+    truth = np.concatenate([np.full(n, i) for i, n in enumerate(sizes)])
+    perm = rng.permutation(len(truth))
+    return O.cos_affinity(emb[perm]), truth[perm]
+
+
+@pytest.mark.parametrize("sizes", [(40, 25, 35), (30, 30), (50, 20, 20, 30), (60,)])
+def test_nmesc_spectral_clustering_recovers_blobs(sizes):
+    """clustering.py on the CPU (it runs where the affinity lives): speaker count and partition of well-separated speakers."""
+    import torch
+    import notsofar_b200.clustering as K
+    rng = np.random.default_rng(len(sizes))
+    aff, truth = _blob_affinity(rng, sizes)
+    a = torch.from_numpy(aff).float()
+    k, p_hat = K.nmesc(a)
+    assert k == len(sizes) and p_hat >= 1
+    labels = K.run_clustering(a)
+    assert len(np.unique(labels)) == len(sizes)
+    for c in np.unique(labels):                                   # every cluster is pure: labels equal truth up to a permutation
+        assert len(np.unique(truth[labels == c])) == 1
+    g = K.affinity_graph(a, p_hat)
+    assert torch.equal(g, g.T) and K.is_fully_connected(g)
+    L = K.laplacian(g)
+    assert torch.allclose(L.sum(1), torch.zeros(len(truth)), atol=1e-5)
+
+
+def test_kneighbors_graph_small_known_answer():
+    import torch
+    import notsofar_b200.clustering as K
+    a = torch.tensor([[1.0, 0.9, 0.1], [0.9, 1.0, 0.2], [0.1, 0.2, 1.0]])
+    x = K.kneighbors_connections(a, 2)                            # row i's two best are {i, its nearest other}; stored transposed
+    assert x.tolist() == [[1.0, 1.0, 0.0], [1.0, 1.0, 1.0], [0.0, 0.0, 1.0]]
+    assert K.affinity_graph(a, 2).tolist() == [[1.0, 1.0, 0.0], [1.0, 1.0, 0.5], [0.0, 0.5, 1.0]]
+    assert K.run_clustering(torch.ones(1, 1)).tolist() == [0]
+
+
 # ------------------------------------------------------------------------------------------------ GPU parity
 @pytest.fixture(scope="module")
 def dev():
@@ -180,3 +218,44 @@ def test_word_based_clustering_with_titanet_backend(dev):
     ref = O.embed(w, [x[plan.stream_id[i], plan.start[i]:plan.start[i] + plan.length[i]] for i in range(3)], SMALL)
     got = seen["emb"][0].cpu().numpy()
     assert rel_l2(got, ref) < 2e-4
+
+
+@pytest.mark.gpu
+def test_word_nmesc_default_backends_from_checkpoint(dev, tmp_path, monkeypatch):
+    """diarization_inference-style use with nothing registered: weights from a .nemo-like archive (NSF_TITANET_CKPT), TitaNet
+    kernels, CUDA affinity, NMESC.  Two synthetic 'speakers' (different harmonic stacks) on two streams are told apart."""
+    import io
+    import tarfile
+    import pandas as pd
+    import torch
+    import notsofar_b200.diarization as D
+    w = O.random_weights(3, blocks=SMALL, att_ch=32, emb=16)
+    ck = tmp_path / "model_weights.ckpt"
+    torch.save({k: torch.from_numpy(v) for k, v in w.items()}, ck)
+    arch = tmp_path / "titanet_small.nemo"
+    with tarfile.open(arch, "w") as tar:
+        tar.add(ck, arcname="./model_weights.ckpt")
+    monkeypatch.setenv("NSF_TITANET_CKPT", str(arch))
+    sr, n = 16000, 16000 * 24
+    t = np.arange(n) / sr
+    rng = np.random.default_rng(12)
+    voices = []
+    for f0, tilt in ((110.0, 1.0), (235.0, 2.2)):
+        v = sum(np.sin(2 * np.pi * f0 * h * t + rng.uniform(0, 6.28)) / h ** tilt for h in range(1, 20))
+        voices.append(v * (0.6 + 0.4 * np.sin(2 * np.pi * 2.7 * t)))
+    pcm_np = np.stack([voices[0], voices[1], 0.01 * rng.standard_normal(n)])
+    pcm_np = (pcm_np / np.abs(pcm_np).max(1, keepdims=True) * 20000).astype(np.int16)
+    pcm = torch.from_numpy(pcm_np).to(dev)
+    words = [[f"w{i}", 1.0 + 1.1 * i, 1.0 + 1.1 * i + 0.5] for i in range(20)]
+    df = pd.DataFrame({"start_time": [1.0, 1.0], "end_time": [23.0, 23.0], "text": ["a", "b"], "word_timing": [words[:10], words[10:]],
+                       "meeting_id": ["m", "m"], "session_id": ["s", "s"], "wav_file_name": ["s0.wav", "s1.wav"],
+                       "wav_file_name_ind": [0, 1]})
+    df["wav_file_name"] = df["wav_file_name"].astype("category")
+    cfg = D.DiarizationCfg(method="word_nmesc", min_embedding_windows=[1.5, 1.0, 0.5], apply_deduplication=False)
+    out = D.word_based_clustering(pcm, sr, df, cfg)
+    by_stream = out.groupby("wav_file_name", observed=True)["speaker_id"].agg(lambda x: sorted(set(x)))
+    assert len(by_stream) == 2 and all(len(v) == 1 for v in by_stream) and by_stream.iloc[0] != by_stream.iloc[1], by_stream
+    monkeypatch.delenv("NSF_TITANET_CKPT")
+    D._TITANET = None
+    with pytest.raises(D._cabi.NsfError if hasattr(D, "_cabi") else Exception):
+        D.word_based_clustering(pcm, sr, df, cfg)
