@@ -202,25 +202,51 @@ def _embedding_backend(cfg: DiarizationCfg, device):
 _TITANET = None
 
 
-def word_based_clustering(pcm, sr: int, segments_df: pd.DataFrame, cfg: DiarizationCfg, batch_words: int = 256):
+def word_shard_bounds(n_words: int, world: int) -> List[int]:
+    """Contiguous, balanced blocks of words per rank: rank r embeds words [bounds[r], bounds[r + 1])."""
+    return [n_words * r // world for r in range(world + 1)]
+
+
+def word_based_clustering(pcm, sr: int, segments_df: pd.DataFrame, cfg: DiarizationCfg, batch_words: int = 256, group=None,
+                          shard_words: bool = False):
     """word_based_diarization.py:135-189 on device-resident streams: crops -> TitaNet embeddings (csrc/titanet.cu) -> multi-scale
     cosine affinity -> NMESC + spectral clustering (clustering.py) -> prepare_diarized_data_frame.  ``pcm`` int16 CUDA tensor
     [n_streams, n].  Both stages can be replaced through set_embedding_backend / set_clustering_backend.  Embeddings do not
-    depend on the batch composition (padding is masked), so batches are larger than the reference's 32 words."""
+    depend on the batch composition (padding is masked), so batches are larger than the reference's 32 words.
+
+    ``shard_words``: with torch.distributed initialised, every rank (holding the same ``pcm`` and ``segments_df``)
+    embeds a contiguous block of the words and one all-gather of the [n_words, n_scales, D] embeddings precedes the affinity and
+    clustering, which every rank repeats identically (O(n_words^2), small next to the embedding forward)."""
     embed_fn = _embedding_backend(cfg, getattr(pcm, "device", None))
     if _CLUSTERING_BACKEND is not None:
         cluster_fn = _CLUSTERING_BACKEND
     else:
         from .clustering import nmesc_backend as cluster_fn
     import torch
+    import torch.distributed as dist
     n_scales = len(cfg.min_embedding_windows)
     plan = word_crop_plan(segments_df, pcm.shape[1], sr, cfg.min_embedding_windows, cfg.max_allowed_word_duration)
+    n_words = len(plan.words)
+    world = dist.get_world_size(group) if (shard_words and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    bounds = word_shard_bounds(n_words, world)
+    lo, hi = bounds[rank] * n_scales, bounds[rank + 1] * n_scales
     embs = []
     step = batch_words * n_scales
-    for first in range(0, len(plan.start), step):
-        crops, lens = gather_word_crops(pcm, plan, first, min(step, len(plan.start) - first))
+    for first in range(lo, hi, step):
+        crops, lens = gather_word_crops(pcm, plan, first, min(step, hi - first))
         embs.append(embed_fn(crops, lens, cfg))
-    emb = torch.cat(embs, 0).view(len(plan.words), n_scales, -1)
+    if world > 1:
+        from .sharded import allgather_varlen
+        own = torch.cat(embs, 0) if embs else None
+        d = torch.tensor([own.shape[1] if own is not None else 0], device=pcm.device)
+        dist.all_reduce(d, op=dist.ReduceOp.MAX, group=group)
+        if own is None:
+            own = torch.zeros((0, int(d.item())), dtype=torch.float32, device=pcm.device)
+        emb = allgather_varlen(own.float().contiguous(), [(bounds[r + 1] - bounds[r]) * n_scales for r in range(world)], group)
+    else:
+        emb = torch.cat(embs, 0)
+    emb = emb.view(n_words, n_scales, -1)
     keep = ~plan.too_long
     labels = cluster_fn(emb[torch.from_numpy(keep).to(emb.device)], cfg)
     kept_words = [w for w, k in zip(plan.words, keep) if k]

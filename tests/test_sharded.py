@@ -247,3 +247,85 @@ def test_sessions_distributed_under_gloo_world2():
         mp.spawn(_sched_worker, args=(2, port, ret), nprocs=2, join=True)
         c0, c1 = ret["calls0"], ret["calls1"]
         assert sorted(c0 + c1) == [f"multichannel/MTG_{i}" for i in range(5)] and c0 and c1
+
+
+# ----------------------------------------------------------------------------------------------- diarization: words over ranks
+def _words_df():
+    import pandas as pd
+    words = [[f"w{i}", 0.5 + 0.7 * i, 0.5 + 0.7 * i + 0.15 + 0.05 * (i % 7)] for i in range(23)]
+    df = pd.DataFrame({"start_time": [0.5, 8.0], "end_time": [8.0, 17.0], "text": ["a", "b"], "word_timing": [words[:11], words[11:]],
+                       "meeting_id": ["m", "m"], "session_id": ["s", "s"], "wav_file_name": ["s0.wav", "s1.wav"],
+                       "wav_file_name_ind": [0, 1]})
+    df["wav_file_name"] = df["wav_file_name"].astype("category")
+    return df
+
+
+class _FakePcm:
+    """Host stand-in for the device-resident PCM16 streams (the gloo test has no GPU): shape / device like a tensor."""
+    def __init__(self, a):
+        self.a, self.shape, self.device = a, a.shape, torch.device("cpu")
+
+
+def _host_gather(pcm, plan, first=0, count=None):
+    count = len(plan.start) - first if count is None else count
+    L = int(plan.length[first:first + count].max()) if count else 0
+    out = torch.zeros((count, L))
+    for i in range(count):
+        r = first + i
+        out[i, :plan.length[r]] = torch.from_numpy(pcm.a[plan.stream_id[r], plan.start[r]:plan.start[r] + plan.length[r]].astype(np.float32) / 32767.0)
+    return out, torch.from_numpy(plan.length[first:first + count].copy())
+
+
+def _fake_embed(crops, lens, cfg):
+    n = torch.arange(crops.shape[1])[None, :] < lens[:, None]
+    s = (crops * n).sum(1)
+    return torch.stack([s, (crops.abs() * n).sum(1), lens.float() / 16000.0, torch.ones(len(lens))], 1)
+
+
+def _words_worker(rank, world, port, ret):
+    import torch.distributed as dist
+    import notsofar_b200.diarization as D
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(3)
+        pcm = _FakePcm((rng.standard_normal((2, 16000 * 18)) * 4000).astype(np.int16))
+        seen = {}
+        D.gather_word_crops = _host_gather                       # test stand-in for the CUDA gather
+        D.set_embedding_backend(_fake_embed)
+        D.set_clustering_backend(lambda emb, cfg: (seen.setdefault("emb", emb.clone()), (emb[:, 0, 2] > emb[:, 0, 2].median()).int().numpy())[1])
+        cfg = D.DiarizationCfg(method="word_nmesc", min_embedding_windows=[1.0, 0.5])
+        out = D.word_based_clustering(pcm, 16000, _words_df(), cfg, batch_words=4, shard_words=True)
+        ret[f"emb{rank}"] = seen["emb"].numpy()
+        ret[f"spk{rank}"] = out.speaker_id.tolist()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_word_sharded_embeddings_under_gloo(world):
+    """SURVEY 8e, diarization: every rank embeds a block of the words, one all-gather, identical clustering input everywhere
+    and equal to the unsharded run."""
+    import torch.multiprocessing as mp
+    import notsofar_b200.diarization as D
+    assert D.word_shard_bounds(23, 3) == [0, 7, 15, 23] and D.word_shard_bounds(2, 4) == [0, 0, 1, 1, 2]
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_words_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+        rng = np.random.default_rng(3)
+        pcm = _FakePcm((rng.standard_normal((2, 16000 * 18)) * 4000).astype(np.int16))
+        seen = {}
+        real_gather = D.gather_word_crops
+        D.gather_word_crops = _host_gather
+        D.set_embedding_backend(_fake_embed)
+        D.set_clustering_backend(lambda emb, cfg: (seen.setdefault("emb", emb.clone()), (emb[:, 0, 2] > emb[:, 0, 2].median()).int().numpy())[1])
+        try:
+            cfg = D.DiarizationCfg(method="word_nmesc", min_embedding_windows=[1.0, 0.5])
+            one = D.word_based_clustering(pcm, 16000, _words_df(), cfg, batch_words=4)
+        finally:
+            D.gather_word_crops = real_gather
+            D.set_embedding_backend(None)
+            D.set_clustering_backend(None)
+        for r in range(world):
+            assert np.array_equal(ret[f"emb{r}"], seen["emb"].numpy())
+            assert ret[f"spk{r}"] == one.speaker_id.tolist()
