@@ -259,3 +259,30 @@ def test_word_nmesc_default_backends_from_checkpoint(dev, tmp_path, monkeypatch)
     D._TITANET = None
     with pytest.raises(D._cabi.NsfError if hasattr(D, "_cabi") else Exception):
         D.word_based_clustering(pcm, sr, df, cfg)
+
+
+@pytest.mark.gpu
+def test_titanet_ragged_and_degenerate_crops(dev):
+    """Ragged batch with crops at the stream edges (clipped to almost nothing), a single-crop batch, bucketed == one padded batch."""
+    import torch
+    import notsofar_b200.titanet as T
+    w = O.random_weights(3, blocks=SMALL, att_ch=32, emb=16)
+    model = T.TitaNetB200(w, dev)
+    rng = np.random.default_rng(9)
+    lens = [0, 1, 100, 159, 160, 257, 1000, 8000, 47999]
+    crops = _crops(rng, [max(n, 1) for n in lens])
+    _, x, _ = _run(model, crops, dev)
+    l = torch.tensor(lens, dtype=torch.int32, device=dev)
+    hi, lo, nf, t_pad = model.features(x, l)
+    assert nf.cpu().tolist() == [0, 1, 1, 1, 2, 2, 7, 51, 300]                 # len // 160 + 1 (0 for an empty crop)
+    e_b = model.embed(x, l, bucket=True).cpu().numpy()
+    e_p = model.embed(x, l, bucket=False).cpu().numpy()
+    assert np.isfinite(e_b).all() and np.isfinite(e_p).all()
+    assert rel_l2(e_b, e_p) < 1e-5
+    ref = O.embed(w, [c[:n] for c, n in zip(crops, lens) if n >= 257], SMALL)   # reflect padding needs more than n_fft / 2 samples
+    got = e_b[[i for i, n in enumerate(lens) if n >= 257]]
+    assert max(rel_l2(g, r) for g, r in zip(got, ref)) < 2e-4
+    one = model.embed(x[7:8, :8000].contiguous(), l[7:8]).cpu().numpy()
+    assert rel_l2(one[0], e_b[7]) < 1e-5
+    with pytest.raises(T._cabi.NsfError):
+        model.features(x.cpu(), l)
