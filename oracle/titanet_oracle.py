@@ -17,8 +17,10 @@ titanet-large.yaml recipe and the modules it instantiates]:
   SpeakerDecoder (pool_mode attention, emb_sizes 192)       attentive statistics pooling with global context (TDNN 9216->128
         1x1 conv, ReLU, BatchNorm; tanh; 1x1 conv 128->3072; masked softmax over time; weighted mean and std, clamp 1e-10),
         BatchNorm(6144) + 1x1 conv -> 192-d embedding
-**Parity unpinned**: NeMo and the checkpoint are absent offline and the reference holds no test or golden vector for this
-path; the CUDA path is checked against this restatement only.
+**Parity unpinned** with respect to NeMo itself: NeMo and the checkpoint are absent offline and the reference holds no test or
+golden vector for this path.  The pins available offline (tests/test_titanet.py): the front end against the
+torch.stft / torch.hann_window / torch.std calls FilterbankFeatures is made of (1e-9), the network against the same recipe
+assembled from torch.nn Conv1d / BatchNorm1d modules loading these weights by name (1e-10), and the published parameter count.
 """
 from __future__ import annotations
 

@@ -286,3 +286,85 @@ def test_titanet_ragged_and_degenerate_crops(dev):
     assert rel_l2(one[0], e_b[7]) < 1e-5
     with pytest.raises(T._cabi.NsfError):
         model.features(x.cpu(), l)
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle vs torch building blocks
+def test_oracle_frontend_against_torch_stft():
+    """The numpy front end against the torch calls NeMo's FilterbankFeatures is made of [upstream]: torch.stft(n_fft 512, hop 160,
+    win_length 400, hann_window(400, periodic=False), center=True -> reflect), |.|^2, mel matmul, log(. + 2^-24), per-feature
+    normalisation with the unbiased std."""
+    import torch
+    rng = np.random.default_rng(21)
+    x = _crops(rng, [20000])[0]
+    xt = torch.from_numpy(x).double()
+    xt = torch.cat([xt[:1], xt[1:] - 0.97 * xt[:-1]])
+    spec = torch.stft(xt, n_fft=512, hop_length=160, win_length=400, window=torch.hann_window(400, periodic=False, dtype=torch.float64),
+                      center=True, return_complex=True)
+    power = spec.abs() ** 2                                                       # [257, T]
+    mel = torch.from_numpy(O.mel_filterbank()) @ power
+    lm = torch.log(mel + 2.0 ** -24)
+    T = O.seq_len(len(x))
+    assert lm.shape[1] == T
+    lm = lm[:, :T]
+    ref = ((lm - lm.mean(1, keepdim=True)) / (lm.std(1, keepdim=True) + 1e-5)).T.numpy()     # torch.std: unbiased
+    assert rel_l2(O.features(x), ref) < 1e-9
+
+
+def test_oracle_network_against_torch_modules():
+    """The numpy encoder / decoder against the same network assembled from torch.nn modules the way the NeMo recipe assembles it
+    (Conv1d groups=C depthwise + 1x1 pointwise, BatchNorm1d eps 1e-3 in eval mode, squeeze-excite with bias-free Linear layers,
+    residual 1x1 conv + BatchNorm, attentive pooling with TDNN(conv, ReLU, BatchNorm) -> Tanh -> Conv1d, BatchNorm + Conv1d embedding),
+    loading the oracle's weights by name."""
+    import torch
+    from torch import nn
+    w = O.random_weights(11, blocks=SMALL, att_ch=32, emb=16)
+    sd = {k: torch.from_numpy(v).double() for k, v in w.items()}
+
+    def bn(name, c, eps):
+        m = nn.BatchNorm1d(c, eps=eps).double()
+        m.load_state_dict({k[len(name) + 1:]: v for k, v in sd.items() if k.startswith(name + ".")}, strict=False)
+        return m.eval()
+
+    def conv(name, ci, co, k, groups=1, bias=False):
+        m = nn.Conv1d(ci, co, k, padding=k // 2, groups=groups, bias=bias).double()
+        m.weight.data = sd[name + ".weight"]
+        if bias:
+            m.bias.data = sd[name + ".bias"]
+        return m
+
+    rng = np.random.default_rng(13)
+    feats = [rng.standard_normal((T, 80)) for T in (37, 64)]
+    got = O.decoder(w, O.encoder(w, feats, SMALL))
+    outs = []
+    with torch.no_grad():
+        for f in feats:
+            x = torch.from_numpy(f).T[None]                                         # [1, C, T]
+            c_in = 80
+            for b, (co, rep, k, res) in enumerate(SMALL):
+                p, x_in, c, i = f"encoder.encoder.{b}.", x, c_in, 0
+                for r in range(rep):
+                    x = conv(p + f"mconv.{i}.conv", c, c, k, groups=c)(x)
+                    x = bn(p + f"mconv.{i + 2}", co, 1e-3)(conv(p + f"mconv.{i + 1}.conv", c, co, 1)(x))
+                    if r < rep - 1:
+                        x = torch.relu(x)
+                    i += 3 if r == rep - 1 else 5
+                    c = co
+                y = x.mean(-1)                                                      # squeeze-excite, context -1
+                y = torch.sigmoid(torch.relu(y @ sd[p + f"mconv.{i}.fc.0.weight"].T) @ sd[p + f"mconv.{i}.fc.2.weight"].T)
+                x = x * y[..., None]
+                if res:
+                    x = x + bn(p + "res.0.1", co, 1e-3)(conv(p + "res.0.0.conv", c_in, co, 1)(x_in))
+                x = torch.relu(x)
+                c_in = co
+            q = "decoder._pooling.attention_layer."
+            mean = x.mean(-1, keepdim=True)
+            std = ((x - mean) ** 2).mean(-1, keepdim=True).clamp(1e-10).sqrt()
+            ctx = torch.cat([x, mean.expand_as(x), std.expand_as(x)], 1)
+            h = torch.tanh(bn(q + "0.bn", 32, 1e-5)(torch.relu(conv(q + "0.conv_layer", 3 * c_in, 32, 1, bias=True)(ctx))))
+            alpha = torch.softmax(conv(q + "2", 32, c_in, 1, bias=True)(h), dim=2)
+            mu = (alpha * x).sum(2)
+            sg = (alpha * (x - mu[..., None]) ** 2).sum(2).clamp(1e-10).sqrt()
+            pool = torch.cat([mu, sg], 1)[..., None]
+            e = conv("decoder.emb_layers.0.1", 2 * c_in, 16, 1, bias=True)(bn("decoder.emb_layers.0.0", 2 * c_in, 1e-5)(pool))
+            outs.append(e[0, :, 0].numpy())
+    assert rel_l2(got, np.stack(outs)) < 1e-10
