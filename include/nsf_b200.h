@@ -264,6 +264,21 @@ int nsf_whisper_decoder_step_dev(nsf_whisper_decoder* h, int32_t* cur_tokens, in
                                  const int32_t* forced, int total_len, int eot, int32_t* out_tokens, int32_t* argmaxes, uint8_t* done,
                                  void* stream);
 
+/* Logit filters of the decoding loop [upstream whisper/decoding.py: SuppressBlank, SuppressTokens, ApplyTimestampRules; the
+ * reference decodes with timestamps, asr/asr.py:52-56 -> whisper.transcribe], applied in place to logits [n_batch][vocab]
+ * before the arg-max.  tokens [n_batch][total_len] holds the fed tokens up to position *pos_dev; sample_begin = length of the
+ * prompt (sot sequence); timestamp_begin < 0 switches the timestamp rules off; max_initial_timestamp_index < 0: none;
+ * suppress [n_suppress] token ids always suppressed, suppress_first [n_suppress_first] (blank tokens + eot) at the first
+ * sampled position.  Same arithmetic as transformers' WhisperTimeStampLogitsProcessor (the pin used by the tests). */
+typedef struct { int sample_begin, timestamp_begin, no_timestamps, eot, max_initial_timestamp_index, n_suppress, n_suppress_first; } nsf_whisper_rules;
+int nsf_whisper_logit_rules(float* logits, int n_batch, int vocab, const int32_t* tokens, int total_len, const int32_t* pos_dev,
+                            const nsf_whisper_rules* rules, const int32_t* suppress, const int32_t* suppress_first, void* stream);
+/* nsf_whisper_decoder_step_dev with the filters between the logits and the arg-max (graph-replayable like it). */
+int nsf_whisper_decoder_step_rules(nsf_whisper_decoder* h, int32_t* cur_tokens, int32_t* pos_dev, int n_batch, void* state,
+                                   int64_t state_bytes, const int32_t* forced, int total_len, int eot, int32_t* out_tokens,
+                                   int32_t* argmaxes, uint8_t* done, const nsf_whisper_rules* rules, const int32_t* suppress,
+                                   const int32_t* suppress_first, void* stream);
+
 /* ---- TitaNet speaker-embedding forward + multi-scale cosine affinity (row a16: diarization/word_based_diarization.py:26
  * loads NeMo's EncDecSpeakerLabelModel "titanet_large", :105 calls spk_model.forward(input_signal, input_signal_length) under
  * autocast, :171-177 build the per-scale affinity with NeMo's getCosAffinityMatrix and average it.  NeMo is third-party and

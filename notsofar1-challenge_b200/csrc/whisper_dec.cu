@@ -162,6 +162,77 @@ wd_argmax_kernel(const float* __restrict__ logits, int vocab, int32_t* __restric
     }
 }
 
+// Logit filters of the decoding loop, applied in place before the arg-max, one block per sequence
+// [upstream whisper/decoding.py: SuppressBlank, SuppressTokens, ApplyTimestampRules -- DecodingTask applies them in this order]:
+//   * at the first sampled position: blank tokens and eot are suppressed; always: the suppress list
+//   * <|notimestamps|> is suppressed; timestamps come in pairs (after one timestamp: no text; after two: no timestamp);
+//     timestamps do not decrease (and a segment has non-zero length); the first sampled token is a timestamp not later than
+//     max_initial_timestamp_index; if the probability mass of all timestamps exceeds the most likely text token, text is
+//     suppressed (log-softmax normalisers cancel: logsumexp(timestamp logits) > max(text logits)).
+// tokens [n_batch][total_len]: the fed tokens, valid up to position *pos_ptr (the token consumed by this step).
+__global__ void __launch_bounds__(1024)
+wd_logit_rules_kernel(float* __restrict__ logits, int vocab, const int32_t* __restrict__ tokens, int total_len,
+                      const int32_t* __restrict__ pos_ptr, nsf_whisper_rules R, const int32_t* __restrict__ suppress,
+                      const int32_t* __restrict__ suppress_first) {
+    __shared__ float redf[32];
+    __shared__ int redi[32];
+    float* row = logits + (size_t)blockIdx.x * vocab;
+    const int n_sampled = *pos_ptr + 1 - R.sample_begin;
+    if (n_sampled < 0) return;                                   // still inside the prompt: the next token is forced
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (n_sampled == 0)
+        for (int i = tid; i < R.n_suppress_first; i += blockDim.x) { const int t = suppress_first[i]; if (t >= 0 && t < vocab) row[t] = -INFINITY; }
+    for (int i = tid; i < R.n_suppress; i += blockDim.x) { const int t = suppress[i]; if (t >= 0 && t < vocab) row[t] = -INFINITY; }
+    const int tb = R.timestamp_begin;
+    if (tb < 0) return;
+    __syncthreads();
+    auto block_max_i = [&](int v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        __syncthreads();
+        if (lane == 0) redi[wid] = v;
+        __syncthreads();
+        int r = redi[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = max(r, redi[w]);
+        return r;
+    };
+    auto block_red_f = [&](float v, bool is_max) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const float ov = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, ov) : v + ov; }
+        __syncthreads();
+        if (lane == 0) redf[wid] = v;
+        __syncthreads();
+        float r = redf[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = is_max ? fmaxf(r, redf[w]) : r + redf[w];
+        return r;
+    };
+    const int32_t* seq = tokens + (size_t)blockIdx.x * total_len + R.sample_begin;
+    const bool last_ts = n_sampled >= 1 && seq[n_sampled - 1] >= tb;
+    const bool penult_ts = n_sampled < 2 || seq[n_sampled - 2] >= tb;
+    int li = -1;
+    for (int i = tid; i < n_sampled; i += blockDim.x) if (seq[i] >= tb) li = max(li, i);
+    li = block_max_i(li);
+    const int forbid_end = li < 0 ? tb : (last_ts && !penult_ts) ? seq[li] : seq[li] + 1;     // timestamps [tb, forbid_end) are forbidden
+    float mx_text = -INFINITY, mx_ts = -INFINITY;
+    for (int i = tid; i < vocab; i += blockDim.x) {
+        bool f = i == R.no_timestamps;
+        f |= last_ts && (penult_ts ? i >= tb : i < R.eot);
+        f |= i >= tb && i < forbid_end;
+        f |= n_sampled == 0 && (i < tb || (R.max_initial_timestamp_index >= 0 && i > tb + R.max_initial_timestamp_index));
+        float v = row[i];
+        if (f) { v = -INFINITY; row[i] = v; }
+        if (i < tb) mx_text = fmaxf(mx_text, v); else mx_ts = fmaxf(mx_ts, v);
+    }
+    mx_text = block_red_f(mx_text, true);
+    mx_ts = block_red_f(mx_ts, true);
+    if (mx_ts == -INFINITY) return;                              // no timestamp allowed: nothing to compare (uniform)
+    float sum = 0.f;
+    for (int i = max(tb, 0) + tid; i < vocab; i += blockDim.x) sum += expf(row[i] - mx_ts);
+    sum = block_red_f(sum, false);
+    if (mx_ts + logf(sum) > mx_text)
+        for (int i = tid; i < tb; i += blockDim.x) row[i] = -INFINITY;
+}
+
 // Bookkeeping of one greedy step, one block: which token is fed next (the prompt / teacher-forced token if forced >= 0, the
 // end-of-text token once a sequence is done, else the arg-max), the record of fed tokens and arg-maxes, the position.
 __global__ void __launch_bounds__(1024)
@@ -304,8 +375,10 @@ extern "C" int nsf_whisper_decoder_prefill_cross(nsf_whisper_decoder* h, const v
     return NSF_OK;
 }
 
+struct WdRulesArgs { const nsf_whisper_rules* rules; const int32_t* suppress; const int32_t* suppress_first; const int32_t* tokens; int total_len; };
+
 static int wd_step_impl(nsf_whisper_decoder* h, const int32_t* tokens, const int32_t* pos_dev, int n_batch, void* state, int64_t state_bytes,
-                        float* logits_out, int32_t* next_tokens, cudaStream_t s) {
+                        float* logits_out, int32_t* next_tokens, cudaStream_t s, const WdRulesArgs* ra = nullptr) {
     const nsf_whisper_dec_dims& D = h->dims;
     NSF_REQUIRE(((uintptr_t)state & 255) == 0, "nsf_whisper_decoder_step: state must be 256-byte aligned");
     WdState st = wd_carve(D, n_batch, reinterpret_cast<unsigned char*>(state));
@@ -347,6 +420,10 @@ static int wd_step_impl(nsf_whisper_decoder* h, const int32_t* tokens, const int
     if ((rc = ln_launch(st.x, B, d, h->g(WD_LN_G), h->g(WD_LN_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
     float* lg = logits_out ? logits_out : st.logits;
     if ((rc = linear(st.h, d, h->g(WD_TOK_EMB), nullptr, D.vocab, EPI_STORE, lg, D.vocab))) return rc;
+    if (ra) {
+        wd_logit_rules_kernel<<<B, 1024, 0, s>>>(lg, D.vocab, ra->tokens, ra->total_len, pos_dev, *ra->rules, ra->suppress, ra->suppress_first);
+        if ((rc = check_launch("wd_logit_rules_kernel"))) return rc;
+    }
     wd_argmax_kernel<<<B, 1024, 0, s>>>(lg, D.vocab, next_tokens);
     return check_launch("wd_argmax_kernel");
 }
@@ -374,6 +451,40 @@ extern "C" int nsf_whisper_decoder_step_dev(nsf_whisper_decoder* h, int32_t* cur
     cudaStream_t s = (cudaStream_t)stream_;
     int rc = wd_step_impl(h, cur_tokens, pos_dev, n_batch, state, state_bytes, nullptr, st.next, s);
     if (rc) return rc;
+    wd_advance_kernel<<<1, 1024, 0, s>>>(st.next, forced, total_len, eot, cur_tokens, out_tokens, argmaxes, done, pos_dev, n_batch);
+    return check_launch("wd_advance_kernel");
+}
+
+static int wd_check_rules(const nsf_whisper_rules* r, const int32_t* suppress, const int32_t* suppress_first, int vocab) {
+    NSF_REQUIRE(r, "whisper rules: null pointer");
+    NSF_REQUIRE(r->sample_begin >= 1 && r->n_suppress >= 0 && r->n_suppress_first >= 0, "whisper rules: bad sizes");
+    NSF_REQUIRE((r->n_suppress == 0 || suppress) && (r->n_suppress_first == 0 || suppress_first), "whisper rules: missing suppress list");
+    NSF_REQUIRE(r->timestamp_begin < vocab && (r->timestamp_begin < 0 || (r->eot >= 0 && r->eot <= r->timestamp_begin)),
+                "whisper rules: need eot <= timestamp_begin < vocab");
+    return NSF_OK;
+}
+
+extern "C" int nsf_whisper_logit_rules(float* logits, int n_batch, int vocab, const int32_t* tokens, int total_len, const int32_t* pos_dev,
+                                       const nsf_whisper_rules* rules, const int32_t* suppress, const int32_t* suppress_first, void* stream_) {
+    NSF_REQUIRE(logits && tokens && pos_dev && n_batch >= 1 && vocab >= 1 && total_len >= 1, "nsf_whisper_logit_rules: bad arguments");
+    int rc = wd_check_rules(rules, suppress, suppress_first, vocab);
+    if (rc) return rc;
+    wd_logit_rules_kernel<<<n_batch, 1024, 0, (cudaStream_t)stream_>>>(logits, vocab, tokens, total_len, pos_dev, *rules, suppress, suppress_first);
+    return check_launch("wd_logit_rules_kernel");
+}
+
+extern "C" int nsf_whisper_decoder_step_rules(nsf_whisper_decoder* h, int32_t* cur_tokens, int32_t* pos_dev, int n_batch, void* state,
+                                              int64_t state_bytes, const int32_t* forced, int total_len, int eot, int32_t* out_tokens,
+                                              int32_t* argmaxes, uint8_t* done, const nsf_whisper_rules* rules, const int32_t* suppress,
+                                              const int32_t* suppress_first, void* stream_) {
+    NSF_REQUIRE(h && cur_tokens && pos_dev && state && out_tokens && argmaxes && done, "nsf_whisper_decoder_step_rules: null pointer");
+    NSF_REQUIRE(n_batch >= 1 && total_len >= 1 && total_len <= h->dims.n_text_ctx, "nsf_whisper_decoder_step_rules: bad sizes");
+    int rc = wd_check_rules(rules, suppress, suppress_first, h->dims.vocab);
+    if (rc) return rc;
+    WdState st = wd_carve(h->dims, n_batch, reinterpret_cast<unsigned char*>(state));
+    cudaStream_t s = (cudaStream_t)stream_;
+    const WdRulesArgs ra = {rules, suppress, suppress_first, out_tokens, total_len};
+    if ((rc = wd_step_impl(h, cur_tokens, pos_dev, n_batch, state, state_bytes, nullptr, st.next, s, &ra))) return rc;
     wd_advance_kernel<<<1, 1024, 0, s>>>(st.next, forced, total_len, eot, cur_tokens, out_tokens, argmaxes, done, pos_dev, n_batch);
     return check_launch("wd_advance_kernel");
 }

@@ -302,6 +302,46 @@ def pack_whisper_decoder(state_dict: Dict[str, object], n_audio_ctx: int = 1500)
     return dims, np.concatenate(chunks), np.asarray(offsets, np.int64)
 
 
+class _RulesStruct(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("sample_begin", "timestamp_begin", "no_timestamps", "eot", "max_initial_timestamp_index",
+                                        "n_suppress", "n_suppress_first")]
+
+
+class WhisperRules:
+    """Logit filters of the decoding loop (SuppressBlank, SuppressTokens, ApplyTimestampRules [upstream whisper/decoding.py]); the
+    token ids come from the tokenizer of the checkpoint in use (multilingual large-v3: eot 50257, <|notimestamps|> 50364,
+    <|0.00|> 50365).  ``timestamp_begin=None``: no timestamp rules (the without_timestamps mode)."""
+
+    def __init__(self, eot: int, timestamp_begin: Optional[int] = None, no_timestamps: int = -1,
+                 max_initial_timestamp_index: Optional[int] = 50, suppress=(), suppress_first=()):
+        self.eot, self.timestamp_begin, self.no_timestamps = int(eot), timestamp_begin, int(no_timestamps)
+        self.max_initial_timestamp_index = max_initial_timestamp_index
+        self.suppress, self.suppress_first = [int(t) for t in suppress], [int(t) for t in suppress_first]
+
+    def to_device(self, sample_begin: int, device):
+        st = _RulesStruct(int(sample_begin), -1 if self.timestamp_begin is None else int(self.timestamp_begin), self.no_timestamps, self.eot,
+                          -1 if self.max_initial_timestamp_index is None else int(self.max_initial_timestamp_index),
+                          len(self.suppress), len(self.suppress_first))
+        sup = torch.tensor(self.suppress or [0], dtype=torch.int32, device=device)
+        sup1 = torch.tensor(self.suppress_first or [0], dtype=torch.int32, device=device)
+        return st, sup, sup1
+
+
+def apply_logit_rules(logits: torch.Tensor, tokens: torch.Tensor, sample_begin: int, rules: WhisperRules) -> torch.Tensor:
+    """logits [B, vocab] f32 cuda, tokens [B, n] int32 (the tokens so far, n >= sample_begin) -> filtered copy (nsf_whisper_logit_rules)."""
+    if not (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 2):
+        raise _cabi.NsfError("apply_logit_rules needs float32 CUDA logits [B, vocab]; there is no CPU path")
+    lib = _cabi.load()
+    out = logits.clone().contiguous()
+    tok = tokens.to(device=logits.device, dtype=torch.int32).contiguous()
+    pos = torch.tensor([tok.shape[1] - 1], dtype=torch.int32, device=logits.device)
+    st, sup, sup1 = rules.to_device(sample_begin, logits.device)
+    with torch.cuda.device(logits.device):
+        _cabi.check(lib.nsf_whisper_logit_rules(_cabi.ptr(out), out.shape[0], out.shape[1], _cabi.ptr(tok), tok.shape[1], _cabi.ptr(pos),
+                                                C.byref(st), _cabi.ptr(sup), _cabi.ptr(sup1), _cabi.stream_ptr()), "nsf_whisper_logit_rules")
+    return out
+
+
 class WhisperB200:
     """Encoder + greedy decoder of one Whisper model on one B200: audio chunks in, token ids out.
 
@@ -351,10 +391,12 @@ class WhisperB200:
 
     @torch.no_grad()
     def decode_greedy(self, enc_bf16: torch.Tensor, prompt, max_new_tokens: int = 224, eot: Optional[int] = None,
-                      forced_tokens: Optional[torch.Tensor] = None, return_logits: bool = False):
+                      forced_tokens: Optional[torch.Tensor] = None, return_logits: bool = False, rules: Optional["WhisperRules"] = None):
         """enc_bf16 int16 [B, 1500, d] (from ``encode``).  prompt: list of token ids fed first.  Returns tokens int32
         [B, len(prompt) + n_new] (and the fp32 logits of every step if return_logits).  forced_tokens [B, n]: teacher forcing
-        (the arg-max is still computed and returned, the forced token is fed) -- used by the parity tests."""
+        (the arg-max is still computed and returned, the forced token is fed) -- used by the parity tests.  rules: logit filters
+        (timestamp rules, suppressed tokens) applied on the device between the logits and the arg-max of every sampled position
+        (graph path only)."""
         B = enc_bf16.shape[0]
         D = self.dec_dims
         need = self._ensure_state(B)
@@ -364,8 +406,10 @@ class WhisperB200:
                         "nsf_whisper_decoder_prefill_cross")
             n_prompt = len(prompt)
             total = min(D.n_text_ctx, n_prompt + max_new_tokens)
+            if rules is not None and return_logits:
+                raise _cabi.NsfError("decode_greedy: rules are applied inside the graph-replayed step; return_logits is the unfiltered test path")
             if not return_logits:
-                return self._decode_graph(B, need, prompt, total, eot, forced_tokens)
+                return self._decode_graph(B, need, prompt, total, eot, forced_tokens, rules)
             tokens = torch.zeros((B, total), dtype=torch.int32, device=self.device)
             tokens[:, :n_prompt] = torch.tensor(prompt, dtype=torch.int32, device=self.device)
             nxt = torch.empty((B,), dtype=torch.int32, device=self.device)
@@ -394,13 +438,16 @@ class WhisperB200:
             return tokens, argmaxes, logits_all
         return tokens
 
-    def _decode_graph(self, B: int, need: int, prompt, total: int, eot: Optional[int], forced_tokens: Optional[torch.Tensor]):
+    def _decode_graph(self, B: int, need: int, prompt, total: int, eot: Optional[int], forced_tokens: Optional[torch.Tensor],
+                      rules: Optional["WhisperRules"] = None):
         """The decode loop as replays of ONE captured CUDA graph: position, current tokens, done flags and the token record
         live on the device (nsf_whisper_decoder_step_dev), so every step launches the same ~450 kernels with the same
         arguments."""
         dev = self.device
         n_prompt = len(prompt)
-        key = (B, total, self._state.data_ptr())
+        rkey = None if rules is None else (n_prompt, rules.eot, rules.timestamp_begin, rules.no_timestamps, rules.max_initial_timestamp_index,
+                                           tuple(rules.suppress), tuple(rules.suppress_first))
+        key = (B, total, self._state.data_ptr(), rkey)
         if getattr(self, "_graphs", None) is None:
             self._graphs = {}
         if key not in self._graphs:
@@ -409,7 +456,16 @@ class WhisperB200:
                         out=torch.zeros((B, total), dtype=torch.int32, device=dev), arg=torch.zeros((B, total), dtype=torch.int32, device=dev),
                         done=torch.zeros((B,), dtype=torch.uint8, device=dev), eot=torch.zeros((), dtype=torch.int32))
 
+            rdev = rules.to_device(n_prompt, dev) if rules is not None else None
+            bufs["rules"] = rdev                                  # keeps the device lists alive as long as the graph
+
             def launch(eot_val):
+                if rdev is not None:
+                    _cabi.check(self._lib.nsf_whisper_decoder_step_rules(
+                        self._dh, _cabi.ptr(bufs["cur"]), _cabi.ptr(bufs["pos"]), B, _cabi.ptr(self._state), need, _cabi.ptr(bufs["forced"]), total,
+                        eot_val, _cabi.ptr(bufs["out"]), _cabi.ptr(bufs["arg"]), _cabi.ptr(bufs["done"]), C.byref(rdev[0]), _cabi.ptr(rdev[1]),
+                        _cabi.ptr(rdev[2]), _cabi.stream_ptr()), "nsf_whisper_decoder_step_rules")
+                    return
                 _cabi.check(self._lib.nsf_whisper_decoder_step_dev(
                     self._dh, _cabi.ptr(bufs["cur"]), _cabi.ptr(bufs["pos"]), B, _cabi.ptr(self._state), need, _cabi.ptr(bufs["forced"]), total,
                     eot_val, _cabi.ptr(bufs["out"]), _cabi.ptr(bufs["arg"]), _cabi.ptr(bufs["done"]), _cabi.stream_ptr()),

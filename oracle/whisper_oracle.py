@@ -84,3 +84,48 @@ def encoder(w: Dict[str, np.ndarray], mel: np.ndarray, dtype=np.float64) -> np.n
         x = x + _gelu(h @ W[p + "mlp.0.weight"].T + W[p + "mlp.0.bias"]) @ W[p + "mlp.2.weight"].T + W[p + "mlp.2.bias"]
         l += 1
     return _ln(x, W["ln_post.weight"], W["ln_post.bias"])
+
+
+def apply_logit_rules(logits: np.ndarray, tokens: np.ndarray, sample_begin: int, timestamp_begin: int, no_timestamps: int, eot: int,
+                      max_initial_timestamp_index=None, suppress=(), suppress_first=()) -> np.ndarray:
+    """The logit filters of openai-whisper's decoding loop [upstream whisper/decoding.py: SuppressBlank, SuppressTokens,
+    ApplyTimestampRules, applied in this order by DecodingTask] on logits [B, vocab] given the tokens so far [B, n]
+    (n >= sample_begin).  timestamp_begin < 0 switches the timestamp rules off.  Pinned in tests/test_whisper.py against
+    transformers' WhisperTimeStampLogitsProcessor, which implements the same timestamp rules."""
+    lg = np.array(logits, np.float32, copy=True)
+    B, n = tokens.shape
+    if n == sample_begin and len(suppress_first):
+        lg[:, list(suppress_first)] = -np.inf                                        # SuppressBlank
+    if len(suppress):
+        lg[:, list(suppress)] = -np.inf                                              # SuppressTokens
+    if timestamp_begin < 0:
+        return lg
+    tb = timestamp_begin
+    lg[:, no_timestamps] = -np.inf
+    for k in range(B):
+        seq = tokens[k, sample_begin:].tolist()
+        last = len(seq) >= 1 and seq[-1] >= tb
+        penult = len(seq) < 2 or seq[-2] >= tb
+        if last:
+            if penult:
+                lg[k, tb:] = -np.inf                                                  # has to be non-timestamp
+            else:
+                lg[k, :eot] = -np.inf                                                 # cannot be normal text tokens
+        ts = [t for t in seq if t >= tb]
+        if ts:                                                                        # timestamps shouldn't decrease; segments have non-zero length
+            t_last = ts[-1] if (last and not penult) else ts[-1] + 1
+            lg[k, tb:t_last] = -np.inf
+    if n == sample_begin:
+        lg[:, :tb] = -np.inf                                                          # the first sampled token is a timestamp
+        if max_initial_timestamp_index is not None:
+            lg[:, tb + max_initial_timestamp_index + 1:] = -np.inf
+    for k in range(B):                                                               # timestamp mass above every text token -> timestamp
+        row = lg[k].astype(np.float64)
+        m = row.max()
+        logprobs = row - (m + np.log(np.exp(row - m).sum())) if np.isfinite(m) else row
+        t = logprobs[tb:]
+        tm = t.max()
+        ts_lp = tm + np.log(np.exp(t - tm).sum()) if np.isfinite(tm) else -np.inf
+        if ts_lp > logprobs[:tb].max():
+            lg[k, :tb] = -np.inf
+    return lg
