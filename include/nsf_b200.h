@@ -273,11 +273,24 @@ int nsf_whisper_decoder_step_dev(nsf_whisper_decoder* h, int32_t* cur_tokens, in
 typedef struct { int sample_begin, timestamp_begin, no_timestamps, eot, max_initial_timestamp_index, n_suppress, n_suppress_first; } nsf_whisper_rules;
 int nsf_whisper_logit_rules(float* logits, int n_batch, int vocab, const int32_t* tokens, int total_len, const int32_t* pos_dev,
                             const nsf_whisper_rules* rules, const int32_t* suppress, const int32_t* suppress_first, void* stream);
-/* nsf_whisper_decoder_step_dev with the filters between the logits and the arg-max (graph-replayable like it). */
+/* nsf_whisper_decoder_step_dev with the filters between the logits and the arg-max (rules may be NULL) and, optionally, the
+ * capture of the cross-attention softmax rows of the alignment heads (graph-replayable like it): xattn_probs
+ * [n_batch][n_align][total_len][n_audio_ctx] f32 gets row *pos_dev of every head h of layer l with align_map[l][h] = slot >= 0
+ * (align_map [n_layers][n_heads] int32 on the device, -1 elsewhere). */
 int nsf_whisper_decoder_step_rules(nsf_whisper_decoder* h, int32_t* cur_tokens, int32_t* pos_dev, int n_batch, void* state,
                                    int64_t state_bytes, const int32_t* forced, int total_len, int eot, int32_t* out_tokens,
                                    int32_t* argmaxes, uint8_t* done, const nsf_whisper_rules* rules, const int32_t* suppress,
-                                   const int32_t* suppress_first, void* stream);
+                                   const int32_t* suppress_first, float* xattn_probs, const int32_t* align_map, int n_align, void* stream);
+/* Token-level timestamps from the captured weights [upstream whisper/timing.py: find_alignment / median_filter / dtw; the
+ * reference transcribes with word_timestamps=True, asr/asr.py:52-56]: per (sequence, head, audio position) normalisation over
+ * the tokens, median filter of width 7 along the audio axis, mean over the heads, dynamic time warping of the negated matrix;
+ * start_frame [n_batch][n_tokens] int32 = audio position (20 ms units) at which the path enters each token.
+ * weights [n_batch][n_heads][n_tokens][n_frames] f32 (rows of the tokens to align only); the first m_valid audio positions take
+ * part (num_frames // 2 upstream); n_tokens_per_seq [n_batch] or NULL; cost_out [n_batch][n_tokens][m_valid] or NULL. */
+int64_t nsf_whisper_alignment_workspace_bytes(int n_batch, int n_heads, int n_tokens, int n_frames);
+int nsf_whisper_alignment(const float* weights, int n_batch, int n_heads, int n_tokens, int n_frames, int m_valid,
+                          const int32_t* n_tokens_per_seq, int32_t* start_frame, float* cost_out, void* workspace,
+                          int64_t workspace_bytes, void* stream);
 
 /* ---- TitaNet speaker-embedding forward + multi-scale cosine affinity (row a16: diarization/word_based_diarization.py:26
  * loads NeMo's EncDecSpeakerLabelModel "titanet_large", :105 calls spk_model.forward(input_signal, input_signal_length) under

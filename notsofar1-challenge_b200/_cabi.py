@@ -76,7 +76,9 @@ SIGNATURES = {
     "nsf_attention16_test": (i32, [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_whisper_logit_rules": (i32, [c_f32p, i32, i32, C.c_void_p, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsf_whisper_decoder_step_rules": (i32, [C.c_void_p, C.c_void_p, C.c_void_p, i32, C.c_void_p, i64, C.c_void_p, i32, i32, C.c_void_p,
-                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, i32, C.c_void_p]),
+    "nsf_whisper_alignment_workspace_bytes": (i64, [i32, i32, i32, i32]),
+    "nsf_whisper_alignment": (i32, [c_f32p, i32, i32, i32, i32, i32, C.c_void_p, C.c_void_p, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_titanet_num_offsets": (i64, [C.c_void_p]),
     "nsf_titanet_create": (i32, [C.c_void_p, c_f32p, i64, C.POINTER(i64), i32, C.POINTER(C.c_void_p)]),
     "nsf_titanet_destroy": (None, [C.c_void_p]),

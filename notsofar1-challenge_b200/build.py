@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnsf_b200.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["cabi.cu", "stft.cu", "features.cu", "mvdr.cu", "mask_apply.cu", "stitch.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "attention16.cu", "flash_attn.cu", "conformer.cu", "whisper.cu", "whisper_dec.cu", "titanet.cu"]
+SOURCES = ["cabi.cu", "stft.cu", "features.cu", "mvdr.cu", "mask_apply.cu", "stitch.cu", "gemm_simt.cu", "gemm_tc.cu", "attention.cu", "attention16.cu", "flash_attn.cu", "conformer.cu", "whisper.cu", "whisper_dec.cu", "whisper_align.cu", "titanet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

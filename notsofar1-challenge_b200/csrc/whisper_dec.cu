@@ -38,7 +38,8 @@ template <bool APPEND>
 __global__ void __launch_bounds__(256)
 wd_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_new, const float* __restrict__ v_new, int64_t ldq,
                uint16_t* __restrict__ Kc, uint16_t* __restrict__ Vc, int n_keys_host, const int32_t* __restrict__ pos_ptr, int t_max,
-               int n_heads, uint16_t* __restrict__ out, int d_model) {
+               int n_heads, uint16_t* __restrict__ out, int d_model, float* __restrict__ probs_out = nullptr,
+               const int32_t* __restrict__ align_row = nullptr, int n_align = 0, int probs_len = 0) {
     extern __shared__ float sm[];                     // q[64] | p[t_max rounded] | red[32] | acc[8][64]
     const int n_keys = APPEND ? (*pos_ptr + 1) : n_keys_host;       // self-attention: keys 0 .. pos (the position lives on the device)
     float* qs = sm;
@@ -100,6 +101,16 @@ wd_attn_kernel(const float* __restrict__ q, const float* __restrict__ k_new, con
     sum = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) sum += red[w];
+    if (!APPEND && probs_out) {
+        // alignment heads: the softmax row of this position goes to probs [n_batch][n_align][probs_len][n_keys] (word timestamps)
+        const int slot = align_row[h];
+        const int pos = *pos_ptr;
+        if (slot >= 0 && pos < probs_len) {
+            float* dst = probs_out + (((size_t)b * n_align + slot) * probs_len + pos) * n_keys;
+            const float inv = 1.f / sum;
+            for (int t = tid; t < n_keys; t += 256) dst[t] = p[t] * inv;
+        }
+    }
     // weighted values: thread = (key slot tid / 8 of 32, 8 dims tid % 8), 16-byte loads, partial sums reduced through smem
     const int vsub = tid & 7, vrow = tid >> 3;
     float acc[8];
@@ -375,7 +386,10 @@ extern "C" int nsf_whisper_decoder_prefill_cross(nsf_whisper_decoder* h, const v
     return NSF_OK;
 }
 
-struct WdRulesArgs { const nsf_whisper_rules* rules; const int32_t* suppress; const int32_t* suppress_first; const int32_t* tokens; int total_len; };
+struct WdRulesArgs {
+    const nsf_whisper_rules* rules; const int32_t* suppress; const int32_t* suppress_first; const int32_t* tokens; int total_len;
+    float* probs; const int32_t* align_map; int n_align;        // optional capture of the alignment heads' cross-attention rows
+};
 
 static int wd_step_impl(nsf_whisper_decoder* h, const int32_t* tokens, const int32_t* pos_dev, int n_batch, void* state, int64_t state_bytes,
                         float* logits_out, int32_t* next_tokens, cudaStream_t s, const WdRulesArgs* ra = nullptr) {
@@ -410,7 +424,9 @@ static int wd_step_impl(nsf_whisper_decoder* h, const int32_t* tokens, const int
         if ((rc = linear(st.h, d, h->l(L, WDL_WCQ), h->l(L, WDL_BCQ), d, EPI_STORE, st.qc, d))) return rc;
         { ProfScope prof(PROF_MVDR, 4.0 * bh * D.n_audio_ctx * 64 * 2.0 / 2.0, s);       // cross-attention cache reads (bytes), reported under "mvdr"
         wd_attn_kernel<false><<<(unsigned)bh, 256, attn_smem(D.n_audio_ctx), s>>>(st.qc, nullptr, nullptr, d,
-            st.ck + (size_t)L * bh * D.n_audio_ctx * 64, st.cv + (size_t)L * bh * D.n_audio_ctx * 64, D.n_audio_ctx, nullptr, D.n_audio_ctx, H, hb, d); }
+            st.ck + (size_t)L * bh * D.n_audio_ctx * 64, st.cv + (size_t)L * bh * D.n_audio_ctx * 64, D.n_audio_ctx, pos_dev, D.n_audio_ctx, H, hb, d,
+            (ra && ra->probs) ? ra->probs : nullptr, (ra && ra->probs) ? ra->align_map + (size_t)L * H : nullptr, ra ? ra->n_align : 0,
+            ra ? ra->total_len : 0); }
         if ((rc = check_launch("wd_attn_kernel<cross>"))) return rc;
         if ((rc = linear(st.h, d, h->l(L, WDL_WCO), h->l(L, WDL_BCO), d, EPI_RESID, st.x, d))) return rc;
         if ((rc = ln_launch(st.x, B, d, h->l(L, WDL_LN2_G), h->l(L, WDL_LN2_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
@@ -420,7 +436,7 @@ static int wd_step_impl(nsf_whisper_decoder* h, const int32_t* tokens, const int
     if ((rc = ln_launch(st.x, B, d, h->g(WD_LN_G), h->g(WD_LN_B), 0, nullptr, nullptr, nullptr, st.h, st.h, SPLIT_BF16_1, s))) return rc;
     float* lg = logits_out ? logits_out : st.logits;
     if ((rc = linear(st.h, d, h->g(WD_TOK_EMB), nullptr, D.vocab, EPI_STORE, lg, D.vocab))) return rc;
-    if (ra) {
+    if (ra && ra->rules) {
         wd_logit_rules_kernel<<<B, 1024, 0, s>>>(lg, D.vocab, ra->tokens, ra->total_len, pos_dev, *ra->rules, ra->suppress, ra->suppress_first);
         if ((rc = check_launch("wd_logit_rules_kernel"))) return rc;
     }
@@ -476,14 +492,16 @@ extern "C" int nsf_whisper_logit_rules(float* logits, int n_batch, int vocab, co
 extern "C" int nsf_whisper_decoder_step_rules(nsf_whisper_decoder* h, int32_t* cur_tokens, int32_t* pos_dev, int n_batch, void* state,
                                               int64_t state_bytes, const int32_t* forced, int total_len, int eot, int32_t* out_tokens,
                                               int32_t* argmaxes, uint8_t* done, const nsf_whisper_rules* rules, const int32_t* suppress,
-                                              const int32_t* suppress_first, void* stream_) {
+                                              const int32_t* suppress_first, float* xattn_probs, const int32_t* align_map, int n_align,
+                                              void* stream_) {
     NSF_REQUIRE(h && cur_tokens && pos_dev && state && out_tokens && argmaxes && done, "nsf_whisper_decoder_step_rules: null pointer");
     NSF_REQUIRE(n_batch >= 1 && total_len >= 1 && total_len <= h->dims.n_text_ctx, "nsf_whisper_decoder_step_rules: bad sizes");
-    int rc = wd_check_rules(rules, suppress, suppress_first, h->dims.vocab);
+    NSF_REQUIRE(!xattn_probs || (align_map && n_align >= 1), "nsf_whisper_decoder_step_rules: capture needs the alignment-head map");
+    int rc = rules ? wd_check_rules(rules, suppress, suppress_first, h->dims.vocab) : NSF_OK;
     if (rc) return rc;
     WdState st = wd_carve(h->dims, n_batch, reinterpret_cast<unsigned char*>(state));
     cudaStream_t s = (cudaStream_t)stream_;
-    const WdRulesArgs ra = {rules, suppress, suppress_first, out_tokens, total_len};
+    const WdRulesArgs ra = {rules, suppress, suppress_first, out_tokens, total_len, xattn_probs, align_map, n_align};
     if ((rc = wd_step_impl(h, cur_tokens, pos_dev, n_batch, state, state_bytes, nullptr, st.next, s, &ra))) return rc;
     wd_advance_kernel<<<1, 1024, 0, s>>>(st.next, forced, total_len, eot, cur_tokens, out_tokens, argmaxes, done, pos_dev, n_batch);
     return check_launch("wd_advance_kernel");

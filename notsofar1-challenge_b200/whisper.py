@@ -342,6 +342,27 @@ def apply_logit_rules(logits: torch.Tensor, tokens: torch.Tensor, sample_begin: 
     return out
 
 
+def token_alignment(weights: torch.Tensor, m_valid: Optional[int] = None, n_tokens: Optional[torch.Tensor] = None, return_cost: bool = False):
+    """weights [B, A, N, M] f32 cuda: cross-attention softmax rows of the A alignment heads for the N token positions to align
+    (``decode_greedy(..., align_heads=...)`` captures them) -> start_frame int32 [B, N]: the audio position (20 ms units) at which
+    the DTW path enters each token (whisper/timing.py::find_alignment [upstream]; nsf_whisper_alignment)."""
+    if not (weights.is_cuda and weights.dtype == torch.float32 and weights.dim() == 4):
+        raise _cabi.NsfError("token_alignment needs a float32 CUDA tensor [B, A, N, M]; there is no CPU path")
+    lib = _cabi.load()
+    w = weights.contiguous()
+    B, A, N, M = w.shape
+    mv = M if m_valid is None else int(m_valid)
+    need = int(lib.nsf_whisper_alignment_workspace_bytes(B, A, N, M))
+    ws = torch.empty(need, dtype=torch.uint8, device=w.device)
+    out = torch.zeros((B, N), dtype=torch.int32, device=w.device)
+    cost = torch.empty((B, N, mv), dtype=torch.float32, device=w.device) if return_cost else None
+    nt = None if n_tokens is None else n_tokens.to(device=w.device, dtype=torch.int32).contiguous()
+    with torch.cuda.device(w.device):
+        _cabi.check(lib.nsf_whisper_alignment(_cabi.ptr(w), B, A, N, M, mv, _cabi.ptr(nt), _cabi.ptr(out), _cabi.ptr(cost), _cabi.ptr(ws), need,
+                                              _cabi.stream_ptr()), "nsf_whisper_alignment")
+    return (out, cost) if return_cost else out
+
+
 class WhisperB200:
     """Encoder + greedy decoder of one Whisper model on one B200: audio chunks in, token ids out.
 
@@ -391,12 +412,14 @@ class WhisperB200:
 
     @torch.no_grad()
     def decode_greedy(self, enc_bf16: torch.Tensor, prompt, max_new_tokens: int = 224, eot: Optional[int] = None,
-                      forced_tokens: Optional[torch.Tensor] = None, return_logits: bool = False, rules: Optional["WhisperRules"] = None):
+                      forced_tokens: Optional[torch.Tensor] = None, return_logits: bool = False, rules: Optional["WhisperRules"] = None,
+                      align_heads=None):
         """enc_bf16 int16 [B, 1500, d] (from ``encode``).  prompt: list of token ids fed first.  Returns tokens int32
         [B, len(prompt) + n_new] (and the fp32 logits of every step if return_logits).  forced_tokens [B, n]: teacher forcing
         (the arg-max is still computed and returned, the forced token is fed) -- used by the parity tests.  rules: logit filters
         (timestamp rules, suppressed tokens) applied on the device between the logits and the arg-max of every sampled position
-        (graph path only)."""
+        (graph path only).  align_heads: [(layer, head), ...] -- the cross-attention softmax rows of these heads are captured
+        for every position; returns (tokens, probs [B, n_heads, total, 1500]) for ``token_alignment`` (word timestamps)."""
         B = enc_bf16.shape[0]
         D = self.dec_dims
         need = self._ensure_state(B)
@@ -409,7 +432,9 @@ class WhisperB200:
             if rules is not None and return_logits:
                 raise _cabi.NsfError("decode_greedy: rules are applied inside the graph-replayed step; return_logits is the unfiltered test path")
             if not return_logits:
-                return self._decode_graph(B, need, prompt, total, eot, forced_tokens, rules)
+                return self._decode_graph(B, need, prompt, total, eot, forced_tokens, rules, align_heads)
+            if align_heads is not None:
+                raise _cabi.NsfError("decode_greedy: align_heads is captured by the graph-replayed step, not with return_logits")
             tokens = torch.zeros((B, total), dtype=torch.int32, device=self.device)
             tokens[:, :n_prompt] = torch.tensor(prompt, dtype=torch.int32, device=self.device)
             nxt = torch.empty((B,), dtype=torch.int32, device=self.device)
@@ -439,7 +464,7 @@ class WhisperB200:
         return tokens
 
     def _decode_graph(self, B: int, need: int, prompt, total: int, eot: Optional[int], forced_tokens: Optional[torch.Tensor],
-                      rules: Optional["WhisperRules"] = None):
+                      rules: Optional["WhisperRules"] = None, align_heads=None):
         """The decode loop as replays of ONE captured CUDA graph: position, current tokens, done flags and the token record
         live on the device (nsf_whisper_decoder_step_dev), so every step launches the same ~450 kernels with the same
         arguments."""
@@ -447,7 +472,8 @@ class WhisperB200:
         n_prompt = len(prompt)
         rkey = None if rules is None else (n_prompt, rules.eot, rules.timestamp_begin, rules.no_timestamps, rules.max_initial_timestamp_index,
                                            tuple(rules.suppress), tuple(rules.suppress_first))
-        key = (B, total, self._state.data_ptr(), rkey)
+        akey = None if align_heads is None else tuple((int(l), int(h)) for l, h in align_heads)
+        key = (B, total, self._state.data_ptr(), rkey, akey)
         if getattr(self, "_graphs", None) is None:
             self._graphs = {}
         if key not in self._graphs:
@@ -459,12 +485,22 @@ class WhisperB200:
             rdev = rules.to_device(n_prompt, dev) if rules is not None else None
             bufs["rules"] = rdev                                  # keeps the device lists alive as long as the graph
 
+            if akey is not None:
+                D = self.dec_dims
+                amap = torch.full((D.n_layers, D.n_heads), -1, dtype=torch.int32)
+                for slot, (l, h) in enumerate(akey):
+                    amap[l, h] = slot
+                bufs["amap"] = amap.to(dev)
+                bufs["probs"] = torch.zeros((B, len(akey), total, D.n_audio_ctx), dtype=torch.float32, device=dev)
+
             def launch(eot_val):
-                if rdev is not None:
+                if rdev is not None or akey is not None:
                     _cabi.check(self._lib.nsf_whisper_decoder_step_rules(
                         self._dh, _cabi.ptr(bufs["cur"]), _cabi.ptr(bufs["pos"]), B, _cabi.ptr(self._state), need, _cabi.ptr(bufs["forced"]), total,
-                        eot_val, _cabi.ptr(bufs["out"]), _cabi.ptr(bufs["arg"]), _cabi.ptr(bufs["done"]), C.byref(rdev[0]), _cabi.ptr(rdev[1]),
-                        _cabi.ptr(rdev[2]), _cabi.stream_ptr()), "nsf_whisper_decoder_step_rules")
+                        eot_val, _cabi.ptr(bufs["out"]), _cabi.ptr(bufs["arg"]), _cabi.ptr(bufs["done"]),
+                        C.byref(rdev[0]) if rdev is not None else None, _cabi.ptr(rdev[1]) if rdev is not None else None,
+                        _cabi.ptr(rdev[2]) if rdev is not None else None, _cabi.ptr(bufs.get("probs")), _cabi.ptr(bufs.get("amap")),
+                        len(akey) if akey is not None else 0, _cabi.stream_ptr()), "nsf_whisper_decoder_step_rules")
                     return
                 _cabi.check(self._lib.nsf_whisper_decoder_step_dev(
                     self._dh, _cabi.ptr(bufs["cur"]), _cabi.ptr(bufs["pos"]), B, _cabi.ptr(self._state), need, _cabi.ptr(bufs["forced"]), total,
@@ -491,6 +527,8 @@ class WhisperB200:
             n = min(forced_tokens.shape[1], total - n_prompt)
             bufs["forced"][:, n_prompt:n_prompt + n] = forced_tokens[:, :n]
         bufs["out"].zero_(); bufs["arg"].zero_(); bufs["done"].zero_(); bufs["pos"].zero_()
+        if "probs" in bufs:
+            bufs["probs"].zero_()
         bufs["out"][:, 0] = prompt[0]
         bufs["cur"].fill_(prompt[0])
         steps = total - 1
@@ -499,4 +537,6 @@ class WhisperB200:
             if eot is not None and forced_tokens is None and (i + 1) % 16 == 0 and i + 1 >= n_prompt and bool(bufs["done"].all()):
                 steps = i + 1
                 break
+        if akey is not None:
+            return bufs["out"][:, :steps + 1].clone(), bufs["probs"][:, :, :steps + 1].clone()
         return bufs["out"][:, :steps + 1].clone()

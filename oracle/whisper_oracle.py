@@ -129,3 +129,62 @@ def apply_logit_rules(logits: np.ndarray, tokens: np.ndarray, sample_begin: int,
         if ts_lp > logprobs[:tb].max():
             lg[k, :tb] = -np.inf
     return lg
+
+
+def median_filter(x: np.ndarray, width: int = 7) -> np.ndarray:
+    """whisper/timing.py::median_filter [upstream]: median of `width` along the last axis, reflect padding; inputs not longer
+    than width // 2 are returned unchanged."""
+    pad = width // 2
+    if x.shape[-1] <= pad:
+        return x
+    xp = np.pad(x, [(0, 0)] * (x.ndim - 1) + [(pad, pad)], mode="reflect")
+    win = np.lib.stride_tricks.sliding_window_view(xp, width, axis=-1)
+    return np.sort(win, axis=-1)[..., pad]
+
+
+def dtw(cost: np.ndarray):
+    """whisper/timing.py::dtw_cpu + backtrace [upstream]: fp32 accumulated cost, ties resolved diagonal < up < left as there.
+    cost [N, M] -> (text_indices, time_indices) of the monotone path."""
+    N, M = cost.shape
+    D = np.full((N + 1, M + 1), np.inf, np.float32)
+    T = -np.ones((N + 1, M + 1), np.int8)
+    D[0, 0] = 0
+    x = cost.astype(np.float32)
+    for j in range(1, M + 1):
+        for i in range(1, N + 1):
+            c0, c1, c2 = D[i - 1, j - 1], D[i - 1, j], D[i, j - 1]
+            if c0 < c1 and c0 < c2:
+                c, t = c0, 0
+            elif c1 < c0 and c1 < c2:
+                c, t = c1, 1
+            else:
+                c, t = c2, 2
+            D[i, j] = x[i - 1, j - 1] + c
+            T[i, j] = t
+    i, j = N, M
+    T[0, :] = 2
+    T[:, 0] = 1
+    ti, tj = [], []
+    while i > 0 or j > 0:
+        ti.append(i - 1)
+        tj.append(j - 1)
+        if T[i, j] == 0:
+            i, j = i - 1, j - 1
+        elif T[i, j] == 1:
+            i -= 1
+        else:
+            j -= 1
+    return np.asarray(ti)[::-1], np.asarray(tj)[::-1]
+
+
+def alignment(weights: np.ndarray, m_valid: int):
+    """whisper/timing.py::find_alignment, numeric core [upstream]: weights [A, N, M] (softmax cross-attention rows of the
+    alignment heads for the N tokens to align) -> (cost [N, m_valid] float32, start_frame [N]): crop to m_valid audio positions,
+    normalise over the tokens (population std), median filter 7, mean over the heads, dtw(-matrix), first audio position of
+    every token on the path (jump_times = start_frame / 50 s)."""
+    w = np.asarray(weights, np.float32)[..., :m_valid]
+    w = (w - w.mean(-2, keepdims=True)) / w.std(-2, keepdims=True)
+    cost = -median_filter(w, 7).mean(0)
+    ti, tj = dtw(cost)
+    jumps = np.pad(np.diff(ti), (1, 0), constant_values=1).astype(bool)
+    return cost.astype(np.float32), tj[jumps]

@@ -309,3 +309,86 @@ def test_greedy_decode_with_timestamp_rules_matches_host_loop():
         assert seq[0] >= _TB and seq[0] <= _TB + 50                                      # starts with a timestamp within max_initial
         ts = [x for x in seq if x >= _TB]
         assert ts == sorted(ts) and _NOTS not in seq and 1 not in seq and 2 not in seq
+
+
+# ------------------------------------------------------------------------------------------------ token timestamps (DTW)
+def test_alignment_oracle_vs_transformers_functions():
+    """median filter and dynamic time warping of oracle/whisper_oracle.py against transformers' `_median_filter` /
+    `_dynamic_time_warping` (ports of whisper/timing.py)."""
+    from transformers.models.whisper.generation_whisper import _median_filter, _dynamic_time_warping
+    rng = np.random.default_rng(0)
+    for shape in [(2, 3, 5, 40), (1, 2, 4, 7), (1, 1, 3, 3)]:
+        x = rng.standard_normal(shape).astype(np.float32)
+        assert np.array_equal(WO.median_filter(x, 7), _median_filter(torch.from_numpy(x), 7).numpy())
+    for N, M in [(5, 30), (12, 12), (1, 9), (20, 64)]:
+        c = rng.standard_normal((N, M)).astype(np.float32)
+        a, b = WO.dtw(c)
+        ra, rb = _dynamic_time_warping(c)
+        assert np.array_equal(a, ra) and np.array_equal(b, rb)
+    w = rng.random((3, 6, 50)).astype(np.float32)
+    cost, start = WO.alignment(w, 44)
+    assert cost.shape == (6, 44) and len(start) == 6 and (np.diff(start) >= 0).all() and start[0] == 0
+
+
+@pytest.mark.gpu
+def test_alignment_kernels_vs_oracle():
+    from notsofar_b200.whisper import token_alignment
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    B, A, N, M, mv = 3, 4, 17, 120, 101
+    logits = rng.standard_normal((B, A, N, M)) * 2 + 4 * np.exp(-0.5 * ((np.arange(M)[None, :] - np.linspace(5, 95, N)[:, None]) / 4.0) ** 2)
+    w = np.exp(logits)
+    w = (w / w.sum(-1, keepdims=True)).astype(np.float32)
+    n_tok = np.asarray([17, 9, 1], np.int32)
+    start, cost = token_alignment(torch.from_numpy(w).to(dev), mv, torch.from_numpy(n_tok).to(dev), return_cost=True)
+    start, cost = start.cpu().numpy(), cost.cpu().numpy()
+    for b in range(B):
+        n = int(n_tok[b])
+        ref_cost, ref_start = WO.alignment(w[b, :, :n], mv)
+        if n > 1:
+            assert rel_l2(cost[b, :n], ref_cost) < 1e-5
+        # the path is a chain of float comparisons: compare it exactly on the device's own cost matrix, and with the oracle's
+        ti, tj = WO.dtw(cost[b, :n])
+        jumps = np.pad(np.diff(ti), (1, 0), constant_values=1).astype(bool)
+        assert np.array_equal(start[b, :n], tj[jumps]), b
+        if n > 1:
+            assert np.abs(start[b, :n] - ref_start).max() <= 1
+    # a diagonal ridge is followed: token n starts near audio position 5 + 90 n / (N - 1)
+    assert np.abs(start[0] - np.linspace(5, 95, N)).max() < 8
+
+
+@pytest.mark.gpu
+def test_cross_attention_capture_and_token_times():
+    """Cross-attention rows captured by the decode step == transformers' cross_attentions of the same (teacher-forced) tokens for
+    the chosen alignment heads; the alignment kernels then run on them."""
+    from notsofar_b200.whisper import WhisperB200, token_alignment
+    dev = torch.device("cuda", 0)
+    m = _hf_full(128, 2, 2, 256, 80, 500)
+    if hasattr(m, "set_attn_implementation"):
+        m.set_attn_implementation("eager")                   # sdpa does not return attention weights
+    else:
+        m.config._attn_implementation = "eager"
+    wb = WhisperB200(m.state_dict(), device=dev)
+    rng = np.random.default_rng(11)
+    B, n_new = 2, 9
+    mel = (rng.standard_normal((B, 80, 3000)) * 0.5).astype(np.float32)
+    t = torch.zeros((B, 3002, 80), dtype=torch.float32, device=dev)
+    t[:, 1:3001] = torch.from_numpy(mel).to(dev).transpose(1, 2)
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    enc32, enc16 = wb.encode(hi.view(torch.int16).contiguous(), lo.view(torch.int16).contiguous())
+    prompt = [3, 5, 7]
+    forced = torch.from_numpy(rng.integers(4, 500, size=(B, n_new)).astype(np.int32)).to(dev)
+    heads = [(0, 1), (1, 0), (1, 1)]
+    tokens, probs = wb.decode_greedy(enc16, prompt, max_new_tokens=n_new, forced_tokens=forced, align_heads=heads)
+    tok = tokens.cpu().long()
+    with torch.no_grad():
+        out = m.model.decoder(input_ids=tok[:, :-1], encoder_hidden_states=enc32.cpu(), output_attentions=True)
+    got = probs.cpu().numpy()                                                            # [B, 3, total, 1500]
+    n_pos = tok.shape[1] - 1
+    for a, (l, h) in enumerate(heads):
+        ref = out.cross_attentions[l][:, h].numpy()                                      # [B, n_pos, 1500]
+        assert rel_l2(got[:, a, :n_pos], ref) < 3e-2, (l, h, rel_l2(got[:, a, :n_pos], ref))
+        np.testing.assert_allclose(got[:, a, :n_pos].sum(-1), 1.0, atol=1e-4)
+    start = token_alignment(probs[:, :, len(prompt):n_pos].contiguous(), 1500).cpu().numpy()
+    assert start.shape == (B, n_pos - len(prompt)) and (np.diff(start, axis=1) >= 0).all() and (start >= 0).all() and (start < 1500).all()
