@@ -342,6 +342,43 @@ def apply_logit_rules(logits: torch.Tensor, tokens: torch.Tensor, sample_begin: 
     return out
 
 
+def split_segments(tokens, timestamp_begin: int, time_offset: float, segment_size: int, time_precision: float = 0.02,
+                   input_stride: int = 2, hop_seconds: float = 0.01):
+    """One decoded 30-s window -> (segments, frames to advance the seek by): the segmentation rule of whisper/transcribe.py's
+    main loop [upstream, restated; openai-whisper is absent offline, so this host logic is checked by hand-built cases only].
+    ``tokens``: the sampled ids of the window (sot sequence and eot stripped); ``segment_size``: mel frames of the window
+    (min(3000, frames left)).  Consecutive timestamp pairs <|t1|><|t2|> cut the window into segments [t_start, t_end]; a window
+    ending on a single timestamp is consumed whole, otherwise the seek moves to the last closed timestamp and the unfinished
+    tail is decoded again; a window without pairs is one segment ending at its last timestamp (or at the window end)."""
+    tok = [int(t) for t in tokens]
+    is_ts = [t >= timestamp_begin for t in tok]
+    single_timestamp_ending = is_ts[-2:] == [False, True]
+    consecutive = [i + 1 for i in range(len(tok) - 1) if is_ts[i] and is_ts[i + 1]]
+    segments = []
+    if consecutive:
+        slices = list(consecutive)
+        if single_timestamp_ending:
+            slices.append(len(tok))
+        last = 0
+        for cur in slices:
+            sl = tok[last:cur]
+            segments.append(dict(start=time_offset + (sl[0] - timestamp_begin) * time_precision,
+                                 end=time_offset + (sl[-1] - timestamp_begin) * time_precision, tokens=sl))
+            last = cur
+        if single_timestamp_ending:
+            advance = segment_size                         # no speech after the last timestamp
+        else:
+            advance = (tok[last - 1] - timestamp_begin) * input_stride
+    else:
+        duration = segment_size * hop_seconds
+        ts = [t for t in tok if t >= timestamp_begin]
+        if ts and ts[-1] != timestamp_begin:
+            duration = (ts[-1] - timestamp_begin) * time_precision
+        segments.append(dict(start=time_offset, end=time_offset + duration, tokens=tok))
+        advance = segment_size
+    return segments, advance
+
+
 def token_alignment(weights: torch.Tensor, m_valid: Optional[int] = None, n_tokens: Optional[torch.Tensor] = None, return_cost: bool = False):
     """weights [B, A, N, M] f32 cuda: cross-attention softmax rows of the A alignment heads for the N token positions to align
     (``decode_greedy(..., align_heads=...)`` captures them) -> start_frame int32 [B, N]: the audio position (20 ms units) at which

@@ -392,3 +392,28 @@ def test_cross_attention_capture_and_token_times():
         np.testing.assert_allclose(got[:, a, :n_pos].sum(-1), 1.0, atol=1e-4)
     start = token_alignment(probs[:, :, len(prompt):n_pos].contiguous(), 1500).cpu().numpy()
     assert start.shape == (B, n_pos - len(prompt)) and (np.diff(start, axis=1) >= 0).all() and (start >= 0).all() and (start < 1500).all()
+
+
+def test_split_segments_known_answers():
+    """The window -> segments / seek rule of whisper/transcribe.py [upstream, restated] on hand-built token streams
+    (timestamp_begin = 1000: token 1000 + k is <|k * 0.02 s|>)."""
+    from notsofar_b200.whisper import split_segments
+    TB = 1000
+    ts = lambda sec: TB + int(round(sec / 0.02))
+    # two closed segments and an unfinished third one: the seek moves to the last closed timestamp (12.0 s = 600 positions * 2 frames)
+    tok = [ts(0.0), 5, 6, ts(4.0), ts(4.5), 7, ts(12.0), ts(12.0), 8, 9]
+    segs, adv = split_segments(tok, TB, 30.0, 3000)
+    assert [(round(s["start"], 2), round(s["end"], 2)) for s in segs] == [(30.0, 34.0), (34.5, 42.0)]
+    assert segs[0]["tokens"] == [ts(0.0), 5, 6, ts(4.0)] and segs[1]["tokens"] == [ts(4.5), 7, ts(12.0)]
+    assert adv == 600 * 2
+    # the window ends on a single timestamp: the tail is a segment too and the whole window is consumed
+    tok = [ts(0.0), 5, ts(2.0), ts(2.0), 6, ts(29.0)]
+    segs, adv = split_segments(tok, TB, 0.0, 3000)
+    assert [(s["start"], round(s["end"], 2)) for s in segs] == [(0.0, 2.0), (2.0, 29.0)] and adv == 3000
+    # no consecutive pair: one segment up to the last timestamp; without any usable timestamp, up to the window end
+    segs, adv = split_segments([ts(0.0), 5, 6, ts(7.5)], TB, 60.0, 3000)
+    assert len(segs) == 1 and (segs[0]["start"], segs[0]["end"]) == (60.0, 67.5) and adv == 3000
+    segs, adv = split_segments([5, 6, 7], TB, 0.0, 1234)
+    assert (segs[0]["start"], round(segs[0]["end"], 2)) == (0.0, 12.34) and adv == 1234
+    segs, adv = split_segments([ts(0.0), 5], TB, 0.0, 3000)
+    assert round(segs[0]["end"], 2) == 30.0 and adv == 3000                  # only <|0.00|>: not a usable end
