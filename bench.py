@@ -309,7 +309,7 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
                         "h2d_bytes_per_step": int(n_total * 7 * 4 + (world - 1) * (plan.segment_frames + 1) * 256 * 7 * 4),
                         "d2h_bytes_per_step": int(3 * (n_out + 256 * (world - 1)) * 4 + plan.num_segments * 36 * world),
                         "d2h": "every rank reads its own samples (pieces overlap by one 256-sample seam); the NVLink gather to rank 0 is inside the step"},
-                "gpu_launches": int(t[2].item()),
+                "gpu_launches": int(t[2].item()) * args.steps, "gpu_launches_per_step": int(t[2].item()),
                 "roofline": roofline, "kernels": kernels}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
@@ -440,7 +440,7 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": d2h_bytes + plan.num_segments * 36},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
                 "roofline": roofline, "kernels": kernels}
         if world == 1 and not args.no_cpu_baseline:
             sl = x_np[: int(args.cpu_seconds * FS)]
