@@ -93,6 +93,17 @@ def test_nmesc_spectral_clustering_recovers_blobs(sizes):
     assert torch.allclose(L.sum(1), torch.zeros(len(truth)), atol=1e-5)
 
 
+@pytest.mark.parametrize("n", [2, 3, 5, 40, 1100])
+def test_clustering_degenerate_sizes(n):
+    """Tiny sessions (a handful of words) and more words than NeMo's 512-point search matrix: labels for every word, no crash."""
+    import torch
+    import notsofar_b200.clustering as K
+    rng = np.random.default_rng(n)
+    a = torch.from_numpy(O.cos_affinity(rng.standard_normal((n, 16)))).float()
+    labels = K.run_clustering(a)
+    assert labels.shape == (n,) and labels.min() >= 0 and labels.max() < 8
+
+
 def test_kneighbors_graph_small_known_answer():
     import torch
     import notsofar_b200.clustering as K
