@@ -57,6 +57,34 @@ def test_pack_matches_plan():
     assert lib.nsf_titanet_workspace_bytes(C.byref(dims), 4, 32) > 0
 
 
+def test_checkpoint_loader_nemo_archive_and_plain_file(tmp_path):
+    """load_titanet_state_dict: a .nemo archive (tar with model_weights.ckpt) and a plain torch state-dict file; classifier /
+    preprocessor entries are dropped, the block structure is recovered from the names."""
+    import tarfile
+    import torch
+    import notsofar_b200.titanet as T
+    w = O.random_weights(3, blocks=SMALL, att_ch=32, emb=16)
+    sd = {k: torch.from_numpy(v) for k, v in w.items()}
+    sd["decoder.final.weight"] = torch.zeros(10, 16)                       # classifier: kept under decoder.*, unused by the packer
+    sd["preprocessor.featurizer.window"] = torch.zeros(400)
+    ck = tmp_path / "model_weights.ckpt"
+    torch.save(sd, ck)
+    arch = tmp_path / "m.nemo"
+    with tarfile.open(arch, "w:gz") as tar:
+        tar.add(ck, arcname="./model_weights.ckpt")
+    for path in (arch, ck):
+        got = T.load_titanet_state_dict(str(path))
+        assert "preprocessor.featurizer.window" not in got and set(w) <= set(got)
+        assert T.infer_blocks(got) == SMALL
+        dims, blob, offs = T.pack_titanet(got, T.infer_blocks(got))
+        assert (dims.feat_in, dims.n_blocks, dims.att_ch, dims.emb) == (80, len(SMALL), 32, 16)
+    bad = tmp_path / "empty.nemo"
+    with tarfile.open(bad, "w") as tar:
+        tar.add(__file__, arcname="readme.txt")
+    with pytest.raises(T._cabi.NsfError):
+        T.load_titanet_state_dict(str(bad))
+
+
 def test_cos_affinity_oracle():
     rng = np.random.default_rng(1)
     e = rng.standard_normal((7, 16))
