@@ -15,7 +15,6 @@ folded into scale/shift.
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Dict, Optional
 
 import numpy as np

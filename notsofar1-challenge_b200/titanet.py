@@ -9,7 +9,7 @@ getCosAffinityMatrix + mean of :171-177 on the GPU.  ``as_embedding_backend`` pl
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, Optional, Sequence, Tuple
 
 import numpy as np
 import torch

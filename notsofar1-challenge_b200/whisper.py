@@ -10,7 +10,6 @@ plug-in point for a complete transcriber.
 from __future__ import annotations
 
 import ctypes as C
-import math
 from typing import Dict, Optional
 
 import numpy as np

@@ -5,7 +5,6 @@ Inputs follow SURVEY 8d: mix ~ CN(0,1) with a per-bin rank-1 + identity spatial 
 Run on a B200: python tools/bench_mvdr.py"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 from notsofar_b200 import _cabi
 

@@ -5,7 +5,6 @@ measured bf16 peak, audio-seconds per second, and the per-kernel-class split fro
     python tools/bench_whisper_encoder.py [n_chunks=64] [--audio]   (--audio: include the log-mel front end)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
 import torch
 from notsofar_b200 import _cabi
 from notsofar_b200.whisper import WhisperEncoderB200
