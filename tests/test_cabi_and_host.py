@@ -43,6 +43,25 @@ def test_library_argument_errors_without_gpu(N):
     dims = N._cabi.ConformerDims(d_model=100, n_heads=8, d_ff=1024, n_blocks=18, kernel_size=33, in_features=1799,
                                  n_out=1028, maxlen=1000, T=186, gemm_engine=1)
     assert lib.nsf_conformer_num_offsets(dims) == 12 + 32 * 18
+    # the entry points added for the diarization / ASR rows validate their arguments before touching the device
+    import ctypes as C
+    from notsofar_b200.titanet import TitanetDims
+    from notsofar_b200.whisper import _RulesStruct
+    td = TitanetDims()
+    td.feat_in, td.n_blocks, td.att_ch, td.emb = 80, 2, 128, 192
+    td.filters[0], td.repeat[0], td.kernel[0], td.residual[0] = 1024, 1, 3, 0
+    td.filters[1], td.repeat[1], td.kernel[1], td.residual[1] = 1024, 3, 7, 1
+    assert lib.nsf_titanet_num_offsets(C.byref(td)) == (4 * 1 + 2) + (4 * 3 + 2 + 3) + 11
+    assert lib.nsf_titanet_workspace_bytes(C.byref(td), 8, 64) > 8 * 64 * 1024 * 4
+    td.kernel[1] = 8                                                       # even kernel: unsupported
+    assert lib.nsf_titanet_num_offsets(C.byref(td)) == 0 and lib.nsf_titanet_workspace_bytes(C.byref(td), 8, 64) == 0
+    assert lib.nsf_titanet_features(None, None, 1, 100, 16, None, 80, None, None, None, None, None) == -1
+    assert b"null" in lib.nsf_last_error()
+    assert lib.nsf_cos_affinity_accum(None, 192, 192, 5, 1.0, None, None, None, None, None) == -1
+    assert lib.nsf_whisper_alignment_workspace_bytes(2, 3, 10, 1500) >= 2 * 11 * 1501 * 5 and lib.nsf_whisper_alignment_workspace_bytes(0, 3, 10, 1500) == 0
+    assert lib.nsf_whisper_alignment(None, 1, 1, 1, 1, 1, None, None, None, None, 0, None) == -1
+    r = _RulesStruct(0, 450, 449, 400, -1, 0, 0)                            # sample_begin 0: invalid
+    assert lib.nsf_whisper_logit_rules(None, 1, 600, None, 4, None, C.byref(r), None, None, None) == -1
 
 
 def test_sass_has_blackwell_tensor_core_and_tma_instructions(N):
