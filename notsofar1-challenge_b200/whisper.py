@@ -378,6 +378,33 @@ def split_segments(tokens, timestamp_begin: int, time_offset: float, segment_siz
     return segments, advance
 
 
+def transcribe_windows(content_frames: int, decode_window, timestamp_begin: int, eot: int, n_frames: int = N_FRAMES,
+                       hop_seconds: float = HOP / 16000.0):
+    """The seek loop of whisper/transcribe.py [upstream, restated] over one recording of ``content_frames`` mel frames:
+    ``decode_window(seek, segment_size)`` returns the sampled token ids of the 30-s window that starts at mel frame ``seek``
+    (e.g. ``WhisperB200.decode_greedy`` with ``WhisperRules``); the window is cut into segments by ``split_segments`` and the
+    seek advances to the last closed timestamp (a whole window when it ends on a single timestamp or holds no pair).
+    Returns the segments (dicts with start / end seconds, tokens, seek).  Windows depend on each other through the seek, so
+    the loop is sequential per stream; streams and sessions batch across it."""
+    seek, out = 0, []
+    while seek < content_frames:
+        segment_size = min(n_frames, content_frames - seek)
+        tokens = []
+        for t in decode_window(seek, segment_size):
+            if int(t) == eot:
+                break
+            tokens.append(int(t))
+        if not tokens:
+            seek += segment_size
+            continue
+        segs, advance = split_segments(tokens, timestamp_begin, seek * hop_seconds, segment_size, hop_seconds=hop_seconds)
+        for sg in segs:
+            if any(t < timestamp_begin for t in sg["tokens"]):            # segments without text carry nothing
+                out.append(dict(sg, seek=seek))
+        seek += advance if advance > 0 else segment_size                   # a window closed at <|0.00|> must not stall the loop
+    return out
+
+
 def token_alignment(weights: torch.Tensor, m_valid: Optional[int] = None, n_tokens: Optional[torch.Tensor] = None, return_cost: bool = False):
     """weights [B, A, N, M] f32 cuda: cross-attention softmax rows of the A alignment heads for the N token positions to align
     (``decode_greedy(..., align_heads=...)`` captures them) -> start_frame int32 [B, N]: the audio position (20 ms units) at which

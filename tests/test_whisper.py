@@ -417,3 +417,29 @@ def test_split_segments_known_answers():
     assert (segs[0]["start"], round(segs[0]["end"], 2)) == (0.0, 12.34) and adv == 1234
     segs, adv = split_segments([ts(0.0), 5], TB, 0.0, 3000)
     assert round(segs[0]["end"], 2) == 30.0 and adv == 3000                  # only <|0.00|>: not a usable end
+
+
+def test_transcribe_windows_seek_loop():
+    """The sequential window loop over a 75-s recording with canned decodes: seeks follow the last closed timestamp, a window
+    ending on a single timestamp is consumed whole, empty windows are skipped."""
+    from notsofar_b200.whisper import transcribe_windows
+    TB, EOT = 1000, 900
+    ts = lambda sec: TB + int(round(sec / 0.02))
+    canned = {
+        0: [ts(0.0), 5, 6, ts(10.0), ts(10.0), 7, ts(22.0), ts(22.0), 8, EOT, 99],       # third segment unfinished -> seek to 22.0 s
+        2200: [ts(0.0), 8, 9, ts(6.0), EOT],                                             # single ending timestamp -> whole window
+        5200: [EOT],                                                                     # nothing decoded
+    }
+    seen = []
+
+    def decode(seek, size):
+        seen.append((seek, size))
+        return canned[seek]
+
+    segs = transcribe_windows(7500, decode, TB, EOT)
+    assert seen == [(0, 3000), (2200, 3000), (5200, 2300)]
+    assert [(round(s["start"], 2), round(s["end"], 2), s["seek"]) for s in segs] == [(0.0, 10.0, 0), (10.0, 22.0, 0), (22.0, 28.0, 2200)]
+    assert segs[2]["tokens"] == [ts(0.0), 8, 9, ts(6.0)]
+    # a degenerate decode that closes a pair at <|0.00|> cannot stall the loop
+    segs = transcribe_windows(3000, lambda seek, size: [ts(0.0), ts(0.0), 5, EOT], TB, EOT)
+    assert len(segs) <= 1
