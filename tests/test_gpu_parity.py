@@ -787,3 +787,110 @@ def test_masks_odd_network_shapes_vs_oracle(nb, dev, d_model, n_heads, engine_na
     err = rel_l2(m, ref)
     print(f"masks d_model={d_model} heads={n_heads} [{engine_name}]: rel_l2 vs oracle = {err:.3e}")
     assert err < TOL
+
+
+# ----------------------------------------------------------------------------------------------- production segment shape vs the reference
+T186_NET = dict(seed=3, d_model=128, n_heads=2, d_ff=256, n_blocks=2)
+
+
+@pytest.mark.parametrize("engine_name", ["2xbf16", "2xf16", "3xtf32", "simt"])
+def test_t186_masks_vs_reference_golden(nb, dev, golden_t186, engine_name):
+    """The mask network at the production segment length (T = 186: 128 + 58 row blocks of the fused attention, relative
+    positions over +-185) on the reference's own features, against the reference's own masks."""
+    w = O.random_weights(**T186_NET)
+    eng = ENGINES[engine_name]
+    sep = _sep(nb, w, dev, engine=eng)
+    feat = np.zeros((186, sep.ldf), np.float32)
+    ib, isc = w["executor.nnet.input_bias"].reshape(-1), w["executor.nnet.input_scale"].reshape(-1)
+    feat[:, :1799] = (golden_t186["net_feat0"] + ib) * isc                       # conformer.py:297-299
+    from notsofar_b200.separator import split_activations
+    hi, lo = split_activations(feat, eng)
+    m = sep.masks_from_features(torch.from_numpy(hi).to(dev), torch.from_numpy(lo).to(dev), 1, 186).cpu().numpy()[0]
+    ref = golden_t186["net_masks0"]
+    err = rel_l2(m, ref)
+    print(f"T=186 masks[{engine_name}] rel_l2 vs reference = {err:.3e}, max abs = {np.abs(m - ref).max():.3e}")
+    assert err < TOL
+
+
+def _from_audio_flip_accounting(nb, dev, x, feat_ref, masks_ref, w, T, label):
+    from conftest import ipd_flip_report
+    sep = _sep(nb, w, dev)
+    X = sep.stft_device(torch.from_numpy(x).to(dev))
+    raw, _ = sep.features(X, X.shape[1], 0, 1, T, T)
+    f = raw.cpu().numpy()[:, :1799]
+    flips, bins, worst = ipd_flip_report(f, feat_ref)
+    ib, isc = w["executor.nnet.input_bias"].reshape(-1), w["executor.nnet.input_scale"].reshape(-1)
+    from notsofar_b200.separator import split_activations
+
+    def run(ff):
+        feat = np.zeros((T, sep.ldf), np.float32)
+        feat[:, :1799] = (ff + ib) * isc
+        hi, lo = split_activations(feat, sep.gemm_engine)
+        return sep.masks_from_features(torch.from_numpy(hi).to(dev), torch.from_numpy(lo).to(dev), 1, T).cpu().numpy()[0]
+
+    m_dev = sep.masks(X, X.shape[1], 0, 1, T, T).cpu().numpy()[0]              # the product path: features + network on the device
+    m_al = run(np.where(flips, feat_ref, f))
+    print(f"{label}: from audio on the device, {int(flips.sum())} flipped IPD entries of {f.size} (bins {bins}); other entries "
+          f"max |diff| {worst:.2e}; masks vs reference as computed {rel_l2(m_dev, masks_ref):.2e} (max abs {np.abs(m_dev - masks_ref).max():.2e}), "
+          f"flips aligned {rel_l2(m_al, masks_ref):.2e} (max abs {np.abs(m_al - masks_ref).max():.2e})")
+    assert rel_l2(m_al, masks_ref) < TOL
+    if not flips.any():
+        assert rel_l2(m_dev, masks_ref) < TOL
+    return int(flips.sum())
+
+
+def test_from_audio_masks_flip_accounting(nb, dev, golden, golden_t186, small_weights):
+    """masks chained FROM THE AUDIO (device STFT -> device features -> device network) against the
+    reference's, with the IPD sign flips at the +-pi cut counted and located (conftest.ipd_flip_report); with the flipped
+    entries aligned the distance is < 1e-4, and where nothing flips the unmodified product path is < 1e-4 too."""
+    from conftest import t186_inputs
+    x186, _ = t186_inputs(golden_t186)
+    _from_audio_flip_accounting(nb, dev, x186, golden_t186["net_feat0"], golden_t186["net_masks0"], O.random_weights(**T186_NET), 186,
+                                "conditioned mixture, T=186")
+    _from_audio_flip_accounting(nb, dev, _mixture(golden), golden["feat0"], golden["masks"][0], small_weights,
+                                int(golden["segment_frames"]), "sample_data, T=61")
+
+
+def test_t186_mvdr_vs_reference_actual_output(nb, dev, golden_t186):
+    """nsf_mvdr at the production shape against what the reference's complex64 make_mvdr ACTUALLY returned (a fixture on
+    which it is 1e-6 from its own fp64 evaluation), from the device's own STFT of the audio."""
+    from conftest import t186_inputs
+    g = golden_t186
+    x, masks = t186_inputs(g)
+    sep = _sep(nb, O.random_weights(**T186_NET), dev)
+    X = sep.stft_device(torch.from_numpy(x).to(dev))
+    y = sep.mvdr(torch.from_numpy(masks[1:2].copy()).to(dev), X, T_valid=X.shape[1], seg_first=1, hop=93, mask_floor=1.0).cpu().numpy()[0]
+    e32, e64 = rel_l2(y, g["chain_mvdr"]), rel_l2(y, g["chain_mvdr64"])
+    per_bin = np.linalg.norm(y - g["chain_mvdr"], axis=(0, 2)) / np.linalg.norm(g["chain_mvdr"], axis=(0, 2))
+    print(f"T=186 MVDR segment 1: ours vs reference ACTUAL (complex64) {e32:.2e} (worst bin {per_bin.max():.2e}) | vs fp64 lift {e64:.2e} | "
+          f"reference fp32 vs fp64 {float(g['chain_mvdr_floor'][1]):.2e}")
+    assert e32 < TOL and e64 < TOL and per_bin.max() < TOL
+
+
+def test_t186_whole_chain_vs_reference_actual_waveforms(nb, dev, golden_t186):
+    """Same inputs -> the reference's outputs: the device path (STFT, MVDR, PIT costs + chain, WOLA, activity gate, iSTFT)
+    driven by a plug-in separator that returns the fixture's masks, against the waveforms / permutations / activity the
+    reference's separate_and_stitch ACTUALLY returned for them (tests/golden/make_golden_t186.py)."""
+    from conftest import t186_inputs
+    g = golden_t186
+    x, masks = t186_inputs(g)
+    masks_dev = torch.from_numpy(masks).to(dev)
+
+    class CannedMasks(nb.ConformerCssB200):
+        def masks(self, X, T_valid, seg_first, n_seg, T, hop, out=None):
+            out.copy_(masks_dev[seg_first:seg_first + n_seg])
+            return out
+
+    sep = CannedMasks(O.random_weights(**T186_NET), device=dev, segments_per_batch=3)
+    cfg = nb.CssCfg(activity_th=float(g["chain_activity_th"]), show_progressbar=False)
+    stages = {}
+    wavs, side = nb.separate_and_stitch(x[None], sep, 16000, dev, cfg, _stages=stages)
+    assert np.array_equal(stages["perms"][1:], g["chain_perms"])
+    assert np.array_equal(side["activity_b"].numpy(), g["chain_activity_b"])
+    assert np.array_equal(side["activity_final"].numpy(), g["chain_activity_final"])
+    assert np.abs(stages["activity"].cpu().numpy() - g["chain_activity"]).max() < 1e-6
+    errs = [rel_l2(wavs[k], g["chain_wavs"][k]) for k in range(3)]
+    print(f"T=186 chain: waveforms vs the reference's ACTUAL output {[f'{e:.2e}' for e in errs]} "
+          f"(reference fp32 MVDR vs its fp64 lift: {g['chain_mvdr_floor'].max():.2e})")
+    assert wavs[0].shape == g["chain_wavs"][0].shape
+    assert max(errs) < TOL

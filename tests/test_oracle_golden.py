@@ -171,3 +171,69 @@ def test_oracle_no_beamformer_modes_vs_reference(golden, golden_sc, mode):
     assert rel_l2(np.squeeze(side["mask_stitched"]), np.squeeze(g["mask_stitched"])) < 1e-4
     for k in range(3):
         assert rel_l2(wavs[k], g["wavs"][k]) < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- production segment shape
+def test_t186_network_vs_reference(golden_t186):
+    """The oracle's mask network at T = 186 on the reference's own features (tests/golden/make_golden_t186.py)."""
+    w = O.random_weights(seed=3, d_model=128, n_heads=2, d_ff=256, n_blocks=2)
+    m = O.conformer_masks(w, golden_t186["net_feat0"][None])[0]
+    assert m.shape == golden_t186["net_masks0"].shape == (4, 257, 186)
+    assert rel_l2(m, golden_t186["net_masks0"]) < 1e-5
+    assert np.abs(m - golden_t186["net_masks0"]).max() < 5e-5
+
+
+def test_t186_from_audio_features_and_flip_accounting(golden_t186):
+    """From the audio (not from the reference's STFT): features agree with the reference's except for IPD sign flips at the
+    +-pi cut in the real-valued DC / Nyquist bins; with those entries aligned the masks are within 1e-4."""
+    from conftest import t186_inputs, ipd_flip_report
+    x, _ = t186_inputs(golden_t186)
+    X = O.stft(x)
+    f = O.css_features(X[:, :186])
+    flips, bins, worst = ipd_flip_report(f, golden_t186["net_feat0"])
+    print(f"oracle from audio at T=186: {int(flips.sum())} flipped IPD entries of {f.size} in bins {bins}; other entries max |diff| {worst:.2e}")
+    assert worst < 1e-4
+    w = O.random_weights(seed=3, d_model=128, n_heads=2, d_ff=256, n_blocks=2)
+    m_raw = O.conformer_masks(w, f[None])[0]
+    f_al = np.where(flips, golden_t186["net_feat0"], f)
+    m_al = O.conformer_masks(w, f_al[None])[0]
+    ref = golden_t186["net_masks0"]
+    print(f"   masks vs reference: as computed {rel_l2(m_raw, ref):.2e} (max abs {np.abs(m_raw - ref).max():.2e}); "
+          f"flips aligned {rel_l2(m_al, ref):.2e} (max abs {np.abs(m_al - ref).max():.2e})")
+    assert rel_l2(m_al, ref) < 1e-4
+
+
+def test_t186_chain_vs_reference_actual_output(golden_t186):
+    """MVDR -> PIT chain -> WOLA -> gate -> iSTFT on a fixture where the reference's own complex64 beamformer is trustworthy
+    (1e-6 from its fp64 evaluation): the oracle in float32 against what the reference ACTUALLY returned."""
+    from conftest import t186_inputs
+    g = golden_t186
+    x, masks = t186_inputs(g)
+    assert g["chain_mvdr_floor"].max() < 1e-5
+    cfg = O.OracleCfg(activity_th=float(g["chain_activity_th"]))
+    for mvdr_dtype in (np.float32, np.float64):
+        wavs, side = O.separate_and_stitch(x[None], {}, 16000, cfg, masks_override=masks, mvdr_dtype=mvdr_dtype, return_stages=True)
+        assert np.array_equal(side["perms"][1:], g["chain_perms"])
+        assert np.array_equal(side["activity_b"], g["chain_activity_b"])
+        assert np.array_equal(side["activity_final"], g["chain_activity_final"])
+        for k in range(3):
+            assert rel_l2(wavs[k], g["chain_wavs"][k]) < 2e-5, (mvdr_dtype, k)
+    assert not np.array_equal(g["chain_perms"], np.tile(np.arange(3), (3, 1)))
+    assert 0.2 < g["chain_activity_b"].mean() < 0.8
+
+
+def test_from_audio_flip_accounting_on_real_audio(golden, small_weights):
+    """The same accounting on the reference's bundled recording (real audio: the DC / Nyquist bins carry negative real parts
+    and 1e-7 residues), 1-s segments: count of flipped IPD entries, where they are, and the mask distance to the reference
+    with and without them -- the chained "from audio" parity number VERDICT r1 weak #2 asks for."""
+    from conftest import ipd_flip_report
+    X = O.stft(_mixture(golden))
+    T = int(golden["segment_frames"])
+    f = O.css_features(X[:, :T])
+    flips, bins, worst = ipd_flip_report(f, golden["feat0"])
+    m_raw = O.conformer_masks(small_weights, f[None])[0]
+    m_al = O.conformer_masks(small_weights, np.where(flips, golden["feat0"], f)[None])[0]
+    ref = golden["masks"][0]
+    print(f"oracle from audio (sample_data, T={T}): {int(flips.sum())} flipped IPD entries of {f.size} in bins {bins}; others max |diff| {worst:.2e}; "
+          f"masks vs reference as computed {rel_l2(m_raw, ref):.2e}, flips aligned {rel_l2(m_al, ref):.2e}")
+    assert rel_l2(m_al, ref) < 1e-4
