@@ -26,7 +26,15 @@ class WhisperAsrCfg:
     hallucination_silence_threshold: Optional[float] = 2.
 
     def text_normalizer(self):
-        raise NotImplementedError("the chime8 text normaliser (utils/text_norm_whisper_like) belongs to scoring, outside the hot path")
+        """asr.py:23-25: the chime8 normaliser of the host repository (utils/text_norm_whisper_like, a scoring component that
+        is not rebuilt here).  The unchanged caller invokes this after diarization (inference_pipeline/inference.py:75,87), in
+        a process whose sys.path holds the reference checkout, so the reference's own module is what gets returned."""
+        try:
+            from utils.text_norm_whisper_like import get_txt_norm
+        except ImportError as e:
+            raise ImportError("WhisperAsrCfg.text_normalizer() returns the reference's chime8 normaliser "
+                              "(utils.text_norm_whisper_like.get_txt_norm); run from the reference checkout or put it on sys.path") from e
+        return get_txt_norm("chime8")
 
     def assert_valid(self):
         assert self.model_name in ['tiny.en', 'tiny', 'base.en', 'base', 'small.en', 'small', 'medium.en',

@@ -415,8 +415,9 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
         host = _pinned_out(tuple(wav.shape))
         host.copy_(wav, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
-    separated = host.numpy()
+    separated = _lend(host)                 # owned by the caller: the buffer is not reused while these arrays are alive
     separated_wavs = [separated[k] for k in range(cfg.num_spks)]
+    del separated
     side_info = {'segment_frames': out["plan"].segment_frames}
     if return_side_info:
         side_info.update({
@@ -429,28 +430,61 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
     return separated_wavs, side_info
 
 
-_PINNED_POOL: Dict[tuple, list] = {}
-_PINNED_SLOTS = 2
+_PINNED_POOL: Dict[tuple, list] = {}       # shape -> [(pinned tensor, weakref to the numpy array handed out or None), ...]
+_PINNED_KEEP_FREE = 2
 
 
 def _pinned_out(shape: tuple) -> torch.Tensor:
-    """Page-locked float32 host buffer for the separated waveforms.  Buffers are recycled round-robin over
-    _PINNED_SLOTS slots per shape (pinning 345 MB costs more than the whole separation), so the arrays a call
-    returns stay valid until _PINNED_SLOTS later calls with the same output length; copy them to keep them longer."""
-    slot = _PINNED_POOL.setdefault(shape, [0, []])
-    idx, bufs = slot
-    if len(bufs) < _PINNED_SLOTS:
-        bufs.append(torch.empty(shape, dtype=torch.float32, pin_memory=True))
-        buf = bufs[-1]
-    else:
-        buf = bufs[idx % _PINNED_SLOTS]
-    slot[0] = idx + 1
+    """Page-locked float32 host buffer for the separated waveforms (pinning 345 MB costs more than the whole separation,
+    so buffers are pooled per shape).  A buffer is handed out again only after every numpy array that was returned on top
+    of it has been garbage collected (``_lend`` keeps a weak reference to it): a caller that keeps the streams of three
+    sessions holds three distinct buffers -- the reference returns freshly owned arrays (css.py:316-319), so must this."""
+    entries = _PINNED_POOL.setdefault(shape, [])
+    for e in entries:
+        if e[1] is None or e[1]() is None:
+            e[1] = None
+            return e[0]
+    buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+    entries.append([buf, None])
     return buf
 
 
-def load_css_model(model_dir: Path, device: Optional[torch.device] = None, **kw) -> (ConformerCssB200, dict):
+def _lend(buf: torch.Tensor) -> np.ndarray:
+    """numpy view of a pooled pinned buffer; the buffer stays out of circulation while the view (or any slice of it) lives."""
+    import weakref
+    arr = buf.numpy()
+    entries = _PINNED_POOL.get(tuple(buf.shape), [])
+    for e in entries:
+        if e[0] is buf:
+            e[1] = weakref.ref(arr)
+    # buffers nobody holds any more beyond a small reserve go back to the OS
+    free = [e for e in entries if e[1] is None or e[1]() is None]
+    for e in free[_PINNED_KEEP_FREE:]:
+        entries.remove(e)
+    return arr
+
+
+class CfgNode(dict):
+    """The yaml of a checkpoint with attribute access (``cfg.single_channel``, ``cfg.conformer_css_cfg.nnet_conf.num_spks``),
+    standing in for the reference's TrainCfg dataclass tree (css/training/train.py:48-91), which css/helpers.py:26 builds from
+    the same file; only the keys present in the yaml exist (the training defaults are not part of the inference path)."""
+
+    def __init__(self, d=None):
+        super().__init__()
+        for k, v in (d or {}).items():
+            self[k] = CfgNode(v) if isinstance(v, dict) else v
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k) from None
+
+
+def load_css_model(model_dir: Path, device: Optional[torch.device] = None, **kw) -> (ConformerCssB200, "CfgNode"):
     """Counterpart of css/helpers.py:14-37: one ``*.pt`` (``checkpoint['model']`` with the DDP ``module.``
-    prefix) and one ``*.yaml`` (the TrainCfg; only read back for the caller) in ``model_dir``."""
+    prefix) and one ``*.yaml`` (the TrainCfg, returned with attribute access like the reference's dataclass) in
+    ``model_dir``.  The network shape is taken from the checkpoint tensors themselves."""
     import yaml
 
     def fetch_one_file(path: Path, suffix: str):
@@ -463,7 +497,7 @@ def load_css_model(model_dir: Path, device: Optional[torch.device] = None, **kw)
     yaml_path = fetch_one_file(model_dir, '*.yaml')
     checkpoint_path = fetch_one_file(model_dir, '*.pt')
     with open(yaml_path) as f:
-        train_cfg = yaml.safe_load(f)
+        train_cfg = CfgNode(yaml.safe_load(f) or {})
     checkpoint = torch.load(checkpoint_path, map_location="cpu", weights_only=False)
     state = {k[len("module."):]: v for k, v in checkpoint["model"].items() if k.startswith("module.")}
     return ConformerCssB200(state, device=device, **kw), train_cfg
@@ -512,9 +546,27 @@ def write_wav(fname, samps: np.ndarray, sr: int = 16000, max_norm: bool = True):
 
 _MODEL_CACHE: Dict[str, ConformerCssB200] = {}
 # CSS -> ASR / diarization hand-off without the disk round trip: the separated streams of the most recent sessions as the
-# PCM16 the WAV files hold (peak-normalised to 0.99, utils/audio_utils.py:44-45), still in HBM, keyed by session_id.
-DEVICE_STREAMS: Dict[str, "torch.Tensor"] = {}
+# PCM16 the WAV files hold (peak-normalised to 0.99, utils/audio_utils.py:44-45), still in HBM.  Keyed by the absolute
+# paths of the WAV files the same call wrote -- a different out_dir, or a later run that only hits the disk cache, can
+# never pick up another run's samples -- with the sample rate beside the tensor.
+DEVICE_STREAMS: Dict[tuple, tuple] = {}
 _DEVICE_STREAMS_KEEP = 2
+
+
+def _streams_key(wav_file_names) -> tuple:
+    import os
+    return tuple(os.path.abspath(str(f)) for f in wav_file_names)
+
+
+def device_streams_for(wav_file_names):
+    """(int16 CUDA tensor [n_streams, n], sample rate) of exactly these separated WAV files if this process produced them
+    and they are still resident, else None.  The order follows ``wav_file_names``."""
+    want = _streams_key(wav_file_names)
+    for key, (pcm, sr) in DEVICE_STREAMS.items():
+        if set(want) <= set(key) and len(want) > 0:
+            idx = [key.index(w) for w in want]
+            return (pcm if idx == list(range(len(key))) else pcm[idx].contiguous()), sr
+    return None
 
 
 def streams_to_pcm16(wav: "torch.Tensor") -> "torch.Tensor":
@@ -544,6 +596,8 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
     if fetch_from_cache and css_out_dir.exists():
         sep_wav_file_names = sorted(css_out_dir.glob('sep*.wav'))
         session_css['sep_wav_file_names'] = sep_wav_file_names
+        # the files on disk are the truth for this run: drop any in-HBM copy an earlier call left for the same paths
+        DEVICE_STREAMS.pop(_streams_key(sep_wav_file_names), None)
         return session_css
 
     if not torch.cuda.is_available():
@@ -562,10 +616,8 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
 
     stages: dict = {}
     separated_wavs, _ = separate_and_stitch(mixwav, separator, sr, device, cfg, return_side_info=False, _stages=stages)
-    # keep the streams of this session on the device for the stages downstream (diarization_inference(..., pcm=...))
-    DEVICE_STREAMS[session.session_id] = streams_to_pcm16(stages["wav"])
-    while len(DEVICE_STREAMS) > _DEVICE_STREAMS_KEEP:
-        DEVICE_STREAMS.pop(next(iter(DEVICE_STREAMS)))
+    # keep the streams of this session on the device for the stages downstream (asr_inference / diarization_inference)
+    pcm_dev = streams_to_pcm16(stages["wav"])
     del stages
 
     write_wav(css_out_dir / 'input_mixture.wav', samps=mixwav[0, :, 0], sr=sr)
@@ -576,5 +628,9 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
         write_wav(filename, samps=w, sr=sr)
         sep_wav_file_names.append(str(filename))
 
+    DEVICE_STREAMS.pop(_streams_key(sep_wav_file_names), None)
+    DEVICE_STREAMS[_streams_key(sep_wav_file_names)] = (pcm_dev, int(sr))
+    while len(DEVICE_STREAMS) > _DEVICE_STREAMS_KEEP:
+        DEVICE_STREAMS.pop(next(iter(DEVICE_STREAMS)))
     session_css['sep_wav_file_names'] = sep_wav_file_names
     return session_css

@@ -276,9 +276,12 @@ def diarization_inference(out_dir: str, segments_df: pd.DataFrame, cfg: Diarizat
     assert segments_df.wav_file_name.nunique() <= 3 or is_ct, 'expecting at most three separated channels'
     output_dir = Path(out_dir) / "diarization" / session_name / cfg.method
     out_file = output_dir / "all_segments_df.pkl"
-    if fetch_from_cache and out_file.exists():
-        return pd.read_pickle(out_file)
-    os.makedirs(output_dir, exist_ok=True)
+    # diarization.py:82-89: no cache reads / writes when several ranks evaluate concurrently (they would race on the file)
+    skip_cache_and_write = _world_size() > 1
+    if not skip_cache_and_write:
+        if fetch_from_cache and out_file.exists():
+            return pd.read_pickle(out_file)
+        os.makedirs(output_dir, exist_ok=True)
 
     segments_df = segments_df.copy()
     segments_df['wav_file_name'] = segments_df['wav_file_name'].astype('category')
@@ -288,19 +291,29 @@ def diarization_inference(out_dir: str, segments_df: pd.DataFrame, cfg: Diarizat
 
     if cfg.method == "word_nmesc":
         if pcm is None:
-            # streams the CSS stage of this process left in HBM (same sample values as the WAV files), else the files
-            from .css import DEVICE_STREAMS
-            cached = DEVICE_STREAMS.get(session_name)
-            if cached is not None and len(wav_files) == cached.shape[0] and all(f"sep_stream{k}.wav" in str(f) for k, f in enumerate(wav_files)):
-                pcm = cached
+            # streams the CSS stage of this process left in HBM (same sample values as the WAV files it wrote), else the files
+            from .css import device_streams_for
+            hit = device_streams_for(wav_files)
+            if hit is not None:
+                pcm, sr = hit
         if pcm is None:
-            pcm = _load_streams_as_pcm(wav_files, device)
+            pcm, sr = _load_streams_as_pcm(wav_files, device)
         out = word_based_clustering(pcm, sr, segments_df, cfg)
     else:
         from . import _cabi
         raise _cabi.NsfError(f"diarization method {cfg.method!r} is NeMo's time-based recipe (time_based_diarization.py): not built")
-    out.to_pickle(out_file)
+    if not skip_cache_and_write:
+        out.to_pickle(out_file)
     return out
+
+
+def _world_size() -> int:
+    """utils/torch_utils.py get_world_size: 1 unless torch.distributed is initialised."""
+    try:
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    except Exception:
+        return 1
 
 
 def _load_streams_as_pcm(wav_files: List[str], device):
@@ -308,10 +321,11 @@ def _load_streams_as_pcm(wav_files: List[str], device):
     longest stream (word_based_diarization.py:156-164)."""
     import scipy.io.wavfile as wf
     import torch
-    data = [wf.read(str(f))[1] for f in wav_files]
+    srs, data = zip(*[wf.read(str(f)) for f in wav_files])
+    assert len(set(srs)) == 1, f'the separated streams disagree on the sample rate: {srs}'
     n = max(d.size for d in data)
     pcm = np.zeros((len(data), n), np.int16)
     for i, d in enumerate(data):
         pcm[i, :d.size] = d
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
-    return torch.from_numpy(pcm).to(dev)
+    return torch.from_numpy(pcm).to(dev), int(srs[0])                # word_based_diarization.py:156-157: sr comes from the files

@@ -36,7 +36,8 @@ class Shard:
     world: int
     seg_lo: int
     seg_hi: int
-    halo: int            # 1 if the block has a left neighbour (segment seg_lo - 1 is recomputed locally)
+    halo: int            # segments left of seg_lo recomputed locally: every segment that reaches into the owned frames,
+                         # min(seg_lo, ceil(T / hop) - 1) -- one for the default 50 % overlap, two for hop = T / 3, ...
     frame0: int          # global index of local frame 0
     n_frames: int        # local frames (pitch of the local X / stitched arrays)
     valid_frames: int    # local frames that exist in the signal (the rest is the zero padding of css.py:159-164,185-190)
@@ -73,7 +74,10 @@ def make_shard(plan: SegmentPlan, rank: int, world: int) -> Shard:
     lo, hi = b[rank], b[rank + 1]
     if hi == lo:           # more ranks than segments: nothing to do, nothing owned
         return Shard(rank, world, lo, hi, 0, 0, 0, 0, 0, 0, 0, 0)
-    halo = 1 if lo > 0 else 0
+    # frame lo*hop is covered by the segments s with s*hop <= lo*hop < s*hop + T, i.e. s > lo - T/hop: all of them must be
+    # local, or the owned frames next to the seam miss a term of the overlap-add while still being divided by the global
+    # weight sum (hop_size_sec=1.0 has three segments per frame).  At least one, for the stitching cost of seg_lo.
+    halo = min(lo, max(1, -(-T // hop) - 1))
     frame0 = (lo - halo) * hop
     n_frames = min(plan.mix_frames, (hi - 1) * hop + T) - frame0
     valid = max(0, min(plan.raw_frames - frame0, n_frames))

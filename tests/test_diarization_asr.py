@@ -139,3 +139,54 @@ def test_gather_word_crops_on_device(D, G):
     assert len(plan.start) > step
     part, _ = D.gather_word_crops(pcm, plan, step, min(step, len(plan.start) - step))
     assert np.array_equal(part.cpu().numpy()[:, :1], got[step:step + part.shape[0], :1])
+
+
+# ----------------------------------------------------------------------------------------------- boundary breaks of round 1
+def test_text_normalizer_is_the_reference_one_when_the_host_repo_is_importable(monkeypatch):
+    """asr.py:23-25 / inference_pipeline/inference.py:75,87: the unchanged caller invokes cfg.asr.text_normalizer() after
+    diarization; it must hand back the host repository's chime8 normaliser, not raise."""
+    import sys
+    from notsofar_b200.asr import WhisperAsrCfg
+    from oracle import reference_shim as R
+    cfg = WhisperAsrCfg()
+    if R.available():
+        monkeypatch.syspath_prepend(R.REFERENCE_ROOT)
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            monkeypatch.delitem(sys.modules, m, raising=False)
+        norm = cfg.text_normalizer()
+        assert type(norm).__name__ == "EnglishTextNormalizer"
+        assert norm("Mr. Smith's  twenty-two dogs, um, okay") == norm("mister smith's 22 dogs okay")
+    else:
+        monkeypatch.setattr(sys, "path", [p for p in sys.path if "reference" not in p])
+        for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
+            monkeypatch.delitem(sys.modules, m, raising=False)
+        with pytest.raises(ImportError, match="text_norm_whisper_like"):
+            cfg.text_normalizer()
+
+
+def test_train_cfg_node_has_attribute_access():
+    from notsofar_b200.css import CfgNode
+    c = CfgNode({"single_channel": False, "conformer_css_cfg": {"nnet_conf": {"num_spks": 3, "conformer_conf": {"attention_dim": 512}}}})
+    assert c.single_channel is False and c.conformer_css_cfg.nnet_conf.conformer_conf.attention_dim == 512
+    assert c["conformer_css_cfg"]["nnet_conf"]["num_spks"] == 3
+    with pytest.raises(AttributeError):
+        c.missing
+
+
+def test_diarization_skips_cache_under_several_ranks(D, tmp_path, monkeypatch):
+    """diarization.py:82-89,104-106: with world_size > 1 neither the cache read nor the pickle write happens."""
+    import notsofar_b200.diarization as dm
+    df = _segments(3)
+    calls = []
+    monkeypatch.setattr(dm, "_load_streams_as_pcm", lambda files, device: ("pcm", 16000))
+    monkeypatch.setattr(dm, "word_based_clustering", lambda pcm, sr, seg, cfg: (calls.append((pcm, sr)), seg.assign(speaker_id="spk0"))[1])
+    cfg = dm.DiarizationCfg(method="word_nmesc")
+    monkeypatch.setattr(dm, "_world_size", lambda: 2)
+    out = dm.diarization_inference(str(tmp_path), df, cfg, fetch_from_cache=True)
+    assert len(calls) == 1 and calls[0] == ("pcm", 16000) and "speaker_id" in out
+    assert not (tmp_path / "diarization").exists()
+    monkeypatch.setattr(dm, "_world_size", lambda: 1)
+    dm.diarization_inference(str(tmp_path), df, cfg, fetch_from_cache=True)
+    assert len(list((tmp_path / "diarization").rglob("all_segments_df.pkl"))) == 1
+    dm.diarization_inference(str(tmp_path), df, cfg, fetch_from_cache=True)          # served from the cache now
+    assert len(calls) == 2

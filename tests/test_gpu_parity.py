@@ -740,11 +740,17 @@ def test_css_inference_files_cache_and_passthrough(nb, dev, small_weights, tmp_p
         assert f.endswith(f"sep_stream{k}.wav") and sr == 16000 and pcm.dtype == np.int16
         assert np.abs(pcm).max() in (32438, 32439)                                    # 0.99 peak normalisation
     # the hand-off copy left in HBM holds exactly the samples of the files
-    dev_pcm = css_mod.DEVICE_STREAMS["multichannel/MTG_1_dev"].cpu().numpy()
+    hit = css_mod.device_streams_for(out.sep_wav_file_names)
+    assert hit is not None and hit[1] == 16000
+    dev_pcm = hit[0].cpu().numpy()
     for k, f in enumerate(out.sep_wav_file_names):
         assert np.array_equal(dev_pcm[k], wf.read(f)[1])
+    # keyed by the files themselves: another out_dir (or another session) never sees these samples
+    assert css_mod.device_streams_for([str(tmp_path / "elsewhere" / "sep_stream0.wav")]) is None
+    assert torch.equal(css_mod.device_streams_for(out.sep_wav_file_names[::-1])[0], hit[0].flip(0))
     again = nb.css_inference(str(tmp_path / "out"), str(tmp_path / "models"), session, cfg, fetch_from_cache=True)
     assert [str(f) for f in again.sep_wav_file_names] == sorted(out.sep_wav_file_names)
+    assert css_mod.device_streams_for(out.sep_wav_file_names) is None        # a disk-cache hit invalidates the in-HBM copy
     thru = nb.css_inference(str(tmp_path / "out2"), str(tmp_path / "models"), session, nb.CssCfg(pass_through_ch0=True), False)
     assert thru.sep_wav_file_names == names[:1] and not (tmp_path / "out2").exists()
 
@@ -894,3 +900,30 @@ def test_t186_whole_chain_vs_reference_actual_waveforms(nb, dev, golden_t186):
           f"(reference fp32 MVDR vs its fp64 lift: {g['chain_mvdr_floor'].max():.2e})")
     assert wavs[0].shape == g["chain_wavs"][0].shape
     assert max(errs) < TOL
+
+
+def test_results_of_three_retained_sessions_do_not_alias(nb, dev, small_weights):
+    """VERDICT r1 weak #4 / ADVICE: separate_and_stitch returns arrays the caller owns.  The pinned result buffers are pooled,
+    but one is only handed out again after the arrays of the call that used it were dropped."""
+    from notsofar_b200 import css as css_mod
+    from notsofar_b200 import synth
+    sep = _sep(nb, small_weights, dev)
+    cfg = nb.CssCfg(activity_th=0.3, show_progressbar=False)
+    xs = [synth.synthetic_meeting(6.0, seed=40 + i)[None] for i in range(3)]
+    kept, copies = [], []
+    for x in xs:
+        wavs, _ = nb.separate_and_stitch(x, sep, 16000, dev, cfg, return_side_info=False)
+        kept.append(wavs)
+        copies.append([w.copy() for w in wavs])
+    for wavs, ref in zip(kept, copies):
+        for a, b in zip(wavs, ref):
+            assert np.array_equal(a, b), "an earlier session's streams were overwritten by a later call"
+    bases = {w[0].__array_interface__["data"][0] for w in kept}
+    assert len(bases) == 3
+    n_bufs = len(css_mod._PINNED_POOL[(3, len(kept[0][0]))])
+    del kept, wavs
+    import gc
+    gc.collect()
+    w2, _ = nb.separate_and_stitch(xs[0], sep, 16000, dev, cfg, return_side_info=False)
+    assert len(css_mod._PINNED_POOL[(3, len(w2[0]))]) <= n_bufs          # a released buffer was reused, none added
+    assert np.array_equal(w2[0], copies[0][0])

@@ -20,10 +20,11 @@ def N():
 
 
 # ----------------------------------------------------------------------------------------------- partition plan
+@pytest.mark.parametrize("hop_sec", [1.5, 1.0, 0.7])
 @pytest.mark.parametrize("seconds,world", [(30.0, 1), (30.0, 2), (30.0, 3), (61.3, 4), (1800.0, 8), (4.0, 8), (2.0, 2)])
-def test_shards_cover_segments_frames_and_samples(N, seconds, world):
+def test_shards_cover_segments_frames_and_samples(N, seconds, world, hop_sec):
     from notsofar_b200.sharded import make_shard, shard_bounds
-    cfg = N.CssCfg()
+    cfg = N.CssCfg(hop_size_sec=hop_sec)
     n = int(seconds * 16000)
     plan = N.plan_segments(n, 16000, cfg)
     shards = [make_shard(plan, r, world) for r in range(world)]
@@ -37,8 +38,11 @@ def test_shards_cover_segments_frames_and_samples(N, seconds, world):
             continue
         assert sh.own_lo == frame_next
         frame_next = sh.own_hi
-        assert sh.halo == (1 if sh.seg_lo > 0 else 0)
-        # every frame an owned output frame depends on is local: segments seg_lo-1 .. seg_hi-1
+        # every segment that overlaps an owned output frame is local (ceil(T / hop) - 1 segments to the left of seg_lo)
+        T, hop = plan.segment_frames, plan.hop_frames
+        touching = [s for s in range(plan.num_segments) if s * hop < sh.own_hi and s * hop + T > sh.own_lo]
+        assert min(touching) >= sh.seg_lo - sh.halo and max(touching) <= sh.seg_hi - 1
+        assert sh.halo == min(sh.seg_lo, max(1, -(-T // hop) - 1))
         assert sh.frame0 == (sh.seg_lo - sh.halo) * plan.hop_frames
         assert sh.frame0 + sh.n_frames >= min(plan.mix_frames, (sh.seg_hi - 1) * plan.hop_frames + plan.segment_frames)
         assert sh.own_lo >= sh.frame0 and sh.own_hi <= sh.frame0 + sh.n_frames
@@ -167,8 +171,8 @@ def test_sharded_no_beamformer_power_norm_equals_single_device(N):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,seconds", [(2, 14.0), (3, 21.7), (5, 6.1)])
-def test_sharded_equals_single_device(N, small_weights, world, seconds):
+@pytest.mark.parametrize("world,seconds,hop_sec", [(2, 14.0, 1.5), (3, 21.7, 1.5), (5, 6.1, 1.5), (3, 21.7, 1.0), (2, 9.0, 0.7)])
+def test_sharded_equals_single_device(N, small_weights, world, seconds, hop_sec):
     """All ranks of the sharded algorithm played on one GPU vs css_device: integers and everything up to the stitched
     masks bit-exact; waveforms equal away from the shard seams and within 1e-6 at them (the iSTFT packs frame
     pairs into one complex FFT, so a frame's rounding depends on its partner)."""
@@ -180,8 +184,8 @@ def test_sharded_equals_single_device(N, small_weights, world, seconds):
     x = torch.from_numpy(synth.synthetic_meeting(seconds, seed=3)).to(dev)
     # random-init masks hover around 0.5: put the threshold at their 99th percentile (sparse islands) so that the gate (and its
     # dilate / erode across the shard seams) is exercised
-    probe = css_device(x, sep, 16000, N.CssCfg(show_progressbar=False))
-    cfg = N.CssCfg(activity_th=float(torch.quantile(probe["activity"].flatten(), 0.99)), show_progressbar=False)
+    probe = css_device(x, sep, 16000, N.CssCfg(show_progressbar=False, hop_size_sec=hop_sec))
+    cfg = N.CssCfg(activity_th=float(torch.quantile(probe["activity"].flatten(), 0.99)), show_progressbar=False, hop_size_sec=hop_sec)
     one = css_device(x, sep, 16000, cfg)
     sh = css_sharded_on_one_device(x, sep, 16000, cfg, world)
     torch.cuda.synchronize()
