@@ -151,6 +151,13 @@ def test_text_normalizer_is_the_reference_one_when_the_host_repo_is_importable(m
     cfg = WhisperAsrCfg()
     if R.available():
         monkeypatch.syspath_prepend(R.REFERENCE_ROOT)
+        try:
+            import more_itertools  # noqa: F401  (a dependency of the reference's normaliser, requirements.txt; absent in this image)
+        except ImportError:
+            import types
+            stub = types.ModuleType("more_itertools")
+            stub.windowed = lambda seq, n: (tuple(seq[i:i + n]) for i in range(max(len(seq) - n + 1, 1)))
+            monkeypatch.setitem(sys.modules, "more_itertools", stub)
         for m in [k for k in sys.modules if k == "utils" or k.startswith("utils.")]:
             monkeypatch.delitem(sys.modules, m, raising=False)
         norm = cfg.text_normalizer()
@@ -176,7 +183,8 @@ def test_train_cfg_node_has_attribute_access():
 def test_diarization_skips_cache_under_several_ranks(D, tmp_path, monkeypatch):
     """diarization.py:82-89,104-106: with world_size > 1 neither the cache read nor the pickle write happens."""
     import notsofar_b200.diarization as dm
-    df = _segments(3)
+    df = _segments(3).drop(columns=["wav_file_name_ind"], errors="ignore")
+    df["wav_file_name"] = df["wav_file_name"].astype(str)
     calls = []
     monkeypatch.setattr(dm, "_load_streams_as_pcm", lambda files, device: ("pcm", 16000))
     monkeypatch.setattr(dm, "word_based_clustering", lambda pcm, sr, seg, cfg: (calls.append((pcm, sr)), seg.assign(speaker_id="spk0"))[1])
