@@ -133,7 +133,10 @@ int nsf_conformer_forward(nsf_conformer* h, const float* feat, const float* feat
  * fp64-lifted reference).  mask_floor = 10^(floor_dB/20); 1.0 => pure MVDR.
  * Segment geometry as in nsf_css_features.  X is [n_bins][T_long][C]; masks [n_seg][S+Nn][n_bins][T];
  * Y [n_seg][S][n_bins][T].  Bin 0 gets the den += 1e-15 of mvdr_util.py:73.
- * Built for S = 3, C = 7 (NSF_ERR_UNSUPPORTED otherwise); any T (the slab streams through chip in 32-frame chunks). */
+ * Built for S = 2..4 speaker masks and C = 7 microphones (NSF_ERR_UNSUPPORTED otherwise; the reference's covariance code
+ * is itself written for 7 microphones, mvdr_util.py:63); any T and hop.  When T == 2 hop (50 % overlap: every shipped
+ * configuration) and hop <= 96 the streaming kernel runs -- a warp walks a run of consecutive segments of one bin and forms
+ * every outer product once for the two segments that share the frame -- otherwise one warp per (segment, bin). */
 int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float* X, int64_t T_long, int64_t T_valid, int n_ch,
              int64_t seg_first, int n_seg, int T, int hop, int n_bins, float mask_floor,
              float* Y, void* stream);

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libnsf_b200.so")
 
 GEMM_SIMT_FP32, GEMM_TC_3XTF32, GEMM_TC_TF32, GEMM_TC_2XBF16, GEMM_TC_2XF16, GEMM_TC_BF16 = 0, 1, 2, 3, 4, 5
 SPLIT_TF32, SPLIT_BF16, SPLIT_F16, SPLIT_BF16_1, SPLIT_FP32 = 0, 1, 2, 3, 4
+NSF_OK, NSF_ERR_INVALID_ARG, NSF_ERR_CUDA, NSF_ERR_UNSUPPORTED = 0, -1, -2, -3      # include/nsf_b200.h
 F16_ACT_SCALE, F16_WEIGHT_SCALE = 16.0, 256.0        # csrc/common.cuh kF16ActScale / kF16WeightScale
 
 

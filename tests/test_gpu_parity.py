@@ -328,33 +328,105 @@ def test_mvdr_vs_reference_golden(nb, dev, golden, small_weights):
         assert e32 < 2 * floor + TOL
 
 
-def test_mvdr_production_shape_vs_oracle(nb, dev, small_weights):
-    """T = 186, batch of segments cut from one long X, sharp masks, last segment zero-padded."""
+def _coherent_mixture(rng, T_valid, n_src=3):
+    """coherent sources + diffuse noise -> realistic (ill-conditioned at low rank) covariances"""
+    steer = np.exp(1j * rng.uniform(0, 2 * np.pi, (n_src, 257, 1, 7)))
+    src = (rng.standard_normal((n_src, 257, T_valid, 1)) + 1j * rng.standard_normal((n_src, 257, T_valid, 1))) * \
+        (rng.random((n_src, 1, T_valid, 1)) > 0.5)
+    Xn = (steer * src).sum(0) + 0.05 * (rng.standard_normal((257, T_valid, 7)) + 1j * rng.standard_normal((257, T_valid, 7)))
+    return Xn.astype(np.complex64)
+
+
+def _mvdr_vs_oracle(sep, dev, Xn, masks, T_valid, hop, n_spk=3):
+    n_seg, T = masks.shape[0], masks.shape[-1]
+    sep.num_spks = n_spk
+    y = sep.mvdr(torch.from_numpy(masks).to(dev), torch.from_numpy(Xn).to(dev), T_valid, 0, hop, 1.0).cpu().numpy()
+    worst, worst_bin = 0.0, 0.0
+    for i in range(n_seg):
+        seg = np.zeros((257, T, 7), np.complex64)
+        en = min(i * hop + T, T_valid)
+        if en > i * hop:
+            seg[:, :en - i * hop] = Xn[:, i * hop:en]
+        ref = O.make_mvdr(masks[i, :n_spk], masks[i, n_spk:], seg.transpose(2, 0, 1), np.float64)
+        worst = max(worst, rel_l2(y[i], ref))
+        per_bin = np.linalg.norm((y[i] - ref).reshape(n_spk, 257, -1), axis=(0, 2)) / np.maximum(np.linalg.norm(ref.reshape(n_spk, 257, -1), axis=(0, 2)), 1e-30)
+        worst_bin = max(worst_bin, per_bin.max())
+    return y, worst, worst_bin
+
+
+@pytest.mark.parametrize("impl", ["stream", "fano", "entry32", "generic"])
+def test_mvdr_production_shape_vs_oracle(nb, dev, small_weights, monkeypatch, impl):
+    """T = 186, hop 93, batch of segments cut from one long X, sharp masks, last segment zero-padded: the streaming kernel
+    (segments share their half blocks) and the one-warp-per-(segment, bin) kernel against the fp64 oracle."""
+    monkeypatch.setenv("NSF_MVDR_IMPL", impl)
     sep = _sep(nb, small_weights, dev)
     rng = np.random.default_rng(11)
     n_seg, T, hop = 5, 186, 93
     T_valid = (n_seg - 1) * hop + 150
-    # coherent sources + diffuse noise -> realistic (ill-conditioned at low rank) covariances
-    steer = np.exp(1j * rng.uniform(0, 2 * np.pi, (3, 257, 1, 7)))
-    src = (rng.standard_normal((3, 257, T_valid, 1)) + 1j * rng.standard_normal((3, 257, T_valid, 1))) * \
-        (rng.random((3, 1, T_valid, 1)) > 0.5)
-    Xn = (steer * src).sum(0) + 0.05 * (rng.standard_normal((257, T_valid, 7)) + 1j * rng.standard_normal((257, T_valid, 7)))
-    Xn = Xn.astype(np.complex64)
+    Xn = _coherent_mixture(rng, T_valid)
     masks = rng.standard_normal((n_seg, 4, 257, T)).astype(np.float32) * 3
     masks = (np.exp(masks) / np.exp(masks).sum(1, keepdims=True)).astype(np.float32)
     masks[0, :, 5, :7] = 0.25                                    # exact ties: every tied mask keeps its value
-    y = sep.mvdr(torch.from_numpy(masks).to(dev), torch.from_numpy(Xn).to(dev), T_valid, 0, hop, 1.0).cpu().numpy()
-    worst = 0.0
-    for i in range(n_seg):
-        seg = np.zeros((257, T, 7), np.complex64)
-        en = min(i * hop + T, T_valid)
-        seg[:, :en - i * hop] = Xn[:, i * hop:en]
-        ref = O.make_mvdr(masks[i, :3], masks[i, 3:], seg.transpose(2, 0, 1), np.float64)
-        worst = max(worst, rel_l2(y[i], ref))
-        per_bin = np.linalg.norm((y[i] - ref).reshape(3, 257, -1), axis=(0, 2)) / np.linalg.norm(ref.reshape(3, 257, -1), axis=(0, 2))
-        assert per_bin.max() < 1e-3, f"segment {i} worst bin {per_bin.argmax()} {per_bin.max():.2e}"
-    print(f"mvdr production shape: worst segment rel_l2 vs fp64 oracle {worst:.2e}")
-    assert worst < TOL
+    masks[2, :2, 9, 100:103] = 0.5; masks[2, 2:, 9, 100:103] = 0.0   # a two-way tie in the second half of a segment
+    _, worst, worst_bin = _mvdr_vs_oracle(sep, dev, Xn, masks, T_valid, hop)
+    print(f"mvdr production shape [{impl}]: worst segment rel_l2 vs fp64 oracle {worst:.2e}, worst bin {worst_bin:.2e}")
+    assert worst < TOL and worst_bin < 1e-3
+
+
+@pytest.mark.parametrize("impl", ["stream", "fano"])
+@pytest.mark.parametrize("run_len", [1, 3, 8])
+def test_mvdr_stream_runs_and_padding(nb, dev, small_weights, monkeypatch, run_len, impl):
+    """The streaming kernel over several warp runs (run boundaries fall inside the batch), a batch that starts in the middle
+    of the meeting (seg_first > 0), segments that lie partly / entirely in the zero padding, and a mask that never wins in
+    some bins (R = 1e-10 x total: the fp64 total matters there)."""
+    monkeypatch.setenv("NSF_MVDR_IMPL", impl)
+    monkeypatch.setenv("NSF_MVDR_RUN", str(run_len))
+    sep = _sep(nb, small_weights, dev)
+    rng = np.random.default_rng(run_len)
+    n_seg, T, hop = 11, 186, 93
+    T_valid = 9 * hop + 40                                       # segment 9 mostly padding, segment 10 entirely
+    Xn = _coherent_mixture(rng, T_valid)
+    masks = rng.standard_normal((n_seg, 4, 257, T)).astype(np.float32) * 3
+    masks = (np.exp(masks) / np.exp(masks).sum(1, keepdims=True)).astype(np.float32)
+    masks[:, 1, 40:60] *= 1e-3                                   # speaker 1 never wins in bins 40..59
+    y, worst, worst_bin = _mvdr_vs_oracle(sep, dev, Xn, masks, T_valid, hop)
+    assert np.isfinite(y).all()
+    print(f"mvdr stream run_len={run_len}: worst segment {worst:.2e}, worst bin {worst_bin:.2e}")
+    assert worst < TOL and worst_bin < 1e-3
+    # the same batch in two calls (segments 0..4 and 5..10 with seg_first = 5) gives the same answer as one call
+    tm, tX = torch.from_numpy(masks).to(dev), torch.from_numpy(Xn).to(dev)
+    y2 = torch.cat([sep.mvdr(tm[:5].contiguous(), tX, T_valid, 0, hop, 1.0), sep.mvdr(tm[5:].contiguous(), tX, T_valid, 5, hop, 1.0)]).cpu().numpy()
+    assert rel_l2(y2, y) < 1e-6
+
+
+@pytest.mark.parametrize("impl", ["stream", "fano", "generic"])
+@pytest.mark.parametrize("n_spk,n_noise", [(2, 1), (4, 1), (2, 2), (3, 2)])
+def test_mvdr_other_speaker_counts_vs_oracle(nb, dev, small_weights, monkeypatch, impl, n_spk, n_noise):
+    """CssCfg.num_spks is configurable (css.py:45); the CSS-with-Conformer ancestor had 2 speaker + 2 noise masks
+    (conformer_wrapper.py:44-45)."""
+    monkeypatch.setenv("NSF_MVDR_IMPL", impl)
+    sep = _sep(nb, small_weights, dev)
+    rng = np.random.default_rng(n_spk * 10 + n_noise)
+    n_seg, T, hop = 3, 186, 93
+    T_valid = (n_seg - 1) * hop + T
+    Xn = _coherent_mixture(rng, T_valid, n_src=n_spk)
+    masks = rng.standard_normal((n_seg, n_spk + n_noise, 257, T)).astype(np.float32) * 2
+    masks = (np.exp(masks) / np.exp(masks).sum(1, keepdims=True)).astype(np.float32)
+    try:
+        _, worst, worst_bin = _mvdr_vs_oracle(sep, dev, Xn, masks, T_valid, hop, n_spk=n_spk)
+    finally:
+        sep.num_spks = 3
+    print(f"mvdr S={n_spk} Nn={n_noise} [{impl}]: worst segment {worst:.2e}, worst bin {worst_bin:.2e}")
+    assert worst < TOL and worst_bin < 1e-3
+
+
+def test_mvdr_rejects_unsupported_shapes(nb, dev):
+    lib = nb._cabi.load()
+    t = torch.zeros(16, device=dev)
+    rc = lib.nsf_mvdr(nb._cabi.ptr(t), 5, 1, nb._cabi.ptr(t), 10, 10, 7, 0, 1, 4, 4, 1, 1.0, nb._cabi.ptr(t), nb._cabi.stream_ptr())
+    assert rc == nb._cabi.NSF_ERR_UNSUPPORTED and b"2..4 speaker" in lib.nsf_last_error()
+    rc = lib.nsf_mvdr(nb._cabi.ptr(t), 3, 1, nb._cabi.ptr(t), 10, 10, 6, 0, 1, 4, 4, 1, 1.0, nb._cabi.ptr(t), nb._cabi.stream_ptr())
+    assert rc == nb._cabi.NSF_ERR_UNSUPPORTED
 
 
 def test_mvdr_mask_floor(nb, dev, small_weights):

@@ -166,7 +166,7 @@ def test_sharded_no_beamformer_power_norm_equals_single_device(N):
     torch.cuda.synchronize()
     assert np.array_equal(sh["perms"], one["perms"]) and torch.equal(sh["mask_stitched"], one["mask_stitched"])
     for w_Y, s in zip(sh["Y"], sh["shards"]):
-        assert torch.equal(w_Y.view(torch.float32), one["Y"][s.seg_lo - s.halo:s.seg_hi].view(torch.float32))
+        assert torch.equal(w_Y.view(torch.float32), one["Y"][s.seg_lo - s.halo:s.seg_hi].view(torch.float32))      # no beamformer: bit-exact
     assert rel_l2(sh["wav"].cpu().numpy(), one["wav"].cpu().numpy()) < 1e-6
 
 
@@ -196,7 +196,10 @@ def test_sharded_equals_single_device(N, small_weights, world, seconds, hop_sec)
     for w_masks, w_Y, s in zip(sh["masks"], sh["Y"], sh["shards"]):
         if s.n_loc_seg:
             assert torch.equal(w_masks, one["masks"][s.seg_lo - s.halo:s.seg_hi])
-            assert torch.equal(w_Y.view(torch.float32), one["Y"][s.seg_lo - s.halo:s.seg_hi].view(torch.float32))
+            # MVDR: the streaming kernel sums a block's frames in the order of the (older, newer) winner classes, so the last
+            # segment of a rank (no newer neighbour in its batch) rounds its fp64 covariances differently: equal to fp32 round-off
+            a_, b_ = w_Y.view(torch.float32), one["Y"][s.seg_lo - s.halo:s.seg_hi].view(torch.float32)
+            assert float((a_ - b_).norm() / b_.norm()) < 1e-5
     a, b = sh["wav"].cpu().numpy(), one["wav"].cpu().numpy()
     assert a.shape == b.shape
     err = rel_l2(a, b)

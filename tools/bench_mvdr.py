@@ -22,12 +22,15 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json"))) \
         if os.path.exists("MEASURED_PEAKS.json") else {"hbm_gbs": 6650.0}
-    T, hop, F, C, S = 186, 186, 257, 7, 3
+    T, F, C, S = 186, 257, 7, 3
     g = torch.Generator(device=dev).manual_seed(0)
     sizes = [int(a) for a in sys.argv[1:]] or [1000, 3000, 10000, 30000, 100000]      # python tools/bench_mvdr.py [frames ...]
+    # form "segments": the pipeline shape -- 186-frame segments every 93 frames (css.py:141-152); NSF_MVDR_HOP=186 gives
+    # disjoint segments (the round-1 sweep; one warp per (segment, bin) kernel)
+    hop = int(os.environ.get("NSF_MVDR_HOP", "93"))
     for frames in sizes:
-        n_seg = -(-frames // T)
-        T_long = n_seg * T
+        n_seg = max(1, -(-(frames - (T - hop)) // hop))
+        T_long = (n_seg - 1) * hop + T
         a = torch.randn(F, 1, C, 2, device=dev, generator=g)
         s = torch.randn(F, T_long, 1, 2, device=dev, generator=g)
         steer = torch.view_as_complex(a.contiguous()) * torch.view_as_complex(s.contiguous())
@@ -47,9 +50,9 @@ def main():
             dist.all_reduce(t)
             gbs = t.item()
         if int(os.environ.get("RANK", "0")) == 0:
-            print(json.dumps({"frames_per_gpu": frames, "segments_per_gpu": n_seg, "n_gpus": world, "us_per_launch": ms / cnt * 1e3,
+            print(json.dumps({"form": f"batched {T}-frame segments, hop {hop}", "impl": os.environ.get("NSF_MVDR_IMPL", "default"), "frames_per_gpu": frames, "segments_per_gpu": n_seg, "n_gpus": world, "us_per_launch": ms / cnt * 1e3,
                               "GB/s": gbs, "frac_of_measured_hbm": gbs / (world * peaks["hbm_gbs"]),
-                              "note": "96 algorithmic bytes per (bin, frame); the kernel is fp64-pipe bound (covariances and solves in fp64)"}), flush=True)
+                              "note": "96 algorithmic bytes per (bin, segment frame): 56 mix + 16 masks + 24 out"}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
