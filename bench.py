@@ -6,12 +6,14 @@
 
 Workload (BASELINE.json configs[1]): continuous speech separation of a 30-minute 7-channel meeting -- multichannel
 STFT, 1 209 overlapping 3-s segments through the v1.0-MC Conformer mask network (d=512, 8 heads, 18 blocks, seeded
-random weights: no checkpoints offline) in fp32-parity (3xTF32) mode, fp64 mask-weighted MVDR, permutation-aligned
-overlap-add, activity gate, iSTFT.  One "step" = one pass of that path over the whole meeting.
+random weights: no checkpoints offline) with fp32-grade GEMMs (bf16 head + remainder pairs, three tcgen05 kind::f16 MMAs
+per product, fp32 accumulate), fp64 mask-weighted MVDR, permutation-aligned overlap-add, activity gate, iSTFT.  One "step"
+= one pass of that path over the whole meeting.
 
   value : audio-seconds / wall-second with the raw audio already resident in HBM (device-timed, CUDA events,
-          max over ranks).  N > 1: every rank separates its own meeting (sessions are independent by rule,
-          inference_pipeline/inference.py:58) -> weak scaling, no data-path collective.
+          max over ranks).  N > 1 (default --multi shard): ONE meeting of N x --seconds, its segments sharded over the
+          ranks (notsofar_b200.sharded: two small NCCL all-gathers + the waveform hand-off to rank 0) -> weak scaling;
+          --scaling strong keeps the meeting at --seconds in total; --multi replicas gives every rank its own meeting.
   e2e   : the same through the public API notsofar_b200.separate_and_stitch with HOST buffers -- H2D of the pinned
           raw audio and D2H of the three separated waveforms inside the timed region.
   roofline     : the dominant kernel class of the step (the tcgen05 GEMM), algorithmic flops / event-timed duration
@@ -19,6 +21,12 @@ overlap-add, activity gate, iSTFT.  One "step" = one pass of that path over the 
   cpu_baseline : the numpy port of the reference's path (oracle/, same algorithm, all host cores) on a bounded slice.
 
 --impl reference times that CPU port alone (rank 0 only), same metric / unit / config.
+--workload session: a 6-minute session (the NOTSOFAR session length) per GPU through the plug-in call css_inference, 7 WAV
+  files in (pageable numpy from the file reader), 4 WAV files out, inside the timed region.
+--check: correctness of the sharded path under the real process group: rank 0's sharded waveforms / permutations /
+  activity against the single-device path on a 2-minute meeting (one JSON line, non-zero exit on mismatch).
+tcpWER is not evaluated anywhere here: dataset, checkpoints and meeteval are unavailable offline (BASELINE.md section 1);
+the stage-wise parity suite under tests/ stands in.
 """
 from __future__ import annotations
 
@@ -47,6 +55,24 @@ NCU_TRAFFIC = {
 }
 METRIC = "audio-sec/sec (xRT) CSS+MVDR 7-ch 16kHz"
 UNIT = "audio-s/s"
+QUALITY = "tcpWER not evaluated (dataset, checkpoints and meeteval unavailable offline); stage-wise parity vs the reference: tests/ -m gpu"
+
+
+def restore_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arms are meant to use every host core (the BLAS pools were
+    sized at import time, so the limit is lifted at run time)."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cores)
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:
+        pass
+    return cores
 
 
 def _peaks():
@@ -118,6 +144,7 @@ def make_meeting(seconds: float, seed: int):
 def cpu_port_xrt(x_slice: np.ndarray, weights, repeats: int = 1):
     """Times the numpy port of the reference path on x_slice [n, 7]; returns (xRT, seconds of CPU work)."""
     from oracle import css_oracle as O
+    restore_host_threads()
     t0 = time.perf_counter()
     for _ in range(repeats):
         O.separate_and_stitch(x_slice[None], weights, FS, O.OracleCfg(activity_th=0.3), dtype=np.float32)
@@ -131,7 +158,7 @@ def run_reference(args):
     if rank != 0:
         return
     from notsofar_b200 import synth
-    cores = os.cpu_count() or 1
+    cores = restore_host_threads()
     sample_s = args.ref_seconds
     x = make_meeting(sample_s, seed=0)
     w = synth.random_state_dict(0)
@@ -156,7 +183,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{sample_s:.0f} s of the synthetic 7-ch meeting per step, numpy/BLAS on all host threads"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "quality": QUALITY}
     print(json.dumps(line), flush=True)
 
 
@@ -207,7 +234,7 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
     from notsofar_b200.css import HostFeeder
     from notsofar_b200.sharded import css_device_sharded, make_shard
 
-    seconds = args.seconds
+    seconds = args.seconds if args.scaling == "weak" else args.seconds / world
     total_s = seconds * world
     n_total = int(round(total_s * FS))
     cfg = N.CssCfg(activity_th=0.3, show_progressbar=False)
@@ -295,14 +322,14 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
         n_out = (plan.mix_frames - 1) * 256 + 512
         kernels, roofline = roofline_of(prof, prof_ms, args.steps, args.engine)
         line = {"metric": METRIC, "value": total_s / (dev_ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": DTYPES[args.engine],
+                "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+                "dtype": DTYPES[args.engine], "quality": QUALITY,
                 "data": "synthetic (seeded 5-min 7-ch pattern tiled; random-init v1.0-MC weights)",
                 "config": {"workload": f"CSS Conformer v1.0-MC + MVDR, 7-ch 16 kHz, ONE {total_s / 60:.0f}-min synthetic meeting "
                                        f"({plan.num_segments} segments of 186 frames) sharded over {world} GPUs = {seconds / 60:.0f} min per GPU",
                            "segments_per_batch": args.segments_per_batch, "gemm_engine": args.engine,
                            "parallelism": f"segment-sharded x{world}: contiguous blocks + 1-segment halo; NCCL all-gather of stitching costs "
-                                          f"(36 B/segment) and mask means (12 B/frame), gather of the separated streams to rank 0",
+                                          f"(36 B/segment) and mask means (12 B/frame), point-to-point hand-off of the separated streams to rank 0",
                            "l2": "inputs and intermediates exceed L2 (>5 GB touched per step per GPU)"},
                 "clocks": clocks,
                 "e2e": {"value": total_s / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
@@ -409,8 +436,11 @@ def run_b200(args):
     # ---- timed: end to end through the public API with host buffers
     e2e_ms = float("nan")
     if not args.skip_e2e:
-        for _ in range(min(2, args.warmup)):
-            step_e2e()
+        # the caller keeps the previous result while the next call runs (results are owned arrays: a pinned buffer is only
+        # recycled once its arrays were dropped), so two page-locked buffers alternate; both exist after the warm-up
+        wavs = None
+        for _ in range(max(3, min(3, args.warmup))):
+            wavs, _ = step_e2e()
         barrier()
         t0 = time.perf_counter()
         ev0.record()
@@ -430,7 +460,7 @@ def run_b200(args):
         kernels, roofline = roofline_of(prof, prof_ms, args.steps, args.engine)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": DTYPES[args.engine],
+                "dtype": DTYPES[args.engine], "quality": QUALITY,
                 "data": "synthetic (seeded 5-min 7-ch pattern tiled; random-init v1.0-MC weights)",
                 "config": {"workload": f"CSS Conformer v1.0-MC + MVDR, 7-ch 16 kHz, {seconds / 60:.0f}-min synthetic meeting per GPU "
                                        f"({plan.num_segments} segments of 186 frames)",
@@ -453,6 +483,143 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_check(args):
+    """--check: the sharded path under the real process group (NCCL on the GPUs of this box) against the single-device path
+    on the same 2-minute meeting: permutations and activity masks bit-exact, waveforms to float32 round-off."""
+    import torch
+    import torch.distributed as dist
+    import notsofar_b200 as N
+    from notsofar_b200 import synth
+    from notsofar_b200.css import css_device
+    from notsofar_b200.sharded import css_device_sharded, make_shard
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    else:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1"); os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    seconds = args.check_seconds
+    x_np = synth.synthetic_meeting(seconds, seed=1)
+    n_total = len(x_np)
+    sep = N.ConformerCssB200(synth.random_state_dict(0), device=dev, segments_per_batch=args.segments_per_batch)
+    probe_cfg = N.CssCfg(show_progressbar=False)
+    plan = N.plan_segments(n_total, FS, probe_cfg)
+    x_full = torch.from_numpy(x_np).to(dev)
+    # a threshold inside the activity spread so that the gate (dilate / erode across the shard seams) is exercised; every
+    # rank derives the same one from the same single-device probe
+    probe = css_device(x_full, sep, FS, probe_cfg)
+    cfg = N.CssCfg(activity_th=float(torch.quantile(probe["activity"].flatten(), 0.9)), show_progressbar=False)
+    one = css_device(x_full, sep, FS, cfg)
+    sh = make_shard(plan, rank, world)
+    x_loc = x_full[sh.sample_lo:sh.sample_hi].contiguous()
+    out = css_device_sharded(x_loc, sep, FS, cfg, n_total)
+    torch.cuda.synchronize()
+    ok = torch.tensor([1], device=dev)
+    line = None
+    if rank == 0:
+        a, b = out["wav"], one["wav"]
+        rel = float((a - b).norm() / b.norm())
+        perms_equal = bool(np.array_equal(out["perms"], one["perms"]))
+        act_equal = bool(torch.equal(out["activity_b"], one["activity_b"]) and torch.equal(out["activity_final"], one["activity_final"]))
+        gate_on = float(one["activity_final"].float().mean())
+        good = perms_equal and act_equal and rel < 1e-5 and a.shape == b.shape
+        line = {"check": "sharded (NCCL) vs single-device css_device", "n_gpus": world, "seconds": seconds, "segments": plan.num_segments,
+                "wav_rel_l2": rel, "wav_max_abs": float((a - b).abs().max()), "perms_equal": perms_equal, "activity_equal": act_equal,
+                "activity_final_on_fraction": gate_on, "tolerance": 1e-5, "ok": bool(good)}
+        ok[0] = 1 if good else 0
+    dist.broadcast(ok, 0)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+    if int(ok.item()) != 1:
+        sys.exit(1)
+
+
+def run_session(args):
+    """--workload session: one NOTSOFAR-sized session (default 6 min) per GPU through the reference-facing plug-in call
+    css_inference -- 7 mono WAVs read from disk into pageable numpy, model resident, separated streams peak-normalised and
+    written as 16-bit WAVs -- everything inside the timed region (wall clock, max over ranks)."""
+    import tempfile
+    import pandas as pd
+    import scipy.io.wavfile as wf
+    import torch
+    import torch.distributed as dist
+    import notsofar_b200 as N
+    from notsofar_b200 import synth, _cabi
+    from notsofar_b200 import css as css_mod
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.load()
+    seconds = args.session_seconds
+    tmp = tempfile.mkdtemp(prefix=f"nsf_bench_r{rank}_")
+    x = synth.synthetic_meeting(seconds, seed=rank)
+    names = []
+    for c in range(7):
+        f = os.path.join(tmp, f"ch{c}.wav")
+        wf.write(f, FS, np.clip(np.rint(x[:, c] * 32768.0 * 8), -32768, 32767).astype(np.int16))
+        names.append(f)
+    model_dir = os.path.join(tmp, "models", "notsofar", "conformer1.0", "mc")
+    os.makedirs(model_dir)
+    torch.save({"model": {"module." + k: torch.from_numpy(np.asarray(v)) for k, v in synth.random_state_dict(0).items()}},
+               os.path.join(model_dir, "model.pt"))
+    open(os.path.join(model_dir, "cfg.yaml"), "w").write("single_channel: false\n")
+    session = pd.Series(dict(session_id=f"multichannel/MTG_bench_{rank}", meeting_id="MTG_bench", is_mc=True, wav_file_names=names))
+    cfg = N.CssCfg(show_progressbar=False, activity_th=0.3)
+    css_mod.ASYNC_WAV_WRITES = bool(args.async_wav)
+
+    def step(i):
+        return N.css_inference(os.path.join(tmp, f"out{i % 2}"), os.path.join(tmp, "models"), session, cfg, fetch_from_cache=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 1)):
+        step(i)
+    barrier()
+    launches0 = lib.nsf_launch_count()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    css_mod.flush_wav_writes()
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    launches = (lib.nsf_launch_count() - launches0) // args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if rank == 0:
+        n_out = (N.plan_segments(len(x), FS, cfg).mix_frames - 1) * 256 + 512
+        val = world * seconds / (ms / 1e3)
+        print(json.dumps({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES["2xbf16"],
+                          "quality": QUALITY, "data": "synthetic (seeded 7-ch session; random-init v1.0-MC weights)",
+                          "config": {"workload": f"css_inference plug-in call on a {seconds / 60:.0f}-min 7-ch 16 kHz session per GPU: 7 WAV files in "
+                                                 f"(pageable host memory), model resident, 1 + 3 peak-normalised PCM16 WAV files out",
+                                     "parallelism": f"{world} independent sessions (one per GPU)", "timing": "wall clock around the call, max over ranks",
+                                     "wav_writes": "asynchronous (flushed before the clock stops)" if args.async_wav else "synchronous (parallel writer threads)"},
+                          "e2e": {"value": val, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(len(x) * 7 * 4),
+                                  "d2h_bytes_per_step": int(3 * n_out * 4), "file_bytes_read": int(len(x) * 7 * 2), "file_bytes_written": int(4 * n_out * 2)},
+                          "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -468,6 +635,14 @@ def main():
     ap.add_argument("--multi", default="shard", choices=["shard", "replicas"],
                     help="N > 1: shard ONE N x --seconds meeting by segments over the ranks (default), or give every rank its own meeting")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: device-resident loop alone")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1, --multi shard: weak = one meeting of N x --seconds, strong = one meeting of --seconds split over the ranks")
+    ap.add_argument("--workload", default="meeting", choices=["meeting", "session"],
+                    help="meeting: BASELINE config 2 (default); session: a --session-seconds session per GPU through css_inference with file I/O")
+    ap.add_argument("--session-seconds", type=float, default=360.0)
+    ap.add_argument("--async-wav", action="store_true", help="--workload session: css_inference returns while the WAV files are still being written")
+    ap.add_argument("--check", action="store_true", help="compare the sharded path under the real process group with the single-device path")
+    ap.add_argument("--check-seconds", type=float, default=120.0)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world == 1 and args.gpus > 1 and args.impl == "b200":
@@ -477,6 +652,10 @@ def main():
         sys.exit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args)
+    elif args.check:
+        run_check(args)
+    elif args.workload == "session":
+        run_session(args)
     else:
         run_b200(args)
 

@@ -193,6 +193,11 @@ int nsf_istft(const float* S_st, int n_streams, int64_t T_long, float* wav, void
  * peak [n_streams] f32 scratch/output (max |x| per stream). */
 int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, float* peak, int16_t* pcm, void* stream);
 
+/* File boundary, input side.  Replaces load_audio (css/helpers.py:40-65: soundfile.read of 7 mono files, np.stack(axis=-1)) for
+ * 16-bit files: pcm [n_ch][n] int16 (one row per channel file) -> out [n][n_ch] f32 = pcm / 32768 (libsndfile's int16 -> float32
+ * scaling, exact).  n_ch <= 8. */
+int nsf_pcm16_to_float_interleaved(const int16_t* pcm, int n_ch, int64_t n, float* out, void* stream);
+
 /* CSS -> diarization hand-off without the disk round trip.  Replaces read_wav(normalize=True) (utils/audio_utils.py:10-34:
  * int16 / 32767) + the per-(word, scale) slicing and pad_sequence of extract_speaker_embedding_for_words
  * (diarization/word_based_diarization.py:78-104): out[i][j] = pcm[stream_id[i]][start[i] + j] / 32767 for j < len[i], else 0.

@@ -52,6 +52,7 @@ SIGNATURES = {
     "nsf_stitch_stft": (i32, [c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, i32, i32, i32, i32, i32, i64, c_f32p, C.c_void_p]),
     "nsf_istft": (i32, [c_f32p, i32, i64, c_f32p, C.c_void_p]),
     "nsf_peaknorm_pcm16": (i32, [c_f32p, i32, i64, c_f32p, C.c_void_p, C.c_void_p]),
+    "nsf_pcm16_to_float_interleaved": (i32, [C.c_void_p, i32, i64, c_f32p, C.c_void_p]),
     "nsf_attention_test_workspace_bytes": (i64, [i32, i32, i32, i32]),
     "nsf_attention_test": (i32, [c_f32p, c_f32p, c_f32p, c_f32p, i32, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_mask_apply": (i32, [c_f32p, i32, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, C.c_float, c_f32p, C.c_void_p]),

@@ -235,9 +235,35 @@ pcm16_kernel(const float* __restrict__ wav, int64_t n, const float* __restrict__
     }
 }
 
+// mono PCM16 channel files -> the [N][C] float32 recording the STFT reads (css/helpers.py:40-65 + soundfile's int16 -> float32
+// scaling x / 32768); tiled through shared memory so that both the per-channel reads and the interleaved writes coalesce
+__global__ void __launch_bounds__(256)
+pcm16_interleave_kernel(const int16_t* __restrict__ pcm, int64_t n, int C, float* __restrict__ out) {
+    __shared__ float tile[8][257];
+    const int64_t n0 = (int64_t)blockIdx.x * 256;
+    for (int c = 0; c < C; ++c) {
+        const int64_t j = n0 + threadIdx.x;
+        tile[c][threadIdx.x] = j < n ? (float)pcm[(size_t)c * n + j] * (1.f / 32768.f) : 0.f;
+    }
+    __syncthreads();
+    const int total = 256 * C;
+    for (int e = threadIdx.x; e < total; e += 256) {
+        const int t = e / C, c = e - t * C;
+        if (n0 + t < n) out[(size_t)(n0 + t) * C + c] = tile[c][t];
+    }
+}
+
 }  // namespace nsf
 
 using namespace nsf;
+
+extern "C" int nsf_pcm16_to_float_interleaved(const int16_t* pcm, int n_ch, int64_t n, float* out, void* stream) {
+    NSF_REQUIRE(pcm && out, "nsf_pcm16_to_float_interleaved: null pointer");
+    NSF_REQUIRE(n_ch >= 1 && n_ch <= 8 && n >= 0, "nsf_pcm16_to_float_interleaved: n_ch=%d n=%lld", n_ch, (long long)n);
+    if (n == 0) return NSF_OK;
+    pcm16_interleave_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(pcm, n, n_ch, out);
+    return check_launch("pcm16_interleave_kernel");
+}
 
 extern "C" int nsf_pit_cost(const void* in, int input_kind, int loss_kind, int n_seg, int n_ch_total, int n_spk,
                             int n_bins, int T, int overlap, float* cost, void* stream) {

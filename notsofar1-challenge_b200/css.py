@@ -582,9 +582,80 @@ def streams_to_pcm16(wav: "torch.Tensor") -> "torch.Tensor":
     return pcm
 
 
+# ---- file boundary helpers of css_inference: threaded WAV I/O, PCM16 in and out of the device ------------------------------------
+ASYNC_WAV_WRITES = False        # True: css_inference returns while its WAV files are still being written (flush_wav_writes waits)
+_WAV_POOL = None
+_WAV_PENDING: Dict[str, object] = {}
+
+
+def _wav_pool():
+    global _WAV_POOL
+    if _WAV_POOL is None:
+        import atexit
+        from concurrent.futures import ThreadPoolExecutor
+        _WAV_POOL = ThreadPoolExecutor(max_workers=8, thread_name_prefix="nsf-wav")
+        atexit.register(flush_wav_writes)
+    return _WAV_POOL
+
+
+def _write_pcm16_file(fname: str, pcm: np.ndarray, sr: int):
+    import os
+    import scipy.io.wavfile as wf
+    os.makedirs(os.path.dirname(fname), exist_ok=True)
+    wf.write(fname, sr, pcm)
+
+
+def flush_wav_writes(paths=None):
+    """Waits for the WAV files css_inference handed to its writer threads (all of them, or the given paths); re-raises a
+    writer's exception.  asr_inference / diarization_inference call it before they touch files; so does interpreter exit."""
+    import os
+    keys = list(_WAV_PENDING) if paths is None else [os.path.abspath(str(p)) for p in paths]
+    for k in keys:
+        fut = _WAV_PENDING.pop(k, None)
+        if fut is not None:
+            fut.result()
+
+
+def _read_pcm16_channels(wav_file_names):
+    """The channel files as one int16 array [C, n] (+ sample rate) when every file is mono PCM_16 of the same length and rate
+    -- the NOTSOFAR recordings are -- else None (the caller then goes through load_audio).  Files are read concurrently."""
+    import scipy.io.wavfile as wf
+
+    def read(f):
+        return wf.read(str(f), mmap=True)
+    try:
+        res = list(_wav_pool().map(read, wav_file_names))
+    except Exception:
+        return None
+    srs = {r[0] for r in res}
+    datas = [r[1] for r in res]
+    if len(srs) != 1 or any(d.dtype != np.int16 or d.ndim != 1 or d.size != datas[0].size for d in datas):
+        return None
+    return datas, int(res[0][0])
+
+
+def pcm16_to_device(datas, device) -> "torch.Tensor":
+    """List of C int16 arrays [n] -> x [n, C] float32 on the device = pcm / 32768 (nsf_pcm16_to_float_interleaved)."""
+    lib = _cabi.load()
+    n, c = datas[0].size, len(datas)
+    with torch.cuda.device(device):
+        pcm = torch.empty((c, n), dtype=torch.int16, device=device)
+        for k, d in enumerate(datas):
+            pcm[k].copy_(torch.from_numpy(np.asarray(d)), non_blocking=True)
+        x = torch.empty((n, c), dtype=torch.float32, device=device)
+        _cabi.check(lib.nsf_pcm16_to_float_interleaved(_cabi.ptr(pcm), c, n, _cabi.ptr(x), _cabi.stream_ptr()), "nsf_pcm16_to_float_interleaved")
+    return x
+
+
 def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_from_cache: bool):
     """Applies CSS to one session -- same signature, file layout and cache semantics as the reference's
-    css_inference (css/css.py:51-107).  Returns a copy of ``session`` with 'sep_wav_file_names'."""
+    css_inference (css/css.py:51-107).  Returns a copy of ``session`` with 'sep_wav_file_names'.
+
+    The file boundary is kept off the critical path: 16-bit channel files are read concurrently and uploaded as int16 (the
+    float conversion and the [N, C] interleave happen on the device), the separated streams are peak-normalised and quantised
+    to PCM_16 on the device (nsf_peaknorm_pcm16: the very samples write_wav would produce), so that 2 bytes per sample cross
+    PCIe instead of 4 and no host pass over the waveforms remains, and the four WAV files are written by parallel threads
+    (by default the call still returns only once they are on disk, like the reference)."""
     session_css = session.copy()
 
     assert isinstance(session.wav_file_names, list)
@@ -594,6 +665,7 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
 
     css_out_dir = Path(out_dir) / "css_inference" / session.session_id
     if fetch_from_cache and css_out_dir.exists():
+        flush_wav_writes()
         sep_wav_file_names = sorted(css_out_dir.glob('sep*.wav'))
         session_css['sep_wav_file_names'] = sep_wav_file_names
         # the files on disk are the truth for this run: drop any in-HBM copy an earlier call left for the same paths
@@ -609,25 +681,38 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
         _MODEL_CACHE[model_dir] = load_css_model(Path(model_dir), device=device)[0]
     separator = _MODEL_CACHE[model_dir]
     separator.eval()
-    mixwav, sr = load_audio(session.wav_file_names, is_mc=session.is_mc)
+    separator.to(device)
 
+    n_expected = 7 if session.is_mc else 1
+    assert len(session.wav_file_names) == n_expected, 'expecting 7 microphones' if session.is_mc else 'expecting one file'
+    fast = _read_pcm16_channels(session.wav_file_names)
+    if fast is not None:
+        datas, sr = fast
+        x = pcm16_to_device(datas, device)
+    else:                                                       # float / 24-bit / ragged files: the reference's host path
+        mixwav, sr = load_audio(session.wav_file_names, is_mc=session.is_mc)
+        x = torch.from_numpy(np.ascontiguousarray(mixwav[0], dtype=np.float32)).to(device)
     if cfg.slice_audio_for_debug:
-        mixwav = mixwav[:, sr * 20:sr * 30, :]
+        x = x[sr * 20:sr * 30].contiguous()
 
-    stages: dict = {}
-    separated_wavs, _ = separate_and_stitch(mixwav, separator, sr, device, cfg, return_side_info=False, _stages=stages)
-    # keep the streams of this session on the device for the stages downstream (asr_inference / diarization_inference)
-    pcm_dev = streams_to_pcm16(stages["wav"])
-    del stages
+    out = css_device(x, separator, sr, cfg)
+    # write_wav (utils/audio_utils.py:37-49) on the device: 0.99 peak normalisation + PCM_16 rounding of the three streams and
+    # of channel 0 of the input (input_mixture.wav); the int16 streams also stay in HBM for the stages downstream
+    pcm_dev = streams_to_pcm16(out["wav"])
+    mix_pcm = streams_to_pcm16(x[:, 0].contiguous()[None])
+    del out
+    pcm_host = pcm_dev.cpu().numpy()
+    mix_host = mix_pcm.cpu().numpy()[0]
 
-    write_wav(css_out_dir / 'input_mixture.wav', samps=mixwav[0, :, 0], sr=sr)
+    names = [str(css_out_dir / 'input_mixture.wav')] + [str(css_out_dir / f"sep_stream{i}.wav") for i in range(pcm_host.shape[0])]
+    import os
+    for fname, samps in zip(names, [mix_host] + [pcm_host[i] for i in range(pcm_host.shape[0])]):
+        flush_wav_writes([fname])                               # an earlier write of the same path must not overtake this one
+        _WAV_PENDING[os.path.abspath(fname)] = _wav_pool().submit(_write_pcm16_file, fname, samps, int(sr))
+    if not ASYNC_WAV_WRITES:
+        flush_wav_writes(names)
 
-    sep_wav_file_names = []
-    for i, w in enumerate(separated_wavs):
-        filename = css_out_dir / f"sep_stream{i}.wav"
-        write_wav(filename, samps=w, sr=sr)
-        sep_wav_file_names.append(str(filename))
-
+    sep_wav_file_names = names[1:]
     DEVICE_STREAMS.pop(_streams_key(sep_wav_file_names), None)
     DEVICE_STREAMS[_streams_key(sep_wav_file_names)] = (pcm_dev, int(sr))
     while len(DEVICE_STREAMS) > _DEVICE_STREAMS_KEEP:

@@ -297,6 +297,8 @@ def diarization_inference(out_dir: str, segments_df: pd.DataFrame, cfg: Diarizat
             if hit is not None:
                 pcm, sr = hit
         if pcm is None:
+            from .css import flush_wav_writes
+            flush_wav_writes(wav_files)
             pcm, sr = _load_streams_as_pcm(wav_files, device)
         out = word_based_clustering(pcm, sr, segments_df, cfg)
     else:

@@ -8,8 +8,9 @@ cross-segment dependency; only the permutation chain (css.py:266-285), the 50 %-
   1. all-gather of the 3x3 stitching costs of the owned segments (36 B / segment) -> every rank replays the
      6-permutation chain on the host and knows the global channel order of its block;
   2. all-gather of the per-frame mask means (12 B / frame) -> every rank runs the (global) dilate / erode gate;
-  3. gather of the separated waveforms of the owned frames to the rank that hands the streams to ASR /
-     diarization (3 x 4 B / sample; 345 MB per 30 min), where the 256-sample seams are overlap-added.
+  3. the separated waveforms of the owned frames go to the rank that hands the streams to ASR / diarization
+     (3 x 4 B / sample; 345 MB per 30 min): point-to-point, straight into their final place; only the 256-sample
+     seams between ranks are added there (gather_waveforms).
 
 Everything else (STFT of the rank's sample range, features, mask network, MVDR, local WOLA, iSTFT) is the
 single-GPU path of css.py on the rank's slice.  torch.distributed (NCCL over NVLink on the GPUs, gloo in the
@@ -134,6 +135,59 @@ def assemble_waveforms(pieces: Sequence[torch.Tensor], shards: Sequence[Shard], 
         assert p.shape[1] == n
         out[:, sh.own_lo * FRAME_HOP: sh.own_lo * FRAME_HOP + n] += p
     return out
+
+
+def gather_waveforms(piece: torch.Tensor, shards: Sequence[Shard], mix_frames: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
+    """The waveform hand-off without padding, zero-fill or full-size adds: rank ``dst`` receives the body of every piece
+    (its first n_own_frames*256 samples) straight into its final place in the [S, N'] output -- the bodies tile the time axis
+    exactly -- and only the 256-sample tails (the second half of each rank's last frame, which overlaps the next rank's first
+    256 samples) are added on top.  One point-to-point message per (rank, stream) plus one small one per rank."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    world = len(shards)
+    S = piece.shape[0]
+    sh = shards[rank]
+    n_out = (mix_frames - 1) * FRAME_HOP + FRAME_LEN
+    body = sh.n_own_frames * FRAME_HOP
+    assert piece.shape[1] == (body + FRAME_HOP if sh.n_own_frames else 0)
+    ops, tails = [], {}
+    if rank == dst:
+        out = torch.empty((S, n_out), dtype=piece.dtype, device=piece.device)
+        for r, s_r in enumerate(shards):
+            if s_r.n_own_frames == 0:
+                continue
+            lo, n = s_r.own_lo * FRAME_HOP, s_r.n_own_frames * FRAME_HOP
+            if r == rank:
+                out[:, lo:lo + n].copy_(piece[:, :n])
+                tails[r] = piece[:, n:]
+            else:
+                for k in range(S):
+                    ops.append(dist.P2POp(dist.irecv, out[k, lo:lo + n], _global_rank(r, group), group))
+                tails[r] = torch.empty((S, FRAME_HOP), dtype=piece.dtype, device=piece.device)
+                ops.append(dist.P2POp(dist.irecv, tails[r], _global_rank(r, group), group))
+    elif sh.n_own_frames:
+        tail = piece[:, body:].contiguous()
+        for k in range(S):
+            ops.append(dist.P2POp(dist.isend, piece[k, :body], _global_rank(dst, group), group))
+        ops.append(dist.P2POp(dist.isend, tail, _global_rank(dst, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if rank != dst:
+        return None
+    last = max((r for r, s_r in enumerate(shards) if s_r.n_own_frames), default=None)
+    for r, t in tails.items():
+        at = shards[r].own_hi * FRAME_HOP
+        if r == last:
+            out[:, at:at + FRAME_HOP].copy_(t)                        # the very end of the recording: nobody else writes it
+        else:
+            out[:, at:at + FRAME_HOP] += t
+    return out
+
+
+def _global_rank(r: int, group) -> int:
+    import torch.distributed as dist
+    return r if group is None else dist.get_global_rank(group, r)
 
 
 # ------------------------------------------------------------------------------------------- per-rank work
@@ -299,8 +353,7 @@ def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total
     mark("all-gather activity")
     out = wk.phase3(activity_all)
     mark("phase3 (gate + STFT WOLA + iSTFT)")
-    counts = [s.n_own_frames * FRAME_HOP + FRAME_HOP if s.n_own_frames else 0 for s in wk.shards]
-    pieces = gather_varlen(out["wav_piece"], counts, dst, group, dim=1)
+    wav = gather_waveforms(out["wav_piece"], wk.shards, wk.plan.mix_frames, dst, group)
     mark("gather waveforms")
     res = dict(activity_b=out["activity_b"], activity_final=out["activity_final"], perms=wk.perms, plan=wk.plan, shard=wk.sh,
                wav_piece=out["wav_piece"])        # this rank's own samples [S, n_own_frames*256 + 256], first sample own_lo*256
@@ -308,8 +361,7 @@ def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total
     if want_side_info:
         mask_pieces = gather_varlen(out["mask_piece"].contiguous(), [s.n_own_frames for s in wk.shards], dst, group, dim=1)
     if rank == dst:
-        res["wav"] = assemble_waveforms(pieces, wk.shards, wk.plan.mix_frames)
-        mark("assemble")
+        res["wav"] = wav
         if mask_pieces is not None:
             res["mask_stitched"] = torch.cat(mask_pieces, dim=1)
     return res

@@ -999,3 +999,41 @@ def test_results_of_three_retained_sessions_do_not_alias(nb, dev, small_weights)
     w2, _ = nb.separate_and_stitch(xs[0], sep, 16000, dev, cfg, return_side_info=False)
     assert len(css_mod._PINNED_POOL[(3, len(w2[0]))]) <= n_bufs          # a released buffer was reused, none added
     assert np.array_equal(w2[0], copies[0][0])
+
+
+def test_css_inference_float_wav_inputs_take_the_host_reader(nb, dev, small_weights, tmp_path):
+    """Channel files that are not PCM_16 (here IEEE-float WAVs) go through load_audio (css/helpers.py:40-65) instead of the int16
+    upload; the written streams are still exactly the device-side PCM16 hand-off copy."""
+    import pandas as pd
+    import scipy.io.wavfile as wf
+    from notsofar_b200 import synth
+    from notsofar_b200 import css as css_mod
+    model_dir = tmp_path / "models" / "notsofar" / "conformer1.0" / "mc"
+    model_dir.mkdir(parents=True)
+    torch.save({"model": {"module." + k: torch.from_numpy(np.asarray(v)) for k, v in small_weights.items()}}, model_dir / "model.pt")
+    (model_dir / "cfg.yaml").write_text("single_channel: false\n")
+    x = synth.synthetic_meeting(5.0, seed=10)
+    names = []
+    for c in range(7):
+        f = tmp_path / f"ch{c}.wav"
+        wf.write(str(f), 16000, (x[:, c] * 8).astype(np.float32))
+        names.append(str(f))
+    session = pd.Series(dict(session_id="multichannel/MTG_2_dev", meeting_id="MTG_2", is_mc=True, wav_file_names=names))
+    css_mod._MODEL_CACHE.clear()
+    assert css_mod._read_pcm16_channels(names) is None
+    out = nb.css_inference(str(tmp_path / "out"), str(tmp_path / "models"), session, nb.CssCfg(show_progressbar=False, activity_th=0.3), False)
+    hit = css_mod.device_streams_for(out.sep_wav_file_names)
+    for k, f in enumerate(out.sep_wav_file_names):
+        sr, pcm = wf.read(f)
+        assert sr == 16000 and np.array_equal(hit[0][k].cpu().numpy(), pcm)
+    # the same recording as PCM_16 files through the int16 upload: the device float input is pcm / 32768, bit for bit what the
+    # host reader produces for those files
+    names16 = []
+    for c in range(7):
+        f = tmp_path / f"i16_ch{c}.wav"
+        wf.write(str(f), 16000, np.clip(np.rint(x[:, c] * 32768.0 * 8), -32768, 32767).astype(np.int16))
+        names16.append(str(f))
+    datas, sr = css_mod._read_pcm16_channels(names16)
+    x_dev = css_mod.pcm16_to_device(datas, dev).cpu().numpy()
+    x_host, sr2 = css_mod.load_audio(names16, is_mc=True)
+    assert sr == sr2 == 16000 and np.array_equal(x_dev, x_host[0])

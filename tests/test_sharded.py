@@ -90,7 +90,7 @@ def _free_port():
 def _gloo_worker(rank, world, port, n_samples, ret):
     import torch.distributed as dist
     import notsofar_b200 as N
-    from notsofar_b200.sharded import make_shard, allgather_varlen, gather_varlen, assemble_waveforms
+    from notsofar_b200.sharded import make_shard, allgather_varlen, gather_varlen, assemble_waveforms, gather_waveforms
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -123,15 +123,18 @@ def _gloo_worker(rank, world, port, n_samples, ret):
             p[:, o:o + 512] += frames[:, t]
         counts = [s.n_own_frames * 256 + 256 if s.n_own_frames else 0 for s in shards]
         pieces = gather_varlen(torch.from_numpy(p), counts, dst=0, dim=1)
+        direct = gather_waveforms(torch.from_numpy(p), shards, plan.mix_frames, dst=0)
         if rank == 0:
             got = assemble_waveforms(pieces, shards, plan.mix_frames).numpy()
             ref = np.zeros_like(got)
             for t in range(plan.mix_frames):
                 ref[:, t * 256:t * 256 + 512] += frames[:, t]
             assert np.array_equal(got, ref)
+            # the point-to-point hand-off (bodies in place + seam adds): a + b against (0 + a) + b -- the same float32
+            assert np.array_equal(direct.numpy(), ref)
             ret["perms"] = perms
         else:
-            assert pieces is None
+            assert pieces is None and direct is None
         ret[f"ok{rank}"] = True
     finally:
         dist.destroy_process_group()
