@@ -241,6 +241,16 @@ int64_t nsf_whisper_mel_plane_elems(int n_mels, int n_batch);
  * filters [n_mels][201] f32 (slaney mel filterbank); log_spec [n_batch][n_mels][3000] f32 and gmax [n_batch] u32 are scratch. */
 int nsf_whisper_logmel(const float* audio, int n_batch, int64_t n_samples, const float* filters, int n_mels, float* log_spec,
                        uint32_t* gmax, void* mel_hi, void* mel_lo, void* stream);
+/* Whole-recording front end of transcribe() (whisper/audio.py log_mel_spectrogram with padding = 30 s, whisper/transcribe.py
+ * [upstream]; call site asr/asr.py:74): audio [n_samples] f32 (the recording followed by 30 s of zeros) -> log_spec [n_mels][n_frames]
+ * f32 = log10(max(mel power, 1e-10)) of the n_frames = n_samples / 160 centred frames (reflect padding at both ends) and gmax
+ * [1] = its order-encoded maximum; nsf_whisper_mel_windows then cuts n_windows 30-s windows starting at frames seeks[] (device
+ * int32) holding sizes[] content frames each (NULL: 3000; the rest of a window is zero like pad_or_trim) and applies
+ * max(., gmax - 8), (. + 4) / 4: the recording-wide normalisation of the reference, not a per-window one. */
+int nsf_whisper_logmel_recording(const float* audio, int64_t n_samples, const float* filters, int n_mels, int64_t n_frames,
+                                 float* log_spec, uint32_t* gmax, void* stream);
+int nsf_whisper_mel_windows(const float* log_spec, int64_t n_frames, const uint32_t* gmax, int n_mels, const int32_t* seeks,
+                            const int32_t* sizes, int n_windows, void* mel_hi, void* mel_lo, void* stream);
 /* out [n_batch * 1500][d_model] f32 = ln_post(encoder(mel)); out_bf16 (optional): the same as a bf16 plane, the operand
  * nsf_whisper_decoder_prefill_cross reads */
 int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* mel_hi, const void* mel_lo, int n_batch, float* out, void* out_bf16,
@@ -263,6 +273,17 @@ int nsf_whisper_decoder_prefill_cross(nsf_whisper_decoder* h, const void* enc_bf
 int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* tokens, int pos, int n_batch, void* state, int64_t state_bytes,
                              float* logits_out, int32_t* next_tokens, void* stream);
 
+/* One decoder position without the sampling bookkeeping: logits_out [n_batch][vocab] f32 of tokens[b] at position *pos_dev (the
+ * self-attention keys / values of that position are appended to the caches).  Beam search and temperature sampling
+ * (whisper/decoding.py BeamSearchDecoder / GreedyDecoder [upstream]; the reference decodes with beam_size = 5, asr/asr.py:17-21,52-56)
+ * choose the next tokens from these logits on the host side of the API; nsf_whisper_decoder_reorder then makes sequence b
+ * continue the hypothesis of slot src[b] (rearrange_kv_cache [upstream]): rows [0, *n_pos_dev) of the self-attention caches are
+ * permuted through `scratch` (nsf_whisper_decoder_reorder_scratch_bytes). */
+int nsf_whisper_decoder_forward(nsf_whisper_decoder* h, const int32_t* tokens, const int32_t* pos_dev, int n_batch, void* state,
+                                int64_t state_bytes, float* logits_out, void* stream);
+int64_t nsf_whisper_decoder_reorder_scratch_bytes(const nsf_whisper_dec_dims* dims, int n_batch);
+int nsf_whisper_decoder_reorder(nsf_whisper_decoder* h, const int32_t* src, const int32_t* n_pos_dev, int n_batch, void* state,
+                                int64_t state_bytes, void* scratch, int64_t scratch_bytes, void* stream);
 /* The same step with all loop state on the device, so that one captured CUDA graph can be replayed for every position:
  * consumes cur_tokens [n_batch] at position *pos_dev, then (one bookkeeping kernel) records the arg-max in
  * argmaxes[b][pos+1], chooses the token fed next -- forced[b][pos+1] if >= 0 (prompt / teacher forcing), eot once the

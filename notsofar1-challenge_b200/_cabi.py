@@ -64,6 +64,8 @@ SIGNATURES = {
     "nsf_whisper_encoder_workspace_bytes": (i64, [C.c_void_p, i32]),
     "nsf_whisper_mel_plane_elems": (i64, [i32, i32]),
     "nsf_whisper_logmel": (i32, [c_f32p, i32, i64, c_f32p, i32, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsf_whisper_logmel_recording": (i32, [c_f32p, i64, c_f32p, i32, i64, c_f32p, C.c_void_p, C.c_void_p]),
+    "nsf_whisper_mel_windows": (i32, [c_f32p, i64, C.c_void_p, i32, C.c_void_p, C.c_void_p, i32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsf_whisper_encoder_forward": (i32, [C.c_void_p, C.c_void_p, C.c_void_p, i32, c_f32p, C.c_void_p, C.c_void_p, i64, C.c_void_p]),
     "nsf_whisper_decoder_num_offsets": (i64, [C.c_void_p]),
     "nsf_whisper_decoder_create": (i32, [C.c_void_p, c_f32p, i64, C.POINTER(i64), i32, C.POINTER(C.c_void_p)]),
@@ -72,6 +74,9 @@ SIGNATURES = {
     "nsf_whisper_decoder_prefill_cross": (i32, [C.c_void_p, C.c_void_p, i32, C.c_void_p, i64, C.c_void_p]),
     "nsf_whisper_decoder_step_dev": (i32, [C.c_void_p, C.c_void_p, C.c_void_p, i32, C.c_void_p, i64, C.c_void_p, i32, i32, C.c_void_p,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsf_whisper_decoder_forward": (i32, [C.c_void_p, C.c_void_p, C.c_void_p, i32, C.c_void_p, i64, c_f32p, C.c_void_p]),
+    "nsf_whisper_decoder_reorder_scratch_bytes": (i64, [C.c_void_p, i32]),
+    "nsf_whisper_decoder_reorder": (i32, [C.c_void_p, C.c_void_p, C.c_void_p, i32, C.c_void_p, i64, C.c_void_p, i64, C.c_void_p]),
     "nsf_whisper_decoder_step": (i32, [C.c_void_p, C.c_void_p, i32, i32, C.c_void_p, i64, c_f32p, C.c_void_p, C.c_void_p]),
     "nsf_flash_attention_test_workspace_bytes": (i64, [i32, i32, i32]),
     "nsf_flash_attention_test": (i32, [c_f32p, c_f32p, c_f32p, i32, i32, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),

@@ -2,10 +2,11 @@
 reference's signature, cache file, per-stream loop and segments_df layout (asr.py:31-101).
 
 The transcription itself is openai-whisper in the reference (``whisper.load_model`` / ``model.transcribe``, asr.py:69-74):
-a third-party package that is absent offline together with its weights and tokenizer (parity unpinned).
-It is reached through one plug-in point, ``set_transcriber``; a transcriber gets a stream (a WAV path, or -- extension --
-the device-resident PCM16 stream the CSS stage produced) and returns whisper's result dict
-``{'segments': [{'start', 'end', 'text', 'words': [{'word', 'start', 'end'}, ...]}, ...]}``.
+a third-party package that is absent offline together with its weights and vocabulary (parity unpinned).  Here it
+is ``whisper_asr.WhisperB200Transcriber`` -- log-mel, encoder, beam-search / fallback decoding, word timestamps on the in-tree
+kernels -- built from ``NSF_WHISPER_CKPT`` + ``NSF_WHISPER_VOCAB`` on first use, or registered explicitly with
+``set_transcriber``; a transcriber gets a stream (a WAV path, or the device-resident PCM16 stream the CSS stage left in HBM)
+and returns whisper's result dict ``{'segments': [{'start', 'end', 'text', 'words': [{'word', 'start', 'end'}, ...]}, ...]}``.
 """
 from __future__ import annotations
 
@@ -73,17 +74,33 @@ def asr_inference(out_dir: str, session: pd.Series, cfg: WhisperAsrCfg, fetch_fr
     out_file = Path(out_dir) / 'asr' / session.session_id / cfg.model_name / "all_segments_df.pkl"
     if fetch_from_cache and out_file.exists():
         return pd.read_pickle(out_file)
-    if _TRANSCRIBER is None:
-        from ._cabi import NsfError
-        raise NsfError("asr_inference needs a transcriber (the reference's is openai-whisper, absent offline: SURVEY 8c); "
-                       "register one with notsofar_b200.asr.set_transcriber")
+    transcriber = _TRANSCRIBER
+    if transcriber is None:
+        from .whisper_asr import transcriber_from_env
+        transcriber = transcriber_from_env()              # NSF_WHISPER_CKPT + NSF_WHISPER_VOCAB
+        if transcriber is None:
+            from ._cabi import NsfError
+            raise NsfError("asr_inference needs Whisper weights and vocabulary (the reference downloads them through openai-whisper, asr.py:69; "
+                           "there is no network here): set NSF_WHISPER_CKPT and NSF_WHISPER_VOCAB, or register a transcriber with "
+                           "notsofar_b200.asr.set_transcriber")
+        set_transcriber(transcriber)
+    if streams is None:
+        # the separated streams the CSS stage of this process left in HBM (the very samples of the WAV files), else the files
+        from .css import device_streams_for, flush_wav_writes
+        hit = device_streams_for(wav_files)
+        if hit is not None and hit[1] == 16000:
+            streams = [hit[0][i] for i in range(len(wav_files))]
+        else:
+            flush_wav_writes(wav_files)
     dfs = []
     for i, wav_file in enumerate(wav_files):
-        results = _TRANSCRIBER(streams[i] if streams is not None else str(wav_file), cfg, options)
+        results = transcriber(streams[i] if streams is not None else str(wav_file), cfg, options)
         df = segments_frame(results, session, wav_file)
         if df is not None:
             dfs.append(df)
-    all_segments_df = pd.concat(dfs, ignore_index=True)
+    # (the reference's pd.concat raises on an all-silent session; an empty frame with the same columns is returned instead)
+    all_segments_df = pd.concat(dfs, ignore_index=True) if dfs else pd.DataFrame(
+        columns=['start_time', 'end_time', 'text', 'word_timing', 'meeting_id', 'session_id', 'wav_file_name'])
     out_file.parent.mkdir(parents=True, exist_ok=True)
     all_segments_df.to_pickle(out_file)
     return all_segments_df

@@ -52,7 +52,7 @@ __device__ __forceinline__ float wh_unorder(unsigned u) {
 // filterbank, log10.  log_spec [B][n_mels][3000] f32; gmax [B] order-encoded running maximum.
 __global__ void __launch_bounds__(256)
 wh_logmel_kernel(const float* __restrict__ audio, int64_t n_samples, const float* __restrict__ filters, int n_mels,
-                 float* __restrict__ log_spec, unsigned* __restrict__ gmax) {
+                 float* __restrict__ log_spec, unsigned* __restrict__ gmax, int64_t n_frames) {
     __shared__ float xw[kWhNfft];
     __shared__ float2 tw[kWhNfft];
     __shared__ float pw[kWhBins];
@@ -86,7 +86,7 @@ wh_logmel_kernel(const float* __restrict__ audio, int64_t n_samples, const float
         float acc = 0.f;
         for (int k = 0; k < kWhBins; ++k) acc = fmaf(__ldg(f + k), pw[k], acc);
         const float v = log10f(fmaxf(acc, 1e-10f));
-        log_spec[((size_t)b * n_mels + m) * kWhFrames + t] = v;
+        log_spec[((size_t)b * n_mels + m) * n_frames + t] = v;
         mx = fmaxf(mx, v);
     }
     mx = warp_max(mx);
@@ -109,6 +109,25 @@ wh_logmel_finish_kernel(const float* __restrict__ log_spec, const unsigned* __re
         const int row = (int)(e / n_mels), m = (int)(e - (int64_t)row * n_mels);
         float v = 0.f;
         if (row >= 1 && row <= kWhFrames) v = (fmaxf(log_spec[((size_t)b * n_mels + m) * kWhFrames + row - 1], floor_) + 4.f) * 0.25f;
+        split_store(SPLIT_BF16, mel_hi, mel_lo, (size_t)b * n + e, v);
+    }
+}
+
+// one 30-s window of a whole-recording log-mel (normalised with the recording's maximum, whisper/audio.py:150-155 [upstream]):
+// max(., gmax - 8), (. + 4) / 4 of frames [seek, seek + 3000) (zero beyond the recording = pad_or_trim), time-major bf16 planes
+__global__ void __launch_bounds__(256)
+wh_mel_window_kernel(const float* __restrict__ log_spec, int64_t n_frames, const unsigned* __restrict__ gmax, int n_mels,
+                     const int32_t* __restrict__ seeks, const int32_t* __restrict__ sizes, float* __restrict__ mel_hi, float* __restrict__ mel_lo) {
+    const int b = blockIdx.y;
+    const float floor_ = wh_unorder(gmax[0]) - 8.f;
+    const int64_t seek = seeks[b];
+    const int size = sizes ? sizes[b] : kWhFrames;                  // frames of the window that hold content; the rest is zero (pad_or_trim)
+    const int64_t n = (int64_t)kWhPadRows * n_mels;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / n_mels), m = (int)(e - (int64_t)row * n_mels);
+        float v = 0.f;
+        const int64_t t = seek + row - 1;
+        if (row >= 1 && row <= size && t < n_frames) v = (fmaxf(log_spec[(size_t)m * n_frames + t], floor_) + 4.f) * 0.25f;
         split_store(SPLIT_BF16, mel_hi, mel_lo, (size_t)b * n + e, v);
     }
 }
@@ -215,10 +234,33 @@ extern "C" int nsf_whisper_logmel(const float* audio, int n_batch, int64_t n_sam
     if (rc) return rc;
     NSF_CUDA(cudaMemsetAsync(gmax, 0, sizeof(uint32_t) * n_batch, s));        // order-encoded: 0 is below every float
     ProfScope prof(PROF_FEATURES, (double)n_batch * (kWhSamples * 4.0 + 2.0 * kWhPadRows * n_mels * 2.0), s);
-    wh_logmel_kernel<<<dim3(kWhFrames, n_batch), 256, 0, s>>>(audio, n_samples, filters, n_mels, log_spec, gmax);
+    wh_logmel_kernel<<<dim3(kWhFrames, n_batch), 256, 0, s>>>(audio, n_samples, filters, n_mels, log_spec, gmax, kWhFrames);
     if ((rc = check_launch("wh_logmel_kernel"))) return rc;
     wh_logmel_finish_kernel<<<dim3(64, n_batch), 256, 0, s>>>(log_spec, gmax, n_mels, reinterpret_cast<float*>(mel_hi), reinterpret_cast<float*>(mel_lo));
     return check_launch("wh_logmel_finish_kernel");
+}
+
+extern "C" int nsf_whisper_logmel_recording(const float* audio, int64_t n_samples, const float* filters, int n_mels, int64_t n_frames,
+                                            float* log_spec, uint32_t* gmax, void* stream_) {
+    NSF_REQUIRE(audio && filters && log_spec && gmax, "nsf_whisper_logmel_recording: null pointer");
+    NSF_REQUIRE(n_samples >= kWhNfft && n_mels >= 1 && n_frames >= 1 && n_frames <= n_samples / kWhHop && n_frames <= 0x7fffffff,
+                "nsf_whisper_logmel_recording: n_samples=%lld n_frames=%lld", (long long)n_samples, (long long)n_frames);
+    cudaStream_t s = (cudaStream_t)stream_;
+    int rc = wh_ensure_tables(s);
+    if (rc) return rc;
+    NSF_CUDA(cudaMemsetAsync(gmax, 0, sizeof(uint32_t), s));
+    ProfScope prof(PROF_FEATURES, (double)n_samples * 4.0 + (double)n_frames * n_mels * 4.0, s);
+    wh_logmel_kernel<<<dim3((unsigned)n_frames, 1), 256, 0, s>>>(audio, n_samples, filters, n_mels, log_spec, gmax, n_frames);
+    return check_launch("wh_logmel_kernel");
+}
+
+extern "C" int nsf_whisper_mel_windows(const float* log_spec, int64_t n_frames, const uint32_t* gmax, int n_mels, const int32_t* seeks,
+                                       const int32_t* sizes, int n_windows, void* mel_hi, void* mel_lo, void* stream_) {
+    NSF_REQUIRE(log_spec && gmax && seeks && mel_hi && mel_lo, "nsf_whisper_mel_windows: null pointer");
+    NSF_REQUIRE(n_windows >= 1 && n_windows <= 65535 && n_mels >= 1 && n_frames >= 1, "nsf_whisper_mel_windows: bad sizes");
+    wh_mel_window_kernel<<<dim3(64, n_windows), 256, 0, (cudaStream_t)stream_>>>(log_spec, n_frames, gmax, n_mels, seeks, sizes,
+                                                                                 reinterpret_cast<float*>(mel_hi), reinterpret_cast<float*>(mel_lo));
+    return check_launch("wh_mel_window_kernel");
 }
 
 extern "C" int nsf_whisper_encoder_forward(nsf_whisper_encoder* h, const void* mel_hi, const void* mel_lo, int n_batch, float* out,

@@ -285,6 +285,21 @@ namespace nsf {
 
 static inline int64_t wd_align(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// beam search: sequence b continues the hypothesis that sat in slot src[b] (whisper/decoding.py PyTorchInference.rearrange_kv_cache
+// [upstream]).  Rows [0, *n_pos) of every (layer, sequence, head) self-attention cache go through a scratch copy (gather, then
+// copy back: a permutation cannot be applied in place without cycles).
+__global__ void __launch_bounds__(256)
+wd_cache_gather_kernel(const uint16_t* __restrict__ src_cache, uint16_t* __restrict__ dst_cache, const int32_t* __restrict__ src,
+                       const int32_t* __restrict__ n_pos, int n_heads, int n_text_ctx, int64_t layer_stride, int from_scratch) {
+    const int bh = blockIdx.x, L = blockIdx.y;
+    const int b = bh / n_heads, hd = bh - b * n_heads;
+    const int sb = from_scratch ? b : src[b];
+    const int n = min(*n_pos, n_text_ctx) * 64 / 8;                 // 16-byte words
+    const uint4* s4 = reinterpret_cast<const uint4*>(src_cache + (size_t)L * layer_stride + ((size_t)sb * n_heads + hd) * n_text_ctx * 64);
+    uint4* d4 = reinterpret_cast<uint4*>(dst_cache + (size_t)L * layer_stride + ((size_t)b * n_heads + hd) * n_text_ctx * 64);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d4[i] = s4[i];
+}
+
 struct WdState {
     uint16_t *ck, *cv, *sk, *sv;       // cross / self caches: [L][n_bh][t][64]
     float *x, *qkv, *qc, *logits;
@@ -456,6 +471,39 @@ extern "C" int nsf_whisper_decoder_step(nsf_whisper_decoder* h, const int32_t* t
     int rc = check_launch("wd_set_int_kernel");
     if (rc) return rc;
     return wd_step_impl(h, tokens, st.pos, n_batch, state, state_bytes, logits_out, next_tokens, s);
+}
+
+extern "C" int nsf_whisper_decoder_forward(nsf_whisper_decoder* h, const int32_t* tokens, const int32_t* pos_dev, int n_batch, void* state,
+                                           int64_t state_bytes, float* logits_out, void* stream_) {
+    NSF_REQUIRE(h && tokens && pos_dev && state && logits_out, "nsf_whisper_decoder_forward: null pointer");
+    NSF_REQUIRE(n_batch >= 1, "nsf_whisper_decoder_forward: n_batch=%d", n_batch);
+    WdState st = wd_carve(h->dims, n_batch, reinterpret_cast<unsigned char*>(state));
+    return wd_step_impl(h, tokens, pos_dev, n_batch, state, state_bytes, logits_out, st.next, (cudaStream_t)stream_);
+}
+
+extern "C" int64_t nsf_whisper_decoder_reorder_scratch_bytes(const nsf_whisper_dec_dims* dims, int n_batch) {
+    if (!dims || n_batch <= 0) return 0;
+    return 2 * (int64_t)dims->n_layers * n_batch * dims->n_heads * dims->n_text_ctx * 64 * 2;
+}
+
+extern "C" int nsf_whisper_decoder_reorder(nsf_whisper_decoder* h, const int32_t* src, const int32_t* n_pos_dev, int n_batch, void* state,
+                                           int64_t state_bytes, void* scratch, int64_t scratch_bytes, void* stream_) {
+    NSF_REQUIRE(h && src && n_pos_dev && state && scratch, "nsf_whisper_decoder_reorder: null pointer");
+    const nsf_whisper_dec_dims& D = h->dims;
+    NSF_REQUIRE(n_batch >= 1 && ((uintptr_t)state & 255) == 0 && ((uintptr_t)scratch & 15) == 0, "nsf_whisper_decoder_reorder: bad arguments");
+    WdState st = wd_carve(D, n_batch, reinterpret_cast<unsigned char*>(state));
+    NSF_REQUIRE(state_bytes >= st.total_bytes && scratch_bytes >= nsf_whisper_decoder_reorder_scratch_bytes(&D, n_batch),
+                "nsf_whisper_decoder_reorder: state or scratch too small");
+    cudaStream_t s = (cudaStream_t)stream_;
+    const int64_t layer_stride = (int64_t)n_batch * D.n_heads * D.n_text_ctx * 64;
+    uint16_t* tk = reinterpret_cast<uint16_t*>(scratch);
+    uint16_t* tv = tk + (size_t)D.n_layers * layer_stride;
+    const dim3 grid((unsigned)(n_batch * D.n_heads), (unsigned)D.n_layers);
+    wd_cache_gather_kernel<<<grid, 256, 0, s>>>(st.sk, tk, src, n_pos_dev, D.n_heads, D.n_text_ctx, layer_stride, 0);
+    wd_cache_gather_kernel<<<grid, 256, 0, s>>>(st.sv, tv, src, n_pos_dev, D.n_heads, D.n_text_ctx, layer_stride, 0);
+    wd_cache_gather_kernel<<<grid, 256, 0, s>>>(tk, st.sk, src, n_pos_dev, D.n_heads, D.n_text_ctx, layer_stride, 1);
+    wd_cache_gather_kernel<<<grid, 256, 0, s>>>(tv, st.sv, src, n_pos_dev, D.n_heads, D.n_text_ctx, layer_stride, 1);
+    return check_launch("wd_cache_gather_kernel");
 }
 
 extern "C" int nsf_whisper_decoder_step_dev(nsf_whisper_decoder* h, int32_t* cur_tokens, int32_t* pos_dev, int n_batch, void* state,

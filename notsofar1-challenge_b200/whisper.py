@@ -208,6 +208,38 @@ class WhisperEncoderB200:
         hi, lo, _ = self.log_mel(audio)
         return self.encode_mel(hi, lo)
 
+    def log_mel_recording(self, audio: torch.Tensor):
+        """The front end of transcribe() [upstream whisper/transcribe.py: log_mel_spectrogram(audio, n_mels, padding=N_SAMPLES)]:
+        audio [n] float32 on the device -> (log_spec [n_mels, n_frames] before the clamp, gmax [1] order-encoded recording
+        maximum, content_frames = n_frames - 3000).  The 30 s of zero padding are appended here."""
+        assert audio.is_cuda and audio.dtype == torch.float32 and audio.dim() == 1
+        n = audio.shape[0]
+        padded = torch.zeros((n + N_SAMPLES,), dtype=torch.float32, device=audio.device)
+        padded[:n] = audio
+        n_frames = (n + N_SAMPLES) // HOP
+        nm = self.dims.n_mels
+        log_spec = torch.empty((nm, n_frames), dtype=torch.float32, device=audio.device)
+        gmax = torch.empty((1,), dtype=torch.int32, device=audio.device)
+        with torch.cuda.device(audio.device):
+            _cabi.check(self._lib.nsf_whisper_logmel_recording(_cabi.ptr(padded), n + N_SAMPLES, _cabi.ptr(self._filters), nm, n_frames,
+                                                               _cabi.ptr(log_spec), _cabi.ptr(gmax), _cabi.stream_ptr()), "nsf_whisper_logmel_recording")
+        return log_spec, gmax, n_frames - N_FRAMES
+
+    def mel_windows(self, log_spec: torch.Tensor, gmax: torch.Tensor, seeks, sizes=None):
+        """30-s windows of a recording's log-mel starting at mel frames ``seeks`` with ``sizes`` content frames each (the rest is
+        zero: pad_or_trim), normalised with the recording's maximum -> (mel_hi, mel_lo) int16 [n, 3002, n_mels] for ``encode_mel``."""
+        nm, n_frames = log_spec.shape
+        B = len(seeks)
+        dev = log_spec.device
+        sk = torch.tensor([int(v) for v in seeks], dtype=torch.int32, device=dev)
+        sz = None if sizes is None else torch.tensor([int(v) for v in sizes], dtype=torch.int32, device=dev)
+        hi = torch.empty((B, PAD_ROWS, nm), dtype=torch.int16, device=dev)
+        lo = torch.empty_like(hi)
+        with torch.cuda.device(dev):
+            _cabi.check(self._lib.nsf_whisper_mel_windows(_cabi.ptr(log_spec), n_frames, _cabi.ptr(gmax), nm, _cabi.ptr(sk), _cabi.ptr(sz), B,
+                                                          _cabi.ptr(hi), _cabi.ptr(lo), _cabi.stream_ptr()), "nsf_whisper_mel_windows")
+        return hi, lo
+
 
 # ------------------------------------------------------------------------------------------- text decoder (greedy)
 class WhisperDecDims(C.Structure):
@@ -466,6 +498,68 @@ class WhisperB200:
                                                               _cabi.ptr(out16), _cabi.ptr(enc._ws), need, _cabi.stream_ptr()),
                         "nsf_whisper_encoder_forward")
         return out, out16
+
+    def log_mel_recording(self, audio: torch.Tensor):
+        return self.encoder.log_mel_recording(audio)
+
+    def mel_windows(self, log_spec, gmax, seeks, sizes=None):
+        return self.encoder.mel_windows(log_spec, gmax, seeks, sizes)
+
+    # ---- one decoder position at a time with the logits handed back: the engine under beam search / temperature sampling --------
+    def begin_sequences(self, enc_bf16: torch.Tensor):
+        """Projects the cross-attention keys / values of enc_bf16 int16 [B, 1500, d] and resets the position: ``step_logits`` then
+        feeds one token per sequence and position."""
+        B = enc_bf16.shape[0]
+        need = self._ensure_state(B)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.nsf_whisper_decoder_prefill_cross(self._dh, _cabi.ptr(enc_bf16.contiguous()), B, _cabi.ptr(self._state), need,
+                                                                    _cabi.stream_ptr()), "nsf_whisper_decoder_prefill_cross")
+        key = (B, self._state.data_ptr())
+        if getattr(self, "_fwd", None) is None:
+            self._fwd = {}
+        if key not in self._fwd:
+            bufs = dict(cur=torch.zeros((B,), dtype=torch.int32, device=self.device), pos=torch.zeros((1,), dtype=torch.int32, device=self.device),
+                        logits=torch.empty((B, self.dec_dims.vocab), dtype=torch.float32, device=self.device))
+
+            def launch():
+                _cabi.check(self._lib.nsf_whisper_decoder_forward(self._dh, _cabi.ptr(bufs["cur"]), _cabi.ptr(bufs["pos"]), B, _cabi.ptr(self._state),
+                                                                  need, _cabi.ptr(bufs["logits"]), _cabi.stream_ptr()), "nsf_whisper_decoder_forward")
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                launch()
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                launch()
+            self._fwd[key] = (bufs, g)
+        self._cur_fwd = self._fwd[key]
+        self._cur_fwd[0]["pos"].zero_()
+        return B
+
+    def step_logits(self, tokens: torch.Tensor) -> torch.Tensor:
+        """tokens int32 [B] at the current position -> logits [B, vocab] (a view that the next call overwrites); the position
+        advances by one."""
+        bufs, g = self._cur_fwd
+        bufs["cur"].copy_(tokens.to(torch.int32))
+        g.replay()
+        bufs["pos"] += 1
+        return bufs["logits"]
+
+    def reorder_sequences(self, src: torch.Tensor):
+        """Sequence b continues the hypothesis of slot src[b] (beam search): permutes the self-attention caches up to the current
+        position (rearrange_kv_cache [upstream])."""
+        bufs, _ = self._cur_fwd
+        B = bufs["cur"].shape[0]
+        need = self._ensure_state(B)
+        sb = int(self._lib.nsf_whisper_decoder_reorder_scratch_bytes(C.byref(self.dec_dims), B))
+        if getattr(self, "_scratch", None) is None or self._scratch.numel() < sb:
+            self._scratch = torch.empty(sb, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.nsf_whisper_decoder_reorder(self._dh, _cabi.ptr(src.to(device=self.device, dtype=torch.int32).contiguous()), _cabi.ptr(bufs["pos"]),
+                                                              B, _cabi.ptr(self._state), need, _cabi.ptr(self._scratch), sb, _cabi.stream_ptr()),
+                        "nsf_whisper_decoder_reorder")
 
     def _ensure_state(self, B: int):
         need = int(self._lib.nsf_whisper_decoder_state_bytes(C.byref(self.dec_dims), B))
