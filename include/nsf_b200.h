@@ -141,6 +141,13 @@ int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float* X, int64_t
              int64_t seg_first, int n_seg, int T, int hop, int n_bins, float mask_floor,
              float* Y, void* stream);
 
+/* The same beamformer on ONE utterance of any length (make_mvdr accepts any T, mvdr_util.py:5-47; BASELINE config 5): one covariance
+ * set per bin over all T frames, accumulated by T-chunks in parallel (partial sums -> per-bin solve -> apply).
+ * masks [S+Nn][n_bins][T], X [n_bins][T][C], Y [S][n_bins][T]; workspace: nsf_mvdr_utterance_workspace_bytes, 16-byte aligned. */
+int64_t nsf_mvdr_utterance_workspace_bytes(int n_spk, int64_t T, int n_bins);
+int nsf_mvdr_utterance(const float* masks, int n_spk, int n_noise, const float* X, int64_t T, int n_ch, int n_bins, float mask_floor,
+                       float* Y, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Separation without the beamformer (single-channel input, or CssCfg.mc_mvdr = False): css.py:218-227,
  *   Y[seg][s][f][t] = X[f][(seg_first+seg)*hop + t][channel 0] * max(masks[seg][s][f][t], mask_floor).
  * Layouts and segment geometry as in nsf_mvdr; X may have any number of channels (the reference channel is 0). */

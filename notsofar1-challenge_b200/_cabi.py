@@ -46,6 +46,8 @@ SIGNATURES = {
     "nsf_conformer_workspace_bytes": (i64, [C.POINTER(ConformerDims), i32]),
     "nsf_conformer_forward": (i32, [C.c_void_p, c_f32p, c_f32p, i64, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_mvdr": (i32, [c_f32p, i32, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, C.c_float, c_f32p, C.c_void_p]),
+    "nsf_mvdr_utterance_workspace_bytes": (i64, [i32, i64, i32]),
+    "nsf_mvdr_utterance": (i32, [c_f32p, i32, i32, c_f32p, i64, i32, i32, C.c_float, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_pit_cost": (i32, [C.c_void_p, i32, i32, i32, i32, i32, i32, i32, i32, c_f32p, C.c_void_p]),
     "nsf_stitch_masks": (i32, [c_f32p, i32, C.c_void_p, c_f32p, c_f32p, i32, i32, i32, i32, i32, i64, c_f32p, c_f32p, C.c_void_p]),
     "nsf_activity": (i32, [c_f32p, i64, i32, C.c_float, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -481,6 +481,126 @@ mvdr_kernel(const float* __restrict__ masks, int n_noise, const float2* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------------ one long utterance (split-T)
+// make_mvdr accepts any T (mvdr_util.py:5-47): one covariance set per bin over the whole utterance.  A warp per (bin, T-chunk)
+// accumulates partial covariances (phase 1), a warp per bin adds the partials in chunk order, solves and stores the coefficients
+// (phase 2), a warp per (bin, T-chunk) applies them (phase 3).  partial: [n_chunks][n_bins][S + 2][7][7] f64 (lane c's 7 reals of
+// every mask + the total), coef: [n_bins][S][8] complex f64.
+template <int S>
+__global__ void __launch_bounds__(kMvdrWarps * 32, 4)
+mvdr_partial_kernel(const float* __restrict__ masks, int n_noise, const float2* __restrict__ X, int64_t T, int n_bins, int chunk,
+                    double* __restrict__ partial) {
+    constexpr int C = kMvdrC, NK = S + 1;
+    extern __shared__ __align__(16) unsigned char mvdr_smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kMvdrWarps + warp;
+    if (f >= n_bins) return;
+    MvdrSmem<S>& sm = reinterpret_cast<MvdrSmem<S>*>(mvdr_smem_raw)[warp];
+    const int64_t t_lo = (int64_t)blockIdx.y * chunk, t_hi = min(T, t_lo + chunk);
+    const size_t mstride = (size_t)n_bins * T;
+    const float* mrow = masks + (size_t)f * T;
+    const float2* Xbin = X + (size_t)f * T * C;
+    double aA[NK][7], aB[NK][7], h[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+        h[i] = 0.0;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) { aA[k][i] = 0.0; aB[k][i] = 0.0; }
+    }
+    for (int64_t t0 = t_lo; t0 < t_hi; t0 += kMvdrHopMax) {
+        const int n_fr = (int)min((int64_t)kMvdrHopMax, t_hi - t0);
+        mvdr_stage_block<S, kMvdrHopMax>(sm, lane, false, true, nullptr, mrow + t0, mstride, n_noise, n_fr, Xbin + t0 * C, n_fr * C);
+        if (t0 + kMvdrHopMax < t_hi) mvdr_prefetch_block(lane, Xbin + (t0 + kMvdrHopMax) * C, (int)min((int64_t)kMvdrHopMax, t_hi - t0 - kMvdrHopMax) * C, nullptr, mstride, 0, 0);
+        mvdr_accumulate<S, false, true>(sm, lane, aA, aB, h);
+        __syncwarp();
+    }
+    double* out = partial + (((size_t)blockIdx.y * n_bins + f) * (S + 2)) * 49;
+#pragma unroll
+    for (int k = 0; k <= S + 1; ++k) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+            const double v = group_sum(k <= S ? aB[k < NK ? k : 0][i] : h[i]);
+            if (lane < 7) out[(k * 7 + lane) * 7 + i] = v;
+        }
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(kMvdrWarps * 32, 4)
+mvdr_coef_kernel(const double* __restrict__ partial, int n_chunks, int n_bins, double2* __restrict__ coef) {
+    constexpr int C = kMvdrC;
+    __shared__ __align__(16) MvdrSolveSmem<S> sv_all[kMvdrWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kMvdrWarps + warp;
+    if (f >= n_bins) return;
+    MvdrSolveSmem<S>& sv = sv_all[warp];
+    if (lane < 7) {
+        const int c = lane, b = (c + 1) % 7, d = (c + 3) % 7;
+        double tot[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) tot[i] = 0.0;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            const double* p = partial + ((((size_t)ch * n_bins + f) * (S + 2) + (S + 1)) * 7 + c) * 7;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) tot[i] += p[i];
+        }
+        for (int k = 0; k <= S; ++k) {
+            double r[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) r[i] = 0.0;
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                const double* p = partial + ((((size_t)ch * n_bins + f) * (S + 2) + k) * 7 + c) * 7;
+#pragma unroll
+                for (int i = 0; i < 7; ++i) r[i] += p[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 7; ++i) r[i] += 1e-10 * tot[i];
+            double2* R = sv.Rm + k * C * C;
+            R[c * C + c] = make_double2(r[0] + 1e-15, 0.0);
+            R[c * C + b] = make_double2(r[1], r[2]);  R[b * C + c] = make_double2(r[1], -r[2]);
+            R[c * C + d] = make_double2(r[3], r[4]);  R[d * C + c] = make_double2(r[3], -r[4]);
+            R[b * C + d] = make_double2(r[5], r[6]);  R[d * C + b] = make_double2(r[5], -r[6]);
+        }
+    }
+    __syncwarp();
+    mvdr_solve<S>(sv, lane, f);
+    __syncwarp();
+    if (lane < S * 8) coef[(size_t)f * S * 8 + lane] = sv.Wc[lane];
+}
+
+template <int S>
+__global__ void __launch_bounds__(kMvdrWarps * 32, 8)
+mvdr_apply_kernel(const double2* __restrict__ coef, const float* __restrict__ masks, const float2* __restrict__ X, int64_t T, int n_bins,
+                  int chunk, float mask_floor, float2* __restrict__ Y) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = blockIdx.x * kMvdrWarps + warp;
+    if (f >= n_bins) return;
+    const int64_t t_lo = (int64_t)blockIdx.y * chunk;
+    const int n = (int)min((int64_t)chunk, T - t_lo);
+    const size_t mstride = (size_t)n_bins * T;
+    mvdr_apply<S>(coef + (size_t)f * S * 8, X + ((size_t)f * T + t_lo) * kMvdrC, n * kMvdrC, masks + (size_t)f * T + t_lo, mstride, n, mask_floor,
+                  Y + (size_t)f * T + t_lo, lane);
+}
+
+template <int S>
+static int launch_mvdr_utterance(const float* masks, int n_noise, const float2* X, int64_t T, int n_bins, float mask_floor, float2* Y,
+                                 void* workspace, cudaStream_t stream) {
+    const int chunk = 4 * kMvdrHopMax;                                   // 384 frames per warp
+    const int n_chunks = (int)ceil_div64(T, chunk);
+    double* partial = reinterpret_cast<double*>(workspace);
+    double2* coef = reinterpret_cast<double2*>(partial + (size_t)n_chunks * n_bins * (S + 2) * 49);
+    const size_t smem = sizeof(MvdrSmem<S>) * kMvdrWarps;
+    NSF_CUDA(cudaFuncSetAttribute(mvdr_partial_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(ceil_div(n_bins, kMvdrWarps), n_chunks);
+    mvdr_partial_kernel<S><<<grid, kMvdrWarps * 32, smem, stream>>>(masks, n_noise, X, T, n_bins, chunk, partial);
+    int rc = check_launch("mvdr_partial_kernel");
+    if (rc) return rc;
+    mvdr_coef_kernel<S><<<ceil_div(n_bins, kMvdrWarps), kMvdrWarps * 32, 0, stream>>>(partial, n_chunks, n_bins, coef);
+    if ((rc = check_launch("mvdr_coef_kernel"))) return rc;
+    mvdr_apply_kernel<S><<<grid, kMvdrWarps * 32, 0, stream>>>(coef, masks, X, T, n_bins, chunk, mask_floor, Y);
+    return check_launch("mvdr_apply_kernel");
+}
+
 // ------------------------------------------------------------------------------------------------ streaming, one entry per lane
 // The same streaming decomposition with the round-1 register layout: lane l < 28 owns upper-triangle entry (i, j) and loads x_i,
 // x_j per frame.  Twice the shared-memory bytes per product of the Fano layout, but 20 instead of 63 fp64 accumulators per lane:
@@ -637,6 +757,32 @@ static int launch_mvdr(int impl, const float* masks, int n_noise, const float2* 
 }  // namespace nsf
 
 using namespace nsf;
+
+extern "C" int64_t nsf_mvdr_utterance_workspace_bytes(int n_spk, int64_t T, int n_bins) {
+    if (n_spk < 2 || n_spk > 4 || T < 1 || n_bins < 1) return 0;
+    const int64_t n_chunks = ceil_div64(T, 4 * kMvdrHopMax);
+    return n_chunks * n_bins * (n_spk + 2) * 49 * 8 + (int64_t)n_bins * n_spk * 8 * 16 + 256;
+}
+
+extern "C" int nsf_mvdr_utterance(const float* masks, int n_spk, int n_noise, const float* X, int64_t T, int n_ch, int n_bins, float mask_floor,
+                                  float* Y, void* workspace, int64_t workspace_bytes, void* stream) {
+    NSF_REQUIRE(masks && X && Y && workspace, "nsf_mvdr_utterance: null pointer");
+    if (n_spk < 2 || n_spk > 4 || n_ch != kMvdrC) {
+        set_error("nsf_mvdr_utterance: built for 2..4 speaker masks and 7 microphones (got n_spk=%d, n_ch=%d)", n_spk, n_ch);
+        return NSF_ERR_UNSUPPORTED;
+    }
+    NSF_REQUIRE(n_noise >= 1 && n_noise <= 4 && T >= 1 && n_bins >= 1, "nsf_mvdr_utterance: bad sizes");
+    NSF_REQUIRE(workspace_bytes >= nsf_mvdr_utterance_workspace_bytes(n_spk, T, n_bins) && ((uintptr_t)workspace & 15) == 0,
+                "nsf_mvdr_utterance: workspace too small or misaligned");
+    ProfScope prof(PROF_MVDR, (double)n_bins * T * (kMvdrC * 8.0 + (n_spk + n_noise) * 4.0 + n_spk * 8.0), (cudaStream_t)stream);
+    const float2* Xc = reinterpret_cast<const float2*>(X);
+    float2* Yc = reinterpret_cast<float2*>(Y);
+    switch (n_spk) {
+        case 2: return launch_mvdr_utterance<2>(masks, n_noise, Xc, T, n_bins, mask_floor, Yc, workspace, (cudaStream_t)stream);
+        case 3: return launch_mvdr_utterance<3>(masks, n_noise, Xc, T, n_bins, mask_floor, Yc, workspace, (cudaStream_t)stream);
+        default: return launch_mvdr_utterance<4>(masks, n_noise, Xc, T, n_bins, mask_floor, Yc, workspace, (cudaStream_t)stream);
+    }
+}
 
 extern "C" int nsf_mvdr(const float* masks, int n_spk, int n_noise, const float* X, int64_t T_long, int64_t T_valid,
                         int n_ch, int64_t seg_first, int n_seg, int T, int hop, int n_bins, float mask_floor, float* Y,

@@ -351,6 +351,20 @@ class ConformerCssB200:
                                        _cabi.stream_ptr()), "nsf_mvdr")
         return out
 
+    def mvdr_utterance(self, spk_masks: torch.Tensor, noise_masks: torch.Tensor, X: torch.Tensor, mask_floor: float = 1.0) -> torch.Tensor:
+        """make_mvdr(spk_masks, noise_masks, mix_stft=..., return_stft=True) on ONE utterance of any length (mvdr_util.py:5-47):
+        spk_masks [S, F, T], noise_masks [Nn, F, T] float32, X [F, T, C] complex64 -> [S, F, T] complex64 (split-T kernels)."""
+        self._require_cuda()
+        S, F_, T = spk_masks.shape
+        masks = torch.cat([spk_masks, noise_masks], 0).contiguous()
+        assert masks.dtype == torch.float32 and X.dtype == torch.complex64 and X.is_contiguous() and tuple(X.shape[:2]) == (F_, T)
+        need = int(self._lib.nsf_mvdr_utterance_workspace_bytes(S, T, F_))
+        ws = torch.empty(need, dtype=torch.uint8, device=masks.device)
+        out = torch.empty((S, F_, T), dtype=torch.complex64, device=masks.device)
+        _cabi.check(self._lib.nsf_mvdr_utterance(_cabi.ptr(masks), S, masks.shape[0] - S, _cabi.ptr(X), T, X.shape[2], F_, float(mask_floor),
+                                                 _cabi.ptr(out), _cabi.ptr(ws), need, _cabi.stream_ptr()), "nsf_mvdr_utterance")
+        return out
+
     def mask_apply(self, masks: torch.Tensor, X: torch.Tensor, T_valid: int, seg_first: int, hop: int, mask_floor: float,
                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Separation without the beamformer (css.py:218-227): reference channel x floored mask -> Y [n_seg, S, F, T]."""

@@ -420,6 +420,27 @@ def test_mvdr_other_speaker_counts_vs_oracle(nb, dev, small_weights, monkeypatch
     assert worst < TOL and worst_bin < 1e-3
 
 
+@pytest.mark.parametrize("T", [50, 384, 1000, 2311])
+def test_mvdr_one_long_utterance_vs_oracle(nb, dev, small_weights, T):
+    """make_mvdr on one utterance of arbitrary length (BASELINE config 5, "one long utterance" form): covariances accumulated by
+    T-chunks in parallel, added in chunk order, one solve per bin -- against the fp64 oracle."""
+    sep = _sep(nb, small_weights, dev)
+    rng = np.random.default_rng(T)
+    Xn = _coherent_mixture(rng, T)
+    masks = rng.standard_normal((4, 257, T)).astype(np.float32) * 3
+    masks = (np.exp(masks) / np.exp(masks).sum(0, keepdims=True)).astype(np.float32)
+    masks[:, 3, :5] = 0.25                                                   # exact ties
+    tm = torch.from_numpy(masks).to(dev)
+    y = sep.mvdr_utterance(tm[:3], tm[3:], torch.from_numpy(Xn).to(dev)).cpu().numpy()
+    ref = O.make_mvdr(masks[:3], masks[3:], Xn.transpose(2, 0, 1), np.float64)
+    per_bin = np.linalg.norm(y - ref, axis=(0, 2)) / np.linalg.norm(ref, axis=(0, 2))
+    print(f"mvdr utterance T={T}: rel_l2 vs fp64 oracle {rel_l2(y, ref):.2e}, worst bin {per_bin.max():.2e}")
+    assert rel_l2(y, ref) < TOL and per_bin.max() < 1e-3
+    # and it agrees with the segment kernel on a single "segment" of the same length
+    y_seg = sep.mvdr(tm[None].contiguous(), torch.from_numpy(Xn).to(dev), T, 0, T, 1.0).cpu().numpy()[0]
+    assert rel_l2(y, y_seg) < 1e-6
+
+
 def test_mvdr_rejects_unsupported_shapes(nb, dev):
     lib = nb._cabi.load()
     t = torch.zeros(16, device=dev)
