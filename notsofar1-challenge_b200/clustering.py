@@ -81,14 +81,14 @@ def nmesc(aff: torch.Tensor, max_num_speakers: int = 8, max_rp_threshold: float 
         if best is None or g_p < best[0]:
             best = (g_p, p)
     p_hat = best[1]
-    if not is_fully_connected(affinity_graph(mat, p_hat)):                            # getMinimumConnection: grow p until connected
-        for p in range(p_hat + 1, n + 1):
-            if is_fully_connected(affinity_graph(mat, p)):
-                p_hat = p
+    if not is_fully_connected(affinity_graph(mat, p_hat)):
+        # getMinimumConnection [upstream]: walk the candidate list itself (not every integer) until the graph is connected or p
+        # exceeds max_N; the speaker count is the one already estimated for that candidate (est_spk_n_dict)
+        for p in p_list:
+            p_hat = p
+            if is_fully_connected(affinity_graph(mat, p)) or p > max_n:
                 break
-    k = est.get(p_hat)
-    if k is None:
-        k = estimate_num_speakers(affinity_graph(mat, p_hat), max_num_speakers)[0]
+    k = est[p_hat]
     return k, ratio * p_hat
 
 
@@ -137,4 +137,5 @@ def nmesc_backend(emb: torch.Tensor, cfg=None):
     """Clustering backend for ``diarization.set_clustering_backend``: emb [n_words, n_scales, D] -> labels, with the affinity
     of word_based_diarization.py:171-177 computed by the CUDA kernels of csrc/titanet.cu."""
     from .titanet import multiscale_affinity
-    return run_clustering(multiscale_affinity(emb.float()))
+    # word_based_diarization.py:171: the embeddings are rounded to fp16 before the affinity (which NeMo then evaluates in fp32)
+    return run_clustering(multiscale_affinity(emb.half().float()))
