@@ -137,10 +137,12 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             // ===== MMA issuer
             const uint32_t idesc_s = make_idesc_f16(192, 1), idesc_b = make_idesc_f16(nBh, 1), idesc_o = make_idesc_f16_bmn(64, 1);
             mbar_wait(pe_full, 0);
-            uint32_t it = 0;
-            for (int bh = first; bh < p.n_bh; bh += stride, ++it) {
-                mbar_wait(o_drained, (it & 1) ^ 1);             // previous item's O has been read out of TMEM
-                mbar_wait(qk_full, it & 1);
+            // scores S = Q K^T into columns [0, 192) and the first half of the relative-position product Bm into [192, 192 + nBh):
+            // neither touches the output accumulator O of the previous item (columns [384, 448)), so they are issued right
+            // behind that item's P V product and run while the softmax warps still read its O; only the second half of Bm
+            // (columns [192 + nBh, 192 + 2 nBh), which cover O) waits for o_drained.
+            auto issue_scores_and_bm = [&](uint32_t it_next, bool wait_drain, uint32_t drain_parity) {
+                mbar_wait(qk_full, it_next & 1);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {                // d_k = 64 = 4 k-steps of 16
@@ -150,18 +152,33 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                     tcgen05_mma_f16(tmem_base, a_lo, bk_hi, idesc_s, ks != 0);
                     tcgen05_mma_f16(tmem_base, a_hi, bk_lo, idesc_s, 1);
                     tcgen05_mma_f16(tmem_base, a_hi, bk_hi, idesc_s, 1);
+                    const uint64_t bp_hi = make_smem_desc(pe_smem + ko), bp_lo = make_smem_desc(pe_smem + kA2PeHalf + ko);
+                    const uint32_t d = tmem_base + kA2ColB;
+                    tcgen05_mma_f16(d, a_lo, bp_hi, idesc_b, ks != 0);
+                    tcgen05_mma_f16(d, a_hi, bp_lo, idesc_b, 1);
+                    tcgen05_mma_f16(d, a_hi, bp_hi, idesc_b, 1);
+                }
+                if (wait_drain) {
+                    mbar_wait(o_drained, drain_parity);         // the previous item's O has been read out of TMEM
+                    tcgen05_fence_after();
+                }
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const uint32_t po = (uint32_t)(h * nBh) * 128u + ko;
-                        const uint64_t bp_hi = make_smem_desc(pe_smem + po), bp_lo = make_smem_desc(pe_smem + kA2PeHalf + po);
-                        const uint32_t d = tmem_base + kA2ColB + h * nBh;
-                        tcgen05_mma_f16(d, a_lo, bp_hi, idesc_b, ks != 0);
-                        tcgen05_mma_f16(d, a_hi, bp_lo, idesc_b, 1);
-                        tcgen05_mma_f16(d, a_hi, bp_hi, idesc_b, 1);
-                    }
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t ko = ks * 32;
+                    const uint64_t a_hi = make_smem_desc(q_smem + ko), a_lo = make_smem_desc(q_smem + kA2QHalf + ko);
+                    const uint32_t po = (uint32_t)nBh * 128u + ko;
+                    const uint64_t bp_hi = make_smem_desc(pe_smem + po), bp_lo = make_smem_desc(pe_smem + kA2PeHalf + po);
+                    const uint32_t d = tmem_base + kA2ColB + nBh;
+                    tcgen05_mma_f16(d, a_lo, bp_hi, idesc_b, ks != 0);
+                    tcgen05_mma_f16(d, a_hi, bp_lo, idesc_b, 1);
+                    tcgen05_mma_f16(d, a_hi, bp_hi, idesc_b, 1);
                 }
                 tcgen05_commit(qk_empty);
                 tcgen05_commit(s_ready);
+            };
+            issue_scores_and_bm(0, false, 0);
+            uint32_t it = 0;
+            for (int bh = first; bh < p.n_bh; bh += stride, ++it) {
                 mbar_wait(p_ready, it & 1);                     // probabilities are in TMEM
                 mbar_wait(v_full, it & 1);
                 tcgen05_fence_after();
@@ -175,6 +192,8 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 }
                 tcgen05_commit(v_empty);
                 tcgen05_commit(o_ready);
+                // the next item's scores overwrite P only after the P V product above (tensor-pipe order)
+                if (bh + stride < p.n_bh) issue_scores_and_bm(it + 1, true, it & 1);
             }
         }
     } else {
