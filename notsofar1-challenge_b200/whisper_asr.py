@@ -199,7 +199,13 @@ class WhisperDecoder:
                                   max_initial_timestamp_index=50, suppress=sup, suppress_first=blank)
         self.n_ctx = model.dec_dims.n_text_ctx
         self.sample_len = self.n_ctx // 2
+        self.seed = seed
         self.gen = torch.Generator(device=model.device).manual_seed(seed)
+
+    def reseed(self):
+        """The temperature-fallback sampler restarts from the same seed for every recording: a stream transcribes to the same
+        result whatever was transcribed before it (upstream draws from torch's global generator)."""
+        self.gen.manual_seed(self.seed)
 
     def initial_tokens(self, prompt: Optional[Sequence[int]]) -> List[int]:
         tokens = list(self.tok.sot_sequence)
@@ -492,6 +498,8 @@ class WhisperB200Transcriber:
         """whisper/transcribe.py::transcribe [upstream] for one stream."""
         tok, model = self.tok, self.model
         audio = self._audio(stream)
+        if hasattr(self.decoder, "reseed"):
+            self.decoder.reseed()
         log_spec, gmax, content_frames = model.log_mel_recording(audio.contiguous())
         content_duration = content_frames * HOP / SAMPLE_RATE
         word_timestamps = bool(options.get("word_timestamps", False))
