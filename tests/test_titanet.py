@@ -409,3 +409,34 @@ def test_oracle_network_against_torch_modules():
             e = conv("decoder.emb_layers.0.1", 2 * c_in, 16, 1, bias=True)(bn("decoder.emb_layers.0.0", 2 * c_in, 1e-5)(pool))
             outs.append(e[0, :, 0].numpy())
     assert rel_l2(got, np.stack(outs)) < 1e-10
+
+
+@pytest.mark.gpu
+def test_titanet_vs_nemo_when_available():
+    """The pin that cannot run offline (VERDICT r1 missing #5): with NeMo installed and NSF_TITANET_CKPT pointing at titanet_large.nemo,
+    the embeddings of word_based_diarization.py:102-105 (``spk_model.forward`` under autocast) must agree with TitaNetB200 on the
+    same crops.  Skips -- and says so -- where NeMo or the archive is missing: TitaNet / NMESC parity unpinned."""
+    import os
+    try:
+        from nemo.collections.asr.models import EncDecSpeakerLabelModel
+    except Exception:
+        pytest.skip("NeMo is not installed: TitaNet / NMESC parity stays unpinned against upstream (SURVEY 8c)")
+    path = os.environ.get("NSF_TITANET_CKPT")
+    if not path or not os.path.exists(path):
+        pytest.skip("NSF_TITANET_CKPT not set: TitaNet parity stays unpinned against upstream")
+    import torch
+    from notsofar_b200.titanet import load_titanet
+    dev = torch.device("cuda", 0)
+    ref = EncDecSpeakerLabelModel.restore_from(path, map_location=dev).eval()
+    mine = load_titanet(path, dev)
+    rng = np.random.default_rng(0)
+    lens = torch.tensor([48000, 32000, 17000, 8000], device=dev)
+    crops = torch.from_numpy((rng.standard_normal((4, 48000)) * 0.05).astype(np.float32)).to(dev)
+    for i, n in enumerate(lens.tolist()):
+        crops[i, n:] = 0
+    with torch.no_grad(), torch.autocast("cuda"):
+        _, emb_ref = ref.forward(input_signal=crops, input_signal_length=lens)
+    emb = mine.as_embedding_backend()(crops, lens, None)
+    cos = torch.nn.functional.cosine_similarity(emb.float(), emb_ref.float(), dim=-1)
+    print("TitaNetB200 vs NeMo (autocast fp16): cosine similarity per crop", cos.tolist())
+    assert float(cos.min()) > 0.999
