@@ -563,23 +563,48 @@ def run_session(args):
     lib = _cabi.load()
     seconds = args.session_seconds
     tmp = tempfile.mkdtemp(prefix=f"nsf_bench_r{rank}_")
-    x = synth.synthetic_meeting(seconds, seed=rank)
-    names = []
-    for c in range(7):
-        f = os.path.join(tmp, f"ch{c}.wav")
-        wf.write(f, FS, np.clip(np.rint(x[:, c] * 32768.0 * 8), -32768, 32767).astype(np.int16))
-        names.append(f)
     model_dir = os.path.join(tmp, "models", "notsofar", "conformer1.0", "mc")
     os.makedirs(model_dir)
     torch.save({"model": {"module." + k: torch.from_numpy(np.asarray(v)) for k, v in synth.random_state_dict(0).items()}},
                os.path.join(model_dir, "model.pt"))
     open(os.path.join(model_dir, "cfg.yaml"), "w").write("single_channel: false\n")
-    session = pd.Series(dict(session_id=f"multichannel/MTG_bench_{rank}", meeting_id="MTG_bench", is_mc=True, wav_file_names=names))
     cfg = N.CssCfg(show_progressbar=False, activity_th=0.3)
     css_mod.ASYNC_WAV_WRITES = bool(args.async_wav)
 
-    def step(i):
-        return N.css_inference(os.path.join(tmp, f"out{i % 2}"), os.path.join(tmp, "models"), session, cfg, fetch_from_cache=False)
+    def make_session(idx, secs):
+        x = synth.synthetic_meeting(secs, seed=idx)
+        names = []
+        for c in range(7):
+            f = os.path.join(tmp, f"s{idx}_ch{c}.wav")
+            wf.write(f, FS, np.clip(np.rint(x[:, c] * 32768.0 * 8), -32768, 32767).astype(np.int16))
+            names.append(f)
+        return pd.Series(dict(session_id=f"multichannel/MTG_bench_{idx}", meeting_id=f"MTG_bench_{idx}", is_mc=True, wav_file_names=names)), len(x)
+
+    if world == 1:
+        session, n_samp = make_session(0, seconds)
+        total_audio_s, total_samples = seconds, n_samp
+
+        def step(i):
+            return N.css_inference(os.path.join(tmp, f"out{i % 2}"), os.path.join(tmp, "models"), session, cfg, fetch_from_cache=False)
+    else:
+        # 2 sessions per GPU of 2/3, 1 and 4/3 of --session-seconds, handed out longest-first by the session scheduler
+        # (scheduler.css_inference_distributed: one all_gather_object of the finished rows over the process group)
+        from notsofar_b200.scheduler import assign_sessions, css_inference_distributed
+        durations = [seconds * (2 + (i % 3)) / 3.0 for i in range(2 * world)]
+        mine = set(assign_sessions(durations, world)[rank])
+        sessions, total_samples = [], 0
+        for i, d in enumerate(durations):
+            if i in mine:
+                sess, n_samp = make_session(i, d)
+            else:                                                   # another rank's session: the row alone (its files live in that rank's directory)
+                sess, n_samp = pd.Series(dict(session_id=f"multichannel/MTG_bench_{i}", meeting_id=f"MTG_bench_{i}", is_mc=True,
+                                              wav_file_names=[f"/nonexistent/s{i}_ch{c}.wav" for c in range(7)])), int(round(d * FS))
+            sessions.append(sess)
+            total_samples += n_samp
+        total_audio_s = float(sum(durations))
+
+        def step(i):
+            return css_inference_distributed(os.path.join(tmp, f"out{i % 2}"), os.path.join(tmp, "models"), sessions, cfg, False, durations=durations)
 
     def barrier():
         if world > 1:
@@ -602,17 +627,19 @@ def run_session(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     if rank == 0:
-        n_out = (N.plan_segments(len(x), FS, cfg).mix_frames - 1) * 256 + 512
-        val = world * seconds / (ms / 1e3)
+        val = total_audio_s / (ms / 1e3)
         print(json.dumps({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPES["2xbf16"],
                           "quality": QUALITY, "data": "synthetic (seeded 7-ch session; random-init v1.0-MC weights)",
-                          "config": {"workload": f"css_inference plug-in call on a {seconds / 60:.0f}-min 7-ch 16 kHz session per GPU: 7 WAV files in "
-                                                 f"(pageable host memory), model resident, 1 + 3 peak-normalised PCM16 WAV files out",
-                                     "parallelism": f"{world} independent sessions (one per GPU)", "timing": "wall clock around the call, max over ranks",
+                          "config": {"workload": (f"css_inference plug-in call on a {seconds / 60:.0f}-min 7-ch 16 kHz session" if world == 1 else
+                                                  f"{2 * world} sessions of {seconds * 2 / 180:.0f}-{seconds * 4 / 180:.0f} min through scheduler.css_inference_distributed") +
+                                                 ": 7 WAV files in (pageable host memory), model resident, 1 + 3 peak-normalised PCM16 WAV files out per session",
+                                     "parallelism": "one session at a time on one GPU" if world == 1 else f"sessions assigned longest-first to {world} GPUs (one process each)",
+                                     "timing": "wall clock around the call, max over ranks",
                                      "wav_writes": "asynchronous (flushed before the clock stops)" if args.async_wav else "synchronous (parallel writer threads)"},
-                          "e2e": {"value": val, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(len(x) * 7 * 4),
-                                  "d2h_bytes_per_step": int(3 * n_out * 4), "file_bytes_read": int(len(x) * 7 * 2), "file_bytes_written": int(4 * n_out * 2)},
+                          "e2e": {"value": val, "unit": UNIT, "ms_per_step": ms, "h2d_bytes_per_step": int(total_samples * 7 * 2),
+                                  "d2h_bytes_per_step": int(4 * total_samples * 2), "file_bytes_read": int(total_samples * 7 * 2),
+                                  "file_bytes_written": int(4 * total_samples * 2), "note": "int16 crosses PCIe in both directions (device-side conversion / quantisation)"},
                           "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches)}), flush=True)
     if world > 1:
         dist.destroy_process_group()

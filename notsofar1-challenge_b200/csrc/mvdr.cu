@@ -588,7 +588,8 @@ static int launch_mvdr_utterance(const float* masks, int n_noise, const float2* 
     const int chunk = 4 * kMvdrHopMax;                                   // 384 frames per warp
     const int n_chunks = (int)ceil_div64(T, chunk);
     double* partial = reinterpret_cast<double*>(workspace);
-    double2* coef = reinterpret_cast<double2*>(partial + (size_t)n_chunks * n_bins * (S + 2) * 49);
+    const size_t n_partial = ((size_t)n_chunks * n_bins * (S + 2) * 49 + 1) & ~(size_t)1;          // coef (double2) stays 16-byte aligned
+    double2* coef = reinterpret_cast<double2*>(partial + n_partial);
     const size_t smem = sizeof(MvdrSmem<S>) * kMvdrWarps;
     NSF_CUDA(cudaFuncSetAttribute(mvdr_partial_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(ceil_div(n_bins, kMvdrWarps), n_chunks);
@@ -761,7 +762,7 @@ using namespace nsf;
 extern "C" int64_t nsf_mvdr_utterance_workspace_bytes(int n_spk, int64_t T, int n_bins) {
     if (n_spk < 2 || n_spk > 4 || T < 1 || n_bins < 1) return 0;
     const int64_t n_chunks = ceil_div64(T, 4 * kMvdrHopMax);
-    return n_chunks * n_bins * (n_spk + 2) * 49 * 8 + (int64_t)n_bins * n_spk * 8 * 16 + 256;
+    return ((n_chunks * n_bins * (n_spk + 2) * 49 + 1) & ~(int64_t)1) * 8 + (int64_t)n_bins * n_spk * 8 * 16 + 256;
 }
 
 extern "C" int nsf_mvdr_utterance(const float* masks, int n_spk, int n_noise, const float* X, int64_t T, int n_ch, int n_bins, float mask_floor,

@@ -245,10 +245,17 @@ def test_transcribe_and_asr_inference_end_to_end(tmp_path):
     from notsofar_b200.whisper_asr import WhisperB200Transcriber
     dev = torch.device("cuda", 0)
     _, wb, tok = _model_and_tok(dev, seed=3)
-    tr = WhisperB200Transcriber(wb, tok)
     pcm = _speechy_audio(37.0, seed=2)
     opts = dict(task="transcribe", language="en", word_timestamps=True, beam_size=5, hallucination_silence_threshold=2.0)
+    # the reference's thresholds first: a random-weight model talks nonsense with low confidence, so the fallback ladder and the
+    # no-speech skip are what gets exercised (the result may well be empty)
+    strict = WhisperB200Transcriber(wb, tok, temperatures=(0.0, 0.4, 1.0))
+    res0 = strict.transcribe(torch.from_numpy(pcm[: 16000 * 12]).to(dev), opts)
+    assert set(res0) == {"text", "segments", "language"}
+    # thresholds off: every window's beam-search result is kept, so segments, word timestamps and the seek logic all run
+    tr = WhisperB200Transcriber(wb, tok, compression_ratio_threshold=None, logprob_threshold=None, no_speech_threshold=None)
     res = tr.transcribe(torch.from_numpy(pcm).to(dev), opts)
+    assert len(res["segments"]) >= 1 and sum(len(s["words"]) for s in res["segments"]) >= 1 and res["text"]
     assert set(res) == {"text", "segments", "language"} and res["language"] == "en"
     for s in res["segments"]:
         assert {"id", "seek", "start", "end", "text", "tokens", "temperature", "avg_logprob", "compression_ratio", "no_speech_prob", "words"} <= set(s)
