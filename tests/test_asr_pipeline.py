@@ -254,6 +254,11 @@ def test_transcribe_and_asr_inference_end_to_end(tmp_path):
     assert set(res0) == {"text", "segments", "language"}
     # thresholds off: every window's beam-search result is kept, so segments, word timestamps and the seek logic all run
     tr = WhisperB200Transcriber(wb, tok, compression_ratio_threshold=None, logprob_threshold=None, no_speech_threshold=None)
+    # a trained model never emits language / task tokens in the text; a random one does, so they join the suppression list here
+    from notsofar_b200.whisper import WhisperRules
+    r = tr.decoder.rules
+    tr.decoder.rules = WhisperRules(eot=r.eot, timestamp_begin=r.timestamp_begin, no_timestamps=r.no_timestamps, max_initial_timestamp_index=50,
+                                    suppress=sorted(set(r.suppress) | set(range(tok.eot + 1, tok.timestamp_begin))), suppress_first=r.suppress_first)
     res = tr.transcribe(torch.from_numpy(pcm).to(dev), opts)
     assert len(res["segments"]) >= 1 and sum(len(s["words"]) for s in res["segments"]) >= 1 and res["text"]
     assert set(res) == {"text", "segments", "language"} and res["language"] == "en"

@@ -277,7 +277,7 @@ def test_word_nmesc_default_backends_from_checkpoint(dev, tmp_path, monkeypatch)
     with tarfile.open(arch, "w") as tar:
         tar.add(ck, arcname="./model_weights.ckpt")
     monkeypatch.setenv("NSF_TITANET_CKPT", str(arch))
-    sr, n = 16000, 16000 * 24
+    sr, n = 16000, 16000 * 60
     t = np.arange(n) / sr
     rng = np.random.default_rng(12)
     voices = []
@@ -287,8 +287,10 @@ def test_word_nmesc_default_backends_from_checkpoint(dev, tmp_path, monkeypatch)
     pcm_np = np.stack([voices[0], voices[1], 0.01 * rng.standard_normal(n)])
     pcm_np = (pcm_np / np.abs(pcm_np).max(1, keepdims=True) * 20000).astype(np.int16)
     pcm = torch.from_numpy(pcm_np).to(dev)
-    words = [[f"w{i}", 1.0 + 1.1 * i, 1.0 + 1.1 * i + 0.5] for i in range(20)]
-    df = pd.DataFrame({"start_time": [1.0, 1.0], "end_time": [23.0, 23.0], "text": ["a", "b"], "word_timing": [words[:10], words[10:]],
+    # a session-like number of words: with a handful, NMESC's candidate list ends at p = 2 neighbours and the speaker count read off
+    # that shattered graph is meaningless (upstream's getMinimumConnection walk behaves the same)
+    words = [[f"w{i}", 1.0 + 0.47 * (i % 60), 1.0 + 0.47 * (i % 60) + 0.3] for i in range(120)]
+    df = pd.DataFrame({"start_time": [1.0, 1.0], "end_time": [30.0, 30.0], "text": ["a", "b"], "word_timing": [words[:60], words[60:]],
                        "meeting_id": ["m", "m"], "session_id": ["s", "s"], "wav_file_name": ["s0.wav", "s1.wav"],
                        "wav_file_name_ind": [0, 1]})
     df["wav_file_name"] = df["wav_file_name"].astype("category")
