@@ -655,7 +655,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seconds", type=float, default=1800.0, help="meeting length per GPU")
     ap.add_argument("--engine", default="2xbf16", choices=["3xtf32", "tf32", "simt", "2xbf16", "2xf16"])
-    ap.add_argument("--segments-per-batch", type=int, default=640)
+    ap.add_argument("--segments-per-batch", type=int, default=1280)
     ap.add_argument("--cpu-seconds", type=float, default=120.0, help="slice of the meeting the CPU baseline leg runs")
     ap.add_argument("--ref-seconds", type=float, default=15.0, help="--impl reference: audio seconds per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -188,7 +188,7 @@ class ConformerCssB200:
     """Segment-wise CSS model on one B200.  Not an nn.Module: all arithmetic is in libnsf_b200.so."""
 
     def __init__(self, state_dict: Dict[str, object], num_spks: int = 3, device: Optional[torch.device] = None,
-                 gemm_engine: int = _cabi.GEMM_TC_2XBF16, segments_per_batch: int = 640):
+                 gemm_engine: int = _cabi.GEMM_TC_2XBF16, segments_per_batch: int = 1280):
         self._lib = _cabi.load()
         self._sd = _strip_prefix(state_dict)
         self.training = False

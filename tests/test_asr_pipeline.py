@@ -259,6 +259,8 @@ def test_transcribe_and_asr_inference_end_to_end(tmp_path):
     r = tr.decoder.rules
     tr.decoder.rules = WhisperRules(eot=r.eot, timestamp_begin=r.timestamp_begin, no_timestamps=r.no_timestamps, max_initial_timestamp_index=50,
                                     suppress=sorted(set(r.suppress) | set(range(tok.eot + 1, tok.timestamp_begin))), suppress_first=r.suppress_first)
+    tr.transcribe(torch.from_numpy(pcm[: 16000 * 20]).to(dev), opts)           # with the hallucination-silence rules (improbable words: skips)
+    opts = dict(opts, hallucination_silence_threshold=None)
     res = tr.transcribe(torch.from_numpy(pcm).to(dev), opts)
     assert len(res["segments"]) >= 1 and sum(len(s["words"]) for s in res["segments"]) >= 1 and res["text"]
     assert set(res) == {"text", "segments", "language"} and res["language"] == "en"
