@@ -329,23 +329,49 @@ ln_stats_vec_kernel(const float* __restrict__ x, int M, float2* __restrict__ sta
     if (lane == 0) stats[row] = make_float2(mean, rstd);
 }
 
-__global__ void __launch_bounds__(256, 2)
+// CTA = (segment, 32 channels), 128 threads.  Staging: one float4 of x per thread and row, LN + GLU with the per-channel
+// constants folded (xn = x rstd - mean rstd; a = xn (g w1a) + (b w1a + b1a); gate exponent = xn (-log2e g w1g) - log2e (b w1g + b1g)):
+// three FMAs, two MUFUs, one add and one multiply per element.  Convolution: a thread owns a channel PAIR and a run of
+// frames; the two channels ride in the halves of packed fp32 FMAs (fma.rn.f32x2: one issue slot for two products), the
+// 33 taps are taken in three passes of 11 so that the register window is 18 rows, tap weights come from shared memory
+// (one 8-byte load per 8 packed FMAs).  Small CTAs (5 resident per SM) keep the staging loads of one CTA under the FMAs
+// of the others.  Summation order per output = taps ascending, as before.
+constexpr int kDw2Ch = 32, kDw2Threads = 128, kDw2Groups = kDw2Threads / (kDw2Ch / 2), kDw2Pass = 11, kDw2Slack = 8;
+static_assert(kDwMaxK == 3 * kDw2Pass, "three tap passes");
+__global__ void __launch_bounds__(kDw2Threads, 5)
 dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ ln_g,
                     const float* __restrict__ ln_b, int T, int d, int ks, const float* __restrict__ dw_w,
                     const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const float* __restrict__ scalars) {
-    extern __shared__ __align__(16) float tile[];     // [T + ks - 1][kDwCh], row r <-> frame r - pad, holds u = GLU(LN(x))
-    const int seg = blockIdx.y, c0 = blockIdx.x * kDwCh;
+    extern __shared__ __align__(16) float tile[];     // [T + ks - 1][kDw2Ch] u = GLU(LN(x)), row r <-> frame r - pad; then [kDwMaxK][kDw2Ch] taps
+    const int seg = blockIdx.y, c0 = blockIdx.x * kDw2Ch;
     const int pad = (ks - 1) / 2;
-    const int rows = T + ks - 1;
+    const int rows = T + kDwMaxK - 1 + kDw2Slack;     // rows past the halo are zero: the last window of a frame run reads up to row t0 + 39
+    float* wt = tile + (size_t)rows * kDw2Ch;
     const float w1a = __ldg(scalars + 0), b1a = __ldg(scalars + 1), w1g = __ldg(scalars + 2), b1g = __ldg(scalars + 3);
+    for (int i = threadIdx.x; i < kDwMaxK * kDw2Ch; i += kDw2Threads) {
+        const int j = i / kDw2Ch, c = i - j * kDw2Ch;
+        wt[i] = (j < ks && c0 + c < d) ? __ldg(dw_w + (size_t)(c0 + c) * ks + j) : 0.f;
+    }
     {
-        const int c4 = threadIdx.x & (kDwCh / 4 - 1);                 // fixed per thread: blockDim is a multiple of 16
+        constexpr int kC4 = kDw2Ch / 4;                               // float4 columns of a tile row
+        constexpr int kRowStep = kDw2Threads / kC4;                   // rows covered by the CTA per load
+        const int c4 = threadIdx.x & (kC4 - 1);
         const bool c_ok = c0 + c4 * 4 < d;
         const float4 g4 = c_ok ? ldg4(ln_g + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 b4 = c_ok ? ldg4(ln_b + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr float kNegLog2e = -1.4426950408889634f;
+        const float4 gw = make_float4(g4.x * w1a, g4.y * w1a, g4.z * w1a, g4.w * w1a);
+        const float4 bw = make_float4(fmaf(b4.x, w1a, b1a), fmaf(b4.y, w1a, b1a), fmaf(b4.z, w1a, b1a), fmaf(b4.w, w1a, b1a));
+        const float4 gg = make_float4(kNegLog2e * g4.x * w1g, kNegLog2e * g4.y * w1g, kNegLog2e * g4.z * w1g, kNegLog2e * g4.w * w1g);
+        const float4 bg = make_float4(kNegLog2e * fmaf(b4.x, w1g, b1g), kNegLog2e * fmaf(b4.y, w1g, b1g),
+                                      kNegLog2e * fmaf(b4.z, w1g, b1g), kNegLog2e * fmaf(b4.w, w1g, b1g));
+        auto glu = [](float xn, float gw_, float bw_, float gg_, float bg_) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(xn, gg_, bg_)));
+            return __fdividef(fmaf(xn, gw_, bw_), 1.f + e);
+        };
         // four rows per trip: all global loads of a trip are in flight before the first use
-        constexpr int kRowStep = 256 / (kDwCh / 4);
-        for (int rb = threadIdx.x / (kDwCh / 4); rb < rows; rb += 4 * kRowStep) {
+        for (int rb = threadIdx.x / kC4; rb < rows; rb += 4 * kRowStep) {
             float4 xv[4];
             float2 st[4];
 #pragma unroll
@@ -362,38 +388,52 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
                 if (r >= rows) break;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (t >= 0 && t < T && c_ok) {
-                    const float4 h = ln_apply(xv[u], st[u].x, st[u].y, g4, b4);
-                    v = make_float4(glu1_fast(h.x, w1a, b1a, w1g, b1g), glu1_fast(h.y, w1a, b1a, w1g, b1g),
-                                    glu1_fast(h.z, w1a, b1a, w1g, b1g), glu1_fast(h.w, w1a, b1a, w1g, b1g));
+                    const float A = st[u].y, B = -st[u].x * st[u].y;
+                    v = make_float4(glu(fmaf(xv[u].x, A, B), gw.x, bw.x, gg.x, bg.x), glu(fmaf(xv[u].y, A, B), gw.y, bw.y, gg.y, bg.y),
+                                    glu(fmaf(xv[u].z, A, B), gw.z, bw.z, gg.z, bg.z), glu(fmaf(xv[u].w, A, B), gw.w, bw.w, gg.w, bg.w));
                 }
-                st4(tile + r * kDwCh + c4 * 4, v);
+                st4(tile + r * kDw2Ch + c4 * 4, v);
             }
         }
     }
     __syncthreads();
-    const int c = threadIdx.x & (kDwCh - 1), grp = threadIdx.x / kDwCh;       // 4 frame groups
-    if (c0 + c >= d) return;
-    float w[kDwMaxK];
-#pragma unroll
-    for (int j = 0; j < kDwMaxK; ++j) w[j] = j < ks ? __ldg(dw_w + (size_t)(c0 + c) * ks + j) : 0.f;
-    const float sc = __ldg(bn_scale + c0 + c), sh = __ldg(bn_shift + c0 + c);
+    const int cp = threadIdx.x & (kDw2Ch / 2 - 1), grp = threadIdx.x / (kDw2Ch / 2);
+    const int c = c0 + 2 * cp;
+    if (c >= d) return;
+    const float2 sc = __ldg(reinterpret_cast<const float2*>(bn_scale + c)), sh = __ldg(reinterpret_cast<const float2*>(bn_shift + c));
     const float w2 = __ldg(scalars + 4), b2 = __ldg(scalars + 5);
-    const int per = ceil_div(ceil_div(T, 4), kDwOut) * kDwOut;
+    const int per = ceil_div(ceil_div(T, kDw2Groups), kDwOut) * kDwOut;
     const int t_end = min(T, (grp + 1) * per);
+    const float2* tile2 = reinterpret_cast<const float2*>(tile) + cp;         // row stride kDw2Ch / 2
+    const float2* wt2 = reinterpret_cast<const float2*>(wt) + cp;
     for (int t0 = grp * per; t0 < t_end; t0 += kDwOut) {
-        float win[kDwOut + kDwMaxK - 1];
+        float2 xo[kDwOut];
 #pragma unroll
-        for (int i = 0; i < kDwOut + kDwMaxK - 1; ++i) win[i] = (t0 + i < rows) ? tile[(t0 + i) * kDwCh + c] : 0.f;
-        float xo[kDwOut];
+        for (int o = 0; o < kDwOut; ++o)
+            xo[o] = (t0 + o < t_end) ? *reinterpret_cast<const float2*>(x + ((size_t)seg * T + t0 + o) * d + c) : make_float2(0.f, 0.f);
+        float2 acc[kDwOut];
 #pragma unroll
-        for (int o = 0; o < kDwOut; ++o) xo[o] = (t0 + o < t_end) ? x[((size_t)seg * T + t0 + o) * d + c0 + c] : 0.f;
+        for (int o = 0; o < kDwOut; ++o) acc[o] = make_float2(0.f, 0.f);
+#pragma unroll 1
+        for (int p = 0; p < 3; ++p) {
+            float2 win[kDwOut + kDw2Pass - 1];
+            const float2* tp = tile2 + (t0 + kDw2Pass * p) * (kDw2Ch / 2);   // rows up to t0 + 39 < rows + kDw2Slack exist (zero filled)
+#pragma unroll
+            for (int i = 0; i < kDwOut + kDw2Pass - 1; ++i) win[i] = tp[i * (kDw2Ch / 2)];
+            const float2* wp = wt2 + kDw2Pass * p * (kDw2Ch / 2);
+#pragma unroll
+            for (int jj = 0; jj < kDw2Pass; ++jj) {
+                const float2 wj = wp[jj * (kDw2Ch / 2)];
+#pragma unroll
+                for (int o = 0; o < kDwOut; ++o) acc[o] = __ffma2_rn(wj, win[o + jj], acc[o]);
+            }
+        }
 #pragma unroll
         for (int o = 0; o < kDwOut; ++o) {
-            float acc = 0.f;
-#pragma unroll
-            for (int j = 0; j < kDwMaxK; ++j) acc = fmaf(w[j], win[o + j], acc);
-            const float y = fmaxf(acc * sc + sh, 0.f);
-            if (t0 + o < t_end) x[((size_t)seg * T + t0 + o) * d + c0 + c] = xo[o] + (w2 * y + b2);
+            if (t0 + o < t_end) {
+                const float y0 = fmaxf(fmaf(acc[o].x, sc.x, sh.x), 0.f), y1 = fmaxf(fmaf(acc[o].y, sc.y, sh.y), 0.f);
+                *reinterpret_cast<float2*>(x + ((size_t)seg * T + t0 + o) * d + c) = make_float2(xo[o].x + fmaf(w2, y0, b2), xo[o].y + fmaf(w2, y1, b2));
+            }
         }
     }
 }
@@ -668,11 +708,11 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                 default: ln_stats_vec_kernel<8><<<grid_s, 256, 0, s>>>(w.x, M, stats); break;
             }
             if ((rc = check_launch("ln_stats_vec_kernel"))) return rc;
-            dim3 grid(ceil_div(d, kDwCh), n_seg);
-            const size_t smem = (size_t)(T + D.kernel_size - 1) * kDwCh * sizeof(float);
+            dim3 grid(ceil_div(d, kDw2Ch), n_seg);
+            const size_t smem = (size_t)(T + kDwMaxK - 1 + kDw2Slack + kDwMaxK) * kDw2Ch * sizeof(float);
             NSF_CUDA(cudaFuncSetAttribute(dwconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            dwconv_fused_kernel<<<grid, 256, smem, s>>>(w.x, stats, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), T, d, D.kernel_size,
-                                                        h->l(L, L_DW_W), h->l(L, L_BN_SCALE), h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS));
+            dwconv_fused_kernel<<<grid, kDw2Threads, smem, s>>>(w.x, stats, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), T, d, D.kernel_size,
+                                                                h->l(L, L_DW_W), h->l(L, L_BN_SCALE), h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS));
             if ((rc = check_launch("dwconv_fused_kernel"))) return rc;
         } else {
             { ProfScope prof(PROF_NET_OTHER, 0.0, s);
