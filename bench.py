@@ -234,6 +234,8 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
     from notsofar_b200.css import HostFeeder
     from notsofar_b200.sharded import css_device_sharded, make_shard
 
+    from notsofar_b200.scheduler import bind_host_to_gpu
+    numa = bind_host_to_gpu(local_rank)          # before the first page-locked allocation: host buffers on the GPU's NUMA node
     seconds = args.seconds if args.scaling == "weak" else args.seconds / world
     total_s = seconds * world
     n_total = int(round(total_s * FS))
@@ -335,7 +337,8 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
                 "e2e": {"value": total_s / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": int(n_total * 7 * 4 + (world - 1) * (plan.segment_frames + 1) * 256 * 7 * 4),
                         "d2h_bytes_per_step": int(3 * (n_out + 256 * (world - 1)) * 4 + plan.num_segments * 36 * world),
-                        "d2h": "every rank reads its own samples (pieces overlap by one 256-sample seam); the NVLink gather to rank 0 is inside the step"},
+                        "d2h": "every rank reads its own samples (pieces overlap by one 256-sample seam); the NVLink gather to rank 0 is inside the step",
+                        "host_numa": numa},
                 "gpu_launches": int(t[2].item()) * args.steps, "gpu_launches_per_step": int(t[2].item()),
                 "roofline": roofline, "kernels": kernels}
         print(json.dumps(line), flush=True)

@@ -348,17 +348,28 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
     const int rows = T + kDwMaxK - 1 + kDw2Slack;     // rows past the halo are zero: the last window of a frame run reads up to row t0 + 39
     float* wt = tile + (size_t)rows * kDw2Ch;
     const float w1a = __ldg(scalars + 0), b1a = __ldg(scalars + 1), w1g = __ldg(scalars + 2), b1g = __ldg(scalars + 3);
-    for (int i = threadIdx.x; i < kDwMaxK * kDw2Ch; i += kDw2Threads) {
-        const int j = i / kDw2Ch, c = i - j * kDw2Ch;
-        wt[i] = (j < ks && c0 + c < d) ? __ldg(dw_w + (size_t)(c0 + c) * ks + j) : 0.f;
+    // tap weights of the CTA's channels: one contiguous run of dw_w (coalesced); the loads are issued now and land in shared
+    // memory after the tile has been staged
+    constexpr int kWPer = (kDwMaxK * kDw2Ch + kDw2Threads - 1) / kDw2Threads;
+    float wreg[kWPer];
+    const int n_w = min(kDw2Ch, d - c0) * ks;
+#pragma unroll
+    for (int k = 0; k < kWPer; ++k) {
+        const int i = threadIdx.x + k * kDw2Threads;
+        wreg[k] = i < n_w ? __ldg(dw_w + (size_t)c0 * ks + i) : 0.f;
     }
+    for (int i = threadIdx.x; i < kDwMaxK * kDw2Ch; i += kDw2Threads) wt[i] = 0.f;     // taps >= ks, channels >= d
     {
         constexpr int kC4 = kDw2Ch / 4;                               // float4 columns of a tile row
         constexpr int kRowStep = kDw2Threads / kC4;                   // rows covered by the CTA per load
-        const int c4 = threadIdx.x & (kC4 - 1);
+        constexpr int kDeep = 6;                                      // rows per thread in flight
+        const int c4 = threadIdx.x & (kC4 - 1), tr = threadIdx.x / kC4;
         const bool c_ok = c0 + c4 * 4 < d;
-        const float4 g4 = c_ok ? ldg4(ln_g + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 b4 = c_ok ? ldg4(ln_b + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        // halo and slack rows
+        for (int r = tr; r < rows - T; r += kRowStep) st4(tile + (r < pad ? r : r + T) * kDw2Ch + c4 * 4, zero4);
+        const float4 g4 = c_ok ? ldg4(ln_g + c0 + c4 * 4) : zero4;
+        const float4 b4 = c_ok ? ldg4(ln_b + c0 + c4 * 4) : zero4;
         constexpr float kNegLog2e = -1.4426950408889634f;
         const float4 gw = make_float4(g4.x * w1a, g4.y * w1a, g4.z * w1a, g4.w * w1a);
         const float4 bw = make_float4(fmaf(b4.x, w1a, b1a), fmaf(b4.y, w1a, b1a), fmaf(b4.z, w1a, b1a), fmaf(b4.w, w1a, b1a));
@@ -370,31 +381,38 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(xn, gg_, bg_)));
             return __fdividef(fmaf(xn, gw_, bw_), 1.f + e);
         };
-        // four rows per trip: all global loads of a trip are in flight before the first use
-        for (int rb = threadIdx.x / kC4; rb < rows; rb += 4 * kRowStep) {
-            float4 xv[4];
-            float2 st[4];
+        const float* xs = x + (size_t)seg * T * d + c0 + c4 * 4;       // row t at xs + t * d
+        const float2* ss = stats + (size_t)seg * T;
+        float* ts = tile + pad * kDw2Ch + c4 * 4;                     // row t at ts + t * kDw2Ch
+        // kDeep rows per trip: all global loads of a trip are in flight before the first use
+        for (int t0 = tr; t0 < T; t0 += kDeep * kRowStep) {
+            float4 xv[kDeep];
+            float2 sv[kDeep];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int t = rb + u * kRowStep - pad;
-                const bool ok = t >= 0 && t < T && c_ok;
-                const size_t row = (size_t)seg * T + (ok ? t : 0);
-                xv[u] = ok ? ld4(x + row * d + c0 + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                st[u] = ok ? __ldg(stats + row) : make_float2(0.f, 0.f);
+            for (int u = 0; u < kDeep; ++u) {
+                const int t = t0 + u * kRowStep;
+                const bool ok = t < T && c_ok;
+                xv[u] = ok ? ld4(xs + t * d) : zero4;
+                sv[u] = ok ? __ldg(ss + t) : make_float2(0.f, 0.f);
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = rb + u * kRowStep, t = r - pad;
-                if (r >= rows) break;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (t >= 0 && t < T && c_ok) {
-                    const float A = st[u].y, B = -st[u].x * st[u].y;
-                    v = make_float4(glu(fmaf(xv[u].x, A, B), gw.x, bw.x, gg.x, bg.x), glu(fmaf(xv[u].y, A, B), gw.y, bw.y, gg.y, bg.y),
-                                    glu(fmaf(xv[u].z, A, B), gw.z, bw.z, gg.z, bg.z), glu(fmaf(xv[u].w, A, B), gw.w, bw.w, gg.w, bg.w));
+            for (int u = 0; u < kDeep; ++u) {
+                const int t = t0 + u * kRowStep;
+                if (t < T) {
+                    const float A = sv[u].y, B = -sv[u].x * sv[u].y;
+                    const float4 v = c_ok ? make_float4(glu(fmaf(xv[u].x, A, B), gw.x, bw.x, gg.x, bg.x), glu(fmaf(xv[u].y, A, B), gw.y, bw.y, gg.y, bg.y),
+                                                        glu(fmaf(xv[u].z, A, B), gw.z, bw.z, gg.z, bg.z), glu(fmaf(xv[u].w, A, B), gw.w, bw.w, gg.w, bg.w))
+                                          : zero4;
+                    st4(ts + t * kDw2Ch, v);
                 }
-                st4(tile + r * kDw2Ch + c4 * 4, v);
             }
         }
+    }
+    __syncthreads();                                                  // the zero fill of wt is complete
+#pragma unroll
+    for (int k = 0; k < kWPer; ++k) {
+        const int i = threadIdx.x + k * kDw2Threads;
+        if (i < n_w) { const int c = i / ks, j = i - c * ks; wt[j * kDw2Ch + c] = wreg[k]; }
     }
     __syncthreads();
     const int cp = threadIdx.x & (kDw2Ch / 2 - 1), grp = threadIdx.x / (kDw2Ch / 2);
@@ -406,11 +424,12 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
     const int t_end = min(T, (grp + 1) * per);
     const float2* tile2 = reinterpret_cast<const float2*>(tile) + cp;         // row stride kDw2Ch / 2
     const float2* wt2 = reinterpret_cast<const float2*>(wt) + cp;
+    float* xc = x + (size_t)seg * T * d + c;                                  // frame t of the channel pair at xc + t * d
     for (int t0 = grp * per; t0 < t_end; t0 += kDwOut) {
         float2 xo[kDwOut];
 #pragma unroll
         for (int o = 0; o < kDwOut; ++o)
-            xo[o] = (t0 + o < t_end) ? *reinterpret_cast<const float2*>(x + ((size_t)seg * T + t0 + o) * d + c) : make_float2(0.f, 0.f);
+            xo[o] = (t0 + o < t_end) ? *reinterpret_cast<const float2*>(xc + (t0 + o) * d) : make_float2(0.f, 0.f);
         float2 acc[kDwOut];
 #pragma unroll
         for (int o = 0; o < kDwOut; ++o) acc[o] = make_float2(0.f, 0.f);
@@ -432,7 +451,7 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
         for (int o = 0; o < kDwOut; ++o) {
             if (t0 + o < t_end) {
                 const float y0 = fmaxf(fmaf(acc[o].x, sc.x, sh.x), 0.f), y1 = fmaxf(fmaf(acc[o].y, sc.y, sh.y), 0.f);
-                *reinterpret_cast<float2*>(x + ((size_t)seg * T + t0 + o) * d + c) = make_float2(xo[o].x + fmaf(w2, y0, b2), xo[o].y + fmaf(w2, y1, b2));
+                *reinterpret_cast<float2*>(xc + (t0 + o) * d) = make_float2(xo[o].x + fmaf(w2, y0, b2), xo[o].y + fmaf(w2, y1, b2));
             }
         }
     }

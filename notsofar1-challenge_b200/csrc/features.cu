@@ -18,6 +18,32 @@ constexpr int kFeatBinsPerCta = 8;     // one warp per bin
 constexpr int kFeatMaxIter = 8;        // T <= 256
 constexpr float kEps32 = 1.1920928955078125e-07f;   // th.finfo(th.float32).eps, feature.py:15
 
+
+
+// atan2 without branches: |error| < 1e-7 rad (1 ulp at pi/4).  atan(a) = a P(a^2) on [0, 1] (degree-8 minimax fit in a^2,
+// 9.2e-8 evaluated in fp32), the octant folded back with pi/2 - r and pi - r, the sign of y copied on: the +-pi cut is
+// decided by the sign bit of y exactly as in atan2f (atan2f itself is ~70 instructions with branches; 36 calls per lane
+// were 45 % of this kernel's instructions, profiles/r02_ncu_full_hbm_kernels_summary.csv).
+__device__ __forceinline__ float atan2_poly(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.f ? __fdividef(mn, mx) : 0.f;             // atan2(0, 0) = 0
+    const float s = a * a;
+    float r = 0.0024567132350057364f;
+    r = fmaf(r, s, -0.014401310123503208f);
+    r = fmaf(r, s, 0.03978114202618599f);
+    r = fmaf(r, s, -0.07234849780797958f);
+    r = fmaf(r, s, 0.1049894243478775f);
+    r = fmaf(r, s, -0.14161227643489838f);
+    r = fmaf(r, s, 0.19985906779766083f);
+    r = fmaf(r, s, -0.33332598209381104f);
+    r = fmaf(r, s, 0.9999998807907104f);
+    r *= a;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = (__float_as_uint(x) >> 31) ? 3.14159265358979324f - r : r;   // x < 0 or x = -0
+    return copysignf(r, y);
+}
+
 // NITER = ceil(T / 32) register slots per lane (6 for the pipeline's T = 186: two CTAs per SM instead of one)
 template <int C, int NITER>
 __global__ void __launch_bounds__(kFeatBinsPerCta * 32, NITER <= 6 ? 2 : 1)
@@ -49,7 +75,10 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
                 const bool valid = (st + t) < T_valid;       // zero-padded tail of the last segment, css.py:185-190
 #pragma unroll
                 for (int c = 0; c < C; ++c) x[c] = valid ? __ldg(Xf + (size_t)t * C + c) : make_float2(0.f, 0.f);
-                const float a0 = sqrtf(x[0].x * x[0].x + x[0].y * x[0].y);
+                // |X_0| and 1 / |X_0| from one MUFU.RSQ (2 ulp; the IEEE sqrt + division pair is ~16 instructions per channel)
+                const float p0sq = x[0].x * x[0].x + x[0].y * x[0].y;
+                const float inv0r = rsqrtf(p0sq);
+                const float a0 = p0sq > 0.f ? p0sq * inv0r : 0.f;
                 const float fm = fmaxf(a0, kEps32);
                 mag0[it] = fm;
                 s_mag += fm;
@@ -68,12 +97,12 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
                     }
                 } else {
                     // unit phasor of X_0 (angle(0) == 0 -> (1, 0))
-                    const float inv0 = a0 > 0.f ? 1.f / a0 : 0.f;
+                    const float inv0 = a0 > 0.f ? inv0r : 0.f;
                     const float u0x = a0 > 0.f ? x[0].x * inv0 : 1.f, u0y = x[0].y * inv0;
 #pragma unroll
                     for (int m = 0; m < C - 1; ++m) {
-                        const float am = sqrtf(x[m + 1].x * x[m + 1].x + x[m + 1].y * x[m + 1].y);
-                        const float invm = am > 0.f ? 1.f / am : 0.f;
+                        const float am = x[m + 1].x * x[m + 1].x + x[m + 1].y * x[m + 1].y;      // |X_m|^2: only its sign test and rsqrt are used
+                        const float invm = am > 0.f ? rsqrtf(am) : 0.f;
                         const float umx = am > 0.f ? x[m + 1].x * invm : 1.f, umy = x[m + 1].y * invm;
                         // u_m * conj(u_0) = exp(i (angle_m - angle_0))
                         const float cr = umx * u0x + umy * u0y;
@@ -109,13 +138,35 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
                 o[0] = (mag0[it] - mean) * rstd;
 #pragma unroll
                 for (int m = 0; m < C - 1; ++m)
-                    o[(m + 1) * kFeatBinsPerCta] = atan2f(yi[it][m] - m_yi[m], yr[it][m] - m_yr[m]);
+                    o[(m + 1) * kFeatBinsPerCta] = atan2_poly(yi[it][m] - m_yi[m], yr[it][m] - m_yr[m]);
             }
         }
     }
     __syncthreads();
     // write-out: row (seg*T + t), column m*257 + f, runs of up to 8 consecutive bins
     const int nb = min(kFeatBinsPerCta, kBins - f0bin);
+    if ((fmt == SPLIT_BF16 || fmt == SPLIT_F16) && feat_lo) {
+        // 16-bit planes: warp m writes channel m; 8 lanes cover the run of 8 bins of one frame (the eight 2-byte stores of a
+        // run leave the SM as one 16-byte request), 4 frames per instruction.  Bin, channel, bias and scale are fixed per
+        // thread, the address advances by a constant: ~10 instructions per element instead of ~30 for the generic loop below.
+        if (warp < C) {
+            const int m = warp, b = lane & 7, col = m * kBins + f0bin + b;
+            if (b < nb) {
+                const float bi = in_bias ? __ldg(in_bias + col) : 0.f, sc = in_scale ? __ldg(in_scale + col) : 1.f;
+                uint16_t* hp = reinterpret_cast<uint16_t*>(feat) + (size_t)seg * T * ldf + col;
+                uint16_t* lp = reinterpret_cast<uint16_t*>(feat_lo) + (size_t)seg * T * ldf + col;
+                const float* src = tile + m * kFeatBinsPerCta + b;
+                for (int t = lane >> 3; t < T; t += 4) {
+                    const float v = (src[t * (C * kFeatBinsPerCta)] + bi) * sc;                // conformer.py:297-299 (bi = 0, sc = 1: exact)
+                    uint16_t h, l;
+                    if (fmt == SPLIT_BF16) split_bf16(v, h, l); else split_f16(v, kF16ActScale, h, l);
+                    hp[(size_t)t * ldf] = h;
+                    lp[(size_t)t * ldf] = l;
+                }
+            }
+        }
+        return;
+    }
     const int total = T * C * kFeatBinsPerCta;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
         const int b = idx % kFeatBinsPerCta;
