@@ -117,6 +117,11 @@ int nsf_conformer_create(const nsf_conformer_dims* dims, const float* blob, int6
                          const int64_t* offsets /*host*/, int n_offsets, nsf_conformer** out);
 void nsf_conformer_destroy(nsf_conformer* h);
 int64_t nsf_conformer_num_offsets(const nsf_conformer_dims* dims);
+/* 1 if a handle with these dimensions runs with two LayerNorms of every block folded into the GEMMs on either side
+ * (the attention LayerNorm into the QKV projection, the feed_forward_out LayerNorm into its first linear layer;
+ * conformer.py:153-156,180-182): the blob must then hold gamma-scaled weights, bias + W beta and the column sums of the
+ * scaled weights for those two layers (pack_weights does; 2xBF16 engine, d_model = 128 * {1,2,4}; NSF_LN_FOLD=0 disables). */
+int nsf_conformer_ln_fold(const nsf_conformer_dims* dims);
 /* bytes of scratch HBM nsf_conformer_forward needs for a batch of n_seg segments */
 int64_t nsf_conformer_workspace_bytes(const nsf_conformer_dims* dims, int n_seg);
 /* feat (+feat_lo): [n_seg*T][ldf] already input-normalised, in the split format of the handle's engine

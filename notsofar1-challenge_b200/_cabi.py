@@ -43,6 +43,7 @@ SIGNATURES = {
     "nsf_conformer_create": (i32, [C.POINTER(ConformerDims), c_f32p, i64, C.POINTER(i64), i32, C.POINTER(C.c_void_p)]),
     "nsf_conformer_destroy": (None, [C.c_void_p]),
     "nsf_conformer_num_offsets": (i64, [C.POINTER(ConformerDims)]),
+    "nsf_conformer_ln_fold": (i32, [C.POINTER(ConformerDims)]),
     "nsf_conformer_workspace_bytes": (i64, [C.POINTER(ConformerDims), i32]),
     "nsf_conformer_forward": (i32, [C.c_void_p, c_f32p, c_f32p, i64, i32, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_mvdr": (i32, [c_f32p, i32, i32, c_f32p, i64, i64, i32, i64, i32, i32, i32, i32, C.c_float, c_f32p, C.c_void_p]),

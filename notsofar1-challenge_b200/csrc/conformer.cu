@@ -14,7 +14,7 @@
 
 namespace nsf {
 
-constexpr int kPerLayer = 32;
+constexpr int kPerLayer = 34;
 constexpr int kGlobalOffsets = 12;
 // pe_k is packed twice: TF32 pairs for attention.cu / the unfused path, bf16 pairs for attention16.cu (which one is used
 // depends on the engine AND on the segment length, which the handle only learns at forward time)
@@ -25,7 +25,8 @@ enum LayerOff {
     L_ATT_LN_G, L_ATT_LN_B, L_WQKV_HI, L_WQKV_LO, L_BQKV, L_WO_HI, L_WO_LO, L_BO,
     L_CONV_LN_G, L_CONV_LN_B, L_CONV_SCALARS, L_DW_W, L_BN_SCALE, L_BN_SHIFT,
     L_FFO_LN_G, L_FFO_LN_B, L_FFO_W1_HI, L_FFO_W1_LO, L_FFO_B1, L_FFO_W2_HI, L_FFO_W2_LO, L_FFO_B2,
-    L_OUT_LN_G, L_OUT_LN_B
+    L_OUT_LN_G, L_OUT_LN_B,
+    L_QKV_CSUM, L_FFO_CSUM          // column sums of the gamma-scaled Wqkv / feed_forward_out W1 (folded LayerNorms; zeros otherwise)
 };
 
 }  // namespace nsf
@@ -36,6 +37,7 @@ struct nsf_conformer {
     int64_t blob_floats;
     int n_offsets;
     int64_t* offsets;
+    bool ln_fold;               // the blob was packed for folded LayerNorms (nsf_conformer_ln_fold)
     const float* g(int i) const { return blob + offsets[i]; }
     const float* l(int layer, int i) const { return blob + offsets[nsf::kGlobalOffsets + layer * nsf::kPerLayer + i]; }
 };
@@ -341,7 +343,8 @@ static_assert(kDwMaxK == 3 * kDw2Pass, "three tap passes");
 __global__ void __launch_bounds__(kDw2Threads, 5)
 dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, const float* __restrict__ ln_g,
                     const float* __restrict__ ln_b, int T, int d, int ks, const float* __restrict__ dw_w,
-                    const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const float* __restrict__ scalars) {
+                    const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const float* __restrict__ scalars,
+                    uint32_t* __restrict__ ln_hi, uint32_t* __restrict__ ln_lo, float* __restrict__ ln_part, int ln_stride) {
     extern __shared__ __align__(16) float tile[];     // [T + ks - 1][kDw2Ch] u = GLU(LN(x)), row r <-> frame r - pad; then [kDwMaxK][kDw2Ch] taps
     const int seg = blockIdx.y, c0 = blockIdx.x * kDw2Ch;
     const int pad = (ks - 1) / 2;
@@ -425,36 +428,108 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
     const float2* tile2 = reinterpret_cast<const float2*>(tile) + cp;         // row stride kDw2Ch / 2
     const float2* wt2 = reinterpret_cast<const float2*>(wt) + cp;
     float* xc = x + (size_t)seg * T * d + c;                                  // frame t of the channel pair at xc + t * d
-    for (int t0 = grp * per; t0 < t_end; t0 += kDwOut) {
-        float2 xo[kDwOut];
+    // every thread runs the same number of windows (the row moments below are warp collectives); a window past the
+    // thread's frame run is skipped but for the shuffles
+    for (int wi = 0; wi < per / kDwOut; ++wi) {
+        const int t0 = grp * per + wi * kDwOut;
+        const bool live = t0 < t_end;
+        float2 xn[kDwOut];
 #pragma unroll
-        for (int o = 0; o < kDwOut; ++o)
-            xo[o] = (t0 + o < t_end) ? *reinterpret_cast<const float2*>(xc + (t0 + o) * d) : make_float2(0.f, 0.f);
-        float2 acc[kDwOut];
+        for (int o = 0; o < kDwOut; ++o) xn[o] = make_float2(0.f, 0.f);
+        if (live) {
+            float2 xo[kDwOut];
 #pragma unroll
-        for (int o = 0; o < kDwOut; ++o) acc[o] = make_float2(0.f, 0.f);
+            for (int o = 0; o < kDwOut; ++o)
+                xo[o] = (t0 + o < t_end) ? *reinterpret_cast<const float2*>(xc + (t0 + o) * d) : make_float2(0.f, 0.f);
+            float2 acc[kDwOut];
+#pragma unroll
+            for (int o = 0; o < kDwOut; ++o) acc[o] = make_float2(0.f, 0.f);
 #pragma unroll 1
-        for (int p = 0; p < 3; ++p) {
-            float2 win[kDwOut + kDw2Pass - 1];
-            const float2* tp = tile2 + (t0 + kDw2Pass * p) * (kDw2Ch / 2);   // rows up to t0 + 39 < rows + kDw2Slack exist (zero filled)
+            for (int p = 0; p < 3; ++p) {
+                float2 win[kDwOut + kDw2Pass - 1];
+                const float2* tp = tile2 + (t0 + kDw2Pass * p) * (kDw2Ch / 2);   // rows up to t0 + 39 exist (zero filled past the halo)
 #pragma unroll
-            for (int i = 0; i < kDwOut + kDw2Pass - 1; ++i) win[i] = tp[i * (kDw2Ch / 2)];
-            const float2* wp = wt2 + kDw2Pass * p * (kDw2Ch / 2);
+                for (int i = 0; i < kDwOut + kDw2Pass - 1; ++i) win[i] = tp[i * (kDw2Ch / 2)];
+                const float2* wp = wt2 + kDw2Pass * p * (kDw2Ch / 2);
 #pragma unroll
-            for (int jj = 0; jj < kDw2Pass; ++jj) {
-                const float2 wj = wp[jj * (kDw2Ch / 2)];
+                for (int jj = 0; jj < kDw2Pass; ++jj) {
+                    const float2 wj = wp[jj * (kDw2Ch / 2)];
 #pragma unroll
-                for (int o = 0; o < kDwOut; ++o) acc[o] = __ffma2_rn(wj, win[o + jj], acc[o]);
+                    for (int o = 0; o < kDwOut; ++o) acc[o] = __ffma2_rn(wj, win[o + jj], acc[o]);
+                }
+            }
+#pragma unroll
+            for (int o = 0; o < kDwOut; ++o) {
+                if (t0 + o < t_end) {
+                    const float y0 = fmaxf(fmaf(acc[o].x, sc.x, sh.x), 0.f), y1 = fmaxf(fmaf(acc[o].y, sc.y, sh.y), 0.f);
+                    xn[o] = make_float2(xo[o].x + fmaf(w2, y0, b2), xo[o].y + fmaf(w2, y1, b2));
+                    *reinterpret_cast<float2*>(xc + (t0 + o) * d) = xn[o];
+                    if (ln_part) {
+                        // LayerNorm source of feed_forward_out: the new rows as raw bf16 head / remainder planes
+                        const __nv_bfloat162 hq = __floats2bfloat162_rn(xn[o].x, xn[o].y);
+                        const __nv_bfloat162 lq = __floats2bfloat162_rn(xn[o].x - __low2float(hq), xn[o].y - __high2float(hq));
+                        const size_t e2 = (((size_t)seg * T + t0 + o) * d + c) >> 1;
+                        ln_hi[e2] = *reinterpret_cast<const uint32_t*>(&hq);
+                        ln_lo[e2] = *reinterpret_cast<const uint32_t*>(&lq);
+                    }
+                }
             }
         }
+        if (ln_part) {
+            // (sum, sum of squares) of the CTA's 32 channels for the window's 8 rows: 16 values per thread, a transposing
+            // butterfly over the 16 lanes of the frame group (15 shuffles instead of 64); lane cp ends with value cp
+            float v8[8], v4[4], v2[2];
+            {
+                const bool up = (cp & 8) != 0;
 #pragma unroll
-        for (int o = 0; o < kDwOut; ++o) {
-            if (t0 + o < t_end) {
-                const float y0 = fmaxf(fmaf(acc[o].x, sc.x, sh.x), 0.f), y1 = fmaxf(fmaf(acc[o].y, sc.y, sh.y), 0.f);
-                *reinterpret_cast<float2*>(xc + (t0 + o) * d) = make_float2(xo[o].x + fmaf(w2, y0, b2), xo[o].y + fmaf(w2, y1, b2));
+                for (int j = 0; j < 8; ++j) {
+                    const int o = j >> 1;
+                    // value index i = 2 o + kind; lower half i < 8 <-> outputs 0..3, upper half <-> outputs 4..7
+                    const float lo_v = (j & 1) ? fmaf(xn[o].x, xn[o].x, xn[o].y * xn[o].y) : xn[o].x + xn[o].y;
+                    const float hi_v = (j & 1) ? fmaf(xn[o + 4].x, xn[o + 4].x, xn[o + 4].y * xn[o + 4].y) : xn[o + 4].x + xn[o + 4].y;
+                    const float keep = up ? hi_v : lo_v, send = up ? lo_v : hi_v;
+                    v8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
             }
+            {
+                const bool up = (cp & 4) != 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float keep = up ? v8[j + 4] : v8[j], send = up ? v8[j] : v8[j + 4];
+                    v4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+            }
+            {
+                const bool up = (cp & 2) != 0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float keep = up ? v4[j + 2] : v4[j], send = up ? v4[j] : v4[j + 2];
+                    v2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                }
+            }
+            const bool up = (cp & 1) != 0;
+            const float tot = (up ? v2[1] : v2[0]) + __shfl_xor_sync(0xffffffffu, up ? v2[0] : v2[1], 1);
+            // lane cp holds value index cp: output row t0 + (cp >> 1), kind cp & 1 (0: sum, 1: sum of squares)
+            const int t = t0 + (cp >> 1);
+            if (t < t_end) ln_part[(((size_t)seg * T + t) * ln_stride + blockIdx.x) * 2 + (cp & 1)] = tot;
         }
     }
+}
+
+// (mean, rstd) of every row from the partial moments the producer of the rows left behind (slots per row, d columns)
+__global__ void __launch_bounds__(256)
+ln_finalize_kernel(const float2* __restrict__ part, int M, int stride, int used, float inv_d, float2* __restrict__ stats) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    float s = 0.f, q = 0.f;
+    for (int i = 0; i < used; ++i) {
+        const float2 v = __ldg(part + (size_t)m * stride + i);
+        s += v.x;
+        q += v.y;
+    }
+    const float mean = s * inv_d;
+    const float var = fmaxf(fmaf(-mean, mean, q * inv_d), 0.f);
+    stats[m] = make_float2(mean, 1.f / sqrtf(var + 1e-5f));
 }
 
 // softmax over t2 of (S1[bh][t1][t2] + S2[bh*T + t1][t1 - t2 + T - 1]) / sqrt(d_k)       conformer.py:73-87
@@ -507,8 +582,25 @@ split_kernel(const float* __restrict__ in, int64_t n, float* __restrict__ hi, fl
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
+// Folded LayerNorms (the attention LayerNorm into the QKV projection, the feed_forward_out LayerNorm into its first linear
+// layer): LN(x) W^T = rstd (x (gamma W)^T - mean colsum(gamma W)) + (b + W beta), so the producer of x (the residual
+// epilogue of the previous GEMM / the conv-module kernel) writes x itself as the next GEMM's split operand together with
+// per-row partial moments, and the consumer's epilogue applies the row statistics: the two LayerNorm passes over the
+// activations (920 MB each per block at 1 209 segments) disappear.  Needs the vector epilogues and the fused conv-module
+// kernel: 2xBF16 engine, d_model = 128 * {1, 2, 4, 8}.  The weight blob is packed accordingly (separator.py asks
+// nsf_conformer_ln_fold); NSF_LN_FOLD=0 switches it off (A/B measurements).
+constexpr int kLnSlots = 16;        // partial moments per row: 2 per 256-column GEMM tile, 1 per 32-channel conv CTA
+static bool ln_fold_rule(const nsf_conformer_dims& D) {
+    const char* e = getenv("NSF_LN_FOLD");
+    if (e && e[0] == '0') return false;
+    const int g = D.d_model / 128;
+    return D.gemm_engine == NSF_GEMM_TC_2XBF16 && D.d_model % 128 == 0 && g <= 8 && (g & (g - 1)) == 0 &&
+           D.d_model / kDw2Ch <= kLnSlots;
+}
+
 struct Workspace {
     float *x, *h_hi, *h_lo, *u_hi, *u_lo, *q_hi, *q_lo, *k_hi, *k_lo, *vt_hi, *vt_lo, *s1, *s2, *p_hi, *p_lo;
+    float *ln_part, *ln_stats;      // folded LayerNorms: [M][kLnSlots] partial (sum, sum of squares), [M] (mean, rstd)
     int64_t total_floats;
 };
 
@@ -537,6 +629,8 @@ static Workspace carve(const nsf_conformer_dims& D, int n_seg, float* base) {
     w.s2 = take(unfused ? BH * D.T * ld2 : 0);
     w.p_hi = take(unfused ? BH * D.T * Tp : 0);
     w.p_lo = take(unfused ? BH * D.T * Tp : 0);
+    w.ln_part = take(M * kLnSlots * 2);
+    w.ln_stats = take(M * 2);
     w.total_floats = off;
     return w;
 }
@@ -558,6 +652,8 @@ static int validate_dims(const nsf_conformer_dims& D) {
 
 using namespace nsf;
 
+extern "C" int nsf_conformer_ln_fold(const nsf_conformer_dims* dims) { return dims && ln_fold_rule(*dims) ? 1 : 0; }
+
 extern "C" int64_t nsf_conformer_num_offsets(const nsf_conformer_dims* dims) {
     return dims ? kGlobalOffsets + (int64_t)kPerLayer * dims->n_blocks : 0;
 }
@@ -575,6 +671,7 @@ extern "C" int nsf_conformer_create(const nsf_conformer_dims* dims, const float*
     nsf_conformer* h = new (std::nothrow) nsf_conformer;
     NSF_REQUIRE(h, "nsf_conformer_create: out of memory");
     h->dims = *dims;
+    h->ln_fold = ln_fold_rule(*dims);
     h->blob = blob;
     h->blob_floats = blob_floats;
     h->n_offsets = n_offsets;
@@ -633,9 +730,17 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         p.T = T; p.Tp = Tp; p.n_heads = H; p.d_k = d_k; p.d_model = d;
         return p;
     };
+    const bool fold = h->ln_fold;
+    float2* ln_part = reinterpret_cast<float2*>(w.ln_part);
+    float2* ln_stats = reinterpret_cast<float2*>(w.ln_stats);
+    // ln_src: the residual epilogue also writes the rows as the next GEMM's operand (h planes) + partial moments;
+    // ln_csum: the operand rows are raw, LayerNorm is applied in the epilogue (ln_stats, column sums of the scaled weights)
     auto linear = [&](const float* a_hi, const float* a_lo, int64_t lda, int K, const float* w_hi, const float* w_lo,
-                      const float* bias, int N, int epi, float alpha, float* o0, float* o1, int64_t ldo) {
+                      const float* bias, int N, int epi, float alpha, float* o0, float* o1, int64_t ldo,
+                      bool ln_src = false, const float* ln_csum = nullptr) {
         GemmParams p = base_params();
+        if (ln_src) { p.ln_hi = w.h_hi; p.ln_lo = w.h_lo; p.ln_part = ln_part; p.ln_slots = kLnSlots; }
+        if (ln_csum) { p.ln_stats = ln_stats; p.ln_csum = ln_csum; }
         p.A_hi = a_hi; p.A_lo = a_lo; p.lda = lda;
         p.B_hi = w_hi; p.B_lo = w_lo; p.ldb = K;
         p.M = M; p.N = N; p.K = K; p.n_valid = N;
@@ -666,14 +771,19 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                     1.f, w.u_hi, w.u_lo, dff);
         if (rc) return rc;
         rc = linear(w.u_hi, w.u_lo, dff, dff, h->l(L, L_FFI_W2_HI), h->l(L, L_FFI_W2_LO), h->l(L, L_FFI_B2), d, EPI_RESID, 0.5f,
-                    w.x, nullptr, d);
+                    w.x, nullptr, d, fold);
         if (rc) return rc;
         // x += MHSA(x)                                                                         conformer.py:180
         { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-          rc = ln_launch(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, fmt, s); }
+          if (fold) {
+              ln_finalize_kernel<<<ceil_div(M, 256), 256, 0, s>>>(ln_part, M, kLnSlots, 2 * ceil_div(d, 256), 1.f / (float)d, ln_stats);
+              rc = check_launch("ln_finalize_kernel");
+          } else {
+              rc = ln_launch(w.x, M, d, h->l(L, L_ATT_LN_G), h->l(L, L_ATT_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, fmt, s);
+          } }
         if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WQKV_HI), h->l(L, L_WQKV_LO), h->l(L, L_BQKV), 3 * d, EPI_QKV, 1.f, nullptr,
-                    nullptr, 0);
+                    nullptr, 0, false, fold ? h->l(L, L_QKV_CSUM) : nullptr);
         if (rc) return rc;
         if (attn_fused_supported(T, d_k) && eng != NSF_GEMM_SIMT_FP32) {
             // scores, relative-position skew, softmax and P V in one tcgen05 kernel (attention.cu)
@@ -731,7 +841,9 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
             const size_t smem = (size_t)(T + kDwMaxK - 1 + kDw2Slack + kDwMaxK) * kDw2Ch * sizeof(float);
             NSF_CUDA(cudaFuncSetAttribute(dwconv_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             dwconv_fused_kernel<<<grid, kDw2Threads, smem, s>>>(w.x, stats, h->l(L, L_CONV_LN_G), h->l(L, L_CONV_LN_B), T, d, D.kernel_size,
-                                                                h->l(L, L_DW_W), h->l(L, L_BN_SCALE), h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS));
+                                                                h->l(L, L_DW_W), h->l(L, L_BN_SCALE), h->l(L, L_BN_SHIFT), h->l(L, L_CONV_SCALARS),
+                                                                fold ? reinterpret_cast<uint32_t*>(w.h_hi) : nullptr,
+                                                                fold ? reinterpret_cast<uint32_t*>(w.h_lo) : nullptr, fold ? w.ln_part : nullptr, kLnSlots);
             if ((rc = check_launch("dwconv_fused_kernel"))) return rc;
         } else {
             { ProfScope prof(PROF_NET_OTHER, 0.0, s);
@@ -746,10 +858,15 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
         }
         // x += 0.5 * FF_out(x)                                                                 conformer.py:182
         { ProfScope prof(PROF_NET_OTHER, 0.0, s);
-          rc = ln_launch(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, fmt, s); }
+          if (fold) {
+              ln_finalize_kernel<<<ceil_div(M, 256), 256, 0, s>>>(ln_part, M, kLnSlots, d / kDw2Ch, 1.f / (float)d, ln_stats);
+              rc = check_launch("ln_finalize_kernel");
+          } else {
+              rc = ln_launch(w.x, M, d, h->l(L, L_FFO_LN_G), h->l(L, L_FFO_LN_B), 0, nullptr, nullptr, nullptr, w.h_hi, w.h_lo, fmt, s);
+          } }
         if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_FFO_W1_HI), h->l(L, L_FFO_W1_LO), h->l(L, L_FFO_B1), dff, EPI_RELU_SPLIT,
-                    1.f, w.u_hi, w.u_lo, dff);
+                    1.f, w.u_hi, w.u_lo, dff, false, fold ? h->l(L, L_FFO_CSUM) : nullptr);
         if (rc) return rc;
         rc = linear(w.u_hi, w.u_lo, dff, dff, h->l(L, L_FFO_W2_HI), h->l(L, L_FFO_W2_LO), h->l(L, L_FFO_B2), d, EPI_RESID, 0.5f,
                     w.x, nullptr, d);

@@ -44,6 +44,14 @@ struct GemmParams {
     // geometry for the scatter epilogues
     int T, Tp, n_heads, d_k, d_model;
     float* q_hi; float* q_lo; float* k_hi; float* k_lo; float* vt_hi; float* vt_lo;
+    // LayerNorm folded into the GEMMs on either side of it (tensor-core engines, vector epilogue; conformer.cu):
+    //   producer (EPI_RESID): the updated residual rows also go out as raw split planes (ln_hi, ln_lo; pitch ldo, format
+    //   out_fmt) -- the A operand of the next GEMM -- with per-row partial (sum, sum of squares) in ln_part[m][ln_slots]
+    //   (slot 2 * n_blk + epilogue half);
+    //   consumer (EPI_QKV, EPI_RELU_SPLIT): v = rstd[m] (acc - mean[m] csum[n]) + bias[n] with (mean, rstd) = ln_stats[m],
+    //   csum[n] = sum_k of the gamma-scaled weights as stored, bias[n] = b[n] + sum_k beta[k] W[n][k].
+    float* ln_hi; float* ln_lo; float2* ln_part; int ln_slots;
+    const float2* ln_stats; const float* ln_csum;
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }

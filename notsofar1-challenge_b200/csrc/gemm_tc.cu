@@ -58,7 +58,7 @@ struct RowWalker {      // (segment, frame) of consecutive rows m = seg * T + t 
 };
 
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
-                                               float* stage, int lane) {
+                                               float* stage, int lane, float (&ln_s)[4], float (&ln_q)[4]) {
     const bool lane_is_row = p.epi == EPI_MASK || (p.epi == EPI_QKV && nc >= 2 * p.d_model && !p.v_rowmajor);
     if (lane_is_row) {
         const int m = r0 + lane;
@@ -80,10 +80,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             const int c = nc - 2 * p.d_model;
             const int h = c / p.d_k, d0 = c - h * p.d_k;
             const size_t o = (((size_t)seg * p.n_heads + h) * p.d_k + d0) * p.Tp + t;
+            const float2 st = p.ln_stats ? __ldg(p.ln_stats + m) : make_float2(0.f, 1.f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-                split_store(p.qkv_fmt, p.vt_hi, p.vt_lo, o + (size_t)j * p.Tp,
-                            __uint_as_float(r[j]) * p.acc_scale + (p.bias ? __ldg(p.bias + nc + j) : 0.f));
+            for (int j = 0; j < 32; ++j) {
+                float v = __uint_as_float(r[j]) * p.acc_scale;
+                if (p.ln_stats) v = (v - st.x * __ldg(p.ln_csum + nc + j)) * st.y;
+                split_store(p.qkv_fmt, p.vt_hi, p.vt_lo, o + (size_t)j * p.Tp, v + (p.bias ? __ldg(p.bias + nc + j) : 0.f));
+            }
         }
         return;
     }
@@ -105,6 +108,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             if (p.bias) {
                 const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
                 bs[0] = b0.x; bs[1] = b0.y; bs[2] = b0.z; bs[3] = b0.w; bs[4] = b1.x; bs[5] = b1.y; bs[6] = b1.z; bs[7] = b1.w;
+            }
+            // folded LayerNorm of the operand rows: per-row (mean, rstd), per-column sums of the scaled weights
+            float cs[8];
+            float2 lst[4];
+            if (p.ln_stats) {
+                const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.ln_csum + n0)), c1 = __ldg(reinterpret_cast<const float4*>(p.ln_csum + n0 + 4));
+                cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int m = r0 + rq + 8 * k;
+                    lst[k] = __ldg(p.ln_stats + (m < p.M ? m : r0));
+                }
             }
             const int g0 = (2 * cg) ^ rq, g1 = (2 * cg + 1) ^ rq;
             // EPI_QKV geometry (a 32-column chunk stays inside q or k and inside one head)
@@ -131,8 +146,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                 const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 32 + 4 * g0);
                 const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 32 + 4 * g1);
                 float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                if (p.ln_stats) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = v[e] * p.acc_scale + bs[e];
+                    for (int e = 0; e < 8; ++e) v[e] = (v[e] * p.acc_scale - lst[k].x * cs[e]) * lst[k].y + bs[e];
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = v[e] * p.acc_scale + bs[e];
+                }
                 switch (p.epi) {
                     case EPI_STORE: {
                         float* o = p.out0 + (size_t)b * p.o_batch_stride + (size_t)m * p.ldo + n0;
@@ -163,8 +183,19 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                     case EPI_RESID: {
                         float* o = p.out0 + (size_t)m * p.ldo + n0;
                         const float4 x0 = xo[k][0], x1 = xo[k][1];
-                        *reinterpret_cast<float4*>(o) = make_float4(x0.x + p.alpha * v[0], x0.y + p.alpha * v[1], x0.z + p.alpha * v[2], x0.w + p.alpha * v[3]);
-                        *reinterpret_cast<float4*>(o + 4) = make_float4(x1.x + p.alpha * v[4], x1.y + p.alpha * v[5], x1.z + p.alpha * v[6], x1.w + p.alpha * v[7]);
+                        const float xn[8] = {x0.x + p.alpha * v[0], x0.y + p.alpha * v[1], x0.z + p.alpha * v[2], x0.w + p.alpha * v[3],
+                                             x1.x + p.alpha * v[4], x1.y + p.alpha * v[5], x1.z + p.alpha * v[6], x1.w + p.alpha * v[7]};
+                        *reinterpret_cast<float4*>(o) = make_float4(xn[0], xn[1], xn[2], xn[3]);
+                        *reinterpret_cast<float4*>(o + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
+                        if (p.ln_part) {
+                            // LayerNorm source of the next GEMM: raw planes of the new row + its partial moments
+                            split_store8(p.out_fmt, p.ln_hi, p.ln_lo, (size_t)m * p.ldo + n0, xn);
+                            float s = 0.f, q = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) { s += xn[e]; q = fmaf(xn[e], xn[e], q); }
+                            ln_s[k] += s;
+                            ln_q[k] += q;
+                        }
                         break;
                     }
                     case EPI_QKV: {     // q, k: [seg][head][t][d_k]
@@ -391,12 +422,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tcgen05_fence_after();
             const int n_end = min(p.N - n0, TBN);           // valid columns of this tile (> 0)
             const int c_first = half * 32;
+            const bool ln_src = p.epi == EPI_RESID && p.ln_part != nullptr;
             if (c_first >= n_end) {                         // nothing to read for this warp
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                if (ln_src && r0 + lane < p.M) p.ln_part[(size_t)(r0 + lane) * p.ln_slots + 2 * n_blk + half] = make_float2(0.f, 0.f);
                 continue;
             }
+            float ln_s[4] = {0.f, 0.f, 0.f, 0.f}, ln_q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int c0 = c_first; c0 < n_end; c0 += 64) {
                 uint32_t r[32];
@@ -408,7 +442,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
                 }
                 if (r0 >= p.M) continue;                    // warp-uniform: quarter entirely out of range
-                epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane);
+                epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q);
+            }
+            if (ln_src && r0 < p.M) {
+                // row moments of this warp's columns of the tile: the four lanes that share a row (cg = lane & 3) add up
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float s = ln_s[k], q2 = ln_q[k];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);  q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);  q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
+                    const int m = r0 + (lane >> 2) + 8 * k;
+                    if ((lane & 3) == 0 && m < p.M) p.ln_part[(size_t)m * p.ln_slots + 2 * n_blk + half] = make_float2(s, q2);
+                }
             }
         }
     }
@@ -462,6 +507,15 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
             default: ok = false; break;     // EPI_MASK writes along rows
         }
         pv.vec8 = ok ? 1 : 0;
+        if ((p.ln_part || p.ln_stats) && !ok) { set_error("gemm_tc: the folded-LayerNorm epilogues need the vector path (N, pitches, alignment)"); return NSF_ERR_INVALID_ARG; }
+        if (p.ln_part && !(p.epi == EPI_RESID && p.ldo % 8 == 0 && al16(p.ln_hi) && al16(p.ln_lo) && p.ln_slots >= 2 * ceil_div(p.N, TBN))) {
+            set_error("gemm_tc: LayerNorm source outputs need EPI_RESID, ldo %% 8 == 0, aligned planes and 2 slots per column tile");
+            return NSF_ERR_INVALID_ARG;
+        }
+        if (p.ln_stats && !((p.epi == EPI_QKV || p.epi == EPI_RELU_SPLIT) && p.ln_csum && al16(p.ln_csum))) {
+            set_error("gemm_tc: folded LayerNorm is implemented for EPI_QKV / EPI_RELU_SPLIT with an aligned column-sum vector");
+            return NSF_ERR_INVALID_ARG;
+        }
     }
     NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int tiles_m = ceil_div(p.M, TBM), tiles_n = ceil_div(p.N, TBN);

@@ -93,12 +93,18 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
     Blob order (offsets index): 12 global entries
       0 embed.W hi [d][Kf] | 1 embed.W lo | 2 embed.b | 3 embed LN g | 4 embed LN b | 5 pe_k hi [2*maxlen][d_k] | 6 pe_k lo (TF32 pairs)
       7 head.W hi [n_out][d] | 8 head.W lo | 9 head.b | 10 pe_k hi | 11 pe_k lo (bf16 pairs)
-    then 32 per encoder block
+    then 34 per encoder block
       0-7   feed_forward_in : LN g, LN b, W1 hi, W1 lo, b1, W2 hi, W2 lo, b2
       8-15  self_attn       : LN g, LN b, Wqkv hi [3d][d], Wqkv lo, bqkv, Wo hi, Wo lo, bo
       16-21 conv            : LN g, LN b, scalars[8] = (w1a, b1a, w1g, b1g, w2, b2, 0, 0), dw W [d][ks], BN scale, BN shift
       22-29 feed_forward_out: as feed_forward_in
       30-31 layer_norm      : g, b
+      32-33 column sums of the stored Wqkv / feed_forward_out W1 (folded LayerNorms, see below; zeros otherwise)
+
+    When the library folds the attention and feed_forward_out LayerNorms into the following GEMM (nsf_conformer_ln_fold:
+    2xBF16 engine, d_model = 128 * {1, 2, 4}), LN(x) W^T + b = rstd (x (gamma W)^T - mean colsum(gamma W)) + (b + W beta):
+    those two weights are stored gamma-scaled, their biases as b + W beta (float64 sums), and entries 32-33 hold the column
+    sums of the weights *as stored* (head + remainder), so that the mean term cancels what the tensor cores accumulate.
     """
     w = _strip_prefix(state_dict)
     d_model, in_features = w[_P + "conformer.embed.0.weight"].shape
@@ -126,16 +132,37 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
         cursor += a.size + pad
 
     fmt = _cabi.split_fmt_of_engine(gemm_engine)
+    dims = _cabi.ConformerDims(d_model=d_model, n_heads=n_heads, d_ff=d_ff, n_blocks=n_blocks, kernel_size=ks,
+                               in_features=in_features, n_out=n_out, maxlen=two_maxlen // 2, T=T, gemm_engine=gemm_engine)
+    ln_fold = bool(_cabi.load().nsf_conformer_ln_fold(C.byref(dims)))
+    csums = []
 
     def add_split(a: np.ndarray, tf32: bool = False):
         """GEMM weight in the engine's split format (pe_k feeds the attention kernel, which stays SPLIT_TF32)."""
         hi, lo = _split_tf32(a) if (tf32 or fmt == _cabi.SPLIT_TF32) else _split16(a, fmt)
         add(hi)
         add(lo)
+        return hi, lo
 
-    def add_ffn(q: str):
+    def add_linear_after_ln(W: np.ndarray, b: np.ndarray, g: np.ndarray, beta: np.ndarray):
+        """W [N, K], b [N] of a Linear that follows LayerNorm(gamma=g, beta); returns the column sums entry."""
+        if not ln_fold:
+            add_split(W); add(b)
+            return np.zeros(W.shape[0], np.float32)
+        Wg = (W.astype(np.float32) * g.astype(np.float32)[None, :]).astype(np.float32)
+        hi, lo = add_split(Wg)
+        add((b.astype(np.float64) + W.astype(np.float64) @ beta.astype(np.float64)).astype(np.float32))
+        assert fmt == _cabi.SPLIT_BF16
+        stored = (torch.from_numpy(hi.view(np.int16).copy()).view(torch.bfloat16).to(torch.float64)
+                  + torch.from_numpy(lo.view(np.int16).copy()).view(torch.bfloat16).to(torch.float64)).reshape(W.shape)
+        return stored.sum(dim=1).to(torch.float32).numpy()
+
+    def add_ffn(q: str, after_ln: bool = False):
         add(w[q + "layer_norm.weight"]); add(w[q + "layer_norm.bias"])
-        add_split(w[q + "net.0.weight"]); add(w[q + "net.0.bias"])
+        if after_ln:
+            csums.append(add_linear_after_ln(w[q + "net.0.weight"], w[q + "net.0.bias"], w[q + "layer_norm.weight"], w[q + "layer_norm.bias"]))
+        else:
+            add_split(w[q + "net.0.weight"]); add(w[q + "net.0.bias"])
         add_split(w[q + "net.3.weight"]); add(w[q + "net.3.bias"])
 
     c = _P + "conformer."
@@ -158,8 +185,11 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
         add_ffn(p + "feed_forward_in.")
         a = p + "self_attn."
         add(w[a + "layer_norm.weight"]); add(w[a + "layer_norm.bias"])
-        add_split(np.concatenate([w[a + "linear_q.weight"], w[a + "linear_k.weight"], w[a + "linear_v.weight"]], axis=0))
-        add(np.concatenate([w[a + "linear_q.bias"], w[a + "linear_k.bias"], w[a + "linear_v.bias"]]))
+        csums.clear()
+        csums.append(add_linear_after_ln(
+            np.concatenate([w[a + "linear_q.weight"], w[a + "linear_k.weight"], w[a + "linear_v.weight"]], axis=0),
+            np.concatenate([w[a + "linear_q.bias"], w[a + "linear_k.bias"], w[a + "linear_v.bias"]]),
+            w[a + "layer_norm.weight"], w[a + "layer_norm.bias"]))
         add_split(w[a + "linear_out.weight"]); add(w[a + "linear_out.bias"])
         cv = p + "conv."
         add(w[cv + "layer_norm.weight"]); add(w[cv + "layer_norm.bias"])
@@ -173,12 +203,11 @@ def pack_weights(state_dict: Dict[str, object], T: int, gemm_engine: int):
         shift = (w[cv + "dw_conv_1d.bias"].astype(np.float64) - w[cv + "BN.running_mean"].astype(np.float64)) * scale \
             + w[cv + "BN.bias"].astype(np.float64)
         add(scale.astype(np.float32)); add(shift.astype(np.float32))
-        add_ffn(p + "feed_forward_out.")
+        add_ffn(p + "feed_forward_out.", after_ln=True)
         add(w[p + "layer_norm.weight"]); add(w[p + "layer_norm.bias"])
+        add(csums[0]); add(csums[1])
 
-    dims = _cabi.ConformerDims(d_model=d_model, n_heads=n_heads, d_ff=d_ff, n_blocks=n_blocks, kernel_size=ks,
-                               in_features=in_features, n_out=n_out, maxlen=two_maxlen // 2, T=T, gemm_engine=gemm_engine)
-    assert len(offsets) == 12 + 32 * n_blocks, len(offsets)
+    assert len(offsets) == 12 + 34 * n_blocks, len(offsets)
     return dims, np.concatenate(chunks), np.asarray(offsets, dtype=np.int64), \
         dict(input_bias=w[_P + "input_bias"].reshape(-1).astype(np.float32),
              input_scale=w[_P + "input_scale"].reshape(-1).astype(np.float32))

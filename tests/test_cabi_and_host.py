@@ -42,7 +42,7 @@ def test_library_argument_errors_without_gpu(N):
     assert rc == -1 and b"null" in lib.nsf_last_error()
     dims = N._cabi.ConformerDims(d_model=100, n_heads=8, d_ff=1024, n_blocks=18, kernel_size=33, in_features=1799,
                                  n_out=1028, maxlen=1000, T=186, gemm_engine=1)
-    assert lib.nsf_conformer_num_offsets(dims) == 12 + 32 * 18
+    assert lib.nsf_conformer_num_offsets(dims) == 12 + 34 * 18
     # the entry points added for the diarization / ASR rows validate their arguments before touching the device
     import ctypes as C
     from notsofar_b200.titanet import TitanetDims
@@ -144,7 +144,7 @@ def test_pack_weights_layout(N, small_weights):
     dims, blob, offsets, extra = N.pack_weights(small_weights, T=186, gemm_engine=N.GEMM_TC_3XTF32)
     assert (dims.d_model, dims.n_heads, dims.d_ff, dims.n_blocks, dims.kernel_size) == (128, 2, 256, 2, 33)
     assert (dims.in_features, dims.n_out, dims.maxlen) == (1799, 1028, 1000)
-    assert len(offsets) == 12 + 32 * 2 and np.all(offsets % 64 == 0) and blob.dtype == np.float32
+    assert len(offsets) == 12 + 34 * 2 and np.all(offsets % 64 == 0) and blob.dtype == np.float32
     Kf = 1824
     hi = blob[offsets[0]:offsets[0] + 128 * Kf].reshape(128, Kf)
     lo = blob[offsets[1]:offsets[1] + 128 * Kf].reshape(128, Kf)
