@@ -737,9 +737,10 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
     // ln_csum: the operand rows are raw, LayerNorm is applied in the epilogue (ln_stats, column sums of the scaled weights)
     auto linear = [&](const float* a_hi, const float* a_lo, int64_t lda, int K, const float* w_hi, const float* w_lo,
                       const float* bias, int N, int epi, float alpha, float* o0, float* o1, int64_t ldo,
-                      bool ln_src = false, const float* ln_csum = nullptr) {
+                      int ln_src = 0, const float* ln_csum = nullptr) {
         GemmParams p = base_params();
-        if (ln_src) { p.ln_hi = w.h_hi; p.ln_lo = w.h_lo; p.ln_part = ln_part; p.ln_slots = kLnSlots; }
+        if (ln_src) { p.ln_part = ln_part; p.ln_slots = kLnSlots; }
+        if (ln_src == 1) { p.ln_hi = w.h_hi; p.ln_lo = w.h_lo; }         // 2: row moments only (the conv module's LayerNorm statistics)
         if (ln_csum) { p.ln_stats = ln_stats; p.ln_csum = ln_csum; }
         p.A_hi = a_hi; p.A_lo = a_lo; p.lda = lda;
         p.B_hi = w_hi; p.B_lo = w_lo; p.ldb = K;
@@ -771,7 +772,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                     1.f, w.u_hi, w.u_lo, dff);
         if (rc) return rc;
         rc = linear(w.u_hi, w.u_lo, dff, dff, h->l(L, L_FFI_W2_HI), h->l(L, L_FFI_W2_LO), h->l(L, L_FFI_B2), d, EPI_RESID, 0.5f,
-                    w.x, nullptr, d, fold);
+                    w.x, nullptr, d, fold ? 1 : 0);
         if (rc) return rc;
         // x += MHSA(x)                                                                         conformer.py:180
         { ProfScope prof(PROF_NET_OTHER, 0.0, s);
@@ -783,7 +784,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
           } }
         if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WQKV_HI), h->l(L, L_WQKV_LO), h->l(L, L_BQKV), 3 * d, EPI_QKV, 1.f, nullptr,
-                    nullptr, 0, false, fold ? h->l(L, L_QKV_CSUM) : nullptr);
+                    nullptr, 0, 0, fold ? h->l(L, L_QKV_CSUM) : nullptr);
         if (rc) return rc;
         if (attn_fused_supported(T, d_k) && eng != NSF_GEMM_SIMT_FP32) {
             // scores, relative-position skew, softmax and P V in one tcgen05 kernel (attention.cu)
@@ -822,7 +823,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
                 if ((rc = gemm_launch(eng_attn, p, s))) return rc;
             }
         }
-        rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WO_HI), h->l(L, L_WO_LO), h->l(L, L_BO), d, EPI_RESID, 1.f, w.x, nullptr, d);
+        rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_WO_HI), h->l(L, L_WO_LO), h->l(L, L_BO), d, EPI_RESID, 1.f, w.x, nullptr, d, fold ? 2 : 0);
         if (rc) return rc;
         // x += Conv(x)                                                                         conformer.py:181
         if (d % 128 == 0 && d / 128 <= 8 && ((d / 128) & (d / 128 - 1)) == 0) {
@@ -830,6 +831,10 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
             ProfScope prof(PROF_NET_OTHER, 0.0, s);
             float2* stats = reinterpret_cast<float2*>(w.u_hi);          // [M] (mean, rstd); u_hi is free between the FFNs
             const int grid_s = ceil_div(M, 8);
+            if (fold) {
+                // the out-projection's residual epilogue left the row moments behind
+                ln_finalize_kernel<<<ceil_div(M, 256), 256, 0, s>>>(ln_part, M, kLnSlots, 2 * ceil_div(d, 256), 1.f / (float)d, stats);
+            } else
             switch (d / 128) {
                 case 1: ln_stats_vec_kernel<1><<<grid_s, 256, 0, s>>>(w.x, M, stats); break;
                 case 2: ln_stats_vec_kernel<2><<<grid_s, 256, 0, s>>>(w.x, M, stats); break;
@@ -866,7 +871,7 @@ extern "C" int nsf_conformer_forward(nsf_conformer* h, const float* feat, const 
           } }
         if (rc) return rc;
         rc = linear(w.h_hi, w.h_lo, d, d, h->l(L, L_FFO_W1_HI), h->l(L, L_FFO_W1_LO), h->l(L, L_FFO_B1), dff, EPI_RELU_SPLIT,
-                    1.f, w.u_hi, w.u_lo, dff, false, fold ? h->l(L, L_FFO_CSUM) : nullptr);
+                    1.f, w.u_hi, w.u_lo, dff, 0, fold ? h->l(L, L_FFO_CSUM) : nullptr);
         if (rc) return rc;
         rc = linear(w.u_hi, w.u_lo, dff, dff, h->l(L, L_FFO_W2_HI), h->l(L, L_FFO_W2_LO), h->l(L, L_FFO_B2), d, EPI_RESID, 0.5f,
                     w.x, nullptr, d);

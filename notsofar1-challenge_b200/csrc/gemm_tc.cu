@@ -25,20 +25,22 @@
 namespace nsf {
 
 constexpr int TBM = 128;                           // tile rows; tile columns TN = 256 (default) or 32 (small-M GEMMs, see gemm_tc_launch)
-constexpr int kRowBytes = 128;                     // one swizzle row of K: 32 tf32 or 64 16-bit elements
-constexpr int kATileBytes = TBM * kRowBytes;       // 16 KB
 constexpr int kTcThreads = 320;                   // 1 TMA + 1 MMA + 8 epilogue warps
 constexpr uint32_t kTmemCols = 512;                // two 128 x 256 fp32 accumulators
 constexpr int kEpiPitch = 33;                      // staging row pitch (floats): conflict-free both ways
 constexpr int kEpiBytes = 8 * 32 * kEpiPitch * 4;  // one 32 x 32 staging tile per epilogue warp
 
 // MODE 1: one kind::tf32 pass; 3: 3xTF32; 16: three kind::f16 MMAs on 16-bit head/remainder pairs (2xBF16 / 2xF16)
-template <int MODE, int TN> struct TcCfg {
+// RB: bytes of K per shared-memory row = swizzle span (128: SWIZZLE_128B, the default; 64: SWIZZLE_64B -- half-size stages,
+// twice as many of them: the same bytes in flight at a finer grain; an experiment, see gemm_tc_launch).
+template <int MODE, int TN, int RB = 128> struct TcCfg {
     static constexpr bool kSplit = MODE == 3 || MODE == 16;
-    static constexpr int kBlockK = MODE >= 16 ? 64 : 32;          // elements of K per stage (one 128-byte row)
-    static constexpr int kBTileBytes = TN * kRowBytes;            // 32 KB (TN = 256) or 4 KB (TN = 32)
+    static constexpr int kRowBytes = RB;
+    static constexpr int kBlockK = RB / (MODE >= 16 ? 2 : 4);     // elements of K per stage (one swizzle row)
+    static constexpr int kATileBytes = TBM * RB;                  // 16 KB (RB = 128)
+    static constexpr int kBTileBytes = TN * RB;                   // 32 KB (TN = 256) or 4 KB (TN = 32)
     static constexpr int kStageBytes = (kSplit ? 2 : 1) * (kATileBytes + kBTileBytes);
-    static constexpr int kStages = TN == 32 ? 8 : (kSplit ? 2 : 4);
+    static constexpr int kStages = (TN == 32 ? 8 : (kSplit ? 2 : 4)) * (128 / RB);
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 /*barriers*/ + 1024 /*alignment slack*/;
 };
 
@@ -58,7 +60,8 @@ struct RowWalker {      // (segment, frame) of consecutive rows m = seg * T + t 
 };
 
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
-                                               float* stage, int lane, float (&ln_s)[4], float (&ln_q)[4]) {
+                                               float* stage, int lane, float (&ln_s)[4], float (&ln_q)[4],
+                                               const size_t (&qkv_row)[4]) {
     const bool lane_is_row = p.epi == EPI_MASK || (p.epi == EPI_QKV && nc >= 2 * p.d_model && !p.v_rowmajor);
     if (lane_is_row) {
         const int m = r0 + lane;
@@ -189,7 +192,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                         *reinterpret_cast<float4*>(o + 4) = make_float4(xn[4], xn[5], xn[6], xn[7]);
                         if (p.ln_part) {
                             // LayerNorm source of the next GEMM: raw planes of the new row + its partial moments
-                            split_store8(p.out_fmt, p.ln_hi, p.ln_lo, (size_t)m * p.ldo + n0, xn);
+                            if (p.ln_hi) split_store8(p.out_fmt, p.ln_hi, p.ln_lo, (size_t)m * p.ldo + n0, xn);
                             float s = 0.f, q = 0.f;
 #pragma unroll
                             for (int e = 0; e < 8; ++e) { s += xn[e]; q = fmaf(xn[e], xn[e], q); }
@@ -198,10 +201,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                         }
                         break;
                     }
-                    case EPI_QKV: {     // q, k: [seg][head][t][d_k]
-                        const int seg = m / p.T, t = m - seg * p.T;
+                    case EPI_QKV: {     // q, k: [seg][head][t][d_k]; qkv_row[k] = (seg n_heads T + t) d_k of the lane's k-th row (once per tile)
                         split_store8(p.qkv_fmt, which == 0 ? p.q_hi : which == 1 ? p.k_hi : p.vt_hi, which == 0 ? p.q_lo : which == 1 ? p.k_lo : p.vt_lo,
-                                     (((size_t)seg * p.n_heads + hq) * p.T + t) * p.d_k + dq, v);
+                                     qkv_row[k] + (size_t)(hq * p.T) * p.d_k + dq, v);
                         break;
                     }
                     case EPI_PV: {      // batch = (seg, head); rows are frames of that segment
@@ -295,14 +297,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
     __syncwarp();
 }
 
-template <int MODE, int TN>
+template <int MODE, int TN, int RB>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                const GemmParams p, const int tiles_m, const int tiles_n, const int total_tiles) {
-    using Cfg = TcCfg<MODE, TN>;
+    using Cfg = TcCfg<MODE, TN, RB>;
     constexpr int TBN = TN;
-    constexpr int kBTileBytes = Cfg::kBTileBytes;
+    constexpr int kBTileBytes = Cfg::kBTileBytes, kATileBytes = Cfg::kATileBytes, kRowBytes = Cfg::kRowBytes;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;                       // SWIZZLE_128B tiles need 1024-byte alignment
@@ -383,16 +385,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
                     for (int ks = 0; ks < kRowBytes / 32; ++ks) {             // UMMA_K = 8 tf32 = 16 halves = 32 bytes
                         const uint32_t koff = ks * 32;
-                        const uint64_t da_hi = make_smem_desc(a_hi + koff), db_hi = make_smem_desc(b_hi + koff);
+                        const uint64_t da_hi = make_smem_desc_rb<RB>(a_hi + koff), db_hi = make_smem_desc_rb<RB>(b_hi + koff);
                         if (MODE == 16) {
-                            const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
+                            const uint64_t da_lo = make_smem_desc_rb<RB>(a_lo + koff), db_lo = make_smem_desc_rb<RB>(b_lo + koff);
                             tcgen05_mma_f16(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);     // small terms first
                             tcgen05_mma_f16(d_tmem, da_hi, db_lo, idesc, 1);
                             tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, 1);
                         } else if (MODE == 116) {
                             tcgen05_mma_f16(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
                         } else if (MODE == 3) {
-                            const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
+                            const uint64_t da_lo = make_smem_desc_rb<RB>(a_lo + koff), db_lo = make_smem_desc_rb<RB>(b_lo + koff);
                             tcgen05_mma_tf32(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);    // small terms first
                             tcgen05_mma_tf32(d_tmem, da_hi, db_lo, idesc, 1);
                             tcgen05_mma_tf32(d_tmem, da_hi, db_hi, idesc, 1);
@@ -418,10 +420,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int n0 = n_blk * TBN;
             const int r0 = m_blk * TBM + q * 32;           // first row of this warp's quarter
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
-            mbar_wait(tmem_full_bar(acc), aph);
-            tcgen05_fence_after();
             const int n_end = min(p.N - n0, TBN);           // valid columns of this tile (> 0)
             const int c_first = half * 32;
+            mbar_wait(tmem_full_bar(acc), aph);
+            tcgen05_fence_after();
             const bool ln_src = p.epi == EPI_RESID && p.ln_part != nullptr;
             if (c_first >= n_end) {                         // nothing to read for this warp
                 tcgen05_fence_before();
@@ -431,6 +433,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 continue;
             }
             float ln_s[4] = {0.f, 0.f, 0.f, 0.f}, ln_q[4] = {0.f, 0.f, 0.f, 0.f};
+            // per-tile row work of the vector epilogues (a lane owns rows r0 + (lane >> 2) + 8 k of every chunk)
+            size_t qkv_row[4] = {0, 0, 0, 0};
+            if (p.epi == EPI_QKV) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int m = min(r0 + (lane >> 2) + 8 * k, p.M - 1);
+                    const int seg = m / p.T, t = m - seg * p.T;
+                    qkv_row[k] = ((size_t)seg * p.n_heads * p.T + t) * p.d_k;
+                }
+            }
 #pragma unroll 1
             for (int c0 = c_first; c0 < n_end; c0 += 64) {
                 uint32_t r[32];
@@ -442,7 +454,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
                 }
                 if (r0 >= p.M) continue;                    // warp-uniform: quarter entirely out of range
-                epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q);
+                epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
             }
             if (ln_src && r0 < p.M) {
                 // row moments of this warp's columns of the tile: the four lanes that share a row (cg = lane & 3) add up
@@ -466,15 +478,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------- host side
-template <int MODE, int TN>
+template <int MODE, int TN, int RB = 128>
 static int launch_t(const GemmParams& p, cudaStream_t stream) {
-    using Cfg = TcCfg<MODE, TN>;
+    using Cfg = TcCfg<MODE, TN, RB>;
     constexpr int TBN = TN;
-    constexpr int kBTileBytes = Cfg::kBTileBytes;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo;
     int rc;
     auto make = [&](CUtensorMap* m, const float* base, int64_t rows, int64_t ld, int64_t bstride, int box_rows, int64_t batch) {
-        return MODE >= 16 ? make_tmap_kmajor16(m, base, rows, p.K, ld, batch, bstride, box_rows)
+        return MODE >= 16 ? make_tmap_kmajor16(m, base, rows, p.K, ld, batch, bstride, box_rows, RB)
                           : make_tmap_kmajor(m, base, rows, p.K, ld, batch, bstride, box_rows);
     };
     const int64_t b_batch = p.b_shared ? 1 : p.batch;
@@ -508,7 +519,7 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
         }
         pv.vec8 = ok ? 1 : 0;
         if ((p.ln_part || p.ln_stats) && !ok) { set_error("gemm_tc: the folded-LayerNorm epilogues need the vector path (N, pitches, alignment)"); return NSF_ERR_INVALID_ARG; }
-        if (p.ln_part && !(p.epi == EPI_RESID && p.ldo % 8 == 0 && al16(p.ln_hi) && al16(p.ln_lo) && p.ln_slots >= 2 * ceil_div(p.N, TBN))) {
+        if (p.ln_part && !(p.epi == EPI_RESID && p.ldo % 8 == 0 && (!p.ln_hi || (al16(p.ln_hi) && al16(p.ln_lo))) && p.ln_slots >= 2 * ceil_div(p.N, TBN))) {
             set_error("gemm_tc: LayerNorm source outputs need EPI_RESID, ldo %% 8 == 0, aligned planes and 2 slots per column tile");
             return NSF_ERR_INVALID_ARG;
         }
@@ -517,12 +528,12 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
             return NSF_ERR_INVALID_ARG;
         }
     }
-    NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int tiles_m = ceil_div(p.M, TBM), tiles_n = ceil_div(p.N, TBN);
     const int64_t total = (int64_t)tiles_m * tiles_n * p.batch;
     if (total > 0x7fffffff) { set_error("gemm_tc: too many tiles"); return NSF_ERR_INVALID_ARG; }
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm_tc_kernel<MODE, TN><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total);
+    gemm_tc_kernel<MODE, TN, RB><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total);
     return check_launch("gemm_tc_kernel");
 }
 
@@ -531,7 +542,12 @@ int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream) {
     if (mode == 16) {
         if (p.op_fmt != SPLIT_BF16 && p.op_fmt != SPLIT_F16) { set_error("gemm_tc: 16-bit engine needs SPLIT_BF16 / SPLIT_F16 operands"); return NSF_ERR_INVALID_ARG; }
         if (p.K % 8 != 0) { set_error("gemm_tc: K=%d must be a multiple of 8", p.K); return NSF_ERR_INVALID_ARG; }
-        return launch_t<16, 256>(p, stream);
+        // NSF_GEMM_RB=64 selects four 48 KB stages of 64-byte rows (SWIZZLE_64B) instead of two 96 KB stages of 128-byte rows.
+        // Measured (profiles/r02_bench_m*.json): parity identical, GEMM time 72.3 vs 70.1 ms per step -- the step runs against the
+        // 1 kW power cap (SM clock ~1.6 GHz), where the extra barrier / descriptor / commit work per byte costs more than the finer
+        // prefetch grain hides; kept as a measurement switch.
+        static const bool rb64 = [] { const char* e = getenv("NSF_GEMM_RB"); return e && atoi(e) == 64; }();
+        return rb64 ? launch_t<16, 256, 64>(p, stream) : launch_t<16, 256, 128>(p, stream);
     }
     if (mode == 116) {
         if (p.op_fmt != SPLIT_BF16_1) { set_error("gemm_tc: the bf16 engine needs SPLIT_BF16_1 operands"); return NSF_ERR_INVALID_ARG; }

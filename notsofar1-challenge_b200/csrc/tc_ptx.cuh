@@ -103,6 +103,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// the same for RB-byte rows: SWIZZLE_128B (RB = 128) or SWIZZLE_64B (RB = 64: 8-row groups 512 B apart, layout type 4)
+template <int RB>
+__device__ __forceinline__ uint64_t make_smem_desc_rb(uint32_t saddr) {
+    static_assert(RB == 128 || RB == 64, "swizzle span");
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)((8 * RB) >> 4) << 32) | (1ull << 46) | ((RB == 128 ? 2ull : 4ull) << 61);
+}
+
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128
 __host__ __device__ __forceinline__ constexpr uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -192,21 +199,21 @@ inline int make_tmap_kmajor(CUtensorMap* map, const float* base, int64_t rows, i
 // [batch][rows][K] 16-bit elements (fp16 / bf16 bit patterns), K contiguous; box = 64 x box_rows x 1 (128-byte rows),
 // 128-byte swizzle, zero fill out of bounds (a K tail shorter than 64 reads as zeros)
 inline int make_tmap_kmajor16(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int64_t batch,
-                              int64_t batch_stride, int box_rows) {
+                              int64_t batch_stride, int box_rows, int row_bytes = 128) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("tcgen05: cuTensorMapEncodeTiled is not available from the driver"); return NSF_ERR_CUDA; }
     if (batch_stride == 0) batch_stride = rows * ld;
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
     cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)batch_stride * 2};
-    cuuint32_t box[3] = {64u, (cuuint32_t)box_rows, 1};
+    cuuint32_t box[3] = {(cuuint32_t)(row_bytes / 2), (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15)) {
         set_error("tcgen05: 16-bit operand base/strides must be 16-byte aligned (ld=%lld, batch_stride=%lld)", (long long)ld, (long long)batch_stride);
         return NSF_ERR_INVALID_ARG;
     }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("tcgen05: cuTensorMapEncodeTiled (16-bit) failed with CUresult %d", (int)r); return NSF_ERR_CUDA; }
     return NSF_OK;
 }
