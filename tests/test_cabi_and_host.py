@@ -158,6 +158,54 @@ def test_pack_weights_layout(N, small_weights):
     assert np.array_equal(blob, blob2) and np.array_equal(offsets, off2)
 
 
+def test_pack_weights_folded_layernorms(N, small_weights, monkeypatch):
+    """2xBF16 engine, d_model = 128: the attention and feed_forward_out LayerNorms are folded into the GEMM that follows.
+    LN(x) W^T + b == rstd (x (gamma W)^T - mean colsum) + (b + W beta) with the weights / sums / biases exactly as packed."""
+    import torch
+    import ctypes as C
+    lib = N._cabi.load()
+    dims, blob, offsets, _ = N.pack_weights(small_weights, T=186, gemm_engine=N.GEMM_TC_2XBF16)
+    assert lib.nsf_conformer_ln_fold(C.byref(dims)) == 1 and len(offsets) == 12 + 34 * 2
+    d3 = N._cabi.ConformerDims(dims.d_model, dims.n_heads, dims.d_ff, dims.n_blocks, dims.kernel_size, dims.in_features, dims.n_out,
+                               dims.maxlen, dims.T, N.GEMM_TC_3XTF32)
+    assert lib.nsf_conformer_ln_fold(C.byref(d3)) == 0                      # other engines keep the LayerNorm kernels
+    d = 128
+
+    def bf16_pairs(off, rows, cols, src=None):
+        raw = (blob if src is None else src)[off:off + rows * cols // 2].view(np.int16).copy()
+        return torch.from_numpy(raw).view(torch.bfloat16).to(torch.float64).numpy().reshape(rows, cols)
+
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal((7, d)) * 1.7 + 0.6).astype(np.float64)            # rows with a mean
+    mu, var = x.mean(1, keepdims=True), x.var(1, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + 1e-5)
+    P = "executor.nnet.conformer.encoders.1."
+    base = 12 + 34
+    for name, o_w, o_b, o_cs, n_out, W, b, g, beta in (
+            ("qkv", 10, 12, 32, 3 * d,
+             np.concatenate([small_weights[P + f"self_attn.linear_{c}.weight"] for c in "qkv"], 0),
+             np.concatenate([small_weights[P + f"self_attn.linear_{c}.bias"] for c in "qkv"]),
+             small_weights[P + "self_attn.layer_norm.weight"], small_weights[P + "self_attn.layer_norm.bias"]),
+            ("ffo", 24, 26, 33, 256,
+             small_weights[P + "feed_forward_out.net.0.weight"], small_weights[P + "feed_forward_out.net.0.bias"],
+             small_weights[P + "feed_forward_out.layer_norm.weight"], small_weights[P + "feed_forward_out.layer_norm.bias"])):
+        Wst = bf16_pairs(offsets[base + o_w], n_out, d) + bf16_pairs(offsets[base + o_w + 1], n_out, d)
+        bias = blob[offsets[base + o_b]:offsets[base + o_b] + n_out].astype(np.float64)
+        cs = blob[offsets[base + o_cs]:offsets[base + o_cs] + n_out].astype(np.float64)
+        ref = ((x - mu) * rstd * g.astype(np.float64) + beta.astype(np.float64)) @ W.astype(np.float64).T + b
+        got = rstd * (x @ Wst.T - mu * cs[None, :]) + bias[None, :]
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert err < 2e-5, (name, err)                                         # bf16 head + remainder: 2^-17 per weight
+    # NSF_LN_FOLD=0: the plain layout (no scaling, zero column sums)
+    monkeypatch.setenv("NSF_LN_FOLD", "0")
+    dims0, blob0, offsets0, _ = N.pack_weights(small_weights, T=186, gemm_engine=N.GEMM_TC_2XBF16)
+    assert lib.nsf_conformer_ln_fold(C.byref(dims0)) == 0
+    assert np.all(blob0[offsets0[base + 32]:offsets0[base + 32] + 3 * d] == 0)
+    W0 = bf16_pairs(offsets0[base + 10], 3 * d, d, blob0) + bf16_pairs(offsets0[base + 11], 3 * d, d, blob0)
+    Wq = np.concatenate([small_weights[P + f"self_attn.linear_{c}.weight"] for c in "qkv"], 0)
+    assert np.abs(W0 - Wq).max() <= np.abs(Wq).max() * 2.0 ** -15
+
+
 def test_product_does_not_import_oracle():
     """The product path must not route through the oracle (or the reference)."""
     pkg = os.path.join(ROOT, "notsofar1-challenge_b200")

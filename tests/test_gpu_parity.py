@@ -302,6 +302,25 @@ def test_masks_production_net_vs_oracle(nb, dev, engine_name):
     assert rel_l2(m2, ref) < TOL
 
 
+def test_folded_layernorms_match_the_layernorm_kernels(nb, dev, monkeypatch):
+    """The default 2xBF16 path folds two LayerNorms per block into the GEMMs around them (nsf_conformer_ln_fold);
+    NSF_LN_FOLD=0 runs the separate LayerNorm kernels.  Both must agree with the oracle, and with each other to rounding."""
+    w = O.random_weights(seed=2, gain=0.5)
+    rng = np.random.default_rng(9)
+    x = (rng.standard_normal((48128 + 93 * 256, 7)) * 0.05).astype(np.float32)
+    out = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("NSF_LN_FOLD", fold)
+        sep = _sep(nb, w, dev, engine=nb.GEMM_TC_2XBF16)
+        X = sep.stft_device(torch.from_numpy(x).to(dev))
+        out[fold] = sep.masks(X, X.shape[1], 0, 2, 186, 93).cpu().numpy()
+        raw, _ = sep.features(X, X.shape[1], 0, 2, 186, 93)
+    ref = O.conformer_masks(w, raw.cpu().numpy()[:, :1799].reshape(2, 186, 1799))
+    e1, e0, e10 = rel_l2(out["1"], ref), rel_l2(out["0"], ref), rel_l2(out["1"], out["0"])
+    print(f"folded LayerNorms: masks vs oracle {e1:.3e} (folded) / {e0:.3e} (kernels), folded vs kernels {e10:.3e}")
+    assert e1 < TOL and e0 < TOL and e10 < 3e-5 and not np.array_equal(out["1"], out["0"])
+
+
 def test_separate_protocol(nb, dev, golden, small_weights):
     """separator.separate keeps the reference's dict / [B, F, T, spk] layout (conformer_wrapper.py:79-104)."""
     sep = _sep(nb, small_weights, dev)
