@@ -59,15 +59,16 @@ struct RowWalker {      // (segment, frame) of consecutive rows m = seg * T + t 
     __device__ __forceinline__ void next() { if (++t == T) { t = 0; ++seg; } }
 };
 
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk_t(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
                                                float* stage, int lane, float (&ln_s)[4], float (&ln_q)[4],
                                                const size_t (&qkv_row)[4]) {
-    const bool lane_is_row = p.epi == EPI_MASK || (p.epi == EPI_QKV && nc >= 2 * p.d_model && !p.v_rowmajor);
+    const bool lane_is_row = EPI == EPI_MASK || (EPI == EPI_QKV && nc >= 2 * p.d_model && !p.v_rowmajor);
     if (lane_is_row) {
         const int m = r0 + lane;
         if (m >= p.M) return;
         const int seg = m / p.T, t = m - seg * p.T;
-        if (p.epi == EPI_MASK) {
+        if (EPI == EPI_MASK) {
             const int n_masks = p.n_valid / kBins;
             int k = nc / kBins, f = nc - k * kBins;
             float* base = p.out0 + (size_t)seg * n_masks * kBins * p.T + t;
@@ -115,7 +116,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             // folded LayerNorm of the operand rows: per-row (mean, rstd), per-column sums of the scaled weights
             float cs[8];
             float2 lst[4];
-            if (p.ln_stats) {
+            if ((EPI == EPI_QKV || EPI == EPI_RELU_SPLIT) && p.ln_stats) {
                 const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.ln_csum + n0)), c1 = __ldg(reinterpret_cast<const float4*>(p.ln_csum + n0 + 4));
                 cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
 #pragma unroll
@@ -126,13 +127,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
             }
             const int g0 = (2 * cg) ^ rq, g1 = (2 * cg + 1) ^ rq;
             // EPI_QKV geometry (a 32-column chunk stays inside q or k and inside one head)
-            const int which = p.epi == EPI_QKV ? nc / p.d_model : 0;
+            // (no integer divisions per chunk: q / k / v by comparison, head index by shift for the usual d_k = 64)
+            const int which = EPI == EPI_QKV ? (nc >= 2 * p.d_model ? 2 : (nc >= p.d_model ? 1 : 0)) : 0;
             const int cq = n0 - which * p.d_model;
-            const int hq = p.epi == EPI_QKV ? cq / p.d_k : 0, dq = cq - hq * p.d_k;
+            const int hq = EPI == EPI_QKV ? (p.d_k == 64 ? cq >> 6 : cq / p.d_k) : 0, dq = cq - hq * p.d_k;
             // in-place residual stream: the four rows' old values are all in flight before the first store (a store to
             // x would otherwise fence the next row's loads and expose one HBM round trip per row)
             float4 xo[4][2];
-            if (p.epi == EPI_RESID) {
+            if (EPI == EPI_RESID) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int m = r0 + rq + 8 * k;
@@ -149,14 +151,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
                 const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * 32 + 4 * g0);
                 const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * 32 + 4 * g1);
                 float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                if (p.ln_stats) {
+                if ((EPI == EPI_QKV || EPI == EPI_RELU_SPLIT) && p.ln_stats) {
+                    const float ar = p.acc_scale * lst[k].y, nmr = -lst[k].x * lst[k].y;       // rstd (acc - mean csum) + bias
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = (v[e] * p.acc_scale - lst[k].x * cs[e]) * lst[k].y + bs[e];
+                    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], ar, fmaf(nmr, cs[e], bs[e]));
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = v[e] * p.acc_scale + bs[e];
+                    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], p.acc_scale, bs[e]);
                 }
-                switch (p.epi) {
+                switch (EPI) {
                     case EPI_STORE: {
                         float* o = p.out0 + (size_t)b * p.o_batch_stride + (size_t)m * p.ldo + n0;
                         *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
@@ -229,7 +232,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
         float v[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = stage[i * kEpiPitch + lane] * p.acc_scale + bs;
-        switch (p.epi) {
+        switch (EPI) {
             case EPI_STORE: {
                 float* o = p.out0 + (size_t)b * p.o_batch_stride + (size_t)r0 * p.ldo + n;
 #pragma unroll
@@ -295,6 +298,23 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
         }
     }
     __syncwarp();
+}
+
+// p.epi is uniform: one dispatch per chunk, everything inside is resolved at compile time
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
+                                               float* stage, int lane, float (&ln_s)[4], float (&ln_q)[4],
+                                               const size_t (&qkv_row)[4]) {
+    switch (p.epi) {
+        case EPI_STORE:      epilogue_chunk_t<EPI_STORE>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_RELU_SPLIT: epilogue_chunk_t<EPI_RELU_SPLIT>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_RESID:      epilogue_chunk_t<EPI_RESID>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_QKV:        epilogue_chunk_t<EPI_QKV>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_PV:         epilogue_chunk_t<EPI_PV>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_MASK:       epilogue_chunk_t<EPI_MASK>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_GELU_SPLIT: epilogue_chunk_t<EPI_GELU_SPLIT>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_GELU_POS:   epilogue_chunk_t<EPI_GELU_POS>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        default: break;
+    }
 }
 
 template <int MODE, int TN, int RB>
