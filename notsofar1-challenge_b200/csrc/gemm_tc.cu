@@ -317,7 +317,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
     }
 }
 
-template <int MODE, int TN, int RB>
+// EPI >= 0: the epilogue kind is a compile-time constant of the instantiation (the hot GEMMs of the mask network: smaller
+// code -- the generic kernel is 28 k SASS instructions, `no_inst` was 8-9 % of its stall samples -- and registers allocated
+// for one epilogue instead of the worst of eight); EPI < 0: p.epi is read at run time.
+template <int MODE, int TN, int RB, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
@@ -341,6 +344,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         reinterpret_cast<volatile uint32_t*>(gen_tiles + Cfg::kStages * Cfg::kStageBytes + kEpiBytes + 8 * (2 * Cfg::kStages + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int epi = EPI >= 0 ? EPI : p.epi;
     const int nkb = (p.K + Cfg::kBlockK - 1) / Cfg::kBlockK;      // a K tail is zero-filled by TMA
 
     if (threadIdx.x == 0) {
@@ -444,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int c_first = half * 32;
             mbar_wait(tmem_full_bar(acc), aph);
             tcgen05_fence_after();
-            const bool ln_src = p.epi == EPI_RESID && p.ln_part != nullptr;
+            const bool ln_src = epi == EPI_RESID && p.ln_part != nullptr;
             if (c_first >= n_end) {                         // nothing to read for this warp
                 tcgen05_fence_before();
                 __syncwarp();
@@ -455,7 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             float ln_s[4] = {0.f, 0.f, 0.f, 0.f}, ln_q[4] = {0.f, 0.f, 0.f, 0.f};
             // per-tile row work of the vector epilogues (a lane owns rows r0 + (lane >> 2) + 8 k of every chunk)
             size_t qkv_row[4] = {0, 0, 0, 0};
-            if (p.epi == EPI_QKV) {
+            if (epi == EPI_QKV) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int m = min(r0 + (lane >> 2) + 8 * k, p.M - 1);
@@ -474,7 +478,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
                 }
                 if (r0 >= p.M) continue;                    // warp-uniform: quarter entirely out of range
-                epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
+                if constexpr (EPI >= 0) epilogue_chunk_t<EPI>(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
+                else epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
             }
             if (ln_src && r0 < p.M) {
                 // row moments of this warp's columns of the tile: the four lanes that share a row (cg = lane & 3) add up
@@ -548,12 +553,29 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
             return NSF_ERR_INVALID_ARG;
         }
     }
-    NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN, RB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+
     const int tiles_m = ceil_div(p.M, TBM), tiles_n = ceil_div(p.N, TBN);
     const int64_t total = (int64_t)tiles_m * tiles_n * p.batch;
     if (total > 0x7fffffff) { set_error("gemm_tc: too many tiles"); return NSF_ERR_INVALID_ARG; }
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm_tc_kernel<MODE, TN, RB><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total);
+#define NSF_GEMM_LAUNCH(E)                                                                                                      \
+    do {                                                                                                                        \
+        NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN, RB, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes)); \
+        gemm_tc_kernel<MODE, TN, RB, E><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total); \
+    } while (0)
+    if (MODE == 16 && TN == 256 && RB == 128 && pv.vec8) {
+        // the mask network's GEMMs: one instantiation per epilogue kind
+        switch (p.epi) {
+            case EPI_RELU_SPLIT: NSF_GEMM_LAUNCH(EPI_RELU_SPLIT); break;
+            case EPI_RESID:      NSF_GEMM_LAUNCH(EPI_RESID); break;
+            case EPI_QKV:        NSF_GEMM_LAUNCH(EPI_QKV); break;
+            case EPI_STORE:      NSF_GEMM_LAUNCH(EPI_STORE); break;
+            default:             NSF_GEMM_LAUNCH(-1); break;
+        }
+    } else {
+        NSF_GEMM_LAUNCH(-1);
+    }
+#undef NSF_GEMM_LAUNCH
     return check_launch("gemm_tc_kernel");
 }
 
