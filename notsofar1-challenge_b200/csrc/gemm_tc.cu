@@ -502,7 +502,186 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
 }
 
+// ------------------------------------------------------------------------------------------- CTA pairs (cta_group::2)
+// The 2xBF16 GEMMs of the mask network on pairs of CTAs (clusters of two, one per SM): a pair owns a 256 x 256 tile, each CTA
+// its 128 rows; `tcgen05.mma.cta_group::2` (M = 256) is issued by the leader and reads A from each CTA's own shared memory and
+// the two 128-column halves of B from both -- every CTA stages only HALF of B.  Per K block of 64 a CTA moves 64 KB (A hi/lo 32,
+// half B hi/lo 32) instead of 96 KB from L2 for the same MMAs, and three stages fit where two did: the single-CTA kernel's main
+// loop is bound by that traffic / its latency (58-80 % tensor-active whatever the epilogue does,
+// profiles/r02_ncu_full_gemm16_block_per_epilogue_kernels_summary.csv).
+//   full[s]       leader's barrier: the leader's producer arms it with the bytes of BOTH CTAs, both producers' TMA loads credit it
+//   empty[s]      per CTA: the leader's commit is multicast to both
+//   tmem_full[a]  per CTA (multicast commit); tmem_empty[a]: leader's barrier, 8 epilogue warps of each CTA arrive on it
+constexpr int k2Stages = 3;
+constexpr int k2ATile = TBM * 128;                  // 16 KB: 128 rows x 64 bf16
+constexpr int k2BHalf = 128 * 128;                  // 16 KB: 128 of the tile's 256 columns x 64 bf16
+constexpr int k2StageBytes = 2 * (k2ATile + k2BHalf);
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + kEpiBytes + 256 + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+                const GemmParams p, const int tiles_m, const int tiles_n, const int total_pairs) {
+    constexpr int TBN = 256;
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t tiles = (raw + 1023u) & ~1023u;
+    unsigned char* gen_tiles = smem_raw + (tiles - raw);
+    float* epi_stage = reinterpret_cast<float*>(gen_tiles + k2Stages * k2StageBytes);
+    const uint32_t bars = tiles + k2Stages * k2StageBytes + kEpiBytes;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (k2Stages + s); };
+    auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * k2Stages + a); };
+    auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * k2Stages + 2 + a); };
+    const uint32_t tmem_ptr_addr = bars + 8u * (2 * k2Stages + 4);
+    volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(gen_tiles + k2Stages * k2StageBytes + kEpiBytes + 8 * (2 * k2Stages + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int nkb = (p.K + 63) / 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < k2Stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tmem_full_bar(a), 1); mbar_init(tmem_empty_bar(a), 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // the peer's barriers exist before anything is signalled across
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_gen;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer (both CTAs): own A rows, own half of B
+            uint32_t it = 0;
+            for (int item = pair; item < total_pairs; item += n_pairs) {
+                const int n_blk = item % tiles_n, mp = item / tiles_n;
+                const int m0 = (2 * mp + (int)rank) * TBM, n0 = n_blk * TBN + (int)rank * 128;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % k2Stages;
+                    const uint32_t ph = (it / k2Stages) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(full_bar(s), 2u * k2StageBytes);
+                    const uint32_t st = tiles + s * k2StageBytes;
+                    const int k0 = kb * 64;
+                    tma_load_3d_2sm(st, &map_a_hi, k0, m0, 0, full_bar(s));
+                    tma_load_3d_2sm(st + k2ATile, &map_a_lo, k0, m0, 0, full_bar(s));
+                    tma_load_3d_2sm(st + 2 * k2ATile, &map_b_hi, k0, n0, 0, full_bar(s));
+                    tma_load_3d_2sm(st + 2 * k2ATile + k2BHalf, &map_b_lo, k0, n0, 0, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ===== MMA issuer (leader only)
+            const uint32_t idesc = make_idesc_f16_2sm(TBN, p.op_fmt != SPLIT_F16);
+            uint32_t it = 0, tl = 0;
+            for (int item = pair; item < total_pairs; item += n_pairs, ++tl) {
+                const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+                mbar_wait(tmem_empty_bar(acc), aph ^ 1);       // both CTAs' epilogues have drained this accumulator
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * TBN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % k2Stages;
+                    const uint32_t ph = (it / k2Stages) & 1;
+                    mbar_wait(full_bar(s), ph);
+                    tcgen05_fence_after();
+                    const uint32_t st = tiles + s * k2StageBytes;
+                    const uint32_t a_hi = st, a_lo = st + k2ATile, b_hi = st + 2 * k2ATile, b_lo = b_hi + k2BHalf;
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t koff = ks * 32;
+                        const uint64_t da_hi = make_smem_desc(a_hi + koff), db_hi = make_smem_desc(b_hi + koff);
+                        const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
+                        tcgen05_mma_f16_2sm(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);     // small terms first
+                        tcgen05_mma_f16_2sm(d_tmem, da_hi, db_lo, idesc, 1);
+                        tcgen05_mma_f16_2sm(d_tmem, da_hi, db_hi, idesc, 1);
+                    }
+                    tcgen05_commit_2sm(empty_bar(s));
+                }
+                tcgen05_commit_2sm(tmem_full_bar(acc));
+            }
+        }
+    } else {
+        // ===== epilogue warps (both CTAs): as in gemm_tc_kernel, on this CTA's 128 rows of the pair's tile
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float* stage = epi_stage + (warp - 2) * 32 * kEpiPitch;
+        uint32_t tl = 0;
+        for (int item = pair; item < total_pairs; item += n_pairs, ++tl) {
+            const int n_blk = item % tiles_n, mp = item / tiles_n;
+            const int n0 = n_blk * TBN;
+            const int r0 = (2 * mp + (int)rank) * TBM + q * 32;
+            const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
+            const int n_end = min(p.N - n0, TBN);
+            const int c_first = half * 32;
+            mbar_wait(tmem_full_bar(acc), aph);
+            tcgen05_fence_after();
+            const bool ln_src = EPI == EPI_RESID && p.ln_part != nullptr;
+            if (c_first >= n_end) {
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
+                if (ln_src && r0 + lane < p.M) p.ln_part[(size_t)(r0 + lane) * p.ln_slots + 2 * n_blk + half] = make_float2(0.f, 0.f);
+                continue;
+            }
+            float ln_s[4] = {0.f, 0.f, 0.f, 0.f}, ln_q[4] = {0.f, 0.f, 0.f, 0.f};
+            size_t qkv_row[4] = {0, 0, 0, 0};
+            if (EPI == EPI_QKV) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int m = min(r0 + (lane >> 2) + 8 * k, p.M - 1);
+                    const int seg = m / p.T, t = m - seg * p.T;
+                    qkv_row[k] = ((size_t)seg * p.n_heads * p.T + t) * p.d_k;
+                }
+            }
+#pragma unroll 1
+            for (int c0 = c_first; c0 < n_end; c0 += 64) {
+                uint32_t r[32];
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + (uint32_t)c0, r);
+                if (c0 + 64 >= n_end) {
+                    tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
+                }
+                if (r0 >= p.M) continue;
+                epilogue_chunk_t<EPI>(p, 0, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
+            }
+            if (ln_src && r0 < p.M) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float s = ln_s[k], q2 = ln_q[k];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);  q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);  q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
+                    const int m = r0 + (lane >> 2) + 8 * k;
+                    if ((lane & 3) == 0 && m < p.M) p.ln_part[(size_t)m * p.ln_slots + 2 * n_blk + half] = make_float2(s, q2);
+                }
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                  // neither CTA leaves (or frees tensor memory) while the pair's MMAs / arrivals are in flight
+    tcgen05_fence_after();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host side
+// NSF_GEMM_2SM=0 keeps the single-CTA kernels (A/B measurements)
+static bool use_cta_pairs() {
+    static const bool on = [] { const char* e = getenv("NSF_GEMM_2SM"); return !(e && e[0] == '0'); }();
+    return on;
+}
+
 template <int MODE, int TN, int RB = 128>
 static int launch_t(const GemmParams& p, cudaStream_t stream) {
     using Cfg = TcCfg<MODE, TN, RB>;
@@ -563,6 +742,29 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
         NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN, RB, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes)); \
         gemm_tc_kernel<MODE, TN, RB, E><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total); \
     } while (0)
+    if (MODE == 16 && TN == 256 && RB == 128 && pv.vec8 && p.batch == 1 && sm_count() >= 2 && use_cta_pairs() &&
+        (p.epi == EPI_RELU_SPLIT || p.epi == EPI_RESID || p.epi == EPI_QKV || p.epi == EPI_STORE)) {
+        // CTA pairs: B is staged in halves of 128 columns
+        CUtensorMap mb2_hi, mb2_lo;
+        if ((rc = make_tmap_kmajor16(&mb2_hi, p.B_hi, p.N, p.K, p.ldb, 1, 0, 128))) return rc;
+        if ((rc = make_tmap_kmajor16(&mb2_lo, p.B_lo, p.N, p.K, p.ldb, 1, 0, 128))) return rc;
+        const int pairs_m = (tiles_m + 1) / 2;
+        const int64_t total_pairs = (int64_t)pairs_m * tiles_n;
+        int grid2 = (int)(2 * total_pairs < sm_count() ? 2 * total_pairs : (sm_count() & ~1));
+#define NSF_GEMM2_LAUNCH(E)                                                                                                     \
+        do {                                                                                                                    \
+            NSF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));         \
+            gemm_tc2_kernel<E><<<grid2, kTcThreads, k2SmemBytes, stream>>>(ma_hi, ma_lo, mb2_hi, mb2_lo, pv, tiles_m, tiles_n, (int)total_pairs); \
+        } while (0)
+        switch (p.epi) {
+            case EPI_RELU_SPLIT: NSF_GEMM2_LAUNCH(EPI_RELU_SPLIT); break;
+            case EPI_RESID:      NSF_GEMM2_LAUNCH(EPI_RESID); break;
+            case EPI_QKV:        NSF_GEMM2_LAUNCH(EPI_QKV); break;
+            default:             NSF_GEMM2_LAUNCH(EPI_STORE); break;
+        }
+#undef NSF_GEMM2_LAUNCH
+        return check_launch("gemm_tc2_kernel");
+    }
     if (MODE == 16 && TN == 256 && RB == 128 && pv.vec8) {
         // the mask network's GEMMs: one instantiation per epilogue kind
         switch (p.epi) {
