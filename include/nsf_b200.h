@@ -95,7 +95,7 @@ int nsf_stft_mc(const float* x, int64_t n_samples, int n_ch,
  * value is stored split for the tensor-core GEMM in format split_fmt: NSF_SPLIT_TF32 -> two fp32 arrays (TF32 head,
  * exact remainder); NSF_SPLIT_BF16 / NSF_SPLIT_F16 -> feat and feat_lo are uint16 arrays of pitch ldf holding bf16 /
  * (x 2^4-scaled) fp16 head and remainder, for the NSF_GEMM_TC_2XBF16 / _2XF16 engines.
- * Columns >= 257*n_ch of a row are left untouched (the caller keeps the K padding zeroed). */
+ * Columns [257*n_ch, ldf) of every row (the K padding of the first GEMM) are written as zeros. */
 #define NSF_SPLIT_TF32 0
 #define NSF_SPLIT_BF16 1
 #define NSF_SPLIT_F16  2

@@ -143,6 +143,22 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
         }
     }
     __syncthreads();
+    // the K padding columns [C * 257, ldf) of the segment's rows are zero-filled by the CTA of the last (one-bin) group
+    if (blockIdx.x == gridDim.x - 1) {
+        const int pad0 = C * kBins, npad = (int)ldf - pad0;
+        const bool wide = !(feat_lo && (fmt == SPLIT_BF16 || fmt == SPLIT_F16));       // fp32 planes, else 16-bit planes
+        for (int idx = threadIdx.x; idx < T * npad; idx += blockDim.x) {
+            const int t = idx / npad, c = pad0 + idx - t * npad;
+            const size_t o = ((size_t)seg * T + t) * ldf + c;
+            if (wide) {
+                feat[o] = 0.f;
+                if (feat_lo) feat_lo[o] = 0.f;
+            } else {
+                reinterpret_cast<uint16_t*>(feat)[o] = 0;
+                reinterpret_cast<uint16_t*>(feat_lo)[o] = 0;
+            }
+        }
+    }
     // write-out: row (seg*T + t), column m*257 + f, runs of up to 8 consecutive bins
     const int nb = min(kFeatBinsPerCta, kBins - f0bin);
     if ((fmt == SPLIT_BF16 || fmt == SPLIT_F16) && feat_lo) {

@@ -622,6 +622,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
             const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
             const int n_end = min(p.N - n0, TBN);
             const int c_first = half * 32;
+            if (EPI == EPI_RESID && r0 < p.M) {
+                // in-place residual: ask L2 for the old values of this warp's chunks while the pair's MMAs for the tile still run
+                // (the loads in the chunk loop then see L2 latency; with the main loop at 97 % tensor-active the K = 512
+                // out-projection was left at 75 % by this round trip)
+                for (int c0 = c_first; c0 < n_end; c0 += 64) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int m = r0 + (lane >> 2) + 8 * k;
+                        if (m < p.M && n0 + c0 + 8 * (lane & 3) < p.N)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.out0 + (size_t)m * p.ldo + n0 + c0 + 8 * (lane & 3)));
+                    }
+                }
+            }
             mbar_wait(tmem_full_bar(acc), aph);
             tcgen05_fence_after();
             const bool ln_src = EPI == EPI_RESID && p.ln_part != nullptr;

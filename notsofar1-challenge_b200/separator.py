@@ -340,9 +340,9 @@ class ConformerCssB200:
         assert F_ == NUM_BINS and X.dtype == torch.complex64 and X.is_contiguous()
         rows = n_seg * T
         fmt = _cabi.split_fmt_of_engine(self.gemm_engine) if split else _cabi.SPLIT_TF32
-        # 16-bit split formats: bf16 / scaled-fp16 bit patterns (the K padding columns stay zero)
-        feat = torch.zeros((rows, self.ldf), dtype=torch.float32 if fmt == _cabi.SPLIT_TF32 else torch.int16, device=X.device)
-        feat_lo = torch.zeros_like(feat) if split else None
+        # 16-bit split formats: bf16 / scaled-fp16 bit patterns (the kernel zero-fills the K padding columns)
+        feat = torch.empty((rows, self.ldf), dtype=torch.float32 if fmt == _cabi.SPLIT_TF32 else torch.int16, device=X.device)
+        feat_lo = torch.empty_like(feat) if split else None
         _cabi.check(self._lib.nsf_css_features(
             _cabi.ptr(X), T_long, T_valid, c, seg_first, n_seg, T, hop,
             _cabi.ptr(self._in_bias) if normalize_input else None, _cabi.ptr(self._in_scale) if normalize_input else None,
