@@ -16,6 +16,7 @@
 #include "gemm_common.cuh"
 #include "tc_ptx.cuh"
 #include <math.h>
+#include <cstdlib>
 
 namespace nsf {
 
@@ -95,6 +96,11 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     const int nBh = (((rows_valid + T - 1) + 31) / 32) * 16;        // half of the pe_k window columns (multiple of 16)
     const int nPe = (2 * nBh + 63) / 64;                            // 64-row boxes of the window
     const int nks_pv = (T + 15) / 16;                               // 16-key k-steps of P V
+    // output accumulator O (64 columns): behind the pe_k window where the window leaves room (row block 1: 256 columns), else on
+    // top of the window's second half (row block 0: the window fills the rest of tensor memory) -- only then does the next item's
+    // second half of Bm have to wait until O has been read out
+    const bool o_aliases = kA2ColB + 2 * nBh + 64 > 512;
+    const uint32_t col_o = o_aliases ? (uint32_t)kA2ColO : (uint32_t)(kA2ColB + 2 * nBh);
 
     if (threadIdx.x == 0) {
         mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(pe_full, 1);
@@ -186,14 +192,14 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                     const uint32_t vo = (uint32_t)j * 2048u;                         // 16 key rows of 128 bytes
                     const uint64_t bv_hi = make_smem_desc(v_smem + vo), bv_lo = make_smem_desc(v_smem + kA2VHalf + vo);
                     const uint32_t a_col = tmem_base + 8u * j;                       // 16 keys = 8 packed columns
-                    tcgen05_mma_f16_ts(tmem_base + kA2ColO, a_col + kA2ColPlo, bv_hi, idesc_o, j != 0);
-                    tcgen05_mma_f16_ts(tmem_base + kA2ColO, a_col, bv_lo, idesc_o, 1);
-                    tcgen05_mma_f16_ts(tmem_base + kA2ColO, a_col, bv_hi, idesc_o, 1);
+                    tcgen05_mma_f16_ts(tmem_base + col_o, a_col + kA2ColPlo, bv_hi, idesc_o, j != 0);
+                    tcgen05_mma_f16_ts(tmem_base + col_o, a_col, bv_lo, idesc_o, 1);
+                    tcgen05_mma_f16_ts(tmem_base + col_o, a_col, bv_hi, idesc_o, 1);
                 }
                 tcgen05_commit(v_empty);
                 tcgen05_commit(o_ready);
                 // the next item's scores overwrite P only after the P V product above (tensor-pipe order)
-                if (bh + stride < p.n_bh) issue_scores_and_bm(it + 1, true, it & 1);
+                if (bh + stride < p.n_bh) issue_scores_and_bm(it + 1, o_aliases, it & 1);
             }
         }
     } else {
@@ -293,7 +299,7 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             tcgen05_fence_after();
             if (warp_valid && hh < 2) {
                 uint32_t ov[32];
-                tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)(kA2ColO + 32 * hh), ov);
+                tmem_ld_32x32(tmem_base + lane_sel + col_o + (uint32_t)(32 * hh), ov);
                 const int t1 = R0 + r;
                 if (t1 < T) {
                     const int seg = bh / p.n_heads, h = bh - seg * p.n_heads;
@@ -354,7 +360,8 @@ int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const
     } else {
         grid = 2 * n_bh < sm_count() ? 2 * n_bh : sm_count();
         // both row blocks cost a full 128-row MMA pass; block 1 has the narrower pe_k window and fewer live softmax rows
-        p.g0 = (int)lroundf(grid * 0.52f);
+        static const float g0_frac = [] { const char* e = getenv("NSF_ATTN_G0"); const float v = e ? (float)atof(e) : 0.f; return v > 0.f && v < 1.f ? v : 0.52f; }();
+        p.g0 = (int)lroundf(grid * g0_frac);
         if (p.g0 < 1) p.g0 = 1;
         if (p.g0 > grid - 1) p.g0 = grid - 1;
     }

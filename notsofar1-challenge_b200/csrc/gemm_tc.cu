@@ -512,18 +512,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 //   full[s]       leader's barrier: the leader's producer arms it with the bytes of BOTH CTAs, both producers' TMA loads credit it
 //   empty[s]      per CTA: the leader's commit is multicast to both
 //   tmem_full[a]  per CTA (multicast commit); tmem_empty[a]: leader's barrier, 8 epilogue warps of each CTA arrive on it
-constexpr int k2Stages = 3;
-constexpr int k2ATile = TBM * 128;                  // 16 KB: 128 rows x 64 bf16
-constexpr int k2BHalf = 128 * 128;                  // 16 KB: 128 of the tile's 256 columns x 64 bf16
-constexpr int k2StageBytes = 2 * (k2ATile + k2BHalf);
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + kEpiBytes + 256 + 1024;
+// SPLIT: head + remainder planes, three MMAs per product (2xBF16 / 2xF16: 64 KB stages, 3 of them); !SPLIT: plain bf16 operands,
+// one MMA (the Whisper encoder's GEMMs: 32 KB stages, 6 of them).
+constexpr int k2ATile = TBM * 128;                  // 16 KB: 128 rows x 64 16-bit elements
+constexpr int k2BHalf = 128 * 128;                  // 16 KB: 128 of the tile's 256 columns x 64 elements
+template <bool SPLIT> struct Tc2Cfg {
+    static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (k2ATile + k2BHalf);
+    static constexpr int kStages = SPLIT ? 3 : 6;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 1024;
+};
 
-template <int EPI>
+template <int EPI, bool SPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const GemmParams p, const int tiles_m, const int tiles_n, const int total_pairs) {
     constexpr int TBN = 256;
+    constexpr int k2Stages = Tc2Cfg<SPLIT>::kStages, k2StageBytes = Tc2Cfg<SPLIT>::kStageBytes;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;
@@ -572,16 +577,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     const uint32_t st = tiles + s * k2StageBytes;
                     const int k0 = kb * 64;
                     tma_load_3d_2sm(st, &map_a_hi, k0, m0, 0, full_bar(s));
-                    tma_load_3d_2sm(st + k2ATile, &map_a_lo, k0, m0, 0, full_bar(s));
-                    tma_load_3d_2sm(st + 2 * k2ATile, &map_b_hi, k0, n0, 0, full_bar(s));
-                    tma_load_3d_2sm(st + 2 * k2ATile + k2BHalf, &map_b_lo, k0, n0, 0, full_bar(s));
+                    if (SPLIT) {
+                        tma_load_3d_2sm(st + k2ATile, &map_a_lo, k0, m0, 0, full_bar(s));
+                        tma_load_3d_2sm(st + 2 * k2ATile, &map_b_hi, k0, n0, 0, full_bar(s));
+                        tma_load_3d_2sm(st + 2 * k2ATile + k2BHalf, &map_b_lo, k0, n0, 0, full_bar(s));
+                    } else {
+                        tma_load_3d_2sm(st + k2ATile, &map_b_hi, k0, n0, 0, full_bar(s));
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             // ===== MMA issuer (leader only)
-            const uint32_t idesc = make_idesc_f16_2sm(TBN, p.op_fmt != SPLIT_F16);
+            const uint32_t idesc = make_idesc_f16_2sm(TBN, p.op_fmt != SPLIT_F16);       // bf16 operands unless the scaled-fp16 pairs
             uint32_t it = 0, tl = 0;
             for (int item = pair; item < total_pairs; item += n_pairs, ++tl) {
                 const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
@@ -594,15 +603,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     mbar_wait(full_bar(s), ph);
                     tcgen05_fence_after();
                     const uint32_t st = tiles + s * k2StageBytes;
-                    const uint32_t a_hi = st, a_lo = st + k2ATile, b_hi = st + 2 * k2ATile, b_lo = b_hi + k2BHalf;
+                    const uint32_t a_hi = st, a_lo = st + k2ATile, b_hi = st + (SPLIT ? 2 : 1) * k2ATile, b_lo = b_hi + k2BHalf;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
                         const uint32_t koff = ks * 32;
                         const uint64_t da_hi = make_smem_desc(a_hi + koff), db_hi = make_smem_desc(b_hi + koff);
-                        const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
-                        tcgen05_mma_f16_2sm(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);     // small terms first
-                        tcgen05_mma_f16_2sm(d_tmem, da_hi, db_lo, idesc, 1);
-                        tcgen05_mma_f16_2sm(d_tmem, da_hi, db_hi, idesc, 1);
+                        if (SPLIT) {
+                            const uint64_t da_lo = make_smem_desc(a_lo + koff), db_lo = make_smem_desc(b_lo + koff);
+                            tcgen05_mma_f16_2sm(d_tmem, da_lo, db_hi, idesc, (kb | ks) != 0);     // small terms first
+                            tcgen05_mma_f16_2sm(d_tmem, da_hi, db_lo, idesc, 1);
+                            tcgen05_mma_f16_2sm(d_tmem, da_hi, db_hi, idesc, 1);
+                        } else {
+                            tcgen05_mma_f16_2sm(d_tmem, da_hi, db_hi, idesc, (kb | ks) != 0);
+                        }
                     }
                     tcgen05_commit_2sm(empty_bar(s));
                 }
@@ -755,28 +768,32 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
         NSF_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, TN, RB, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes)); \
         gemm_tc_kernel<MODE, TN, RB, E><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total); \
     } while (0)
-    if (MODE == 16 && TN == 256 && RB == 128 && pv.vec8 && p.batch == 1 && sm_count() >= 2 && use_cta_pairs() &&
-        (p.epi == EPI_RELU_SPLIT || p.epi == EPI_RESID || p.epi == EPI_QKV || p.epi == EPI_STORE)) {
+    if constexpr ((MODE == 16 || MODE == 116) && TN == 256 && RB == 128) {
+    if (pv.vec8 && p.batch == 1 && sm_count() >= 2 && use_cta_pairs() &&
+        (p.epi == EPI_RESID || p.epi == EPI_QKV || p.epi == EPI_STORE || p.epi == (MODE == 16 ? EPI_RELU_SPLIT : EPI_GELU_SPLIT))) {
         // CTA pairs: B is staged in halves of 128 columns
         CUtensorMap mb2_hi, mb2_lo;
         if ((rc = make_tmap_kmajor16(&mb2_hi, p.B_hi, p.N, p.K, p.ldb, 1, 0, 128))) return rc;
-        if ((rc = make_tmap_kmajor16(&mb2_lo, p.B_lo, p.N, p.K, p.ldb, 1, 0, 128))) return rc;
+        if (Cfg::kSplit) { if ((rc = make_tmap_kmajor16(&mb2_lo, p.B_lo, p.N, p.K, p.ldb, 1, 0, 128))) return rc; }
+        else mb2_lo = mb2_hi;
         const int pairs_m = (tiles_m + 1) / 2;
         const int64_t total_pairs = (int64_t)pairs_m * tiles_n;
         int grid2 = (int)(2 * total_pairs < sm_count() ? 2 * total_pairs : (sm_count() & ~1));
 #define NSF_GEMM2_LAUNCH(E)                                                                                                     \
         do {                                                                                                                    \
-            NSF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes));         \
-            gemm_tc2_kernel<E><<<grid2, kTcThreads, k2SmemBytes, stream>>>(ma_hi, ma_lo, mb2_hi, mb2_lo, pv, tiles_m, tiles_n, (int)total_pairs); \
+            constexpr bool kSp = MODE == 16;                                                                                    \
+            NSF_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<E, kSp>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<kSp>::kSmemBytes)); \
+            gemm_tc2_kernel<E, kSp><<<grid2, kTcThreads, Tc2Cfg<kSp>::kSmemBytes, stream>>>(ma_hi, ma_lo, mb2_hi, mb2_lo, pv, tiles_m, tiles_n, (int)total_pairs); \
         } while (0)
         switch (p.epi) {
-            case EPI_RELU_SPLIT: NSF_GEMM2_LAUNCH(EPI_RELU_SPLIT); break;
             case EPI_RESID:      NSF_GEMM2_LAUNCH(EPI_RESID); break;
             case EPI_QKV:        NSF_GEMM2_LAUNCH(EPI_QKV); break;
-            default:             NSF_GEMM2_LAUNCH(EPI_STORE); break;
+            case EPI_STORE:      NSF_GEMM2_LAUNCH(EPI_STORE); break;
+            default:             NSF_GEMM2_LAUNCH((MODE == 16 ? EPI_RELU_SPLIT : EPI_GELU_SPLIT)); break;
         }
 #undef NSF_GEMM2_LAUNCH
         return check_launch("gemm_tc2_kernel");
+    }
     }
     if (MODE == 16 && TN == 256 && RB == 128 && pv.vec8) {
         // the mask network's GEMMs: one instantiation per epilogue kind
