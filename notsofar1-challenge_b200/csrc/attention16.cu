@@ -360,7 +360,7 @@ int attn16_launch(const float* q_hi, const float* q_lo, const float* k_hi, const
     } else {
         grid = 2 * n_bh < sm_count() ? 2 * n_bh : sm_count();
         // both row blocks cost a full 128-row MMA pass; block 1 has the narrower pe_k window and fewer live softmax rows
-        static const float g0_frac = [] { const char* e = getenv("NSF_ATTN_G0"); const float v = e ? (float)atof(e) : 0.f; return v > 0.f && v < 1.f ? v : 0.52f; }();
+        static const float g0_frac = [] { const char* e = getenv("NSF_ATTN_G0"); const float v = e ? (float)atof(e) : 0.f; return v > 0.f && v < 1.f ? v : 0.55f; }();
         p.g0 = (int)lroundf(grid * g0_frac);
         if (p.g0 < 1) p.g0 = 1;
         if (p.g0 > grid - 1) p.g0 = grid - 1;
