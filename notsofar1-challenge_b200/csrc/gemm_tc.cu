@@ -62,7 +62,7 @@ struct RowWalker {      // (segment, frame) of consecutive rows m = seg * T + t 
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk_t(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
                                                float* stage, int lane, float (&ln_s)[4], float (&ln_q)[4],
-                                               const size_t (&qkv_row)[4]) {
+                                               const size_t (&qkv_row)[4], const float4 (&xo)[4][2]) {
     const bool lane_is_row = EPI == EPI_MASK || (EPI == EPI_QKV && nc >= 2 * p.d_model && !p.v_rowmajor);
     if (lane_is_row) {
         const int m = r0 + lane;
@@ -131,18 +131,8 @@ __device__ __forceinline__ void epilogue_chunk_t(const GemmParams& p, int b, int
             const int which = EPI == EPI_QKV ? (nc >= 2 * p.d_model ? 2 : (nc >= p.d_model ? 1 : 0)) : 0;
             const int cq = n0 - which * p.d_model;
             const int hq = EPI == EPI_QKV ? (p.d_k == 64 ? cq >> 6 : cq / p.d_k) : 0, dq = cq - hq * p.d_k;
-            // in-place residual stream: the four rows' old values are all in flight before the first store (a store to
-            // x would otherwise fence the next row's loads and expose one HBM round trip per row)
-            float4 xo[4][2];
-            if (EPI == EPI_RESID) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int m = r0 + rq + 8 * k;
-                    const float* o = p.out0 + (size_t)(m < p.M ? m : r0) * p.ldo + n0;
-                    xo[k][0] = *reinterpret_cast<const float4*>(o);
-                    xo[k][1] = *reinterpret_cast<const float4*>(o + 4);
-                }
-            }
+            // in-place residual stream: the old values of the lane's four rows (xo) were requested by the caller before the
+            // accumulator chunk was read from tensor memory (resid_load), so their latency overlaps that read and the transpose
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const int rr = rq + 8 * k;
@@ -303,16 +293,16 @@ __device__ __forceinline__ void epilogue_chunk_t(const GemmParams& p, int b, int
 // p.epi is uniform: one dispatch per chunk, everything inside is resolved at compile time
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r0, int nc, const uint32_t (&r)[32],
                                                float* stage, int lane, float (&ln_s)[4], float (&ln_q)[4],
-                                               const size_t (&qkv_row)[4]) {
+                                               const size_t (&qkv_row)[4], const float4 (&xo)[4][2]) {
     switch (p.epi) {
-        case EPI_STORE:      epilogue_chunk_t<EPI_STORE>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
-        case EPI_RELU_SPLIT: epilogue_chunk_t<EPI_RELU_SPLIT>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
-        case EPI_RESID:      epilogue_chunk_t<EPI_RESID>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
-        case EPI_QKV:        epilogue_chunk_t<EPI_QKV>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
-        case EPI_PV:         epilogue_chunk_t<EPI_PV>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
-        case EPI_MASK:       epilogue_chunk_t<EPI_MASK>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
-        case EPI_GELU_SPLIT: epilogue_chunk_t<EPI_GELU_SPLIT>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
-        case EPI_GELU_POS:   epilogue_chunk_t<EPI_GELU_POS>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row); break;
+        case EPI_STORE:      epilogue_chunk_t<EPI_STORE>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
+        case EPI_RELU_SPLIT: epilogue_chunk_t<EPI_RELU_SPLIT>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
+        case EPI_RESID:      epilogue_chunk_t<EPI_RESID>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
+        case EPI_QKV:        epilogue_chunk_t<EPI_QKV>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
+        case EPI_PV:         epilogue_chunk_t<EPI_PV>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
+        case EPI_MASK:       epilogue_chunk_t<EPI_MASK>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
+        case EPI_GELU_SPLIT: epilogue_chunk_t<EPI_GELU_SPLIT>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
+        case EPI_GELU_POS:   epilogue_chunk_t<EPI_GELU_POS>(p, b, r0, nc, r, stage, lane, ln_s, ln_q, qkv_row, xo); break;
         default: break;
     }
 }
@@ -320,6 +310,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int b, int r
 // EPI >= 0: the epilogue kind is a compile-time constant of the instantiation (the hot GEMMs of the mask network: smaller
 // code -- the generic kernel is 28 k SASS instructions, `no_inst` was 8-9 % of its stall samples -- and registers allocated
 // for one epilogue instead of the worst of eight); EPI < 0: p.epi is read at run time.
+// old values of the in-place residual stream for the chunk at column nc (vector epilogue): the lane's 8 columns of rows
+// r0 + (lane >> 2) + 8 k, all eight loads in flight at once
+__device__ __forceinline__ void resid_load(const GemmParams& p, int r0, int nc, int lane, float4 (&xo)[4][2]) {
+    const int n0 = nc + 8 * (lane & 3), rq = lane >> 2;
+    if (n0 < p.N) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int m = r0 + rq + 8 * k;
+            const float* o = p.out0 + (size_t)(m < p.M ? m : r0) * p.ldo + n0;
+            xo[k][0] = *reinterpret_cast<const float4*>(o);
+            xo[k][1] = *reinterpret_cast<const float4*>(o + 4);
+        }
+    }
+}
+
 template <int MODE, int TN, int RB, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -470,6 +475,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll 1
             for (int c0 = c_first; c0 < n_end; c0 += 64) {
                 uint32_t r[32];
+                float4 xo[4][2];
+                if (epi == EPI_RESID && p.vec8 && r0 < p.M) resid_load(p, r0, n0 + c0, lane, xo);
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + (uint32_t)c0, r);
                 if (c0 + 64 >= n_end) {
                     // last read of this accumulator by this warp: hand it back to the MMA warp before the stores
@@ -478,8 +485,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
                 }
                 if (r0 >= p.M) continue;                    // warp-uniform: quarter entirely out of range
-                if constexpr (EPI >= 0) epilogue_chunk_t<EPI>(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
-                else epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
+                if constexpr (EPI >= 0) epilogue_chunk_t<EPI>(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row, xo);
+                else epilogue_chunk(p, b, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row, xo);
             }
             if (ln_src && r0 < p.M) {
                 // row moments of this warp's columns of the tile: the four lanes that share a row (cg = lane & 3) add up
@@ -671,6 +678,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 #pragma unroll 1
             for (int c0 = c_first; c0 < n_end; c0 += 64) {
                 uint32_t r[32];
+                float4 xo[4][2];
+                if (EPI == EPI_RESID && r0 < p.M) resid_load(p, r0, n0 + c0, lane, xo);
                 tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TBN + (uint32_t)c0, r);
                 if (c0 + 64 >= n_end) {
                     tcgen05_fence_before();
@@ -678,7 +687,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
                     if (lane == 0) mbar_arrive_leader(tmem_empty_bar(acc));
                 }
                 if (r0 >= p.M) continue;
-                epilogue_chunk_t<EPI>(p, 0, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row);
+                epilogue_chunk_t<EPI>(p, 0, r0, n0 + c0, r, stage, lane, ln_s, ln_q, qkv_row, xo);
             }
             if (ln_src && r0 < p.M) {
 #pragma unroll
