@@ -49,9 +49,10 @@ FS = 16000
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class, from the committed
 # `ncu --set full` capture under profiles/ (None until such a capture exists for the class)
 NCU_TRAFFIC = {
-    # mean over the 110 gemm_tc_kernel<16> launches of one 604-segment chunk (profiles/r01_v11_ncu_gemm16_per_launch_604seg.csv):
-    # activations in + out dominate (e.g. FFN2: 460 MB of bf16 pairs read, 230 MB of x read and written)
-    ("gemm_tc", "2xbf16"): 761.7e6,
+    # mean over the six GEMMs of one Conformer block at the bench size (1 209 segments in one chunk), CTA-pair kernels with folded
+    # LayerNorms (profiles/r02_ncu_full_gemm16_cta_pairs_summary.csv: 2.28 / 1.81 / 1.34 / 1.34 / 1.82 / 1.34 GB read + written):
+    # activations in + out dominate (e.g. FFN W2: 920 MB of bf16 pairs read, 460 MB of x read and written, 460 MB of operand planes)
+    ("gemm_tc", "2xbf16"): 1657.0e6,
 }
 METRIC = "audio-sec/sec (xRT) CSS+MVDR 7-ch 16kHz"
 UNIT = "audio-s/s"

@@ -351,17 +351,17 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
     const int rows = T + kDwMaxK - 1 + kDw2Slack;     // rows past the halo are zero: the last window of a frame run reads up to row t0 + 39
     float* wt = tile + (size_t)rows * kDw2Ch;
     const float w1a = __ldg(scalars + 0), b1a = __ldg(scalars + 1), w1g = __ldg(scalars + 2), b1g = __ldg(scalars + 3);
-    // tap weights of the CTA's channels: one contiguous run of dw_w (coalesced); the loads are issued now and land in shared
-    // memory after the tile has been staged
-    constexpr int kWPer = (kDwMaxK * kDw2Ch + kDw2Threads - 1) / kDw2Threads;
+    // tap weights of the CTA's channels: four threads per channel, taps (tid & 3) + 4 m (no index division; the run of the CTA's
+    // weights is contiguous in dw_w); the loads are issued now and land in shared memory after the tile has been staged
+    constexpr int kWPer = (kDwMaxK + 3) / 4;
+    static_assert(kDw2Threads == 4 * kDw2Ch, "four threads per channel load its taps");
     float wreg[kWPer];
-    const int n_w = min(kDw2Ch, d - c0) * ks;
+    const int wc = threadIdx.x >> 2, wj0 = threadIdx.x & 3;
 #pragma unroll
     for (int k = 0; k < kWPer; ++k) {
-        const int i = threadIdx.x + k * kDw2Threads;
-        wreg[k] = i < n_w ? __ldg(dw_w + (size_t)c0 * ks + i) : 0.f;
+        const int j = wj0 + 4 * k;
+        wreg[k] = (j < ks && c0 + wc < d) ? __ldg(dw_w + (size_t)(c0 + wc) * ks + j) : 0.f;
     }
-    for (int i = threadIdx.x; i < kDwMaxK * kDw2Ch; i += kDw2Threads) wt[i] = 0.f;     // taps >= ks, channels >= d
     {
         constexpr int kC4 = kDw2Ch / 4;                               // float4 columns of a tile row
         constexpr int kRowStep = kDw2Threads / kC4;                   // rows covered by the CTA per load
@@ -411,11 +411,10 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
             }
         }
     }
-    __syncthreads();                                                  // the zero fill of wt is complete
 #pragma unroll
     for (int k = 0; k < kWPer; ++k) {
-        const int i = threadIdx.x + k * kDw2Threads;
-        if (i < n_w) { const int c = i / ks, j = i - c * ks; wt[j * kDw2Ch + c] = wreg[k]; }
+        const int j = wj0 + 4 * k;
+        if (j < kDwMaxK) wt[j * kDw2Ch + wc] = wreg[k];               // taps >= ks and channels >= d are zeros
     }
     __syncthreads();
     const int cp = threadIdx.x & (kDw2Ch / 2 - 1), grp = threadIdx.x / (kDw2Ch / 2);
@@ -458,21 +457,27 @@ dwconv_fused_kernel(float* __restrict__ x, const float2* __restrict__ stats, con
                     for (int o = 0; o < kDwOut; ++o) acc[o] = __ffma2_rn(wj, win[o + jj], acc[o]);
                 }
             }
+            // running pointers: one 64-bit add per row instead of an index computation per store
+            float* xw = xc + (size_t)t0 * d;
+            const size_t e0 = (((size_t)seg * T + t0) * d + c) >> 1;
+            uint32_t* hw = ln_hi + e0;
+            uint32_t* lw = ln_lo + e0;
+            const int d2 = d >> 1;
 #pragma unroll
             for (int o = 0; o < kDwOut; ++o) {
                 if (t0 + o < t_end) {
                     const float y0 = fmaxf(fmaf(acc[o].x, sc.x, sh.x), 0.f), y1 = fmaxf(fmaf(acc[o].y, sc.y, sh.y), 0.f);
                     xn[o] = make_float2(xo[o].x + fmaf(w2, y0, b2), xo[o].y + fmaf(w2, y1, b2));
-                    *reinterpret_cast<float2*>(xc + (t0 + o) * d) = xn[o];
+                    *reinterpret_cast<float2*>(xw) = xn[o];
                     if (ln_part) {
                         // LayerNorm source of feed_forward_out: the new rows as raw bf16 head / remainder planes
                         const __nv_bfloat162 hq = __floats2bfloat162_rn(xn[o].x, xn[o].y);
                         const __nv_bfloat162 lq = __floats2bfloat162_rn(xn[o].x - __low2float(hq), xn[o].y - __high2float(hq));
-                        const size_t e2 = (((size_t)seg * T + t0 + o) * d + c) >> 1;
-                        ln_hi[e2] = *reinterpret_cast<const uint32_t*>(&hq);
-                        ln_lo[e2] = *reinterpret_cast<const uint32_t*>(&lq);
+                        *hw = *reinterpret_cast<const uint32_t*>(&hq);
+                        *lw = *reinterpret_cast<const uint32_t*>(&lq);
                     }
                 }
+                xw += d; hw += d2; lw += d2;
             }
         }
         if (ln_part) {

@@ -19,13 +19,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the thread may sleep in hardware up to that long (it wakes when the phase completes) instead
+// of returning to the polling loop after the short default.  The polling loops were ~40 % of the executed instructions of the
+// attention kernel and ~15 % of the GEMMs' (profiles/r02_ncu_full_attn16_dwconv_summary.csv: SYNCS / ISETP / BRA / CS2R / YIELD) --
+// issue slots and power spent on waiting.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (reported as a launch failure), never a hung GPU.
