@@ -263,7 +263,7 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
         return css_device_sharded(x_dev, sep, FS, cfg, n_total)
 
     def step_e2e():
-        chunk = 128 * plan.hop_frames * 256
+        chunk = 32 * plan.hop_frames * 256
         feeder = HostFeeder(x_pinned, dev, chunk)
         out = css_device_sharded(feeder, sep, FS, cfg, n_total)
         # the assembled streams stay on rank 0's GPU (the ASR / diarization hand-off); the host copy of the result is read

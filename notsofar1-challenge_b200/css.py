@@ -177,12 +177,13 @@ def permutation_chain(costs: np.ndarray) -> np.ndarray:
     return cand[states].astype(np.int32)
 
 
-def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batch: int = 128):
+def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batch: int = 176):
     """Chunks of segments the mask network / MVDR run on: [(first segment, count), ...].
 
     Large, equal chunks keep the persistent GEMMs' last wave full (a 128 x 256 tile grid over 148 SMs quantises badly for
     small M); when the audio is still streaming in from the host the first chunk is kept short so that compute starts
-    after the first few MB have landed."""
+    after the first few MB have landed -- but long enough (176 segments = 15 ms of network time) that the rest of a
+    30-minute recording (0.8 GB, ~15 ms over PCIe) has landed when the second chunk wants it."""
     max_batch = max(1, max_batch)
     out, s0 = [], 0
     if streaming and n_seg > first_batch and max_batch > first_batch:
@@ -405,7 +406,7 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
         x_host = x_host.to(torch.float32).contiguous()
         plan0 = plan_segments(x_host.shape[0], fs, cfg)
         # copy granularity: the first (short) chunk of segments, so that the STFT of chunk 0 can start early
-        chunk = min(128, max(1, int(separator.segments_per_batch))) * plan0.hop_frames * FRAME_HOP
+        chunk = min(32, max(1, int(separator.segments_per_batch))) * plan0.hop_frames * FRAME_HOP   # 21 MB per copy: 0.4 ms
         with torch.cuda.device(device):
             x = HostFeeder(x_host, device, chunk)
     out = css_device(x, separator, fs, cfg)
