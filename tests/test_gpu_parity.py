@@ -219,6 +219,51 @@ def test_gemm_engines_vs_fp64(nb, dev, M, N, K):
     assert errs["2xf16"] < 3e-5
 
 
+@pytest.mark.parametrize("M,N,K", [(300, 512, 512), (129, 384, 128), (5000, 1536, 512), (128, 8, 64), (40000, 512, 1024), (257, 1024, 1824)])
+def test_gemm_cta_pairs_vs_single_cta_and_fp64(nb, dev, monkeypatch, M, N, K):
+    """The CTA-pair kernel (tcgen05.mma.cta_group::2; the default for the 2xBF16 / 2xF16 GEMMs with 8-aligned N) on shapes
+    that exercise its edges -- an odd number of 128-row tiles (the pair's second CTA runs past M), N that ends inside a
+    256-column tile or inside the leader's half of it, a K tail, fewer pairs than SM pairs, more tiles than one wave --
+    against the fp64 product, and against the single-CTA kernel (NSF_GEMM_2SM=0 is read once per process, so the comparison
+    runs in a child process)."""
+    import subprocess, sys, json, os, tempfile
+    lib = nb._cabi.load()
+    rng = np.random.default_rng(M + 3 * N + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    ref = A.astype(np.float64) @ W.astype(np.float64).T + bias
+    tA, tW, tb = (torch.from_numpy(a).to(dev) for a in (A, W, bias))
+    ws = torch.empty(8 * (M * K + N * K) + 4096, dtype=torch.uint8, device=dev)
+    outs = {}
+    for name, eng in (("2xbf16", nb.GEMM_TC_2XBF16), ("2xf16", nb.GEMM_TC_2XF16)):
+        out = torch.full((M, N), float("nan"), dtype=torch.float32, device=dev)
+        nb._cabi.check(lib.nsf_gemm_test(eng, nb._cabi.ptr(tA), nb._cabi.ptr(tW), nb._cabi.ptr(tb), nb._cabi.ptr(out), M, N, K,
+                                         nb._cabi.ptr(ws), ws.numel(), nb._cabi.stream_ptr()), "nsf_gemm_test")
+        torch.cuda.synchronize()
+        outs[name] = out.cpu().numpy()
+        err = rel_l2(outs[name], ref)
+        print("pair gemm rel err", (M, N, K), name, err)
+        assert np.isfinite(outs[name]).all() and err < 3e-5
+    if M * N > 3_000_000:
+        return
+    # the single-CTA kernel on the same operands: the two kernels add the same products in the same order per tile
+    with tempfile.TemporaryDirectory() as td:
+        np.savez(os.path.join(td, "in.npz"), A=A, W=W, bias=bias)
+        code = (
+            "import sys, numpy as np, torch; sys.path.insert(0, %r); import notsofar_b200 as nb\n"
+            "d = np.load(%r); lib = nb._cabi.load(); dev = torch.device('cuda', 0)\n"
+            "A, W, b = (torch.from_numpy(d[k]).to(dev) for k in ('A', 'W', 'bias')); M, K = A.shape; N = W.shape[0]\n"
+            "ws = torch.empty(8 * (M * K + N * K) + 4096, dtype=torch.uint8, device=dev); out = torch.empty((M, N), dtype=torch.float32, device=dev)\n"
+            "nb._cabi.check(lib.nsf_gemm_test(nb.GEMM_TC_2XBF16, nb._cabi.ptr(A), nb._cabi.ptr(W), nb._cabi.ptr(b), nb._cabi.ptr(out), M, N, K, nb._cabi.ptr(ws), ws.numel(), nb._cabi.stream_ptr()), 'gemm')\n"
+            "torch.cuda.synchronize(); np.save(%r, out.cpu().numpy())\n"
+        ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(td, "in.npz"), os.path.join(td, "out.npy"))
+        env = dict(os.environ, NSF_GEMM_2SM="0")
+        subprocess.run([sys.executable, "-c", code], check=True, env=env, timeout=300)
+        single = np.load(os.path.join(td, "out.npy"))
+    assert np.array_equal(single, outs["2xbf16"]), f"pair vs single-CTA kernel differ: {np.abs(single - outs['2xbf16']).max()}"
+
+
 # ----------------------------------------------------------------------------------------------- fused attention
 @pytest.mark.parametrize("n_seg,n_heads,T,maxlen", [(2, 2, 186, 1000), (1, 1, 50, 1000), (1, 2, 128, 200), (1, 1, 129, 300),
                                                       (2, 1, 192, 1000), (1, 1, 2, 1000), (3, 8, 186, 1000)])
