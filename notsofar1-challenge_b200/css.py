@@ -186,7 +186,7 @@ def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batc
     30-minute recording (0.8 GB, ~15 ms over PCIe) has landed when the second chunk wants it."""
     max_batch = max(1, max_batch)
     out, s0 = [], 0
-    if streaming and n_seg > first_batch and max_batch > first_batch:
+    if streaming and n_seg >= 2 * first_batch and max_batch > first_batch:      # short sessions: one chunk (a small second chunk wastes GEMM waves)
         out.append((0, first_batch))
         s0 = first_batch
     rest = n_seg - s0
@@ -431,37 +431,48 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
     return separated_wavs, side_info
 
 
-_PINNED_POOL: Dict[tuple, list] = {}       # shape -> [(pinned tensor, weakref to the numpy array handed out or None), ...]
+_PINNED_POOL: Dict[int, list] = {}         # capacity in bytes -> [[pinned uint8 tensor, weakref to the numpy array handed out or None], ...]
 _PINNED_KEEP_FREE = 2
 
 
-def _pinned_out(shape: tuple) -> torch.Tensor:
-    """Page-locked float32 host buffer for the separated waveforms (pinning 345 MB costs more than the whole separation,
-    so buffers are pooled per shape).  A buffer is handed out again only after every numpy array that was returned on top
-    of it has been garbage collected (``_lend`` keeps a weak reference to it): a caller that keeps the streams of three
-    sessions holds three distinct buffers -- the reference returns freshly owned arrays (css.py:316-319), so must this."""
-    entries = _PINNED_POOL.setdefault(shape, [])
+def _pinned_out(shape: tuple, dtype=torch.float32) -> torch.Tensor:
+    """Page-locked host buffer of the given shape (the separated waveforms; the PCM16 staging of css_inference).  Pinning
+    345 MB costs more than the whole separation, so buffers are pooled -- by capacity, rounded up to 64 MB (1 MB for small
+    ones), because every recording has its own length.  A buffer is handed out again only after every numpy array that was
+    returned on top of it has been garbage collected (``_lend`` keeps a weak reference to it): a caller that keeps the streams
+    of three sessions holds three distinct buffers -- the reference returns freshly owned arrays (css.py:316-319), so must this."""
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    nbytes = max(1, numel * torch.empty((), dtype=dtype).element_size())
+    gran = (1 << 26) if nbytes > (1 << 24) else (1 << 20)
+    cap = -(-nbytes // gran) * gran
+    entries = _PINNED_POOL.setdefault(cap, [])
+    base = None
     for e in entries:
         if e[1] is None or e[1]() is None:
             e[1] = None
-            return e[0]
-    buf = torch.empty(shape, dtype=torch.float32, pin_memory=True)
-    entries.append([buf, None])
-    return buf
+            base = e[0]
+            break
+    if base is None:
+        base = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+        entries.append([base, None])
+    return base[:nbytes].view(dtype).view(tuple(int(d) for d in shape))
 
 
 def _lend(buf: torch.Tensor) -> np.ndarray:
     """numpy view of a pooled pinned buffer; the buffer stays out of circulation while the view (or any slice of it) lives."""
     import weakref
     arr = buf.numpy()
-    entries = _PINNED_POOL.get(tuple(buf.shape), [])
-    for e in entries:
-        if e[0] is buf:
-            e[1] = weakref.ref(arr)
-    # buffers nobody holds any more beyond a small reserve go back to the OS
-    free = [e for e in entries if e[1] is None or e[1]() is None]
-    for e in free[_PINNED_KEEP_FREE:]:
-        entries.remove(e)
+    ptr = buf.untyped_storage().data_ptr()
+    for entries in _PINNED_POOL.values():
+        for e in entries:
+            if e[0].untyped_storage().data_ptr() == ptr:
+                e[1] = weakref.ref(arr)
+        # buffers nobody holds any more beyond a small reserve go back to the OS
+        free = [e for e in entries if e[1] is None or e[1]() is None]
+        for e in free[_PINNED_KEEP_FREE:]:
+            entries.remove(e)
     return arr
 
 
@@ -641,10 +652,20 @@ def pcm16_to_device(datas, device) -> "torch.Tensor":
     n, c = datas[0].size, len(datas)
     with torch.cuda.device(device):
         pcm = torch.empty((c, n), dtype=torch.int16, device=device)
-        for k, d in enumerate(datas):
-            pcm[k].copy_(torch.from_numpy(np.asarray(d)), non_blocking=True)
+        # the channel files (memory-mapped) are copied into one pooled page-locked buffer by the reader threads, every channel
+        # goes up as soon as its copy is done: a pageable upload of a 6-minute session took 8 ms, this takes ~2
+        stage = _pinned_out((c, n), torch.int16)
+        view = _lend(stage)                                     # out of circulation until this call is over
+
+        def fill(k):
+            np.copyto(view[k], datas[k])
+            return k
+        for k in _wav_pool().map(fill, range(c)):
+            pcm[k].copy_(stage[k], non_blocking=True)
         x = torch.empty((n, c), dtype=torch.float32, device=device)
         _cabi.check(lib.nsf_pcm16_to_float_interleaved(_cabi.ptr(pcm), c, n, _cabi.ptr(x), _cabi.stream_ptr()), "nsf_pcm16_to_float_interleaved")
+        torch.cuda.current_stream(device).synchronize()        # the staging buffer goes back to the pool when `view` dies
+        del view
     return x
 
 
@@ -686,7 +707,16 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
 
     n_expected = 7 if session.is_mc else 1
     assert len(session.wav_file_names) == n_expected, 'expecting 7 microphones' if session.is_mc else 'expecting one file'
+    import os, time
+    timing = os.environ.get("NSF_TIMING") == "1"          # per-phase wall clock of the call (forces a device sync per phase)
+    marks = [("start", time.perf_counter())]
+
+    def tick(name):
+        if timing:
+            torch.cuda.synchronize(device)
+            marks.append((name, time.perf_counter()))
     fast = _read_pcm16_channels(session.wav_file_names)
+    tick("read")
     if fast is not None:
         datas, sr = fast
         x = pcm16_to_device(datas, device)
@@ -696,23 +726,36 @@ def css_inference(out_dir: str, models_dir: str, session, cfg: CssCfg, fetch_fro
     if cfg.slice_audio_for_debug:
         x = x[sr * 20:sr * 30].contiguous()
 
+    tick("upload")
     out = css_device(x, separator, sr, cfg)
+    tick("css_device")
     # write_wav (utils/audio_utils.py:37-49) on the device: 0.99 peak normalisation + PCM_16 rounding of the three streams and
     # of channel 0 of the input (input_mixture.wav); the int16 streams also stay in HBM for the stages downstream
     pcm_dev = streams_to_pcm16(out["wav"])
     mix_pcm = streams_to_pcm16(x[:, 0].contiguous()[None])
     del out
-    pcm_host = pcm_dev.cpu().numpy()
-    mix_host = mix_pcm.cpu().numpy()[0]
+    # one pooled page-locked buffer for the four files' samples; the writer threads hold views of it (it is not handed out again
+    # before they are done)
+    with torch.cuda.device(device):
+        host = _pinned_out(tuple(pcm_dev.shape), torch.int16)
+        pcm_host = _lend(host)                                        # lent before the next request: never the same buffer twice
+        host_mix = _pinned_out((mix_pcm.shape[1],), torch.int16)      # the streams are a few samples shorter than the input
+        mix_host = _lend(host_mix)
+        host.copy_(pcm_dev, non_blocking=True)
+        host_mix.copy_(mix_pcm[0], non_blocking=True)
+        torch.cuda.current_stream(device).synchronize()
+    tick("pcm16+d2h")
 
     names = [str(css_out_dir / 'input_mixture.wav')] + [str(css_out_dir / f"sep_stream{i}.wav") for i in range(pcm_host.shape[0])]
-    import os
     for fname, samps in zip(names, [mix_host] + [pcm_host[i] for i in range(pcm_host.shape[0])]):
         flush_wav_writes([fname])                               # an earlier write of the same path must not overtake this one
         _WAV_PENDING[os.path.abspath(fname)] = _wav_pool().submit(_write_pcm16_file, fname, samps, int(sr))
     if not ASYNC_WAV_WRITES:
         flush_wav_writes(names)
 
+    tick("wav_submit/flush")
+    if timing:
+        print("css_inference phases [ms]: " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.2f}" for a, b in zip(marks, marks[1:])), flush=True)
     sep_wav_file_names = names[1:]
     DEVICE_STREAMS.pop(_streams_key(sep_wav_file_names), None)
     DEVICE_STREAMS[_streams_key(sep_wav_file_names)] = (pcm_dev, int(sr))
