@@ -471,8 +471,9 @@ def _lend(buf: torch.Tensor) -> np.ndarray:
                 e[1] = weakref.ref(arr)
         # buffers nobody holds any more beyond a small reserve go back to the OS
         free = [e for e in entries if e[1] is None or e[1]() is None]
-        for e in free[_PINNED_KEEP_FREE:]:
-            entries.remove(e)
+        drop = {id(e) for e in free[_PINNED_KEEP_FREE:]}
+        if drop:
+            entries[:] = [e for e in entries if id(e) not in drop]    # by identity: comparing entries would compare tensors
     return arr
 
 
