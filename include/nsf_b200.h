@@ -340,7 +340,12 @@ int nsf_whisper_alignment(const float* weights, int n_batch, int n_heads, int n_
  * dims: Jasper blocks (filters / repeat / kernel / residual per block), attention channels, embedding size.
  * blob layout: notsofar_b200/titanet.py::pack_titanet (BatchNorms folded; GEMM weights as bf16 head / remainder planes). */
 typedef struct nsf_titanet nsf_titanet;
-typedef struct { int feat_in, n_blocks, att_ch, emb; int filters[8], repeat[8], kernel[8], residual[8]; } nsf_titanet_dims;
+typedef struct {
+    int feat_in, n_blocks, att_ch, emb; int filters[8], repeat[8], kernel[8], residual[8];
+    int precision;   /* 0: fp32-grade GEMMs (bf16 head + remainder planes, three MMAs per product; the blob holds both planes);
+                        1: the reference's autocast() arithmetic -- fp16 operands, fp32 accumulation, one MMA per product (the blob's
+                           "head" entries hold fp16 planes, the "remainder" entries are ignored) */
+} nsf_titanet_dims;
 int64_t nsf_titanet_num_offsets(const nsf_titanet_dims* dims);
 int nsf_titanet_create(const nsf_titanet_dims* dims, const float* blob, int64_t blob_floats, const int64_t* offsets /*host*/,
                        int n_offsets, nsf_titanet** out);

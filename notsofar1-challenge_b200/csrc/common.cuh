@@ -95,7 +95,8 @@ __device__ __forceinline__ void split_tf32(float v, float& hi, float& lo) {
 // The 16-bit arrays live in the same buffers as the fp32 ones (element index unchanged, half the bytes used).
 //   SPLIT_BF16_1 one bf16 array (head only): the plain bf16 operand of the single-pass NSF_GEMM_TC_BF16 engine
 //   SPLIT_FP32   one fp32 array (no split): plain outputs written through the same store helpers
-enum SplitFmt : int { SPLIT_TF32 = 0, SPLIT_BF16 = 1, SPLIT_F16 = 2, SPLIT_BF16_1 = 3, SPLIT_FP32 = 4 };
+//   SPLIT_F16_1  one fp16 array (unscaled, saturating): the operand of a single-pass fp16 GEMM (TitaNet under autocast semantics)
+enum SplitFmt : int { SPLIT_TF32 = 0, SPLIT_BF16 = 1, SPLIT_F16 = 2, SPLIT_BF16_1 = 3, SPLIT_FP32 = 4, SPLIT_F16_1 = 5 };
 constexpr float kF16ActScale = 16.f, kF16WeightScale = 256.f;
 
 inline int split_fmt_of_engine(int engine) {
@@ -125,6 +126,8 @@ __device__ __forceinline__ void split_store(int fmt, float* hi, float* lo, size_
         lo[idx] = l;
     } else if (fmt == SPLIT_BF16_1) {
         reinterpret_cast<uint16_t*>(hi)[idx] = __bfloat16_as_ushort(__float2bfloat16_rn(v));
+    } else if (fmt == SPLIT_F16_1) {
+        reinterpret_cast<uint16_t*>(hi)[idx] = __half_as_ushort(__float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)));
     } else if (fmt == SPLIT_FP32) {
         hi[idx] = v;
     } else {
@@ -143,6 +146,11 @@ __device__ __forceinline__ void split_store4(int fmt, float* hi, float* lo, size
         *reinterpret_cast<float4*>(lo + idx) = l;
     } else if (fmt == SPLIT_BF16_1) {
         const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + idx) =
+            make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    } else if (fmt == SPLIT_F16_1) {
+        const __half2 h01 = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
+        const __half2 h23 = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
         *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(hi) + idx) =
             make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     } else if (fmt == SPLIT_FP32) {
@@ -183,6 +191,14 @@ __device__ __forceinline__ void split_store8(int fmt, float* hi, float* lo, size
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * e], v[2 * e + 1]);
+            h[e] = *reinterpret_cast<const uint32_t*>(&hp);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(hi) + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+    } else if (fmt == SPLIT_F16_1) {
+        uint32_t h[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const __half2 hp = __floats2half2_rn(fminf(fmaxf(v[2 * e], -65504.f), 65504.f), fminf(fmaxf(v[2 * e + 1], -65504.f), 65504.f));
             h[e] = *reinterpret_cast<const uint32_t*>(&hp);
         }
         *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(hi) + idx) = make_uint4(h[0], h[1], h[2], h[3]);

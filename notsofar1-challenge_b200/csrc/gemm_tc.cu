@@ -396,7 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else if (warp == 1) {
         if (lane == 0) {
             // ===== MMA issuer
-            const uint32_t idesc = MODE >= 16 ? make_idesc_f16(TBN, p.op_fmt != SPLIT_F16) : make_idesc_tf32(TBN);
+            const uint32_t idesc = MODE >= 16 ? make_idesc_f16(TBN, p.op_fmt != SPLIT_F16 && p.op_fmt != SPLIT_F16_1) : make_idesc_tf32(TBN);
             uint32_t it = 0, tl = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tl) {
                 const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
@@ -597,7 +597,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             // ===== MMA issuer (leader only)
-            const uint32_t idesc = make_idesc_f16_2sm(TBN, p.op_fmt != SPLIT_F16);       // bf16 operands unless the scaled-fp16 pairs
+            const uint32_t idesc = make_idesc_f16_2sm(TBN, p.op_fmt != SPLIT_F16 && p.op_fmt != SPLIT_F16_1);       // bf16 operands unless the scaled-fp16 pairs
             uint32_t it = 0, tl = 0;
             for (int item = pair; item < total_pairs; item += n_pairs, ++tl) {
                 const uint32_t acc = tl & 1, aph = (tl >> 1) & 1;
@@ -746,9 +746,9 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
             case EPI_STORE: case EPI_RESID:
                 ok = ok && p.ldo % 4 == 0 && p.o_batch_stride % 4 == 0 && al16(p.out0); break;
             case EPI_RELU_SPLIT: case EPI_PV:
-                ok = ok && p.ldo % 8 == 0 && al16(p.out0) && al16(p.out1) && p.d_k % 8 == 0; break;
+                ok = ok && p.ldo % 8 == 0 && al16(p.out0) && (p.out_fmt == SPLIT_BF16_1 || p.out_fmt == SPLIT_F16_1 || al16(p.out1)) && p.d_k % 8 == 0; break;
             case EPI_GELU_SPLIT:
-                ok = ok && p.ldo % 8 == 0 && p.o_batch_stride % 8 == 0 && al16(p.out0) && (p.out_fmt == SPLIT_BF16_1 || al16(p.out1)); break;
+                ok = ok && p.ldo % 8 == 0 && p.o_batch_stride % 8 == 0 && al16(p.out0) && (p.out_fmt == SPLIT_BF16_1 || p.out_fmt == SPLIT_F16_1 || al16(p.out1)); break;
             case EPI_GELU_POS:
                 ok = ok && p.ldo % 4 == 0 && al16(p.out0) && al16(p.out1); break;
             case EPI_QKV:
@@ -779,7 +779,7 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
     } while (0)
     if constexpr ((MODE == 16 || MODE == 116) && TN == 256 && RB == 128) {
     if (pv.vec8 && p.batch == 1 && sm_count() >= 2 && use_cta_pairs() &&
-        (p.epi == EPI_RESID || p.epi == EPI_QKV || p.epi == EPI_STORE || p.epi == (MODE == 16 ? EPI_RELU_SPLIT : EPI_GELU_SPLIT))) {
+        (p.epi == EPI_RESID || p.epi == EPI_QKV || p.epi == EPI_STORE || p.epi == EPI_RELU_SPLIT || (MODE == 116 && p.epi == EPI_GELU_SPLIT))) {
         // CTA pairs: B is staged in halves of 128 columns
         CUtensorMap mb2_hi, mb2_lo;
         if ((rc = make_tmap_kmajor16(&mb2_hi, p.B_hi, p.N, p.K, p.ldb, 1, 0, 128))) return rc;
@@ -798,7 +798,8 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
             case EPI_RESID:      NSF_GEMM2_LAUNCH(EPI_RESID); break;
             case EPI_QKV:        NSF_GEMM2_LAUNCH(EPI_QKV); break;
             case EPI_STORE:      NSF_GEMM2_LAUNCH(EPI_STORE); break;
-            default:             NSF_GEMM2_LAUNCH((MODE == 16 ? EPI_RELU_SPLIT : EPI_GELU_SPLIT)); break;
+            case EPI_RELU_SPLIT: NSF_GEMM2_LAUNCH(EPI_RELU_SPLIT); break;
+            default:             if constexpr (MODE == 116) { NSF_GEMM2_LAUNCH(EPI_GELU_SPLIT); } break;
         }
 #undef NSF_GEMM2_LAUNCH
         return check_launch("gemm_tc2_kernel");
@@ -833,7 +834,7 @@ int gemm_tc_launch(const GemmParams& p, int mode, cudaStream_t stream) {
         return rb64 ? launch_t<16, 256, 64>(p, stream) : launch_t<16, 256, 128>(p, stream);
     }
     if (mode == 116) {
-        if (p.op_fmt != SPLIT_BF16_1) { set_error("gemm_tc: the bf16 engine needs SPLIT_BF16_1 operands"); return NSF_ERR_INVALID_ARG; }
+        if (p.op_fmt != SPLIT_BF16_1 && p.op_fmt != SPLIT_F16_1) { set_error("gemm_tc: the single-pass engine needs SPLIT_BF16_1 / SPLIT_F16_1 operands"); return NSF_ERR_INVALID_ARG; }
         if (p.K % 8 != 0) { set_error("gemm_tc: K=%d must be a multiple of 8", p.K); return NSF_ERR_INVALID_ARG; }
         // small M (the Whisper decode step: M = sequences in flight): 128 x 32 tiles spread the weight stream over N / 32 CTAs
         // instead of N / 256, with an 8-deep TMA ring per CTA

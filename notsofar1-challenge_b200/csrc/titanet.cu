@@ -121,6 +121,25 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, fl
     }
 }
 
+__device__ __forceinline__ void f16x8_to_f32(const uint4& h, float (&v)[8]) {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+        v[2 * e] = f.x;
+        v[2 * e + 1] = f.y;
+    }
+}
+// bf16 head / remainder planes -> one fp16 plane (the features enter the fp16 engine through this)
+__global__ void __launch_bounds__(256)
+tn_pairs_to_f16_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo, __half* __restrict__ out, int64_t n8) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n8) return;
+    float v[8];
+    bf16x8_to_f32(*reinterpret_cast<const uint4*>(in_hi + e * 8), *reinterpret_cast<const uint4*>(in_lo + e * 8), v);
+    split_store8(SPLIT_F16_1, reinterpret_cast<float*>(out), nullptr, (size_t)e * 8, v);
+}
+
 // depthwise convolution over time ('same' padding, cross-correlation), input masked beyond the crop's length (MaskedConv1d).
 // CTA = (crop, 64 frames, 64 channels), 128 threads: the 64 + k - 1 input rows are staged once in shared memory as fp32 (each
 // input element crosses L2 1.0 - 1.5 times instead of k times; two planes of 4-channel halves so that the 16-byte reads of a
@@ -130,7 +149,7 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& h, const uint4& l, fl
 constexpr int kDwFrames = 64, kDwCh = 64, kDwMaxK = 31, kDwRowsMax = kDwFrames + kDwMaxK - 1;
 __global__ void __launch_bounds__(128)
 tn_dwconv_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict__ in_lo, const int* __restrict__ n_frames, int t_pad,
-                 int C, int k, const float* __restrict__ w, float* __restrict__ out_hi, float* __restrict__ out_lo) {
+                 int C, int k, const float* __restrict__ w, float* __restrict__ out_hi, float* __restrict__ out_lo, int fmt) {
     __shared__ __align__(16) float4 tile[2][kDwRowsMax][8];
     const int b = blockIdx.z, t0 = blockIdx.y * kDwFrames, c0 = blockIdx.x * kDwCh;
     const int nf = n_frames[b];
@@ -144,7 +163,8 @@ tn_dwconv_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict_
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
         if (v8 < nvec && tt >= 0 && tt < nf) {
             const size_t o = ((size_t)b * t_pad + tt) * C + c0 + v8 * 8;
-            bf16x8_to_f32(*reinterpret_cast<const uint4*>(in_hi + o), *reinterpret_cast<const uint4*>(in_lo + o), v);
+            if (fmt == SPLIT_F16_1) f16x8_to_f32(*reinterpret_cast<const uint4*>(in_hi + o), v);
+            else bf16x8_to_f32(*reinterpret_cast<const uint4*>(in_hi + o), *reinterpret_cast<const uint4*>(in_lo + o), v);
         }
         tile[0][r][v8] = make_float4(v[0], v[1], v[2], v[3]);
         tile[1][r][v8] = make_float4(v[4], v[5], v[6], v[7]);
@@ -172,7 +192,7 @@ tn_dwconv_kernel(const uint16_t* __restrict__ in_hi, const uint16_t* __restrict_
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int t = t0 + fg + 16 * i;
-        if (t < t_pad) split_store8(SPLIT_BF16, out_hi, out_lo, ((size_t)b * t_pad + t) * C + c0 + v8 * 8, acc[i]);
+        if (t < t_pad) split_store8(fmt, out_hi, out_lo, ((size_t)b * t_pad + t) * C + c0 + v8 * 8, acc[i]);
     }
 }
 
@@ -244,7 +264,7 @@ tn_fc_t_kernel(const float* __restrict__ in, int K, const float* __restrict__ Wt
 // y = relu(pre * gate[crop][c] + res), zero beyond the crop's length; bf16 planes for the next block, optionally fp32 in place
 __global__ void __launch_bounds__(256)
 tn_se_apply_kernel(float* __restrict__ pre, const float* __restrict__ gate, const float* __restrict__ res, const int* __restrict__ n_frames,
-                   int t_pad, int C, float* __restrict__ out_hi, float* __restrict__ out_lo, int write_f32, int64_t total) {
+                   int t_pad, int C, float* __restrict__ out_hi, float* __restrict__ out_lo, int write_f32, int64_t total, int fmt) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int c8 = C >> 3;
@@ -266,7 +286,7 @@ tn_se_apply_kernel(float* __restrict__ pre, const float* __restrict__ gate, cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
     }
-    split_store8(SPLIT_BF16, out_hi, out_lo, o, v);
+    split_store8(fmt, out_hi, out_lo, o, v);
     if (write_f32) {
         *reinterpret_cast<float4*>(pre + o) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<float4*>(pre + o + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -277,13 +297,13 @@ tn_se_apply_kernel(float* __restrict__ pre, const float* __restrict__ gate, cons
 // h2 = tanh(a * relu(h1 + bvec[crop]) + c)  (TDNN: conv -> ReLU -> BatchNorm, then Tanh) -> bf16 planes [M][A]
 __global__ void tn_att_act_kernel(const float* __restrict__ h1, const float* __restrict__ bvec, const float* __restrict__ a,
                                   const float* __restrict__ c, int t_pad, int A, float* __restrict__ out_hi, float* __restrict__ out_lo,
-                                  int64_t total) {
+                                  int64_t total, int fmt) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= total) return;
     const int j = (int)(e % A);
     const int b = (int)((e / A) / t_pad);
     const float v = tanhf(fmaf(a[j], fmaxf(h1[e] + bvec[(size_t)b * A + j], 0.f), c[j]));
-    split_store(SPLIT_BF16, out_hi, out_lo, (size_t)e, v);
+    split_store(fmt, out_hi, out_lo, (size_t)e, v);
 }
 
 // attentive statistics per (crop, channel): alpha = softmax over the valid frames of logit, mu = sum alpha x,
@@ -404,6 +424,7 @@ struct TnPlan {                      // offset indices, in the order notsofar_b2
 };
 
 bool tn_dims_ok(const nsf_titanet_dims& d) {
+    if (d.precision != 0 && d.precision != 1) return false;
     if (d.n_blocks < 1 || d.n_blocks > kTnMaxBlocks || d.feat_in < 8 || d.feat_in % 8 || d.att_ch < 8 || d.att_ch % 8 || d.emb < 1) return false;
     for (int b = 0; b < d.n_blocks; ++b)
         if (d.filters[b] < 64 || d.filters[b] % 64 || d.repeat[b] < 1 || d.repeat[b] > 8 || d.kernel[b] < 1 || d.kernel[b] > kDwMaxK || !(d.kernel[b] & 1)) return false;
@@ -518,14 +539,17 @@ extern "C" int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const vo
     auto g = [&](int i) { return h->blob + h->offsets[i]; };
     int rc;
 
+    // precision 0: fp32-grade (bf16 head / remainder planes, three MMAs per product); 1: one fp16 plane, one MMA -- the arithmetic
+    // of the reference's autocast() region (word_based_diarization.py:102-105): fp16 operands, fp32 accumulation
+    const int fmt = D.precision == 1 ? SPLIT_F16_1 : SPLIT_BF16;
     auto gemm = [&](const float* a_hi, const float* a_lo, int K, int w_hi, int w_lo, const float* bias, int N, int epi, float* o0, float* o1,
                     int out_fmt) {
         GemmParams p = {};
         p.batch = 1; p.alpha = 1.f; p.acc_scale = 1.f;
-        p.op_fmt = SPLIT_BF16; p.out_fmt = out_fmt; p.qkv_fmt = SPLIT_BF16; p.d_k = 64;
+        p.op_fmt = fmt; p.out_fmt = out_fmt == SPLIT_BF16 ? fmt : out_fmt; p.qkv_fmt = fmt; p.d_k = 64;
         p.A_hi = a_hi; p.A_lo = a_lo; p.lda = K; p.B_hi = g(w_hi); p.B_lo = g(w_lo); p.ldb = K;
         p.M = M; p.N = N; p.K = K; p.n_valid = N; p.bias = bias; p.epi = epi; p.out0 = o0; p.out1 = o1; p.ldo = N;
-        return gemm_launch(NSF_GEMM_TC_2XBF16, p, s);
+        return gemm_launch(fmt == SPLIT_F16_1 ? NSF_GEMM_TC_BF16 : NSF_GEMM_TC_2XBF16, p, s);      // NSF_GEMM_TC_BF16 = the single-pass engine
     };
     auto fc = [&](const float* in, int K, const float* W, const float* bias, int N, int act, float* out) {
         const int64_t threads = (int64_t)n_crops * N * 32;
@@ -535,6 +559,15 @@ extern "C" int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const vo
 
     const float* in_hi = reinterpret_cast<const float*>(feat_hi);
     const float* in_lo = reinterpret_cast<const float*>(feat_lo);
+    if (fmt == SPLIT_F16_1) {
+        // the features arrive as bf16 pairs: one fp16 plane of them in a remainder plane this engine never writes
+        const int64_t n8 = M64 * D.feat_in / 8;
+        tn_pairs_to_f16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(feat_hi),
+                                                                           reinterpret_cast<const uint16_t*>(feat_lo), reinterpret_cast<__half*>(w.b_lo), n8);
+        if ((rc = check_launch("tn_pairs_to_f16_kernel"))) return rc;
+        in_hi = w.b_lo;
+        in_lo = w.b_lo;
+    }
     int c_in = D.feat_in;
     for (int b = 0; b < D.n_blocks; ++b) {
         const int co = D.filters[b], k = D.kernel[b], rep = D.repeat[b];
@@ -548,7 +581,7 @@ extern "C" int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const vo
         for (int r = 0; r < rep; ++r) {
             { ProfScope prof(PROF_NET_OTHER, 0.0, s);
               tn_dwconv_kernel<<<dim3((c + kDwCh - 1) / kDwCh, (t_pad + kDwFrames - 1) / kDwFrames, n_crops), 128, 0, s>>>(
-                  reinterpret_cast<const uint16_t*>(x_hi), reinterpret_cast<const uint16_t*>(x_lo), n_frames, t_pad, c, k, g(P.dw[b][r]), w.d_hi, w.d_lo);
+                  reinterpret_cast<const uint16_t*>(x_hi), reinterpret_cast<const uint16_t*>(x_lo), n_frames, t_pad, c, k, g(P.dw[b][r]), w.d_hi, w.d_lo, fmt);
               if ((rc = check_launch("tn_dwconv_kernel"))) return rc; }
             if (r < rep - 1) {       // pointwise conv + BatchNorm + ReLU -> planes (the block's scratch output buffer)
                 if ((rc = gemm(w.d_hi, w.d_lo, c, P.pw_hi[b][r], P.pw_lo[b][r], g(P.pw_b[b][r]), co, EPI_RELU_SPLIT, y_hi, y_lo, SPLIT_BF16))) return rc;
@@ -569,7 +602,7 @@ extern "C" int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const vo
             if ((rc = check_launch("tn_fc_t_kernel"))) return rc; }
           const int64_t total = M64 * (co / 8);
           tn_se_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.pre, w.gate, D.residual[b] ? w.res : nullptr, n_frames, t_pad, co,
-                                                                             y_hi, y_lo, last_block ? 1 : 0, total);
+                                                                             y_hi, y_lo, last_block ? 1 : 0, total, fmt);
           if ((rc = check_launch("tn_se_apply_kernel"))) return rc;
           in_hi = y_hi; in_lo = y_lo; }
         c_in = co;
@@ -584,7 +617,7 @@ extern "C" int nsf_titanet_forward(nsf_titanet* h, const void* feat_hi, const vo
     if ((rc = gemm(in_hi, in_lo, C, P.w1x_hi, P.w1x_lo, nullptr, A, EPI_STORE, w.h1, nullptr, SPLIT_FP32))) return rc;
     { ProfScope prof(PROF_NET_OTHER, 0.0, s);
       const int64_t total = M64 * A;
-      tn_att_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.h1, w.bvec, g(P.a1), g(P.c1), t_pad, A, w.h2_hi, w.h2_lo, total);
+      tn_att_act_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(w.h1, w.bvec, g(P.a1), g(P.c1), t_pad, A, w.h2_hi, w.h2_lo, total, fmt);
       if ((rc = check_launch("tn_att_act_kernel"))) return rc; }
     if ((rc = gemm(w.h2_hi, w.h2_lo, A, P.w2_hi, P.w2_lo, g(P.b2), C, EPI_STORE, w.res, nullptr, SPLIT_FP32))) return rc;
     { ProfScope prof(PROF_NET_OTHER, 0.0, s);

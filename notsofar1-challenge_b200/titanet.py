@@ -25,7 +25,10 @@ BN_EPS_ENC, BN_EPS_DEC = 1e-3, 1e-5
 
 class TitanetDims(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("feat_in", "n_blocks", "att_ch", "emb")] + \
-               [(n, C.c_int * 8) for n in ("filters", "repeat", "kernel", "residual")]
+               [(n, C.c_int * 8) for n in ("filters", "repeat", "kernel", "residual")] + [("precision", C.c_int)]
+
+
+PRECISION_FP32, PRECISION_FP16 = 0, 1      # nsf_titanet_dims.precision: bf16 head + remainder pairs (fp32-grade) / one fp16 plane
 
 
 def _np(v) -> np.ndarray:
@@ -58,9 +61,10 @@ def infer_blocks(w: Dict[str, object]) -> Tuple[Tuple[int, int, int, bool], ...]
     return tuple(blocks)
 
 
-def pack_titanet(w: Dict[str, object], blocks: Sequence[Tuple[int, int, int, bool]]):
+def pack_titanet(w: Dict[str, object], blocks: Sequence[Tuple[int, int, int, bool]], precision: int = PRECISION_FP32):
     """-> (dims, blob float32 [n], offsets int64) in the order csrc/titanet.cu::tn_plan expects.  GEMM weights are stored as
-    bf16 head / remainder planes (two 16-bit values per float32 word) with the following BatchNorm folded in."""
+    bf16 head / remainder planes (two 16-bit values per float32 word) with the following BatchNorm folded in; with
+    ``precision = PRECISION_FP16`` the head entry is one fp16 plane (saturating) and the remainder entry a placeholder."""
     chunks, offsets, cursor = [], [], 0
 
     def add(a: np.ndarray):
@@ -74,6 +78,12 @@ def pack_titanet(w: Dict[str, object], blocks: Sequence[Tuple[int, int, int, boo
         cursor += a.size + pad
 
     def add_split(a: np.ndarray):
+        if precision == PRECISION_FP16:
+            h = np.clip(np.asarray(a, np.float32), -65504.0, 65504.0).astype(np.float16)
+            assert h.size % 2 == 0
+            add(h.reshape(-1).view(np.float32))
+            add(np.zeros(64, np.float32))
+            return
         hi, lo = _split16(np.asarray(a, np.float32), _cabi.SPLIT_BF16)
         add(hi)
         add(lo)
@@ -114,6 +124,7 @@ def pack_titanet(w: Dict[str, object], blocks: Sequence[Tuple[int, int, int, boo
     add(_np(w["decoder.emb_layers.0.1.bias"]) + We @ ce)
     dims = TitanetDims()
     dims.feat_in, dims.n_blocks, dims.att_ch, dims.emb = feat_in, len(blocks), att, We.shape[0]
+    dims.precision = int(precision)
     for b, (co, rep, k, res) in enumerate(blocks):
         dims.filters[b], dims.repeat[b], dims.kernel[b], dims.residual[b] = co, rep, k, int(res)
     return dims, np.concatenate(chunks), np.asarray(offsets, np.int64)
@@ -123,13 +134,19 @@ class TitaNetB200:
     """``state_dict``: NeMo EncDecSpeakerLabelModel names (encoder.encoder.*, decoder._pooling.*, decoder.emb_layers.*)."""
 
     def __init__(self, state_dict: Dict[str, object], device: Optional[torch.device] = None,
-                 blocks: Optional[Sequence[Tuple[int, int, int, bool]]] = None):
+                 blocks: Optional[Sequence[Tuple[int, int, int, bool]]] = None, precision: str = "fp16"):
+        """``precision``: "fp16" (default) runs the 1x1 convolutions / linear layers the way the reference does under
+        ``torch.cuda.amp.autocast()`` (word_based_diarization.py:102-105): fp16 operands, fp32 accumulation, one tensor-core pass;
+        "fp32" keeps bf16 head + remainder planes (three passes, fp32-grade: 2e-6 against the fp64 restatement)."""
         self.device = torch.device(device if device is not None else "cuda")
         if self.device.type != "cuda" or not torch.cuda.is_available():
             raise _cabi.NsfError("TitaNetB200 needs a CUDA device; there is no CPU path")
         self._lib = _cabi.load()
         self.blocks = tuple(blocks) if blocks is not None else infer_blocks(state_dict)
-        self.dims, blob, offsets = pack_titanet(state_dict, self.blocks)
+        if precision not in ("fp16", "fp32"):
+            raise _cabi.NsfError(f"TitaNetB200: precision must be 'fp16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        self.dims, blob, offsets = pack_titanet(state_dict, self.blocks, PRECISION_FP16 if precision == "fp16" else PRECISION_FP32)
         self._blob = torch.from_numpy(blob).to(self.device)
         self._offsets = offsets
         self._filters = torch.from_numpy(np.ascontiguousarray(mel_filterbank(self.dims.feat_in, SR, N_FFT).T)).to(self.device)   # [257][n_mels]

@@ -53,6 +53,11 @@ def test_library_argument_errors_without_gpu(N):
     td.filters[1], td.repeat[1], td.kernel[1], td.residual[1] = 1024, 3, 7, 1
     assert lib.nsf_titanet_num_offsets(C.byref(td)) == (4 * 1 + 2) + (4 * 3 + 2 + 3) + 11
     assert lib.nsf_titanet_workspace_bytes(C.byref(td), 8, 64) > 8 * 64 * 1024 * 4
+    td.precision = 1                                                       # fp16 operands: same blob entries
+    assert lib.nsf_titanet_num_offsets(C.byref(td)) == (4 * 1 + 2) + (4 * 3 + 2 + 3) + 11
+    td.precision = 2
+    assert lib.nsf_titanet_num_offsets(C.byref(td)) == 0
+    td.precision = 0
     td.kernel[1] = 8                                                       # even kernel: unsupported
     assert lib.nsf_titanet_num_offsets(C.byref(td)) == 0 and lib.nsf_titanet_workspace_bytes(C.byref(td), 8, 64) == 0
     assert lib.nsf_titanet_features(None, None, 1, 100, 16, None, 80, None, None, None, None, None) == -1

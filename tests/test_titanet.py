@@ -181,14 +181,18 @@ def test_titanet_features_vs_oracle(dev):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("blocks,att,emb,lens,tol", [
-    (SMALL, 32, 16, [8000, 48000, 4321, 24000, 16001, 12000], 2e-4),
-    (O.BLOCKS, 128, 192, [8000, 24000, 40000], 5e-4),                     # titanet-large dims
+@pytest.mark.parametrize("blocks,att,emb,lens,precision,tol", [
+    (SMALL, 32, 16, [8000, 48000, 4321, 24000, 16001, 12000], "fp32", 2e-4),
+    (O.BLOCKS, 128, 192, [8000, 24000, 40000], "fp32", 5e-4),             # titanet-large dims
+    # the default engine: fp16 operands, fp32 accumulation (the reference's autocast arithmetic): 2^-11 per operand
+    (SMALL, 32, 16, [8000, 48000, 4321, 24000, 16001, 12000], "fp16", 5e-3),
+    (O.BLOCKS, 128, 192, [8000, 24000, 40000], "fp16", 5e-3),
 ])
-def test_titanet_embedding_vs_oracle(dev, blocks, att, emb, lens, tol):
+def test_titanet_embedding_vs_oracle(dev, blocks, att, emb, lens, precision, tol):
     import notsofar_b200.titanet as T
     w = O.random_weights(5, blocks=blocks, att_ch=att, emb=emb)
-    model = T.TitaNetB200(w, dev)
+    model = T.TitaNetB200(w, dev, precision=precision)
+    assert model.precision == precision and model.dims.precision == (1 if precision == "fp16" else 0)
     rng = np.random.default_rng(4)
     crops = _crops(rng, lens)
     _, x, l = _run(model, crops, dev)
@@ -196,8 +200,11 @@ def test_titanet_embedding_vs_oracle(dev, blocks, att, emb, lens, tol):
     ref = O.embed(w, crops, blocks)
     assert e.shape == ref.shape == (len(lens), emb)
     errs = [rel_l2(e[i], ref[i]) for i in range(len(lens))]
-    print("titanet embedding rel err vs fp64 oracle", errs)
+    print(f"titanet embedding rel err vs fp64 oracle [{precision}]", errs)
     assert max(errs) < tol, errs
+    if precision == "fp16":
+        cos = [float(np.dot(e[i], ref[i]) / (np.linalg.norm(e[i]) * np.linalg.norm(ref[i]))) for i in range(len(lens))]
+        assert min(cos) > 0.9999, cos                                      # what the affinity matrix sees
     # batching must not change a crop's embedding (padding is masked everywhere): the same crop alone
     _, x1, l1 = _run(model, crops[:1], dev)
     e1 = model.embed(x1, l1).cpu().numpy()
@@ -314,7 +321,7 @@ def test_titanet_ragged_and_degenerate_crops(dev):
     import torch
     import notsofar_b200.titanet as T
     w = O.random_weights(3, blocks=SMALL, att_ch=32, emb=16)
-    model = T.TitaNetB200(w, dev)
+    model = T.TitaNetB200(w, dev, precision="fp32")
     rng = np.random.default_rng(9)
     lens = [0, 1, 100, 159, 160, 257, 1000, 8000, 47999]
     crops = _crops(rng, [max(n, 1) for n in lens])
