@@ -238,39 +238,54 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                 for (int cc = 0; cc < kA2Slots / 32; ++cc) {
                     uint32_t sv[32];
                     tmem_ld_32x32(tmem_base + lane_sel + (uint32_t)(kA2Slots * hh + 32 * cc), sv);
+                    if (kA2Slots * hh + 32 * (cc + 1) <= T) {         // warp-uniform: every key of the chunk exists (no masking)
 #pragma unroll
-                    for (int jx = 0; jx < 32; ++jx) {
-                        const int slot = 32 * cc + jx;
-                        const int t2 = kA2Slots * hh + slot;
-                        float val = (__uint_as_float(sv[jx]) + __uint_as_float(w[kA2Slots - 1 - slot])) * p.scale_log2e;
-                        val = (t2 < T) ? val : -INFINITY;
-                        w[kA2Slots - 1 - slot] = __float_as_uint(val);
-                        mx = fmaxf(mx, val);
+                        for (int jx = 0; jx < 32; ++jx) {
+                            const int slot = 32 * cc + jx;
+                            const float val = (__uint_as_float(sv[jx]) + __uint_as_float(w[kA2Slots - 1 - slot])) * p.scale_log2e;
+                            w[kA2Slots - 1 - slot] = __float_as_uint(val);
+                            mx = fmaxf(mx, val);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jx = 0; jx < 32; ++jx) {
+                            const int slot = 32 * cc + jx;
+                            const int t2 = kA2Slots * hh + slot;
+                            float val = (__uint_as_float(sv[jx]) + __uint_as_float(w[kA2Slots - 1 - slot])) * p.scale_log2e;
+                            val = (t2 < T) ? val : -INFINITY;
+                            w[kA2Slots - 1 - slot] = __float_as_uint(val);
+                            mx = fmaxf(mx, val);
+                        }
                     }
                 }
             }
-            xch_max[hh * 128 + r] = mx;
-            a2_named_bar_sync(1 + q, 32 * kA2Split);
-#pragma unroll
-            for (int o = 1; o < kA2Split; ++o) mx = fmaxf(mx, xch_max[((hh + o) % kA2Split) * 128 + r]);
+            // one exchange per row instead of two: every thread exponentiates against its OWN maximum and publishes (max, sum);
+            // the row total is sum_o sum_o 2^(max_o - M) with M the row maximum, and a thread's probabilities are
+            // e_i 2^(max_own - M) / total.  (The exponentials no longer wait for the other threads of the row.)
+            const float mref = mx == -INFINITY ? 0.f : mx;           // a part with no valid key (short segments): all zeros
             float sum = 0.f;
             if (warp_valid) {
 #pragma unroll
                 for (int i = 0; i < kA2Slots; ++i) {
-                    const float e = ex2_approx(__uint_as_float(w[i]) - mx);
+                    const float e = ex2_approx(__uint_as_float(w[i]) - mref);
                     w[i] = __float_as_uint(e);
                     sum += e;
                 }
             }
+            xch_max[hh * 128 + r] = mx;
             xch_sum[hh * 128 + r] = sum;
             a2_named_bar_sync(1 + q, 32 * kA2Split);
             {
-                // every thread of the row adds the partial sums in the same (part) order: identical totals
+                float M = xch_max[r];
+#pragma unroll
+                for (int o = 1; o < kA2Split; ++o) M = fmaxf(M, xch_max[o * 128 + r]);
+                // every thread of the row adds the rescaled partial sums in the same (part) order: identical totals
                 float tot = 0.f;
 #pragma unroll
-                for (int o = 0; o < kA2Split; ++o) tot += xch_sum[o * 128 + r];
-                sum = tot;
+                for (int o = 0; o < kA2Split; ++o) tot = fmaf(xch_sum[o * 128 + r], ex2_approx(xch_max[o * 128 + r] - M), tot);
+                sum = mx == -INFINITY ? 1.f : tot / ex2_approx(mref - M);   // p_i = e_i / sum (all e_i are zero for a part without keys)
             }
+            // the exchange slots are rewritten by the next item only after this item's p_ready / o_ready round trip
             if (warp_valid) {
                 const float inv = 1.f / sum;
                 // packed column j of this part holds keys kA2Slots hh + 2j (low half) and 2j + 1 (high half)
