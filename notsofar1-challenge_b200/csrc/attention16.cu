@@ -100,7 +100,10 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     // top of the window's second half (row block 0: the window fills the rest of tensor memory) -- only then does the next item's
     // second half of Bm have to wait until O has been read out
     const bool o_aliases = kA2ColB + 2 * nBh + 64 > 512;
-    const uint32_t col_o = o_aliases ? (uint32_t)kA2ColO : (uint32_t)(kA2ColB + 2 * nBh);
+    const uint32_t col_o = o_aliases ? (uint32_t)(kA2ColB + 2 * nBh - 64) : (uint32_t)(kA2ColB + 2 * nBh);
+    // Bm is issued in two pieces: nBmA window columns right behind the previous item's P V product, and -- only where O sits on the
+    // window's last 64 columns -- those 64 once O has been read out
+    const int nBmA = o_aliases ? 2 * nBh - 64 : 2 * nBh, nBmB = o_aliases ? 64 : 0;
 
     if (threadIdx.x == 0) {
         mbar_init(qk_full, 1); mbar_init(qk_empty, 1); mbar_init(v_full, 1); mbar_init(v_empty, 1); mbar_init(pe_full, 1);
@@ -141,14 +144,15 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
     } else if (warp == 1) {
         if (lane == 0 && first < p.n_bh) {
             // ===== MMA issuer
-            const uint32_t idesc_s = make_idesc_f16(192, 1), idesc_b = make_idesc_f16(nBh, 1), idesc_o = make_idesc_f16_bmn(64, 1);
-            mbar_wait(pe_full, 0);
-            // scores S = Q K^T into columns [0, 192) and the first half of the relative-position product Bm into [192, 192 + nBh):
-            // neither touches the output accumulator O of the previous item (columns [384, 448)), so they are issued right
-            // behind that item's P V product and run while the softmax warps still read its O; only the second half of Bm
-            // (columns [192 + nBh, 192 + 2 nBh), which cover O) waits for o_drained.
+            const uint32_t idesc_s = make_idesc_f16(192, 1), idesc_ba = make_idesc_f16(nBmA, 1), idesc_bb = make_idesc_f16(64, 1),
+                           idesc_o = make_idesc_f16_bmn(64, 1);
+            mbar_wait_spin(pe_full, 0);
+            // scores S = Q K^T into columns [0, 192) and the first nBmA columns of the relative-position product Bm: neither touches the
+            // output accumulator O of the previous item, so they are issued right behind that item's P V product and run while the
+            // softmax warps still read its O; only the window's last 64 columns -- where O sits when the window fills tensor
+            // memory (row block 0) -- wait for o_drained.
             auto issue_scores_and_bm = [&](uint32_t it_next, bool wait_drain, uint32_t drain_parity) {
-                mbar_wait(qk_full, it_next & 1);
+                mbar_wait_spin(qk_full, it_next & 1);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {                // d_k = 64 = 4 k-steps of 16
@@ -160,24 +164,26 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                     tcgen05_mma_f16(tmem_base, a_hi, bk_hi, idesc_s, 1);
                     const uint64_t bp_hi = make_smem_desc(pe_smem + ko), bp_lo = make_smem_desc(pe_smem + kA2PeHalf + ko);
                     const uint32_t d = tmem_base + kA2ColB;
-                    tcgen05_mma_f16(d, a_lo, bp_hi, idesc_b, ks != 0);
-                    tcgen05_mma_f16(d, a_hi, bp_lo, idesc_b, 1);
-                    tcgen05_mma_f16(d, a_hi, bp_hi, idesc_b, 1);
+                    tcgen05_mma_f16(d, a_lo, bp_hi, idesc_ba, ks != 0);
+                    tcgen05_mma_f16(d, a_hi, bp_lo, idesc_ba, 1);
+                    tcgen05_mma_f16(d, a_hi, bp_hi, idesc_ba, 1);
                 }
                 if (wait_drain) {
-                    mbar_wait(o_drained, drain_parity);         // the previous item's O has been read out of TMEM
+                    mbar_wait_spin(o_drained, drain_parity);         // the previous item's O has been read out of TMEM
                     tcgen05_fence_after();
                 }
+                if (nBmB > 0) {
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t ko = ks * 32;
-                    const uint64_t a_hi = make_smem_desc(q_smem + ko), a_lo = make_smem_desc(q_smem + kA2QHalf + ko);
-                    const uint32_t po = (uint32_t)nBh * 128u + ko;
-                    const uint64_t bp_hi = make_smem_desc(pe_smem + po), bp_lo = make_smem_desc(pe_smem + kA2PeHalf + po);
-                    const uint32_t d = tmem_base + kA2ColB + nBh;
-                    tcgen05_mma_f16(d, a_lo, bp_hi, idesc_b, ks != 0);
-                    tcgen05_mma_f16(d, a_hi, bp_lo, idesc_b, 1);
-                    tcgen05_mma_f16(d, a_hi, bp_hi, idesc_b, 1);
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint32_t ko = ks * 32;
+                        const uint64_t a_hi = make_smem_desc(q_smem + ko), a_lo = make_smem_desc(q_smem + kA2QHalf + ko);
+                        const uint32_t po = (uint32_t)nBmA * 128u + ko;
+                        const uint64_t bp_hi = make_smem_desc(pe_smem + po), bp_lo = make_smem_desc(pe_smem + kA2PeHalf + po);
+                        const uint32_t d = tmem_base + kA2ColB + nBmA;
+                        tcgen05_mma_f16(d, a_lo, bp_hi, idesc_bb, ks != 0);
+                        tcgen05_mma_f16(d, a_hi, bp_lo, idesc_bb, 1);
+                        tcgen05_mma_f16(d, a_hi, bp_hi, idesc_bb, 1);
+                    }
                 }
                 tcgen05_commit(qk_empty);
                 tcgen05_commit(s_ready);
@@ -185,10 +191,15 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             issue_scores_and_bm(0, false, 0);
             uint32_t it = 0;
             for (int bh = first; bh < p.n_bh; bh += stride, ++it) {
-                mbar_wait(p_ready, it & 1);                     // probabilities are in TMEM
-                mbar_wait(v_full, it & 1);
+                mbar_wait_spin(p_ready, it & 1);                     // probabilities are in TMEM
+                mbar_wait_spin(v_full, it & 1);
                 tcgen05_fence_after();
-                for (int j = 0; j < nks_pv; ++j) {
+                // straight-line issue (the trip count is a run-time value <= 12): descriptor arithmetic and the moves into uniform
+                // registers are hoisted ahead of the waits, the 36 MMAs go out back to back -- issued one by one from a rolled loop
+                // they took about as long to issue as to execute (N = 64: 32 tensor cycles each)
+#pragma unroll
+                for (int j = 0; j < 192 / 16; ++j) {
+                    if (j >= nks_pv) break;
                     const uint32_t vo = (uint32_t)j * 2048u;                         // 16 key rows of 128 bytes
                     const uint64_t bv_hi = make_smem_desc(v_smem + vo), bv_lo = make_smem_desc(v_smem + kA2VHalf + vo);
                     const uint32_t a_col = tmem_base + 8u * j;                       // 16 keys = 8 packed columns
