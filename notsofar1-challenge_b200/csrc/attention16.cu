@@ -146,13 +146,13 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             // ===== MMA issuer
             const uint32_t idesc_s = make_idesc_f16(192, 1), idesc_ba = make_idesc_f16(nBmA, 1), idesc_bb = make_idesc_f16(64, 1),
                            idesc_o = make_idesc_f16_bmn(64, 1);
-            mbar_wait_spin(pe_full, 0);
+            mbar_wait(pe_full, 0);
             // scores S = Q K^T into columns [0, 192) and the first nBmA columns of the relative-position product Bm: neither touches the
             // output accumulator O of the previous item, so they are issued right behind that item's P V product and run while the
             // softmax warps still read its O; only the window's last 64 columns -- where O sits when the window fills tensor
             // memory (row block 0) -- wait for o_drained.
             auto issue_scores_and_bm = [&](uint32_t it_next, bool wait_drain, uint32_t drain_parity) {
-                mbar_wait_spin(qk_full, it_next & 1);
+                mbar_wait(qk_full, it_next & 1);
                 tcgen05_fence_after();
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {                // d_k = 64 = 4 k-steps of 16
@@ -169,7 +169,7 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
                     tcgen05_mma_f16(d, a_hi, bp_hi, idesc_ba, 1);
                 }
                 if (wait_drain) {
-                    mbar_wait_spin(o_drained, drain_parity);         // the previous item's O has been read out of TMEM
+                    mbar_wait(o_drained, drain_parity);         // the previous item's O has been read out of TMEM
                     tcgen05_fence_after();
                 }
                 if (nBmB > 0) {
@@ -191,8 +191,8 @@ attn16_kernel(const __grid_constant__ CUtensorMap map_q_hi, const __grid_constan
             issue_scores_and_bm(0, false, 0);
             uint32_t it = 0;
             for (int bh = first; bh < p.n_bh; bh += stride, ++it) {
-                mbar_wait_spin(p_ready, it & 1);                     // probabilities are in TMEM
-                mbar_wait_spin(v_full, it & 1);
+                mbar_wait(p_ready, it & 1);                     // probabilities are in TMEM
+                mbar_wait(v_full, it & 1);
                 tcgen05_fence_after();
                 // straight-line issue (the trip count is a run-time value <= 12): descriptor arithmetic and the moves into uniform
                 // registers are hoisted ahead of the waits, the 36 MMAs go out back to back -- issued one by one from a rolled loop

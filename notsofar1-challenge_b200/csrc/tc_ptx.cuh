@@ -43,24 +43,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         }
     }
 }
-// Polling wait without the suspend hint, for the single thread that hands work between the pipelines (the MMA issuer): it reacts
-// to the phase flip within a poll instead of a wake-up, and one spinning thread costs little.
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (uint32_t n = 0;; ++n) {
-        uint32_t ok;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-        if (ok) return;
-        if ((n & 1023u) == 1023u && clock64() - t0 > 4000000000LL) {
-            printf("nsf tcgen05: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-            __trap();
-        }
-    }
-}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
