@@ -778,8 +778,9 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
         gemm_tc_kernel<MODE, TN, RB, E><<<grid, kTcThreads, Cfg::kSmemBytes, stream>>>(ma_hi, ma_lo, mb_hi, mb_lo, pv, tiles_m, tiles_n, (int)total); \
     } while (0)
     if constexpr ((MODE == 16 || MODE == 116) && TN == 256 && RB == 128) {
-    if (pv.vec8 && p.batch == 1 && sm_count() >= 2 && use_cta_pairs() &&
-        (p.epi == EPI_RESID || p.epi == EPI_QKV || p.epi == EPI_STORE || p.epi == EPI_RELU_SPLIT || (MODE == 116 && p.epi == EPI_GELU_SPLIT))) {
+    if ((pv.vec8 || (MODE == 16 && p.epi == EPI_MASK)) && p.batch == 1 && sm_count() >= 2 && use_cta_pairs() &&
+        (p.epi == EPI_RESID || p.epi == EPI_QKV || p.epi == EPI_STORE || p.epi == EPI_RELU_SPLIT || (MODE == 116 && p.epi == EPI_GELU_SPLIT) ||
+         (MODE == 16 && p.epi == EPI_MASK))) {
         // CTA pairs: B is staged in halves of 128 columns
         CUtensorMap mb2_hi, mb2_lo;
         if ((rc = make_tmap_kmajor16(&mb2_hi, p.B_hi, p.N, p.K, p.ldb, 1, 0, 128))) return rc;
@@ -799,7 +800,7 @@ static int launch_t(const GemmParams& p, cudaStream_t stream) {
             case EPI_QKV:        NSF_GEMM2_LAUNCH(EPI_QKV); break;
             case EPI_STORE:      NSF_GEMM2_LAUNCH(EPI_STORE); break;
             case EPI_RELU_SPLIT: NSF_GEMM2_LAUNCH(EPI_RELU_SPLIT); break;
-            default:             if constexpr (MODE == 116) { NSF_GEMM2_LAUNCH(EPI_GELU_SPLIT); } break;
+            default:             if constexpr (MODE == 116) { NSF_GEMM2_LAUNCH(EPI_GELU_SPLIT); } else { NSF_GEMM2_LAUNCH(EPI_MASK); } break;   // the mask head writes along rows
         }
 #undef NSF_GEMM2_LAUNCH
         return check_launch("gemm_tc2_kernel");
