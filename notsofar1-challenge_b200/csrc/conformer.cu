@@ -6,9 +6,9 @@
 //   (x += .5 FF; x += MHSA; x += Conv; x += .5 FF; LN), MultiHeadedAttention :57-92,
 //   ConvModule :113-127 (scalar 1x1 "pointwise" convs, GLU, depthwise k=33, BatchNorm eval, ReLU),
 //   FeedForward :146-150.
-// All matrix products go through gemm_launch (tcgen05 3xTF32 by default); everything else is fused
-// into a handful of streaming kernels here.  Activations that feed a GEMM are written "split"
-// (TF32 head + remainder, gemm_common.cuh).
+// All matrix products go through gemm_launch (default engine 2xBF16: tcgen05 kind::f16 on bf16 head + remainder planes, CTA pairs);
+// everything else is fused into a handful of streaming kernels here.  Activations that feed a GEMM are written "split" in the
+// engine's format (common.cuh SplitFmt); with the 2xBF16 engine two LayerNorms per block are folded into the GEMMs (ln_fold_rule).
 #include "gemm_common.cuh"
 #include <new>
 

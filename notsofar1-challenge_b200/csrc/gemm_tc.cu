@@ -1,4 +1,6 @@
-// tcgen05 GEMM engine for sm_100a: persistent, warp-specialised.
+// tcgen05 GEMM engine for sm_100a: persistent, warp-specialised.  Two kernels: gemm_tc_kernel (one CTA per tile, described first)
+// and gemm_tc2_kernel (CTA pairs, tcgen05.mma.cta_group::2 -- the default for the 16-bit engines' unbatched GEMMs, see the section
+// "CTA pairs" below); they share the epilogue code.
 //
 //   D[b][m][n] = sum_k A[b][m][k] B[b][n][k]          both operands K-major
 //
