@@ -46,7 +46,7 @@ __device__ __forceinline__ float atan2_poly(float y, float x) {
 
 // NITER = ceil(T / 32) register slots per lane (6 for the pipeline's T = 186: two CTAs per SM instead of one)
 template <int C, int NITER>
-__global__ void __launch_bounds__(kFeatBinsPerCta * 32, NITER <= 6 ? 2 : 1)
+__global__ void __launch_bounds__(kFeatBinsPerCta * 32, NITER <= 6 ? 4 : 2)
 css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_valid, int64_t seg_first, int T, int hop,
                     const float* __restrict__ in_bias, const float* __restrict__ in_scale,
                     float* __restrict__ feat, float* __restrict__ feat_lo, int64_t ldf, int fmt) {
@@ -60,60 +60,63 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
     if (f < kBins) {
         const bool edge_bin = (f == 0 || f == kBins - 1);
         const float2* Xf = X + ((size_t)f * T_long + st) * C;
-        float mag0[NITER];
-        float yr[NITER][C - 1 > 0 ? C - 1 : 1], yi[NITER][C - 1 > 0 ? C - 1 : 1];
-        float s_mag = 0.f;
-        float s_yr[C - 1 > 0 ? C - 1 : 1], s_yi[C - 1 > 0 ? C - 1 : 1];
+        constexpr int CM = C - 1 > 0 ? C - 1 : 1;
+        // cos / sin of the phase differences and the floored magnitude of one frame.  Evaluated twice per frame -- once for the
+        // time means, once for the features -- instead of keeping 2 x 6 x NITER values in registers: 120 -> ~64 registers, four
+        // CTAs per SM instead of two for a kernel that is bound by the latency of its own dependent chains.
+        auto frame = [&](int t, float& fm, float (&cr)[CM], float (&sr)[CM]) {
+            float2 x[C];
+            const bool valid = (st + t) < T_valid;           // zero-padded tail of the last segment, css.py:185-190
 #pragma unroll
-        for (int m = 0; m < C - 1; ++m) { s_yr[m] = 0.f; s_yi[m] = 0.f; }
+            for (int c = 0; c < C; ++c) x[c] = valid ? __ldg(Xf + (size_t)t * C + c) : make_float2(0.f, 0.f);
+            // |X_0| and 1 / |X_0| from one MUFU.RSQ (2 ulp; the IEEE sqrt + division pair is ~16 instructions per channel)
+            const float p0sq = x[0].x * x[0].x + x[0].y * x[0].y;
+            const float inv0r = rsqrtf(p0sq);
+            const float a0 = p0sq > 0.f ? p0sq * inv0r : 0.f;
+            fm = fmaxf(a0, kEps32);
+            if (edge_bin) {
+                // literal replay: phase in {0, -3.1415925f} (torch angle of (re<0, tiny negative imag))
+                const float p0 = (x[0].x < 0.f) ? -3.1415925f : 0.f;
+#pragma unroll
+                for (int m = 0; m < C - 1; ++m) {
+                    const float pm = (x[m + 1].x < 0.f) ? -3.1415925f : 0.f;
+                    const float d = pm - p0;
+                    // cosf/sinf of {0, +-3.1415925f}: exact table of the correctly rounded values
+                    cr[m] = (d == 0.f) ? 1.f : -1.f;
+                    sr[m] = (d == 0.f) ? 0.f : (d > 0.f ? 1.509958e-07f : -1.509958e-07f);
+                }
+            } else {
+                // unit phasor of X_0 (angle(0) == 0 -> (1, 0))
+                const float inv0 = a0 > 0.f ? inv0r : 0.f;
+                const float u0x = a0 > 0.f ? x[0].x * inv0 : 1.f, u0y = x[0].y * inv0;
+#pragma unroll
+                for (int m = 0; m < C - 1; ++m) {
+                    const float am = x[m + 1].x * x[m + 1].x + x[m + 1].y * x[m + 1].y;      // |X_m|^2: only its sign test and rsqrt are used
+                    const float invm = am > 0.f ? rsqrtf(am) : 0.f;
+                    const float umx = am > 0.f ? x[m + 1].x * invm : 1.f, umy = x[m + 1].y * invm;
+                    // u_m * conj(u_0) = exp(i (angle_m - angle_0))
+                    cr[m] = umx * u0x + umy * u0y;
+                    sr[m] = umy * u0x - umx * u0y;
+                }
+            }
+        };
+        float mag0[NITER];
+        float s_mag = 0.f;
+        float s_yr[CM], s_yi[CM];
+#pragma unroll
+        for (int m = 0; m < CM; ++m) { s_yr[m] = 0.f; s_yi[m] = 0.f; }
 #pragma unroll
         for (int it = 0; it < NITER; ++it) {
             const int t = it * 32 + lane;
             mag0[it] = 0.f;
             if (t < T) {
-                float2 x[C];
-                const bool valid = (st + t) < T_valid;       // zero-padded tail of the last segment, css.py:185-190
+                float cr[CM], sr[CM];
+                frame(t, mag0[it], cr, sr);
+                s_mag += mag0[it];
 #pragma unroll
-                for (int c = 0; c < C; ++c) x[c] = valid ? __ldg(Xf + (size_t)t * C + c) : make_float2(0.f, 0.f);
-                // |X_0| and 1 / |X_0| from one MUFU.RSQ (2 ulp; the IEEE sqrt + division pair is ~16 instructions per channel)
-                const float p0sq = x[0].x * x[0].x + x[0].y * x[0].y;
-                const float inv0r = rsqrtf(p0sq);
-                const float a0 = p0sq > 0.f ? p0sq * inv0r : 0.f;
-                const float fm = fmaxf(a0, kEps32);
-                mag0[it] = fm;
-                s_mag += fm;
-                if (edge_bin) {
-                    // literal replay: phase in {0, -3.1415925f} (torch angle of (re<0, tiny negative imag))
-                    const float p0 = (x[0].x < 0.f) ? -3.1415925f : 0.f;
-#pragma unroll
-                    for (int m = 0; m < C - 1; ++m) {
-                        const float pm = (x[m + 1].x < 0.f) ? -3.1415925f : 0.f;
-                        const float d = pm - p0;
-                        // cosf/sinf of {0, +-3.1415925f}: exact table of the correctly rounded values
-                        const float cr = (d == 0.f) ? 1.f : -1.f;
-                        const float sr = (d == 0.f) ? 0.f : (d > 0.f ? 1.509958e-07f : -1.509958e-07f);
-                        yr[it][m] = cr; yi[it][m] = sr;
-                        s_yr[m] += cr; s_yi[m] += sr;
-                    }
-                } else {
-                    // unit phasor of X_0 (angle(0) == 0 -> (1, 0))
-                    const float inv0 = a0 > 0.f ? inv0r : 0.f;
-                    const float u0x = a0 > 0.f ? x[0].x * inv0 : 1.f, u0y = x[0].y * inv0;
-#pragma unroll
-                    for (int m = 0; m < C - 1; ++m) {
-                        const float am = x[m + 1].x * x[m + 1].x + x[m + 1].y * x[m + 1].y;      // |X_m|^2: only its sign test and rsqrt are used
-                        const float invm = am > 0.f ? rsqrtf(am) : 0.f;
-                        const float umx = am > 0.f ? x[m + 1].x * invm : 1.f, umy = x[m + 1].y * invm;
-                        // u_m * conj(u_0) = exp(i (angle_m - angle_0))
-                        const float cr = umx * u0x + umy * u0y;
-                        const float sr = umy * u0x - umx * u0y;
-                        yr[it][m] = cr; yi[it][m] = sr;
-                        s_yr[m] += cr; s_yi[m] += sr;
-                    }
-                }
+                for (int m = 0; m < C - 1; ++m) { s_yr[m] += cr[m]; s_yi[m] += sr[m]; }
             }
         }
-        const float invT = 1.f / (float)T;
         const float mean = warp_sum(s_mag) / (float)T;
         float ssq = 0.f;
 #pragma unroll
@@ -123,22 +126,23 @@ css_features_kernel(const float2* __restrict__ X, int64_t T_long, int64_t T_vali
         }
         const float var = warp_sum(ssq) / (float)(T - 1);       // unbiased, torch.std default
         const float rstd = 1.f / (sqrtf(var) + kEps32);
-        float m_yr[C - 1 > 0 ? C - 1 : 1], m_yi[C - 1 > 0 ? C - 1 : 1];
+        float m_yr[CM], m_yi[CM];
 #pragma unroll
         for (int m = 0; m < C - 1; ++m) {
             m_yr[m] = warp_sum(s_yr[m]) / (float)T;
             m_yi[m] = warp_sum(s_yi[m]) / (float)T;
         }
-        (void)invT;
-#pragma unroll
+#pragma unroll 1
         for (int it = 0; it < NITER; ++it) {
             const int t = it * 32 + lane;
             if (t < T) {
+                float fm, cr[CM], sr[CM];
+                frame(t, fm, cr, sr);                             // the same arithmetic as in the first pass: identical values
                 float* o = tile + ((size_t)t * C) * kFeatBinsPerCta + warp;
-                o[0] = (mag0[it] - mean) * rstd;
+                o[0] = (fm - mean) * rstd;
 #pragma unroll
                 for (int m = 0; m < C - 1; ++m)
-                    o[(m + 1) * kFeatBinsPerCta] = atan2_poly(yi[it][m] - m_yi[m], yr[it][m] - m_yr[m]);
+                    o[(m + 1) * kFeatBinsPerCta] = atan2_poly(sr[m] - m_yi[m], cr[m] - m_yr[m]);
             }
         }
     }
