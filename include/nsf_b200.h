@@ -173,6 +173,10 @@ int nsf_segment_power_norm(float* Y, int n_spk, const float* X, int64_t T_long, 
  * itself runs on the host. */
 int nsf_pit_cost(const void* in, int input_kind, int loss_kind, int n_seg, int n_ch_total, int n_spk,
                  int n_bins, int T, int overlap, float* cost, void* stream);
+/* The same for segments [seg_begin, seg_end) only (`in` and `cost` still address segment 0; segment seg_begin - 1 must exist):
+ * the costs of a chunk of segments as soon as its masks are there, while later chunks are still in the network. */
+int nsf_pit_cost_range(const void* in, int input_kind, int loss_kind, int seg_begin, int seg_end, int n_ch_total, int n_spk,
+                       int n_bins, int T, int overlap, float* cost, void* stream);
 
 /* Weighted overlap-add of the permuted segment masks (css.py:254-299) and the activity mean
  * (css.py:304).  seg_w [n_seg][T] f32 trapezoid weights (calc_segment_weight css.py:341-390, rows
@@ -199,6 +203,21 @@ int nsf_stitch_stft(const float* Y, const int32_t* perms, const float* seg_w, co
  * g = sqrt(hann_periodic)/16; no one-sided doubling, no window-sum normalisation.
  * S_st [n_streams][T_long][F] c64 -> wav [n_streams][(T_long-1)*256+512] f32. */
 int nsf_istft(const float* S_st, int n_streams, int64_t T_long, float* wav, void* stream);
+/* Hops (256-sample blocks of the output) [hop_begin, hop_end) only; reads frames hop_begin-1 .. hop_end-1.  hop_begin must be a
+ * multiple of 8 (the kernel's tile: the launch then pairs frames, and rounds, exactly like nsf_istft). */
+int nsf_istft_range(const float* S_st, int n_streams, int64_t T_long, float* wav, int64_t hop_begin, int64_t hop_end, void* stream);
+
+/* Progressive tail of separate_and_stitch (css.py:287-338 behind the permutation chain): nsf_stitch_masks, nsf_activity,
+ * nsf_stitch_stft and nsf_istft restricted to what became final when the segments [seg_prev, seg_done) were added to
+ * [0, seg_prev) -- every stage is local in time, so the calls for seg_done = s_1 < s_2 < ... < n_seg together write bit for bit
+ * what the four whole-recording calls write.  perms must hold the rows of segments < seg_done; all buffers are the
+ * whole-recording ones (same layouts as above).  hops_written (host, int64[2]) receives the range of waveform hops
+ * (256-sample blocks of every stream of wav) this call produced: the caller can start their device -> host copy while later
+ * segments are still in the mask network. */
+int nsf_stitch_progress(const float* masks, int n_ch_total, const float* Y, const int32_t* perms, const float* seg_w,
+                        const float* wsum, int n_seg, int seg_prev, int seg_done, int n_spk, int n_bins, int T, int hop,
+                        int64_t T_long, float th, int dil, int ero, float* mask_st, float* activity, uint8_t* act_b,
+                        uint8_t* tmp, uint8_t* act_final, float* S_st, float* wav, int64_t* hops_written, void* stream);
 
 /* File boundary.  Replaces write_wav's peak normalisation (utils/audio_utils.py:44-45) and
  * libsndfile's float -> PCM_16 conversion: q = rint(x * 0.99 / (max|x| + 1e-7) * 32767).

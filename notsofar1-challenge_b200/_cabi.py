@@ -50,10 +50,14 @@ SIGNATURES = {
     "nsf_mvdr_utterance_workspace_bytes": (i64, [i32, i64, i32]),
     "nsf_mvdr_utterance": (i32, [c_f32p, i32, i32, c_f32p, i64, i32, i32, C.c_float, c_f32p, C.c_void_p, i64, C.c_void_p]),
     "nsf_pit_cost": (i32, [C.c_void_p, i32, i32, i32, i32, i32, i32, i32, i32, c_f32p, C.c_void_p]),
+    "nsf_pit_cost_range": (i32, [C.c_void_p, i32, i32, i32, i32, i32, i32, i32, i32, i32, c_f32p, C.c_void_p]),
     "nsf_stitch_masks": (i32, [c_f32p, i32, C.c_void_p, c_f32p, c_f32p, i32, i32, i32, i32, i32, i64, c_f32p, c_f32p, C.c_void_p]),
     "nsf_activity": (i32, [c_f32p, i64, i32, C.c_float, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsf_stitch_stft": (i32, [c_f32p, C.c_void_p, c_f32p, c_f32p, C.c_void_p, i32, i32, i32, i32, i32, i64, c_f32p, C.c_void_p]),
     "nsf_istft": (i32, [c_f32p, i32, i64, c_f32p, C.c_void_p]),
+    "nsf_istft_range": (i32, [c_f32p, i32, i64, c_f32p, i64, i64, C.c_void_p]),
+    "nsf_stitch_progress": (i32, [c_f32p, i32, c_f32p, C.c_void_p, c_f32p, c_f32p, i32, i32, i32, i32, i32, i32, i32, i64, C.c_float, i32, i32,
+                                  c_f32p, c_f32p, C.c_void_p, C.c_void_p, C.c_void_p, c_f32p, c_f32p, C.POINTER(C.c_int64), C.c_void_p]),
     "nsf_peaknorm_pcm16": (i32, [c_f32p, i32, i64, c_f32p, C.c_void_p, C.c_void_p]),
     "nsf_pcm16_to_float_interleaved": (i32, [C.c_void_p, i32, i64, c_f32p, C.c_void_p]),
     "nsf_attention_test_workspace_bytes": (i64, [i32, i32, i32, i32]),

@@ -154,7 +154,7 @@ struct IstftSmem {
 // transform: u1 + i u2 = IDFT(Hs1 + i Hs2), Hs = Hermitian-symmetrised half spectrum (so that the
 // real part of the one-sided sum of feature.py:157-162 falls out without doubling).
 __global__ void __launch_bounds__(kIstftThreads, 2)
-istft_kernel(const float2* __restrict__ S, int64_t T_long, float* __restrict__ wav, int64_t n_out) {
+istft_kernel(const float2* __restrict__ S, int64_t T_long, float* __restrict__ wav, int64_t n_out, int64_t hop_begin, int64_t hop_end) {
     __shared__ IstftSmem sm;
     const int tid = threadIdx.x;
     for (int i = tid; i < 512; i += kIstftThreads) {
@@ -162,7 +162,7 @@ istft_kernel(const float2* __restrict__ S, int64_t T_long, float* __restrict__ w
         sm.win[i] = g_sqrt_hann16[i];
     }
     const int stream_id = blockIdx.y;
-    const int64_t t0 = (int64_t)blockIdx.x * kIstftTT;
+    const int64_t t0 = hop_begin + (int64_t)blockIdx.x * kIstftTT;
     const float2* Ss = S + (size_t)stream_id * T_long * kBins;
     float* ws = wav + (size_t)stream_id * n_out;
     __syncthreads();
@@ -204,11 +204,10 @@ istft_kernel(const float2* __restrict__ S, int64_t T_long, float* __restrict__ w
     }
     __syncthreads();
     // overlap-add: hop j (samples 256*(t0+j) ..) = first half of frame t0+j (slot j+1) + second half of frame t0+j-1 (slot j)
-    const int64_t n_hops_total = T_long + 1;     // n_out / 256
     for (int idx = tid; idx < kIstftTT * 256; idx += kIstftThreads) {
         const int j = idx >> 8, m = idx & 255;
         const int64_t hop_idx = t0 + j;
-        if (hop_idx >= n_hops_total) break;
+        if (hop_idx >= hop_end) break;
         // order of the two addends follows conv_transpose1d's accumulation over t (older frame first)
         float acc = 0.f;
         if (hop_idx - 1 >= 0) acc += sm.frames[j][256 + m];
@@ -244,15 +243,25 @@ extern "C" int nsf_stft_mc(const float* x, int64_t n_samples, int n_ch, float* X
     return check_launch("stft_mc_kernel");
 }
 
-extern "C" int nsf_istft(const float* S_st, int n_streams, int64_t T_long, float* wav, void* stream) {
+extern "C" int nsf_istft_range(const float* S_st, int n_streams, int64_t T_long, float* wav, int64_t hop_begin, int64_t hop_end,
+                               void* stream) {
     NSF_REQUIRE(S_st && wav, "nsf_istft: null pointer");
     NSF_REQUIRE(n_streams >= 1 && T_long >= 1, "nsf_istft: bad sizes");
+    NSF_REQUIRE(hop_begin >= 0 && hop_begin % kIstftTT == 0 && hop_end <= T_long + 1,
+                "nsf_istft_range: hops [%lld, %lld) of %lld (the first must be a multiple of %d)", (long long)hop_begin, (long long)hop_end,
+                (long long)(T_long + 1), kIstftTT);
+    if (hop_end <= hop_begin) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
     int rc = ensure_tables(s);
     if (rc) return rc;
     const int64_t n_out = (T_long - 1) * kHop + kFrame;
-    dim3 grid((unsigned)ceil_div64(T_long + 1, kIstftTT), (unsigned)n_streams);
-    ProfScope prof(PROF_ISTFT, (double)T_long * n_streams * (kBins * 8.0 + kHop * 4.0), s);
-    istft_kernel<<<grid, kIstftThreads, 0, s>>>(reinterpret_cast<const float2*>(S_st), T_long, wav, n_out);
+    dim3 grid((unsigned)ceil_div64(hop_end - hop_begin, kIstftTT), (unsigned)n_streams);
+    ProfScope prof(PROF_ISTFT, (double)(hop_end - hop_begin) * n_streams * (kBins * 8.0 + kHop * 4.0), s);
+    istft_kernel<<<grid, kIstftThreads, 0, s>>>(reinterpret_cast<const float2*>(S_st), T_long, wav, n_out, hop_begin, hop_end);
     return check_launch("istft_kernel");
+}
+
+extern "C" int nsf_istft(const float* S_st, int n_streams, int64_t T_long, float* wav, void* stream) {
+    NSF_REQUIRE(T_long >= 1, "nsf_istft: bad sizes");
+    return nsf_istft_range(S_st, n_streams, T_long, wav, 0, T_long + 1, stream);
 }

@@ -13,8 +13,8 @@ constexpr int kMaxSpk = 4;
 // cost[i][a][b] = mean_{f, t < ov} loss(left_a[f][T-ov+t], right_b[f][t]); left = segment i-1, right = segment i.
 template <int INPUT_KIND, int LOSS_KIND>
 __global__ void __launch_bounds__(256)
-pit_cost_kernel(const void* __restrict__ in, int n_ch_total, int n_spk, int n_bins, int T, int ov, float* __restrict__ cost) {
-    const int i = blockIdx.x;          // segment index, >= 1 does work
+pit_cost_kernel(const void* __restrict__ in, int n_ch_total, int n_spk, int n_bins, int T, int ov, float* __restrict__ cost, int seg_begin) {
+    const int i = seg_begin + blockIdx.x;          // segment index, >= 1 does work
     __shared__ double red[8][kMaxSpk * kMaxSpk];
     double acc[kMaxSpk][kMaxSpk];
 #pragma unroll
@@ -76,10 +76,10 @@ pit_cost_kernel(const void* __restrict__ in, int n_ch_total, int n_spk, int n_bi
 __global__ void __launch_bounds__(256)
 stitch_masks_kernel(const float* __restrict__ masks, int n_ch_total, const int32_t* __restrict__ perms,
                     const float* __restrict__ seg_w, const float* __restrict__ wsum, int n_seg, int n_spk, int n_bins,
-                    int T, int hop, int64_t T_long, float* __restrict__ mask_st) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                    int T, int hop, int64_t T_long, float* __restrict__ mask_st, int64_t t_begin, int64_t t_end) {
+    const int64_t t = t_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int f = blockIdx.y;
-    if (t >= T_long) return;
+    if (t >= t_end) return;
     int64_t i_min = (t - T + 1 + hop - 1) / hop;      // ceil((t-T+1)/hop) for positive numerator
     if (t - T + 1 <= 0) i_min = 0;
     int64_t i_max = t / hop;
@@ -106,9 +106,10 @@ stitch_masks_kernel(const float* __restrict__ masks, int n_ch_total, const int32
 
 // activity[t][k] = mean_f mask_st[f][t][k]   (css.py:304)
 __global__ void __launch_bounds__(256)
-activity_mean_kernel(const float* __restrict__ mask_st, int n_bins, int64_t n_tk, float* __restrict__ activity) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // t * n_spk + k
-    if (j >= n_tk) return;
+activity_mean_kernel(const float* __restrict__ mask_st, int n_bins, int64_t n_tk, float* __restrict__ activity, int64_t j_begin,
+                     int64_t j_end) {
+    const int64_t j = j_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // t * n_spk + k
+    if (j >= j_end) return;
     double s = 0.0;
     for (int f = 0; f < n_bins; ++f) s += (double)__ldg(mask_st + (size_t)f * n_tk + j);
     activity[j] = (float)(s / n_bins);
@@ -118,9 +119,9 @@ activity_mean_kernel(const float* __restrict__ mask_st, int n_bins, int64_t n_tk
 // act_b = activity >= th ; tmp = dilate(act_b, dil) (zero padding)
 __global__ void __launch_bounds__(256)
 activity_threshold_dilate_kernel(const float* __restrict__ activity, int64_t T_long, int n_spk, float th, int dil,
-                                 uint8_t* __restrict__ act_b, uint8_t* __restrict__ tmp) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= T_long * n_spk) return;
+                                 uint8_t* __restrict__ act_b, uint8_t* __restrict__ tmp, int64_t j_begin, int64_t j_end) {
+    const int64_t j = j_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j_end) return;
     const int64_t t = j / n_spk;
     const int k = (int)(j - t * n_spk);
     act_b[j] = __ldg(activity + j) >= th;
@@ -133,9 +134,10 @@ activity_threshold_dilate_kernel(const float* __restrict__ activity, int64_t T_l
 }
 // act_final = erode(tmp, ero) (one padding)
 __global__ void __launch_bounds__(256)
-activity_erode_kernel(const uint8_t* __restrict__ tmp, int64_t T_long, int n_spk, int ero, uint8_t* __restrict__ act_final) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= T_long * n_spk) return;
+activity_erode_kernel(const uint8_t* __restrict__ tmp, int64_t T_long, int n_spk, int ero, uint8_t* __restrict__ act_final,
+                      int64_t j_begin, int64_t j_end) {
+    const int64_t j = j_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= j_end) return;
     const int64_t t = j / n_spk;
     const int k = (int)(j - t * n_spk);
     int64_t lo = t - ero, hi = t + ero;
@@ -152,14 +154,14 @@ activity_erode_kernel(const uint8_t* __restrict__ tmp, int64_t T_long, int n_spk
 __global__ void __launch_bounds__(256)
 stitch_stft_kernel(const float2* __restrict__ Y, const int32_t* __restrict__ perms, const float* __restrict__ seg_w,
                    const float* __restrict__ wsum, const uint8_t* __restrict__ act_final, int n_seg, int n_spk,
-                   int n_bins, int T, int hop, int64_t T_long, float2* __restrict__ S_st) {
+                   int n_bins, int T, int hop, int64_t T_long, float2* __restrict__ S_st, int64_t t_begin, int64_t t_end) {
     __shared__ float2 tile[kMaxSpk][32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
-    const int64_t t0 = (int64_t)blockIdx.x * 32;
+    const int64_t t0 = t_begin + (int64_t)blockIdx.x * 32;
     const int f0 = blockIdx.y * 32;
     {
         const int64_t t = t0 + tx;
-        if (t < T_long) {
+        if (t < t_end) {
             int64_t i_min = (t - T + 1 <= 0) ? 0 : (t - T + 1 + hop - 1) / hop;
             int64_t i_max = t / hop;
             if (i_max > n_seg - 1) i_max = n_seg - 1;
@@ -197,7 +199,7 @@ stitch_stft_kernel(const float2* __restrict__ Y, const int32_t* __restrict__ per
         if (f < n_bins) {
             for (int tyy = ty; tyy < 32; tyy += 8) {
                 const int64_t t = t0 + tyy;
-                if (t >= T_long) break;
+                if (t >= t_end) break;
 #pragma unroll
                 for (int k = 0; k < kMaxSpk; ++k)
                     if (k < n_spk) S_st[((size_t)k * T_long + t) * n_bins + f] = tile[k][tx][tyy];
@@ -265,21 +267,55 @@ extern "C" int nsf_pcm16_to_float_interleaved(const int16_t* pcm, int n_ch, int6
     return check_launch("pcm16_interleave_kernel");
 }
 
-extern "C" int nsf_pit_cost(const void* in, int input_kind, int loss_kind, int n_seg, int n_ch_total, int n_spk,
-                            int n_bins, int T, int overlap, float* cost, void* stream) {
+extern "C" int nsf_pit_cost_range(const void* in, int input_kind, int loss_kind, int seg_begin, int seg_end, int n_ch_total, int n_spk,
+                                  int n_bins, int T, int overlap, float* cost, void* stream) {
     NSF_REQUIRE(in && cost, "nsf_pit_cost: null pointer");
+    NSF_REQUIRE(seg_begin >= 0, "nsf_pit_cost: seg_begin=%d", seg_begin);
+    const int n_seg = seg_end;
     NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && n_ch_total >= n_spk, "nsf_pit_cost: n_spk=%d", n_spk);
     NSF_REQUIRE(overlap >= 1 && overlap <= T, "nsf_pit_cost: overlap=%d T=%d", overlap, T);
     NSF_REQUIRE((input_kind == 0 || input_kind == 1) && (loss_kind == 0 || loss_kind == 1), "nsf_pit_cost: bad kind");
-    if (n_seg <= 0) return NSF_OK;
+    if (seg_end <= seg_begin) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    ProfScope prof(PROF_PIT, (double)(n_seg - 1) * n_bins * overlap * 2.0 * n_spk * (input_kind == 0 ? 4.0 : 8.0), s);
-    if (input_kind == 0 && loss_kind == 0) pit_cost_kernel<0, 0><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
-    else if (input_kind == 0) pit_cost_kernel<0, 1><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
-    else if (loss_kind == 0) pit_cost_kernel<1, 0><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
-    else pit_cost_kernel<1, 1><<<n_seg, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost);
+    ProfScope prof(PROF_PIT, (double)(n_seg - max(seg_begin, 1)) * n_bins * overlap * 2.0 * n_spk * (input_kind == 0 ? 4.0 : 8.0), s);
+    if (input_kind == 0 && loss_kind == 0) pit_cost_kernel<0, 0><<<seg_end - seg_begin, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost, seg_begin);
+    else if (input_kind == 0) pit_cost_kernel<0, 1><<<seg_end - seg_begin, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost, seg_begin);
+    else if (loss_kind == 0) pit_cost_kernel<1, 0><<<seg_end - seg_begin, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost, seg_begin);
+    else pit_cost_kernel<1, 1><<<seg_end - seg_begin, 256, 0, s>>>(in, n_ch_total, n_spk, n_bins, T, overlap, cost, seg_begin);
     return check_launch("pit_cost_kernel");
 }
+
+extern "C" int nsf_pit_cost(const void* in, int input_kind, int loss_kind, int n_seg, int n_ch_total, int n_spk,
+                            int n_bins, int T, int overlap, float* cost, void* stream) {
+    return nsf_pit_cost_range(in, input_kind, loss_kind, 0, n_seg, n_ch_total, n_spk, n_bins, T, overlap, cost, stream);
+}
+
+namespace {
+// The stages behind the permutation chain on a frame range (each of them is frame-local on global indices, so a
+// range call writes exactly what the whole-recording call writes there).
+int stitch_masks_range(const float* masks, int n_ch_total, const int32_t* perms, const float* seg_w, const float* wsum, int n_seg,
+                       int n_spk, int n_bins, int T, int hop, int64_t T_long, float* mask_st, float* activity, int64_t t0, int64_t t1,
+                       cudaStream_t s) {
+    if (t1 <= t0) return NSF_OK;
+    dim3 grid((unsigned)ceil_div64(t1 - t0, 256), n_bins);
+    ProfScope prof(PROF_STITCH, (double)(t1 - t0) * n_bins * n_spk * 4.0 * ((double)T / hop + 2.0), s);
+    stitch_masks_kernel<<<grid, 256, 0, s>>>(masks, n_ch_total, perms, seg_w, wsum, n_seg, n_spk, n_bins, T, hop, T_long, mask_st, t0, t1);
+    int rc = check_launch("stitch_masks_kernel");
+    if (rc) return rc;
+    activity_mean_kernel<<<(unsigned)ceil_div64((t1 - t0) * n_spk, 256), 256, 0, s>>>(mask_st, n_bins, T_long * n_spk, activity,
+                                                                                      t0 * n_spk, t1 * n_spk);
+    return check_launch("activity_mean_kernel");
+}
+int stitch_stft_range(const float* Y, const int32_t* perms, const float* seg_w, const float* wsum, const uint8_t* act_final, int n_seg,
+                      int n_spk, int n_bins, int T, int hop, int64_t T_long, float* S_st, int64_t t0, int64_t t1, cudaStream_t s) {
+    if (t1 <= t0) return NSF_OK;
+    dim3 grid((unsigned)ceil_div64(t1 - t0, 32), ceil_div(n_bins, 32));
+    ProfScope prof(PROF_STITCH, (double)(t1 - t0) * n_bins * n_spk * 8.0 * ((double)T / hop + 1.0), s);
+    stitch_stft_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float2*>(Y), perms, seg_w, wsum, act_final, n_seg, n_spk, n_bins, T,
+                                            hop, T_long, reinterpret_cast<float2*>(S_st), t0, t1);
+    return check_launch("stitch_stft_kernel");
+}
+}  // namespace
 
 extern "C" int nsf_stitch_masks(const float* masks, int n_ch_total, const int32_t* perms, const float* seg_w,
                                 const float* wsum, int n_seg, int n_spk, int n_bins, int T, int hop, int64_t T_long,
@@ -288,15 +324,8 @@ extern "C" int nsf_stitch_masks(const float* masks, int n_ch_total, const int32_
     NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && n_ch_total >= n_spk && hop >= 1 && T >= 1, "nsf_stitch_masks: bad sizes");
     if (T_long <= 0) return NSF_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    dim3 grid((unsigned)ceil_div64(T_long, 256), n_bins);
-    const double contrib = (double)T / hop;      // segments contributing to one output frame
-    ProfScope prof(PROF_STITCH, (double)T_long * n_bins * n_spk * 4.0 * (contrib + 2.0), s);
-    stitch_masks_kernel<<<grid, 256, 0, s>>>(masks, n_ch_total, perms, seg_w, wsum, n_seg, n_spk, n_bins, T, hop, T_long, mask_st);
-    int rc = check_launch("stitch_masks_kernel");
-    if (rc) return rc;
-    const int64_t n_tk = T_long * n_spk;
-    activity_mean_kernel<<<(unsigned)ceil_div64(n_tk, 256), 256, 0, s>>>(mask_st, n_bins, n_tk, activity);
-    return check_launch("activity_mean_kernel");
+    return stitch_masks_range(masks, n_ch_total, perms, seg_w, wsum, n_seg, n_spk, n_bins, T, hop, T_long, mask_st, activity, 0, T_long,
+                              (cudaStream_t)stream);
 }
 
 extern "C" int nsf_activity(const float* activity, int64_t T_long, int n_spk, float th, int dil, int ero,
@@ -307,10 +336,10 @@ extern "C" int nsf_activity(const float* activity, int64_t T_long, int n_spk, fl
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t n = T_long * n_spk;
     ProfScope prof(PROF_ACTIVITY, (double)n * 7.0, s);
-    activity_threshold_dilate_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(activity, T_long, n_spk, th, dil, act_b, tmp);
+    activity_threshold_dilate_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(activity, T_long, n_spk, th, dil, act_b, tmp, 0, n);
     int rc = check_launch("activity_threshold_dilate_kernel");
     if (rc) return rc;
-    activity_erode_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(tmp, T_long, n_spk, ero, act_final);
+    activity_erode_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, s>>>(tmp, T_long, n_spk, ero, act_final, 0, n);
     return check_launch("activity_erode_kernel");
 }
 
@@ -320,12 +349,55 @@ extern "C" int nsf_stitch_stft(const float* Y, const int32_t* perms, const float
     NSF_REQUIRE(Y && perms && seg_w && wsum && S_st, "nsf_stitch_stft: null pointer");
     NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && hop >= 1 && T >= 1, "nsf_stitch_stft: bad sizes");
     if (T_long <= 0) return NSF_OK;
-    dim3 grid((unsigned)ceil_div64(T_long, 32), ceil_div(n_bins, 32));
-    ProfScope prof(PROF_STITCH, (double)T_long * n_bins * n_spk * 8.0 * ((double)T / hop + 1.0), (cudaStream_t)stream);
-    stitch_stft_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(Y), perms, seg_w, wsum, act_final,
-                                                              n_seg, n_spk, n_bins, T, hop, T_long,
-                                                              reinterpret_cast<float2*>(S_st));
-    return check_launch("stitch_stft_kernel");
+    return stitch_stft_range(Y, perms, seg_w, wsum, act_final, n_seg, n_spk, n_bins, T, hop, T_long, S_st, 0, T_long, (cudaStream_t)stream);
+}
+
+// Progressive tail: see include/nsf_b200.h.  Bounds of what is final once segments [0, sd) exist (hop = segment hop in frames):
+//   stitched masks / activity  t < m = sd * hop          (every segment i <= t / hop is there)
+//   act_b / dilated            t < d = m - dil
+//   act_final / S_st           t < e = d - ero
+//   waveform hops              j < h = floor(e / 8) * 8   (hop j reads frames j-1 and j; multiples of the iSTFT's CTA tile keep its
+//                                                          frame pairing, hence its rounding, that of the one-shot launch)
+// and everything once sd == n_seg.
+extern "C" int nsf_stitch_progress(const float* masks, int n_ch_total, const float* Y, const int32_t* perms, const float* seg_w,
+                                   const float* wsum, int n_seg, int seg_prev, int seg_done, int n_spk, int n_bins, int T, int hop,
+                                   int64_t T_long, float th, int dil, int ero, float* mask_st, float* activity, uint8_t* act_b,
+                                   uint8_t* tmp, uint8_t* act_final, float* S_st, float* wav, int64_t* hops_written, void* stream) {
+    NSF_REQUIRE(masks && Y && perms && seg_w && wsum && mask_st && activity && act_b && tmp && act_final && S_st && wav && hops_written,
+                "nsf_stitch_progress: null pointer");
+    NSF_REQUIRE(n_spk >= 1 && n_spk <= kMaxSpk && n_ch_total >= n_spk && hop >= 1 && T >= 1 && dil >= 0 && ero >= 0 && T_long >= 1,
+                "nsf_stitch_progress: bad sizes");
+    NSF_REQUIRE(0 <= seg_prev && seg_prev <= seg_done && seg_done <= n_seg, "nsf_stitch_progress: segments %d -> %d of %d", seg_prev,
+                seg_done, n_seg);
+    struct Bounds { int64_t m, d, e, h; };
+    auto bounds = [&](int sd) {
+        Bounds b;
+        if (sd >= n_seg) { b.m = b.d = b.e = T_long; b.h = T_long + 1; return b; }
+        b.m = std::min<int64_t>(T_long, (int64_t)sd * hop);
+        b.d = std::max<int64_t>(0, b.m - dil);
+        b.e = std::max<int64_t>(0, b.d - ero);
+        b.h = b.e / 8 * 8;
+        return b;
+    };
+    const Bounds p = bounds(seg_prev), q = bounds(seg_done);
+    hops_written[0] = p.h;
+    hops_written[1] = q.h;
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = stitch_masks_range(masks, n_ch_total, perms, seg_w, wsum, n_seg, n_spk, n_bins, T, hop, T_long, mask_st, activity, p.m, q.m, s);
+    if (rc) return rc;
+    if (q.d > p.d) {
+        activity_threshold_dilate_kernel<<<(unsigned)ceil_div64((q.d - p.d) * n_spk, 256), 256, 0, s>>>(activity, T_long, n_spk, th, dil,
+                                                                                                        act_b, tmp, p.d * n_spk, q.d * n_spk);
+        if ((rc = check_launch("activity_threshold_dilate_kernel"))) return rc;
+    }
+    if (q.e > p.e) {
+        activity_erode_kernel<<<(unsigned)ceil_div64((q.e - p.e) * n_spk, 256), 256, 0, s>>>(tmp, T_long, n_spk, ero, act_final, p.e * n_spk,
+                                                                                             q.e * n_spk);
+        if ((rc = check_launch("activity_erode_kernel"))) return rc;
+    }
+    rc = stitch_stft_range(Y, perms, seg_w, wsum, act_final, n_seg, n_spk, n_bins, T, hop, T_long, S_st, p.e, q.e, s);
+    if (rc) return rc;
+    return nsf_istft_range(S_st, n_spk, T_long, wav, p.h, q.h, stream);
 }
 
 extern "C" int nsf_peaknorm_pcm16(const float* wav, int n_streams, int64_t n, float* peak, int16_t* pcm, void* stream) {

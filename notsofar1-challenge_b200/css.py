@@ -17,6 +17,8 @@ Reference flow (css/css.py:110-338) vs this module
 """
 from __future__ import annotations
 
+import ctypes
+import os
 import itertools
 from dataclasses import dataclass
 from pathlib import Path
@@ -123,7 +125,7 @@ def _perm_tables(S: int):
     return _PERM_TABLES[S]
 
 
-def permutation_chain(costs: np.ndarray) -> np.ndarray:
+def permutation_chain(costs: np.ndarray, prev_state: Optional[int] = None, return_state: bool = False):
     """Sequential alignment of css.py:266-285 from the pairwise costs of the *unpermuted* segments.
 
     costs[i][a][b] = loss(left channel a of segment i-1, right channel b of segment i) on the original
@@ -136,6 +138,9 @@ def permutation_chain(costs: np.ndarray) -> np.ndarray:
     summed in channel order) for every possible previous order q, best[i][q] = first arg-min over p; the chain
     itself is then a table walk (0.3 ms instead of 14 ms of Python for a 30-minute meeting, during which the GPU
     would sit idle behind the cost read-back).
+
+    prev_state / return_state continue a chain: with prev_state = the state returned for segments [0, s), costs[s:] yields
+    the rows s.. of the one-shot call (the progressive tail of css_device walks the chain chunk by chunk).
     """
     n_seg, S, _ = costs.shape
     (cand,) = _perm_tables(S)
@@ -155,7 +160,8 @@ def permutation_chain(costs: np.ndarray) -> np.ndarray:
         bidx[better] = pi
         np.minimum(bval, total[:, pi], out=bval)
     best = np.ascontiguousarray(bidx.T)                    # [n_seg, P]
-    best[0] = np.arange(P)                               # segment 0 keeps its order
+    if prev_state is None:
+        best[0] = np.arange(P)                           # segment 0 keeps its order
     # state_i = best[i][state_{i-1}], state_{-1} = 0 (identity = cand[0]).  The maps compose associatively: blocked prefix
     # composition -- inside blocks of ~sqrt(n) segments vectorised across blocks, then one short carry walk over the
     # blocks (0.6 ms for the 9 677 segments every rank of a sharded 4-hour meeting replays with its GPU waiting).
@@ -169,22 +175,35 @@ def permutation_chain(costs: np.ndarray) -> np.ndarray:
         G[:, j] = G[:, j][rows, G[:, j - 1]]             # G_j <- best_j o G_{j-1} inside every block
     carry = np.zeros(nb, np.int64)
     last = G[:, L - 1].tolist()
-    q = 0
+    q = 0 if prev_state is None else int(prev_state)
     for b in range(nb):
         carry[b] = q
         q = last[b][q]
     states = np.take_along_axis(G, np.broadcast_to(carry[:, None, None], (nb, L, 1)), axis=2).reshape(-1)[:n_seg]
-    return cand[states].astype(np.int32)
+    perms = cand[states].astype(np.int32)
+    return (perms, int(states[-1])) if return_state else perms
 
 
-def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batch: int = 176):
+def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batch: int = 176, progressive: int = 0):
     """Chunks of segments the mask network / MVDR run on: [(first segment, count), ...].
 
     Large, equal chunks keep the persistent GEMMs' last wave full (a 128 x 256 tile grid over 148 SMs quantises badly for
     small M); when the audio is still streaming in from the host the first chunk is kept short so that compute starts
     after the first few MB have landed -- but long enough (176 segments = 15 ms of network time) that the rest of a
-    30-minute recording (0.8 GB, ~15 ms over PCIe) has landed when the second chunk wants it."""
+    30-minute recording (0.8 GB, ~15 ms over PCIe) has landed when the second chunk wants it.
+
+    progressive > 0 (the separated waveforms go back to the host piece by piece, css_device(host_out=...)): what follows the
+    first chunk is cut into chunks of at most that many segments, so that all but the last chunk's share of the output has
+    crossed PCIe when the network finishes."""
     max_batch = max(1, max_batch)
+    if streaming and progressive > 0 and n_seg >= 2 * first_batch:
+        max_batch = min(max_batch, max(progressive, first_batch + 1))
+        out, s0 = [(0, first_batch)], first_batch
+        while n_seg - s0 > max_batch + max_batch // 4:          # full chunks, then the remainder (a short one is merged)
+            out.append((s0, max_batch))
+            s0 += max_batch
+        out.append((s0, n_seg - s0))
+        return out
     out, s0 = [], 0
     if streaming and n_seg >= 2 * first_batch and max_batch > first_batch:      # short sessions: one chunk (a small second chunk wastes GEMM waves)
         out.append((0, first_batch))
@@ -239,6 +258,24 @@ def _segment_weights(plan: SegmentPlan):
     return seg_w, wsum
 
 
+_SEG_W_DEV: Dict[tuple, tuple] = {}
+
+
+def _segment_weights_device(plan: SegmentPlan, device: torch.device):
+    """_segment_weights on the device, kept per plan: the two small uploads would otherwise queue behind the recording on the
+    host -> device copy engine (15 ms for a 30-min meeting) when the tail is set up before the network runs."""
+    key = (plan.segment_frames, plan.hop_frames, plan.m0_frames, plan.m1_frames, plan.num_segments, plan.mix_frames, str(device))
+    hit = _SEG_W_DEV.get(key)
+    if hit is None:
+        seg_w_np, wsum_np = _segment_weights(plan)
+        assert (wsum_np > 1e-5).all(), 'zero weights found. check hop_size, segment_size or m0, m1'
+        hit = (torch.from_numpy(seg_w_np).to(device), torch.from_numpy(wsum_np).to(device))
+        _SEG_W_DEV[key] = hit
+        if len(_SEG_W_DEV) > 8:
+            _SEG_W_DEV.pop(next(iter(_SEG_W_DEV)))
+    return hit
+
+
 class HostFeeder:
     """Streams a pinned (or pageable) host recording [Nsamples, Channels] into HBM in chunks on a side stream, so the
     STFT / mask network of the first segments run while the rest of the meeting is still crossing PCIe.
@@ -270,6 +307,31 @@ class HostFeeder:
 
 
 _SIDE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_TAIL_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+_SMALL_PINNED: Dict[tuple, "torch.Tensor"] = {}
+# Segments per chunk behind the first one when the output streams back piece by piece; 0: one-shot tail.  356 segments of
+# 186 frames are 259 = 7 x 37 row tiles of 256: every GEMM of the block (2, 6 or 8 column tiles) fills its last wave of
+# 74 CTA pairs (345-segment chunks measured 4 % slower per segment).
+PROGRESSIVE_CHUNK = int(os.environ.get("NSF_PROGRESSIVE_CHUNK", "356"))
+
+
+def _tail_stream(device: torch.device):
+    """High-priority stream of the progressive tail (stitching + iSTFT + D2H of what is final) next to the mask network."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _TAIL_STREAMS:
+        _TAIL_STREAMS[idx] = torch.cuda.Stream(device, priority=-1)      # 0.4-0.7 ms per chunk; 1.7 ms when it has to share fairly
+    return _TAIL_STREAMS[idx]
+
+
+def _small_pinned(tag: str, shape: tuple, dtype) -> "torch.Tensor":
+    """Page-locked scratch for the few KB of costs / permutations that cross PCIe per chunk (kept: pinning is a syscall)."""
+    key = (tag, dtype)
+    n = int(np.prod(shape))
+    buf = _SMALL_PINNED.get(key)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 4096), dtype=dtype, pin_memory=True)
+        _SMALL_PINNED[key] = buf
+    return buf[:n].view(shape)
 
 
 def _side_stream(device: torch.device):
@@ -280,7 +342,8 @@ def _side_stream(device: torch.device):
 
 
 @torch.no_grad()
-def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_info: bool = True) -> Dict:
+def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_info: bool = True,
+               host_out: Optional[torch.Tensor] = None) -> Dict:
     """The whole CSS path on tensors that already live in HBM (or are on their way there: x may be a HostFeeder).
 
     x: [Nsamples, Channels] float32 on the CUDA device.  Returns a dict of device tensors:
@@ -288,6 +351,13 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
     [T_long, S] uint8, plus the per-segment 'masks' [n_seg, S+Nn, F, T], 'Y' [n_seg, S, F, T], 'X' [F, T_long, C],
     'perms' (numpy [n_seg, S]) and 'plan'.  The only host round trip inside is the [n_seg, S, S] cost matrix of
     the permutation chain (css.py:266-285), 36 bytes per segment.
+
+    host_out: optional page-locked [S, N'] float32 tensor that receives 'wav' (asynchronously: synchronise the current
+    stream before reading it).  With it, and more than one chunk of segments, the tail runs *progressively*: after every
+    chunk the costs of its segments go to the host, the chain advances, and nsf_stitch_progress stitches / gates /
+    inverse-transforms the frames that have become final on a side stream whose D2H copies overlap the next chunk's
+    mask network -- only the last chunk's share of the output is copied after the network has finished.  Every tail
+    stage is local in time, so the result is bit for bit that of the one-shot tail (tests/test_gpu_parity.py).
     """
     feeder = x if isinstance(x, HostFeeder) else None
     if feeder is not None:
@@ -319,7 +389,56 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
         n_masks = separator.num_masks
         masks = torch.empty((n_seg, n_masks, NUM_BINS, T), dtype=torch.float32, device=device)
         Y = torch.empty((n_seg, S, NUM_BINS, T), dtype=torch.complex64, device=device)
-        for s0, nb in plan_batches(n_seg, int(separator.segments_per_batch), streaming=feeder is not None):
+        chunks = plan_batches(n_seg, int(separator.segments_per_batch), streaming=feeder is not None,
+                              progressive=PROGRESSIVE_CHUNK if host_out is not None else 0)
+        progressive = host_out is not None and len(chunks) > 1 and PROGRESSIVE_CHUNK > 0
+        costs = torch.empty((n_seg, S, S), dtype=torch.float32, device=device)
+        in_kind = 0 if cfg.stitching_input == 'mask' else 1
+        loss_kind = 0 if cfg.stitching_loss == 'l1' else 1
+        src = masks if in_kind == 0 else Y
+        n_out = (mix_frames - 1) * FRAME_HOP + FRAME_LEN
+        if host_out is not None:
+            assert tuple(host_out.shape) == (S, n_out) and host_out.dtype == torch.float32 and not host_out.is_cuda
+        if progressive:
+            # II'/III'. everything behind the chain, advanced chunk by chunk on a side stream (nsf_stitch_progress)
+            seg_w, wsum = _segment_weights_device(plan, device)
+            mask_st = torch.empty((NUM_BINS, mix_frames, S), dtype=torch.float32, device=device)
+            activity = torch.empty((mix_frames, S), dtype=torch.float32, device=device)
+            act_b = torch.empty((mix_frames, S), dtype=torch.uint8, device=device)
+            act_tmp = torch.empty_like(act_b)
+            act_final = torch.empty_like(act_b)
+            S_st = torch.empty((S, mix_frames, NUM_BINS), dtype=torch.complex64, device=device)
+            wav = torch.empty((S, n_out), dtype=torch.float32, device=device)
+            perms = torch.empty((n_seg, S), dtype=torch.int32, device=device)
+            costs_host = _small_pinned("costs", (n_seg, S, S), torch.float32)
+            perms_host = _small_pinned("perms", (n_seg, S), torch.int32)
+            tail = _tail_stream(device)
+            main = torch.cuda.current_stream(device)
+            tail.wait_stream(main)                     # the buffers above may recycle memory still in use upstream
+            cost_events = []
+            hops = (ctypes.c_int64 * 2)()
+            chain_state = [None]
+            th = float(np.float32(cfg.activity_th))
+
+            def advance(ci):
+                c0, cn = chunks[ci]
+                cost_events[ci].synchronize()          # the GPU is busy with chunk ci + 1 meanwhile
+                p_np, chain_state[0] = permutation_chain(costs_host[c0:c0 + cn].numpy(), prev_state=chain_state[0], return_state=True)
+                perms_host[c0:c0 + cn] = torch.from_numpy(p_np)
+                with torch.cuda.stream(tail):
+                    tail.wait_event(cost_events[ci])   # the tail of this chunk reads its masks / Y (complete: formal ordering)
+                    perms[c0:c0 + cn].copy_(perms_host[c0:c0 + cn], non_blocking=True)
+                    _cabi.check(lib.nsf_stitch_progress(
+                        _cabi.ptr(masks), n_masks, _cabi.ptr(Y), _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), n_seg, c0, c0 + cn,
+                        S, NUM_BINS, T, hop, mix_frames, th, plan.dilation_frames, plan.erosion_frames, _cabi.ptr(mask_st),
+                        _cabi.ptr(activity), _cabi.ptr(act_b), _cabi.ptr(act_tmp), _cabi.ptr(act_final), _cabi.ptr(S_st), _cabi.ptr(wav),
+                        hops, sp()), "nsf_stitch_progress")
+                    a, b = int(hops[0]) * FRAME_HOP, min(int(hops[1]) * FRAME_HOP, n_out)
+                    if b > a:
+                        for k in range(S):             # contiguous runs: plain cudaMemcpyAsync (a strided copy_ is staged through pageable memory)
+                            host_out[k, a:b].copy_(wav[k, a:b], non_blocking=True)
+
+        for ci, (s0, nb) in enumerate(chunks):
             # STFT of the frames this chunk of segments needs (and, when streaming from the host, only once they landed)
             f_need = min(T_valid, (s0 + nb - 1) * hop + T)
             if f_need > frames_done:
@@ -334,40 +453,52 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
                 separator.mask_apply(masks[s0:s0 + nb], X, T_valid, s0, hop, mask_floor, out=Y[s0:s0 + nb])
             if cfg.normalize_segment_power:
                 separator.power_norm(Y[s0:s0 + nb], X, T_valid, s0, hop, mix_frames)
+            if progressive:
+                _cabi.check(lib.nsf_pit_cost_range(_cabi.ptr(src), in_kind, loss_kind, s0, s0 + nb, n_masks if in_kind == 0 else S, S,
+                                                   NUM_BINS, T, plan.overlap_frames, _cabi.ptr(costs), sp()), "nsf_pit_cost_range")
+                costs_host[s0:s0 + nb].copy_(costs[s0:s0 + nb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                cost_events.append(ev)
+                if ci >= 1:
+                    advance(ci - 1)                    # one chunk behind: the queue of the main stream never runs dry
 
         if feeder is not None:
             feeder.ready(n_samples)       # every copy has been ordered before the buffers can be recycled
 
-        # II. permutation chain + weighted overlap-add (css.py:254-299)
-        costs = torch.empty((n_seg, S, S), dtype=torch.float32, device=device)
-        in_kind = 0 if cfg.stitching_input == 'mask' else 1
-        loss_kind = 0 if cfg.stitching_loss == 'l1' else 1
-        src = masks if in_kind == 0 else Y
-        _cabi.check(lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_seg, n_masks if in_kind == 0 else S, S, NUM_BINS, T,
-                                     plan.overlap_frames, _cabi.ptr(costs), sp()), "nsf_pit_cost")
-        # host work that does not depend on the costs runs while the GPU is still busy with the segments
-        seg_w_np, wsum_np = _segment_weights(plan)
-        assert (wsum_np > 1e-5).all(), 'zero weights found. check hop_size, segment_size or m0, m1'
-        seg_w = torch.from_numpy(seg_w_np).to(device)
-        wsum = torch.from_numpy(wsum_np).to(device)
-        mask_st = torch.empty((NUM_BINS, mix_frames, S), dtype=torch.float32, device=device)
-        activity = torch.empty((mix_frames, S), dtype=torch.float32, device=device)
-        perms_np = permutation_chain(costs.cpu().numpy())            # the only device -> host sync of the path
-        perms = torch.from_numpy(perms_np).to(device)
-        _cabi.check(lib.nsf_stitch_masks(_cabi.ptr(masks), n_masks, _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), n_seg, S,
-                                         NUM_BINS, T, hop, mix_frames, _cabi.ptr(mask_st), _cabi.ptr(activity), sp()),
-                    "nsf_stitch_masks")
-        # III. activity gate (css.py:303-312)
-        act_b = torch.empty((mix_frames, S), dtype=torch.uint8, device=device)
-        act_tmp = torch.empty_like(act_b)
-        act_final = torch.empty_like(act_b)
-        _cabi.check(lib.nsf_activity(_cabi.ptr(activity), mix_frames, S, float(np.float32(cfg.activity_th)), plan.dilation_frames,
-                                     plan.erosion_frames, _cabi.ptr(act_b), _cabi.ptr(act_tmp), _cabi.ptr(act_final), sp()),
-                    "nsf_activity")
-        S_st = torch.empty((S, mix_frames, NUM_BINS), dtype=torch.complex64, device=device)
-        _cabi.check(lib.nsf_stitch_stft(_cabi.ptr(Y), _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), _cabi.ptr(act_final),
-                                        n_seg, S, NUM_BINS, T, hop, mix_frames, _cabi.ptr(S_st), sp()), "nsf_stitch_stft")
-        wav = separator.istft_device(S_st)                                      # [S, N']
+        if progressive:
+            advance(len(chunks) - 1)
+            main.wait_stream(tail)                     # downstream readers (and the allocator) see the tail's work
+            perms_np = perms_host.numpy().copy()
+        else:
+            # II. permutation chain + weighted overlap-add (css.py:254-299)
+            _cabi.check(lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_seg, n_masks if in_kind == 0 else S, S, NUM_BINS, T,
+                                         plan.overlap_frames, _cabi.ptr(costs), sp()), "nsf_pit_cost")
+            # host work that does not depend on the costs runs while the GPU is still busy with the segments
+            seg_w_np, wsum_np = _segment_weights(plan)
+            assert (wsum_np > 1e-5).all(), 'zero weights found. check hop_size, segment_size or m0, m1'
+            seg_w = torch.from_numpy(seg_w_np).to(device)
+            wsum = torch.from_numpy(wsum_np).to(device)
+            mask_st = torch.empty((NUM_BINS, mix_frames, S), dtype=torch.float32, device=device)
+            activity = torch.empty((mix_frames, S), dtype=torch.float32, device=device)
+            perms_np = permutation_chain(costs.cpu().numpy())            # the only device -> host sync of the path
+            perms = torch.from_numpy(perms_np).to(device)
+            _cabi.check(lib.nsf_stitch_masks(_cabi.ptr(masks), n_masks, _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), n_seg, S,
+                                             NUM_BINS, T, hop, mix_frames, _cabi.ptr(mask_st), _cabi.ptr(activity), sp()),
+                        "nsf_stitch_masks")
+            # III. activity gate (css.py:303-312)
+            act_b = torch.empty((mix_frames, S), dtype=torch.uint8, device=device)
+            act_tmp = torch.empty_like(act_b)
+            act_final = torch.empty_like(act_b)
+            _cabi.check(lib.nsf_activity(_cabi.ptr(activity), mix_frames, S, float(np.float32(cfg.activity_th)), plan.dilation_frames,
+                                         plan.erosion_frames, _cabi.ptr(act_b), _cabi.ptr(act_tmp), _cabi.ptr(act_final), sp()),
+                        "nsf_activity")
+            S_st = torch.empty((S, mix_frames, NUM_BINS), dtype=torch.complex64, device=device)
+            _cabi.check(lib.nsf_stitch_stft(_cabi.ptr(Y), _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), _cabi.ptr(act_final),
+                                            n_seg, S, NUM_BINS, T, hop, mix_frames, _cabi.ptr(S_st), sp()), "nsf_stitch_stft")
+            wav = separator.istft_device(S_st)                                      # [S, N']
+            if host_out is not None:
+                host_out.copy_(wav, non_blocking=True)
     return dict(wav=wav, mask_stitched=mask_st, activity=activity, activity_b=act_b, activity_final=act_final, masks=masks,
                 Y=Y, X=X, S_st=S_st, costs=costs, perms=perms_np, plan=plan)
 
@@ -409,12 +540,12 @@ def separate_and_stitch(speech_mix, separator: ConformerCssB200, fs: int, device
         chunk = min(32, max(1, int(separator.segments_per_batch))) * plan0.hop_frames * FRAME_HOP   # 21 MB per copy: 0.4 ms
         with torch.cuda.device(device):
             x = HostFeeder(x_host, device, chunk)
-    out = css_device(x, separator, fs, cfg)
-    # D2H of the separated streams into a (recycled) pinned buffer
-    wav = out["wav"]
+    # D2H of the separated streams into a (pooled) pinned buffer, piece by piece behind the mask network (css_device)
+    n_samples = x.x_dev.shape[0] if isinstance(x, HostFeeder) else x.shape[0]
+    plan0 = plan_segments(n_samples, fs, cfg)
     with torch.cuda.device(device):
-        host = _pinned_out(tuple(wav.shape))
-        host.copy_(wav, non_blocking=True)
+        host = _pinned_out((cfg.num_spks, (plan0.mix_frames - 1) * FRAME_HOP + FRAME_LEN))
+        out = css_device(x, separator, fs, cfg, host_out=host)
         torch.cuda.current_stream(device).synchronize()
     separated = _lend(host)                 # owned by the caller: the buffer is not reused while these arrays are alive
     separated_wavs = [separated[k] for k in range(cfg.num_spks)]

@@ -718,6 +718,36 @@ def test_separate_and_stitch_production_vs_oracle(nb, dev):
     assert e < TOL
 
 
+@pytest.mark.parametrize("hop_sec,per_batch", [(0.5, 3), (0.25, 2), (0.5, 1)])
+def test_progressive_tail_is_the_one_shot_tail(nb, dev, golden, small_weights, hop_sec, per_batch):
+    """separate_and_stitch with a host recording stitches / gates / inverse-transforms what is final after every chunk of
+    segments and copies it out behind the network (nsf_stitch_progress, nsf_pit_cost_range, nsf_istft_range, the chain
+    continued chunk by chunk); css_device on the resident recording runs the four whole-recording calls after the last
+    chunk.  Every tail stage is local in time: the two must agree bit for bit -- for two (hop = T/2) and four (hop = T/4)
+    segments per frame, and with dilation / erosion radii reaching across chunk boundaries."""
+    from notsofar_b200 import css as css_mod
+    x = np.tile(_mixture(golden), (3, 1))[: 16000 * 9 + 1234]
+    cfg = nb.CssCfg(activity_th=float(golden["activity_th"]), segment_size_sec=1.0, hop_size_sec=hop_sec, show_progressbar=False)
+    sep = _sep(nb, small_weights, dev, segments_per_batch=per_batch)
+    ref = css_mod.css_device(torch.from_numpy(x).to(dev), sep, 16000, cfg)
+    n_seg = ref["plan"].num_segments
+    assert len(css_mod.plan_batches(n_seg, per_batch, streaming=True, progressive=css_mod.PROGRESSIVE_CHUNK)) >= 5
+    stages = {}
+    wavs, side = nb.separate_and_stitch(x[None], sep, 16000, dev, cfg, _stages=stages)
+    assert np.array_equal(stages["perms"], ref["perms"])
+    for k in ("masks", "Y", "costs", "mask_stitched", "activity", "activity_b", "activity_final", "S_st", "wav"):
+        assert torch.equal(stages[k], ref[k]), k
+    w_ref = ref["wav"].cpu().numpy()
+    for k in range(3):
+        assert np.array_equal(wavs[k], w_ref[k])                 # every piece landed at its place in the host buffer
+    assert np.array_equal(side["activity_final"][0].numpy(), ref["activity_final"].cpu().numpy().astype(bool))
+    # the range entry points reject what they cannot do
+    lib = nb._cabi.load()
+    with pytest.raises(nb.NsfError):
+        nb._cabi.check(lib.nsf_istft_range(nb._cabi.ptr(ref["S_st"]), 3, ref["plan"].mix_frames, nb._cabi.ptr(ref["wav"]), 4, 16,
+                                           nb._cabi.stream_ptr()), "nsf_istft_range")
+
+
 def test_no_cpu_path(nb):
     cfg = nb.CssCfg()
     w = O.random_weights(seed=1, d_model=128, n_heads=2, d_ff=256, n_blocks=1)
