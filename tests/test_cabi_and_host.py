@@ -145,6 +145,42 @@ def test_permutation_chain_equals_sequential_hungarian(N):
     assert not np.array_equal(perms, np.tile(np.arange(S), (n_seg, 1)))
 
 
+def test_permutation_chain_continues_chunk_by_chunk(N):
+    """The progressive tail walks the chain one chunk of segments at a time: (perms, state) of a prefix + the rest with
+    prev_state == the one-shot walk, wherever the cut is (also inside / at the ends of the blocked prefix composition)."""
+    rng = np.random.default_rng(3)
+    for n_seg, S in ((1, 3), (2, 3), (7, 3), (37, 2), (400, 3), (101, 4)):
+        costs = rng.random((n_seg, S, S)).astype(np.float32)
+        costs[0] = 0
+        full = N.permutation_chain(costs)
+        for cuts in ([1], [n_seg // 2], [n_seg - 1], [n_seg // 3, 2 * n_seg // 3]):
+            cuts = sorted({c for c in cuts if 0 < c < n_seg})
+            if not cuts:
+                continue
+            parts, state, lo = [], None, 0
+            for hi in cuts + [n_seg]:
+                p, state = N.permutation_chain(costs[lo:hi], prev_state=state, return_state=True)
+                parts.append(p)
+                lo = hi
+            assert np.array_equal(np.concatenate(parts), full), (n_seg, S, cuts)
+
+
+def test_plan_batches_progressive():
+    """Chunks of the streaming path: short first chunk, then full (wave-filling) chunks, a short remainder merged into
+    the last one; nothing changes for resident recordings, short sessions or with the progressive tail switched off."""
+    from notsofar_b200.css import plan_batches
+    assert plan_batches(1209, 1280, streaming=True, progressive=356) == [(0, 176), (176, 356), (532, 356), (888, 321)]
+    assert plan_batches(1209, 1280, streaming=True) == [(0, 176), (176, 1033)]
+    assert plan_batches(1209, 1280, streaming=False, progressive=356) == [(0, 1209)]
+    assert plan_batches(241, 1280, streaming=True, progressive=356) == [(0, 241)]
+    assert plan_batches(176 + 356 + 80, 1280, streaming=True, progressive=356) == [(0, 176), (176, 436)]
+    for n in (352, 353, 800, 5000, 9677):
+        chunks = plan_batches(n, 1280, streaming=True, progressive=356)
+        assert chunks[0] == (0, 176) and sum(c for _, c in chunks) == n
+        assert all(a[0] + a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+        assert all(c == 356 for _, c in chunks[1:-1]) and 0 < chunks[-1][1] <= 356 + 356 // 4
+
+
 def test_pack_weights_layout(N, small_weights):
     dims, blob, offsets, extra = N.pack_weights(small_weights, T=186, gemm_engine=N.GEMM_TC_3XTF32)
     assert (dims.d_model, dims.n_heads, dims.d_ff, dims.n_blocks, dims.kernel_size) == (128, 2, 256, 2, 33)
