@@ -51,12 +51,13 @@ static int ensure_tables(cudaStream_t stream) {
 
 // ------------------------------------------------------------------------------------------- STFT
 constexpr int kStftTT = 4;          // frames per CTA
-constexpr int kStftThreads = 256;   // 4 groups of 64 threads = 4 channel pairs
+constexpr int kStftThreads = 512;   // 8 groups of 64 threads = 4 channel pairs x 2 frames in flight (the FFT stages are
+                                    // barrier-latency bound: 32 warps per SM instead of 16)
 
 struct StftSmem {
     float2 tw[512];
     float hann[512];
-    float scratch[4][kFftScratchFloats];
+    float scratch[kStftThreads / 64][kFftScratchFloats];
     // out[k][tt][c] follows (dynamic, 257 * TT * n_ch float2)
 };
 
@@ -73,9 +74,9 @@ stft_mc_kernel(const float* __restrict__ x, int n_ch, float2* __restrict__ X, in
     }
     __syncthreads();
 
-    const int group = tid >> 6;          // channel pair
+    const int group = tid >> 6;          // (frame parity, channel pair)
     const int lane64 = tid & 63;
-    const int ch_a = 2 * group, ch_b = 2 * group + 1;
+    const int ch_a = 2 * (group & 3), ch_b = 2 * (group & 3) + 1;
     const int64_t t0 = (int64_t)blockIdx.x * kStftTT;
     const int n_tt = (int)min((int64_t)kStftTT, n_frames - t0);
     const bool active = ch_a < n_ch;
@@ -83,7 +84,7 @@ stft_mc_kernel(const float* __restrict__ x, int n_ch, float2* __restrict__ X, in
     auto group_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(group + 1) : "memory"); };
 
     if (active) {
-        for (int tt = 0; tt < n_tt; ++tt) {
+        for (int tt = group >> 2; tt < n_tt; tt += kStftThreads / 256) {
             const float* xf = x + (t0 + tt) * (int64_t)kHop * n_ch;
             float2 v[8];
 #pragma unroll

@@ -32,13 +32,26 @@ orig_chain = C.permutation_chain
 def chain(*a, **k):
     t = time.perf_counter(); r = orig_chain(*a, **k); marks.append(("chain_done", time.perf_counter(), None)); return r
 C.permutation_chain = chain
-for it in range(5):
+if os.environ.get("NSF_TRACE_PLAN"):            # e.g. "176,356,356,321": chunk sizes to try instead of plan_batches' own
+    sizes = [int(v) for v in os.environ["NSF_TRACE_PLAN"].split(",")]
+    def fixed_plan(n_seg, *a, **k):
+        assert sum(sizes) == n_seg, (sum(sizes), n_seg)
+        out, s0 = [], 0
+        for c in sizes:
+            out.append((s0, c)); s0 += c
+        return out
+    C.plan_batches = fixed_plan
+walls = []
+for it in range(9):
     marks.clear()
     torch.cuda.synchronize()
     t0 = time.perf_counter(); e0 = torch.cuda.Event(enable_timing=True); e0.record()
     wavs, _ = N.separate_and_stitch(x[None], sep, 16000, dev, cfg, return_side_info=False)
     t1 = time.perf_counter()
-    if it == 4:
+    if it >= 3:
+        walls.append((t1 - t0) * 1e3)
+    if it == 8:
+        print("mean wall of 6 calls %.2f ms (min %.2f)" % (sum(walls) / len(walls), min(walls)))
         print("total wall %.1f ms" % ((t1 - t0) * 1e3))
         for name, th, ev in marks:
             print(f"{name:12s} host {1e3*(th-t0):7.2f} ms   gpu " + ("   -" if ev is None else f"{e0.elapsed_time(ev):7.2f} ms"))
