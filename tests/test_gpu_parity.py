@@ -718,16 +718,21 @@ def test_separate_and_stitch_production_vs_oracle(nb, dev):
     assert e < TOL
 
 
-@pytest.mark.parametrize("hop_sec,per_batch", [(0.5, 3), (0.25, 2), (0.5, 1)])
-def test_progressive_tail_is_the_one_shot_tail(nb, dev, golden, small_weights, hop_sec, per_batch):
+@pytest.mark.parametrize("hop_sec,per_batch,extra", [
+    (0.5, 3, {}), (0.25, 2, {}), (0.5, 1, {}),
+    (0.5, 2, dict(stitching_input='separation_result', stitching_loss='mse', normalize_segment_power=True, mc_mvdr=False,
+                  mc_mask_floor_db=-20.0))])
+def test_progressive_tail_is_the_one_shot_tail(nb, dev, golden, small_weights, hop_sec, per_batch, extra):
     """separate_and_stitch with a host recording stitches / gates / inverse-transforms what is final after every chunk of
     segments and copies it out behind the network (nsf_stitch_progress, nsf_pit_cost_range, nsf_istft_range, the chain
     continued chunk by chunk); css_device on the resident recording runs the four whole-recording calls after the last
     chunk.  Every tail stage is local in time: the two must agree bit for bit -- for two (hop = T/2) and four (hop = T/4)
-    segments per frame, and with dilation / erosion radii reaching across chunk boundaries."""
+    segments per frame, with dilation / erosion radii reaching across chunk boundaries, and with the costs taken from the
+    power-normalised masked STFTs instead of the masks."""
     from notsofar_b200 import css as css_mod
     x = np.tile(_mixture(golden), (3, 1))[: 16000 * 9 + 1234]
-    cfg = nb.CssCfg(activity_th=float(golden["activity_th"]), segment_size_sec=1.0, hop_size_sec=hop_sec, show_progressbar=False)
+    cfg = nb.CssCfg(activity_th=float(golden["activity_th"]), segment_size_sec=1.0, hop_size_sec=hop_sec, show_progressbar=False,
+                    **extra)
     sep = _sep(nb, small_weights, dev, segments_per_batch=per_batch)
     ref = css_mod.css_device(torch.from_numpy(x).to(dev), sep, 16000, cfg)
     n_seg = ref["plan"].num_segments
