@@ -265,13 +265,12 @@ def run_b200_sharded(args, world, rank, local_rank, dev, lib):
     def step_e2e():
         chunk = 32 * plan.hop_frames * 256
         feeder = HostFeeder(x_pinned, dev, chunk)
-        out = css_device_sharded(feeder, sep, FS, cfg, n_total)
         # the assembled streams stay on rank 0's GPU (the ASR / diarization hand-off); the host copy of the result is read
-        # by every rank for its own samples in parallel (each over its own PCIe link), seams included in the pieces
+        # by every rank for its own samples in parallel (each over its own PCIe link), seams included in the pieces -- the
+        # interior of a piece while the mask network is still running (ShardWorker.phase1 / finish_host)
         from notsofar_b200.css import _pinned_out
-        piece = out["wav_piece"]
-        host = _pinned_out(tuple(piece.shape))
-        host.copy_(piece, non_blocking=True)
+        host = _pinned_out((3, sh.n_own_frames * 256 + 256))
+        out = css_device_sharded(feeder, sep, FS, cfg, n_total, host_piece=host)
         torch.cuda.current_stream(dev).synchronize()
         return out
 

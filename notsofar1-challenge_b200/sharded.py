@@ -26,6 +26,9 @@ import numpy as np
 import torch
 
 from . import _cabi
+import ctypes
+
+from . import css as _css
 from .css import (CssCfg, SegmentPlan, plan_segments, plan_batches, permutation_chain, _segment_weights, HostFeeder)
 from .separator import NUM_BINS, FRAME_HOP, FRAME_LEN
 
@@ -191,6 +194,9 @@ def _global_rank(r: int, group) -> int:
 
 
 # ------------------------------------------------------------------------------------------- per-rank work
+_SHARD_W_DEV: Dict[tuple, tuple] = {}
+
+
 class ShardWorker:
     """The work of one rank, split at the three exchange points so that the same code runs under torch.distributed
     (css_device_sharded) and, rank after rank on one device, in the single-GPU parity test of the sharding logic."""
@@ -206,9 +212,17 @@ class ShardWorker:
 
     # ---- phase 1: STFT, mask network, MVDR and stitching costs of the local block --------------------------------
     @torch.no_grad()
-    def phase1(self, x_local) -> torch.Tensor:
+    def phase1(self, x_local, host_piece: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x_local: samples [sample_lo, sample_hi) of the recording, [n, C] float32 on the device (or a HostFeeder
-        over that slice).  Returns the costs of the owned segments [n_own_seg, S, S] (device)."""
+        over that slice).  Returns the costs of the owned segments [n_own_seg, S, S] (device).
+
+        host_piece: optional page-locked [S, n_own_frames*256 + 256] float32 tensor that is to receive this rank's
+        waveform piece (finish_host).  With it the *interior* of the piece crosses PCIe while the mask network is still
+        running: a rank cannot know the global channel order of its block before every earlier rank has finished, but that
+        order is only a relabelling of its three streams -- the optimal assignment is equivariant, p*(q) = sigma o q --, so
+        the rank walks a local chain from the identity, runs the progressive tail of css_device on its local arrays
+        (nsf_stitch_progress) and copies out, still under the local labels, the hops that depend neither on a
+        neighbour's activity (dilation + erosion frames next to a seam) nor on the last chunk of segments."""
         sh, plan, cfg, sep = self.sh, self.plan, self.cfg, self.sep
         feeder = x_local if isinstance(x_local, HostFeeder) else None
         x = feeder.x_dev if feeder is not None else x_local
@@ -229,7 +243,16 @@ class ShardWorker:
             self.masks = torch.empty((n_loc, n_masks, NUM_BINS, T), dtype=torch.float32, device=device)
             self.Y = torch.empty((n_loc, S, NUM_BINS, T), dtype=torch.complex64, device=device)
             frames_done = 0
-            for s0, nb in plan_batches(n_loc, int(sep.segments_per_batch), streaming=feeder is not None):
+            chunks = plan_batches(n_loc, int(sep.segments_per_batch), streaming=feeder is not None,
+                                  progressive=_css.PROGRESSIVE_CHUNK if host_piece is not None else 0)
+            costs = torch.empty((n_loc, S, S), dtype=torch.float32, device=device)
+            in_kind = 0 if cfg.stitching_input == 'mask' else 1
+            loss_kind = 0 if cfg.stitching_loss == 'l1' else 1
+            src = self.masks if in_kind == 0 else self.Y
+            self.prog = None
+            if host_piece is not None and len(chunks) > 1 and _css.PROGRESSIVE_CHUNK > 0:
+                self._progressive_setup(host_piece, chunks, device)
+            for ci, (s0, nb) in enumerate(chunks):
                 f_need = min(sh.valid_frames, (s0 + nb - 1) * hop + T)
                 if f_need > frames_done:
                     if feeder is not None:
@@ -244,16 +267,129 @@ class ShardWorker:
                 if cfg.normalize_segment_power:
                     # the reference's t = en - st counts frames up to mix_frames (global): local pitch ends there too
                     sep.power_norm(self.Y[s0:s0 + nb], X, sh.valid_frames, s0, hop, plan.mix_frames - sh.frame0)
+                if self.prog is not None:
+                    _cabi.check(self.lib.nsf_pit_cost_range(_cabi.ptr(src), in_kind, loss_kind, s0, s0 + nb, n_masks if in_kind == 0 else S,
+                                                            S, NUM_BINS, T, plan.overlap_frames, _cabi.ptr(costs), _cabi.stream_ptr()),
+                                "nsf_pit_cost_range")
+                    self._progressive_chunk_done(ci, costs)
             if feeder is not None:
                 feeder.ready(x.shape[0])
-            costs = torch.empty((n_loc, S, S), dtype=torch.float32, device=device)
-            in_kind = 0 if cfg.stitching_input == 'mask' else 1
-            loss_kind = 0 if cfg.stitching_loss == 'l1' else 1
-            src = self.masks if in_kind == 0 else self.Y
-            _cabi.check(self.lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_loc, n_masks if in_kind == 0 else S, S, NUM_BINS,
-                                              T, plan.overlap_frames, _cabi.ptr(costs), _cabi.stream_ptr()), "nsf_pit_cost")
+            if self.prog is None:
+                _cabi.check(self.lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_loc, n_masks if in_kind == 0 else S, S, NUM_BINS,
+                                                  T, plan.overlap_frames, _cabi.ptr(costs), _cabi.stream_ptr()), "nsf_pit_cost")
+            elif len(chunks) >= 2:
+                self._progressive_advance(len(chunks) - 2)      # the last chunk's frames wait for the global tail (phase 3)
         self.X = X
         return costs[sh.halo:]
+
+    # ---- progressive read-back of the piece's interior (see phase1) ------------------------------------------------
+    def _progressive_setup(self, host_piece: torch.Tensor, chunks, device):
+        sh, plan, cfg = self.sh, self.plan, self.cfg
+        S, T = cfg.num_spks, plan.segment_frames
+        assert tuple(host_piece.shape) == (S, sh.n_own_frames * FRAME_HOP + FRAME_HOP) and host_piece.dtype == torch.float32
+        loc0 = sh.seg_lo - sh.halo
+        key = (plan.segment_frames, plan.hop_frames, plan.m0_frames, plan.m1_frames, plan.num_segments, plan.mix_frames, loc0, sh.seg_hi,
+               sh.frame0, sh.n_frames, str(device))
+        hit = _SHARD_W_DEV.get(key)
+        if hit is None:            # small uploads, kept: next to the recording they would queue behind it on the copy engine
+            seg_w_np, wsum_np = _segment_weights(plan)
+            hit = (torch.from_numpy(np.ascontiguousarray(seg_w_np[loc0:sh.seg_hi])).to(device),
+                   torch.from_numpy(np.ascontiguousarray(wsum_np[sh.frame0:sh.frame0 + sh.n_frames])).to(device))
+            _SHARD_W_DEV[key] = hit
+            if len(_SHARD_W_DEV) > 8:
+                _SHARD_W_DEV.pop(next(iter(_SHARD_W_DEV)))
+        nf = sh.n_frames
+        p = dict(chunks=chunks, host=host_piece, seg_w=hit[0], wsum=hit[1], events=[], state=None, copied=[],
+                 mask_st=torch.empty((NUM_BINS, nf, S), dtype=torch.float32, device=device),
+                 activity=torch.empty((nf, S), dtype=torch.float32, device=device),
+                 act_b=torch.empty((nf, S), dtype=torch.uint8, device=device),
+                 act_tmp=torch.empty((nf, S), dtype=torch.uint8, device=device),
+                 act_final=torch.empty((nf, S), dtype=torch.uint8, device=device),
+                 S_st=torch.empty((S, nf, NUM_BINS), dtype=torch.complex64, device=device),
+                 wav=torch.empty((S, (nf - 1) * FRAME_HOP + FRAME_LEN), dtype=torch.float32, device=device),
+                 perms=torch.empty((sh.n_loc_seg, S), dtype=torch.int32, device=device),
+                 costs_host=_css._small_pinned(f"shard_costs{sh.rank}", (sh.n_loc_seg, S, S), torch.float32),
+                 perms_host=_css._small_pinned(f"shard_perms{sh.rank}", (sh.n_loc_seg, S), torch.int32), perms_np=[],
+                 tail=_css._tail_stream(device), main=torch.cuda.current_stream(device), hops=(ctypes.c_int64 * 2)())
+        # hops of the local waveform that may leave early: complete frames on both sides (hop j reads frames j-1 and j),
+        # gate decided without a neighbour's activity
+        R = plan.dilation_frames + plan.erosion_frames
+        a, b = sh.own_lo - sh.frame0, sh.own_hi - sh.frame0
+        p["a"] = a
+        p["hop_lo"] = a + R + 1 if sh.seg_lo > 0 else 0
+        p["hop_hi"] = b - R if sh.seg_hi < plan.num_segments else b + 1
+        p["tail"].wait_stream(p["main"])
+        self.prog = p
+
+    def _progressive_chunk_done(self, ci: int, costs: torch.Tensor):
+        p = self.prog
+        c0, cn = p["chunks"][ci]
+        p["costs_host"][c0:c0 + cn].copy_(costs[c0:c0 + cn], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(p["main"])
+        p["events"].append(ev)
+        if ci >= 1:
+            self._progressive_advance(ci - 1)          # one chunk behind: the main stream's queue never runs dry
+
+    def _progressive_advance(self, ci: int):
+        p, sh, plan, cfg = self.prog, self.sh, self.plan, self.cfg
+        if ci < 0 or ci >= len(p["chunks"]) - 1 or ci < len(p["copied"]):
+            return
+        S = cfg.num_spks
+        c0, cn = p["chunks"][ci]
+        p["events"][ci].synchronize()
+        p_np, p["state"] = permutation_chain(p["costs_host"][c0:c0 + cn].numpy(), prev_state=p["state"], return_state=True)
+        p["perms_host"][c0:c0 + cn] = torch.from_numpy(p_np)
+        p["perms_np"].append(p_np)
+        with torch.cuda.stream(p["tail"]):
+            p["tail"].wait_event(p["events"][ci])
+            p["perms"][c0:c0 + cn].copy_(p["perms_host"][c0:c0 + cn], non_blocking=True)
+            _cabi.check(self.lib.nsf_stitch_progress(
+                _cabi.ptr(self.masks), self.sep.num_masks, _cabi.ptr(self.Y), _cabi.ptr(p["perms"]), _cabi.ptr(p["seg_w"]), _cabi.ptr(p["wsum"]),
+                sh.n_loc_seg, c0, c0 + cn, S, NUM_BINS, plan.segment_frames, plan.hop_frames, sh.n_frames, float(np.float32(cfg.activity_th)),
+                plan.dilation_frames, plan.erosion_frames, _cabi.ptr(p["mask_st"]), _cabi.ptr(p["activity"]), _cabi.ptr(p["act_b"]),
+                _cabi.ptr(p["act_tmp"]), _cabi.ptr(p["act_final"]), _cabi.ptr(p["S_st"]), _cabi.ptr(p["wav"]), p["hops"], _cabi.stream_ptr()),
+                "nsf_stitch_progress")
+            h0, h1 = max(int(p["hops"][0]), p["hop_lo"]), min(int(p["hops"][1]), p["hop_hi"])
+            if h1 > h0:
+                lo, hi = (h0 - p["a"]) * FRAME_HOP, (h1 - p["a"]) * FRAME_HOP          # samples of the piece
+                for k in range(S):
+                    p["host"][k, lo:hi].copy_(p["wav"][k, h0 * FRAME_HOP:h1 * FRAME_HOP], non_blocking=True)
+                p["copied"].append((lo, hi))
+            else:
+                p["copied"].append((0, 0))
+
+    @torch.no_grad()
+    def finish_host(self, wav_piece: torch.Tensor, host_piece: torch.Tensor) -> List[torch.Tensor]:
+        """The rank's waveform piece on the host: rows in the global stream order (views of host_piece; synchronise the
+        current stream before reading).  What left early under the local labels is kept if the local chain, relabelled by
+        the channel order at the rank's first local segment, is the global chain on those segments (it is, away from exact
+        ties between assignments); the rest -- seams, last chunk -- is copied now.  Otherwise the whole piece is copied."""
+        S = self.cfg.num_spks
+        p = getattr(self, "prog", None)
+        n = wav_piece.shape[1]
+        if p is None or n == 0:
+            host_piece.copy_(wav_piece, non_blocking=True)
+            return [host_piece[k] for k in range(S)]
+        p["main"].wait_stream(p["tail"])
+        sh = self.sh
+        loc0 = sh.seg_lo - sh.halo
+        local = np.concatenate(p["perms_np"], axis=0)                          # local segments the local chain has walked
+        n_adv = local.shape[0]
+        tau = np.asarray(self.perms[loc0], dtype=np.int64)                       # global slot k == local slot tau[k]
+        self.relabel = tau
+        self.progressive_ok = bool(np.array_equal(self.perms[loc0:loc0 + n_adv], local[:, tau]))
+        if not self.progressive_ok:
+            host_piece.copy_(wav_piece, non_blocking=True)
+            return [host_piece[k] for k in range(S)]
+        done = sorted((lo, hi) for lo, hi in p["copied"] if hi > lo)
+        at = 0
+        for lo, hi in done + [(n, n)]:
+            if lo > at:
+                for k in range(S):
+                    host_piece[int(tau[k]), at:lo].copy_(wav_piece[k, at:lo], non_blocking=True)
+            at = max(at, hi)
+        return [host_piece[int(tau[k])] for k in range(S)]
 
     # ---- phase 2: permutation chain (host, replicated), local mask WOLA -> owned rows of the activity mean --------
     @torch.no_grad()
@@ -321,11 +457,13 @@ class ShardWorker:
 
 @torch.no_grad()
 def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total: int, group=None, dst: int = 0,
-                       want_side_info: bool = False) -> Dict:
+                       want_side_info: bool = False, host_piece: Optional[torch.Tensor] = None) -> Dict:
     """One meeting sharded over the ranks of ``group`` (default: the world).  x_local is this rank's sample range
     (``make_shard(plan, rank, world).sample_lo/hi``), on the device or behind a HostFeeder.  Returns on rank ``dst``
     {'wav' [S, N'], 'activity_b', 'activity_final', 'perms', 'plan' (+ 'mask_stitched' if want_side_info)}; on the
-    other ranks the dict has no 'wav'."""
+    other ranks the dict has no 'wav'.  host_piece (page-locked [S, n_own_frames*256 + 256]): this rank's own samples are
+    also read back to the host, their interior while the mask network is still running (ShardWorker.phase1); the dict then
+    holds 'wav_host', the rows in the global stream order (synchronise the current stream before reading them)."""
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     wk = ShardWorker(separator, fs, cfg, n_samples_total, rank, world)
@@ -342,7 +480,7 @@ def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total
                 print(f"[shard timing] {label}: {(now - _t[0]) * 1e3:.2f} ms", file=sys.stderr, flush=True)
             _t[0] = now
     mark("start")
-    own_costs = wk.phase1(x_local)
+    own_costs = wk.phase1(x_local, host_piece)
     mark("phase1 (segments)")
     costs_all = allgather_varlen(own_costs, [s.n_own_seg for s in wk.shards], group)
     costs_np = costs_all.cpu().numpy()
@@ -357,6 +495,8 @@ def css_device_sharded(x_local, separator, fs: int, cfg: CssCfg, n_samples_total
     mark("gather waveforms")
     res = dict(activity_b=out["activity_b"], activity_final=out["activity_final"], perms=wk.perms, plan=wk.plan, shard=wk.sh,
                wav_piece=out["wav_piece"])        # this rank's own samples [S, n_own_frames*256 + 256], first sample own_lo*256
+    if host_piece is not None:
+        res["wav_host"] = wk.finish_host(out["wav_piece"], host_piece)
     mask_pieces = None
     if want_side_info:
         mask_pieces = gather_varlen(out["mask_piece"].contiguous(), [s.n_own_frames for s in wk.shards], dst, group, dim=1)

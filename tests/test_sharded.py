@@ -212,6 +212,72 @@ def test_sharded_equals_single_device(N, small_weights, world, seconds, hop_sec)
 
 
 # ----------------------------------------------------------------------------------------------- sessions over ranks
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,seconds,hop_sec,per_batch", [(3, 30.0, 1.5, 2), (2, 20.0, 1.0, 3), (4, 24.0, 1.5, 1)])
+def test_sharded_progressive_host_pieces(N, small_weights, world, seconds, hop_sec, per_batch):
+    """Every rank reads the interior of its waveform piece back while its segments are still in the network, under
+    the labels of a local permutation chain, and relabels at the end (ShardWorker.phase1(host_piece) / finish_host):
+    the host rows must be bit for bit the piece the global tail produces.  All ranks are played by one device."""
+    from notsofar_b200.sharded import ShardWorker
+    from notsofar_b200.css import css_device
+    from notsofar_b200 import synth
+    dev = torch.device("cuda:0")
+    x = synth.synthetic_meeting(seconds, seed=4)
+    n = x.shape[0]
+    probe = css_device(torch.from_numpy(x).to(dev), N.ConformerCssB200(small_weights, device=dev), 16000,
+                       N.CssCfg(show_progressbar=False, hop_size_sec=hop_sec))
+    cfg = N.CssCfg(activity_th=float(torch.quantile(probe["activity"].flatten(), 0.9)), show_progressbar=False, hop_size_sec=hop_sec)
+    import itertools
+    orders = list(itertools.permutations(range(3)))
+
+    class Shuffled(N.ConformerCssB200):
+        """The network's speaker channels in a different order for every (global) segment: the chain has to undo it, so
+        the ranks behind the first one start in a permuted order and the relabelling is exercised."""
+        seg_offset = 0
+
+        def masks(self, X, T_valid, s0, nb, T, hop, out=None):
+            out = super().masks(X, T_valid, s0, nb, T, hop, out=out)
+            for i in range(nb):
+                order = list(orders[((self.seg_offset + s0 + i) * 5 + 2) % 6])
+                out[i, :3] = out[i, order].clone()
+            return out
+
+    sep = Shuffled(small_weights, device=dev, segments_per_batch=per_batch)
+    xd = torch.from_numpy(x).to(dev)
+    wks = [ShardWorker(sep, 16000, cfg, n, r, world) for r in range(world)]
+    hosts = [torch.empty((3, w.sh.n_own_frames * 256 + 256), dtype=torch.float32).pin_memory() for w in wks]
+    for h in hosts:
+        h.fill_(float("nan"))
+    costs = []
+    for w, h in zip(wks, hosts):
+        sep.seg_offset = w.sh.seg_lo - w.sh.halo
+        costs.append(w.phase1(xd[w.sh.sample_lo:w.sh.sample_hi].contiguous(), h))
+    assert all(w.prog is not None for w in wks if w.sh.n_loc_seg > per_batch)
+    costs_all = torch.cat(costs, 0).cpu().numpy()
+    # what the one-shot path computes for the same block (costs of all local segments in one launch)
+    ref = [ShardWorker(sep, 16000, cfg, n, r, world) for r in range(world)]
+    costs_ref = []
+    for w in ref:
+        sep.seg_offset = w.sh.seg_lo - w.sh.halo
+        costs_ref.append(w.phase1(xd[w.sh.sample_lo:w.sh.sample_hi].contiguous()))
+    assert np.array_equal(costs_all, torch.cat(costs_ref, 0).cpu().numpy())
+    activity_all = torch.cat([w.phase2(costs_all) for w in wks], 0)
+    early, relabelled = 0, 0
+    for w, h in zip(wks, hosts):
+        out = w.phase3(activity_all)
+        rows = w.finish_host(out["wav_piece"], h)
+        torch.cuda.synchronize()
+        assert w.progressive_ok
+        piece = out["wav_piece"].cpu()
+        for k in range(3):
+            assert torch.equal(rows[k], piece[k]), (w.sh.rank, k)
+        early += sum(hi - lo for lo, hi in w.prog["copied"])
+        print(f"rank {w.sh.rank}: relabel {w.relabel.tolist()}, early samples {sum(hi - lo for lo, hi in w.prog['copied'])} of {piece.shape[1]}")
+        relabelled += int(w.relabel.tolist() != [0, 1, 2])
+    assert early > 0                                   # something did leave early
+    assert relabelled > 0                              # ... and some rank's local labels were not the global ones
+
+
 def test_assign_sessions_balances_and_covers():
     from notsofar_b200.scheduler import assign_sessions
     rng = np.random.default_rng(0)
