@@ -184,7 +184,8 @@ def permutation_chain(costs: np.ndarray, prev_state: Optional[int] = None, retur
     return (perms, int(states[-1])) if return_state else perms
 
 
-def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batch: int = 176, progressive: int = 0):
+def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batch: int = 176, progressive: int = 0,
+                 last_batch: int = 0):
     """Chunks of segments the mask network / MVDR run on: [(first segment, count), ...].
 
     Large, equal chunks keep the persistent GEMMs' last wave full (a 128 x 256 tile grid over 148 SMs quantises badly for
@@ -194,7 +195,8 @@ def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batc
 
     progressive > 0 (the separated waveforms go back to the host piece by piece, css_device(host_out=...)): what follows the
     first chunk is cut into chunks of at most that many segments, so that all but the last chunk's share of the output has
-    crossed PCIe when the network finishes."""
+    crossed PCIe when the network finishes.  last_batch > 0 cuts a short chunk off the end of the last one: what is copied
+    after the last kernel shrinks with it (worth a fourth chunk where several ranks share the host's memory bandwidth)."""
     max_batch = max(1, max_batch)
     if streaming and progressive > 0 and n_seg >= 2 * first_batch:
         max_batch = min(max_batch, max(progressive, first_batch + 1))
@@ -202,6 +204,10 @@ def plan_batches(n_seg: int, max_batch: int, streaming: bool = False, first_batc
         while n_seg - s0 > max_batch + max_batch // 4:          # full chunks, then the remainder (a short one is merged)
             out.append((s0, max_batch))
             s0 += max_batch
+        rest = n_seg - s0
+        if last_batch > 0 and rest >= 2 * last_batch:
+            out.append((s0, rest - last_batch))
+            s0 += rest - last_batch
         out.append((s0, n_seg - s0))
         return out
     out, s0 = [], 0
