@@ -13,7 +13,11 @@ cross-segment dependency; only the permutation chain (css.py:266-285), the 50 %-
      seams between ranks are added there (gather_waveforms).
 
 Everything else (STFT of the rank's sample range, features, mask network, MVDR, local WOLA, iSTFT) is the
-single-GPU path of css.py on the rank's slice.  torch.distributed (NCCL over NVLink on the GPUs, gloo in the
+single-GPU path of css.py on the rank's slice.  When a rank also reads its own samples back to the host
+(phase1(host_piece) / finish_host), the interior of its piece leaves while its segments are still in the mask network:
+a local permutation chain from the identity, the progressive tail of css_device on the local arrays, and a relabelling
+of the three streams once the global chain is known (the assignment is equivariant under a relabelling of the previous
+segment; checked, with a fall-back to copying the whole piece).  torch.distributed (NCCL over NVLink on the GPUs, gloo in the
 CPU tests of the exchange logic) carries the three exchanges; there is no CPU compute path.
 """
 from __future__ import annotations
