@@ -165,6 +165,38 @@ def test_permutation_chain_continues_chunk_by_chunk(N):
             assert np.array_equal(np.concatenate(parts), full), (n_seg, S, cuts)
 
 
+def test_permutation_chain_is_equivariant_under_relabelling(N):
+    """What the sharded progressive read-back rests on: a chain that starts from the identity at segment s is the global
+    chain up to one relabelling of the output slots, tau = perms[s] -- perms[i][k] == local[i - s][tau[k]] for every
+    i >= s -- because the best order after a previous order q is sigma o q (sums of three float32 costs are exact in
+    float64, so the arg-min does not depend on the labelling).  An exact tie between two assignments breaks it; the
+    product detects that by this very comparison and falls back."""
+    rng = np.random.default_rng(11)
+    for n_seg, S in ((40, 3), (25, 2), (30, 4)):
+        costs = rng.random((n_seg, S, S)).astype(np.float32)
+        costs[0] = 0
+        full = N.permutation_chain(costs)
+        assert len({tuple(p) for p in full}) > 1
+        for s in (1, 7, n_seg - 2):
+            loc = costs[s:].copy()
+            loc[0] = 0                                  # a rank's first local segment has no predecessor
+            local = N.permutation_chain(loc)
+            tau = full[s]
+            assert np.array_equal(local[0], np.arange(S))
+            assert np.array_equal(full[s:], local[:, tau])
+    # a tie: two assignments with identical totals -> the first in enumeration order wins, whatever the labels are
+    costs = np.zeros((3, 3, 3), np.float32)
+    costs[1] = np.array([[1, 0, 2], [0, 1, 2], [2, 2, 0]], np.float32)      # unambiguous: order (1, 0, 2) costs 0
+    costs[2] = 1.0                                                         # every order costs 3: a six-way tie
+    full = N.permutation_chain(costs)
+    loc = costs[1:].copy()
+    loc[0] = 0
+    local = N.permutation_chain(loc)
+    tau = full[1]
+    assert np.array_equal(full[1], [1, 0, 2])
+    assert not np.array_equal(full[1:], local[:, tau])                      # the tie at the last segment is what the check catches
+
+
 def test_plan_batches_progressive():
     """Chunks of the streaming path: short first chunk, then full (wave-filling) chunks, a short remainder merged into
     the last one; nothing changes for resident recordings, short sessions or with the progressive tail switched off."""
