@@ -15,7 +15,9 @@ per product, fp32 accumulate), fp64 mask-weighted MVDR, permutation-aligned over
           ranks (notsofar_b200.sharded: two small NCCL all-gathers + the waveform hand-off to rank 0) -> weak scaling;
           --scaling strong keeps the meeting at --seconds in total; --multi replicas gives every rank its own meeting.
   e2e   : the same through the public API notsofar_b200.separate_and_stitch with HOST buffers -- H2D of the pinned
-          raw audio and D2H of the three separated waveforms inside the timed region.
+          raw audio and D2H of the three separated waveforms inside the timed region (the audio streams in behind the
+          first chunk of segments, the waveforms stream out behind the mask network: progressive tail, DESIGN.md 4;
+          N > 1: every rank reads its own samples back the same way, css_device_sharded(host_piece=...)).
   roofline     : the dominant kernel class of the step (the tcgen05 GEMM), algorithmic flops / event-timed duration
                  vs MEASURED_PEAKS.json; the other classes are listed in "kernels".
   cpu_baseline : the numpy port of the reference's path (oracle/, same algorithm, all host cores) on a bounded slice.
