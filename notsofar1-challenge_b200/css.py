@@ -347,81 +347,6 @@ def _side_stream(device: torch.device):
     return _SIDE_STREAMS[idx]
 
 
-class ProgressiveTail:
-    """Everything behind the permutation chain (css.py:287-338), advanced chunk by chunk on a high-priority side stream
-    while later chunks of segments are still in the mask network: the costs of a chunk go to the host, the chain
-    continues (permutation_chain(prev_state=...)), nsf_stitch_progress stitches / gates / inverse-transforms the frames
-    that have become final, and ``copy_out(hop_begin, hop_end, wav)`` -- called with the side stream current -- sends the
-    new waveform hops wherever they are wanted.  Used by css_device on a whole recording and by ShardWorker on a rank's
-    local arrays (there with a chain that starts from the identity and without the last chunk, see sharded.py).
-
-    masks / Y: the per-segment buffers the chunks are written into; seg_w / wsum: device weights of exactly these
-    segments / frames; n_frames: pitch of the stitched arrays."""
-
-    def __init__(self, lib, device, chunks, masks, Y, seg_w, wsum, S: int, T: int, hop: int, n_frames: int, th: float, dil: int,
-                 ero: int, copy_out, tag: str = "", skip_last: bool = False):
-        self.lib, self.chunks, self.masks, self.Y, self.seg_w, self.wsum = lib, chunks, masks, Y, seg_w, wsum
-        self.S, self.T, self.hop, self.n_frames, self.th, self.dil, self.ero = S, T, hop, n_frames, th, dil, ero
-        self.copy_out, self.skip_last = copy_out, skip_last
-        n_seg = masks.shape[0]
-        self.n_seg = n_seg
-        self.mask_st = torch.empty((NUM_BINS, n_frames, S), dtype=torch.float32, device=device)
-        self.activity = torch.empty((n_frames, S), dtype=torch.float32, device=device)
-        self.act_b = torch.empty((n_frames, S), dtype=torch.uint8, device=device)
-        self.act_tmp = torch.empty_like(self.act_b)
-        self.act_final = torch.empty_like(self.act_b)
-        self.S_st = torch.empty((S, n_frames, NUM_BINS), dtype=torch.complex64, device=device)
-        self.wav = torch.empty((S, (n_frames - 1) * FRAME_HOP + FRAME_LEN), dtype=torch.float32, device=device)
-        self.perms = torch.empty((n_seg, S), dtype=torch.int32, device=device)
-        self.costs_host = _small_pinned("costs" + tag, (n_seg, S, S), torch.float32)
-        self.perms_host = _small_pinned("perms" + tag, (n_seg, S), torch.int32)
-        self.tail = _tail_stream(device)
-        self.main = torch.cuda.current_stream(device)
-        self.tail.wait_stream(self.main)               # the buffers above may recycle memory still in use upstream
-        self.events, self.perms_np, self.state, self.done = [], [], None, 0
-        self._hops = (ctypes.c_int64 * 2)()
-
-    def chunk_done(self, ci: int, costs: torch.Tensor):
-        """On the main stream, once the costs of chunk ci have been enqueued; advances the tail of the chunk *before* --
-        one chunk behind, so that the main stream's queue never runs dry while the host waits for the costs."""
-        c0, cn = self.chunks[ci]
-        self.costs_host[c0:c0 + cn].copy_(costs[c0:c0 + cn], non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(self.main)
-        self.events.append(ev)
-        if ci >= 1:
-            self.advance(ci - 1)
-
-    def advance(self, ci: int):
-        if ci != self.done or ci >= len(self.chunks) - (1 if self.skip_last else 0):
-            return
-        c0, cn = self.chunks[ci]
-        self.events[ci].synchronize()                  # the GPU is busy with chunk ci + 1 meanwhile
-        p_np, self.state = permutation_chain(self.costs_host[c0:c0 + cn].numpy(), prev_state=self.state, return_state=True)
-        self.perms_host[c0:c0 + cn] = torch.from_numpy(p_np)
-        self.perms_np.append(p_np)
-        with torch.cuda.stream(self.tail):
-            self.tail.wait_event(self.events[ci])      # the tail of this chunk reads its masks / Y (complete: formal ordering)
-            self.perms[c0:c0 + cn].copy_(self.perms_host[c0:c0 + cn], non_blocking=True)
-            _cabi.check(self.lib.nsf_stitch_progress(
-                _cabi.ptr(self.masks), self.masks.shape[1], _cabi.ptr(self.Y), _cabi.ptr(self.perms), _cabi.ptr(self.seg_w),
-                _cabi.ptr(self.wsum), self.n_seg, c0, c0 + cn, self.S, NUM_BINS, self.T, self.hop, self.n_frames, self.th, self.dil, self.ero,
-                _cabi.ptr(self.mask_st), _cabi.ptr(self.activity), _cabi.ptr(self.act_b), _cabi.ptr(self.act_tmp), _cabi.ptr(self.act_final),
-                _cabi.ptr(self.S_st), _cabi.ptr(self.wav), self._hops, _cabi.stream_ptr()), "nsf_stitch_progress")
-            self.copy_out(int(self._hops[0]), int(self._hops[1]), self.wav)
-        self.done += 1
-
-    def finish(self):
-        """Advances what is left and makes the main stream (downstream readers, the allocator) wait for the tail's work."""
-        for ci in range(self.done, len(self.chunks)):
-            self.advance(ci)
-        self.main.wait_stream(self.tail)
-
-    def chain(self) -> np.ndarray:
-        """Rows of the chain walked so far [segments, S]."""
-        return np.concatenate(self.perms_np, axis=0) if self.perms_np else np.zeros((0, self.S), np.int32)
-
-
 @torch.no_grad()
 def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_info: bool = True,
                host_out: Optional[torch.Tensor] = None) -> Dict:
@@ -481,15 +406,43 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
         if host_out is not None:
             assert tuple(host_out.shape) == (S, n_out) and host_out.dtype == torch.float32 and not host_out.is_cuda
         if progressive:
-            # II'/III'. everything behind the chain, advanced chunk by chunk on a side stream
+            # II'/III'. everything behind the chain, advanced chunk by chunk on a side stream (nsf_stitch_progress)
             seg_w, wsum = _segment_weights_device(plan, device)
+            mask_st = torch.empty((NUM_BINS, mix_frames, S), dtype=torch.float32, device=device)
+            activity = torch.empty((mix_frames, S), dtype=torch.float32, device=device)
+            act_b = torch.empty((mix_frames, S), dtype=torch.uint8, device=device)
+            act_tmp = torch.empty_like(act_b)
+            act_final = torch.empty_like(act_b)
+            S_st = torch.empty((S, mix_frames, NUM_BINS), dtype=torch.complex64, device=device)
+            wav = torch.empty((S, n_out), dtype=torch.float32, device=device)
+            perms = torch.empty((n_seg, S), dtype=torch.int32, device=device)
+            costs_host = _small_pinned("costs", (n_seg, S, S), torch.float32)
+            perms_host = _small_pinned("perms", (n_seg, S), torch.int32)
+            tail = _tail_stream(device)
+            main = torch.cuda.current_stream(device)
+            tail.wait_stream(main)                     # the buffers above may recycle memory still in use upstream
+            cost_events = []
+            hops = (ctypes.c_int64 * 2)()
+            chain_state = [None]
+            th = float(np.float32(cfg.activity_th))
 
-            def copy_out(h0, h1, wav_):
-                a_, b_ = h0 * FRAME_HOP, min(h1 * FRAME_HOP, n_out)
-                for k in range(S if b_ > a_ else 0):   # contiguous runs: plain cudaMemcpyAsync (a strided copy_ is staged through pageable memory)
-                    host_out[k, a_:b_].copy_(wav_[k, a_:b_], non_blocking=True)
-            pt = ProgressiveTail(lib, device, chunks, masks, Y, seg_w, wsum, S, T, hop, mix_frames, float(np.float32(cfg.activity_th)),
-                                 plan.dilation_frames, plan.erosion_frames, copy_out)
+            def advance(ci):
+                c0, cn = chunks[ci]
+                cost_events[ci].synchronize()          # the GPU is busy with chunk ci + 1 meanwhile
+                p_np, chain_state[0] = permutation_chain(costs_host[c0:c0 + cn].numpy(), prev_state=chain_state[0], return_state=True)
+                perms_host[c0:c0 + cn] = torch.from_numpy(p_np)
+                with torch.cuda.stream(tail):
+                    tail.wait_event(cost_events[ci])   # the tail of this chunk reads its masks / Y (complete: formal ordering)
+                    perms[c0:c0 + cn].copy_(perms_host[c0:c0 + cn], non_blocking=True)
+                    _cabi.check(lib.nsf_stitch_progress(
+                        _cabi.ptr(masks), n_masks, _cabi.ptr(Y), _cabi.ptr(perms), _cabi.ptr(seg_w), _cabi.ptr(wsum), n_seg, c0, c0 + cn,
+                        S, NUM_BINS, T, hop, mix_frames, th, plan.dilation_frames, plan.erosion_frames, _cabi.ptr(mask_st),
+                        _cabi.ptr(activity), _cabi.ptr(act_b), _cabi.ptr(act_tmp), _cabi.ptr(act_final), _cabi.ptr(S_st), _cabi.ptr(wav),
+                        hops, sp()), "nsf_stitch_progress")
+                    a, b = int(hops[0]) * FRAME_HOP, min(int(hops[1]) * FRAME_HOP, n_out)
+                    if b > a:
+                        for k in range(S):             # contiguous runs: plain cudaMemcpyAsync (a strided copy_ is staged through pageable memory)
+                            host_out[k, a:b].copy_(wav[k, a:b], non_blocking=True)
 
         for ci, (s0, nb) in enumerate(chunks):
             # STFT of the frames this chunk of segments needs (and, when streaming from the host, only once they landed)
@@ -509,15 +462,20 @@ def css_device(x, separator: ConformerCssB200, fs: int, cfg: CssCfg, want_side_i
             if progressive:
                 _cabi.check(lib.nsf_pit_cost_range(_cabi.ptr(src), in_kind, loss_kind, s0, s0 + nb, n_masks if in_kind == 0 else S, S,
                                                    NUM_BINS, T, plan.overlap_frames, _cabi.ptr(costs), sp()), "nsf_pit_cost_range")
-                pt.chunk_done(ci, costs)
+                costs_host[s0:s0 + nb].copy_(costs[s0:s0 + nb], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                cost_events.append(ev)
+                if ci >= 1:
+                    advance(ci - 1)                    # one chunk behind: the queue of the main stream never runs dry
 
         if feeder is not None:
             feeder.ready(n_samples)       # every copy has been ordered before the buffers can be recycled
 
         if progressive:
-            pt.finish()
-            perms_np = pt.chain()
-            wav, mask_st, activity, act_b, act_final, S_st = pt.wav, pt.mask_st, pt.activity, pt.act_b, pt.act_final, pt.S_st
+            advance(len(chunks) - 1)
+            main.wait_stream(tail)                     # downstream readers (and the allocator) see the tail's work
+            perms_np = perms_host.numpy().copy()
         else:
             # II. permutation chain + weighted overlap-add (css.py:254-299)
             _cabi.check(lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_seg, n_masks if in_kind == 0 else S, S, NUM_BINS, T,

@@ -30,6 +30,7 @@ import numpy as np
 import torch
 
 from . import _cabi
+import ctypes
 import os
 
 from . import css as _css
@@ -278,21 +279,21 @@ class ShardWorker:
                     _cabi.check(self.lib.nsf_pit_cost_range(_cabi.ptr(src), in_kind, loss_kind, s0, s0 + nb, n_masks if in_kind == 0 else S,
                                                             S, NUM_BINS, T, plan.overlap_frames, _cabi.ptr(costs), _cabi.stream_ptr()),
                                 "nsf_pit_cost_range")
-                    self.prog.chunk_done(ci, costs)
+                    self._progressive_chunk_done(ci, costs)
             if feeder is not None:
                 feeder.ready(x.shape[0])
             if self.prog is None:
                 _cabi.check(self.lib.nsf_pit_cost(_cabi.ptr(src), in_kind, loss_kind, n_loc, n_masks if in_kind == 0 else S, S, NUM_BINS,
                                                   T, plan.overlap_frames, _cabi.ptr(costs), _cabi.stream_ptr()), "nsf_pit_cost")
-            else:
-                self.prog.finish()
+            elif len(chunks) >= 2:
+                self._progressive_advance(len(chunks) - 2)      # the last chunk's frames wait for the global tail (phase 3)
         self.X = X
         return costs[sh.halo:]
 
     # ---- progressive read-back of the piece's interior (see phase1) ------------------------------------------------
     def _progressive_setup(self, host_piece: torch.Tensor, chunks, device):
         sh, plan, cfg = self.sh, self.plan, self.cfg
-        S = cfg.num_spks
+        S, T = cfg.num_spks, plan.segment_frames
         assert tuple(host_piece.shape) == (S, sh.n_own_frames * FRAME_HOP + FRAME_HOP) and host_piece.dtype == torch.float32
         loc0 = sh.seg_lo - sh.halo
         key = (plan.segment_frames, plan.hop_frames, plan.m0_frames, plan.m1_frames, plan.num_segments, plan.mix_frames, loc0, sh.seg_hi,
@@ -305,25 +306,66 @@ class ShardWorker:
             _SHARD_W_DEV[key] = hit
             if len(_SHARD_W_DEV) > 8:
                 _SHARD_W_DEV.pop(next(iter(_SHARD_W_DEV)))
+        nf = sh.n_frames
+        p = dict(chunks=chunks, host=host_piece, seg_w=hit[0], wsum=hit[1], events=[], state=None, copied=[],
+                 mask_st=torch.empty((NUM_BINS, nf, S), dtype=torch.float32, device=device),
+                 activity=torch.empty((nf, S), dtype=torch.float32, device=device),
+                 act_b=torch.empty((nf, S), dtype=torch.uint8, device=device),
+                 act_tmp=torch.empty((nf, S), dtype=torch.uint8, device=device),
+                 act_final=torch.empty((nf, S), dtype=torch.uint8, device=device),
+                 S_st=torch.empty((S, nf, NUM_BINS), dtype=torch.complex64, device=device),
+                 wav=torch.empty((S, (nf - 1) * FRAME_HOP + FRAME_LEN), dtype=torch.float32, device=device),
+                 perms=torch.empty((sh.n_loc_seg, S), dtype=torch.int32, device=device),
+                 costs_host=_css._small_pinned(f"shard_costs{sh.rank}", (sh.n_loc_seg, S, S), torch.float32),
+                 perms_host=_css._small_pinned(f"shard_perms{sh.rank}", (sh.n_loc_seg, S), torch.int32), perms_np=[],
+                 tail=_css._tail_stream(device), main=torch.cuda.current_stream(device), hops=(ctypes.c_int64 * 2)())
         # hops of the local waveform that may leave early: complete frames on both sides (hop j reads frames j-1 and j),
         # gate decided without a neighbour's activity
         R = plan.dilation_frames + plan.erosion_frames
         a, b = sh.own_lo - sh.frame0, sh.own_hi - sh.frame0
-        hop_lo = a + R + 1 if sh.seg_lo > 0 else 0
-        hop_hi = b - R if sh.seg_hi < plan.num_segments else b + 1
-        self.copied = []
+        p["a"] = a
+        p["hop_lo"] = a + R + 1 if sh.seg_lo > 0 else 0
+        p["hop_hi"] = b - R if sh.seg_hi < plan.num_segments else b + 1
+        p["tail"].wait_stream(p["main"])
+        self.prog = p
 
-        def copy_out(h0, h1, wav):
-            h0, h1 = max(h0, hop_lo), min(h1, hop_hi)
+    def _progressive_chunk_done(self, ci: int, costs: torch.Tensor):
+        p = self.prog
+        c0, cn = p["chunks"][ci]
+        p["costs_host"][c0:c0 + cn].copy_(costs[c0:c0 + cn], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(p["main"])
+        p["events"].append(ev)
+        if ci >= 1:
+            self._progressive_advance(ci - 1)          # one chunk behind: the main stream's queue never runs dry
+
+    def _progressive_advance(self, ci: int):
+        p, sh, plan, cfg = self.prog, self.sh, self.plan, self.cfg
+        if ci < 0 or ci >= len(p["chunks"]) - 1 or ci < len(p["copied"]):
+            return
+        S = cfg.num_spks
+        c0, cn = p["chunks"][ci]
+        p["events"][ci].synchronize()
+        p_np, p["state"] = permutation_chain(p["costs_host"][c0:c0 + cn].numpy(), prev_state=p["state"], return_state=True)
+        p["perms_host"][c0:c0 + cn] = torch.from_numpy(p_np)
+        p["perms_np"].append(p_np)
+        with torch.cuda.stream(p["tail"]):
+            p["tail"].wait_event(p["events"][ci])
+            p["perms"][c0:c0 + cn].copy_(p["perms_host"][c0:c0 + cn], non_blocking=True)
+            _cabi.check(self.lib.nsf_stitch_progress(
+                _cabi.ptr(self.masks), self.sep.num_masks, _cabi.ptr(self.Y), _cabi.ptr(p["perms"]), _cabi.ptr(p["seg_w"]), _cabi.ptr(p["wsum"]),
+                sh.n_loc_seg, c0, c0 + cn, S, NUM_BINS, plan.segment_frames, plan.hop_frames, sh.n_frames, float(np.float32(cfg.activity_th)),
+                plan.dilation_frames, plan.erosion_frames, _cabi.ptr(p["mask_st"]), _cabi.ptr(p["activity"]), _cabi.ptr(p["act_b"]),
+                _cabi.ptr(p["act_tmp"]), _cabi.ptr(p["act_final"]), _cabi.ptr(p["S_st"]), _cabi.ptr(p["wav"]), p["hops"], _cabi.stream_ptr()),
+                "nsf_stitch_progress")
+            h0, h1 = max(int(p["hops"][0]), p["hop_lo"]), min(int(p["hops"][1]), p["hop_hi"])
             if h1 > h0:
-                lo, hi = (h0 - a) * FRAME_HOP, (h1 - a) * FRAME_HOP          # samples of the piece
+                lo, hi = (h0 - p["a"]) * FRAME_HOP, (h1 - p["a"]) * FRAME_HOP          # samples of the piece
                 for k in range(S):
-                    host_piece[k, lo:hi].copy_(wav[k, h0 * FRAME_HOP:h1 * FRAME_HOP], non_blocking=True)
-                self.copied.append((lo, hi))
-        # the last chunk's frames wait for the global tail (phase 3): nothing could hide behind them
-        self.prog = _css.ProgressiveTail(self.lib, device, chunks, self.masks, self.Y, hit[0], hit[1], S, plan.segment_frames, plan.hop_frames,
-                                         sh.n_frames, float(np.float32(cfg.activity_th)), plan.dilation_frames, plan.erosion_frames,
-                                         copy_out, tag=f"_shard{sh.rank}", skip_last=True)
+                    p["host"][k, lo:hi].copy_(p["wav"][k, h0 * FRAME_HOP:h1 * FRAME_HOP], non_blocking=True)
+                p["copied"].append((lo, hi))
+            else:
+                p["copied"].append((0, 0))
 
     @torch.no_grad()
     def finish_host(self, wav_piece: torch.Tensor, host_piece: torch.Tensor) -> List[torch.Tensor]:
@@ -337,9 +379,10 @@ class ShardWorker:
         if p is None or n == 0:
             host_piece.copy_(wav_piece, non_blocking=True)
             return [host_piece[k] for k in range(S)]
+        p["main"].wait_stream(p["tail"])
         sh = self.sh
         loc0 = sh.seg_lo - sh.halo
-        local = p.chain()                                                        # local segments the local chain has walked
+        local = np.concatenate(p["perms_np"], axis=0)                          # local segments the local chain has walked
         n_adv = local.shape[0]
         tau = np.asarray(self.perms[loc0], dtype=np.int64)                       # global slot k == local slot tau[k]
         self.relabel = tau
@@ -347,7 +390,7 @@ class ShardWorker:
         if not self.progressive_ok:
             host_piece.copy_(wav_piece, non_blocking=True)
             return [host_piece[k] for k in range(S)]
-        done = sorted(self.copied)
+        done = sorted((lo, hi) for lo, hi in p["copied"] if hi > lo)
         at = 0
         for lo, hi in done + [(n, n)]:
             if lo > at:

@@ -271,8 +271,8 @@ def test_sharded_progressive_host_pieces(N, small_weights, world, seconds, hop_s
         piece = out["wav_piece"].cpu()
         for k in range(3):
             assert torch.equal(rows[k], piece[k]), (w.sh.rank, k)
-        early += sum(hi - lo for lo, hi in w.copied)
-        print(f"rank {w.sh.rank}: relabel {w.relabel.tolist()}, early samples {sum(hi - lo for lo, hi in w.copied)} of {piece.shape[1]}")
+        early += sum(hi - lo for lo, hi in w.prog["copied"])
+        print(f"rank {w.sh.rank}: relabel {w.relabel.tolist()}, early samples {sum(hi - lo for lo, hi in w.prog['copied'])} of {piece.shape[1]}")
         relabelled += int(w.relabel.tolist() != [0, 1, 2])
     assert early > 0                                   # something did leave early
     assert relabelled > 0                              # ... and some rank's local labels were not the global ones
